@@ -1,0 +1,95 @@
+"""Deterministic synthetic weights and contexts for random-init configs.
+
+There are no pretrained weights offline, so every config in BASELINE.json is
+"csm-1b random-init".  The reference's own init is not reproducible without the
+reference class (HF `post_init` order; `audio_head` is never initialised at all,
+modeling_csm.py:236-240), so random-init is defined here instead: every tensor of
+the reference `state_dict` (187 keys) gets its own seeded CPU
+generator.  The same state_dict is loaded into the reference model when golden
+vectors are minted (oracle/make_golden.py), into the oracle, and into the CUDA
+engine, so all three see bit-identical parameters.
+"""
+from __future__ import annotations
+
+import zlib
+from typing import Dict, Tuple
+
+import torch
+
+from .config import CSMConfig, LlamaDims
+
+
+def state_dict_shapes(cfg: CSMConfig) -> Dict[str, Tuple[int, ...]]:
+    """Key -> shape of the reference CSMModel.state_dict() (modeling_csm.py:214-245)."""
+    shapes: Dict[str, Tuple[int, ...]] = {}
+
+    def llama(prefix: str, d: LlamaDims):
+        H, I = d.hidden_size, d.intermediate_size
+        hd = d.head_dim
+        for l in range(d.num_hidden_layers):
+            p = f"{prefix}.layers.{l}"
+            shapes[f"{p}.self_attn.q_proj.weight"] = (d.num_attention_heads * hd, H)
+            shapes[f"{p}.self_attn.k_proj.weight"] = (d.num_key_value_heads * hd, H)
+            shapes[f"{p}.self_attn.v_proj.weight"] = (d.num_key_value_heads * hd, H)
+            shapes[f"{p}.self_attn.o_proj.weight"] = (H, d.num_attention_heads * hd)
+            shapes[f"{p}.mlp.gate_proj.weight"] = (I, H)
+            shapes[f"{p}.mlp.up_proj.weight"] = (I, H)
+            shapes[f"{p}.mlp.down_proj.weight"] = (H, I)
+            shapes[f"{p}.input_layernorm.weight"] = (H,)
+            shapes[f"{p}.post_attention_layernorm.weight"] = (H,)
+        shapes[f"{prefix}.norm.weight"] = (H,)
+
+    llama("backbone", cfg.backbone_config)
+    llama("decoder", cfg.decoder_config)
+    Hb, Hd = cfg.backbone_config.hidden_size, cfg.decoder_config.hidden_size
+    shapes["text_embeddings.weight"] = (cfg.text_vocab_size, Hb)
+    shapes["audio_embeddings.weight"] = (cfg.audio_vocab_size * cfg.audio_num_codebooks, Hb)
+    shapes["projection.weight"] = (Hd, Hb)
+    shapes["codebook0_head.weight"] = (cfg.audio_vocab_size, Hb)
+    shapes["audio_head"] = (cfg.audio_num_codebooks - 1, Hd, cfg.audio_vocab_size)
+    return shapes
+
+
+def make_state_dict(cfg: CSMConfig, seed: int = 0, dtype: torch.dtype = torch.float32,
+                    std: float = 0.02, norm_jitter: float = 0.0,
+                    head_gain: float = 1.0) -> Dict[str, torch.Tensor]:
+    """N(0, std) for every matrix, norm weights 1 (+ jitter), one generator per key.
+
+    head_gain multiplies codebook0_head / audio_head: the "peaky" variant of
+    SURVEY.md §8d, whose top-1 margins are far above one bf16 ulp so that free-running
+    greedy tokens are well defined across accumulation orders.
+    """
+    sd: Dict[str, torch.Tensor] = {}
+    for name, shape in state_dict_shapes(cfg).items():
+        g = torch.Generator().manual_seed((seed * 1000003 + zlib.crc32(name.encode())) & 0x7FFFFFFF)
+        if name.endswith("norm.weight") or name.endswith("layernorm.weight"):
+            t = torch.ones(shape, dtype=torch.float32)
+            if norm_jitter:
+                t += norm_jitter * torch.randn(shape, generator=g, dtype=torch.float32)
+        else:
+            t = torch.empty(shape, dtype=torch.float32).normal_(0.0, std, generator=g)
+            if name in ("codebook0_head.weight", "audio_head"):
+                t *= head_gain
+        sd[name] = t.to(dtype)
+    return sd
+
+
+def make_context(cfg: CSMConfig, batch: int, frames: int, seed: int = 1234,
+                 text_frames: int = 0):
+    """Synthetic all-audio context: ids [B,T,33] int64 with the text
+    column zero, int32 mask with columns 0..31 set.  `text_frames` > 0 prepends that
+    many text-only frames (column 32 = token, mask column 32 only), the shape
+    CSMProcessor emits for a prompt (processor.py:254-267)."""
+    g = torch.Generator().manual_seed(seed)
+    nq = cfg.audio_num_codebooks
+    ids = torch.randint(0, cfg.audio_vocab_size, (batch, frames, nq + 1), generator=g, dtype=torch.int64)
+    ids[:, :, nq] = 0
+    mask = torch.zeros(batch, frames, nq + 1, dtype=torch.int32)
+    mask[:, :, :nq] = 1
+    if text_frames:
+        tt = torch.randint(0, cfg.text_vocab_size, (batch, text_frames), generator=g, dtype=torch.int64)
+        ids[:, :text_frames, :] = 0
+        ids[:, :text_frames, nq] = tt
+        mask[:, :text_frames, :] = 0
+        mask[:, :text_frames, nq] = 1
+    return ids, mask

@@ -1,0 +1,55 @@
+"""The oracle (oracle/csm_oracle.py) against golden vectors minted from the UNMODIFIED
+reference (oracle/make_golden.py).  CPU only."""
+import pytest
+import torch
+
+from helpers import assert_logits_close, assert_tokens_match_where_decided, load_golden
+from oracle.csm_oracle import CSMOracle
+
+
+@pytest.mark.parametrize("name", ["tiny_fp32.pt", "tiny_b1_fp32.pt"])
+def test_fp32_free_running_exact(name):
+    g, cfg, dtype, sd, ids, mask = load_golden(name)
+    o = CSMOracle(cfg, sd, dtype)
+    tr = []
+    frames = o.generate(ids, mask, g["recipe"]["new_frames"], traces=tr)
+    assert torch.equal(frames, g["frames"])            # bit-exact ids
+    c0 = torch.stack([t["c0_logits"] for t in tr])
+    cb = torch.stack([t["cb_logits"] for t in tr])
+    lh = torch.stack([t["last_h"] for t in tr])
+    # fp32 tolerance: accumulation-order noise only
+    assert (c0 - g["c0_logits"]).abs().max() < 2e-5
+    assert (cb - g["cb_logits"]).abs().max() < 2e-5
+    assert (lh - g["last_h"]).abs().max() < 5e-5
+
+
+@pytest.mark.parametrize("name", ["tiny_bf16.pt", "tiny_b1_bf16.pt"])
+def test_bf16_teacher_forced(name):
+    """bf16: feed the reference's own tokens and compare every sampling point.
+    Tolerance: 2 % of the logit range (the reference's SDPA rounds P to bf16, ours does
+    not; everything else shares rounding points)."""
+    g, cfg, dtype, sd, ids, mask = load_golden(name)
+    o = CSMOracle(cfg, sd, dtype)
+    tr = []
+    frames = o.generate(ids, mask, g["recipe"]["new_frames"], traces=tr, force_frames=g["frames"])
+    c0 = torch.stack([t["c0_logits"] for t in tr])
+    cb = torch.stack([t["cb_logits"] for t in tr])
+    rel = 0.02
+    assert_logits_close(c0, g["c0_logits"], rel, "c0 logits")
+    assert_logits_close(cb, g["cb_logits"], rel, "codebook logits")
+    tol = rel * g["cb_logits"].float().abs().max().item()
+    all_logits = torch.cat([g["c0_logits"].unsqueeze(2), g["cb_logits"]], dim=2).permute(1, 0, 2, 3)  # [B,n,32,V]
+    frac = assert_tokens_match_where_decided(frames, g["frames"], all_logits, tol, "tokens")
+    assert frac > 0.5
+
+
+def test_csm1b_config1_fp32_tokens():
+    """BASELINE.json configs[0] on the full csm-1b shape: fp32 oracle reproduces the
+    reference's 8x32 greedy ids exactly."""
+    g, cfg, dtype, sd, ids, mask = load_golden("csm1b_cfg1_fp32.pt")
+    o = CSMOracle(cfg, sd, dtype)
+    tr = []
+    frames = o.generate(ids, mask, 8, traces=tr)
+    assert torch.equal(frames, g["frames"])
+    c0 = torch.stack([t["c0_logits"] for t in tr])
+    assert (c0 - g["c0_logits"]).abs().max() < 5e-5
