@@ -1,0 +1,263 @@
+#!/usr/bin/env python
+"""bench.py -- audio frames/s of CSM greedy generation (BASELINE.json metric).
+
+A "step" is one CSMModel.generate() of `--frames` new frames after a `--ctx`-frame context at
+`--batch` sequences per GPU (default: BASELINE.json configs[1] = csm-1b bf16, 2048-frame
+context, 200 new frames, batch 1, one B200).  Prints ONE JSON line (rank 0).
+
+  value   whole-job frames/s (all ranks), inputs resident in HBM, prefill included
+  e2e     the same call through the host-buffer C-ABI entry (csm_generate_host): pinned H2D of
+          ids+mask and D2H of the frames inside the timed region
+  roofline  the persistent decode-frame kernel (csm_stream_kernel): algorithmic bytes per
+          launch / CUDA-event time per launch, against MEASURED_PEAKS.json
+  cpu_baseline / --impl reference: the oracle port of the reference's CPU path (the Python
+          reference cannot travel to the GPU box), fp32, all host threads, bounded sample
+"""
+import argparse
+import json
+import os
+import statistics
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+# parameter counts of csm-1b
+P_BB, P_C0, P_DEC, P_AH, P_PROJ = 973_078_528, 4_200_448, 111_149_056, 65_106_944, 2_097_152
+
+
+def algorithmic_bytes(B, T):
+    """bf16 bytes one decode step must move: every weight once (decoder 31x: its passes are
+    sequentially dependent) + the cached K/V of every sequence + the gathered embedding rows."""
+    return 2 * (P_BB + P_C0 + 31 * P_DEC + P_AH + P_PROJ) + B * T * 32768 + B * 65 * 4096
+
+
+def measured_peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.isfile(p):
+        with open(p) as f:
+            return float(json.load(f)["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
+    return 6650.0, "fallback (B200_PROFILING.md 6.65 TB/s)"
+
+
+class ClockSampler:
+    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        self.rows, self.proc, self.index = [], None, index
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--id={self.index}", f"--query-gpu={self.Q}",
+                                          "--format=csv,noheader,nounits", "-lms", "200"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            threading.Thread(target=self._read, daemon=True).start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([x.strip() for x in line.split(",")])
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        sm = [float(r[0]) for r in self.rows if r and r[0].replace(".", "").isdigit()]
+        mx = [float(r[1]) for r in self.rows if len(r) > 1 and r[1].replace(".", "").isdigit()]
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        reasons = [n for i, n in enumerate(names) if any(len(r) > 3 + i and r[3 + i] == "Active" for r in self.rows)]
+        return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": reasons, "samples": len(sm)}
+
+
+def cpu_reference_sample(cfg, sd_fp32, ctx, frames_sample, new_frames):
+    """Oracle port of the reference CPU path (fp32, all threads): prefill `ctx` frames + a few
+    decode frames, projected to the full `new_frames` workload."""
+    import torch
+    from csm_hf_b200.synthetic import make_context
+    from oracle.csm_oracle import CSMOracle   # the one place bench.py executes oracle/: as the timed CPU baseline
+    torch.set_num_threads(os.cpu_count() or 1)
+    oracle = CSMOracle(cfg, sd_fp32, torch.float32)
+    ids, mask = make_context(cfg, 1, ctx, seed=1234)
+    with torch.inference_mode():
+        cache = oracle.new_cache(1, ctx + frames_sample + 1)
+        t0 = time.perf_counter()
+        toks, _, _ = oracle.generate_frame(ids, mask, cache)
+        t_first = time.perf_counter() - t0
+        t1 = time.perf_counter()
+        for _ in range(frames_sample):
+            row = torch.cat([toks, torch.zeros(1, 1, dtype=torch.long)], dim=1).unsqueeze(1)
+            m = torch.zeros(1, 1, 33, dtype=torch.int32)
+            m[:, :, :32] = 1
+            toks, _, _ = oracle.generate_frame(row, m, cache)
+        t_frame = (time.perf_counter() - t1) / frames_sample
+    total = t_first + (new_frames - 1) * t_frame
+    return new_frames / total, t_first, t_frame
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=3)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--batch", type=int, default=1, help="sequences per GPU")
+    ap.add_argument("--ctx", type=int, default=2048)
+    ap.add_argument("--frames", type=int, default=200)
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--cpu-sample-frames", type=int, default=4)
+    a = ap.parse_args()
+
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    workload = (f"csm-1b random-init, greedy (temperature=0), {a.ctx}-frame synthetic context, {a.frames} new frames, "
+                f"batch={a.batch} per GPU, KV cache")
+
+    import torch
+    from csm_hf_b200.config import CSMConfig
+    from csm_hf_b200.synthetic import make_context, make_state_dict
+    cfg = CSMConfig()
+
+    if a.impl == "reference":
+        if rank != 0:
+            return
+        sd = make_state_dict(cfg, seed=0)
+        vals = []
+        for i in range(max(1, min(a.warmup, 1)) + a.steps):          # one warm-up pass is enough on the CPU
+            v, t_first, t_frame = cpu_reference_sample(cfg, sd, a.ctx, a.cpu_sample_frames, a.frames)
+            if i >= max(1, min(a.warmup, 1)):
+                vals.append((v, t_first, t_frame))
+        v = statistics.mean(x[0] for x in vals)
+        sample = (f"oracle port of modeling_csm.py (fp32, torch CPU): {a.ctx}-frame prefill+frame "
+                  f"({statistics.mean(x[1] for x in vals):.2f} s) + {a.cpu_sample_frames} decode frames "
+                  f"({statistics.mean(x[2] for x in vals):.3f} s each), projected to {a.frames} frames, batch 1")
+        print(json.dumps({
+            "impl": "reference", "metric": "audio_frames_per_s", "value": v, "unit": "frames/s", "n_gpus": 0,
+            "steps": a.steps, "warmup": a.warmup, "ms_per_step": 1000.0 * a.frames / v, "higher_is_better": True,
+            "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": {"workload": workload.replace(f"batch={a.batch} per GPU", "batch=1")},
+            "cpu_baseline": {"value": v, "unit": "frames/s", "cores": torch.get_num_threads(), "kind": "port",
+                             "sample": sample},
+            "e2e": {"value": v, "unit": "frames/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        }))
+        return
+
+    # ------------------------------------------------------------------ our arm
+    import torch.distributed as dist
+    from csm_hf_b200.dist import generate_sharded
+    from csm_hf_b200.modeling import CSMModel
+    assert torch.cuda.is_available(), "bench.py needs a GPU (no CPU fallback)"
+    dev = torch.device("cuda", local_rank)
+    torch.cuda.set_device(dev)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    want_cpu = (world == 1 and not a.no_cpu_baseline)
+    sd = make_state_dict(cfg, seed=0, dtype=torch.float32 if want_cpu else torch.bfloat16)
+    model = CSMModel(cfg, sd, device=dev, max_batch=a.batch, max_ctx=a.ctx + a.frames + 8)
+    GB = a.batch * world
+    ids, mask = make_context(cfg, GB, a.ctx, seed=1234)
+    lo = rank * a.batch
+    d_ids, d_mask = ids.to(dev), mask.to(dev)
+    h_ids, h_mask = ids[lo:lo + a.batch].contiguous().pin_memory(), mask[lo:lo + a.batch].contiguous().pin_memory()
+    eng = model.engine(a.batch, a.ctx + a.frames)
+
+    def step_device():
+        if world > 1:
+            return generate_sharded(model, d_ids, d_mask, max_new_frames=a.frames, temperature=0, stop_on_all_zeros=False)
+        return model.generate(d_ids, d_mask, max_new_frames=a.frames, temperature=0, stop_on_all_zeros=False)
+
+    for _ in range(max(a.warmup, 3)):
+        out = step_device()
+    assert tuple(out.shape) == (GB, a.frames, 32)
+
+    def fence():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    sampler = ClockSampler(local_rank)
+    if rank == 0:
+        sampler.start()
+    launches0 = eng.info(4)
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    dec_ms, dec_n = 0.0, 0
+    fence()
+    ev0.record()
+    for _ in range(a.steps):
+        step_device()
+        ms, n = model.last_decode_ms()
+        dec_ms += ms
+        dec_n += n
+    ev1.record()
+    fence()
+    ms_total = ev0.elapsed_time(ev1)
+    launches = eng.info(4) - launches0
+    # end to end through host buffers (same process, same engine)
+    for _ in range(2):
+        model.generate(h_ids, h_mask, max_new_frames=a.frames, temperature=0, stop_on_all_zeros=False)
+    fence()
+    t0 = time.perf_counter()
+    for _ in range(a.steps):
+        fr = model.generate(h_ids, h_mask, max_new_frames=a.frames, temperature=0, stop_on_all_zeros=False)
+        if world > 1:
+            from csm_hf_b200.dist import all_gather_frames
+            all_gather_frames(fr.to(dev), GB)
+    fence()
+    e2e_s = time.perf_counter() - t0
+    clocks = sampler.stop() if rank == 0 else None
+    t = torch.tensor([ms_total, e2e_s * 1000.0, dec_ms / max(dec_n, 1)], device=dev, dtype=torch.float64)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ms_total, e2e_ms, dec_ms_per = [float(x) for x in t.cpu()]
+    if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
+        return
+    ms_per_step = ms_total / a.steps
+    value = GB * a.frames / (ms_per_step / 1000.0)
+    e2e_value = GB * a.frames / (e2e_ms / 1000.0 / a.steps)
+    peak, peak_src = measured_peaks()
+    t_mean = a.ctx + (a.frames + 1) / 2.0                     # mean cached length over the decode frames
+    abytes = algorithmic_bytes(a.batch, t_mean)
+    achieved = abytes / (dec_ms_per / 1000.0) / 1e9 if dec_ms_per > 0 else 0.0
+    traffic = None
+    tp = os.path.join(ROOT, "profiles", "traffic.json")
+    if os.path.isfile(tp):
+        with open(tp) as f:
+            traffic = json.load(f).get(f"b{a.batch}")
+    line = {
+        "metric": "audio_frames_per_s", "value": value, "unit": "frames/s", "n_gpus": world, "steps": a.steps,
+        "warmup": max(a.warmup, 3), "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
+        "config": {"workload": workload, "batch_per_gpu": a.batch, "global_batch": GB, "ctx_frames": a.ctx,
+                   "new_frames": a.frames, "parallelism": f"batch-sharded x{world}, weights replicated",
+                   "l2": "inputs larger than L2: 3.1 GB of weights are streamed every frame",
+                   "decode_ms_per_frame": dec_ms_per, "decode_frames_per_s_per_gpu": a.batch * 1000.0 / dec_ms_per},
+        "roofline": {"bound": "hbm", "kernel": "csm_stream_kernel (one launch = one frame for the whole batch)",
+                     "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
+                     "peak_source": peak_src, "algorithmic_bytes_per_launch": abytes, "traffic": traffic},
+        "e2e": {"value": e2e_value, "unit": "frames/s", "h2d_bytes_per_step": int(h_ids.numel() * 8 + h_mask.numel() * 4),
+                "d2h_bytes_per_step": int(a.batch * a.frames * 32 * 8)},
+        "gpu_launches": int(launches),
+        "clocks": clocks,
+    }
+    if want_cpu:
+        v, t_first, t_frame = cpu_reference_sample(cfg, sd, a.ctx, a.cpu_sample_frames, a.frames)
+        line["cpu_baseline"] = {
+            "value": v, "unit": "frames/s", "cores": torch.get_num_threads(), "kind": "port",
+            "sample": (f"oracle port of modeling_csm.py, fp32 torch CPU, batch 1: {a.ctx}-frame prefill+frame {t_first:.2f} s, "
+                       f"{a.cpu_sample_frames} decode frames {t_frame:.3f} s each, projected to {a.frames} frames")}
+    print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

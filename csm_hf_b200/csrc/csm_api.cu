@@ -1,0 +1,797 @@
+// C ABI of libcsm_b200.so (include/csm_b200.h): context creation (weight packing, workspace,
+// phase table), prefill orchestration, per-frame persistent launches, generate loop.
+#include <cublas_v2.h>
+#include <cuda_runtime.h>
+#include <math.h>
+#include <stdarg.h>
+#include <stdio.h>
+#include <stdlib.h>
+#include <string.h>
+
+#include <string>
+#include <vector>
+
+#include "../../include/csm_b200.h"
+#include "csm_types.h"
+
+// ---- kernels / launchers defined in the other translation units
+struct PackSrc {
+  const bf16* ptr[3];
+  int rows[3];
+  long long row_stride[3];
+  long long col_stride[3];
+};
+extern "C" {
+cudaError_t csm_launch_stream(const StreamParams* p, int grid, size_t smem, cudaStream_t stream, int cooperative);
+cudaError_t csm_pack_launch(const PackSrc* src, const int* row_map_dev, int N, int K, int gran, int G, bf16* dst,
+                            cudaStream_t stream);
+cudaError_t csm_embed_sum_launch(const long long* ids, const int* mask, int default_mask, const bf16* audio_emb,
+                                 const bf16* text_emb, int V, int H, bf16* out, int rows, cudaStream_t st);
+cudaError_t csm_rmsnorm_rows_launch(const bf16* x, const bf16* w, float eps, int H, bf16* y, int rows, cudaStream_t st);
+cudaError_t csm_rope_kv_rows_launch(bf16* qkv, int S, int pos0, int b0, int heads, int kv, int hd, const bf16* cos_t,
+                                    const bf16* sin_t, bf16* kc, bf16* vc, int layer, int Bmax, int Tcap, int rows,
+                                    cudaStream_t st);
+cudaError_t csm_swiglu_rows_launch(const bf16* gu, int I, bf16* act, long long rows, cudaStream_t st);
+cudaError_t csm_add_rows_launch(bf16* h, const bf16* y, long long n, cudaStream_t st);
+cudaError_t csm_take_last_rows_launch(const bf16* h, int S, int H, bf16* dst, int b0, int nseq, cudaStream_t st);
+cudaError_t csm_i64_to_i32_launch(const long long* src, int* dst, int n, cudaStream_t st);
+cudaError_t csm_i32_to_i64_launch(const int* src, long long* dst, int n, cudaStream_t st);
+cudaError_t csm_flash_prefill_launch(const bf16* qkv, int S, int pos0, int b0, int nseq, int heads, int kv,
+                                     const bf16* kc, const bf16* vc, int layer, int Bmax, int Tcap, float scale,
+                                     bf16* out, cudaStream_t st);
+}
+
+namespace {
+
+struct LayerW {
+  // natural-layout copies for the prefill GEMMs (backbone only)
+  bf16 *q = nullptr, *k = nullptr, *v = nullptr, *o = nullptr, *gate = nullptr, *up = nullptr, *down = nullptr;
+  bf16 *ln1 = nullptr, *ln2 = nullptr;
+  // packed for the frame engine
+  bf16 *p_qkv = nullptr, *p_o = nullptr, *p_gu = nullptr, *p_down = nullptr;
+};
+
+struct Stack {
+  StackDims d;
+  std::vector<LayerW> layers;
+  bf16* norm = nullptr;
+  bf16 *cos_t = nullptr, *sin_t = nullptr;
+  int n_pos = 0;
+};
+
+}  // namespace
+
+struct CsmCtx {
+  int device = 0, sms = 0, G = 0;
+  int Bmax = 0, Tcap = 0;
+  int V = 0, text_vocab = 0;
+  Stack bb, dec;
+  bf16 *text_emb = nullptr, *audio_emb = nullptr;
+  bf16 *p_proj = nullptr, *p_c0 = nullptr;
+  std::vector<bf16*> p_heads;
+  // workspace
+  bf16 *kc_bb = nullptr, *vc_bb = nullptr, *kc_dec = nullptr, *vc_dec = nullptr;
+  bf16 *h_bb = nullptr, *h_dec = nullptr, *q_bb = nullptr, *q_dec = nullptr, *attn_bb = nullptr, *attn_dec = nullptr;
+  bf16 *mlp_bb = nullptr, *mlp_dec = nullptr, *last_h = nullptr, *c0_logits = nullptr, *cb_logits = nullptr;
+  float* attn_part = nullptr;
+  int nsplit_max = 0;
+  unsigned int *attn_cnt = nullptr, *head_cnt = nullptr, *bar_counter = nullptr;
+  float2* head_part = nullptr;
+  int *samples = nullptr, *fed = nullptr, *stop_flag = nullptr, *n_frames = nullptr;
+  unsigned long long* prof = nullptr;
+  int prof_on = 0;
+  // prefill workspace (lazy)
+  int pf_rows = 0;
+  bf16 *pf_h = nullptr, *pf_hn = nullptr, *pf_qkv = nullptr, *pf_attn = nullptr, *pf_y = nullptr, *pf_gu = nullptr,
+       *pf_act = nullptr;
+  // host staging for csm_generate_host
+  long long* st_ids = nullptr;
+  int* st_mask = nullptr;
+  long long* st_frames = nullptr;
+  size_t st_ids_n = 0, st_frames_n = 0;
+  // phase table
+  std::vector<Phase> table;
+  Phase* d_table = nullptr;
+  int ph_head_c0 = 0;   // first phase of the "decoder part" of a frame (final norm + c0 head)
+  int cache_len = 0;
+  int stepped = 0;
+  long long launches = 0;
+  cublasHandle_t cublas = nullptr;
+  cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+  int ev_frames = 0;
+  std::vector<void*> allocs;
+  std::string err;
+};
+
+namespace {
+
+int fail(CsmCtx* c, int code, const char* fmt, ...) {
+  char buf[512];
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(buf, sizeof buf, fmt, ap);
+  va_end(ap);
+  if (c) c->err = buf;
+  return code;
+}
+
+#define CK(call)                                                                                         \
+  do {                                                                                                   \
+    cudaError_t e_ = (call);                                                                             \
+    if (e_ != cudaSuccess) return fail(ctx, CSM_ECUDA, "%s failed: %s (%s:%d)", #call, cudaGetErrorString(e_), \
+                                       __FILE__, __LINE__);                                              \
+  } while (0)
+
+template <typename T>
+int dalloc(CsmCtx* ctx, T** p, size_t n) {
+  void* q = nullptr;
+  size_t bytes = n * sizeof(T);
+  if (bytes == 0) bytes = 16;
+  CK(cudaMalloc(&q, bytes));
+  ctx->allocs.push_back(q);
+  *p = reinterpret_cast<T*>(q);
+  return 0;
+}
+#define DA(p, n)                                  \
+  do {                                            \
+    int r_ = dalloc(ctx, &(p), (size_t)(n));      \
+    if (r_) return r_;                            \
+  } while (0)
+
+int copy_weight(CsmCtx* ctx, bf16** dst, const void* src, size_t n, cudaStream_t st) {
+  DA(*dst, n);
+  CK(cudaMemcpyAsync(*dst, src, n * sizeof(bf16), cudaMemcpyDeviceToDevice, st));
+  return 0;
+}
+
+int pack_matrix(CsmCtx* ctx, bf16** dst, const PackSrc& src, const std::vector<int>* row_map, int N, int K, int gran,
+                cudaStream_t st) {
+  DA(*dst, (size_t)N * K);
+  int* d_map = nullptr;
+  if (row_map) {
+    CK(cudaMalloc(&d_map, row_map->size() * sizeof(int)));
+    CK(cudaMemcpyAsync(d_map, row_map->data(), row_map->size() * sizeof(int), cudaMemcpyHostToDevice, st));
+  }
+  CK(csm_pack_launch(&src, d_map, N, K, gran, ctx->G, *dst, st));
+  if (d_map) {
+    CK(cudaStreamSynchronize(st));
+    CK(cudaFree(d_map));
+  }
+  // every CTA may own at most CSM_MAX_NT*8 rows of a matrix
+  int U = N / gran, per = (U + ctx->G - 1) / ctx->G * gran;
+  if (per > CSM_MAX_NT * 8)
+    return fail(ctx, CSM_EINVAL, "matrix with %d rows needs %d rows per CTA on a %d-CTA grid (max %d)", N, per, ctx->G,
+                CSM_MAX_NT * 8);
+  return 0;
+}
+
+PackSrc one_src(const bf16* p, int rows, long long rs, long long cs) {
+  PackSrc s;
+  memset(&s, 0, sizeof s);
+  s.ptr[0] = p; s.rows[0] = rows; s.row_stride[0] = rs; s.col_stride[0] = cs;
+  s.ptr[1] = s.ptr[2] = p; s.rows[1] = s.rows[2] = 0; s.row_stride[1] = s.row_stride[2] = rs;
+  s.col_stride[1] = s.col_stride[2] = cs;
+  return s;
+}
+
+int build_stack(CsmCtx* ctx, Stack& S, const CsmLlamaShape& sh, const void* const* lw, const void* norm,
+                bool keep_natural, cudaStream_t st) {
+  StackDims& d = S.d;
+  d.H = sh.hidden; d.I = sh.inter; d.L = sh.layers; d.heads = sh.heads; d.kv = sh.kv_heads;
+  d.hd = sh.hidden / sh.heads; d.eps = sh.eps; d.scale = 1.0f / sqrtf((float)d.hd);
+  const int H = d.H, I = d.I, hd = d.hd, half = hd / 2;
+  const int nq = d.heads * hd, nkv = d.kv * hd;
+  S.layers.resize(d.L);
+  // row maps
+  std::vector<int> qkv_map((size_t)nq + 2 * nkv), gu_map((size_t)2 * I);
+  {
+    size_t n = 0;
+    for (int h = 0; h < d.heads; ++h)
+      for (int i = 0; i < half; ++i) { qkv_map[n++] = h * hd + i; qkv_map[n++] = h * hd + i + half; }
+    for (int h = 0; h < d.kv; ++h)
+      for (int i = 0; i < half; ++i) { qkv_map[n++] = nq + h * hd + i; qkv_map[n++] = nq + h * hd + i + half; }
+    for (int f = 0; f < nkv; ++f) qkv_map[n++] = nq + nkv + f;
+    for (int j = 0; j < I; ++j) { gu_map[2 * j] = j; gu_map[2 * j + 1] = I + j; }
+  }
+  for (int l = 0; l < d.L; ++l) {
+    const void* const* w = lw + (size_t)l * CSM_W_PER_LAYER;
+    LayerW& L = S.layers[l];
+    int r;
+    if ((r = copy_weight(ctx, &L.ln1, w[CSM_W_LN1], H, st))) return r;
+    if ((r = copy_weight(ctx, &L.ln2, w[CSM_W_LN2], H, st))) return r;
+    if (keep_natural) {
+      if ((r = copy_weight(ctx, &L.q, w[CSM_W_Q], (size_t)nq * H, st))) return r;
+      if ((r = copy_weight(ctx, &L.k, w[CSM_W_K], (size_t)nkv * H, st))) return r;
+      if ((r = copy_weight(ctx, &L.v, w[CSM_W_V], (size_t)nkv * H, st))) return r;
+      if ((r = copy_weight(ctx, &L.o, w[CSM_W_O], (size_t)H * nq, st))) return r;
+      if ((r = copy_weight(ctx, &L.gate, w[CSM_W_GATE], (size_t)I * H, st))) return r;
+      if ((r = copy_weight(ctx, &L.up, w[CSM_W_UP], (size_t)I * H, st))) return r;
+      if ((r = copy_weight(ctx, &L.down, w[CSM_W_DOWN], (size_t)H * I, st))) return r;
+    }
+    PackSrc s;
+    memset(&s, 0, sizeof s);
+    s.ptr[0] = (const bf16*)w[CSM_W_Q]; s.rows[0] = nq;
+    s.ptr[1] = (const bf16*)w[CSM_W_K]; s.rows[1] = nkv;
+    s.ptr[2] = (const bf16*)w[CSM_W_V]; s.rows[2] = nkv;
+    for (int i = 0; i < 3; ++i) { s.row_stride[i] = H; s.col_stride[i] = 1; }
+    if ((r = pack_matrix(ctx, &L.p_qkv, s, &qkv_map, nq + 2 * nkv, H, 2, st))) return r;
+    if ((r = pack_matrix(ctx, &L.p_o, one_src((const bf16*)w[CSM_W_O], H, nq, 1), nullptr, H, nq, 1, st))) return r;
+    memset(&s, 0, sizeof s);
+    s.ptr[0] = (const bf16*)w[CSM_W_GATE]; s.rows[0] = I;
+    s.ptr[1] = (const bf16*)w[CSM_W_UP]; s.rows[1] = I;
+    s.ptr[2] = s.ptr[1]; s.rows[2] = 0;
+    for (int i = 0; i < 3; ++i) { s.row_stride[i] = H; s.col_stride[i] = 1; }
+    if ((r = pack_matrix(ctx, &L.p_gu, s, &gu_map, 2 * I, H, 2, st))) return r;
+    if ((r = pack_matrix(ctx, &L.p_down, one_src((const bf16*)w[CSM_W_DOWN], H, I, 1), nullptr, H, I, 1, st))) return r;
+  }
+  int r;
+  if ((r = copy_weight(ctx, &S.norm, norm, H, st))) return r;
+  S.n_pos = sh.n_pos;
+  DA(S.cos_t, (size_t)sh.n_pos * half);
+  DA(S.sin_t, (size_t)sh.n_pos * half);
+  CK(cudaMemcpyAsync(S.cos_t, sh.rope_cos, (size_t)sh.n_pos * half * 2, cudaMemcpyHostToDevice, st));
+  CK(cudaMemcpyAsync(S.sin_t, sh.rope_sin, (size_t)sh.n_pos * half * 2, cudaMemcpyHostToDevice, st));
+  CK(cudaStreamSynchronize(st));
+  return 0;
+}
+
+Phase gemv(int act_mode, int epi, int gran, int N, int K, int stack, int layer, const bf16* w, const bf16* act,
+           int act_stride, const bf16* norm_w, bf16* out, int out_stride) {
+  Phase P;
+  memset(&P, 0, sizeof P);
+  P.type = PH_GEMV; P.act_mode = act_mode; P.epi = epi; P.gran = gran; P.N = N; P.K = K; P.stack = stack;
+  P.layer = layer; P.w = w; P.act = act; P.act_stride = act_stride; P.norm_w = norm_w; P.out = out;
+  P.out_stride = out_stride;
+  return P;
+}
+
+void add_layer_phases(CsmCtx* ctx, Stack& S, int stack, int l, int dec_pos, bool kv_only) {
+  const StackDims& d = S.d;
+  LayerW& L = S.layers[l];
+  bf16* h = stack ? ctx->h_dec : ctx->h_bb;
+  bf16* qb = stack ? ctx->q_dec : ctx->q_bb;
+  bf16* at = stack ? ctx->attn_dec : ctx->attn_bb;
+  bf16* mlp = stack ? ctx->mlp_dec : ctx->mlp_bb;
+  const int nq = d.heads * d.hd, nkv = d.kv * d.hd;
+  Phase P = gemv(ACT_NORM, EPI_QKV, 2, nq + 2 * nkv, d.H, stack, l, L.p_qkv, h, d.H, L.ln1, qb, nq);
+  P.dec_pos = dec_pos;
+  ctx->table.push_back(P);
+  if (kv_only) return;
+  memset(&P, 0, sizeof P);
+  P.type = stack ? PH_ATTN_DEC : PH_ATTN_BB; P.stack = stack; P.layer = l; P.dec_pos = dec_pos;
+  ctx->table.push_back(P);
+  ctx->table.push_back(gemv(ACT_PLAIN, EPI_RESID, 1, d.H, nq, stack, l, L.p_o, at, nq, nullptr, h, d.H));
+  ctx->table.push_back(gemv(ACT_NORM, EPI_SWIGLU, 2, 2 * d.I, d.H, stack, l, L.p_gu, h, d.H, L.ln2, mlp, d.I));
+  ctx->table.push_back(gemv(ACT_STREAM, EPI_RESID, 1, d.H, d.I, stack, l, L.p_down, mlp, d.I, nullptr, h, d.H));
+}
+
+void build_table(CsmCtx* ctx) {
+  ctx->table.clear();
+  const StackDims& b = ctx->bb.d;
+  const StackDims& d = ctx->dec.d;
+  Phase P;
+  memset(&P, 0, sizeof P);
+  P.type = PH_EMBED;
+  ctx->table.push_back(P);
+  for (int l = 0; l < b.L; ++l) add_layer_phases(ctx, ctx->bb, 0, l, 0, false);
+  ctx->ph_head_c0 = (int)ctx->table.size();
+  // final norm (-> last_hidden_state) + codebook-0 head + greedy sample (modeling_csm.py:361-365,531-532)
+  P = gemv(ACT_NORM, EPI_HEAD, 1, ctx->V, b.H, 0, 0, ctx->p_c0, ctx->h_bb, b.H, ctx->bb.norm, ctx->c0_logits, ctx->V);
+  P.cb = 0;
+  P.norm_out = ctx->last_h;
+  ctx->table.push_back(P);
+  for (int pos = 0; pos < CSM_DEC_POS; ++pos) {
+    // projection of last_h (pos 0) or of the previous codebook's embedding (modeling_csm.py:535-542,564-565)
+    if (pos == 0)
+      P = gemv(ACT_PLAIN, EPI_STORE, 1, d.H, b.H, 1, 0, ctx->p_proj, ctx->last_h, b.H, nullptr, ctx->h_dec, d.H);
+    else {
+      P = gemv(ACT_GATHER, EPI_STORE, 1, d.H, b.H, 1, 0, ctx->p_proj, ctx->audio_emb, b.H, nullptr, ctx->h_dec, d.H);
+      P.cb = pos - 1;
+    }
+    ctx->table.push_back(P);
+    for (int l = 0; l < d.L; ++l) add_layer_phases(ctx, ctx->dec, 1, l, pos, pos == 0 && l == d.L - 1);
+    if (pos >= 1) {
+      // audio_head[pos-1] on the decoder's final-norm output, greedy sample (modeling_csm.py:557-560)
+      P = gemv(ACT_NORM, EPI_HEAD, 1, ctx->V, d.H, 1, 0, ctx->p_heads[pos - 1], ctx->h_dec, d.H, ctx->dec.norm,
+               ctx->cb_logits + (size_t)(pos - 1) * ctx->V, (CSM_NQ - 1) * ctx->V);
+      P.cb = pos;
+      ctx->table.push_back(P);
+    }
+  }
+}
+
+struct SmemPlan {
+  int m_alloc, slot_bytes, n_slots, act_region, red_bytes, stream_tpc_max;
+  size_t total;
+};
+
+int plan_smem(CsmCtx* ctx, int B, SmemPlan* sp) {
+  const int kfull = ctx->bb.d.H > ctx->dec.d.H ? ctx->bb.d.H : ctx->dec.d.H;
+  sp->m_alloc = (B + 7) / 8 * 8;
+  sp->red_bytes = 512 * sp->m_alloc;
+  if (sp->red_bytes < 9216) sp->red_bytes = 9216;
+  sp->act_region = sp->m_alloc * (kfull + 8) * 2;
+  sp->act_region = (sp->act_region + 255) / 256 * 256;
+  const int limit = 227 * 1024;
+  int avail = limit - 256 - sp->red_bytes - sp->act_region;
+  int slot = 32 * 1024;
+  while (slot > 4096 && avail / slot < 3) slot /= 2;
+  if (avail / slot < 2) return fail(ctx, CSM_ECAPACITY, "batch %d leaves no shared memory for the weight ring", B);
+  sp->slot_bytes = slot;
+  sp->n_slots = avail / slot;
+  if (sp->n_slots > CSM_MAX_SLOTS) sp->n_slots = CSM_MAX_SLOTS;
+  const char* e = getenv("CSM_RING_SLOTS");
+  if (e && atoi(e) >= 2 && atoi(e) <= sp->n_slots) sp->n_slots = atoi(e);
+  // activation-stream chunk: two slots of [m_alloc][tpc*16+8] bf16 inside the activation region
+  int per_row = (sp->act_region / 2) / (sp->m_alloc * 2);
+  sp->stream_tpc_max = (per_row - 8) / 16;
+  if (sp->stream_tpc_max < 1) return fail(ctx, CSM_ECAPACITY, "activation region too small");
+  sp->total = 256 + (size_t)sp->red_bytes + sp->act_region + (size_t)sp->slot_bytes * sp->n_slots;
+  return 0;
+}
+
+int launch_frame(CsmCtx* ctx, int B, int ph_begin, int ph_end, const long long* ids, const int* mask, int forced,
+                 long long* out_frames, long long out_stride, long long out_off, int stop_on_zeros, int pos,
+                 cudaStream_t st) {
+  SmemPlan sp;
+  int r = plan_smem(ctx, B, &sp);
+  if (r) return r;
+  StreamParams p;
+  memset(&p, 0, sizeof p);
+  p.phases = ctx->d_table;
+  p.B = B; p.pos = pos; p.Bmax = ctx->Bmax; p.Tcap = ctx->Tcap; p.V = ctx->V; p.text_vocab = ctx->text_vocab;
+  p.bb = ctx->bb.d; p.dec = ctx->dec.d;
+  p.bar_counter = ctx->bar_counter;
+  p.kc_bb = ctx->kc_bb; p.vc_bb = ctx->vc_bb; p.kc_dec = ctx->kc_dec; p.vc_dec = ctx->vc_dec;
+  p.cos_bb = ctx->bb.cos_t; p.sin_bb = ctx->bb.sin_t; p.cos_dec = ctx->dec.cos_t; p.sin_dec = ctx->dec.sin_t;
+  p.q_bb = ctx->q_bb; p.q_dec = ctx->q_dec; p.attn_bb = ctx->attn_bb; p.attn_dec = ctx->attn_dec;
+  p.attn_part = ctx->attn_part; p.nsplit_max = ctx->nsplit_max; p.attn_cnt = ctx->attn_cnt;
+  p.head_part = ctx->head_part; p.head_cnt = ctx->head_cnt;
+  p.samples = ctx->samples; p.fed = ctx->fed; p.forced = forced;
+  p.ids = ids; p.mask = mask; p.text_emb = ctx->text_emb; p.audio_emb = ctx->audio_emb;
+  p.h_bb = ctx->h_bb;
+  p.out_frames = out_frames; p.out_stride = out_stride; p.out_off = out_off;
+  p.stop_flag = ctx->stop_flag; p.n_frames = ctx->n_frames; p.stop_on_zeros = stop_on_zeros;
+  p.m_alloc = sp.m_alloc; p.slot_bytes = sp.slot_bytes; p.n_slots = sp.n_slots;
+  p.act_region_bytes = sp.act_region; p.red_bytes = sp.red_bytes; p.stream_tpc_max = sp.stream_tpc_max;
+  p.prof = ctx->prof_on ? ctx->prof : nullptr;
+  if (!ctx->stepped) {
+    p.phase_begin = ph_begin; p.phase_end = ph_end; p.use_barrier = 1;
+    CK(cudaMemsetAsync(ctx->bar_counter, 0, sizeof(unsigned int), st));
+    CK(csm_launch_stream(&p, ctx->G, sp.total, st, 1));
+    ctx->launches += 1;
+  } else {
+    p.use_barrier = 0;
+    for (int ph = ph_begin; ph < ph_end; ++ph) {
+      p.phase_begin = ph; p.phase_end = ph + 1;
+      CK(csm_launch_stream(&p, ctx->G, sp.total, st, 0));
+      ctx->launches += 1;
+    }
+  }
+  return 0;
+}
+
+int gemm_bf16(CsmCtx* ctx, const bf16* x, int lda, const bf16* W, int N, int K, bf16* y, int ldc, int R,
+              cudaStream_t st) {
+  // row-major y[R,N] = x[R,K] * W[N,K]^T, fp32 accumulation, bf16 output (nn.Linear, no bias)
+  const float alpha = 1.f, beta = 0.f;
+  cublasStatus_t s = cublasSetStream(ctx->cublas, st);
+  if (s != CUBLAS_STATUS_SUCCESS) return fail(ctx, CSM_ECUDA, "cublasSetStream: %d", (int)s);
+  s = cublasGemmEx(ctx->cublas, CUBLAS_OP_T, CUBLAS_OP_N, N, R, K, &alpha, W, CUDA_R_16BF, K, x, CUDA_R_16BF, lda, &beta,
+                   y, CUDA_R_16BF, ldc, CUBLAS_COMPUTE_32F, CUBLAS_GEMM_DEFAULT);
+  if (s != CUBLAS_STATUS_SUCCESS) return fail(ctx, CSM_ECUDA, "cublasGemmEx(%d,%d,%d): %d", N, R, K, (int)s);
+  return 0;   // library kernels are not counted in ctx->launches (that counter is OUR kernels only)
+}
+
+int ensure_prefill_ws(CsmCtx* ctx, int rows) {
+  if (rows <= ctx->pf_rows) return 0;
+  const StackDims& d = ctx->bb.d;
+  const size_t W = (size_t)(d.heads + 2 * d.kv) * d.hd;
+  // (old buffers stay in ctx->allocs and are released at destroy; growth happens at most a few times)
+  ctx->pf_rows = rows;
+  DA(ctx->pf_h, (size_t)rows * d.H);
+  DA(ctx->pf_hn, (size_t)rows * d.H);
+  DA(ctx->pf_qkv, (size_t)rows * W);
+  DA(ctx->pf_attn, (size_t)rows * d.heads * d.hd);
+  DA(ctx->pf_y, (size_t)rows * d.H);
+  DA(ctx->pf_gu, (size_t)rows * 2 * d.I);
+  DA(ctx->pf_act, (size_t)rows * d.I);
+  return 0;
+}
+
+// Backbone over S new positions for sequences [0,B): fills the KV cache and leaves the last position's
+// residual-stream row (pre final-norm) in h_bb[b].
+int prefill(CsmCtx* ctx, const long long* ids, const int* mask, int B, int S, cudaStream_t st) {
+  const StackDims& d = ctx->bb.d;
+  const int W = (d.heads + 2 * d.kv) * d.hd, nq = d.heads * d.hd, nkv = d.kv * d.hd;
+  int group = 16384 / S;
+  if (group < 1) group = 1;
+  if (group > B) group = B;
+  int r = ensure_prefill_ws(ctx, group * S);
+  if (r) return r;
+  const int pos0 = ctx->cache_len;
+  for (int b0 = 0; b0 < B; b0 += group) {
+    const int nseq = (B - b0) < group ? (B - b0) : group;
+    const int R = nseq * S;
+    const long long* gi = ids + (size_t)b0 * S * (CSM_NQ + 1);
+    const int* gm = mask ? mask + (size_t)b0 * S * (CSM_NQ + 1) : nullptr;
+    CK(csm_embed_sum_launch(gi, gm, 2, ctx->audio_emb, ctx->text_emb, ctx->V, d.H, ctx->pf_h, R, st));
+    for (int l = 0; l < d.L; ++l) {
+      LayerW& L = ctx->bb.layers[l];
+      CK(csm_rmsnorm_rows_launch(ctx->pf_h, L.ln1, d.eps, d.H, ctx->pf_hn, R, st));
+      if ((r = gemm_bf16(ctx, ctx->pf_hn, d.H, L.q, nq, d.H, ctx->pf_qkv, W, R, st))) return r;
+      if ((r = gemm_bf16(ctx, ctx->pf_hn, d.H, L.k, nkv, d.H, ctx->pf_qkv + nq, W, R, st))) return r;
+      if ((r = gemm_bf16(ctx, ctx->pf_hn, d.H, L.v, nkv, d.H, ctx->pf_qkv + nq + nkv, W, R, st))) return r;
+      CK(csm_rope_kv_rows_launch(ctx->pf_qkv, S, pos0, b0, d.heads, d.kv, d.hd, ctx->bb.cos_t, ctx->bb.sin_t, ctx->kc_bb,
+                                 ctx->vc_bb, l, ctx->Bmax, ctx->Tcap, R, st));
+      CK(csm_flash_prefill_launch(ctx->pf_qkv, S, pos0, b0, nseq, d.heads, d.kv, ctx->kc_bb, ctx->vc_bb, l, ctx->Bmax,
+                                  ctx->Tcap, d.scale, ctx->pf_attn, st));
+      if ((r = gemm_bf16(ctx, ctx->pf_attn, nq, L.o, d.H, nq, ctx->pf_y, d.H, R, st))) return r;
+      CK(csm_add_rows_launch(ctx->pf_h, ctx->pf_y, (long long)R * d.H, st));
+      CK(csm_rmsnorm_rows_launch(ctx->pf_h, L.ln2, d.eps, d.H, ctx->pf_hn, R, st));
+      if ((r = gemm_bf16(ctx, ctx->pf_hn, d.H, L.gate, d.I, d.H, ctx->pf_gu, 2 * d.I, R, st))) return r;
+      if ((r = gemm_bf16(ctx, ctx->pf_hn, d.H, L.up, d.I, d.H, ctx->pf_gu + d.I, 2 * d.I, R, st))) return r;
+      CK(csm_swiglu_rows_launch(ctx->pf_gu, d.I, ctx->pf_act, R, st));
+      if ((r = gemm_bf16(ctx, ctx->pf_act, d.I, L.down, d.H, d.I, ctx->pf_y, d.H, R, st))) return r;
+      CK(csm_add_rows_launch(ctx->pf_h, ctx->pf_y, (long long)R * d.H, st));
+      ctx->launches += 7;
+    }
+    CK(csm_take_last_rows_launch(ctx->pf_h, S, d.H, ctx->h_bb, b0, nseq, st));
+    ctx->launches += 2;
+  }
+  return 0;
+}
+
+int frame_impl(CsmCtx* ctx, const long long* ids, const int* mask, int B, int S, const long long* force_tokens,
+               long long* out_frames, long long out_stride, long long out_off, int stop_on_zeros, cudaStream_t st) {
+  if (B < 1 || S < 1) return fail(ctx, CSM_EINVAL, "B and S must be >= 1 (got %d, %d)", B, S);
+  if (B > ctx->Bmax) return fail(ctx, CSM_ECAPACITY, "batch %d > max_batch %d", B, ctx->Bmax);
+  if (ctx->cache_len + S > ctx->Tcap)
+    return fail(ctx, CSM_ECAPACITY, "context %d + %d exceeds max_ctx %d", ctx->cache_len, S, ctx->Tcap);
+  int forced = 0;
+  if (force_tokens) {
+    CK(csm_i64_to_i32_launch(force_tokens, ctx->fed, B * CSM_NQ, st));
+    forced = 1;
+  }
+  int r;
+  if (S == 1) {
+    r = launch_frame(ctx, B, 0, (int)ctx->table.size(), ids, mask, forced, out_frames, out_stride, out_off, stop_on_zeros,
+                     ctx->cache_len, st);
+  } else {
+    if (!ids) return fail(ctx, CSM_EINVAL, "prefill needs input ids");
+    if ((r = prefill(ctx, ids, mask, B, S, st))) return r;
+    r = launch_frame(ctx, B, ctx->ph_head_c0, (int)ctx->table.size(), nullptr, nullptr, forced, out_frames, out_stride,
+                     out_off, stop_on_zeros, ctx->cache_len + S - 1, st);
+  }
+  if (r) return r;
+  ctx->cache_len += S;
+  return 0;
+}
+
+}  // namespace
+
+// =================================================================== exported C ABI
+extern "C" {
+
+int csm_create(const CsmShapes* sh, const CsmWeights* w, int max_batch, int max_ctx, void* stream, CsmCtx** out) {
+  if (!out) return CSM_EINVAL;
+  *out = nullptr;
+  CsmCtx* ctx = new CsmCtx();
+  *out = ctx;   // returned even on failure so that csm_last_error works; caller destroys it
+  cudaStream_t st = (cudaStream_t)stream;
+  if (!sh || !w) return fail(ctx, CSM_EINVAL, "null shapes/weights");
+  if (sh->n_codebooks != CSM_NQ) return fail(ctx, CSM_EINVAL, "audio_num_codebooks must be %d", CSM_NQ);
+  const CsmLlamaShape* ls[2] = {&sh->backbone, &sh->decoder};
+  for (int i = 0; i < 2; ++i) {
+    const CsmLlamaShape& s = *ls[i];
+    if (s.hidden % 64 || s.inter % 64 || s.hidden > 2048 || s.heads % s.kv_heads || s.hidden % s.heads)
+      return fail(ctx, CSM_EINVAL, "unsupported llama shape (hidden %d inter %d heads %d kv %d)", s.hidden, s.inter,
+                  s.heads, s.kv_heads);
+    if (!s.rope_cos || !s.rope_sin) return fail(ctx, CSM_EINVAL, "missing rope tables");
+  }
+  if (sh->backbone.hidden / sh->backbone.heads != 64) return fail(ctx, CSM_EINVAL, "backbone head_dim must be 64");
+  if (sh->decoder.hidden / sh->decoder.heads != 128) return fail(ctx, CSM_EINVAL, "decoder head_dim must be 128");
+  {
+    int rep = sh->backbone.heads / sh->backbone.kv_heads;
+    if (rep != 1 && rep != 2 && rep != 4) return fail(ctx, CSM_EINVAL, "backbone GQA ratio must be 1, 2 or 4");
+  }
+  if (max_batch < 1 || max_batch > 32) return fail(ctx, CSM_ECAPACITY, "max_batch must be in [1,32] per GPU");
+  if (max_ctx < 1 || sh->backbone.n_pos < max_ctx) return fail(ctx, CSM_EINVAL, "rope table shorter than max_ctx");
+  if (sh->decoder.n_pos < CSM_DEC_POS) return fail(ctx, CSM_EINVAL, "decoder rope table shorter than %d", CSM_DEC_POS);
+  CK(cudaGetDevice(&ctx->device));
+  CK(cudaDeviceGetAttribute(&ctx->sms, cudaDevAttrMultiProcessorCount, ctx->device));
+  int major = 0;
+  CK(cudaDeviceGetAttribute(&major, cudaDevAttrComputeCapabilityMajor, ctx->device));
+  if (major != 10) return fail(ctx, CSM_EUNSUPPORTED, "libcsm_b200 is built for sm_100a only (device is sm_%d)", major);
+  ctx->G = ctx->sms;
+  if (const char* e = getenv("CSM_GRID")) {
+    int g = atoi(e);
+    if (g >= 1 && g <= ctx->sms) ctx->G = g;
+  }
+  ctx->Bmax = max_batch;
+  ctx->Tcap = max_ctx;
+  ctx->V = sh->audio_vocab;
+  ctx->text_vocab = sh->text_vocab;
+  const int Hb = sh->backbone.hidden, Hd = sh->decoder.hidden;
+  int r;
+  if ((r = copy_weight(ctx, &ctx->text_emb, w->text_embeddings, (size_t)sh->text_vocab * Hb, st))) return r;
+  if ((r = copy_weight(ctx, &ctx->audio_emb, w->audio_embeddings, (size_t)sh->audio_vocab * CSM_NQ * Hb, st))) return r;
+  if ((r = build_stack(ctx, ctx->bb, sh->backbone, w->backbone_layers, w->backbone_norm, true, st))) return r;
+  if ((r = build_stack(ctx, ctx->dec, sh->decoder, w->decoder_layers, w->decoder_norm, false, st))) return r;
+  if ((r = pack_matrix(ctx, &ctx->p_proj, one_src((const bf16*)w->projection, Hd, Hb, 1), nullptr, Hd, Hb, 1, st))) return r;
+  if ((r = pack_matrix(ctx, &ctx->p_c0, one_src((const bf16*)w->codebook0_head, ctx->V, Hb, 1), nullptr, ctx->V, Hb, 1, st)))
+    return r;
+  ctx->p_heads.resize(CSM_NQ - 1);
+  for (int i = 0; i < CSM_NQ - 1; ++i) {
+    // audio_head[i] is [in=Hd, out=V]: packed row n = output n, column k = input k -> strides (1, V)
+    const bf16* base = (const bf16*)w->audio_head + (size_t)i * Hd * ctx->V;
+    if ((r = pack_matrix(ctx, &ctx->p_heads[i], one_src(base, ctx->V, 1, ctx->V), nullptr, ctx->V, Hd, 1, st))) return r;
+  }
+  // ---- workspace
+  const StackDims& b = ctx->bb.d;
+  const StackDims& d = ctx->dec.d;
+  const size_t B = max_batch;
+  DA(ctx->kc_bb, (size_t)b.L * B * b.kv * max_ctx * b.hd);
+  DA(ctx->vc_bb, (size_t)b.L * B * b.kv * max_ctx * b.hd);
+  DA(ctx->kc_dec, (size_t)d.L * B * d.kv * CSM_DEC_POS * d.hd);
+  DA(ctx->vc_dec, (size_t)d.L * B * d.kv * CSM_DEC_POS * d.hd);
+  DA(ctx->h_bb, B * b.H); DA(ctx->h_dec, B * d.H);
+  DA(ctx->q_bb, B * b.heads * b.hd); DA(ctx->q_dec, B * d.heads * d.hd);
+  DA(ctx->attn_bb, B * b.heads * b.hd); DA(ctx->attn_dec, B * d.heads * d.hd);
+  DA(ctx->mlp_bb, B * b.I); DA(ctx->mlp_dec, B * d.I);
+  DA(ctx->last_h, B * b.H); DA(ctx->c0_logits, B * ctx->V); DA(ctx->cb_logits, B * (CSM_NQ - 1) * ctx->V);
+  ctx->nsplit_max = (max_ctx + CSM_ATT_SPLIT - 1) / CSM_ATT_SPLIT;
+  DA(ctx->attn_part, B * b.heads * ctx->nsplit_max * (b.hd + 2));
+  DA(ctx->attn_cnt, B * b.kv);
+  DA(ctx->head_cnt, 4); DA(ctx->bar_counter, 4);
+  DA(ctx->head_part, (size_t)ctx->sms * B);
+  DA(ctx->samples, B * CSM_NQ); DA(ctx->fed, B * CSM_NQ);
+  DA(ctx->stop_flag, 4); DA(ctx->n_frames, 4);
+  CK(cudaMemsetAsync(ctx->attn_cnt, 0, B * b.kv * sizeof(unsigned), st));
+  CK(cudaMemsetAsync(ctx->head_cnt, 0, 16, st));
+  CK(cudaMemsetAsync(ctx->bar_counter, 0, 16, st));
+  CK(cudaMemsetAsync(ctx->stop_flag, 0, 16, st));
+  CK(cudaMemsetAsync(ctx->n_frames, 0, 16, st));
+  CK(cudaMemsetAsync(ctx->samples, 0, B * CSM_NQ * sizeof(int), st));
+  CK(cudaMemsetAsync(ctx->fed, 0, B * CSM_NQ * sizeof(int), st));
+  build_table(ctx);
+  DA(ctx->d_table, ctx->table.size());
+  DA(ctx->prof, 2 * ctx->table.size());
+  CK(cudaMemcpyAsync(ctx->d_table, ctx->table.data(), ctx->table.size() * sizeof(Phase), cudaMemcpyHostToDevice, st));
+  if (cublasCreate(&ctx->cublas) != CUBLAS_STATUS_SUCCESS) return fail(ctx, CSM_ECUDA, "cublasCreate failed");
+  CK(cudaEventCreate(&ctx->ev0));
+  CK(cudaEventCreate(&ctx->ev1));
+  // the persistent kernel needs every CTA resident: check the cooperative-launch limit once
+  SmemPlan sp;
+  if ((r = plan_smem(ctx, max_batch, &sp))) return r;
+  CK(cudaStreamSynchronize(st));
+  return CSM_OK;
+}
+
+int csm_destroy(CsmCtx* ctx) {
+  if (!ctx) return CSM_OK;
+  cudaDeviceSynchronize();
+  for (void* p : ctx->allocs) cudaFree(p);
+  if (ctx->st_ids) cudaFree(ctx->st_ids);
+  if (ctx->st_mask) cudaFree(ctx->st_mask);
+  if (ctx->st_frames) cudaFree(ctx->st_frames);
+  if (ctx->cublas) cublasDestroy(ctx->cublas);
+  if (ctx->ev0) cudaEventDestroy(ctx->ev0);
+  if (ctx->ev1) cudaEventDestroy(ctx->ev1);
+  delete ctx;
+  return CSM_OK;
+}
+
+int csm_reset(CsmCtx* ctx) {
+  if (!ctx) return CSM_EINVAL;
+  ctx->cache_len = 0;
+  return CSM_OK;
+}
+
+int csm_cache_len(const CsmCtx* ctx) { return ctx ? ctx->cache_len : CSM_EINVAL; }
+
+int csm_embed_sum(CsmCtx* ctx, const int64_t* ids, const int32_t* mask, int B, int S, void* out, void* stream) {
+  if (!ctx || !ids || !out) return fail(ctx, CSM_EINVAL, "null argument");
+  CK(csm_embed_sum_launch((const long long*)ids, mask, 1, ctx->audio_emb, ctx->text_emb, ctx->V, ctx->bb.d.H, (bf16*)out,
+                          B * S, (cudaStream_t)stream));
+  ctx->launches += 1;
+  return CSM_OK;
+}
+
+int csm_generate_frame(CsmCtx* ctx, const int64_t* ids, const int32_t* mask, int B, int S, const int64_t* force_tokens,
+                       int64_t* samples, void* last_h, void* c0_logits, void* cb_logits, void* stream) {
+  if (!ctx) return CSM_EINVAL;
+  if (!ids) return fail(ctx, CSM_EINVAL, "input_ids is required");
+  cudaStream_t st = (cudaStream_t)stream;
+  CK(cudaMemsetAsync(ctx->stop_flag, 0, sizeof(int), st));
+  int r = frame_impl(ctx, (const long long*)ids, mask, B, S, (const long long*)force_tokens, nullptr, 0, 0, 0, st);
+  if (r) return r;
+  if (samples) CK(csm_i32_to_i64_launch(ctx->samples, (long long*)samples, B * CSM_NQ, st));
+  if (last_h) CK(cudaMemcpyAsync(last_h, ctx->last_h, (size_t)B * ctx->bb.d.H * 2, cudaMemcpyDeviceToDevice, st));
+  if (c0_logits) CK(cudaMemcpyAsync(c0_logits, ctx->c0_logits, (size_t)B * ctx->V * 2, cudaMemcpyDeviceToDevice, st));
+  if (cb_logits)
+    CK(cudaMemcpyAsync(cb_logits, ctx->cb_logits, (size_t)B * (CSM_NQ - 1) * ctx->V * 2, cudaMemcpyDeviceToDevice, st));
+  return CSM_OK;
+}
+
+int csm_generate(CsmCtx* ctx, const int64_t* ids, const int32_t* mask, int B, int T, int max_new_frames,
+                 int stop_on_all_zeros, int64_t* frames, void* stream) {
+  if (!ctx) return CSM_EINVAL;
+  if (!ids || !frames) return fail(ctx, CSM_EINVAL, "null argument");
+  if (max_new_frames < 0) return fail(ctx, CSM_EINVAL, "max_new_frames < 0");
+  if (T < 1) return fail(ctx, CSM_EINVAL, "empty context");
+  if (T + max_new_frames > ctx->Tcap + 1)
+    return fail(ctx, CSM_ECAPACITY, "context %d + %d new frames exceeds max_ctx %d", T, max_new_frames, ctx->Tcap);
+  cudaStream_t st = (cudaStream_t)stream;
+  ctx->cache_len = 0;
+  ctx->ev_frames = 0;
+  CK(cudaMemsetAsync(ctx->stop_flag, 0, sizeof(int), st));
+  CK(cudaMemsetAsync(ctx->n_frames, 0, sizeof(int), st));
+  if (max_new_frames == 0) return CSM_OK;
+  CK(cudaMemsetAsync(frames, 0, (size_t)B * max_new_frames * CSM_NQ * sizeof(int64_t), st));
+  const long long stride = (long long)max_new_frames * CSM_NQ;
+  int r = frame_impl(ctx, (const long long*)ids, mask, B, T, nullptr, (long long*)frames, stride, 0, stop_on_all_zeros, st);
+  if (r) return r;
+  CK(cudaEventRecord(ctx->ev0, st));
+  for (int f = 1; f < max_new_frames; ++f) {
+    // next input row = the 32 new ids + a zero text column, audio slots unmasked (modeling_csm.py:675-690)
+    r = frame_impl(ctx, nullptr, nullptr, B, 1, nullptr, (long long*)frames, stride, (long long)f * CSM_NQ,
+                   stop_on_all_zeros, st);
+    if (r) return r;
+    ctx->ev_frames += 1;
+  }
+  CK(cudaEventRecord(ctx->ev1, st));
+  return CSM_OK;
+}
+
+int csm_frames_done(CsmCtx* ctx, void* stream) {
+  if (!ctx) return CSM_EINVAL;
+  int n = 0;
+  CK(cudaMemcpyAsync(&n, ctx->n_frames, sizeof(int), cudaMemcpyDeviceToHost, (cudaStream_t)stream));
+  CK(cudaStreamSynchronize((cudaStream_t)stream));
+  return n;
+}
+
+int csm_generate_host(CsmCtx* ctx, const int64_t* ids_host, const int32_t* mask_host, int B, int T, int max_new_frames,
+                      int stop_on_all_zeros, int64_t* frames_host, int* n_out, void* stream) {
+  if (!ctx) return CSM_EINVAL;
+  if (!ids_host || !frames_host) return fail(ctx, CSM_EINVAL, "null argument");
+  cudaStream_t st = (cudaStream_t)stream;
+  const size_t n_in = (size_t)B * T * (CSM_NQ + 1);
+  const size_t n_fr = (size_t)B * (max_new_frames > 0 ? max_new_frames : 1) * CSM_NQ;
+  if (n_in > ctx->st_ids_n) {
+    if (ctx->st_ids) cudaFree(ctx->st_ids);
+    if (ctx->st_mask) cudaFree(ctx->st_mask);
+    ctx->st_ids = nullptr; ctx->st_mask = nullptr; ctx->st_ids_n = 0;
+    CK(cudaMalloc(&ctx->st_ids, n_in * sizeof(long long)));
+    CK(cudaMalloc(&ctx->st_mask, n_in * sizeof(int)));
+    ctx->st_ids_n = n_in;
+  }
+  if (n_fr > ctx->st_frames_n) {
+    if (ctx->st_frames) cudaFree(ctx->st_frames);
+    ctx->st_frames = nullptr; ctx->st_frames_n = 0;
+    CK(cudaMalloc(&ctx->st_frames, n_fr * sizeof(long long)));
+    ctx->st_frames_n = n_fr;
+  }
+  CK(cudaMemcpyAsync(ctx->st_ids, ids_host, n_in * sizeof(long long), cudaMemcpyHostToDevice, st));
+  if (mask_host) CK(cudaMemcpyAsync(ctx->st_mask, mask_host, n_in * sizeof(int), cudaMemcpyHostToDevice, st));
+  int r = csm_generate(ctx, (const int64_t*)ctx->st_ids, mask_host ? ctx->st_mask : nullptr, B, T, max_new_frames,
+                       stop_on_all_zeros, (int64_t*)ctx->st_frames, st);
+  if (r) return r;
+  if (max_new_frames > 0)
+    CK(cudaMemcpyAsync(frames_host, ctx->st_frames, (size_t)B * max_new_frames * CSM_NQ * sizeof(long long),
+                       cudaMemcpyDeviceToHost, st));
+  int n = csm_frames_done(ctx, st);
+  if (n < 0) return n;
+  if (n_out) *n_out = n;
+  return CSM_OK;
+}
+
+int64_t csm_info(const CsmCtx* ctx, int what) {
+  if (!ctx) return -1;
+  switch (what) {
+    case CSM_INFO_SMS: return ctx->sms;
+    case CSM_INFO_GRID: return ctx->G;
+    case CSM_INFO_PHASES_PER_FRAME: return (int64_t)ctx->table.size();
+    case CSM_INFO_SMEM_BYTES: {
+      SmemPlan sp;
+      CsmCtx* c = const_cast<CsmCtx*>(ctx);
+      if (plan_smem(c, ctx->Bmax, &sp)) return -1;
+      return (int64_t)sp.total;
+    }
+    case CSM_INFO_LAUNCHES: return ctx->launches;
+    case CSM_INFO_STEPPED: return ctx->stepped;
+  }
+  return -1;
+}
+
+int csm_set_stepped(CsmCtx* ctx, int stepped) {
+  if (!ctx) return CSM_EINVAL;
+  ctx->stepped = stepped ? 1 : 0;
+  return CSM_OK;
+}
+
+int csm_last_decode_ms(CsmCtx* ctx, float* ms, int* n) {
+  if (!ctx || !ms || !n) return CSM_EINVAL;
+  *ms = 0.f;
+  *n = ctx->ev_frames;
+  if (ctx->ev_frames <= 0) return CSM_OK;
+  CK(cudaEventSynchronize(ctx->ev1));
+  CK(cudaEventElapsedTime(ms, ctx->ev0, ctx->ev1));
+  return CSM_OK;
+}
+
+const char* csm_last_error(const CsmCtx* ctx) { return ctx ? ctx->err.c_str() : "null context"; }
+
+// ---- debug / test hooks (see include/csm_b200.h)
+int csm_debug_copy(CsmCtx* ctx, int which, void* dst_device, int64_t max_bytes, int64_t* bytes_out, void* stream) {
+  if (!ctx) return CSM_EINVAL;
+  const StackDims& b = ctx->bb.d;
+  const StackDims& d = ctx->dec.d;
+  const size_t B = ctx->Bmax;
+  const void* src = nullptr;
+  size_t n = 0;
+  switch (which) {
+    case 0: src = ctx->h_bb; n = B * b.H * 2; break;
+    case 1: src = ctx->h_dec; n = B * d.H * 2; break;
+    case 2: src = ctx->q_bb; n = B * b.heads * b.hd * 2; break;
+    case 3: src = ctx->q_dec; n = B * d.heads * d.hd * 2; break;
+    case 4: src = ctx->attn_bb; n = B * b.heads * b.hd * 2; break;
+    case 5: src = ctx->attn_dec; n = B * d.heads * d.hd * 2; break;
+    case 6: src = ctx->mlp_bb; n = B * b.I * 2; break;
+    case 7: src = ctx->mlp_dec; n = B * d.I * 2; break;
+    case 8: src = ctx->last_h; n = B * b.H * 2; break;
+    case 9: src = ctx->c0_logits; n = B * ctx->V * 2; break;
+    case 10: src = ctx->cb_logits; n = B * (CSM_NQ - 1) * ctx->V * 2; break;
+    case 11: src = ctx->samples; n = B * CSM_NQ * 4; break;
+    case 12: src = ctx->fed; n = B * CSM_NQ * 4; break;
+    case 13: src = ctx->kc_bb; n = (size_t)b.L * B * b.kv * ctx->Tcap * b.hd * 2; break;
+    case 14: src = ctx->vc_bb; n = (size_t)b.L * B * b.kv * ctx->Tcap * b.hd * 2; break;
+    case 15: src = ctx->kc_dec; n = (size_t)d.L * B * d.kv * CSM_DEC_POS * d.hd * 2; break;
+    case 16: src = ctx->vc_dec; n = (size_t)d.L * B * d.kv * CSM_DEC_POS * d.hd * 2; break;
+    default: return fail(ctx, CSM_EINVAL, "unknown debug buffer %d", which);
+  }
+  if (bytes_out) *bytes_out = (int64_t)n;
+  if (!dst_device) return CSM_OK;
+  if ((int64_t)n > max_bytes) n = (size_t)max_bytes;
+  CK(cudaMemcpyAsync(dst_device, src, n, cudaMemcpyDeviceToDevice, (cudaStream_t)stream));
+  return CSM_OK;
+}
+
+int csm_debug_run_phases(CsmCtx* ctx, const int64_t* ids, const int32_t* mask, int B, int ph_begin, int ph_end,
+                         int forced, void* stream) {
+  if (!ctx) return CSM_EINVAL;
+  if (ph_begin < 0 || ph_end > (int)ctx->table.size() || ph_begin >= ph_end)
+    return fail(ctx, CSM_EINVAL, "bad phase range [%d,%d)", ph_begin, ph_end);
+  return launch_frame(ctx, B, ph_begin, ph_end, (const long long*)ids, mask, forced, nullptr, 0, 0, 0, ctx->cache_len,
+                      (cudaStream_t)stream);
+}
+
+int csm_debug_profile_frame(CsmCtx* ctx, int B, uint64_t* clocks_host, int32_t* info_host, void* stream) {
+  // one decode frame (ids from the last sampled frame) with per-phase clock64 stamps of CTA 0
+  if (!ctx || !clocks_host) return CSM_EINVAL;
+  cudaStream_t st = (cudaStream_t)stream;
+  const size_t n = ctx->table.size();
+  CK(cudaMemsetAsync(ctx->prof, 0, 2 * n * sizeof(unsigned long long), st));
+  ctx->prof_on = 1;
+  int r = launch_frame(ctx, B, 0, (int)n, nullptr, nullptr, 0, nullptr, 0, 0, 0, ctx->cache_len, st);
+  ctx->prof_on = 0;
+  if (r) return r;
+  CK(cudaMemcpyAsync(clocks_host, ctx->prof, 2 * n * sizeof(unsigned long long), cudaMemcpyDeviceToHost, st));
+  CK(cudaStreamSynchronize(st));
+  if (info_host)
+    for (size_t i = 0; i < n; ++i) {
+      const Phase& P = ctx->table[i];
+      info_host[4 * i + 0] = P.type; info_host[4 * i + 1] = P.type == PH_GEMV ? P.epi : -1;
+      info_host[4 * i + 2] = P.stack; info_host[4 * i + 3] = P.type == PH_GEMV ? P.act_mode : -1;
+    }
+  return CSM_OK;
+}
+
+int csm_debug_set_cache_len(CsmCtx* ctx, int len) {
+  if (!ctx) return CSM_EINVAL;
+  ctx->cache_len = len;
+  return CSM_OK;
+}
+
+}  // extern "C"

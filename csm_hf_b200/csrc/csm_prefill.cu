@@ -1,0 +1,360 @@
+// Context prefill kernels: the first CSMModel.forward call of generate() (modeling_csm.py:508-517 with
+// S = T context frames).  Row-parallel kernels around the dense projections: masked 33-way
+// embedding gather-sum, RMSNorm, RoPE + KV-cache write, causal GQA flash attention on
+// mma.sync tensor cores, SwiGLU, residual add.  The projections themselves are plain GEMMs
+// (csm_api.cu: csm_gemm_bf16).
+#include "csm_common.cuh"
+
+// ---------------------------------------------------------------- K1: masked 33-way gather-sum
+// out[r] = sum_slot mask[r][slot] * emb(slot, ids[r][slot])   (modeling_csm.py:261-282, 327-334)
+// One CTA per frame row; each thread owns 8 contiguous features (one 16-byte load per slot),
+// fp32 accumulation in slot order (audio 0..31, then text), one bf16 rounding.
+__global__ void csm_embed_sum_kernel(const long long* __restrict__ ids, const int* __restrict__ mask, int default_mask,
+                                     const bf16* __restrict__ audio_emb, const bf16* __restrict__ text_emb, int V, int H,
+                                     bf16* __restrict__ out, int rows) {
+  const int r = blockIdx.x;
+  if (r >= rows) return;
+  __shared__ long long s_tok[CSM_NQ + 1];
+  __shared__ int s_mk[CSM_NQ + 1];
+  if (threadIdx.x <= CSM_NQ) {
+    int slot = threadIdx.x;
+    s_tok[slot] = ids[(size_t)r * (CSM_NQ + 1) + slot];
+    // default_mask 1: all slots present (attention_mask=None, modeling_csm.py:330-331); 2: audio slots only
+    s_mk[slot] = mask ? mask[(size_t)r * (CSM_NQ + 1) + slot] : (default_mask == 1 ? 1 : (slot < CSM_NQ ? 1 : 0));
+  }
+  __syncthreads();
+  for (int c8 = threadIdx.x; c8 < H / 8; c8 += blockDim.x) {
+    float acc[8];
+#pragma unroll
+    for (int i = 0; i < 8; ++i) acc[i] = 0.f;
+    for (int slot = 0; slot <= CSM_NQ; ++slot) {
+      const int mk = s_mk[slot];
+      if (mk == 0) continue;
+      const bf16* row = slot < CSM_NQ ? audio_emb + (size_t)(s_tok[slot] + (long long)slot * V) * H
+                                      : text_emb + (size_t)s_tok[slot] * H;
+      uint4 v = __ldg(reinterpret_cast<const uint4*>(row) + c8);
+      const uint32_t* u = reinterpret_cast<const uint32_t*>(&v);
+      const float f = (float)mk;
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        acc[2 * i] += bf_lo(u[i]) * f;
+        acc[2 * i + 1] += bf_hi(u[i]) * f;
+      }
+    }
+    uint4 o;
+    o.x = pack_bf16(acc[0], acc[1]);
+    o.y = pack_bf16(acc[2], acc[3]);
+    o.z = pack_bf16(acc[4], acc[5]);
+    o.w = pack_bf16(acc[6], acc[7]);
+    reinterpret_cast<uint4*>(out + (size_t)r * H)[c8] = o;
+  }
+}
+
+// ---------------------------------------------------------------- RMSNorm over rows (hf modeling_llama.py:62-67)
+__global__ void csm_rmsnorm_rows_kernel(const bf16* __restrict__ x, const bf16* __restrict__ w, float eps, int H,
+                                        bf16* __restrict__ y, int rows) {
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int r = blockIdx.x * (blockDim.x >> 5) + warp;
+  if (r >= rows) return;
+  const bf16* src = x + (size_t)r * H;
+  uint4 v[8];
+  float ss = 0.f;
+#pragma unroll
+  for (int i = 0; i < 8; ++i) {
+    int idx = (i * 32 + lane) * 8;
+    if (idx < H) {
+      v[i] = *reinterpret_cast<const uint4*>(src + idx);
+      const uint32_t* u = reinterpret_cast<const uint32_t*>(&v[i]);
+#pragma unroll
+      for (int q = 0; q < 4; ++q) { float a = bf_lo(u[q]), b = bf_hi(u[q]); ss += a * a + b * b; }
+    }
+  }
+  ss = warp_sum(ss);
+  const float rstd = rsqrtf(ss / (float)H + eps);
+#pragma unroll
+  for (int i = 0; i < 8; ++i) {
+    int idx = (i * 32 + lane) * 8;
+    if (idx < H) {
+      uint4 wv = __ldg(reinterpret_cast<const uint4*>(w + idx));
+      const uint32_t* u = reinterpret_cast<const uint32_t*>(&v[i]);
+      const uint32_t* ww = reinterpret_cast<const uint32_t*>(&wv);
+      uint4 o;
+      uint32_t* ou = reinterpret_cast<uint32_t*>(&o);
+#pragma unroll
+      for (int q = 0; q < 4; ++q) {
+        float y0 = bfround(bf_lo(u[q]) * rstd), y1 = bfround(bf_hi(u[q]) * rstd);
+        ou[q] = pack_bf16(bf_lo(ww[q]) * y0, bf_hi(ww[q]) * y1);
+      }
+      *reinterpret_cast<uint4*>(y + (size_t)r * H + idx) = o;
+    }
+  }
+}
+
+// ---------------------------------------------------------------- RoPE + KV-cache write for prefill rows
+// qkv rows [(b,s)][q | k | v] in natural feature order.  q is rotated in place, k rotated into the
+// cache, v copied (apply_rotary_pos_emb, hf modeling_llama.py:146-168; DynamicCache.update,
+// hf cache_utils.py:102-121 -- here a write at the position instead of a concat).
+__global__ void csm_rope_kv_rows_kernel(bf16* __restrict__ qkv, int S, int pos0, int b0, int heads, int kv, int hd,
+                                        const bf16* __restrict__ cos_t, const bf16* __restrict__ sin_t,
+                                        bf16* __restrict__ kc, bf16* __restrict__ vc, int layer, int Bmax, int Tcap,
+                                        int rows) {
+  const int r = blockIdx.x;
+  if (r >= rows) return;
+  const int b = b0 + r / S, s = r % S, pos = pos0 + s;
+  const int half = hd / 2;
+  const int width = (heads + 2 * kv) * hd;
+  bf16* row = qkv + (size_t)r * width;
+  const int npairs = (heads + kv) * half;
+  for (int pidx = threadIdx.x; pidx < npairs + kv * half; pidx += blockDim.x) {
+    if (pidx < npairs) {
+      const bool isq = pidx < heads * half;
+      const int pp = isq ? pidx : pidx - heads * half;
+      const int head = pp / half, i = pp % half;
+      bf16* src = row + (isq ? 0 : heads * hd) + head * hd + i;
+      const float x1 = __bfloat162float(src[0]), x2 = __bfloat162float(src[half]);
+      const float cs = __bfloat162float(cos_t[(size_t)pos * half + i]);
+      const float sn = __bfloat162float(sin_t[(size_t)pos * half + i]);
+      const float o1 = bfround(bfround(x1 * cs) + bfround(-x2 * sn));
+      const float o2 = bfround(bfround(x2 * cs) + bfround(x1 * sn));
+      bf16* dst = isq ? src : kc + ((((size_t)layer * Bmax + b) * kv + head) * Tcap + pos) * hd + i;
+      dst[0] = __float2bfloat16_rn(o1);
+      dst[half] = __float2bfloat16_rn(o2);
+    } else {
+      const int f = (pidx - npairs) * 2;
+      const int head = f / hd, d = f % hd;
+      const uint32_t v = *reinterpret_cast<const uint32_t*>(row + (heads + kv) * hd + f);
+      *reinterpret_cast<uint32_t*>(vc + ((((size_t)layer * Bmax + b) * kv + head) * Tcap + pos) * hd + d) = v;
+    }
+  }
+}
+
+// ---------------------------------------------------------------- SwiGLU rows: act = bf16(silu(gate)) * up
+__global__ void csm_swiglu_rows_kernel(const bf16* __restrict__ gu, int I, bf16* __restrict__ act, long long n2) {
+  // gu rows are [gate(I) | up(I)]; n2 = rows * I / 2 pairs
+  for (long long e = (long long)blockIdx.x * blockDim.x + threadIdx.x; e < n2; e += (long long)gridDim.x * blockDim.x) {
+    const long long r = e / (I / 2);
+    const int j2 = (int)(e % (I / 2));
+    const uint32_t g = reinterpret_cast<const uint32_t*>(gu + (size_t)r * 2 * I)[j2];
+    const uint32_t u = reinterpret_cast<const uint32_t*>(gu + (size_t)r * 2 * I + I)[j2];
+    const float g0 = bf_lo(g), g1 = bf_hi(g);
+    const float s0 = bfround(g0 / (1.f + expf(-g0))), s1 = bfround(g1 / (1.f + expf(-g1)));
+    reinterpret_cast<uint32_t*>(act + (size_t)r * I)[j2] = pack_bf16(s0 * bf_lo(u), s1 * bf_hi(u));
+  }
+}
+
+// ---------------------------------------------------------------- residual add: h = bf16(h + y)
+__global__ void csm_add_rows_kernel(bf16* __restrict__ h, const bf16* __restrict__ y, long long n2) {
+  for (long long e = (long long)blockIdx.x * blockDim.x + threadIdx.x; e < n2; e += (long long)gridDim.x * blockDim.x) {
+    const uint32_t a = reinterpret_cast<const uint32_t*>(h)[e], b = reinterpret_cast<const uint32_t*>(y)[e];
+    reinterpret_cast<uint32_t*>(h)[e] = pack_bf16(bf_lo(a) + bf_lo(b), bf_hi(a) + bf_hi(b));
+  }
+}
+
+// ---------------------------------------------------------------- copy the last position's hidden row per sequence
+__global__ void csm_take_last_rows_kernel(const bf16* __restrict__ h, int S, int H, bf16* __restrict__ dst, int b0) {
+  const int b = blockIdx.x;
+  const uint4* src = reinterpret_cast<const uint4*>(h + ((size_t)b * S + (S - 1)) * H);
+  uint4* d = reinterpret_cast<uint4*>(dst + (size_t)(b0 + b) * H);
+  for (int i = threadIdx.x; i < H / 8; i += blockDim.x) d[i] = src[i];
+}
+
+__global__ void csm_i64_to_i32_kernel(const long long* __restrict__ src, int* __restrict__ dst, int n) {
+  int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) dst[i] = (int)src[i];
+}
+__global__ void csm_i32_to_i64_kernel(const int* __restrict__ src, long long* __restrict__ dst, int n) {
+  int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) dst[i] = (long long)src[i];
+}
+
+// ---------------------------------------------------------------- causal GQA flash attention (prefill), hd = 64
+// grid (ceil(S/64), heads, nseq); 4 warps x 16 query rows.  K/V come from the cache (already rotated),
+// q from the qkv rows.  Online softmax in fp32; P is rounded to bf16 for the PV MMA as every
+// flash kernel (incl. the SDPA kernels the reference dispatches to) does.
+__device__ __forceinline__ void ldmatrix_x2_trans(uint32_t& r0, uint32_t& r1, const void* smem_row) {
+  asm volatile("ldmatrix.sync.aligned.m8n8.x2.trans.shared.b16 {%0,%1}, [%2];"
+               : "=r"(r0), "=r"(r1)
+               : "r"(smem_u32(smem_row)));
+}
+
+__global__ void __launch_bounds__(128) csm_flash_prefill_kernel(const bf16* __restrict__ qkv, int S, int pos0, int b0,
+                                                                int heads, int kv, const bf16* __restrict__ kc,
+                                                                const bf16* __restrict__ vc, int layer, int Bmax,
+                                                                int Tcap, float scale, bf16* __restrict__ out) {
+  constexpr int HD = 64, BQ = 64, BK = 64, LDS = 72;
+  __shared__ __align__(16) bf16 sK[BK * LDS];
+  __shared__ __align__(16) bf16 sV[BK * LDS];
+  const int qt = blockIdx.x, head = blockIdx.y, bl = blockIdx.z;
+  const int b = b0 + bl;
+  const int kvh = head / (heads / kv);
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, g = lane >> 2, t = lane & 3;
+  const int width = (heads + 2 * kv) * HD;
+  const int q0 = qt * BQ + warp * 16;        // first query row (sequence-local) of this warp
+  const int r_lo = q0 + g, r_hi = q0 + g + 8;
+  // Q fragments (A operand), 4 k16-tiles
+  uint32_t qa[4][4];
+  {
+    const bf16* qlo = qkv + ((size_t)bl * S + r_lo) * width + head * HD;
+    const bf16* qhi = qkv + ((size_t)bl * S + r_hi) * width + head * HD;
+#pragma unroll
+    for (int kt = 0; kt < 4; ++kt) {
+      const int col = kt * 16 + 2 * t;
+      qa[kt][0] = r_lo < S ? *reinterpret_cast<const uint32_t*>(qlo + col) : 0u;
+      qa[kt][1] = r_hi < S ? *reinterpret_cast<const uint32_t*>(qhi + col) : 0u;
+      qa[kt][2] = r_lo < S ? *reinterpret_cast<const uint32_t*>(qlo + col + 8) : 0u;
+      qa[kt][3] = r_hi < S ? *reinterpret_cast<const uint32_t*>(qhi + col + 8) : 0u;
+    }
+  }
+  float o[8][4];
+#pragma unroll
+  for (int j = 0; j < 8; ++j)
+#pragma unroll
+    for (int q = 0; q < 4; ++q) o[j][q] = 0.f;
+  float m_lo = -INFINITY, m_hi = -INFINITY, l_lo = 0.f, l_hi = 0.f;
+  const int p_lo = pos0 + r_lo, p_hi = pos0 + r_hi;              // absolute positions of this lane's rows
+  const int last_key = min(pos0 + qt * BQ + BQ - 1, pos0 + S - 1);  // causal limit of the CTA
+  const size_t kvbase = (((size_t)layer * Bmax + b) * kv + kvh) * (size_t)Tcap * HD;
+  const float sl2 = scale * 1.4426950408889634f;
+  for (int k0 = 0; k0 <= last_key; k0 += BK) {
+    __syncthreads();
+    for (int i = threadIdx.x; i < BK * HD / 8; i += 128) {
+      const int kr = i / (HD / 8), c8 = i % (HD / 8);
+      uint4 kv4 = make_uint4(0, 0, 0, 0), vv4 = make_uint4(0, 0, 0, 0);
+      if (k0 + kr <= last_key) {
+        kv4 = *reinterpret_cast<const uint4*>(kc + kvbase + (size_t)(k0 + kr) * HD + c8 * 8);
+        vv4 = *reinterpret_cast<const uint4*>(vc + kvbase + (size_t)(k0 + kr) * HD + c8 * 8);
+      }
+      *reinterpret_cast<uint4*>(sK + kr * LDS + c8 * 8) = kv4;
+      *reinterpret_cast<uint4*>(sV + kr * LDS + c8 * 8) = vv4;
+    }
+    __syncthreads();
+    if (k0 > pos0 + q0 + 15) continue;   // whole block is in this warp's future
+    float sc[8][4];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+#pragma unroll
+      for (int q = 0; q < 4; ++q) sc[j][q] = 0.f;
+#pragma unroll
+      for (int kt = 0; kt < 4; ++kt) {
+        const bf16* kp = sK + (8 * j + g) * LDS + kt * 16 + 2 * t;
+        const uint32_t b0r = *reinterpret_cast<const uint32_t*>(kp);
+        const uint32_t b1r = *reinterpret_cast<const uint32_t*>(kp + 8);
+        mma16816(sc[j], qa[kt], b0r, b1r);
+      }
+    }
+    // mask + online softmax (base-2 exponent with the scale folded in)
+    float mx_lo = m_lo, mx_hi = m_hi;
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      const int key = k0 + 8 * j + 2 * t;
+      if (key > p_lo) sc[j][0] = -INFINITY;
+      if (key + 1 > p_lo) sc[j][1] = -INFINITY;
+      if (key > p_hi) sc[j][2] = -INFINITY;
+      if (key + 1 > p_hi) sc[j][3] = -INFINITY;
+      mx_lo = fmaxf(mx_lo, fmaxf(sc[j][0], sc[j][1]));
+      mx_hi = fmaxf(mx_hi, fmaxf(sc[j][2], sc[j][3]));
+    }
+    mx_lo = fmaxf(mx_lo, __shfl_xor_sync(0xffffffffu, mx_lo, 1));
+    mx_lo = fmaxf(mx_lo, __shfl_xor_sync(0xffffffffu, mx_lo, 2));
+    mx_hi = fmaxf(mx_hi, __shfl_xor_sync(0xffffffffu, mx_hi, 1));
+    mx_hi = fmaxf(mx_hi, __shfl_xor_sync(0xffffffffu, mx_hi, 2));
+    const float c_lo = (mx_lo == -INFINITY) ? 1.f : exp2f((m_lo - mx_lo) * sl2);
+    const float c_hi = (mx_hi == -INFINITY) ? 1.f : exp2f((m_hi - mx_hi) * sl2);
+    m_lo = mx_lo;
+    m_hi = mx_hi;
+    l_lo *= c_lo;
+    l_hi *= c_hi;
+#pragma unroll
+    for (int j = 0; j < 8; ++j) { o[j][0] *= c_lo; o[j][1] *= c_lo; o[j][2] *= c_hi; o[j][3] *= c_hi; }
+    const float ms_lo = (mx_lo == -INFINITY) ? 0.f : mx_lo * sl2, ms_hi = (mx_hi == -INFINITY) ? 0.f : mx_hi * sl2;
+    uint32_t pa[4][4];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      const float p0 = exp2f(sc[j][0] * sl2 - ms_lo), p1 = exp2f(sc[j][1] * sl2 - ms_lo);
+      const float p2 = exp2f(sc[j][2] * sl2 - ms_hi), p3 = exp2f(sc[j][3] * sl2 - ms_hi);
+      l_lo += p0 + p1;
+      l_hi += p2 + p3;
+      const int kk = j >> 1;
+      if ((j & 1) == 0) { pa[kk][0] = pack_bf16(p0, p1); pa[kk][1] = pack_bf16(p2, p3); }
+      else { pa[kk][2] = pack_bf16(p0, p1); pa[kk][3] = pack_bf16(p2, p3); }
+    }
+#pragma unroll
+    for (int kk = 0; kk < 4; ++kk) {
+#pragma unroll
+      for (int jd = 0; jd < 8; ++jd) {
+        uint32_t b0r, b1r;
+        ldmatrix_x2_trans(b0r, b1r, sV + (16 * kk + (lane & 15)) * LDS + 8 * jd);
+        mma16816(o[jd], pa[kk], b0r, b1r);
+      }
+    }
+  }
+  l_lo += __shfl_xor_sync(0xffffffffu, l_lo, 1);
+  l_lo += __shfl_xor_sync(0xffffffffu, l_lo, 2);
+  l_hi += __shfl_xor_sync(0xffffffffu, l_hi, 1);
+  l_hi += __shfl_xor_sync(0xffffffffu, l_hi, 2);
+  const float i_lo = 1.f / l_lo, i_hi = 1.f / l_hi;
+  bf16* olo = out + ((size_t)bl * S + r_lo) * (heads * HD) + head * HD;
+  bf16* ohi = out + ((size_t)bl * S + r_hi) * (heads * HD) + head * HD;
+#pragma unroll
+  for (int jd = 0; jd < 8; ++jd) {
+    const int col = 8 * jd + 2 * t;
+    if (r_lo < S) *reinterpret_cast<uint32_t*>(olo + col) = pack_bf16(o[jd][0] * i_lo, o[jd][1] * i_lo);
+    if (r_hi < S) *reinterpret_cast<uint32_t*>(ohi + col) = pack_bf16(o[jd][2] * i_hi, o[jd][3] * i_hi);
+  }
+}
+
+// ---------------------------------------------------------------- host launchers
+extern "C" {
+
+cudaError_t csm_embed_sum_launch(const long long* ids, const int* mask, int default_mask, const bf16* audio_emb,
+                                 const bf16* text_emb, int V, int H, bf16* out, int rows, cudaStream_t st) {
+  if (rows <= 0) return cudaSuccess;
+  csm_embed_sum_kernel<<<rows, 256, 0, st>>>(ids, mask, default_mask, audio_emb, text_emb, V, H, out, rows);
+  return cudaGetLastError();
+}
+cudaError_t csm_rmsnorm_rows_launch(const bf16* x, const bf16* w, float eps, int H, bf16* y, int rows, cudaStream_t st) {
+  csm_rmsnorm_rows_kernel<<<(rows + 7) / 8, 256, 0, st>>>(x, w, eps, H, y, rows);
+  return cudaGetLastError();
+}
+cudaError_t csm_rope_kv_rows_launch(bf16* qkv, int S, int pos0, int b0, int heads, int kv, int hd, const bf16* cos_t,
+                                    const bf16* sin_t, bf16* kc, bf16* vc, int layer, int Bmax, int Tcap, int rows,
+                                    cudaStream_t st) {
+  csm_rope_kv_rows_kernel<<<rows, 256, 0, st>>>(qkv, S, pos0, b0, heads, kv, hd, cos_t, sin_t, kc, vc, layer, Bmax, Tcap,
+                                                rows);
+  return cudaGetLastError();
+}
+cudaError_t csm_swiglu_rows_launch(const bf16* gu, int I, bf16* act, long long rows, cudaStream_t st) {
+  long long n2 = rows * (I / 2);
+  long long blocks = (n2 + 255) / 256;
+  if (blocks > 148 * 32) blocks = 148 * 32;
+  csm_swiglu_rows_kernel<<<(int)blocks, 256, 0, st>>>(gu, I, act, n2);
+  return cudaGetLastError();
+}
+cudaError_t csm_add_rows_launch(bf16* h, const bf16* y, long long n, cudaStream_t st) {
+  long long n2 = n / 2;
+  long long blocks = (n2 + 255) / 256;
+  if (blocks > 148 * 32) blocks = 148 * 32;
+  csm_add_rows_kernel<<<(int)blocks, 256, 0, st>>>(h, y, n2);
+  return cudaGetLastError();
+}
+cudaError_t csm_take_last_rows_launch(const bf16* h, int S, int H, bf16* dst, int b0, int nseq, cudaStream_t st) {
+  csm_take_last_rows_kernel<<<nseq, 256, 0, st>>>(h, S, H, dst, b0);
+  return cudaGetLastError();
+}
+cudaError_t csm_i64_to_i32_launch(const long long* src, int* dst, int n, cudaStream_t st) {
+  csm_i64_to_i32_kernel<<<(n + 255) / 256, 256, 0, st>>>(src, dst, n);
+  return cudaGetLastError();
+}
+cudaError_t csm_i32_to_i64_launch(const int* src, long long* dst, int n, cudaStream_t st) {
+  csm_i32_to_i64_kernel<<<(n + 255) / 256, 256, 0, st>>>(src, dst, n);
+  return cudaGetLastError();
+}
+cudaError_t csm_flash_prefill_launch(const bf16* qkv, int S, int pos0, int b0, int nseq, int heads, int kv,
+                                     const bf16* kc, const bf16* vc, int layer, int Bmax, int Tcap, float scale,
+                                     bf16* out, cudaStream_t st) {
+  dim3 grid((S + 63) / 64, heads, nseq);
+  csm_flash_prefill_kernel<<<grid, 128, 0, st>>>(qkv, S, pos0, b0, heads, kv, kc, vc, layer, Bmax, Tcap, scale, out);
+  return cudaGetLastError();
+}
+
+}  // extern "C"

@@ -1,0 +1,153 @@
+/*
+ * csm_b200.h -- C ABI of libcsm_b200.so, the B200 (sm_100a) engine behind the reference's
+ * CSMModel Python API.
+ *
+ * The reference (thomasgauthier/csm-hf) has no FFI: its boundary is the Python class
+ * CSMModel in modeling_csm.py.  Each entry point below replaces one arrow of that
+ * class's call graph; the Python mirror in
+ * csm_hf_b200/modeling.py binds them with ctypes (INTEGRATION.md shows the stub a
+ * maintainer of the reference would add).
+ *
+ * Conventions
+ *   - plain pointers and sizes only; no torch / C++ types; no exceptions cross the ABI;
+ *   - return 0 on success, a negative CSM_E* code on failure; csm_last_error() gives text;
+ *   - unless the name ends in _host, every data pointer is a DEVICE pointer and all
+ *     work is enqueued on the caller's `stream` (a cudaStream_t passed as void*);
+ *     nothing synchronises the device except csm_generate_host and csm_frames_done;
+ *   - weights are bf16 in the reference state_dict layouts ([out,in] row-major for every
+ *     nn.Linear, audio_head [31, in, out]); the engine packs private copies at create
+ *     time, the caller may free its tensors afterwards;
+ *   - one CsmCtx per device, not thread-safe (the reference is single-threaded Python).
+ */
+#ifndef CSM_B200_H
+#define CSM_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct CsmCtx CsmCtx;
+
+enum {
+  CSM_OK = 0,
+  CSM_EINVAL = -1,      /* bad argument / unsupported shape (maps to ValueError)   */
+  CSM_ECUDA = -2,       /* CUDA runtime error                                       */
+  CSM_ECAPACITY = -3,   /* batch > max_batch or context > max_ctx                   */
+  CSM_EUNSUPPORTED = -4 /* feature of the reference not on the accelerated path     */
+};
+
+/* One Llama stack: LlamaConfig fields read by the path (modeling_csm.py:68-109). */
+typedef struct {
+  int32_t hidden;       /* hidden_size                */
+  int32_t inter;        /* intermediate_size          */
+  int32_t layers;       /* num_hidden_layers          */
+  int32_t heads;        /* num_attention_heads        */
+  int32_t kv_heads;     /* num_key_value_heads        */
+  float eps;            /* rms_norm_eps               */
+  /* HOST pointers, bf16 bits, [n_pos][head_dim/2]: cos/sin of inv_freq*pos rounded to bf16
+   * exactly as LlamaRotaryEmbedding.forward does (hf modeling_llama.py:122-135). */
+  const uint16_t* rope_cos;
+  const uint16_t* rope_sin;
+  int32_t n_pos;
+} CsmLlamaShape;
+
+typedef struct {
+  int32_t text_vocab;   /* CSMConfig.text_vocab_size      (modeling_csm.py:64) */
+  int32_t audio_vocab;  /* CSMConfig.audio_vocab_size     (:65)                */
+  int32_t n_codebooks;  /* CSMConfig.audio_num_codebooks  (:66), must be 32    */
+  CsmLlamaShape backbone;
+  CsmLlamaShape decoder;
+} CsmShapes;
+
+/* Per-layer tensors in this order (state_dict key suffixes). */
+enum { CSM_W_Q = 0, CSM_W_K, CSM_W_V, CSM_W_O, CSM_W_GATE, CSM_W_UP, CSM_W_DOWN, CSM_W_LN1, CSM_W_LN2, CSM_W_PER_LAYER };
+
+typedef struct {
+  const void* text_embeddings;   /* [text_vocab, Hb]                (modeling_csm.py:222) */
+  const void* audio_embeddings;  /* [audio_vocab*32, Hb]            (:223-225)            */
+  const void* projection;        /* [Hd, Hb]                        (:228)                */
+  const void* codebook0_head;    /* [audio_vocab, Hb]               (:231-233)            */
+  const void* audio_head;        /* [31, Hd, audio_vocab]           (:236-240)            */
+  const void* backbone_norm;     /* [Hb]                                                  */
+  const void* decoder_norm;      /* [Hd]                                                  */
+  const void* const* backbone_layers; /* HOST array [layers*CSM_W_PER_LAYER] of device ptrs */
+  const void* const* decoder_layers;  /* HOST array [layers*CSM_W_PER_LAYER] of device ptrs */
+} CsmWeights;
+
+/* CSMModel.__init__ + from_pretrained (modeling_csm.py:214-245): pack weights, size the
+ * backbone KV cache for max_batch x max_ctx positions. */
+int csm_create(const CsmShapes* shapes, const CsmWeights* weights, int max_batch, int max_ctx,
+               void* stream, CsmCtx** out);
+int csm_destroy(CsmCtx* ctx);
+
+/* CSMModel.reset_caches (modeling_csm.py:288-290): forget the cached context. */
+int csm_reset(CsmCtx* ctx);
+/* Number of backbone positions currently cached (== DynamicCache.get_seq_length()). */
+int csm_cache_len(const CsmCtx* ctx);
+
+/* _embed_tokens + mask multiply + sum over the 33 slots (modeling_csm.py:261-282,327-334).
+ * ids int64 [B,S,33]; mask int32 [B,S,33] or NULL (= all ones); out bf16 [B,S,Hb]. */
+int csm_embed_sum(CsmCtx* ctx, const int64_t* ids, const int32_t* mask, int B, int S,
+                  void* out_bf16, void* stream);
+
+/* CSMModel.generate_frame (modeling_csm.py:484-589) at temperature 0 (reference:
+ * topk=1, ties -> lowest index).  S == cached-context continuation: S > 1 is the
+ * prefill call (causal), S == 1 a decode step attending to every cached position.
+ *   ids int64 [B,S,33], mask int32 [B,S,33] (NULL = audio columns set, text clear)
+ *   force_tokens int64 [B,32] or NULL: teacher forcing -- the decoder is fed these
+ *       tokens instead of its own argmax (samples still report the argmax)
+ *   samples int64 [B,32]; last_h bf16 [B,Hb]; c0_logits bf16 [B,V];
+ *   cb_logits bf16 [B,31,V] (logits given to the sampler for codebooks 1..31); any
+ *   output may be NULL. */
+int csm_generate_frame(CsmCtx* ctx, const int64_t* ids, const int32_t* mask, int B, int S,
+                       const int64_t* force_tokens, int64_t* samples, void* last_h,
+                       void* c0_logits, void* cb_logits, void* stream);
+
+/* CSMModel.generate (modeling_csm.py:591-702), use_cache=True, temperature 0.
+ * Resets the cache, prefills T context frames, emits up to max_new_frames frames into
+ * frames int64 [B,max_new_frames,32].  Asynchronous: the number of frames kept
+ * (stop_on_all_zeros, :662-663) is read back with csm_frames_done. */
+int csm_generate(CsmCtx* ctx, const int64_t* ids, const int32_t* mask, int B, int T,
+                 int max_new_frames, int stop_on_all_zeros, int64_t* frames, void* stream);
+/* Synchronises `stream` and returns the frame count of the last csm_generate (<0: error). */
+int csm_frames_done(CsmCtx* ctx, void* stream);
+
+/* Same as csm_generate with HOST buffers: copies ids/mask in, frames out, synchronises,
+ * stores the frame count in *n_out.  This is the end-to-end call bench.py times. */
+int csm_generate_host(CsmCtx* ctx, const int64_t* ids_host, const int32_t* mask_host, int B, int T,
+                      int max_new_frames, int stop_on_all_zeros, int64_t* frames_host, int* n_out,
+                      void* stream);
+
+/* Introspection used by tests and bench.py. */
+enum { CSM_INFO_SMS = 0, CSM_INFO_GRID, CSM_INFO_PHASES_PER_FRAME, CSM_INFO_SMEM_BYTES,
+       CSM_INFO_LAUNCHES, CSM_INFO_STEPPED };
+int64_t csm_info(const CsmCtx* ctx, int what);
+/* stepped != 0: launch one kernel per phase instead of one persistent launch per frame
+ * (debug/bisect aid; results are identical). */
+int csm_set_stepped(CsmCtx* ctx, int stepped);
+/* Device time of the decode-frame launches of the last csm_generate, in ms, measured
+ * with CUDA events on `stream` (synchronises); *n = launches covered. */
+int csm_last_decode_ms(CsmCtx* ctx, float* ms, int* n);
+
+const char* csm_last_error(const CsmCtx* ctx);
+
+/* ---- debug / test hooks: not part of the drop-in surface ------------------------------------
+ * csm_debug_copy: device-to-device copy of an internal buffer (0 h_bb, 1 h_dec, 2 q_bb, 3 q_dec,
+ *   4 attn_bb, 5 attn_dec, 6 mlp_bb, 7 mlp_dec, 8 last_h, 9 c0_logits, 10 cb_logits, 11 samples(i32),
+ *   12 fed(i32), 13/14 backbone K/V cache, 15/16 decoder K/V cache); dst NULL = size query.
+ * csm_debug_run_phases: execute phases [begin,end) of the frame program at the current cache
+ *   length without advancing it (bisecting a frame against the oracle).                        */
+int csm_debug_copy(CsmCtx* ctx, int which, void* dst_device, int64_t max_bytes, int64_t* bytes_out, void* stream);
+int csm_debug_run_phases(CsmCtx* ctx, const int64_t* ids, const int32_t* mask, int B, int ph_begin, int ph_end,
+                         int forced, void* stream);
+int csm_debug_set_cache_len(CsmCtx* ctx, int len);
+/* One decode frame with per-phase clock64 stamps of CTA 0: clocks_host[2*phases] (start,end),
+ * info_host[4*phases] = (type, epilogue, stack, act_mode) per phase. Synchronises. */
+int csm_debug_profile_frame(CsmCtx* ctx, int B, uint64_t* clocks_host, int32_t* info_host, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* CSM_B200_H */
