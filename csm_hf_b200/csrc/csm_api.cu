@@ -75,8 +75,8 @@ struct CsmCtx {
   bf16 *mlp_bb = nullptr, *mlp_dec = nullptr, *last_h = nullptr, *c0_logits = nullptr, *cb_logits = nullptr;
   float* attn_part = nullptr;
   int nsplit_max = 0;
-  unsigned int *attn_cnt = nullptr, *head_cnt = nullptr, *bar_counter = nullptr;
-  float2* head_part = nullptr;
+  unsigned int *attn_cnt = nullptr, *bar_counter = nullptr;
+  float2* cand = nullptr;
   int *samples = nullptr, *fed = nullptr, *stop_flag = nullptr, *n_frames = nullptr;
   unsigned long long* prof = nullptr;
   int prof_on = 0;
@@ -95,6 +95,9 @@ struct CsmCtx {
   int ph_head_c0 = 0;   // first phase of the "decoder part" of a frame (final norm + c0 head)
   int cache_len = 0;
   int stepped = 0;
+  // shared-memory plan of the frame kernel (fixed at create time for max_batch)
+  int m_alloc = 0, slot_bytes = 0, n_slots = 0, rope_bytes = 0, act_region = 0, red_bytes = 0, stream_tpc_max = 0;
+  size_t smem_total = 0;
   long long launches = 0;
   cublasHandle_t cublas = nullptr;
   cudaEvent_t ev0 = nullptr, ev1 = nullptr;
@@ -159,9 +162,9 @@ int pack_matrix(CsmCtx* ctx, bf16** dst, const PackSrc& src, const std::vector<i
   }
   // every CTA may own at most CSM_MAX_NT*8 rows of a matrix
   int U = N / gran, per = (U + ctx->G - 1) / ctx->G * gran;
-  if (per > CSM_MAX_NT * 8)
+  if (per > CSM_MAX_ROWS)
     return fail(ctx, CSM_EINVAL, "matrix with %d rows needs %d rows per CTA on a %d-CTA grid (max %d)", N, per, ctx->G,
-                CSM_MAX_NT * 8);
+                CSM_MAX_ROWS);
   return 0;
 }
 
@@ -298,44 +301,79 @@ void build_table(CsmCtx* ctx) {
       ctx->table.push_back(P);
     }
   }
+  // sample codebook 31, publish the frame, stop rule (modeling_csm.py:657-666)
+  memset(&P, 0, sizeof P);
+  P.type = PH_FINISH;
+  ctx->table.push_back(P);
 }
 
-struct SmemPlan {
-  int m_alloc, slot_bytes, n_slots, act_region, red_bytes, stream_tpc_max;
-  size_t total;
-};
-
-int plan_smem(CsmCtx* ctx, int B, SmemPlan* sp) {
+// Shared-memory plan of the frame kernel for max_batch sequences, and the per-phase row split /
+// ring chunking that depends on it (Phase::q, r, tpc, nch).
+int plan_smem(CsmCtx* ctx) {
+  const int G = ctx->G;
   const int kfull = ctx->bb.d.H > ctx->dec.d.H ? ctx->bb.d.H : ctx->dec.d.H;
-  sp->m_alloc = (B + 7) / 8 * 8;
-  sp->red_bytes = 512 * sp->m_alloc;
-  if (sp->red_bytes < 9216) sp->red_bytes = 9216;
-  sp->act_region = sp->m_alloc * (kfull + 8) * 2;
-  sp->act_region = (sp->act_region + 255) / 256 * 256;
+  ctx->m_alloc = (ctx->Bmax + 7) / 8 * 8;
+  ctx->rope_bytes = (2 * CSM_DEC_POS * (ctx->dec.d.hd / 2) + 2 * (ctx->bb.d.hd / 2)) * 2;
+  ctx->rope_bytes = (ctx->rope_bytes + 255) / 256 * 256;
+  // split-K partial sums: red[ks][m_alloc][mtiles*16+4] floats; attention scratch needs 9216 bytes
+  int red = 9216;
+  for (Phase& P : ctx->table) {
+    if (P.type != PH_GEMV) continue;
+    const int U = P.N / P.gran;
+    P.q = U / G;
+    P.r = U % G;
+    for (int hi = 0; hi < 2; ++hi) {
+      const int rows = (P.q + (hi ? 1 : 0)) * P.gran;
+      if (rows == 0 || (hi && P.r == 0)) continue;
+      const int mt = (rows + 15) / 16;
+      const int ns = mt >= 5 ? 8 : (mt >= 3 ? 4 : (mt >= 2 ? 2 : 1));
+      const int need = (8 / ns) * ctx->m_alloc * (mt * 16 + 4) * 4;
+      if (need > red) red = need;
+    }
+  }
+  ctx->red_bytes = (red + 255) / 256 * 256;
+  ctx->act_region = ctx->m_alloc * (kfull + 8) * 2;
+  ctx->act_region = (ctx->act_region + 255) / 256 * 256;
   const int limit = 227 * 1024;
-  int avail = limit - 256 - sp->red_bytes - sp->act_region;
+  const int avail = limit - CSM_SM_HDR_BYTES - ctx->rope_bytes - ctx->red_bytes - ctx->act_region;
   int slot = 32 * 1024;
   while (slot > 4096 && avail / slot < 3) slot /= 2;
-  if (avail / slot < 2) return fail(ctx, CSM_ECAPACITY, "batch %d leaves no shared memory for the weight ring", B);
-  sp->slot_bytes = slot;
-  sp->n_slots = avail / slot;
-  if (sp->n_slots > CSM_MAX_SLOTS) sp->n_slots = CSM_MAX_SLOTS;
+  if (avail / slot < 2) return fail(ctx, CSM_ECAPACITY, "batch %d leaves no shared memory for the weight ring", ctx->Bmax);
+  ctx->slot_bytes = slot;
+  ctx->n_slots = avail / slot;
+  if (ctx->n_slots > CSM_MAX_SLOTS) ctx->n_slots = CSM_MAX_SLOTS;
   const char* e = getenv("CSM_RING_SLOTS");
-  if (e && atoi(e) >= 2 && atoi(e) <= sp->n_slots) sp->n_slots = atoi(e);
+  if (e && atoi(e) >= 2 && atoi(e) <= ctx->n_slots) ctx->n_slots = atoi(e);
   // activation-stream chunk: two slots of [m_alloc][tpc*16+8] bf16 inside the activation region
-  int per_row = (sp->act_region / 2) / (sp->m_alloc * 2);
-  sp->stream_tpc_max = (per_row - 8) / 16;
-  if (sp->stream_tpc_max < 1) return fail(ctx, CSM_ECAPACITY, "activation region too small");
-  sp->total = 256 + (size_t)sp->red_bytes + sp->act_region + (size_t)sp->slot_bytes * sp->n_slots;
+  const int per_row = (ctx->act_region / 2) / (ctx->m_alloc * 2);
+  ctx->stream_tpc_max = (per_row - 8) / 16;
+  if (ctx->stream_tpc_max < 1) return fail(ctx, CSM_ECAPACITY, "activation region too small");
+  ctx->smem_total = (size_t)CSM_SM_HDR_BYTES + ctx->rope_bytes + ctx->red_bytes + ctx->act_region +
+                    (size_t)ctx->slot_bytes * ctx->n_slots;
+  for (Phase& P : ctx->table) {
+    if (P.type != PH_GEMV) continue;
+    const int ntiles = P.K / 16;
+    for (int hi = 0; hi < 2; ++hi) {
+      const int rows = (P.q + (hi ? 0 : 1)) * P.gran;   // index 0 = larger share
+      int tpc = 0, nch = 0;
+      if (rows > 0) {
+        tpc = ctx->slot_bytes / (rows * 32);
+        if (tpc > ntiles) tpc = ntiles;
+        if (P.act_mode == ACT_STREAM && tpc > ctx->stream_tpc_max) tpc = ctx->stream_tpc_max;
+        if (tpc >= 8) tpc &= ~7;   // the 8 warps split a chunk's k-tiles evenly
+        if (tpc < 1) tpc = 1;
+        nch = (ntiles + tpc - 1) / tpc;
+      }
+      P.tpc[hi] = tpc;
+      P.nch[hi] = nch;
+    }
+  }
   return 0;
 }
 
 int launch_frame(CsmCtx* ctx, int B, int ph_begin, int ph_end, const long long* ids, const int* mask, int forced,
                  long long* out_frames, long long out_stride, long long out_off, int stop_on_zeros, int pos,
                  cudaStream_t st) {
-  SmemPlan sp;
-  int r = plan_smem(ctx, B, &sp);
-  if (r) return r;
   StreamParams p;
   memset(&p, 0, sizeof p);
   p.phases = ctx->d_table;
@@ -346,25 +384,25 @@ int launch_frame(CsmCtx* ctx, int B, int ph_begin, int ph_end, const long long* 
   p.cos_bb = ctx->bb.cos_t; p.sin_bb = ctx->bb.sin_t; p.cos_dec = ctx->dec.cos_t; p.sin_dec = ctx->dec.sin_t;
   p.q_bb = ctx->q_bb; p.q_dec = ctx->q_dec; p.attn_bb = ctx->attn_bb; p.attn_dec = ctx->attn_dec;
   p.attn_part = ctx->attn_part; p.nsplit_max = ctx->nsplit_max; p.attn_cnt = ctx->attn_cnt;
-  p.head_part = ctx->head_part; p.head_cnt = ctx->head_cnt;
+  p.cand = ctx->cand;
   p.samples = ctx->samples; p.fed = ctx->fed; p.forced = forced;
   p.ids = ids; p.mask = mask; p.text_emb = ctx->text_emb; p.audio_emb = ctx->audio_emb;
   p.h_bb = ctx->h_bb;
   p.out_frames = out_frames; p.out_stride = out_stride; p.out_off = out_off;
   p.stop_flag = ctx->stop_flag; p.n_frames = ctx->n_frames; p.stop_on_zeros = stop_on_zeros;
-  p.m_alloc = sp.m_alloc; p.slot_bytes = sp.slot_bytes; p.n_slots = sp.n_slots;
-  p.act_region_bytes = sp.act_region; p.red_bytes = sp.red_bytes; p.stream_tpc_max = sp.stream_tpc_max;
+  p.m_alloc = ctx->m_alloc; p.slot_bytes = ctx->slot_bytes; p.n_slots = ctx->n_slots;
+  p.rope_bytes = ctx->rope_bytes; p.act_region_bytes = ctx->act_region; p.red_bytes = ctx->red_bytes;
   p.prof = ctx->prof_on ? ctx->prof : nullptr;
   if (!ctx->stepped) {
     p.phase_begin = ph_begin; p.phase_end = ph_end; p.use_barrier = 1;
     CK(cudaMemsetAsync(ctx->bar_counter, 0, sizeof(unsigned int), st));
-    CK(csm_launch_stream(&p, ctx->G, sp.total, st, 1));
+    CK(csm_launch_stream(&p, ctx->G, ctx->smem_total, st, 1));
     ctx->launches += 1;
   } else {
     p.use_barrier = 0;
     for (int ph = ph_begin; ph < ph_end; ++ph) {
       p.phase_begin = ph; p.phase_end = ph + 1;
-      CK(csm_launch_stream(&p, ctx->G, sp.total, st, 0));
+      CK(csm_launch_stream(&p, ctx->G, ctx->smem_total, st, 0));
       ctx->launches += 1;
     }
   }
@@ -543,27 +581,25 @@ int csm_create(const CsmShapes* sh, const CsmWeights* w, int max_batch, int max_
   ctx->nsplit_max = (max_ctx + CSM_ATT_SPLIT - 1) / CSM_ATT_SPLIT;
   DA(ctx->attn_part, B * b.heads * ctx->nsplit_max * (b.hd + 2));
   DA(ctx->attn_cnt, B * b.kv);
-  DA(ctx->head_cnt, 4); DA(ctx->bar_counter, 4);
-  DA(ctx->head_part, (size_t)ctx->sms * B);
+  DA(ctx->bar_counter, 4);
+  DA(ctx->cand, (size_t)ctx->sms * B);
   DA(ctx->samples, B * CSM_NQ); DA(ctx->fed, B * CSM_NQ);
   DA(ctx->stop_flag, 4); DA(ctx->n_frames, 4);
   CK(cudaMemsetAsync(ctx->attn_cnt, 0, B * b.kv * sizeof(unsigned), st));
-  CK(cudaMemsetAsync(ctx->head_cnt, 0, 16, st));
+  CK(cudaMemsetAsync(ctx->cand, 0, (size_t)ctx->sms * B * sizeof(float2), st));
   CK(cudaMemsetAsync(ctx->bar_counter, 0, 16, st));
   CK(cudaMemsetAsync(ctx->stop_flag, 0, 16, st));
   CK(cudaMemsetAsync(ctx->n_frames, 0, 16, st));
   CK(cudaMemsetAsync(ctx->samples, 0, B * CSM_NQ * sizeof(int), st));
   CK(cudaMemsetAsync(ctx->fed, 0, B * CSM_NQ * sizeof(int), st));
   build_table(ctx);
+  if ((r = plan_smem(ctx))) return r;
   DA(ctx->d_table, ctx->table.size());
   DA(ctx->prof, 2 * ctx->table.size());
   CK(cudaMemcpyAsync(ctx->d_table, ctx->table.data(), ctx->table.size() * sizeof(Phase), cudaMemcpyHostToDevice, st));
   if (cublasCreate(&ctx->cublas) != CUBLAS_STATUS_SUCCESS) return fail(ctx, CSM_ECUDA, "cublasCreate failed");
   CK(cudaEventCreate(&ctx->ev0));
   CK(cudaEventCreate(&ctx->ev1));
-  // the persistent kernel needs every CTA resident: check the cooperative-launch limit once
-  SmemPlan sp;
-  if ((r = plan_smem(ctx, max_batch, &sp))) return r;
   CK(cudaStreamSynchronize(st));
   return CSM_OK;
 }
@@ -693,12 +729,7 @@ int64_t csm_info(const CsmCtx* ctx, int what) {
     case CSM_INFO_SMS: return ctx->sms;
     case CSM_INFO_GRID: return ctx->G;
     case CSM_INFO_PHASES_PER_FRAME: return (int64_t)ctx->table.size();
-    case CSM_INFO_SMEM_BYTES: {
-      SmemPlan sp;
-      CsmCtx* c = const_cast<CsmCtx*>(ctx);
-      if (plan_smem(c, ctx->Bmax, &sp)) return -1;
-      return (int64_t)sp.total;
-    }
+    case CSM_INFO_SMEM_BYTES: return (int64_t)ctx->smem_total;
     case CSM_INFO_LAUNCHES: return ctx->launches;
     case CSM_INFO_STEPPED: return ctx->stepped;
   }

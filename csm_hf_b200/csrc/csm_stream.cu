@@ -16,18 +16,28 @@
 //               fit in shared memory: bulk-copies [B, k-chunk] tiles after the barrier.
 //
 // Work split of a matrix W[N,K]: rows are divided evenly over the CTAs (granule 1 or 2 rows);
-// csm_pack.cu stores each CTA's rows contiguously, k16-tile major, in mma B-fragment order, so
-// one bulk copy brings a chunk and one conflict-free LDS.64 per lane feeds an
-// mma.sync.m16n8k16 (activations = A operand: batch rows x k; weights = B operand: k x 8 rows).
+// csm_pack.cu stores each CTA's rows contiguously, k16-tile major, 32 bytes per (tile,row) in
+// mma fragment order.  The WEIGHTS are the 16-row A operand of mma.sync.m16n8k16 (two
+// conflict-free LDS.64 per lane), the batch rows of the activations the 8-column B operand, so a
+// batch of 1..8 sequences costs one MMA per 256 weights and nothing is wasted on padding.
+//
+// Latency rules this file follows (the path is a chain of ~700 dependent phases per frame):
+//   * phase descriptors are prefetched into shared memory one phase ahead;
+//   * every cross-CTA read is issued as one batch of independent loads (one L2 round trip);
+//   * all 8 compute warps take part in activation staging, also for a single sequence;
+//   * greedy sampling needs no extra synchronisation: every CTA publishes its best (logit, id)
+//     with the head phase's normal barrier and the consumers reduce the 148 candidates themselves.
 #include "csm_common.cuh"
 
 namespace {
 
-constexpr int SM_BAR_BYTES = 256;
-
 struct Ctx {
   uint64_t *full, *empty, *afull, *aempty;
   volatile int* sflag;   // [0] last-arriver flag, [1] scratch
+  Phase* desc;           // [2] descriptor slots
+  float* scratch;        // 256 floats
+  int* tok;              // [32] tokens gathered by this phase
+  bf16* rope;            // cos_dec | sin_dec ([32][hd/2] each) | cos_bb[pos] | sin_bb[pos]
   float* red;
   unsigned char* actreg;
   unsigned char* ring;
@@ -39,110 +49,32 @@ __device__ __forceinline__ void grid_wait(const unsigned int* counter, unsigned 
   }
 }
 
-// ------------------------------------------------------------------ activation staging
-// Rows of the phase input -> shared memory [M][K+8] bf16, applying RMSNorm exactly as
-// LlamaRMSNorm.forward (hf modeling_llama.py:62-67): fp32 x*rsqrt(mean(x^2)+eps) -> bf16 -> *w -> bf16.
-__device__ __forceinline__ void stage_act(const StreamParams& p, const Phase& P, const Ctx& cx, int astride) {
-  const int K = P.K, M = p.B;
-  const float eps = P.stack ? p.dec.eps : p.bb.eps;
-  bf16* dst = reinterpret_cast<bf16*>(cx.actreg);
-  for (int m = cx.warp; m < M; m += CSM_COMPUTE_WARPS) {
-    const bf16* src;
-    if (P.act_mode == ACT_GATHER) {
-      // _embed_audio (modeling_csm.py:247-259): row tok + codebook*V of the shared audio table
-      int tok = ldcg_i32(p.fed + m * CSM_NQ + P.cb);
-      src = P.act + (size_t)(tok + P.cb * p.V) * K;
-    } else {
-      src = P.act + (size_t)m * P.act_stride;
-    }
-    uint4 v[8];
-    float ss = 0.f;
-#pragma unroll
-    for (int i = 0; i < 8; ++i) {
-      int idx = (i * 32 + cx.lane) * 8;
-      if (idx < K) {
-        v[i] = ldcg_u4(src + idx);
-        const uint32_t* u = reinterpret_cast<const uint32_t*>(&v[i]);
-#pragma unroll
-        for (int q = 0; q < 4; ++q) {
-          float a = bf_lo(u[q]), b = bf_hi(u[q]);
-          ss += a * a + b * b;
-        }
-      }
-    }
-    if (P.act_mode == ACT_NORM) {
-      ss = warp_sum(ss);
-      const float rstd = rsqrtf(ss / (float)K + eps);
-#pragma unroll
-      for (int i = 0; i < 8; ++i) {
-        int idx = (i * 32 + cx.lane) * 8;
-        if (idx < K) {
-          uint4 wv = __ldg(reinterpret_cast<const uint4*>(P.norm_w + idx));
-          const uint32_t* u = reinterpret_cast<const uint32_t*>(&v[i]);
-          const uint32_t* w = reinterpret_cast<const uint32_t*>(&wv);
-          uint4 o;
-          uint32_t* ou = reinterpret_cast<uint32_t*>(&o);
-#pragma unroll
-          for (int q = 0; q < 4; ++q) {
-            float y0 = bfround(bf_lo(u[q]) * rstd), y1 = bfround(bf_hi(u[q]) * rstd);
-            ou[q] = pack_bf16(bf_lo(w[q]) * y0, bf_hi(w[q]) * y1);
-          }
-          *reinterpret_cast<uint4*>(dst + (size_t)m * astride + idx) = o;
-          if (P.norm_out != nullptr && (m % cx.G) == cx.c)
-            *reinterpret_cast<uint4*>(P.norm_out + (size_t)m * K + idx) = o;
-        }
-      }
-    } else {
-#pragma unroll
-      for (int i = 0; i < 8; ++i) {
-        int idx = (i * 32 + cx.lane) * 8;
-        if (idx < K) *reinterpret_cast<uint4*>(dst + (size_t)m * astride + idx) = v[i];
-      }
-    }
-  }
-}
-
-// ------------------------------------------------------------------ head argmax (greedy sampling)
-// sample_topk at topk=1 (modeling_csm.py:179-189) with the canonical lowest-index tie-break.
-// Every CTA publishes the best (value, index) of its rows; the last CTA to arrive reduces them.
 __device__ __forceinline__ bool better(float v, int i, float bv, int bi) { return v > bv || (v == bv && i < bi); }
 
-__device__ __forceinline__ void head_finish(const StreamParams& p, const Phase& P, const Ctx& cx, const Geom& g,
-                                            int rows_pad) {
+// ------------------------------------------------------------------ greedy sample of a finished head phase
+// sample_topk at topk=1 (modeling_csm.py:179-189) with the canonical lowest-index tie-break: reduce
+// the (best logit, id) candidates every CTA published in the head phase for codebook `cb`.
+// Result in cx.tok[m]; CTA 0 also records samples / fed.  Ends with a compute_sync.
+__device__ __forceinline__ void reduce_candidates(const StreamParams& p, const Ctx& cx, int cb) {
   const int M = p.B;
   for (int m = cx.warp; m < M; m += CSM_COMPUTE_WARPS) {
     float best = -INFINITY;
     int bi = 0x7fffffff;
-    for (int n = cx.lane; n < g.rows; n += 32) {
-      float v = cx.red[(size_t)m * rows_pad + n];
-      if (better(v, g.row0 + n, best, bi)) { best = v; bi = g.row0 + n; }
+    float2 pr[5];
+#pragma unroll
+    for (int j = 0; j < 5; ++j) {
+      const int cc = cx.lane + 32 * j;
+      pr[j] = cc < cx.G ? __ldcg(p.cand + (size_t)cc * p.Bmax + m) : make_float2(-INFINITY, __int_as_float(0x7fffffff));
     }
 #pragma unroll
-    for (int o = 16; o > 0; o >>= 1) {
-      float ov = __shfl_xor_sync(0xffffffffu, best, o);
-      int oi = __shfl_xor_sync(0xffffffffu, bi, o);
-      if (better(ov, oi, best, bi)) { best = ov; bi = oi; }
+    for (int j = 0; j < 5; ++j) {
+      const int oi = __float_as_int(pr[j].y);
+      if (better(pr[j].x, oi, best, bi)) { best = pr[j].x; bi = oi; }
     }
-    if (cx.lane == 0) p.head_part[(size_t)cx.c * p.Bmax + m] = make_float2(best, __int_as_float(bi));
-  }
-  compute_sync();
-  if (cx.tid == 0) {
-    __threadfence();
-    unsigned old = atomicAdd(p.head_cnt, 1u);
-    cx.sflag[0] = (old == (unsigned)cx.G - 1u);
-    cx.sflag[1] = 0;
-  }
-  compute_sync();
-  if (!cx.sflag[0]) return;
-  // ---- last CTA: reduce the per-CTA candidates
-  __threadfence();
-  for (int m = cx.warp; m < M; m += CSM_COMPUTE_WARPS) {
-    float best = -INFINITY;
-    int bi = 0x7fffffff;
-    for (int cc = cx.lane; cc < cx.G; cc += 32) {
-      float2 pr = __ldcg(p.head_part + (size_t)cc * p.Bmax + m);
-      int oi = __float_as_int(pr.y);
-      if (better(pr.x, oi, best, bi)) { best = pr.x; bi = oi; }
+    for (int cc = cx.lane + 160; cc < cx.G; cc += 32) {   // grids larger than 160 CTAs (not B200)
+      float2 q = __ldcg(p.cand + (size_t)cc * p.Bmax + m);
+      const int oi = __float_as_int(q.y);
+      if (better(q.x, oi, best, bi)) { best = q.x; bi = oi; }
     }
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) {
@@ -151,61 +83,174 @@ __device__ __forceinline__ void head_finish(const StreamParams& p, const Phase& 
       if (better(ov, oi, best, bi)) { best = ov; bi = oi; }
     }
     if (cx.lane == 0) {
-      p.samples[m * CSM_NQ + P.cb] = bi;
-      if (!p.forced) p.fed[m * CSM_NQ + P.cb] = bi;
+      int fedtok = bi;
+      if (p.forced) fedtok = ldcg_i32(p.fed + m * CSM_NQ + cb);
+      cx.tok[m] = fedtok;
+      if (cx.c == 0) {
+        p.samples[m * CSM_NQ + cb] = bi;
+        if (!p.forced) p.fed[m * CSM_NQ + cb] = bi;
+      }
     }
   }
-  if (cx.tid == 0) *p.head_cnt = 0u;
-  if (P.cb != CSM_NQ - 1) return;
-  // ---- frame complete: publish the 32 ids (modeling_csm.py:657-666), evaluate the stop rule (:662)
-  __threadfence();
   compute_sync();
-  int nz = 0;
-  for (int e = cx.tid; e < M * CSM_NQ; e += CSM_COMPUTE_THREADS) {
-    int tok = ldcg_i32(p.samples + e);
-    nz |= (tok != 0);
-    if (p.out_frames) {
-      int m = e / CSM_NQ, q = e % CSM_NQ;
-      p.out_frames[(size_t)m * p.out_stride + p.out_off + q] = (long long)tok;
+}
+
+// ------------------------------------------------------------------ activation staging
+// Rows of the phase input -> shared memory [M][K+8] bf16, applying RMSNorm exactly as
+// LlamaRMSNorm.forward (hf modeling_llama.py:62-67): fp32 x*rsqrt(mean(x^2)+eps) -> bf16 -> *w -> bf16.
+// A row is spread over K/8 threads (one 16-byte load each), 256*8/K rows per pass, so that even
+// a single sequence is loaded by all warps with one round trip to L2.
+__device__ __forceinline__ void stage_act(const StreamParams& p, const Phase& P, const Ctx& cx, int astride) {
+  const int K = P.K, M = p.B;
+  const float eps = P.stack ? p.dec.eps : p.bb.eps;
+  bf16* dst = reinterpret_cast<bf16*>(cx.actreg);
+  if (P.act_mode == ACT_GATHER) reduce_candidates(p, cx, P.cb);
+  const int tpr = K >> 3;                      // threads per row (K <= 2048 -> <= 256)
+  const int rpp = CSM_COMPUTE_THREADS / tpr;   // rows per pass
+  const int wpr = tpr >> 5;                    // warps per row (0 when a row is narrower than a warp)
+  const int rl = cx.tid / tpr, col = (cx.tid - rl * tpr) * 8;
+  uint4 wv = make_uint4(0, 0, 0, 0);
+  if (P.act_mode == ACT_NORM && rl < rpp) wv = __ldg(reinterpret_cast<const uint4*>(P.norm_w + col));
+  for (int m0 = 0; m0 < M; m0 += rpp) {
+    const int m = m0 + rl;
+    const bool on = rl < rpp && m < M;
+    uint4 v = make_uint4(0, 0, 0, 0);
+    if (on) {
+      const bf16* src;
+      if (P.act_mode == ACT_GATHER)   // _embed_audio (modeling_csm.py:247-259): row tok + codebook*V of the audio table
+        src = P.act + (size_t)(cx.tok[m] + P.cb * p.V) * K;
+      else
+        src = P.act + (size_t)m * P.act_stride;
+      v = ldcg_u4(src + col);
     }
-  }
-  if (nz) cx.sflag[1] = 1;
-  compute_sync();
-  if (cx.tid == 0) {
-    if (p.stop_on_zeros && !cx.sflag[1]) *p.stop_flag = 1;   // all-zero frame: not kept, generation ends
-    else if (p.n_frames) *p.n_frames += 1;
+    if (P.act_mode == ACT_NORM) {
+      const uint32_t* u = reinterpret_cast<const uint32_t*>(&v);
+      float ss = 0.f;
+#pragma unroll
+      for (int q = 0; q < 4; ++q) {
+        float a = bf_lo(u[q]), b = bf_hi(u[q]);
+        ss += a * a + b * b;
+      }
+      // reduce over the threads of the row: inside the warp, then across the row's warps
+      if (wpr == 0) {
+        for (int o = tpr >> 1; o > 0; o >>= 1) ss += __shfl_xor_sync(0xffffffffu, ss, o);
+      } else {
+        ss = warp_sum(ss);
+        if (wpr > 1) {
+          if (cx.lane == 0) cx.scratch[cx.warp] = ss;
+          compute_sync();
+          const int w0 = (cx.warp / wpr) * wpr;
+          ss = 0.f;
+          for (int w = 0; w < wpr; ++w) ss += cx.scratch[w0 + w];
+          compute_sync();
+        }
+      }
+      if (on) {
+        const float rstd = rsqrtf(ss / (float)K + eps);
+        const uint32_t* w = reinterpret_cast<const uint32_t*>(&wv);
+        uint4 o;
+        uint32_t* ou = reinterpret_cast<uint32_t*>(&o);
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+          float y0 = bfround(bf_lo(u[q]) * rstd), y1 = bfround(bf_hi(u[q]) * rstd);
+          ou[q] = pack_bf16(bf_lo(w[q]) * y0, bf_hi(w[q]) * y1);
+        }
+        *reinterpret_cast<uint4*>(dst + (size_t)m * astride + col) = o;
+        if (P.norm_out != nullptr && (m % cx.G) == cx.c) *reinterpret_cast<uint4*>(P.norm_out + (size_t)m * K + col) = o;
+      }
+    } else if (on) {
+      *reinterpret_cast<uint4*>(dst + (size_t)m * astride + col) = v;
+    }
   }
 }
 
-// ------------------------------------------------------------------ GEMV / skinny-GEMM phase
-__device__ __forceinline__ void gemv_phase(const StreamParams& p, const Phase& P, const Ctx& cx, uint32_t& it,
-                                           uint32_t& ait) {
-  const int M = p.B, K = P.K;
-  const bool stream = (P.act_mode == ACT_STREAM);
-  const Geom g = csm_geom(P.N, K, P.gran, cx.G, cx.c, p.slot_bytes, stream ? p.stream_tpc_max : 0x7fffffff);
-  const int mt = (p.m_alloc + 15) >> 4;
-  int astride;
-  if (!stream) {
-    astride = K + 8;
-    stage_act(p, P, cx, astride);
-    compute_sync();
+// ------------------------------------------------------------------ tensor-core inner loop
+// acc[j][nb] (+)= W[16 rows of m-tile j] x act[8 batch rows of n-tile nb] over this warp's k16-tiles of
+// one ring chunk.  SINGLE: the warp owns one m-tile; consecutive tiles alternate between the two
+// accumulator sets so that two independent MMA chains are in flight.
+template <int NB, bool SINGLE>
+__device__ __forceinline__ void mma_chunk(float (&acc)[2][NB][4], const unsigned char* wslot, const bf16* abase, int astride,
+                                          int acol0, int tiles, int tl0, int ks, int rows, int mt0, int mt1, int M, int gq,
+                                          int tq) {
+  // per-lane constant parts of the addresses
+  const int rA0 = 16 * mt0 + gq, rA1 = rA0 + 8;
+  const int rB0 = 16 * mt1 + gq, rB1 = rB0 + 8;
+  const bool vA0 = rA0 < rows, vA1 = rA1 < rows;
+  const bool vB0 = !SINGLE && mt1 >= 0 && rB0 < rows, vB1 = !SINGLE && mt1 >= 0 && rB1 < rows;
+  const unsigned char* wl = wslot + tq * 8;
+  const bf16* al = abase + acol0 + 2 * tq;
+  if (SINGLE) {
+    for (int tl = tl0; tl < tiles; tl += 2 * ks) {
+      const int tl2 = tl + ks;
+      const bool two = tl2 < tiles;
+      uint2 w0 = make_uint2(0, 0), w1 = make_uint2(0, 0), x0 = make_uint2(0, 0), x1 = make_uint2(0, 0);
+      if (vA0) w0 = *reinterpret_cast<const uint2*>(wl + ((size_t)tl * rows + rA0) * 32);
+      if (vA1) w1 = *reinterpret_cast<const uint2*>(wl + ((size_t)tl * rows + rA1) * 32);
+      if (two && vA0) x0 = *reinterpret_cast<const uint2*>(wl + ((size_t)tl2 * rows + rA0) * 32);
+      if (two && vA1) x1 = *reinterpret_cast<const uint2*>(wl + ((size_t)tl2 * rows + rA1) * 32);
+      uint32_t b[NB][2], d[NB][2];
+#pragma unroll
+      for (int nb = 0; nb < NB; ++nb) {
+        const int n = nb * 8 + gq;
+        const bf16* pa = al + (size_t)n * astride + tl * 16;
+        const bool v = n < M;
+        b[nb][0] = v ? *reinterpret_cast<const uint32_t*>(pa) : 0u;
+        b[nb][1] = v ? *reinterpret_cast<const uint32_t*>(pa + 8) : 0u;
+        d[nb][0] = (v && two) ? *reinterpret_cast<const uint32_t*>(pa + ks * 16) : 0u;
+        d[nb][1] = (v && two) ? *reinterpret_cast<const uint32_t*>(pa + ks * 16 + 8) : 0u;
+      }
+      const uint32_t a0[4] = {w0.x, w1.x, w0.y, w1.y};
+      const uint32_t a1[4] = {x0.x, x1.x, x0.y, x1.y};
+#pragma unroll
+      for (int nb = 0; nb < NB; ++nb) {
+        mma16816(acc[0][nb], a0, b[nb][0], b[nb][1]);
+        mma16816(acc[1][nb], a1, d[nb][0], d[nb][1]);
+      }
+    }
   } else {
-    astride = g.tpc * 16 + 8;
+    for (int tl = tl0; tl < tiles; tl += ks) {
+      uint2 w0 = make_uint2(0, 0), w1 = make_uint2(0, 0), x0 = make_uint2(0, 0), x1 = make_uint2(0, 0);
+      if (vA0) w0 = *reinterpret_cast<const uint2*>(wl + ((size_t)tl * rows + rA0) * 32);
+      if (vA1) w1 = *reinterpret_cast<const uint2*>(wl + ((size_t)tl * rows + rA1) * 32);
+      if (vB0) x0 = *reinterpret_cast<const uint2*>(wl + ((size_t)tl * rows + rB0) * 32);
+      if (vB1) x1 = *reinterpret_cast<const uint2*>(wl + ((size_t)tl * rows + rB1) * 32);
+      uint32_t b[NB][2];
+#pragma unroll
+      for (int nb = 0; nb < NB; ++nb) {
+        const int n = nb * 8 + gq;
+        const bf16* pa = al + (size_t)n * astride + tl * 16;
+        const bool v = n < M;
+        b[nb][0] = v ? *reinterpret_cast<const uint32_t*>(pa) : 0u;
+        b[nb][1] = v ? *reinterpret_cast<const uint32_t*>(pa + 8) : 0u;
+      }
+      const uint32_t a0[4] = {w0.x, w1.x, w0.y, w1.y};
+      const uint32_t a1[4] = {x0.x, x1.x, x0.y, x1.y};
+#pragma unroll
+      for (int nb = 0; nb < NB; ++nb) {
+        mma16816(acc[0][nb], a0, b[nb][0], b[nb][1]);
+        if (mt1 >= 0) mma16816(acc[1][nb], a1, b[nb][0], b[nb][1]);
+      }
+    }
   }
-  if (g.rows == 0) {
-    if (P.epi == EPI_HEAD) head_finish(p, P, cx, g, 8);
-    return;
-  }
-  float acc[2][2][4];
+}
+
+// All chunks of one phase for this warp; partial sums -> red[kg][m][rows_pad].
+template <int NB>
+__device__ __forceinline__ void gemv_core(const StreamParams& p, const Phase& P, const Ctx& cx, const Geom& g, bool stream,
+                                          int astride, int rows_pad, uint32_t& it, uint32_t& ait) {
+  const int M = p.B;
+  float acc[2][NB][4];
 #pragma unroll
   for (int j = 0; j < 2; ++j)
 #pragma unroll
-    for (int mi = 0; mi < 2; ++mi)
+    for (int nb = 0; nb < NB; ++nb)
 #pragma unroll
-      for (int q = 0; q < 4; ++q) acc[j][mi][q] = 0.f;
-
+      for (int q = 0; q < 4; ++q) acc[j][nb][q] = 0.f;
   const int gq = cx.lane >> 2, tq = cx.lane & 3;
-  const int ng = cx.warp % g.ns, kg = cx.warp / g.ns;
+  const int ng = cx.warp & (g.ns - 1), kg = cx.warp / g.ns;
+  const int mt0 = ng, mt1 = (ng + g.ns < g.mtiles) ? ng + g.ns : -1;
+  const bool active = mt0 < g.mtiles;
+  const bool single = mt1 < 0;
 
   for (int ch = 0; ch < g.nchunks; ++ch) {
     const int T0 = ch * g.tpc;
@@ -225,33 +270,10 @@ __device__ __forceinline__ void gemv_phase(const StreamParams& p, const Phase& P
       abase = reinterpret_cast<const bf16*>(cx.actreg);
       acol0 = T0 * 16;
     }
-    int tl = (kg - (T0 % g.ks) + g.ks) % g.ks;
-    for (; tl < tiles; tl += g.ks) {
-      const int col = acol0 + tl * 16 + 2 * tq;
-      uint32_t a[2][4];
-#pragma unroll
-      for (int mi = 0; mi < 2; ++mi) {
-        const int r0 = mi * 16 + gq, r1 = r0 + 8;
-        const bf16* p0 = abase + (size_t)r0 * astride + col;
-        const bf16* p1 = abase + (size_t)r1 * astride + col;
-        const bool v0 = (mi < mt) && (r0 < M), v1 = (mi < mt) && (r1 < M);
-        a[mi][0] = v0 ? *reinterpret_cast<const uint32_t*>(p0) : 0u;
-        a[mi][1] = v1 ? *reinterpret_cast<const uint32_t*>(p1) : 0u;
-        a[mi][2] = v0 ? *reinterpret_cast<const uint32_t*>(p0 + 8) : 0u;
-        a[mi][3] = v1 ? *reinterpret_cast<const uint32_t*>(p1 + 8) : 0u;
-      }
-#pragma unroll
-      for (int j = 0; j < 2; ++j) {
-        const int i = ng + j * g.ns;
-        if (i < g.nt) {
-          const int row = 8 * i + gq;
-          uint2 b = make_uint2(0u, 0u);
-          if (row < g.rows) b = *reinterpret_cast<const uint2*>(wslot + ((size_t)tl * g.rows + row) * 32 + tq * 8);
-#pragma unroll
-          for (int mi = 0; mi < 2; ++mi)
-            if (mi < mt) mma16816(acc[j][mi], a[mi], b.x, b.y);
-        }
-      }
+    if (active) {
+      const int tl0 = (kg - T0) & (g.ks - 1);
+      if (single) mma_chunk<NB, true>(acc, wslot, abase, astride, acol0, tiles, tl0, g.ks, g.rows, mt0, -1, M, gq, tq);
+      else mma_chunk<NB, false>(acc, wslot, abase, astride, acol0, tiles, tl0, g.ks, g.rows, mt0, mt1, M, gq, tq);
     }
     __syncwarp();
     if (cx.lane == 0) {
@@ -261,124 +283,245 @@ __device__ __forceinline__ void gemv_phase(const StreamParams& p, const Phase& P
     ++it;
     if (stream) ++ait;
   }
-
-  // ---- cross-warp (split-K) reduction through shared memory: red[kg][m][n]
-  const int rows_pad = g.nt * 8;
+  if (!active) return;
+  if (single) {
+#pragma unroll
+    for (int nb = 0; nb < NB; ++nb)
+#pragma unroll
+      for (int q = 0; q < 4; ++q) acc[0][nb][q] += acc[1][nb][q];
+  }
+  // D fragment: c0,c1 = (weight row g, batch 2t, 2t+1), c2,c3 = (row g+8, same batch columns)
 #pragma unroll
   for (int j = 0; j < 2; ++j) {
-    const int i = ng + j * g.ns;
-    if (i < g.nt) {
+    const int mt = j == 0 ? mt0 : mt1;
+    if (j == 1 && single) break;
+    const int row = 16 * mt + gq;
 #pragma unroll
-      for (int mi = 0; mi < 2; ++mi) {
-        if (mi < mt) {
-          const int n = 8 * i + 2 * tq;
-          const int m0 = mi * 16 + gq, m1 = m0 + 8;
-          if (m0 < M)
-            *reinterpret_cast<float2*>(cx.red + ((size_t)kg * p.m_alloc + m0) * rows_pad + n) =
-                make_float2(acc[j][mi][0], acc[j][mi][1]);
-          if (m1 < M)
-            *reinterpret_cast<float2*>(cx.red + ((size_t)kg * p.m_alloc + m1) * rows_pad + n) =
-                make_float2(acc[j][mi][2], acc[j][mi][3]);
-        }
-      }
+    for (int nb = 0; nb < NB; ++nb) {
+      const int n0 = nb * 8 + 2 * tq, n1 = n0 + 1;
+      float* r0 = cx.red + ((size_t)kg * p.m_alloc + n0) * rows_pad + row;
+      float* r1 = cx.red + ((size_t)kg * p.m_alloc + n1) * rows_pad + row;
+      if (n0 < M) { r0[0] = acc[j][nb][0]; r0[8] = acc[j][nb][2]; }
+      if (n1 < M) { r1[0] = acc[j][nb][1]; r1[8] = acc[j][nb][3]; }
     }
+  }
+}
+
+// ------------------------------------------------------------------ GEMV / skinny-GEMM phase
+__device__ __forceinline__ void gemv_phase(const StreamParams& p, const Phase& P, const Ctx& cx, uint32_t& it,
+                                           uint32_t& ait) {
+  const int M = p.B, K = P.K;
+  const bool stream = (P.act_mode == ACT_STREAM);
+  const Geom g = csm_geom(P, cx.c);
+  int astride;
+  if (!stream) {
+    astride = K + 8;
+    stage_act(p, P, cx, astride);
+    compute_sync();
+  } else {
+    astride = g.tpc * 16 + 8;
+  }
+  const int rows_pad = g.mtiles * 16 + 4;
+  if (g.rows > 0) {
+    if (M <= 8) gemv_core<1>(p, P, cx, g, stream, astride, rows_pad, it, ait);
+    else if (M <= 16) gemv_core<2>(p, P, cx, g, stream, astride, rows_pad, it, ait);
+    else gemv_core<4>(p, P, cx, g, stream, astride, rows_pad, it, ait);
   }
   compute_sync();
 
-  // ---- fused epilogues
+  // ---- fused epilogues: thread -> (batch row m, granule u), granules padded to a power of two
   const int gran = P.gran;
   const int upc = g.rows / gran;
+  int up2 = 1;
+  while (up2 < upc) up2 <<= 1;
+  const int u = cx.tid & (up2 - 1);
+  const int mstep = up2 >= CSM_COMPUTE_THREADS ? 1 : CSM_COMPUTE_THREADS / up2;
+  const int m_first = up2 >= CSM_COMPUTE_THREADS ? 0 : cx.tid / up2;
   const StackDims& sd = P.stack ? p.dec : p.bb;
-  for (int e = cx.tid; e < M * upc; e += CSM_COMPUTE_THREADS) {
-    const int m = e / upc, u = e % upc, n = u * gran;
-    float v0 = 0.f, v1 = 0.f;
-    for (int kk = 0; kk < g.ks; ++kk) {
-      const float* r = cx.red + ((size_t)kk * p.m_alloc + m) * rows_pad + n;
-      v0 += r[0];
-      if (gran == 2) v1 += r[1];
-    }
-    v0 = bfround(v0);   // nn.Linear output is bf16
-    v1 = bfround(v1);
-    const int gn = g.row0 + n;   // packed row index
-    switch (P.epi) {
-      case EPI_STORE:
-        P.out[(size_t)m * P.out_stride + gn] = __float2bfloat16_rn(v0);
-        break;
-      case EPI_RESID: {   // hf modeling_llama.py:325,331: residual + f(x), both bf16
-        bf16* o = P.out + (size_t)m * P.out_stride + gn;
-        float r = ldcg_bf16(o);
-        *o = __float2bfloat16_rn(r + v0);
-        break;
+  const int half = sd.hd >> 1;
+  if (u < upc) {
+    for (int m = m_first; m < M; m += mstep) {
+      const int n = u * gran;
+      float v0 = 0.f, v1 = 0.f;
+      for (int kk = 0; kk < g.ks; ++kk) {
+        const float* r = cx.red + ((size_t)kk * p.m_alloc + m) * rows_pad + n;
+        v0 += r[0];
+        if (gran == 2) v1 += r[1];
       }
-      case EPI_SWIGLU: {  // hf modeling_llama.py:183: bf16(silu(gate)) * up -> bf16 ; rows (2j,2j+1)=(gate_j,up_j)
-        float sl = bfround(v0 / (1.f + expf(-v0)));
-        P.out[(size_t)m * P.out_stride + (gn >> 1)] = __float2bfloat16_rn(sl * v1);
-        break;
-      }
-      case EPI_QKV: {     // rows (2j,2j+1) = RoPE pair (i, i+hd/2) of q/k, or two adjacent v features
-        const int half = sd.hd >> 1;
-        const int pidx = gn >> 1;
-        const int nq = sd.heads * half, nk = sd.kv * half;
-        const int pos = P.stack ? P.dec_pos : p.pos;
-        const int cap = P.stack ? CSM_DEC_POS : p.Tcap;
-        bf16* kc = P.stack ? p.kc_dec : p.kc_bb;
-        bf16* vc = P.stack ? p.vc_dec : p.vc_bb;
-        if (pidx < nq + nk) {
-          const bool isq = pidx < nq;
-          const int pp = isq ? pidx : pidx - nq;
-          const int head = pp / half, i = pp % half;
-          const bf16* ct = (P.stack ? p.cos_dec : p.cos_bb) + (size_t)pos * half + i;
-          const bf16* st = (P.stack ? p.sin_dec : p.sin_bb) + (size_t)pos * half + i;
-          const float cs = __bfloat162float(*ct), sn = __bfloat162float(*st);
-          // apply_rotary_pos_emb (hf modeling_llama.py:146-168): every product and the sum round to bf16
-          const float o1 = bfround(bfround(v0 * cs) + bfround(-v1 * sn));
-          const float o2 = bfround(bfround(v1 * cs) + bfround(v0 * sn));
-          bf16* dstp;
-          if (isq) dstp = P.out + (size_t)m * P.out_stride + head * sd.hd + i;
-          else dstp = kc + ((((size_t)P.layer * p.Bmax + m) * sd.kv + head) * cap + pos) * sd.hd + i;
-          dstp[0] = __float2bfloat16_rn(o1);
-          dstp[half] = __float2bfloat16_rn(o2);
-        } else {
-          const int f = (pidx - nq - nk) * 2;
-          const int head = f / sd.hd, d = f % sd.hd;
-          bf16* dstp = vc + ((((size_t)P.layer * p.Bmax + m) * sd.kv + head) * cap + pos) * sd.hd + d;
-          *reinterpret_cast<uint32_t*>(dstp) = pack_bf16(v0, v1);
+      v0 = bfround(v0);   // nn.Linear output is bf16
+      v1 = bfround(v1);
+      const int gn = g.row0 + n;   // packed row index
+      switch (P.epi) {
+        case EPI_STORE:
+          P.out[(size_t)m * P.out_stride + gn] = __float2bfloat16_rn(v0);
+          break;
+        case EPI_RESID: {   // hf modeling_llama.py:325,331: residual + f(x), both bf16
+          bf16* o = P.out + (size_t)m * P.out_stride + gn;
+          float r = ldcg_bf16(o);
+          *o = __float2bfloat16_rn(r + v0);
+          break;
         }
-        break;
-      }
-      case EPI_HEAD: {
-        if (P.out) P.out[(size_t)m * P.out_stride + gn] = __float2bfloat16_rn(v0);
-        cx.red[(size_t)m * rows_pad + n] = v0;   // kk = 0 plane, own element only
-        break;
+        case EPI_SWIGLU: {  // hf modeling_llama.py:183: bf16(silu(gate)) * up -> bf16 ; rows (2j,2j+1)=(gate_j,up_j)
+          float sl = bfround(v0 / (1.f + expf(-v0)));
+          P.out[(size_t)m * P.out_stride + (gn >> 1)] = __float2bfloat16_rn(sl * v1);
+          break;
+        }
+        case EPI_QKV: {     // rows (2j,2j+1) = RoPE pair (i, i+hd/2) of q/k, or two adjacent v features
+          const int pidx = gn >> 1;
+          const int nq = sd.heads * half, nk = sd.kv * half;
+          const int pos = P.stack ? P.dec_pos : p.pos;
+          const int cap = P.stack ? CSM_DEC_POS : p.Tcap;
+          bf16* kc = P.stack ? p.kc_dec : p.kc_bb;
+          bf16* vc = P.stack ? p.vc_dec : p.vc_bb;
+          if (pidx < nq + nk) {
+            const bool isq = pidx < nq;
+            const int pp = isq ? pidx : pidx - nq;
+            const int head = pp / half, i = pp - head * half;
+            // rope tables staged in shared memory at kernel start: decoder [32][half] cos|sin, backbone row `pos`
+            const bf16* ct = P.stack ? cx.rope + pos * half + i : cx.rope + 2 * CSM_DEC_POS * (p.dec.hd >> 1) + i;
+            const bf16* st = P.stack ? ct + CSM_DEC_POS * half : ct + half;
+            const float cs = __bfloat162float(*ct), sn = __bfloat162float(*st);
+            // apply_rotary_pos_emb (hf modeling_llama.py:146-168): every product and the sum round to bf16
+            const float o1 = bfround(bfround(v0 * cs) + bfround(-v1 * sn));
+            const float o2 = bfround(bfround(v1 * cs) + bfround(v0 * sn));
+            bf16* dstp;
+            if (isq) dstp = P.out + (size_t)m * P.out_stride + head * sd.hd + i;
+            else dstp = kc + ((((size_t)P.layer * p.Bmax + m) * sd.kv + head) * cap + pos) * sd.hd + i;
+            dstp[0] = __float2bfloat16_rn(o1);
+            dstp[half] = __float2bfloat16_rn(o2);
+          } else {
+            const int f = (pidx - nq - nk) * 2;
+            const int head = f / sd.hd, d = f - head * sd.hd;
+            bf16* dstp = vc + ((((size_t)P.layer * p.Bmax + m) * sd.kv + head) * cap + pos) * sd.hd + d;
+            *reinterpret_cast<uint32_t*>(dstp) = pack_bf16(v0, v1);
+          }
+          break;
+        }
+        case EPI_HEAD: {
+          if (P.out) P.out[(size_t)m * P.out_stride + gn] = __float2bfloat16_rn(v0);
+          cx.red[(size_t)m * rows_pad + n] = v0;   // kk = 0 plane, own element only
+          break;
+        }
       }
     }
   }
   if (P.epi == EPI_HEAD) {
+    // publish this CTA's best (logit, id) per sequence; consumers reduce after the barrier
     compute_sync();
-    head_finish(p, P, cx, g, rows_pad);
+    for (int m = cx.warp; m < M; m += CSM_COMPUTE_WARPS) {
+      float best = -INFINITY;
+      int bi = 0x7fffffff;
+      for (int n = cx.lane; n < g.rows; n += 32) {
+        float v = cx.red[(size_t)m * rows_pad + n];
+        if (better(v, g.row0 + n, best, bi)) { best = v; bi = g.row0 + n; }
+      }
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) {
+        float ov = __shfl_xor_sync(0xffffffffu, best, o);
+        int oi = __shfl_xor_sync(0xffffffffu, bi, o);
+        if (better(ov, oi, best, bi)) { best = ov; bi = oi; }
+      }
+      if (cx.lane == 0) p.cand[(size_t)cx.c * p.Bmax + m] = make_float2(best, __int_as_float(bi));
+    }
+  }
+}
+
+// ------------------------------------------------------------------ end of frame
+// After the last head: sample codebook 31, publish the 32 ids (modeling_csm.py:657-666) and evaluate
+// the stop rule torch.all(new_frame == 0) (:662).  CTA 0 only.
+__device__ __forceinline__ void finish_phase(const StreamParams& p, const Ctx& cx) {
+  if (cx.c != 0) return;
+  const int M = p.B;
+  reduce_candidates(p, cx, CSM_NQ - 1);
+  __threadfence_block();
+  if (cx.tid == 0) cx.sflag[1] = 0;
+  compute_sync();
+  int nz = 0;
+  for (int e = cx.tid; e < M * CSM_NQ; e += CSM_COMPUTE_THREADS) {
+    const int tok = p.samples[e];   // written by this CTA (this phase or earlier ones of this launch)
+    nz |= (tok != 0);
+    if (p.out_frames) {
+      int m = e / CSM_NQ, q = e % CSM_NQ;
+      p.out_frames[(size_t)m * p.out_stride + p.out_off + q] = (long long)tok;
+    }
+  }
+  if (nz) cx.sflag[1] = 1;
+  compute_sync();
+  if (cx.tid == 0) {
+    if (p.stop_on_zeros && !cx.sflag[1]) *p.stop_flag = 1;   // all-zero frame: not kept, generation ends
+    else if (p.n_frames) *p.n_frames += 1;
   }
 }
 
 // ------------------------------------------------------------------ 33-way masked embedding gather-sum
-// _embed_tokens + mask multiply + sum (modeling_csm.py:261-282,327-334): fp32 accumulate, one bf16 rounding.
+// _embed_tokens + mask multiply + sum (modeling_csm.py:261-282,327-334): fp32 accumulate in slot order,
+// one bf16 rounding.  Unit = (sequence, 256-column chunk), one warp each, spread over the CTAs.
 __device__ __forceinline__ void embed_phase(const StreamParams& p, const Ctx& cx) {
   const int H = p.bb.H;
-  for (int m = cx.c; m < p.B; m += cx.G) {
-    for (int d2 = cx.tid; d2 < H / 2; d2 += CSM_COMPUTE_THREADS) {
-      float a0 = 0.f, a1 = 0.f;
-      for (int slot = 0; slot <= CSM_NQ; ++slot) {
-        int mk = p.mask ? p.mask[m * (CSM_NQ + 1) + slot] : (slot < CSM_NQ ? 1 : 0);
-        if (mk == 0) continue;
+  const int nchunk = (H + 255) / 256;
+  const int nunits = p.B * nchunk;
+  for (int unit = cx.warp * cx.G + cx.c; unit < nunits; unit += CSM_COMPUTE_WARPS * cx.G) {
+    const int m = unit / nchunk, col = (unit - m * nchunk) * 256 + cx.lane * 8;
+    // lane l holds (id, mask) of slot l; slot 32 (text) is held by every lane
+    long long my_tok, txt_tok;
+    int my_mk, txt_mk;
+    if (p.ids) {
+      my_tok = p.ids[m * (CSM_NQ + 1) + cx.lane];
+      txt_tok = p.ids[m * (CSM_NQ + 1) + CSM_NQ];
+    } else {
+      my_tok = (long long)ldcg_i32(p.fed + m * CSM_NQ + cx.lane);
+      txt_tok = 0;
+    }
+    if (p.mask) {
+      my_mk = p.mask[m * (CSM_NQ + 1) + cx.lane];
+      txt_mk = p.mask[m * (CSM_NQ + 1) + CSM_NQ];
+    } else {
+      my_mk = 1;
+      txt_mk = 0;
+    }
+    float acc[8];
+#pragma unroll
+    for (int i = 0; i < 8; ++i) acc[i] = 0.f;
+    const bool incol = col < H;
+#pragma unroll
+    for (int s0 = 0; s0 < 33; s0 += 11) {
+      uint4 v[11];
+      int mk[11];
+#pragma unroll
+      for (int j = 0; j < 11; ++j) {
+        const int slot = s0 + j;
         long long tok;
-        if (p.ids) tok = p.ids[m * (CSM_NQ + 1) + slot];
-        else tok = slot < CSM_NQ ? (long long)ldcg_i32(p.fed + m * CSM_NQ + slot) : 0;
+        if (slot < CSM_NQ) {
+          tok = __shfl_sync(0xffffffffu, my_tok, slot);
+          mk[j] = __shfl_sync(0xffffffffu, my_mk, slot);
+        } else {
+          tok = txt_tok;
+          mk[j] = txt_mk;
+        }
         const bf16* row = slot < CSM_NQ ? p.audio_emb + (size_t)(tok + (long long)slot * p.V) * H
                                         : p.text_emb + (size_t)tok * H;
-        uint32_t u = __ldg(reinterpret_cast<const unsigned int*>(row) + d2);
-        a0 += bf_lo(u) * (float)mk;
-        a1 += bf_hi(u) * (float)mk;
+        v[j] = make_uint4(0, 0, 0, 0);
+        if (mk[j] != 0 && incol) v[j] = __ldg(reinterpret_cast<const uint4*>(row + col));
       }
-      reinterpret_cast<uint32_t*>(p.h_bb + (size_t)m * H)[d2] = pack_bf16(a0, a1);
+#pragma unroll
+      for (int j = 0; j < 11; ++j) {
+        if (mk[j] == 0) continue;
+        const uint32_t* u = reinterpret_cast<const uint32_t*>(&v[j]);
+        const float f = (float)mk[j];
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+          acc[2 * i] += bf_lo(u[i]) * f;
+          acc[2 * i + 1] += bf_hi(u[i]) * f;
+        }
+      }
+    }
+    if (incol) {
+      uint4 o;
+      o.x = pack_bf16(acc[0], acc[1]);
+      o.y = pack_bf16(acc[2], acc[3]);
+      o.z = pack_bf16(acc[4], acc[5]);
+      o.w = pack_bf16(acc[6], acc[7]);
+      *reinterpret_cast<uint4*>(p.h_bb + (size_t)m * H + col) = o;
     }
   }
 }
@@ -406,6 +549,20 @@ __device__ __forceinline__ void attn_bb_phase(const StreamParams& p, const Phase
     const size_t kvbase = (((size_t)P.layer * p.Bmax + b) * nk + kvh) * (size_t)p.Tcap * HD;
     const bf16* Kp = p.kc_bb + kvbase;
     const bf16* Vp = p.vc_bb + kvbase;
+    const int pbase = sp * CSM_ATT_SPLIT + cx.warp * 16;
+    // K and V of this warp's 16 positions: all eight 16-byte loads issued before anything is used
+    uint4 kv4[4], vv4[4];
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const int pj = pbase + 4 * j + grp;
+      if (pj < Ttot) {
+        kv4[j] = ldcg_u4(Kp + (size_t)pj * HD + dl * 8);
+        vv4[j] = ldcg_u4(Vp + (size_t)pj * HD + dl * 8);
+      } else {
+        kv4[j] = make_uint4(0, 0, 0, 0);
+        vv4[j] = make_uint4(0, 0, 0, 0);
+      }
+    }
     // q slice of this lane: REP heads x 8 dims, pre-scaled
     float q[REP][8];
 #pragma unroll
@@ -418,15 +575,7 @@ __device__ __forceinline__ void attn_bb_phase(const StreamParams& p, const Phase
         q[h][2 * i + 1] = bf_hi(u[i]) * p.bb.scale;
       }
     }
-    const int pbase = sp * CSM_ATT_SPLIT + cx.warp * 16;
     float s[REP][4];
-    uint4 kv4[4];
-#pragma unroll
-    for (int j = 0; j < 4; ++j) {
-      const int pj = pbase + 4 * j + grp;
-      if (pj < Ttot) kv4[j] = ldcg_u4(Kp + (size_t)pj * HD + dl * 8);
-      else kv4[j] = make_uint4(0, 0, 0, 0);
-    }
 #pragma unroll
     for (int j = 0; j < 4; ++j) {
       const int pj = pbase + 4 * j + grp;
@@ -444,13 +593,6 @@ __device__ __forceinline__ void attn_bb_phase(const StreamParams& p, const Phase
         d += __shfl_xor_sync(0xffffffffu, d, 4);
         s[h][j] = (pj < Ttot) ? d : -INFINITY;
       }
-    }
-    // V loads issued before the softmax math
-#pragma unroll
-    for (int j = 0; j < 4; ++j) {
-      const int pj = pbase + 4 * j + grp;
-      if (pj < Ttot) kv4[j] = ldcg_u4(Vp + (size_t)pj * HD + dl * 8);
-      else kv4[j] = make_uint4(0, 0, 0, 0);
     }
     float mx[REP], ls[REP], o[REP][8];
 #pragma unroll
@@ -474,7 +616,7 @@ __device__ __forceinline__ void attn_bb_phase(const StreamParams& p, const Phase
     }
 #pragma unroll
     for (int j = 0; j < 4; ++j) {
-      const uint32_t* u = reinterpret_cast<const uint32_t*>(&kv4[j]);
+      const uint32_t* u = reinterpret_cast<const uint32_t*>(&vv4[j]);
       float vf[8];
 #pragma unroll
       for (int i = 0; i < 4; ++i) { vf[2 * i] = bf_lo(u[i]); vf[2 * i + 1] = bf_hi(u[i]); }
@@ -549,39 +691,65 @@ __device__ __forceinline__ void attn_bb_phase(const StreamParams& p, const Phase
 }
 
 // ------------------------------------------------------------------ decoder attention (<= 32 positions, hd 128)
+// One warp per (sequence, query head), spread over the CTAs.  Lane t owns cached position t for the
+// scores and output dims 4*lane.. for P.V; every load of a stage is issued before its first use.
 __device__ __forceinline__ void attn_dec_phase(const StreamParams& p, const Phase& P, const Ctx& cx) {
   constexpr int HD = 128;
   const int nh = p.dec.heads, nk = p.dec.kv, rep = nh / nk;
   const int T = P.dec_pos + 1;
   const int nunits = p.B * nh;
   for (int unit = cx.warp * cx.G + cx.c; unit < nunits; unit += CSM_COMPUTE_WARPS * cx.G) {
-    const int b = unit / nh, head = unit % nh, kvh = head / rep;
+    const int b = unit / nh, head = unit - b * nh, kvh = head / rep;
     const size_t kvbase = (((size_t)P.layer * p.Bmax + b) * nk + kvh) * (size_t)CSM_DEC_POS * HD;
     const bf16* qp = p.q_dec + (size_t)b * (nh * HD) + head * HD;
-    float sc = -INFINITY;
+    const bf16* kp = p.kc_dec + kvbase + (size_t)cx.lane * HD;
+    uint4 kq[HD / 8];
+    // q: lane l holds dims 4l..4l+3 (8 bytes), redistributed by shuffles below
+    const uint2 qmine = ldcg_u2(qp + cx.lane * 4);
     if (cx.lane < T) {
-      const bf16* kp = p.kc_dec + kvbase + (size_t)cx.lane * HD;
-      float d = 0.f;
-#pragma unroll 4
-      for (int ci = 0; ci < HD / 8; ++ci) {
-        uint4 qv = ldcg_u4(qp + ci * 8);
-        uint4 kv = ldcg_u4(kp + ci * 8);
-        const uint32_t* qu = reinterpret_cast<const uint32_t*>(&qv);
-        const uint32_t* ku = reinterpret_cast<const uint32_t*>(&kv);
 #pragma unroll
-        for (int i = 0; i < 4; ++i) d += bf_lo(qu[i]) * bf_lo(ku[i]) + bf_hi(qu[i]) * bf_hi(ku[i]);
-      }
-      sc = d * p.dec.scale;
+      for (int ci = 0; ci < HD / 8; ++ci) kq[ci] = ldcg_u4(kp + ci * 8);
+    } else {
+#pragma unroll
+      for (int ci = 0; ci < HD / 8; ++ci) kq[ci] = make_uint4(0, 0, 0, 0);
     }
+    // V rows (independent of the scores): 8 bytes per lane per position, first half issued with K
+    const bf16* vp = p.vc_dec + kvbase + cx.lane * 4;
+    uint2 va[CSM_DEC_POS / 2];
+#pragma unroll
+    for (int t = 0; t < CSM_DEC_POS / 2; ++t) va[t] = t < T ? ldcg_u2(vp + (size_t)t * HD) : make_uint2(0, 0);
+    float d = 0.f;
+#pragma unroll
+    for (int ci = 0; ci < HD / 8; ++ci) {
+      // dims 8ci..8ci+7 of q live in lanes 2ci (first 4) and 2ci+1 (last 4)
+      const uint32_t q0 = __shfl_sync(0xffffffffu, qmine.x, 2 * ci), q1 = __shfl_sync(0xffffffffu, qmine.y, 2 * ci);
+      const uint32_t q2 = __shfl_sync(0xffffffffu, qmine.x, 2 * ci + 1), q3 = __shfl_sync(0xffffffffu, qmine.y, 2 * ci + 1);
+      const uint4 kv = kq[ci];
+      d += bf_lo(q0) * bf_lo(kv.x) + bf_hi(q0) * bf_hi(kv.x);
+      d += bf_lo(q1) * bf_lo(kv.y) + bf_hi(q1) * bf_hi(kv.y);
+      d += bf_lo(q2) * bf_lo(kv.z) + bf_hi(q2) * bf_hi(kv.z);
+      d += bf_lo(q3) * bf_lo(kv.w) + bf_hi(q3) * bf_hi(kv.w);
+    }
+    uint2 vb[CSM_DEC_POS / 2];
+#pragma unroll
+    for (int t = 0; t < CSM_DEC_POS / 2; ++t)
+      vb[t] = (t + CSM_DEC_POS / 2) < T ? ldcg_u2(vp + (size_t)(t + CSM_DEC_POS / 2) * HD) : make_uint2(0, 0);
+    const float sc = cx.lane < T ? d * p.dec.scale : -INFINITY;
     const float mx = warp_max(sc);
     const float pe = (cx.lane < T) ? __expf(sc - mx) : 0.f;
     const float l = warp_sum(pe);
     float o0 = 0.f, o1 = 0.f, o2 = 0.f, o3 = 0.f;
-    for (int t = 0; t < T; ++t) {
+#pragma unroll
+    for (int t = 0; t < CSM_DEC_POS / 2; ++t) {
       const float pv = __shfl_sync(0xffffffffu, pe, t);
-      uint2 vv = ldcg_u2(p.vc_dec + kvbase + (size_t)t * HD + cx.lane * 4);
-      o0 += pv * bf_lo(vv.x); o1 += pv * bf_hi(vv.x);
-      o2 += pv * bf_lo(vv.y); o3 += pv * bf_hi(vv.y);
+      o0 += pv * bf_lo(va[t].x); o1 += pv * bf_hi(va[t].x);
+      o2 += pv * bf_lo(va[t].y); o3 += pv * bf_hi(va[t].y);
+    }
+#pragma unroll
+    for (int t = 0; t < CSM_DEC_POS / 2; ++t) {
+      const float pv = __shfl_sync(0xffffffffu, pe, t + CSM_DEC_POS / 2);
+      o0 += pv * bf_lo(vb[t].x); o1 += pv * bf_hi(vb[t].x);
+      o2 += pv * bf_lo(vb[t].y); o3 += pv * bf_hi(vb[t].y);
     }
     const float inv = 1.f / l;
     uint2 ov = make_uint2(pack_bf16(o0 * inv, o1 * inv), pack_bf16(o2 * inv, o3 * inv));
@@ -602,8 +770,12 @@ __global__ void __launch_bounds__(CSM_THREADS, 1) csm_stream_kernel(const Stream
   cx.afull = cx.empty + CSM_MAX_SLOTS;
   cx.aempty = cx.afull + 2;
   cx.sflag = reinterpret_cast<volatile int*>(cx.aempty + 2);
-  cx.red = reinterpret_cast<float*>(csm_smem + SM_BAR_BYTES);
-  cx.actreg = csm_smem + SM_BAR_BYTES + p.red_bytes;
+  cx.desc = reinterpret_cast<Phase*>(csm_smem + 256);
+  cx.scratch = reinterpret_cast<float*>(csm_smem + 512);
+  cx.tok = reinterpret_cast<int*>(csm_smem + 1536);
+  cx.rope = reinterpret_cast<bf16*>(csm_smem + CSM_SM_HDR_BYTES);
+  cx.red = reinterpret_cast<float*>(csm_smem + CSM_SM_HDR_BYTES + p.rope_bytes);
+  cx.actreg = csm_smem + CSM_SM_HDR_BYTES + p.rope_bytes + p.red_bytes;
   cx.ring = cx.actreg + p.act_region_bytes;
   cx.tid = threadIdx.x;
   cx.warp = threadIdx.x >> 5;
@@ -622,6 +794,23 @@ __global__ void __launch_bounds__(CSM_THREADS, 1) csm_stream_kernel(const Stream
     }
     mbar_fence_init();
   }
+  if (cx.tid < CSM_COMPUTE_THREADS) {
+    // rope tables -> shared memory: decoder cos|sin for its 32 positions, backbone row `pos`
+    const int hd2 = p.dec.hd >> 1, hb2 = p.bb.hd >> 1;
+    const int nd = CSM_DEC_POS * hd2;
+    for (int i = cx.tid; i < nd; i += CSM_COMPUTE_THREADS) {
+      cx.rope[i] = p.cos_dec[i];
+      cx.rope[nd + i] = p.sin_dec[i];
+    }
+    if (cx.tid < hb2) {
+      cx.rope[2 * nd + cx.tid] = p.cos_bb[(size_t)p.pos * hb2 + cx.tid];
+      cx.rope[2 * nd + hb2 + cx.tid] = p.sin_bb[(size_t)p.pos * hb2 + cx.tid];
+    }
+    // first phase descriptor
+    if (cx.tid < 8)
+      reinterpret_cast<uint4*>(&cx.desc[p.phase_begin & 1])[cx.tid] =
+          __ldg(reinterpret_cast<const uint4*>(p.phases + p.phase_begin) + cx.tid);
+  }
   __syncthreads();
 
   if (cx.warp == CSM_COMPUTE_WARPS) {
@@ -629,10 +818,9 @@ __global__ void __launch_bounds__(CSM_THREADS, 1) csm_stream_kernel(const Stream
     if (cx.lane == 0) {
       uint32_t it = 0;
       for (int ph = p.phase_begin; ph < p.phase_end; ++ph) {
-        const Phase& P = p.phases[ph];
+        const Phase P = p.phases[ph];
         if (P.type != PH_GEMV) continue;
-        const Geom g = csm_geom(P.N, P.K, P.gran, cx.G, cx.c, p.slot_bytes,
-                                P.act_mode == ACT_STREAM ? p.stream_tpc_max : 0x7fffffff);
+        const Geom g = csm_geom(P, cx.c);
         const unsigned char* src = reinterpret_cast<const unsigned char*>(P.w) + (size_t)g.row0 * P.K * 2;
         for (int ch = 0; ch < g.nchunks; ++ch) {
           const int tiles = min(g.tpc, g.ntiles - ch * g.tpc);
@@ -653,10 +841,12 @@ __global__ void __launch_bounds__(CSM_THREADS, 1) csm_stream_kernel(const Stream
     if (cx.lane == 0) {
       uint32_t ait = 0;
       for (int ph = p.phase_begin; ph < p.phase_end; ++ph) {
-        const Phase& P = p.phases[ph];
+        const Phase P = p.phases[ph];
         if (P.type != PH_GEMV || P.act_mode != ACT_STREAM) continue;
-        const Geom g = csm_geom(P.N, P.K, P.gran, cx.G, cx.c, p.slot_bytes, p.stream_tpc_max);
+        const Geom g = csm_geom(P, cx.c);
         if (g.nchunks == 0) continue;
+        const bf16* actp = P.act;
+        const int act_stride = P.act_stride;
         if (p.use_barrier && ph > p.phase_begin) grid_wait(p.bar_counter, (unsigned)(ph - p.phase_begin) * cx.G);
         fence_proxy_async();
         const int astride_b = (g.tpc * 16 + 8) * 2;
@@ -667,10 +857,9 @@ __global__ void __launch_bounds__(CSM_THREADS, 1) csm_stream_kernel(const Stream
           if (ait >= 2u) mbar_wait(&cx.aempty[s], ((ait >> 1) - 1u) & 1u);
           mbar_expect_tx(&cx.afull[s], rowbytes * (uint32_t)p.B);
           unsigned char* dst = cx.actreg + (size_t)s * (p.act_region_bytes / 2);
-          const unsigned char* src =
-              reinterpret_cast<const unsigned char*>(P.act) + (size_t)ch * g.tpc * 32;
+          const unsigned char* src = reinterpret_cast<const unsigned char*>(actp) + (size_t)ch * g.tpc * 32;
           for (int m = 0; m < p.B; ++m)
-            bulk_g2s(dst + (size_t)m * astride_b, src + (size_t)m * P.act_stride * 2, rowbytes, &cx.afull[s]);
+            bulk_g2s(dst + (size_t)m * astride_b, src + (size_t)m * act_stride * 2, rowbytes, &cx.afull[s]);
           ++ait;
         }
       }
@@ -685,7 +874,11 @@ __global__ void __launch_bounds__(CSM_THREADS, 1) csm_stream_kernel(const Stream
       if (cx.tid == 0) grid_wait(p.bar_counter, (unsigned)(ph - p.phase_begin) * cx.G);
       compute_sync();
     }
-    const Phase& P = p.phases[ph];
+    // descriptor of this phase is in shared memory; fetch the next one while this phase runs
+    const Phase P = cx.desc[ph & 1];
+    uint4 nxt = make_uint4(0, 0, 0, 0);
+    const bool fetch = cx.warp == CSM_COMPUTE_WARPS - 1 && cx.lane < 8 && ph + 1 < p.phase_end;
+    if (fetch) nxt = __ldg(reinterpret_cast<const uint4*>(p.phases + ph + 1) + cx.lane);
     if (p.prof != nullptr && cx.c == 0 && cx.tid == 0) p.prof[2 * ph] = clock64();
     switch (P.type) {
       case PH_EMBED: embed_phase(p, cx); break;
@@ -698,11 +891,13 @@ __global__ void __launch_bounds__(CSM_THREADS, 1) csm_stream_kernel(const Stream
         break;
       }
       case PH_ATTN_DEC: attn_dec_phase(p, P, cx); break;
+      case PH_FINISH: finish_phase(p, cx); break;
     }
     if (p.prof != nullptr && cx.c == 0 && cx.tid == 0) p.prof[2 * ph + 1] = clock64();
-    if (p.use_barrier && ph + 1 < p.phase_end) {
+    if (fetch) reinterpret_cast<uint4*>(&cx.desc[(ph + 1) & 1])[cx.lane] = nxt;
+    if (ph + 1 < p.phase_end) {
       compute_sync();
-      if (cx.tid == 0) {
+      if (p.use_barrier && cx.tid == 0) {
         __threadfence();
         atomicAdd(p.bar_counter, 1u);
       }

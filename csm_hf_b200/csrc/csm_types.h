@@ -13,15 +13,17 @@ typedef __nv_bfloat16 bf16;
 #define CSM_NQ 32            // codebooks per frame (modeling_csm.py:66)
 #define CSM_DEC_POS 32       // decoder positions per frame: last_h + 31 codebook embeddings
 #define CSM_ATT_SPLIT 128    // backbone positions per split-KV unit
-#define CSM_MAX_NT 16        // at most 128 weight rows per CTA per matrix
+#define CSM_MAX_ROWS 256     // at most 16 m-tiles of 16 weight rows per CTA per matrix
+#define CSM_SM_HDR_BYTES 2048   // mbarriers, phase-descriptor slots, small scratch
 
-enum PhaseType { PH_EMBED = 0, PH_GEMV = 1, PH_ATTN_BB = 2, PH_ATTN_DEC = 3 };
+enum PhaseType { PH_EMBED = 0, PH_GEMV = 1, PH_ATTN_BB = 2, PH_ATTN_DEC = 3, PH_FINISH = 4 };
 enum ActMode { ACT_NORM = 0, ACT_PLAIN = 1, ACT_GATHER = 2, ACT_STREAM = 3 };
 enum EpiMode { EPI_STORE = 0, EPI_RESID = 1, EPI_SWIGLU = 2, EPI_QKV = 3, EPI_HEAD = 4 };
 
 // One step of the per-frame program.  A frame is ~800 of these executed in order by every
 // CTA of one persistent launch, with a grid-wide barrier between consecutive phases.
-struct Phase {
+// 128 bytes: the kernel copies the next descriptor into shared memory while a phase runs.
+struct __align__(16) Phase {
   int type;         // PhaseType
   int act_mode;     // ActMode   (PH_GEMV)
   int epi;          // EpiMode   (PH_GEMV)
@@ -33,12 +35,19 @@ struct Phase {
   int dec_pos;      // decoder position of this pass (RoPE / attention length)
   int act_stride;   // elements between activation rows
   int out_stride;
+  // row split over the grid, computed on the host for the launch grid G: CTAs c < r own q+1
+  // granules, the others q; [0] = values for the larger share, [1] for the smaller
+  int q, r;
+  int tpc[2];       // k16-tiles per ring chunk
+  int nch[2];       // chunks per CTA
+  int pad_[4];
   const bf16* w;        // packed weights, see csm_pack.cu
   const bf16* act;      // activation rows (ACT_GATHER: embedding table)
   const bf16* norm_w;   // ACT_NORM weight
   bf16* out;            // STORE/RESID/SWIGLU destination; QKV: q buffer; HEAD: logits (nullable)
   bf16* norm_out;       // optional copy of the normalised rows (last_hidden_state)
 };
+static_assert(sizeof(Phase) == 128, "Phase must be 128 bytes");
 
 struct StackDims {
   int H, I, L, heads, kv, hd;
@@ -64,8 +73,7 @@ struct StreamParams {
   float* attn_part;             // [Bmax][heads_bb][nsplit_max][hd+2]
   int nsplit_max;
   unsigned int* attn_cnt;       // [Bmax][kv_bb]
-  float2* head_part;            // [grid][Bmax] (value, index)
-  unsigned int* head_cnt;
+  float2* cand;                 // [grid][Bmax] per-CTA (best logit, index) of the last head phase
   int* samples;                 // [Bmax][32] argmax of every head
   int* fed;                     // [Bmax][32] tokens fed onward (== samples unless forced)
   int forced;
@@ -78,43 +86,35 @@ struct StreamParams {
   int* stop_flag;
   int* n_frames;
   int stop_on_zeros;
-  // shared-memory plan
+  // shared-memory plan (host: plan_smem)
   int m_alloc;                  // activation rows rounded up to 8
   int slot_bytes, n_slots;
-  int act_region_bytes, red_bytes;
-  int stream_tpc_max;
+  int rope_bytes, act_region_bytes, red_bytes;
   unsigned long long* prof;     // debug: CTA 0 writes clock64 at [2*ph] phase start, [2*ph+1] phase end
 };
 
-// Row split and chunking of one weight matrix for CTA `c` of `G`.
+// Row split and chunking of one weight matrix for one CTA.
 struct Geom {
   int row0, rows;     // packed rows owned by this CTA
   int ntiles;         // K/16
   int tpc;            // k16-tiles per ring slot
   int nchunks;
-  int nt, ns, ks;     // n8-tiles, n-split and k-split over the 8 compute warps
+  int mtiles;         // 16-row m-tiles
+  int ns, ks;         // m-tile split and k split over the 8 compute warps (ns*ks == 8)
 };
 
-__host__ __device__ inline Geom csm_geom(int N, int K, int gran, int G, int c, int slot_bytes, int tpc_cap) {
+__host__ __device__ inline Geom csm_geom(const Phase& P, int c) {
   Geom g;
-  int U = N / gran, q = U / G, r = U % G;
-  int start = c * q + (c < r ? c : r);
-  int cnt = q + (c < r ? 1 : 0);
-  g.row0 = start * gran;
-  g.rows = cnt * gran;
-  g.ntiles = K / 16;
-  if (g.rows == 0) {
-    g.tpc = 0; g.nchunks = 0; g.nt = 0; g.ns = 1; g.ks = 8;
-    return g;
-  }
-  int tpc = slot_bytes / (g.rows * 32);
-  if (tpc > g.ntiles) tpc = g.ntiles;
-  if (tpc > tpc_cap) tpc = tpc_cap;
-  if (tpc < 1) tpc = 1;
-  g.tpc = tpc;
-  g.nchunks = (g.ntiles + tpc - 1) / tpc;
-  g.nt = (g.rows + 7) / 8;
-  g.ns = g.nt >= 8 ? 8 : (g.nt >= 4 ? 4 : (g.nt >= 2 ? 2 : 1));
+  const int hi = c < P.r;
+  const int cnt = P.q + hi;
+  const int start = c * P.q + (hi ? c : P.r);
+  g.row0 = start * P.gran;
+  g.rows = cnt * P.gran;
+  g.ntiles = P.K >> 4;
+  g.tpc = hi ? P.tpc[0] : P.tpc[1];
+  g.nchunks = hi ? P.nch[0] : P.nch[1];
+  g.mtiles = (g.rows + 15) >> 4;
+  g.ns = g.mtiles >= 5 ? 8 : (g.mtiles >= 3 ? 4 : (g.mtiles >= 2 ? 2 : 1));
   g.ks = 8 / g.ns;
   return g;
 }

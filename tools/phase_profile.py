@@ -17,7 +17,7 @@ from csm_hf_b200.config import CSMConfig, tiny_config  # noqa: E402
 from csm_hf_b200.modeling import CSMModel  # noqa: E402
 from csm_hf_b200.synthetic import make_context, make_state_dict  # noqa: E402
 
-TYPES = {0: "embed", 1: "gemv", 2: "attn_bb", 3: "attn_dec"}
+TYPES = {0: "embed", 1: "gemv", 2: "attn_bb", 3: "attn_dec", 4: "finish"}
 EPI = {0: "store(proj)", 1: "resid", 2: "swiglu(gate/up)", 3: "qkv+rope", 4: "head+argmax"}
 
 
@@ -49,8 +49,6 @@ def main():
     for ph in range(nph):
         ty, ep, stack, am = info[4 * ph], info[4 * ph + 1], info[4 * ph + 2], info[4 * ph + 3]
         kind = TYPES[ty] if ty != 1 else ("dec " if stack else "bb  ") + EPI[ep] + (" [K-stream]" if am == 3 else "")
-        if ty in (2, 3):
-            kind = TYPES[ty]
         b = t[2 * ph + 1] - t[2 * ph]
         w = t[2 * ph] - t[2 * ph - 1] if ph > 0 else 0
         body[kind] += b
