@@ -4,12 +4,12 @@
 // [in,out], modeling_csm.py:236-240,557).  Destination for a matrix with N packed rows and
 // reduction length K, split over G CTAs (csm_geom in csm_types.h):
 //
-//   for CTA c (rows row0..row0+rows): for k16-tile T: for local row r: 32 bytes =
-//       k-permuted 16 bf16  [k0 k1 k8 k9 | k2 k3 k10 k11 | k4 k5 k12 k13 | k6 k7 k14 k15]
+//   for CTA c (rows row0..row0+rows): for k16-tile T: for k-half h (k 0-7, 8-15): for local row r:
+//       16 bytes = the 8 bf16 W[row0+r][16T+8h .. 16T+8h+7]
 //
 // so that (a) a CTA's whole slice, and any k-range of it, is one contiguous byte range for a
-// bulk copy, and (b) lane (g,t) of a warp reads its mma.m16n8k16 B fragment {b0b1,b2b3} for
-// row 8i+g with one 8-byte shared-memory load at [(T*rows + 8i+g)*32 + 8t].
+// bulk copy, and (b) the mma.m16n8k16 A fragment of 16 rows x 16 k is one ldmatrix.x4 whose four
+// 8x8 matrices (8 consecutive rows of one k-half) are 128 contiguous, bank-conflict-free bytes.
 //
 // `row_map[n]` gives, for packed row n, the row of the virtual concatenation of up to three
 // sources (q|k|v or gate|up), which is how RoPE pairs (i, i+hd/2) and (gate_j, up_j) pairs
@@ -49,17 +49,13 @@ __global__ void csm_pack_kernel(PackSrc src, const int* __restrict__ row_map, in
     bf16 v[16];
 #pragma unroll
     for (int k = 0; k < 16; ++k) v[k] = sp[k * cs];
-    bf16 o[16];
+    // [tile][k-half][row][8]: each 8x8 ldmatrix tile (8 rows x one k-half) is 128 contiguous bytes
+    bf16* dp = dst + (long long)row0 * K + ((long long)T * 2 * rows + lr) * 8;
 #pragma unroll
-    for (int t = 0; t < 4; ++t) {
-      o[4 * t + 0] = v[2 * t];
-      o[4 * t + 1] = v[2 * t + 1];
-      o[4 * t + 2] = v[2 * t + 8];
-      o[4 * t + 3] = v[2 * t + 9];
-    }
-    bf16* dp = dst + (long long)row0 * K + ((long long)T * rows + lr) * 16;
+    for (int k = 0; k < 8; ++k) dp[k] = v[k];
+    dp += (long long)rows * 8;
 #pragma unroll
-    for (int k = 0; k < 16; ++k) dp[k] = o[k];
+    for (int k = 0; k < 8; ++k) dp[k] = v[8 + k];
   }
 }
 

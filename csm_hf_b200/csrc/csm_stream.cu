@@ -42,6 +42,7 @@ struct Ctx {
   unsigned char* actreg;
   unsigned char* ring;
   int tid, warp, lane, c, G;
+  uint32_t slot, slot_par, aslot, aslot_par;   // ring positions of the consumer side
 };
 
 __device__ __forceinline__ void grid_wait(const unsigned int* counter, unsigned target) {
@@ -165,79 +166,65 @@ __device__ __forceinline__ void stage_act(const StreamParams& p, const Phase& P,
 }
 
 // ------------------------------------------------------------------ tensor-core inner loop
-// acc[j][nb] (+)= W[16 rows of m-tile j] x act[8 batch rows of n-tile nb] over this warp's k16-tiles of
-// one ring chunk.  SINGLE: the warp owns one m-tile; consecutive tiles alternate between the two
-// accumulator sets so that two independent MMA chains are in flight.
+// One ring chunk holds this CTA's rows for `tiles` k16-tiles as [tile][k-half][row][8 bf16] (csm_pack.cu), so
+// the 16x16 A fragment of an m-tile is ONE ldmatrix.x4 (four conflict-free 8x8 matrices).  The B fragments
+// (8 batch rows x 16 k) of two k-tiles come from the activation rows with one more ldmatrix.x4.  Rows past the
+// CTA's last weight row and batch rows past M read arbitrary shared memory: they only feed accumulator
+// rows / columns that are never stored.
+__device__ __forceinline__ void ldsm_x4(uint32_t (&r)[4], uint32_t addr) {
+  asm volatile("ldmatrix.sync.aligned.m8n8.x4.shared.b16 {%0,%1,%2,%3}, [%4];"
+               : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3])
+               : "r"(addr));
+}
+
+// acc[j][nb] (+)= W[m-tile] x act[n-tile nb] over this warp's k16-tiles (tl0, tl0+ks, ...) of one chunk, two
+// k-tiles per iteration.  SINGLE: one m-tile, the two k-tiles of an iteration go to the two accumulator
+// sets (two independent MMA chains); otherwise accumulator set j belongs to m-tile j.
 template <int NB, bool SINGLE>
-__device__ __forceinline__ void mma_chunk(float (&acc)[2][NB][4], const unsigned char* wslot, const bf16* abase, int astride,
-                                          int acol0, int tiles, int tl0, int ks, int rows, int mt0, int mt1, int M, int gq,
-                                          int tq) {
-  // per-lane constant parts of the addresses
-  const int rA0 = 16 * mt0 + gq, rA1 = rA0 + 8;
-  const int rB0 = 16 * mt1 + gq, rB1 = rB0 + 8;
-  const bool vA0 = rA0 < rows, vA1 = rA1 < rows;
-  const bool vB0 = !SINGLE && mt1 >= 0 && rB0 < rows, vB1 = !SINGLE && mt1 >= 0 && rB1 < rows;
-  const unsigned char* wl = wslot + tq * 8;
-  const bf16* al = abase + acol0 + 2 * tq;
-  if (SINGLE) {
-    for (int tl = tl0; tl < tiles; tl += 2 * ks) {
-      const int tl2 = tl + ks;
-      const bool two = tl2 < tiles;
-      uint2 w0 = make_uint2(0, 0), w1 = make_uint2(0, 0), x0 = make_uint2(0, 0), x1 = make_uint2(0, 0);
-      if (vA0) w0 = *reinterpret_cast<const uint2*>(wl + ((size_t)tl * rows + rA0) * 32);
-      if (vA1) w1 = *reinterpret_cast<const uint2*>(wl + ((size_t)tl * rows + rA1) * 32);
-      if (two && vA0) x0 = *reinterpret_cast<const uint2*>(wl + ((size_t)tl2 * rows + rA0) * 32);
-      if (two && vA1) x1 = *reinterpret_cast<const uint2*>(wl + ((size_t)tl2 * rows + rA1) * 32);
-      uint32_t b[NB][2], d[NB][2];
+__device__ __forceinline__ void mma_chunk(float (&acc)[2][NB][4], uint32_t wa0, uint32_t wa1, const uint32_t (&ab)[NB],
+                                          int tiles, int tl0, int ks, uint32_t tile_bytes) {
+  const uint32_t wsec = (uint32_t)ks * tile_bytes;        // second k-tile of the iteration
+  const uint32_t wstep = 2u * wsec, astep = 2u * (uint32_t)ks * 32u;
+  wa0 += (uint32_t)tl0 * tile_bytes;
+  wa1 += (uint32_t)tl0 * tile_bytes;
+  uint32_t aoff = (uint32_t)tl0 * 32u;
+  for (int tl = tl0; tl < tiles; tl += 2 * ks) {
+    const bool two = tl + ks < tiles;
+    uint32_t aA[4], aB[4], aC[4], aD[4], b[NB][4];
+    ldsm_x4(aA, wa0);
+    if (!SINGLE) ldsm_x4(aB, wa1);
+    if (two) {
+      ldsm_x4(aC, wa0 + wsec);
+      if (!SINGLE) ldsm_x4(aD, wa1 + wsec);
+    }
+#pragma unroll
+    for (int nb = 0; nb < NB; ++nb) ldsm_x4(b[nb], ab[nb] + aoff);
+#pragma unroll
+    for (int nb = 0; nb < NB; ++nb) {
+      mma16816(acc[0][nb], aA, b[nb][0], b[nb][1]);
+      if (!SINGLE) mma16816(acc[1][nb], aB, b[nb][0], b[nb][1]);
+    }
+    if (two) {
 #pragma unroll
       for (int nb = 0; nb < NB; ++nb) {
-        const int n = nb * 8 + gq;
-        const bf16* pa = al + (size_t)n * astride + tl * 16;
-        const bool v = n < M;
-        b[nb][0] = v ? *reinterpret_cast<const uint32_t*>(pa) : 0u;
-        b[nb][1] = v ? *reinterpret_cast<const uint32_t*>(pa + 8) : 0u;
-        d[nb][0] = (v && two) ? *reinterpret_cast<const uint32_t*>(pa + ks * 16) : 0u;
-        d[nb][1] = (v && two) ? *reinterpret_cast<const uint32_t*>(pa + ks * 16 + 8) : 0u;
-      }
-      const uint32_t a0[4] = {w0.x, w1.x, w0.y, w1.y};
-      const uint32_t a1[4] = {x0.x, x1.x, x0.y, x1.y};
-#pragma unroll
-      for (int nb = 0; nb < NB; ++nb) {
-        mma16816(acc[0][nb], a0, b[nb][0], b[nb][1]);
-        mma16816(acc[1][nb], a1, d[nb][0], d[nb][1]);
+        if (SINGLE) {
+          mma16816(acc[1][nb], aC, b[nb][2], b[nb][3]);
+        } else {
+          mma16816(acc[0][nb], aC, b[nb][2], b[nb][3]);
+          mma16816(acc[1][nb], aD, b[nb][2], b[nb][3]);
+        }
       }
     }
-  } else {
-    for (int tl = tl0; tl < tiles; tl += ks) {
-      uint2 w0 = make_uint2(0, 0), w1 = make_uint2(0, 0), x0 = make_uint2(0, 0), x1 = make_uint2(0, 0);
-      if (vA0) w0 = *reinterpret_cast<const uint2*>(wl + ((size_t)tl * rows + rA0) * 32);
-      if (vA1) w1 = *reinterpret_cast<const uint2*>(wl + ((size_t)tl * rows + rA1) * 32);
-      if (vB0) x0 = *reinterpret_cast<const uint2*>(wl + ((size_t)tl * rows + rB0) * 32);
-      if (vB1) x1 = *reinterpret_cast<const uint2*>(wl + ((size_t)tl * rows + rB1) * 32);
-      uint32_t b[NB][2];
-#pragma unroll
-      for (int nb = 0; nb < NB; ++nb) {
-        const int n = nb * 8 + gq;
-        const bf16* pa = al + (size_t)n * astride + tl * 16;
-        const bool v = n < M;
-        b[nb][0] = v ? *reinterpret_cast<const uint32_t*>(pa) : 0u;
-        b[nb][1] = v ? *reinterpret_cast<const uint32_t*>(pa + 8) : 0u;
-      }
-      const uint32_t a0[4] = {w0.x, w1.x, w0.y, w1.y};
-      const uint32_t a1[4] = {x0.x, x1.x, x0.y, x1.y};
-#pragma unroll
-      for (int nb = 0; nb < NB; ++nb) {
-        mma16816(acc[0][nb], a0, b[nb][0], b[nb][1]);
-        if (mt1 >= 0) mma16816(acc[1][nb], a1, b[nb][0], b[nb][1]);
-      }
-    }
+    wa0 += wstep;
+    wa1 += wstep;
+    aoff += astep;
   }
 }
 
 // All chunks of one phase for this warp; partial sums -> red[kg][m][rows_pad].
 template <int NB>
-__device__ __forceinline__ void gemv_core(const StreamParams& p, const Phase& P, const Ctx& cx, const Geom& g, bool stream,
-                                          int astride, int rows_pad, uint32_t& it, uint32_t& ait) {
+__device__ __forceinline__ void gemv_core(const StreamParams& p, const Phase& P, Ctx& cx, const Geom& g, bool stream,
+                                          int astride, int rows_pad) {
   const int M = p.B;
   float acc[2][NB][4];
 #pragma unroll
@@ -251,37 +238,50 @@ __device__ __forceinline__ void gemv_core(const StreamParams& p, const Phase& P,
   const int mt0 = ng, mt1 = (ng + g.ns < g.mtiles) ? ng + g.ns : -1;
   const bool active = mt0 < g.mtiles;
   const bool single = mt1 < 0;
+  // per-lane ldmatrix row addresses: lane = 8*mat + r
+  const int mat = cx.lane >> 3, r8 = cx.lane & 7;
+  const uint32_t tile_bytes = (uint32_t)g.rows * 32u;
+  int ra0 = 16 * mt0 + (mat & 1) * 8 + r8, ra1 = 16 * (single ? mt0 : mt1) + (mat & 1) * 8 + r8;
+  if (ra0 >= g.rows) ra0 = 0;
+  if (ra1 >= g.rows) ra1 = 0;
+  const uint32_t offA0 = (uint32_t)((mat >> 1) * g.rows + ra0) * 16u;
+  const uint32_t offA1 = (uint32_t)((mat >> 1) * g.rows + ra1) * 16u;
+  uint32_t offB[NB];
+#pragma unroll
+  for (int nb = 0; nb < NB; ++nb)
+    offB[nb] = (uint32_t)((nb * 8 + r8) * astride + (mat >> 1) * g.ks * 16 + (mat & 1) * 8) * 2u;
+  const uint32_t ring0 = smem_u32(cx.ring), act0 = smem_u32(cx.actreg);
 
   for (int ch = 0; ch < g.nchunks; ++ch) {
     const int T0 = ch * g.tpc;
     const int tiles = min(g.tpc, g.ntiles - T0);
-    const uint32_t s = it % (uint32_t)p.n_slots;
-    mbar_wait(&cx.full[s], (it / (uint32_t)p.n_slots) & 1u);
-    const unsigned char* wslot = cx.ring + (size_t)s * p.slot_bytes;
-    const bf16* abase;
-    int acol0;
+    const uint32_t s = cx.slot;
+    mbar_wait(&cx.full[s], cx.slot_par);
+    uint32_t abase = act0;
     uint32_t as = 0;
     if (stream) {
-      as = ait & 1u;
-      mbar_wait(&cx.afull[as], (ait >> 1) & 1u);
-      abase = reinterpret_cast<const bf16*>(cx.actreg + (size_t)as * (p.act_region_bytes / 2));
-      acol0 = 0;
+      as = cx.aslot;
+      mbar_wait(&cx.afull[as], cx.aslot_par);
+      abase += as * (uint32_t)(p.act_region_bytes / 2);
     } else {
-      abase = reinterpret_cast<const bf16*>(cx.actreg);
-      acol0 = T0 * 16;
+      abase += (uint32_t)T0 * 32u;
     }
     if (active) {
       const int tl0 = (kg - T0) & (g.ks - 1);
-      if (single) mma_chunk<NB, true>(acc, wslot, abase, astride, acol0, tiles, tl0, g.ks, g.rows, mt0, -1, M, gq, tq);
-      else mma_chunk<NB, false>(acc, wslot, abase, astride, acol0, tiles, tl0, g.ks, g.rows, mt0, mt1, M, gq, tq);
+      const uint32_t wbase = ring0 + s * (uint32_t)p.slot_bytes;
+      uint32_t ab[NB];
+#pragma unroll
+      for (int nb = 0; nb < NB; ++nb) ab[nb] = abase + offB[nb];
+      if (single) mma_chunk<NB, true>(acc, wbase + offA0, wbase + offA0, ab, tiles, tl0, g.ks, tile_bytes);
+      else mma_chunk<NB, false>(acc, wbase + offA0, wbase + offA1, ab, tiles, tl0, g.ks, tile_bytes);
     }
     __syncwarp();
     if (cx.lane == 0) {
       mbar_arrive(&cx.empty[s]);
       if (stream) mbar_arrive(&cx.aempty[as]);
     }
-    ++it;
-    if (stream) ++ait;
+    if (++cx.slot == (uint32_t)p.n_slots) { cx.slot = 0; cx.slot_par ^= 1u; }
+    if (stream) { cx.aslot ^= 1u; if (cx.aslot == 0) cx.aslot_par ^= 1u; }
   }
   if (!active) return;
   if (single) {
@@ -308,8 +308,8 @@ __device__ __forceinline__ void gemv_core(const StreamParams& p, const Phase& P,
 }
 
 // ------------------------------------------------------------------ GEMV / skinny-GEMM phase
-__device__ __forceinline__ void gemv_phase(const StreamParams& p, const Phase& P, const Ctx& cx, uint32_t& it,
-                                           uint32_t& ait) {
+template <int NB>
+__device__ __forceinline__ void gemv_phase(const StreamParams& p, const Phase& P, Ctx& cx) {
   const int M = p.B, K = P.K;
   const bool stream = (P.act_mode == ACT_STREAM);
   const Geom g = csm_geom(P, cx.c);
@@ -322,11 +322,7 @@ __device__ __forceinline__ void gemv_phase(const StreamParams& p, const Phase& P
     astride = g.tpc * 16 + 8;
   }
   const int rows_pad = g.mtiles * 16 + 4;
-  if (g.rows > 0) {
-    if (M <= 8) gemv_core<1>(p, P, cx, g, stream, astride, rows_pad, it, ait);
-    else if (M <= 16) gemv_core<2>(p, P, cx, g, stream, astride, rows_pad, it, ait);
-    else gemv_core<4>(p, P, cx, g, stream, astride, rows_pad, it, ait);
-  }
+  if (g.rows > 0) gemv_core<NB>(p, P, cx, g, stream, astride, rows_pad);
   compute_sync();
 
   // ---- fused epilogues: thread -> (batch row m, granule u), granules padded to a power of two
@@ -761,6 +757,7 @@ __device__ __forceinline__ void attn_dec_phase(const StreamParams& p, const Phas
 
 extern __shared__ __align__(128) unsigned char csm_smem[];
 
+template <int NB, int REP>
 __global__ void __launch_bounds__(CSM_THREADS, 1) csm_stream_kernel(const StreamParams p) {
   if (p.stop_flag != nullptr && *p.stop_flag) return;   // generation already ended (set by an earlier launch)
 
@@ -782,6 +779,7 @@ __global__ void __launch_bounds__(CSM_THREADS, 1) csm_stream_kernel(const Stream
   cx.lane = threadIdx.x & 31;
   cx.c = blockIdx.x;
   cx.G = gridDim.x;
+  cx.slot = cx.slot_par = cx.aslot = cx.aslot_par = 0;
 
   if (cx.tid == 0) {
     for (int s = 0; s < CSM_MAX_SLOTS; ++s) {
@@ -816,7 +814,7 @@ __global__ void __launch_bounds__(CSM_THREADS, 1) csm_stream_kernel(const Stream
   if (cx.warp == CSM_COMPUTE_WARPS) {
     // ===================== weight stream producer =====================
     if (cx.lane == 0) {
-      uint32_t it = 0;
+      uint32_t s = 0, round = 0;
       for (int ph = p.phase_begin; ph < p.phase_end; ++ph) {
         const Phase P = p.phases[ph];
         if (P.type != PH_GEMV) continue;
@@ -825,12 +823,11 @@ __global__ void __launch_bounds__(CSM_THREADS, 1) csm_stream_kernel(const Stream
         for (int ch = 0; ch < g.nchunks; ++ch) {
           const int tiles = min(g.tpc, g.ntiles - ch * g.tpc);
           const uint32_t bytes = (uint32_t)tiles * g.rows * 32u;
-          const uint32_t s = it % (uint32_t)p.n_slots;
-          if (it >= (uint32_t)p.n_slots) mbar_wait(&cx.empty[s], ((it / (uint32_t)p.n_slots) - 1u) & 1u);
+          if (round > 0) mbar_wait(&cx.empty[s], (round - 1u) & 1u);
           mbar_expect_tx(&cx.full[s], bytes);
           bulk_g2s(cx.ring + (size_t)s * p.slot_bytes, src, bytes, &cx.full[s]);
           src += bytes;
-          ++it;
+          if (++s == (uint32_t)p.n_slots) { s = 0; ++round; }
         }
       }
     }
@@ -868,7 +865,6 @@ __global__ void __launch_bounds__(CSM_THREADS, 1) csm_stream_kernel(const Stream
   }
 
   // ===================== compute warps =====================
-  uint32_t it = 0, ait = 0;
   for (int ph = p.phase_begin; ph < p.phase_end; ++ph) {
     if (p.use_barrier && ph > p.phase_begin) {
       if (cx.tid == 0) grid_wait(p.bar_counter, (unsigned)(ph - p.phase_begin) * cx.G);
@@ -882,14 +878,8 @@ __global__ void __launch_bounds__(CSM_THREADS, 1) csm_stream_kernel(const Stream
     if (p.prof != nullptr && cx.c == 0 && cx.tid == 0) p.prof[2 * ph] = clock64();
     switch (P.type) {
       case PH_EMBED: embed_phase(p, cx); break;
-      case PH_GEMV: gemv_phase(p, P, cx, it, ait); break;
-      case PH_ATTN_BB: {
-        const int rep = p.bb.heads / p.bb.kv;
-        if (rep == 4) attn_bb_phase<4>(p, P, cx);
-        else if (rep == 2) attn_bb_phase<2>(p, P, cx);
-        else attn_bb_phase<1>(p, P, cx);
-        break;
-      }
+      case PH_GEMV: gemv_phase<NB>(p, P, cx); break;
+      case PH_ATTN_BB: attn_bb_phase<REP>(p, P, cx); break;
       case PH_ATTN_DEC: attn_dec_phase(p, P, cx); break;
       case PH_FINISH: finish_phase(p, cx); break;
     }
@@ -906,18 +896,33 @@ __global__ void __launch_bounds__(CSM_THREADS, 1) csm_stream_kernel(const Stream
 }
 
 // ------------------------------------------------------------------ host launch
+// One instantiation per (batch n-tiles, backbone GQA ratio): the kernel then carries a single GEMV and
+// attention variant, which keeps its instruction footprint small.
+typedef void (*StreamKernel)(const StreamParams);
+
+static StreamKernel pick_kernel(int nb, int rep) {
+#define CSM_PICK(NBV)                                                    \
+  switch (rep) {                                                         \
+    case 1: return csm_stream_kernel<NBV, 1>;                            \
+    case 2: return csm_stream_kernel<NBV, 2>;                            \
+    default: return csm_stream_kernel<NBV, 4>;                           \
+  }
+  if (nb <= 1) { CSM_PICK(1) }
+  if (nb <= 2) { CSM_PICK(2) }
+  CSM_PICK(4)
+#undef CSM_PICK
+}
+
 extern "C" cudaError_t csm_launch_stream(const StreamParams* p, int grid, size_t smem, cudaStream_t stream,
                                          int cooperative) {
-  static bool attr_set = false;
-  if (!attr_set) {
-    cudaError_t e = cudaFuncSetAttribute(csm_stream_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
-    if (e != cudaSuccess) return e;
-    attr_set = true;
-  }
+  const int nb = (p->B + 7) / 8, rep = p->bb.heads / p->bb.kv;
+  StreamKernel k = pick_kernel(nb, rep);
+  cudaError_t e = cudaFuncSetAttribute((const void*)k, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+  if (e != cudaSuccess) return e;
   if (cooperative) {
     void* args[] = {(void*)p};
-    return cudaLaunchCooperativeKernel((const void*)csm_stream_kernel, dim3(grid), dim3(CSM_THREADS), args, smem, stream);
+    return cudaLaunchCooperativeKernel((const void*)k, dim3(grid), dim3(CSM_THREADS), args, smem, stream);
   }
-  csm_stream_kernel<<<grid, CSM_THREADS, smem, stream>>>(*p);
+  k<<<grid, CSM_THREADS, smem, stream>>>(*p);
   return cudaGetLastError();
 }
