@@ -95,6 +95,8 @@ struct CsmCtx {
   int ph_head_c0 = 0;   // first phase of the "decoder part" of a frame (final norm + c0 head)
   int cache_len = 0;
   int stepped = 0;
+  int fuse_attn = 0;     // decoder attention computed inside the o_proj phase (max_batch <= 2)
+  int direct_mlp = 0;    // MLP activations staged whole in shared memory (max_batch <= 4)
   // shared-memory plan of the frame kernel (fixed at create time for max_batch)
   int m_alloc = 0, slot_bytes = 0, n_slots = 0, rope_bytes = 0, act_region = 0, red_bytes = 0, stream_tpc_max = 0;
   size_t smem_total = 0;
@@ -260,10 +262,17 @@ void add_layer_phases(CsmCtx* ctx, Stack& S, int stack, int l, int dec_pos, bool
   P.dec_pos = dec_pos;
   ctx->table.push_back(P);
   if (kv_only) return;
-  memset(&P, 0, sizeof P);
-  P.type = stack ? PH_ATTN_DEC : PH_ATTN_BB; P.stack = stack; P.layer = l; P.dec_pos = dec_pos;
-  ctx->table.push_back(P);
-  ctx->table.push_back(gemv(ACT_PLAIN, EPI_RESID, 1, d.H, nq, stack, l, L.p_o, at, nq, nullptr, h, d.H));
+  if (stack && ctx->fuse_attn) {
+    // small batch: every CTA computes the (tiny) decoder attention itself while staging o_proj's input
+    P = gemv(ACT_ATTN, EPI_RESID, 1, d.H, nq, stack, l, L.p_o, at, nq, nullptr, h, d.H);
+    P.dec_pos = dec_pos;
+    ctx->table.push_back(P);
+  } else {
+    memset(&P, 0, sizeof P);
+    P.type = stack ? PH_ATTN_DEC : PH_ATTN_BB; P.stack = stack; P.layer = l; P.dec_pos = dec_pos;
+    ctx->table.push_back(P);
+    ctx->table.push_back(gemv(ACT_PLAIN, EPI_RESID, 1, d.H, nq, stack, l, L.p_o, at, nq, nullptr, h, d.H));
+  }
   ctx->table.push_back(gemv(ACT_NORM, EPI_SWIGLU, 2, 2 * d.I, d.H, stack, l, L.p_gu, h, d.H, L.ln2, mlp, d.I));
   ctx->table.push_back(gemv(ACT_STREAM, EPI_RESID, 1, d.H, d.I, stack, l, L.p_down, mlp, d.I, nullptr, h, d.H));
 }
@@ -333,6 +342,13 @@ int plan_smem(CsmCtx* ctx) {
   }
   ctx->red_bytes = (red + 255) / 256 * 256;
   ctx->act_region = ctx->m_alloc * (kfull + 8) * 2;
+  if (ctx->direct_mlp) {
+    const int imax = ctx->bb.d.I > ctx->dec.d.I ? ctx->bb.d.I : ctx->dec.d.I;
+    const int need = ctx->Bmax * (imax + 8) * 2;
+    if (need > ctx->act_region) ctx->act_region = need;
+    for (Phase& P : ctx->table)
+      if (P.type == PH_GEMV && P.act_mode == ACT_STREAM) P.act_mode = ACT_PLAIN;
+  }
   ctx->act_region = (ctx->act_region + 255) / 256 * 256;
   const int limit = 227 * 1024;
   const int avail = limit - CSM_SM_HDR_BYTES - ctx->rope_bytes - ctx->red_bytes - ctx->act_region;
@@ -393,6 +409,7 @@ int launch_frame(CsmCtx* ctx, int B, int ph_begin, int ph_end, const long long* 
   p.m_alloc = ctx->m_alloc; p.slot_bytes = ctx->slot_bytes; p.n_slots = ctx->n_slots;
   p.rope_bytes = ctx->rope_bytes; p.act_region_bytes = ctx->act_region; p.red_bytes = ctx->red_bytes;
   p.prof = ctx->prof_on ? ctx->prof : nullptr;
+  p.n_phases_total = (int)ctx->table.size();
   if (!ctx->stepped) {
     p.phase_begin = ph_begin; p.phase_end = ph_end; p.use_barrier = 1;
     CK(cudaMemsetAsync(ctx->bar_counter, 0, sizeof(unsigned int), st));
@@ -592,10 +609,14 @@ int csm_create(const CsmShapes* sh, const CsmWeights* w, int max_batch, int max_
   CK(cudaMemsetAsync(ctx->n_frames, 0, 16, st));
   CK(cudaMemsetAsync(ctx->samples, 0, B * CSM_NQ * sizeof(int), st));
   CK(cudaMemsetAsync(ctx->fed, 0, B * CSM_NQ * sizeof(int), st));
+  ctx->fuse_attn = 0;   // measured slower (148 CTAs re-reading the same K/V lines from L2); kept behind CSM_FUSE_ATTN
+  ctx->direct_mlp = max_batch <= 4;
+  if (const char* e = getenv("CSM_FUSE_ATTN")) ctx->fuse_attn = atoi(e) != 0;
+  if (const char* e = getenv("CSM_DIRECT_MLP")) ctx->direct_mlp = atoi(e) != 0;
   build_table(ctx);
   if ((r = plan_smem(ctx))) return r;
   DA(ctx->d_table, ctx->table.size());
-  DA(ctx->prof, 2 * ctx->table.size());
+  DA(ctx->prof, 16 * ctx->table.size());
   CK(cudaMemcpyAsync(ctx->d_table, ctx->table.data(), ctx->table.size() * sizeof(Phase), cudaMemcpyHostToDevice, st));
   if (cublasCreate(&ctx->cublas) != CUBLAS_STATUS_SUCCESS) return fail(ctx, CSM_ECUDA, "cublasCreate failed");
   CK(cudaEventCreate(&ctx->ev0));
@@ -799,16 +820,16 @@ int csm_debug_run_phases(CsmCtx* ctx, const int64_t* ids, const int32_t* mask, i
 }
 
 int csm_debug_profile_frame(CsmCtx* ctx, int B, uint64_t* clocks_host, int32_t* info_host, void* stream) {
-  // one decode frame (ids from the last sampled frame) with per-phase clock64 stamps of CTA 0
+  // one decode frame (ids from the last sampled frame) with per-phase clock64 stamps of the first and last CTA
   if (!ctx || !clocks_host) return CSM_EINVAL;
   cudaStream_t st = (cudaStream_t)stream;
   const size_t n = ctx->table.size();
-  CK(cudaMemsetAsync(ctx->prof, 0, 2 * n * sizeof(unsigned long long), st));
+  CK(cudaMemsetAsync(ctx->prof, 0, 16 * n * sizeof(unsigned long long), st));
   ctx->prof_on = 1;
   int r = launch_frame(ctx, B, 0, (int)n, nullptr, nullptr, 0, nullptr, 0, 0, 0, ctx->cache_len, st);
   ctx->prof_on = 0;
   if (r) return r;
-  CK(cudaMemcpyAsync(clocks_host, ctx->prof, 2 * n * sizeof(unsigned long long), cudaMemcpyDeviceToHost, st));
+  CK(cudaMemcpyAsync(clocks_host, ctx->prof, 16 * n * sizeof(unsigned long long), cudaMemcpyDeviceToHost, st));
   CK(cudaStreamSynchronize(st));
   if (info_host)
     for (size_t i = 0; i < n; ++i) {

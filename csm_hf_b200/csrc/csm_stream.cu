@@ -43,7 +43,13 @@ struct Ctx {
   unsigned char* ring;
   int tid, warp, lane, c, G;
   uint32_t slot, slot_par, aslot, aslot_par;   // ring positions of the consumer side
+  unsigned long long* prof;                    // debug stamps of this phase (thread 0 of the first / last CTA) or null
 };
+
+#define CSM_STAMP(cx, i)                      \
+  do {                                        \
+    if ((cx).prof) (cx).prof[i] = clock64();  \
+  } while (0)
 
 __device__ __forceinline__ void grid_wait(const unsigned int* counter, unsigned target) {
   while (ld_acquire_u32(counter) < target) {
@@ -96,6 +102,84 @@ __device__ __forceinline__ void reduce_candidates(const StreamParams& p, const C
   compute_sync();
 }
 
+// ------------------------------------------------------------------ decoder attention (<= 32 positions, hd 128)
+// One warp per (sequence, query head).  Lane t owns cached position t for the
+// scores and output dims 4*lane.. for P.V; every load of a stage is issued before its first use.
+__device__ __forceinline__ void attn_dec_unit(const StreamParams& p, int layer, int dec_pos, int b, int head, bf16* dst,
+                                              int lane) {
+  constexpr int HD = 128;
+  const int nh = p.dec.heads, nk = p.dec.kv, rep = nh / nk;
+  const int T = dec_pos + 1;
+  {
+    const int kvh = head / rep;
+    const size_t kvbase = (((size_t)layer * p.Bmax + b) * nk + kvh) * (size_t)CSM_DEC_POS * HD;
+    const bf16* qp = p.q_dec + (size_t)b * (nh * HD) + head * HD;
+    const bf16* kp = p.kc_dec + kvbase + (size_t)lane * HD;
+    uint4 kq[HD / 8];
+    // q: lane l holds dims 4l..4l+3 (8 bytes), redistributed by shuffles below
+    const uint2 qmine = ldcg_u2(qp + lane * 4);
+    if (lane < T) {
+#pragma unroll
+      for (int ci = 0; ci < HD / 8; ++ci) kq[ci] = ldcg_u4(kp + ci * 8);
+    } else {
+#pragma unroll
+      for (int ci = 0; ci < HD / 8; ++ci) kq[ci] = make_uint4(0, 0, 0, 0);
+    }
+    // V rows (independent of the scores): 8 bytes per lane per position, first half issued with K
+    const bf16* vp = p.vc_dec + kvbase + lane * 4;
+    uint2 va[CSM_DEC_POS / 2];
+#pragma unroll
+    for (int t = 0; t < CSM_DEC_POS / 2; ++t) va[t] = t < T ? ldcg_u2(vp + (size_t)t * HD) : make_uint2(0, 0);
+    float d = 0.f;
+#pragma unroll
+    for (int ci = 0; ci < HD / 8; ++ci) {
+      // dims 8ci..8ci+7 of q live in lanes 2ci (first 4) and 2ci+1 (last 4)
+      const uint32_t q0 = __shfl_sync(0xffffffffu, qmine.x, 2 * ci), q1 = __shfl_sync(0xffffffffu, qmine.y, 2 * ci);
+      const uint32_t q2 = __shfl_sync(0xffffffffu, qmine.x, 2 * ci + 1), q3 = __shfl_sync(0xffffffffu, qmine.y, 2 * ci + 1);
+      const uint4 kv = kq[ci];
+      d += bf_lo(q0) * bf_lo(kv.x) + bf_hi(q0) * bf_hi(kv.x);
+      d += bf_lo(q1) * bf_lo(kv.y) + bf_hi(q1) * bf_hi(kv.y);
+      d += bf_lo(q2) * bf_lo(kv.z) + bf_hi(q2) * bf_hi(kv.z);
+      d += bf_lo(q3) * bf_lo(kv.w) + bf_hi(q3) * bf_hi(kv.w);
+    }
+    uint2 vb[CSM_DEC_POS / 2];
+#pragma unroll
+    for (int t = 0; t < CSM_DEC_POS / 2; ++t)
+      vb[t] = (t + CSM_DEC_POS / 2) < T ? ldcg_u2(vp + (size_t)(t + CSM_DEC_POS / 2) * HD) : make_uint2(0, 0);
+    const float sc = lane < T ? d * p.dec.scale : -INFINITY;
+    const float mx = warp_max(sc);
+    const float pe = (lane < T) ? __expf(sc - mx) : 0.f;
+    const float l = warp_sum(pe);
+    float o0 = 0.f, o1 = 0.f, o2 = 0.f, o3 = 0.f;
+#pragma unroll
+    for (int t = 0; t < CSM_DEC_POS / 2; ++t) {
+      const float pv = __shfl_sync(0xffffffffu, pe, t);
+      o0 += pv * bf_lo(va[t].x); o1 += pv * bf_hi(va[t].x);
+      o2 += pv * bf_lo(va[t].y); o3 += pv * bf_hi(va[t].y);
+    }
+#pragma unroll
+    for (int t = 0; t < CSM_DEC_POS / 2; ++t) {
+      const float pv = __shfl_sync(0xffffffffu, pe, t + CSM_DEC_POS / 2);
+      o0 += pv * bf_lo(vb[t].x); o1 += pv * bf_hi(vb[t].x);
+      o2 += pv * bf_lo(vb[t].y); o3 += pv * bf_hi(vb[t].y);
+    }
+    const float inv = 1.f / l;
+    uint2 ov = make_uint2(pack_bf16(o0 * inv, o1 * inv), pack_bf16(o2 * inv, o3 * inv));
+    *reinterpret_cast<uint2*>(dst + lane * 4) = ov;
+  }
+}
+
+
+// Separate-phase form (larger batches): units spread over the CTAs, result to global memory.
+__device__ __forceinline__ void attn_dec_phase(const StreamParams& p, const Phase& P, const Ctx& cx) {
+  const int nh = p.dec.heads;
+  const int nunits = p.B * nh;
+  for (int unit = cx.warp * cx.G + cx.c; unit < nunits; unit += CSM_COMPUTE_WARPS * cx.G) {
+    const int b = unit / nh, head = unit - b * nh;
+    attn_dec_unit(p, P.layer, P.dec_pos, b, head, p.attn_dec + (size_t)b * (nh * p.dec.hd) + head * p.dec.hd, cx.lane);
+  }
+}
+
 // ------------------------------------------------------------------ activation staging
 // Rows of the phase input -> shared memory [M][K+8] bf16, applying RMSNorm exactly as
 // LlamaRMSNorm.forward (hf modeling_llama.py:62-67): fp32 x*rsqrt(mean(x^2)+eps) -> bf16 -> *w -> bf16.
@@ -106,6 +190,38 @@ __device__ __forceinline__ void stage_act(const StreamParams& p, const Phase& P,
   const float eps = P.stack ? p.dec.eps : p.bb.eps;
   bf16* dst = reinterpret_cast<bf16*>(cx.actreg);
   if (P.act_mode == ACT_GATHER) reduce_candidates(p, cx, P.cb);
+  if (P.act_mode == ACT_ATTN) {
+    // decoder attention of every (sequence, head), computed redundantly by every CTA straight into the
+    // activation rows of the o_proj that consumes it (small batches only: saves a phase and a barrier)
+    const int nh = p.dec.heads;
+    for (int unit = cx.warp; unit < M * nh; unit += CSM_COMPUTE_WARPS) {
+      const int b = unit / nh, head = unit - b * nh;
+      attn_dec_unit(p, P.layer, P.dec_pos, b, head, dst + (size_t)b * astride + head * p.dec.hd, cx.lane);
+    }
+    return;
+  }
+  if (K > 2048) {
+    // wide plain rows (the MLP activations when they fit in shared memory): straight 16-byte copies
+    const int cpr = K >> 3;
+    for (int m = 0; m < M; ++m) {
+      const uint4* src = reinterpret_cast<const uint4*>(P.act + (size_t)m * P.act_stride);
+      uint4* d4 = reinterpret_cast<uint4*>(dst + (size_t)m * astride);
+      for (int c0 = cx.tid; c0 < cpr; c0 += 4 * CSM_COMPUTE_THREADS) {
+        uint4 v[4];
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          const int cc = c0 + j * CSM_COMPUTE_THREADS;
+          if (cc < cpr) v[j] = ldcg_u4(src + cc);
+        }
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          const int cc = c0 + j * CSM_COMPUTE_THREADS;
+          if (cc < cpr) d4[cc] = v[j];
+        }
+      }
+    }
+    return;
+  }
   const int tpr = K >> 3;                      // threads per row (K <= 2048 -> <= 256)
   const int rpp = CSM_COMPUTE_THREADS / tpr;   // rows per pass
   const int wpr = tpr >> 5;                    // warps per row (0 when a row is narrower than a warp)
@@ -169,8 +285,8 @@ __device__ __forceinline__ void stage_act(const StreamParams& p, const Phase& P,
 // One ring chunk holds this CTA's rows for `tiles` k16-tiles as [tile][k-half][row][8 bf16] (csm_pack.cu), so
 // the 16x16 A fragment of an m-tile is ONE ldmatrix.x4 (four conflict-free 8x8 matrices).  The B fragments
 // (8 batch rows x 16 k) of two k-tiles come from the activation rows with one more ldmatrix.x4.  Rows past the
-// CTA's last weight row and batch rows past M read arbitrary shared memory: they only feed accumulator
-// rows / columns that are never stored.
+// CTA's last weight row and batch rows past M re-read a valid row: they only feed accumulator rows /
+// columns that are never stored.
 __device__ __forceinline__ void ldsm_x4(uint32_t (&r)[4], uint32_t addr) {
   asm volatile("ldmatrix.sync.aligned.m8n8.x4.shared.b16 {%0,%1,%2,%3}, [%4];"
                : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3])
@@ -248,8 +364,10 @@ __device__ __forceinline__ void gemv_core(const StreamParams& p, const Phase& P,
   const uint32_t offA1 = (uint32_t)((mat >> 1) * g.rows + ra1) * 16u;
   uint32_t offB[NB];
 #pragma unroll
-  for (int nb = 0; nb < NB; ++nb)
-    offB[nb] = (uint32_t)((nb * 8 + r8) * astride + (mat >> 1) * g.ks * 16 + (mat & 1) * 8) * 2u;
+  for (int nb = 0; nb < NB; ++nb) {
+    const int n = nb * 8 + r8;   // batch rows past M re-read row M-1: their accumulator columns are never stored
+    offB[nb] = (uint32_t)((n < M ? n : M - 1) * astride + (mat >> 1) * g.ks * 16 + (mat & 1) * 8) * 2u;
+  }
   const uint32_t ring0 = smem_u32(cx.ring), act0 = smem_u32(cx.actreg);
 
   for (int ch = 0; ch < g.nchunks; ++ch) {
@@ -318,21 +436,29 @@ __device__ __forceinline__ void gemv_phase(const StreamParams& p, const Phase& P
     astride = K + 8;
     stage_act(p, P, cx, astride);
     compute_sync();
+    CSM_STAMP(cx, 4);   // activations staged
   } else {
     astride = g.tpc * 16 + 8;
   }
   const int rows_pad = g.mtiles * 16 + 4;
-  if (g.rows > 0) gemv_core<NB>(p, P, cx, g, stream, astride, rows_pad);
-  compute_sync();
-
-  // ---- fused epilogues: thread -> (batch row m, granule u), granules padded to a power of two
+  // epilogue mapping: thread -> (batch row m, granule u), granules padded to a power of two
   const int gran = P.gran;
   const int upc = g.rows / gran;
-  int up2 = 1;
-  while (up2 < upc) up2 <<= 1;
+  int up2 = 1, ush = 0;
+  while (up2 < upc) { up2 <<= 1; ++ush; }
   const int u = cx.tid & (up2 - 1);
-  const int mstep = up2 >= CSM_COMPUTE_THREADS ? 1 : CSM_COMPUTE_THREADS / up2;
-  const int m_first = up2 >= CSM_COMPUTE_THREADS ? 0 : cx.tid / up2;
+  const int mstep = up2 >= CSM_COMPUTE_THREADS ? 1 : CSM_COMPUTE_THREADS >> ush;
+  const int m_first = up2 >= CSM_COMPUTE_THREADS ? 0 : cx.tid >> ush;
+  // residual value of the first element this thread will update: fetched now, used after the MMAs
+  float resid0 = 0.f;
+  if (P.epi == EPI_RESID && u < upc && m_first < M)
+    resid0 = ldcg_bf16(P.out + (size_t)m_first * P.out_stride + g.row0 + u);
+  if (g.rows > 0) gemv_core<NB>(p, P, cx, g, stream, astride, rows_pad);
+  CSM_STAMP(cx, 5);     // this warp's MMAs done
+  compute_sync();
+  CSM_STAMP(cx, 6);     // all warps' MMAs done
+
+  // ---- fused epilogues
   const StackDims& sd = P.stack ? p.dec : p.bb;
   const int half = sd.hd >> 1;
   if (u < upc) {
@@ -353,7 +479,7 @@ __device__ __forceinline__ void gemv_phase(const StreamParams& p, const Phase& P
           break;
         case EPI_RESID: {   // hf modeling_llama.py:325,331: residual + f(x), both bf16
           bf16* o = P.out + (size_t)m * P.out_stride + gn;
-          float r = ldcg_bf16(o);
+          const float r = m == m_first ? resid0 : ldcg_bf16(o);
           *o = __float2bfloat16_rn(r + v0);
           break;
         }
@@ -686,73 +812,6 @@ __device__ __forceinline__ void attn_bb_phase(const StreamParams& p, const Phase
   }
 }
 
-// ------------------------------------------------------------------ decoder attention (<= 32 positions, hd 128)
-// One warp per (sequence, query head), spread over the CTAs.  Lane t owns cached position t for the
-// scores and output dims 4*lane.. for P.V; every load of a stage is issued before its first use.
-__device__ __forceinline__ void attn_dec_phase(const StreamParams& p, const Phase& P, const Ctx& cx) {
-  constexpr int HD = 128;
-  const int nh = p.dec.heads, nk = p.dec.kv, rep = nh / nk;
-  const int T = P.dec_pos + 1;
-  const int nunits = p.B * nh;
-  for (int unit = cx.warp * cx.G + cx.c; unit < nunits; unit += CSM_COMPUTE_WARPS * cx.G) {
-    const int b = unit / nh, head = unit - b * nh, kvh = head / rep;
-    const size_t kvbase = (((size_t)P.layer * p.Bmax + b) * nk + kvh) * (size_t)CSM_DEC_POS * HD;
-    const bf16* qp = p.q_dec + (size_t)b * (nh * HD) + head * HD;
-    const bf16* kp = p.kc_dec + kvbase + (size_t)cx.lane * HD;
-    uint4 kq[HD / 8];
-    // q: lane l holds dims 4l..4l+3 (8 bytes), redistributed by shuffles below
-    const uint2 qmine = ldcg_u2(qp + cx.lane * 4);
-    if (cx.lane < T) {
-#pragma unroll
-      for (int ci = 0; ci < HD / 8; ++ci) kq[ci] = ldcg_u4(kp + ci * 8);
-    } else {
-#pragma unroll
-      for (int ci = 0; ci < HD / 8; ++ci) kq[ci] = make_uint4(0, 0, 0, 0);
-    }
-    // V rows (independent of the scores): 8 bytes per lane per position, first half issued with K
-    const bf16* vp = p.vc_dec + kvbase + cx.lane * 4;
-    uint2 va[CSM_DEC_POS / 2];
-#pragma unroll
-    for (int t = 0; t < CSM_DEC_POS / 2; ++t) va[t] = t < T ? ldcg_u2(vp + (size_t)t * HD) : make_uint2(0, 0);
-    float d = 0.f;
-#pragma unroll
-    for (int ci = 0; ci < HD / 8; ++ci) {
-      // dims 8ci..8ci+7 of q live in lanes 2ci (first 4) and 2ci+1 (last 4)
-      const uint32_t q0 = __shfl_sync(0xffffffffu, qmine.x, 2 * ci), q1 = __shfl_sync(0xffffffffu, qmine.y, 2 * ci);
-      const uint32_t q2 = __shfl_sync(0xffffffffu, qmine.x, 2 * ci + 1), q3 = __shfl_sync(0xffffffffu, qmine.y, 2 * ci + 1);
-      const uint4 kv = kq[ci];
-      d += bf_lo(q0) * bf_lo(kv.x) + bf_hi(q0) * bf_hi(kv.x);
-      d += bf_lo(q1) * bf_lo(kv.y) + bf_hi(q1) * bf_hi(kv.y);
-      d += bf_lo(q2) * bf_lo(kv.z) + bf_hi(q2) * bf_hi(kv.z);
-      d += bf_lo(q3) * bf_lo(kv.w) + bf_hi(q3) * bf_hi(kv.w);
-    }
-    uint2 vb[CSM_DEC_POS / 2];
-#pragma unroll
-    for (int t = 0; t < CSM_DEC_POS / 2; ++t)
-      vb[t] = (t + CSM_DEC_POS / 2) < T ? ldcg_u2(vp + (size_t)(t + CSM_DEC_POS / 2) * HD) : make_uint2(0, 0);
-    const float sc = cx.lane < T ? d * p.dec.scale : -INFINITY;
-    const float mx = warp_max(sc);
-    const float pe = (cx.lane < T) ? __expf(sc - mx) : 0.f;
-    const float l = warp_sum(pe);
-    float o0 = 0.f, o1 = 0.f, o2 = 0.f, o3 = 0.f;
-#pragma unroll
-    for (int t = 0; t < CSM_DEC_POS / 2; ++t) {
-      const float pv = __shfl_sync(0xffffffffu, pe, t);
-      o0 += pv * bf_lo(va[t].x); o1 += pv * bf_hi(va[t].x);
-      o2 += pv * bf_lo(va[t].y); o3 += pv * bf_hi(va[t].y);
-    }
-#pragma unroll
-    for (int t = 0; t < CSM_DEC_POS / 2; ++t) {
-      const float pv = __shfl_sync(0xffffffffu, pe, t + CSM_DEC_POS / 2);
-      o0 += pv * bf_lo(vb[t].x); o1 += pv * bf_hi(vb[t].x);
-      o2 += pv * bf_lo(vb[t].y); o3 += pv * bf_hi(vb[t].y);
-    }
-    const float inv = 1.f / l;
-    uint2 ov = make_uint2(pack_bf16(o0 * inv, o1 * inv), pack_bf16(o2 * inv, o3 * inv));
-    *reinterpret_cast<uint2*>(p.attn_dec + (size_t)b * (nh * HD) + head * HD + cx.lane * 4) = ov;
-  }
-}
-
 }  // namespace
 
 extern __shared__ __align__(128) unsigned char csm_smem[];
@@ -866,8 +925,13 @@ __global__ void __launch_bounds__(CSM_THREADS, 1) csm_stream_kernel(const Stream
 
   // ===================== compute warps =====================
   for (int ph = p.phase_begin; ph < p.phase_end; ++ph) {
+    unsigned long long* prof = nullptr;   // debug stamps of the first and the last CTA: [cta][phase][8]
+    if (p.prof != nullptr && cx.tid == 0 && (cx.c == 0 || cx.c == cx.G - 1))
+      prof = p.prof + ((size_t)(cx.c == 0 ? 0 : 1) * p.n_phases_total + ph) * 8;
+    cx.prof = prof;
     if (p.use_barrier && ph > p.phase_begin) {
       if (cx.tid == 0) grid_wait(p.bar_counter, (unsigned)(ph - p.phase_begin) * cx.G);
+      if (prof) prof[0] = clock64();     // barrier observed
       compute_sync();
     }
     // descriptor of this phase is in shared memory; fetch the next one while this phase runs
@@ -875,7 +939,7 @@ __global__ void __launch_bounds__(CSM_THREADS, 1) csm_stream_kernel(const Stream
     uint4 nxt = make_uint4(0, 0, 0, 0);
     const bool fetch = cx.warp == CSM_COMPUTE_WARPS - 1 && cx.lane < 8 && ph + 1 < p.phase_end;
     if (fetch) nxt = __ldg(reinterpret_cast<const uint4*>(p.phases + ph + 1) + cx.lane);
-    if (p.prof != nullptr && cx.c == 0 && cx.tid == 0) p.prof[2 * ph] = clock64();
+    if (prof) prof[1] = clock64();       // phase body starts
     switch (P.type) {
       case PH_EMBED: embed_phase(p, cx); break;
       case PH_GEMV: gemv_phase<NB>(p, P, cx); break;
@@ -883,15 +947,16 @@ __global__ void __launch_bounds__(CSM_THREADS, 1) csm_stream_kernel(const Stream
       case PH_ATTN_DEC: attn_dec_phase(p, P, cx); break;
       case PH_FINISH: finish_phase(p, cx); break;
     }
-    if (p.prof != nullptr && cx.c == 0 && cx.tid == 0) p.prof[2 * ph + 1] = clock64();
+    if (prof) prof[2] = clock64();       // this thread's share of the body done
     if (fetch) reinterpret_cast<uint4*>(&cx.desc[(ph + 1) & 1])[cx.lane] = nxt;
     if (ph + 1 < p.phase_end) {
       compute_sync();
       if (p.use_barrier && cx.tid == 0) {
-        __threadfence();
-        atomicAdd(p.bar_counter, 1u);
+        // release: everything this CTA wrote (ordered before by the CTA barrier) becomes visible before the count
+        asm volatile("red.release.gpu.global.add.u32 [%0], 1;" ::"l"(p.bar_counter) : "memory");
       }
     }
+    if (prof) prof[3] = clock64();       // arrived at the grid barrier
   }
 }
 

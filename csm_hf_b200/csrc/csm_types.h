@@ -17,7 +17,7 @@ typedef __nv_bfloat16 bf16;
 #define CSM_SM_HDR_BYTES 2048   // mbarriers, phase-descriptor slots, small scratch
 
 enum PhaseType { PH_EMBED = 0, PH_GEMV = 1, PH_ATTN_BB = 2, PH_ATTN_DEC = 3, PH_FINISH = 4 };
-enum ActMode { ACT_NORM = 0, ACT_PLAIN = 1, ACT_GATHER = 2, ACT_STREAM = 3 };
+enum ActMode { ACT_NORM = 0, ACT_PLAIN = 1, ACT_GATHER = 2, ACT_STREAM = 3, ACT_ATTN = 4 };
 enum EpiMode { EPI_STORE = 0, EPI_RESID = 1, EPI_SWIGLU = 2, EPI_QKV = 3, EPI_HEAD = 4 };
 
 // One step of the per-frame program.  A frame is ~800 of these executed in order by every
@@ -90,7 +90,8 @@ struct StreamParams {
   int m_alloc;                  // activation rows rounded up to 8
   int slot_bytes, n_slots;
   int rope_bytes, act_region_bytes, red_bytes;
-  unsigned long long* prof;     // debug: CTA 0 writes clock64 at [2*ph] phase start, [2*ph+1] phase end
+  unsigned long long* prof;     // debug: clock64 stamps [2 CTAs (first,last)][n_phases_total][4], see csm_stream.cu
+  int n_phases_total;
 };
 
 // Row split and chunking of one weight matrix for one CTA.

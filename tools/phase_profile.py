@@ -37,28 +37,41 @@ def main():
     print(f"decode frame (events): {ms / n:.3f} ms")
     e = model.engine()
     nph = e.info(2)
-    clocks = (C.c_uint64 * (2 * nph))()
+    clocks = (C.c_uint64 * (16 * nph))()
     info = (C.c_int32 * (4 * nph))()
     for _ in range(2):
         e.call(e.lib.csm_debug_profile_frame, a.batch, clocks, info, e._stream())
-    t = list(clocks)
-    total_cyc = t[2 * nph - 1] - t[0]
-    mhz = total_cyc / (ms / n * 1000.0)
-    print(f"frame = {total_cyc} cycles of CTA 0  (~{mhz:.0f} MHz if the profiled frame took the same time)")
-    body, wait, cnt = defaultdict(float), defaultdict(float), defaultdict(int)
-    for ph in range(nph):
-        ty, ep, stack, am = info[4 * ph], info[4 * ph + 1], info[4 * ph + 2], info[4 * ph + 3]
-        kind = TYPES[ty] if ty != 1 else ("dec " if stack else "bb  ") + EPI[ep] + (" [K-stream]" if am == 3 else "")
-        b = t[2 * ph + 1] - t[2 * ph]
-        w = t[2 * ph] - t[2 * ph - 1] if ph > 0 else 0
-        body[kind] += b
-        wait[kind] += w
-        cnt[kind] += 1
-    print(f"{'phase kind':34s} {'n':>4s} {'body us':>9s} {'wait us':>9s} {'total ms':>9s} {'share':>6s}")
-    for k in sorted(cnt, key=lambda k: -(body[k] + wait[k])):
-        tot = body[k] + wait[k]
-        print(f"{k:34s} {cnt[k]:4d} {body[k] / cnt[k] / mhz:9.2f} {wait[k] / cnt[k] / mhz:9.2f} "
-              f"{tot / mhz / 1000:9.3f} {100 * tot / total_cyc:5.1f}%")
+    for cta, label in ((0, "first CTA"), (1, "last CTA")):
+        t = [list(clocks[(cta * nph + ph) * 8:(cta * nph + ph) * 8 + 8]) for ph in range(nph)]
+        total_cyc = t[nph - 1][2] - t[0][1]
+        mhz = total_cyc / (ms / n * 1000.0)
+        print(f"{label}: frame = {total_cyc} cycles (~{mhz:.0f} MHz if the profiled frame took the same time), {nph} phases")
+        keys = ("body", "sync", "arrive", "poll", "bsync")
+        sub = {k: defaultdict(float) for k in ("stage", "mma", "msync", "epi")}
+        acc = {k: defaultdict(float) for k in keys}
+        cnt = defaultdict(int)
+        for ph in range(nph):
+            ty, ep, stack, am = info[4 * ph], info[4 * ph + 1], info[4 * ph + 2], info[4 * ph + 3]
+            kind = TYPES[ty] if ty != 1 else ("dec " if stack else "bb  ") + EPI[ep] + {3: " [K-stream]", 4: " [+attn]"}.get(am, "")
+            cnt[kind] += 1
+            acc["body"][kind] += t[ph][2] - t[ph][1]
+            if ty == 1 and t[ph][6]:
+                s4 = t[ph][4] or t[ph][1]
+                sub["stage"][kind] += s4 - t[ph][1]
+                sub["mma"][kind] += t[ph][5] - s4
+                sub["msync"][kind] += t[ph][6] - t[ph][5]
+                sub["epi"][kind] += t[ph][2] - t[ph][6]
+            if ph + 1 < nph:
+                acc["arrive"][kind] += t[ph][3] - t[ph][2]            # CTA sync + fence + atomic
+                acc["poll"][kind] += t[ph + 1][0] - t[ph][3]          # waiting for the other CTAs
+                acc["bsync"][kind] += t[ph + 1][1] - t[ph + 1][0]     # CTA sync + descriptor after the barrier
+        print(f"{'phase kind':30s} {'n':>4s} {'body us':>8s} {'arrive':>7s} {'poll':>7s} {'bsync':>7s} {'total ms':>9s} {'share':>6s}  | {'stage':>6s} {'mma':>6s} {'msync':>6s} {'epi':>6s}")
+        for k in sorted(cnt, key=lambda k: -sum(acc[x][k] for x in keys)):
+            tot = sum(acc[x][k] for x in keys)
+            c = cnt[k]
+            print(f"{k:30s} {c:4d} {acc['body'][k] / c / mhz:8.2f} {acc['arrive'][k] / c / mhz:7.2f} "
+                  f"{acc['poll'][k] / c / mhz:7.2f} {acc['bsync'][k] / c / mhz:7.2f} {tot / mhz / 1000:9.3f} {100 * tot / total_cyc:5.1f}%"
+                  + (f"  | {sub['stage'][k] / c / mhz:6.2f} {sub['mma'][k] / c / mhz:6.2f} {sub['msync'][k] / c / mhz:6.2f} {sub['epi'][k] / c / mhz:6.2f}" if k in sub["mma"] else ""))
 
 
 if __name__ == "__main__":
