@@ -33,7 +33,9 @@ cudaError_t csm_rope_kv_rows_launch(bf16* qkv, int S, int pos0, int b0, int head
                                     cudaStream_t st);
 cudaError_t csm_swiglu_rows_launch(const bf16* gu, int I, bf16* act, long long rows, cudaStream_t st);
 cudaError_t csm_add_rows_launch(bf16* h, const bf16* y, long long n, cudaStream_t st);
-cudaError_t csm_take_last_rows_launch(const bf16* h, int S, int H, bf16* dst, int b0, int nseq, cudaStream_t st);
+cudaError_t csm_take_last_rows_launch(const bf16* h, int S, int H, uint32_t* dst, int b0, int nseq, uint32_t tag,
+                                      cudaStream_t st);
+cudaError_t csm_untag_rows_launch(const uint32_t* src, long long src_stride, int cols, int rows, bf16* dst, cudaStream_t st);
 cudaError_t csm_i64_to_i32_launch(const long long* src, int* dst, int n, cudaStream_t st);
 cudaError_t csm_i32_to_i64_launch(const int* src, long long* dst, int n, cudaStream_t st);
 cudaError_t csm_flash_prefill_launch(const bf16* qkv, int S, int pos0, int b0, int nseq, int heads, int kv,
@@ -71,12 +73,19 @@ struct CsmCtx {
   std::vector<bf16*> p_heads;
   // workspace
   bf16 *kc_bb = nullptr, *vc_bb = nullptr, *kc_dec = nullptr, *vc_dec = nullptr;
-  bf16 *h_bb = nullptr, *h_dec = nullptr, *q_bb = nullptr, *q_dec = nullptr, *attn_bb = nullptr, *attn_dec = nullptr;
-  bf16 *mlp_bb = nullptr, *mlp_dec = nullptr, *last_h = nullptr, *c0_logits = nullptr, *cb_logits = nullptr;
+  // inter-phase vectors: tagged words (csm_common.cuh), one uint32 per element
+  uint32_t *h_bb = nullptr, *h_dec = nullptr, *q_bb = nullptr, *q_dec = nullptr, *attn_bb = nullptr, *attn_dec = nullptr;
+  uint32_t *mlp_bb = nullptr, *mlp_dec = nullptr;   // tagged words, or plain bf16 when the down_proj input is TMA-streamed
+  bf16 *last_h = nullptr, *c0_logits = nullptr, *cb_logits = nullptr;
+  std::vector<std::pair<void*, size_t>> tagged;     // buffers to clear when the 16-bit tag epoch wraps
+  unsigned int tagbase = 1;                          // tag of phase ph of the next frame = tagbase + ph (1..65535)
+  int l2_ahead = 256 * 1024;
+  int repl = 1;                                      // copies of every tagged vector (StreamParams::repl)
+  int evict_first = 1;
   float* attn_part = nullptr;
   int nsplit_max = 0;
   unsigned int *attn_cnt = nullptr, *bar_counter = nullptr;
-  float2* cand = nullptr;
+  unsigned long long* cand = nullptr;
   int *samples = nullptr, *fed = nullptr, *stop_flag = nullptr, *n_frames = nullptr;
   unsigned long long* prof = nullptr;
   int prof_on = 0;
@@ -240,41 +249,47 @@ int build_stack(CsmCtx* ctx, Stack& S, const CsmLlamaShape& sh, const void* cons
   return 0;
 }
 
-Phase gemv(int act_mode, int epi, int gran, int N, int K, int stack, int layer, const bf16* w, const bf16* act,
-           int act_stride, const bf16* norm_w, bf16* out, int out_stride) {
+Phase gemv(int act_mode, int epi, int gran, int N, int K, int stack, int layer, const bf16* w, const void* act,
+           int act_stride, const bf16* norm_w, void* out, int out_stride, int src_ph, int res_ph = 0) {
   Phase P;
   memset(&P, 0, sizeof P);
   P.type = PH_GEMV; P.act_mode = act_mode; P.epi = epi; P.gran = gran; P.N = N; P.K = K; P.stack = stack;
-  P.layer = layer; P.w = w; P.act = act; P.act_stride = act_stride; P.norm_w = norm_w; P.out = out;
-  P.out_stride = out_stride;
+  P.layer = layer; P.w = w; P.act = (const bf16*)act; P.act_stride = act_stride; P.norm_w = norm_w; P.out = (bf16*)out;
+  P.out_stride = out_stride; P.src_ph = src_ph; P.res_ph = res_ph;
   return P;
 }
 
-void add_layer_phases(CsmCtx* ctx, Stack& S, int stack, int l, int dec_pos, bool kv_only) {
+// One transformer layer.  h_ph: index of the phase that last wrote the residual stream (in/out).
+void add_layer_phases(CsmCtx* ctx, Stack& S, int stack, int l, int dec_pos, bool kv_only, int& h_ph) {
   const StackDims& d = S.d;
   LayerW& L = S.layers[l];
-  bf16* h = stack ? ctx->h_dec : ctx->h_bb;
-  bf16* qb = stack ? ctx->q_dec : ctx->q_bb;
-  bf16* at = stack ? ctx->attn_dec : ctx->attn_bb;
-  bf16* mlp = stack ? ctx->mlp_dec : ctx->mlp_bb;
+  uint32_t* h = stack ? ctx->h_dec : ctx->h_bb;
+  uint32_t* qb = stack ? ctx->q_dec : ctx->q_bb;
+  uint32_t* at = stack ? ctx->attn_dec : ctx->attn_bb;
+  uint32_t* mlp = stack ? ctx->mlp_dec : ctx->mlp_bb;
   const int nq = d.heads * d.hd, nkv = d.kv * d.hd;
-  Phase P = gemv(ACT_NORM, EPI_QKV, 2, nq + 2 * nkv, d.H, stack, l, L.p_qkv, h, d.H, L.ln1, qb, nq);
+  auto idx = [&]() { return (int)ctx->table.size(); };
+  const int iq = idx();
+  Phase P = gemv(ACT_NORM, EPI_QKV, 2, nq + 2 * nkv, d.H, stack, l, L.p_qkv, h, d.H, L.ln1, qb, nq + 2 * nkv, h_ph);
   P.dec_pos = dec_pos;
   ctx->table.push_back(P);
   if (kv_only) return;
-  if (stack && ctx->fuse_attn) {
-    // small batch: every CTA computes the (tiny) decoder attention itself while staging o_proj's input
-    P = gemv(ACT_ATTN, EPI_RESID, 1, d.H, nq, stack, l, L.p_o, at, nq, nullptr, h, d.H);
-    P.dec_pos = dec_pos;
-    ctx->table.push_back(P);
-  } else {
-    memset(&P, 0, sizeof P);
-    P.type = stack ? PH_ATTN_DEC : PH_ATTN_BB; P.stack = stack; P.layer = l; P.dec_pos = dec_pos;
-    ctx->table.push_back(P);
-    ctx->table.push_back(gemv(ACT_PLAIN, EPI_RESID, 1, d.H, nq, stack, l, L.p_o, at, nq, nullptr, h, d.H));
-  }
-  ctx->table.push_back(gemv(ACT_NORM, EPI_SWIGLU, 2, 2 * d.I, d.H, stack, l, L.p_gu, h, d.H, L.ln2, mlp, d.I));
-  ctx->table.push_back(gemv(ACT_STREAM, EPI_RESID, 1, d.H, d.I, stack, l, L.p_down, mlp, d.I, nullptr, h, d.H));
+  const int ia = idx();
+  memset(&P, 0, sizeof P);
+  P.type = stack ? PH_ATTN_DEC : PH_ATTN_BB; P.stack = stack; P.layer = l; P.dec_pos = dec_pos; P.src_ph = iq;
+  ctx->table.push_back(P);
+  const int io = idx();
+  ctx->table.push_back(gemv(ACT_PLAIN, EPI_RESID, 1, d.H, nq, stack, l, L.p_o, at, nq, nullptr, h, d.H, ia, h_ph));
+  const int ig = idx();
+  P = gemv(ACT_NORM, EPI_SWIGLU, 2, 2 * d.I, d.H, stack, l, L.p_gu, h, d.H, L.ln2, mlp, d.I, io);
+  if (!ctx->direct_mlp) P.flags |= CSM_PF_OUT_PLAIN | CSM_PF_BAR_OUT;
+  ctx->table.push_back(P);
+  const int id = idx();
+  P = gemv(ctx->direct_mlp ? ACT_PLAIN : ACT_STREAM, EPI_RESID, 1, d.H, d.I, stack, l, L.p_down, mlp, d.I, nullptr, h, d.H,
+           ig, io);
+  if (!ctx->direct_mlp) P.flags |= CSM_PF_BAR_IN;
+  ctx->table.push_back(P);
+  h_ph = id;
 }
 
 void build_table(CsmCtx* ctx) {
@@ -285,27 +300,34 @@ void build_table(CsmCtx* ctx) {
   memset(&P, 0, sizeof P);
   P.type = PH_EMBED;
   ctx->table.push_back(P);
-  for (int l = 0; l < b.L; ++l) add_layer_phases(ctx, ctx->bb, 0, l, 0, false);
+  int hb_ph = 0;
+  for (int l = 0; l < b.L; ++l) add_layer_phases(ctx, ctx->bb, 0, l, 0, false, hb_ph);
   ctx->ph_head_c0 = (int)ctx->table.size();
   // final norm (-> last_hidden_state) + codebook-0 head + greedy sample (modeling_csm.py:361-365,531-532)
-  P = gemv(ACT_NORM, EPI_HEAD, 1, ctx->V, b.H, 0, 0, ctx->p_c0, ctx->h_bb, b.H, ctx->bb.norm, ctx->c0_logits, ctx->V);
+  int head_ph = (int)ctx->table.size();
+  P = gemv(ACT_NORM, EPI_HEAD, 1, ctx->V, b.H, 0, 0, ctx->p_c0, ctx->h_bb, b.H, ctx->bb.norm, ctx->c0_logits, ctx->V, hb_ph);
   P.cb = 0;
   P.norm_out = ctx->last_h;
   ctx->table.push_back(P);
   for (int pos = 0; pos < CSM_DEC_POS; ++pos) {
-    // projection of last_h (pos 0) or of the previous codebook's embedding (modeling_csm.py:535-542,564-565)
-    if (pos == 0)
-      P = gemv(ACT_PLAIN, EPI_STORE, 1, d.H, b.H, 1, 0, ctx->p_proj, ctx->last_h, b.H, nullptr, ctx->h_dec, d.H);
-    else {
-      P = gemv(ACT_GATHER, EPI_STORE, 1, d.H, b.H, 1, 0, ctx->p_proj, ctx->audio_emb, b.H, nullptr, ctx->h_dec, d.H);
+    // projection of last_h (pos 0: the backbone's final norm is recomputed from the residual stream, which is
+    // bit-identical to reading last_h and saves a dependency) or of the previous codebook's embedding
+    // (modeling_csm.py:535-542,564-565)
+    int hd_ph = (int)ctx->table.size();
+    if (pos == 0) {
+      P = gemv(ACT_NORM, EPI_STORE, 1, d.H, b.H, 0, 0, ctx->p_proj, ctx->h_bb, b.H, ctx->bb.norm, ctx->h_dec, d.H, hb_ph);
+    } else {
+      P = gemv(ACT_GATHER, EPI_STORE, 1, d.H, b.H, 1, 0, ctx->p_proj, ctx->audio_emb, b.H, nullptr, ctx->h_dec, d.H, 0,
+               head_ph);
       P.cb = pos - 1;
     }
     ctx->table.push_back(P);
-    for (int l = 0; l < d.L; ++l) add_layer_phases(ctx, ctx->dec, 1, l, pos, pos == 0 && l == d.L - 1);
+    for (int l = 0; l < d.L; ++l) add_layer_phases(ctx, ctx->dec, 1, l, pos, pos == 0 && l == d.L - 1, hd_ph);
     if (pos >= 1) {
       // audio_head[pos-1] on the decoder's final-norm output, greedy sample (modeling_csm.py:557-560)
+      head_ph = (int)ctx->table.size();
       P = gemv(ACT_NORM, EPI_HEAD, 1, ctx->V, d.H, 1, 0, ctx->p_heads[pos - 1], ctx->h_dec, d.H, ctx->dec.norm,
-               ctx->cb_logits + (size_t)(pos - 1) * ctx->V, (CSM_NQ - 1) * ctx->V);
+               ctx->cb_logits + (size_t)(pos - 1) * ctx->V, (CSM_NQ - 1) * ctx->V, hd_ph);
       P.cb = pos;
       ctx->table.push_back(P);
     }
@@ -313,7 +335,13 @@ void build_table(CsmCtx* ctx) {
   // sample codebook 31, publish the frame, stop rule (modeling_csm.py:657-666)
   memset(&P, 0, sizeof P);
   P.type = PH_FINISH;
+  P.res_ph = head_ph;
   ctx->table.push_back(P);
+  int nbar = 0;
+  for (Phase& Q : ctx->table) {
+    if (Q.flags & CSM_PF_BAR_IN) ++nbar;
+    Q.bar_idx = nbar;
+  }
 }
 
 // Shared-memory plan of the frame kernel for max_batch sequences, and the per-phase row split /
@@ -346,8 +374,6 @@ int plan_smem(CsmCtx* ctx) {
     const int imax = ctx->bb.d.I > ctx->dec.d.I ? ctx->bb.d.I : ctx->dec.d.I;
     const int need = ctx->Bmax * (imax + 8) * 2;
     if (need > ctx->act_region) ctx->act_region = need;
-    for (Phase& P : ctx->table)
-      if (P.type == PH_GEMV && P.act_mode == ACT_STREAM) P.act_mode = ACT_PLAIN;
   }
   ctx->act_region = (ctx->act_region + 255) / 256 * 256;
   const int limit = 227 * 1024;
@@ -387,6 +413,17 @@ int plan_smem(CsmCtx* ctx) {
   return 0;
 }
 
+// Tags are 16 bits: when the next frame's tags would pass 65535, clear every tagged buffer (tag 0 = never
+// written) and restart at 1.  Happens once every ~80 frames; a few hundred KB of stream-ordered memsets.
+int begin_epoch(CsmCtx* ctx, cudaStream_t st) {
+  if (ctx->tagbase + ctx->table.size() > 65535u) {
+    for (auto& t : ctx->tagged) CK(cudaMemsetAsync(t.first, 0, t.second, st));
+    ctx->tagbase = 1;
+  }
+  return 0;
+}
+void end_epoch(CsmCtx* ctx) { ctx->tagbase += (unsigned)ctx->table.size(); }
+
 int launch_frame(CsmCtx* ctx, int B, int ph_begin, int ph_end, const long long* ids, const int* mask, int forced,
                  long long* out_frames, long long out_stride, long long out_off, int stop_on_zeros, int pos,
                  cudaStream_t st) {
@@ -410,6 +447,10 @@ int launch_frame(CsmCtx* ctx, int B, int ph_begin, int ph_end, const long long* 
   p.rope_bytes = ctx->rope_bytes; p.act_region_bytes = ctx->act_region; p.red_bytes = ctx->red_bytes;
   p.prof = ctx->prof_on ? ctx->prof : nullptr;
   p.n_phases_total = (int)ctx->table.size();
+  p.tagbase = ctx->tagbase;
+  p.l2_ahead_bytes = ctx->l2_ahead;
+  p.repl = ctx->repl;
+  p.evict_first = ctx->evict_first;
   if (!ctx->stepped) {
     p.phase_begin = ph_begin; p.phase_end = ph_end; p.use_barrier = 1;
     CK(cudaMemsetAsync(ctx->bar_counter, 0, sizeof(unsigned int), st));
@@ -491,7 +532,10 @@ int prefill(CsmCtx* ctx, const long long* ids, const int* mask, int B, int S, cu
       CK(csm_add_rows_launch(ctx->pf_h, ctx->pf_y, (long long)R * d.H, st));
       ctx->launches += 7;
     }
-    CK(csm_take_last_rows_launch(ctx->pf_h, S, d.H, ctx->h_bb, b0, nseq, st));
+    // hand the last position's residual row to the frame kernel as tagged words of the last backbone phase
+    for (int rr = 0; rr < ctx->repl; ++rr)
+      CK(csm_take_last_rows_launch(ctx->pf_h, S, d.H, ctx->h_bb + (size_t)rr * ctx->Bmax * d.H, b0, nseq,
+                                   (ctx->tagbase + (unsigned)(ctx->ph_head_c0 - 1)) & 0xffffu, st));
     ctx->launches += 2;
   }
   return 0;
@@ -509,6 +553,7 @@ int frame_impl(CsmCtx* ctx, const long long* ids, const int* mask, int B, int S,
     forced = 1;
   }
   int r;
+  if ((r = begin_epoch(ctx, st))) return r;
   if (S == 1) {
     r = launch_frame(ctx, B, 0, (int)ctx->table.size(), ids, mask, forced, out_frames, out_stride, out_off, stop_on_zeros,
                      ctx->cache_len, st);
@@ -519,6 +564,7 @@ int frame_impl(CsmCtx* ctx, const long long* ids, const int* mask, int B, int S,
                      out_off, stop_on_zeros, ctx->cache_len + S - 1, st);
   }
   if (r) return r;
+  end_epoch(ctx);
   ctx->cache_len += S;
   return 0;
 }
@@ -558,6 +604,7 @@ int csm_create(const CsmShapes* sh, const CsmWeights* w, int max_batch, int max_
   int major = 0;
   CK(cudaDeviceGetAttribute(&major, cudaDevAttrComputeCapabilityMajor, ctx->device));
   if (major != 10) return fail(ctx, CSM_EUNSUPPORTED, "libcsm_b200 is built for sm_100a only (device is sm_%d)", major);
+  if (ctx->sms > 160) return fail(ctx, CSM_EUNSUPPORTED, "more than 160 SMs (%d): candidate reduction assumes <= 160 CTAs", ctx->sms);
   ctx->G = ctx->sms;
   if (const char* e = getenv("CSM_GRID")) {
     int g = atoi(e);
@@ -590,20 +637,35 @@ int csm_create(const CsmShapes* sh, const CsmWeights* w, int max_batch, int max_
   DA(ctx->vc_bb, (size_t)b.L * B * b.kv * max_ctx * b.hd);
   DA(ctx->kc_dec, (size_t)d.L * B * d.kv * CSM_DEC_POS * d.hd);
   DA(ctx->vc_dec, (size_t)d.L * B * d.kv * CSM_DEC_POS * d.hd);
-  DA(ctx->h_bb, B * b.H); DA(ctx->h_dec, B * d.H);
-  DA(ctx->q_bb, B * b.heads * b.hd); DA(ctx->q_dec, B * d.heads * d.hd);
-  DA(ctx->attn_bb, B * b.heads * b.hd); DA(ctx->attn_dec, B * d.heads * d.hd);
-  DA(ctx->mlp_bb, B * b.I); DA(ctx->mlp_dec, B * d.I);
+  // every tagged vector exists in `repl` copies so that no L2 line is polled by all CTAs at once
+  ctx->repl = 1;   // measured: replication does not pay on B200 (polls are one L2 trip either way)
+  if (const char* e = getenv("CSM_REPL")) ctx->repl = atoi(e);
+  if (ctx->repl < 1) ctx->repl = 1;
+  if (ctx->repl > 32) ctx->repl = 32;
+  if (ctx->repl > ctx->G) ctx->repl = ctx->G;
+  if (const char* e = getenv("CSM_EVICT_FIRST")) ctx->evict_first = atoi(e) != 0;
+  const size_t R = ctx->repl;
+  DA(ctx->h_bb, R * B * b.H); DA(ctx->h_dec, R * B * d.H);
+  DA(ctx->q_bb, R * B * (b.heads + 2 * b.kv) * b.hd); DA(ctx->q_dec, R * B * (d.heads + 2 * d.kv) * d.hd);
+  DA(ctx->attn_bb, R * B * b.heads * b.hd); DA(ctx->attn_dec, R * B * d.heads * d.hd);
+  DA(ctx->mlp_bb, R * B * b.I); DA(ctx->mlp_dec, R * B * d.I);
+  ctx->tagged = {{ctx->h_bb, R * B * b.H * 4}, {ctx->h_dec, R * B * d.H * 4},
+                 {ctx->q_bb, R * B * (b.heads + 2 * b.kv) * b.hd * 4}, {ctx->q_dec, R * B * (d.heads + 2 * d.kv) * d.hd * 4},
+                 {ctx->attn_bb, R * B * b.heads * b.hd * 4}, {ctx->attn_dec, R * B * d.heads * d.hd * 4},
+                 {ctx->mlp_bb, R * B * b.I * 4}, {ctx->mlp_dec, R * B * d.I * 4}};
   DA(ctx->last_h, B * b.H); DA(ctx->c0_logits, B * ctx->V); DA(ctx->cb_logits, B * (CSM_NQ - 1) * ctx->V);
   ctx->nsplit_max = (max_ctx + CSM_ATT_SPLIT - 1) / CSM_ATT_SPLIT;
   DA(ctx->attn_part, B * b.heads * ctx->nsplit_max * (b.hd + 2));
   DA(ctx->attn_cnt, B * b.kv);
   DA(ctx->bar_counter, 4);
-  DA(ctx->cand, (size_t)ctx->sms * B);
+  DA(ctx->cand, R * ctx->sms * B);
+  ctx->tagged.push_back({ctx->cand, R * ctx->sms * B * sizeof(unsigned long long)});
+  for (auto& t : ctx->tagged) CK(cudaMemsetAsync(t.first, 0, t.second, st));
+  ctx->tagbase = 1;
+  if (const char* e = getenv("CSM_L2_AHEAD_KB")) ctx->l2_ahead = atoi(e) * 1024;
   DA(ctx->samples, B * CSM_NQ); DA(ctx->fed, B * CSM_NQ);
   DA(ctx->stop_flag, 4); DA(ctx->n_frames, 4);
   CK(cudaMemsetAsync(ctx->attn_cnt, 0, B * b.kv * sizeof(unsigned), st));
-  CK(cudaMemsetAsync(ctx->cand, 0, (size_t)ctx->sms * B * sizeof(float2), st));
   CK(cudaMemsetAsync(ctx->bar_counter, 0, 16, st));
   CK(cudaMemsetAsync(ctx->stop_flag, 0, 16, st));
   CK(cudaMemsetAsync(ctx->n_frames, 0, 16, st));
@@ -616,7 +678,7 @@ int csm_create(const CsmShapes* sh, const CsmWeights* w, int max_batch, int max_
   build_table(ctx);
   if ((r = plan_smem(ctx))) return r;
   DA(ctx->d_table, ctx->table.size());
-  DA(ctx->prof, 16 * ctx->table.size());
+  DA(ctx->prof, (32 + (size_t)ctx->sms) * ctx->table.size());
   CK(cudaMemcpyAsync(ctx->d_table, ctx->table.data(), ctx->table.size() * sizeof(Phase), cudaMemcpyHostToDevice, st));
   if (cublasCreate(&ctx->cublas) != CUBLAS_STATUS_SUCCESS) return fail(ctx, CSM_ECUDA, "cublasCreate failed");
   CK(cudaEventCreate(&ctx->ev0));
@@ -777,21 +839,25 @@ const char* csm_last_error(const CsmCtx* ctx) { return ctx ? ctx->err.c_str() : 
 
 // ---- debug / test hooks (see include/csm_b200.h)
 int csm_debug_copy(CsmCtx* ctx, int which, void* dst_device, int64_t max_bytes, int64_t* bytes_out, void* stream) {
+  // buffers 0..7 are tagged words inside the engine; they are returned as plain bf16 rows [Bmax][cols]
   if (!ctx) return CSM_EINVAL;
   const StackDims& b = ctx->bb.d;
   const StackDims& d = ctx->dec.d;
   const size_t B = ctx->Bmax;
   const void* src = nullptr;
   size_t n = 0;
+  const uint32_t* tsrc = nullptr;
+  long long tstride = 0;
+  int tcols = 0;
   switch (which) {
-    case 0: src = ctx->h_bb; n = B * b.H * 2; break;
-    case 1: src = ctx->h_dec; n = B * d.H * 2; break;
-    case 2: src = ctx->q_bb; n = B * b.heads * b.hd * 2; break;
-    case 3: src = ctx->q_dec; n = B * d.heads * d.hd * 2; break;
-    case 4: src = ctx->attn_bb; n = B * b.heads * b.hd * 2; break;
-    case 5: src = ctx->attn_dec; n = B * d.heads * d.hd * 2; break;
-    case 6: src = ctx->mlp_bb; n = B * b.I * 2; break;
-    case 7: src = ctx->mlp_dec; n = B * d.I * 2; break;
+    case 0: tsrc = ctx->h_bb; tcols = b.H; tstride = b.H; break;
+    case 1: tsrc = ctx->h_dec; tcols = d.H; tstride = d.H; break;
+    case 2: tsrc = ctx->q_bb; tcols = b.heads * b.hd; tstride = (b.heads + 2 * b.kv) * b.hd; break;
+    case 3: tsrc = ctx->q_dec; tcols = d.heads * d.hd; tstride = (d.heads + 2 * d.kv) * d.hd; break;
+    case 4: tsrc = ctx->attn_bb; tcols = b.heads * b.hd; tstride = tcols; break;
+    case 5: tsrc = ctx->attn_dec; tcols = d.heads * d.hd; tstride = tcols; break;
+    case 6: if (ctx->direct_mlp) { tsrc = ctx->mlp_bb; tcols = b.I; tstride = b.I; } else { src = ctx->mlp_bb; n = B * b.I * 2; } break;
+    case 7: if (ctx->direct_mlp) { tsrc = ctx->mlp_dec; tcols = d.I; tstride = d.I; } else { src = ctx->mlp_dec; n = B * d.I * 2; } break;
     case 8: src = ctx->last_h; n = B * b.H * 2; break;
     case 9: src = ctx->c0_logits; n = B * ctx->V * 2; break;
     case 10: src = ctx->cb_logits; n = B * (CSM_NQ - 1) * ctx->V * 2; break;
@@ -803,8 +869,14 @@ int csm_debug_copy(CsmCtx* ctx, int which, void* dst_device, int64_t max_bytes, 
     case 16: src = ctx->vc_dec; n = (size_t)d.L * B * d.kv * CSM_DEC_POS * d.hd * 2; break;
     default: return fail(ctx, CSM_EINVAL, "unknown debug buffer %d", which);
   }
+  if (tsrc) n = B * (size_t)tcols * 2;
   if (bytes_out) *bytes_out = (int64_t)n;
   if (!dst_device) return CSM_OK;
+  if (tsrc) {
+    if ((int64_t)n > max_bytes) return fail(ctx, CSM_EINVAL, "debug buffer %d needs %lld bytes", which, (long long)n);
+    CK(csm_untag_rows_launch(tsrc, tstride, tcols, (int)B, (bf16*)dst_device, (cudaStream_t)stream));
+    return CSM_OK;
+  }
   if ((int64_t)n > max_bytes) n = (size_t)max_bytes;
   CK(cudaMemcpyAsync(dst_device, src, n, cudaMemcpyDeviceToDevice, (cudaStream_t)stream));
   return CSM_OK;
@@ -815,8 +887,12 @@ int csm_debug_run_phases(CsmCtx* ctx, const int64_t* ids, const int32_t* mask, i
   if (!ctx) return CSM_EINVAL;
   if (ph_begin < 0 || ph_end > (int)ctx->table.size() || ph_begin >= ph_end)
     return fail(ctx, CSM_EINVAL, "bad phase range [%d,%d)", ph_begin, ph_end);
-  return launch_frame(ctx, B, ph_begin, ph_end, (const long long*)ids, mask, forced, nullptr, 0, 0, 0, ctx->cache_len,
-                      (cudaStream_t)stream);
+  int r = begin_epoch(ctx, (cudaStream_t)stream);
+  if (r) return r;
+  r = launch_frame(ctx, B, ph_begin, ph_end, (const long long*)ids, mask, forced, nullptr, 0, 0, 0, ctx->cache_len,
+                   (cudaStream_t)stream);
+  if (r == 0 && ph_end == (int)ctx->table.size()) end_epoch(ctx);   // phases of one frame share one tag epoch
+  return r;
 }
 
 int csm_debug_profile_frame(CsmCtx* ctx, int B, uint64_t* clocks_host, int32_t* info_host, void* stream) {
@@ -824,12 +900,16 @@ int csm_debug_profile_frame(CsmCtx* ctx, int B, uint64_t* clocks_host, int32_t* 
   if (!ctx || !clocks_host) return CSM_EINVAL;
   cudaStream_t st = (cudaStream_t)stream;
   const size_t n = ctx->table.size();
-  CK(cudaMemsetAsync(ctx->prof, 0, 16 * n * sizeof(unsigned long long), st));
+  const size_t nprof = (32 + (size_t)ctx->G) * n;   // [2 CTAs][n][16] clock64 stamps + [G][n] globaltimer at phase end
+  CK(cudaMemsetAsync(ctx->prof, 0, nprof * sizeof(unsigned long long), st));
+  int r = begin_epoch(ctx, st);
+  if (r) return r;
   ctx->prof_on = 1;
-  int r = launch_frame(ctx, B, 0, (int)n, nullptr, nullptr, 0, nullptr, 0, 0, 0, ctx->cache_len, st);
+  r = launch_frame(ctx, B, 0, (int)n, nullptr, nullptr, 0, nullptr, 0, 0, 0, ctx->cache_len, st);
   ctx->prof_on = 0;
   if (r) return r;
-  CK(cudaMemcpyAsync(clocks_host, ctx->prof, 16 * n * sizeof(unsigned long long), cudaMemcpyDeviceToHost, st));
+  end_epoch(ctx);
+  CK(cudaMemcpyAsync(clocks_host, ctx->prof, nprof * sizeof(unsigned long long), cudaMemcpyDeviceToHost, st));
   CK(cudaStreamSynchronize(st));
   if (info_host)
     for (size_t i = 0; i < n; ++i) {

@@ -33,6 +33,56 @@ __device__ __forceinline__ uint32_t ld_acquire_u32(const unsigned int* p) {
   return v;
 }
 
+// ---- tagged words: bf16 payload (low half) | 16-bit tag of the producing phase (high half) ----
+// One relaxed 32-bit store publishes value and flag together; consumers poll with relaxed loads that
+// bypass L1.  Vector forms are four independent 32-bit atoms (each word carries its own tag).
+__device__ __forceinline__ uint32_t tw_pack(float v, uint32_t tag) {
+  return (tag << 16) | (uint32_t)float_to_bf16_bits(v);
+}
+__device__ __forceinline__ float tw_val(uint32_t w) { return __uint_as_float(w << 16); }
+__device__ __forceinline__ void st_tag(uint32_t* p, uint32_t w) {
+  asm volatile("st.relaxed.gpu.global.u32 [%0], %1;" ::"l"(p), "r"(w) : "memory");
+}
+__device__ __forceinline__ void st_tag2(uint32_t* p, uint32_t a, uint32_t b) {
+  asm volatile("st.relaxed.gpu.global.v2.u32 [%0], {%1,%2};" ::"l"(p), "r"(a), "r"(b) : "memory");
+}
+__device__ __forceinline__ void st_tag4(uint32_t* p, uint32_t a, uint32_t b, uint32_t c, uint32_t d) {
+  asm volatile("st.relaxed.gpu.global.v4.u32 [%0], {%1,%2,%3,%4};" ::"l"(p), "r"(a), "r"(b), "r"(c), "r"(d) : "memory");
+}
+// replicated stores: the same word(s) into `repl` copies `rs` words apart
+__device__ __forceinline__ void st_tag_r(uint32_t* p, uint32_t w, int repl, size_t rs) {
+  for (int r = 0; r < repl; ++r) st_tag(p + r * rs, w);
+}
+__device__ __forceinline__ void st_tag2_r(uint32_t* p, uint32_t a, uint32_t b, int repl, size_t rs) {
+  for (int r = 0; r < repl; ++r) st_tag2(p + r * rs, a, b);
+}
+__device__ __forceinline__ void st_tag4_r(uint32_t* p, uint32_t a, uint32_t b, uint32_t c, uint32_t d, int repl, size_t rs) {
+  for (int r = 0; r < repl; ++r) st_tag4(p + r * rs, a, b, c, d);
+}
+__device__ __forceinline__ uint32_t ld_tag(const uint32_t* p) {
+  uint32_t v;
+  asm volatile("ld.relaxed.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+  return v;
+}
+__device__ __forceinline__ uint4 ld_tag4(const uint32_t* p) {
+  uint4 v;
+  asm volatile("ld.relaxed.gpu.global.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "l"(p) : "memory");
+  return v;
+}
+__device__ __forceinline__ bool tw_ok4(const uint4& w, uint32_t tag) {
+  return ((w.x >> 16) == tag) & ((w.y >> 16) == tag) & ((w.z >> 16) == tag) & ((w.w >> 16) == tag);
+}
+// two tagged words -> one packed bf16 pair (first word in the low half)
+__device__ __forceinline__ uint32_t tw_pair(uint32_t w0, uint32_t w1) { return (w0 & 0xffffu) | (w1 << 16); }
+__device__ __forceinline__ void st_tag64(unsigned long long* p, unsigned long long w) {
+  asm volatile("st.relaxed.gpu.global.u64 [%0], %1;" ::"l"(p), "l"(w) : "memory");
+}
+__device__ __forceinline__ unsigned long long ld_tag64(const unsigned long long* p) {
+  unsigned long long v;
+  asm volatile("ld.relaxed.gpu.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
+  return v;
+}
+
 // ---- mbarrier ----
 __device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
   asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
@@ -68,6 +118,25 @@ __device__ __forceinline__ void bulk_g2s(void* dst_smem, const void* src_gmem, u
       "cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(smem_u32(dst_smem)),
       "l"(src_gmem), "r"(bytes), "r"(smem_u32(bar))
       : "memory");
+}
+// Same copy, marked evict-first in L2: a weight byte is used once per pass, the line should not push out
+// the lines the prefetcher has brought in for the next phases.
+__device__ __forceinline__ uint64_t l2_policy_evict_first() {
+  uint64_t pol;
+  asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(pol));
+  return pol;
+}
+__device__ __forceinline__ void bulk_g2s_hint(void* dst_smem, const void* src_gmem, uint32_t bytes, uint64_t* bar,
+                                              uint64_t pol) {
+  asm volatile(
+      "cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes.L2::cache_hint [%0], [%1], %2, [%3], %4;" ::"r"(
+          smem_u32(dst_smem)),
+      "l"(src_gmem), "r"(bytes), "r"(smem_u32(bar)), "l"(pol)
+      : "memory");
+}
+// HBM -> L2 only (no shared memory needed): lets HBM keep streaming while the ring is full.
+__device__ __forceinline__ void bulk_prefetch_l2(const void* src_gmem, uint32_t bytes) {
+  asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(src_gmem), "r"(bytes) : "memory");
 }
 __device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async;" ::: "memory"); }
 

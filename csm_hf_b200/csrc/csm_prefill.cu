@@ -150,12 +150,22 @@ __global__ void csm_add_rows_kernel(bf16* __restrict__ h, const bf16* __restrict
   }
 }
 
-// ---------------------------------------------------------------- copy the last position's hidden row per sequence
-__global__ void csm_take_last_rows_kernel(const bf16* __restrict__ h, int S, int H, bf16* __restrict__ dst, int b0) {
+// ---------------------------------------------------------------- the last position's hidden row per sequence,
+// handed to the frame kernel as tagged words (bf16 | tag of the last backbone phase, csm_common.cuh)
+__global__ void csm_take_last_rows_kernel(const bf16* __restrict__ h, int S, int H, uint32_t* __restrict__ dst, int b0,
+                                          uint32_t tag) {
   const int b = blockIdx.x;
-  const uint4* src = reinterpret_cast<const uint4*>(h + ((size_t)b * S + (S - 1)) * H);
-  uint4* d = reinterpret_cast<uint4*>(dst + (size_t)(b0 + b) * H);
-  for (int i = threadIdx.x; i < H / 8; i += blockDim.x) d[i] = src[i];
+  const unsigned short* src = reinterpret_cast<const unsigned short*>(h + ((size_t)b * S + (S - 1)) * H);
+  uint32_t* d = dst + (size_t)(b0 + b) * H;
+  for (int i = threadIdx.x; i < H; i += blockDim.x) d[i] = (tag << 16) | (uint32_t)src[i];
+}
+
+// tagged rows -> plain bf16 rows (debug / tests)
+__global__ void csm_untag_rows_kernel(const uint32_t* __restrict__ src, long long src_stride, int cols,
+                                      bf16* __restrict__ dst) {
+  const int r = blockIdx.x;
+  unsigned short* d = reinterpret_cast<unsigned short*>(dst + (size_t)r * cols);
+  for (int i = threadIdx.x; i < cols; i += blockDim.x) d[i] = (unsigned short)(src[(size_t)r * src_stride + i] & 0xffffu);
 }
 
 __global__ void csm_i64_to_i32_kernel(const long long* __restrict__ src, int* __restrict__ dst, int n) {
@@ -337,8 +347,13 @@ cudaError_t csm_add_rows_launch(bf16* h, const bf16* y, long long n, cudaStream_
   csm_add_rows_kernel<<<(int)blocks, 256, 0, st>>>(h, y, n2);
   return cudaGetLastError();
 }
-cudaError_t csm_take_last_rows_launch(const bf16* h, int S, int H, bf16* dst, int b0, int nseq, cudaStream_t st) {
-  csm_take_last_rows_kernel<<<nseq, 256, 0, st>>>(h, S, H, dst, b0);
+cudaError_t csm_take_last_rows_launch(const bf16* h, int S, int H, uint32_t* dst, int b0, int nseq, uint32_t tag,
+                                      cudaStream_t st) {
+  csm_take_last_rows_kernel<<<nseq, 256, 0, st>>>(h, S, H, dst, b0, tag);
+  return cudaGetLastError();
+}
+cudaError_t csm_untag_rows_launch(const uint32_t* src, long long src_stride, int cols, int rows, bf16* dst, cudaStream_t st) {
+  csm_untag_rows_kernel<<<rows, 256, 0, st>>>(src, src_stride, cols, dst);
   return cudaGetLastError();
 }
 cudaError_t csm_i64_to_i32_launch(const long long* src, int* dst, int n, cudaStream_t st) {

@@ -14,6 +14,14 @@
 //               weights while the compute warps sit in a barrier or an epilogue.
 //   warp  9     activation stream for K=8192 (down_proj) phases, whose activations do not
 //               fit in shared memory: bulk-copies [B, k-chunk] tiles after the barrier.
+//   warp 10     L2 prefetcher: walks the phase table further ahead still and pulls this CTA's weight
+//               slices (and norm weights, and the K/V blocks of its attention units) from HBM into L2
+//               with cp.async.bulk.prefetch.L2, so HBM keeps streaming even when the ring is full.
+//
+// Phases are chained by dataflow: every vector that crosses CTAs is an array of tagged words
+// (bf16 | 16-bit tag of the producing phase, csm_common.cuh) that the consumer polls while staging, so
+// one hand-over costs one trip through L2 -- no fence, no atomic, no separate barrier round.  Only the
+// K=8192 phases fed by the TMA engine at batch > 4 still use a grid barrier (plain bf16 input).
 //
 // Work split of a matrix W[N,K]: rows are divided evenly over the CTAs (granule 1 or 2 rows);
 // csm_pack.cu stores each CTA's rows contiguously, k16-tile major, 32 bytes per (tile,row) in
@@ -34,6 +42,9 @@ namespace {
 struct Ctx {
   uint64_t *full, *empty, *afull, *aempty;
   volatile int* sflag;   // [0] last-arriver flag, [1] scratch
+  volatile unsigned int* sprog;   // bytes of this CTA's weight stream issued so far (read by the prefetcher)
+  int ph;                // phase being executed
+  int rep;               // which copy of the tagged vectors this CTA reads (c % repl)
   Phase* desc;           // [2] descriptor slots
   float* scratch;        // 256 floats
   int* tok;              // [32] tokens gathered by this phase
@@ -57,31 +68,40 @@ __device__ __forceinline__ void grid_wait(const unsigned int* counter, unsigned 
 }
 
 __device__ __forceinline__ bool better(float v, int i, float bv, int bi) { return v > bv || (v == bv && i < bi); }
+__device__ __forceinline__ uint32_t tg(const StreamParams& p, int ph) { return (p.tagbase + (uint32_t)ph) & 0xffffu; }
 
 // ------------------------------------------------------------------ greedy sample of a finished head phase
 // sample_topk at topk=1 (modeling_csm.py:179-189) with the canonical lowest-index tie-break: reduce
-// the (best logit, id) candidates every CTA published in the head phase for codebook `cb`.
+// the (best logit, id) candidates every CTA published in head phase `head_ph` for codebook `cb`
+// (tagged 64-bit words: polling them IS the synchronisation with that phase).
 // Result in cx.tok[m]; CTA 0 also records samples / fed.  Ends with a compute_sync.
-__device__ __forceinline__ void reduce_candidates(const StreamParams& p, const Ctx& cx, int cb) {
+__device__ __forceinline__ void reduce_candidates(const StreamParams& p, const Ctx& cx, int cb, int head_ph) {
   const int M = p.B;
+  const unsigned long long tag = tg(p, head_ph);
   for (int m = cx.warp; m < M; m += CSM_COMPUTE_WARPS) {
+    unsigned long long w[5];
+    bool ok;
+    do {
+      ok = true;
+#pragma unroll
+      for (int j = 0; j < 5; ++j) {
+        const int cc = cx.lane + 32 * j;
+        w[j] = 0;
+        if (cc < cx.G) {
+          w[j] = ld_tag64(p.cand + ((size_t)cx.rep * cx.G + cc) * p.Bmax + m);
+          ok &= ((w[j] >> 32) & 0xffffull) == tag;
+        }
+      }
+    } while (!__all_sync(0xffffffffu, ok));
     float best = -INFINITY;
     int bi = 0x7fffffff;
-    float2 pr[5];
 #pragma unroll
     for (int j = 0; j < 5; ++j) {
-      const int cc = cx.lane + 32 * j;
-      pr[j] = cc < cx.G ? __ldcg(p.cand + (size_t)cc * p.Bmax + m) : make_float2(-INFINITY, __int_as_float(0x7fffffff));
-    }
-#pragma unroll
-    for (int j = 0; j < 5; ++j) {
-      const int oi = __float_as_int(pr[j].y);
-      if (better(pr[j].x, oi, best, bi)) { best = pr[j].x; bi = oi; }
-    }
-    for (int cc = cx.lane + 160; cc < cx.G; cc += 32) {   // grids larger than 160 CTAs (not B200)
-      float2 q = __ldcg(p.cand + (size_t)cc * p.Bmax + m);
-      const int oi = __float_as_int(q.y);
-      if (better(q.x, oi, best, bi)) { best = q.x; bi = oi; }
+      if (cx.lane + 32 * j < cx.G) {
+        const int oi = (int)((w[j] >> 16) & 0xffffull);
+        const float ov = tw_val((uint32_t)w[j]);
+        if (better(ov, oi, best, bi)) { best = ov; bi = oi; }
+      }
     }
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) {
@@ -103,181 +123,205 @@ __device__ __forceinline__ void reduce_candidates(const StreamParams& p, const C
 }
 
 // ------------------------------------------------------------------ decoder attention (<= 32 positions, hd 128)
-// One warp per (sequence, query head).  Lane t owns cached position t for the
-// scores and output dims 4*lane.. for P.V; every load of a stage is issued before its first use.
-__device__ __forceinline__ void attn_dec_unit(const StreamParams& p, int layer, int dec_pos, int b, int head, bf16* dst,
-                                              int lane) {
+// One warp per (sequence, query head).  Lane t owns cached position t for the scores and output dims
+// 4*lane.. for P.V.  q and the K/V of the position being processed come as tagged words straight from
+// the qkv phase (polled here); older positions come from the cache, loaded before the poll starts.
+// Returns the normalised output dims 4*lane..4*lane+3.
+__device__ __forceinline__ void attn_dec_unit(const StreamParams& p, const uint32_t* qbase, int layer, int dec_pos, int b,
+                                              int head, uint32_t qtag, int lane, float (&out)[4]) {
   constexpr int HD = 128;
   const int nh = p.dec.heads, nk = p.dec.kv, rep = nh / nk;
   const int T = dec_pos + 1;
-  {
-    const int kvh = head / rep;
-    const size_t kvbase = (((size_t)layer * p.Bmax + b) * nk + kvh) * (size_t)CSM_DEC_POS * HD;
-    const bf16* qp = p.q_dec + (size_t)b * (nh * HD) + head * HD;
-    const bf16* kp = p.kc_dec + kvbase + (size_t)lane * HD;
-    uint4 kq[HD / 8];
-    // q: lane l holds dims 4l..4l+3 (8 bytes), redistributed by shuffles below
-    const uint2 qmine = ldcg_u2(qp + lane * 4);
-    if (lane < T) {
+  const int kvh = head / rep;
+  const int W = (nh + 2 * nk) * HD;
+  const size_t kvbase = (((size_t)layer * p.Bmax + b) * nk + kvh) * (size_t)CSM_DEC_POS * HD;
+  const bf16* kp = p.kc_dec + kvbase + (size_t)lane * HD;
+  const bf16* vp = p.vc_dec + kvbase + lane * 4;
+  uint4 kq[HD / 8];
+  if (lane < dec_pos) {
 #pragma unroll
-      for (int ci = 0; ci < HD / 8; ++ci) kq[ci] = ldcg_u4(kp + ci * 8);
-    } else {
+    for (int ci = 0; ci < HD / 8; ++ci) kq[ci] = ldcg_u4(kp + ci * 8);
+  } else {
 #pragma unroll
-      for (int ci = 0; ci < HD / 8; ++ci) kq[ci] = make_uint4(0, 0, 0, 0);
-    }
-    // V rows (independent of the scores): 8 bytes per lane per position, first half issued with K
-    const bf16* vp = p.vc_dec + kvbase + lane * 4;
-    uint2 va[CSM_DEC_POS / 2];
-#pragma unroll
-    for (int t = 0; t < CSM_DEC_POS / 2; ++t) va[t] = t < T ? ldcg_u2(vp + (size_t)t * HD) : make_uint2(0, 0);
-    float d = 0.f;
-#pragma unroll
-    for (int ci = 0; ci < HD / 8; ++ci) {
-      // dims 8ci..8ci+7 of q live in lanes 2ci (first 4) and 2ci+1 (last 4)
-      const uint32_t q0 = __shfl_sync(0xffffffffu, qmine.x, 2 * ci), q1 = __shfl_sync(0xffffffffu, qmine.y, 2 * ci);
-      const uint32_t q2 = __shfl_sync(0xffffffffu, qmine.x, 2 * ci + 1), q3 = __shfl_sync(0xffffffffu, qmine.y, 2 * ci + 1);
-      const uint4 kv = kq[ci];
-      d += bf_lo(q0) * bf_lo(kv.x) + bf_hi(q0) * bf_hi(kv.x);
-      d += bf_lo(q1) * bf_lo(kv.y) + bf_hi(q1) * bf_hi(kv.y);
-      d += bf_lo(q2) * bf_lo(kv.z) + bf_hi(q2) * bf_hi(kv.z);
-      d += bf_lo(q3) * bf_lo(kv.w) + bf_hi(q3) * bf_hi(kv.w);
-    }
-    uint2 vb[CSM_DEC_POS / 2];
-#pragma unroll
-    for (int t = 0; t < CSM_DEC_POS / 2; ++t)
-      vb[t] = (t + CSM_DEC_POS / 2) < T ? ldcg_u2(vp + (size_t)(t + CSM_DEC_POS / 2) * HD) : make_uint2(0, 0);
-    const float sc = lane < T ? d * p.dec.scale : -INFINITY;
-    const float mx = warp_max(sc);
-    const float pe = (lane < T) ? __expf(sc - mx) : 0.f;
-    const float l = warp_sum(pe);
-    float o0 = 0.f, o1 = 0.f, o2 = 0.f, o3 = 0.f;
-#pragma unroll
-    for (int t = 0; t < CSM_DEC_POS / 2; ++t) {
-      const float pv = __shfl_sync(0xffffffffu, pe, t);
-      o0 += pv * bf_lo(va[t].x); o1 += pv * bf_hi(va[t].x);
-      o2 += pv * bf_lo(va[t].y); o3 += pv * bf_hi(va[t].y);
-    }
-#pragma unroll
-    for (int t = 0; t < CSM_DEC_POS / 2; ++t) {
-      const float pv = __shfl_sync(0xffffffffu, pe, t + CSM_DEC_POS / 2);
-      o0 += pv * bf_lo(vb[t].x); o1 += pv * bf_hi(vb[t].x);
-      o2 += pv * bf_lo(vb[t].y); o3 += pv * bf_hi(vb[t].y);
-    }
-    const float inv = 1.f / l;
-    uint2 ov = make_uint2(pack_bf16(o0 * inv, o1 * inv), pack_bf16(o2 * inv, o3 * inv));
-    *reinterpret_cast<uint2*>(dst + lane * 4) = ov;
+    for (int ci = 0; ci < HD / 8; ++ci) kq[ci] = make_uint4(0, 0, 0, 0);
   }
+  uint2 va[CSM_DEC_POS / 2], vb[CSM_DEC_POS / 2];
+#pragma unroll
+  for (int t = 0; t < CSM_DEC_POS / 2; ++t) va[t] = t < dec_pos ? ldcg_u2(vp + (size_t)t * HD) : make_uint2(0, 0);
+#pragma unroll
+  for (int t = 0; t < CSM_DEC_POS / 2; ++t)
+    vb[t] = (t + CSM_DEC_POS / 2) < dec_pos ? ldcg_u2(vp + (size_t)(t + CSM_DEC_POS / 2) * HD) : make_uint2(0, 0);
+  // q | k | v of this position: lane l holds dims 4l..4l+3 of each
+  const uint32_t* qw = qbase + (size_t)b * W + head * HD + lane * 4;
+  const uint32_t* kw = qbase + (size_t)b * W + nh * HD + kvh * HD + lane * 4;
+  const uint32_t* vw = kw + nk * HD;
+  uint4 q4, k4, v4;
+  bool ok;
+  do {
+    q4 = ld_tag4(qw);
+    k4 = ld_tag4(kw);
+    v4 = ld_tag4(vw);
+    ok = tw_ok4(q4, qtag) & tw_ok4(k4, qtag) & tw_ok4(v4, qtag);
+  } while (!__all_sync(0xffffffffu, ok));
+  const uint2 qmine = make_uint2(tw_pair(q4.x, q4.y), tw_pair(q4.z, q4.w));
+  const uint2 kmine = make_uint2(tw_pair(k4.x, k4.y), tw_pair(k4.z, k4.w));
+  const uint2 vmine = make_uint2(tw_pair(v4.x, v4.y), tw_pair(v4.z, v4.w));
+  float d = 0.f;
+#pragma unroll
+  for (int ci = 0; ci < HD / 8; ++ci) {
+    // dims 8ci..8ci+7 live in lanes 2ci (first 4) and 2ci+1 (last 4)
+    const uint32_t q0 = __shfl_sync(0xffffffffu, qmine.x, 2 * ci), q1 = __shfl_sync(0xffffffffu, qmine.y, 2 * ci);
+    const uint32_t q2 = __shfl_sync(0xffffffffu, qmine.x, 2 * ci + 1), q3 = __shfl_sync(0xffffffffu, qmine.y, 2 * ci + 1);
+    const uint32_t k0 = __shfl_sync(0xffffffffu, kmine.x, 2 * ci), k1 = __shfl_sync(0xffffffffu, kmine.y, 2 * ci);
+    const uint32_t k2 = __shfl_sync(0xffffffffu, kmine.x, 2 * ci + 1), k3 = __shfl_sync(0xffffffffu, kmine.y, 2 * ci + 1);
+    uint4 kv = kq[ci];
+    if (lane == dec_pos) kv = make_uint4(k0, k1, k2, k3);
+    d += bf_lo(q0) * bf_lo(kv.x) + bf_hi(q0) * bf_hi(kv.x);
+    d += bf_lo(q1) * bf_lo(kv.y) + bf_hi(q1) * bf_hi(kv.y);
+    d += bf_lo(q2) * bf_lo(kv.z) + bf_hi(q2) * bf_hi(kv.z);
+    d += bf_lo(q3) * bf_lo(kv.w) + bf_hi(q3) * bf_hi(kv.w);
+  }
+  const float sc = lane < T ? d * p.dec.scale : -INFINITY;
+  const float mx = warp_max(sc);
+  const float pe = (lane < T) ? __expf(sc - mx) : 0.f;
+  const float l = warp_sum(pe);
+  float o0 = 0.f, o1 = 0.f, o2 = 0.f, o3 = 0.f;
+#pragma unroll
+  for (int t = 0; t < CSM_DEC_POS / 2; ++t) {
+    const float pv = __shfl_sync(0xffffffffu, pe, t);
+    const uint2 vv = (t == dec_pos) ? vmine : va[t];
+    o0 += pv * bf_lo(vv.x); o1 += pv * bf_hi(vv.x);
+    o2 += pv * bf_lo(vv.y); o3 += pv * bf_hi(vv.y);
+  }
+#pragma unroll
+  for (int t = 0; t < CSM_DEC_POS / 2; ++t) {
+    const float pv = __shfl_sync(0xffffffffu, pe, t + CSM_DEC_POS / 2);
+    const uint2 vv = (t + CSM_DEC_POS / 2 == dec_pos) ? vmine : vb[t];
+    o0 += pv * bf_lo(vv.x); o1 += pv * bf_hi(vv.x);
+    o2 += pv * bf_lo(vv.y); o3 += pv * bf_hi(vv.y);
+  }
+  const float inv = 1.f / l;
+  out[0] = o0 * inv; out[1] = o1 * inv; out[2] = o2 * inv; out[3] = o3 * inv;
 }
 
-
-// Separate-phase form (larger batches): units spread over the CTAs, result to global memory.
+// Separate-phase form: units spread over the CTAs, result published as tagged words.
 __device__ __forceinline__ void attn_dec_phase(const StreamParams& p, const Phase& P, const Ctx& cx) {
   const int nh = p.dec.heads;
   const int nunits = p.B * nh;
+  const uint32_t qtag = tg(p, P.src_ph), otag = tg(p, cx.ph);
+  const size_t qrs = (size_t)p.Bmax * (nh + 2 * p.dec.kv) * p.dec.hd, ors = (size_t)p.Bmax * nh * p.dec.hd;
   for (int unit = cx.warp * cx.G + cx.c; unit < nunits; unit += CSM_COMPUTE_WARPS * cx.G) {
     const int b = unit / nh, head = unit - b * nh;
-    attn_dec_unit(p, P.layer, P.dec_pos, b, head, p.attn_dec + (size_t)b * (nh * p.dec.hd) + head * p.dec.hd, cx.lane);
+    float o[4];
+    attn_dec_unit(p, p.q_dec + cx.rep * qrs, P.layer, P.dec_pos, b, head, qtag, cx.lane, o);
+    st_tag4_r(p.attn_dec + (size_t)b * (nh * p.dec.hd) + head * p.dec.hd + cx.lane * 4, tw_pack(o[0], otag),
+              tw_pack(o[1], otag), tw_pack(o[2], otag), tw_pack(o[3], otag), p.repl, ors);
   }
 }
 
 // ------------------------------------------------------------------ activation staging
-// Rows of the phase input -> shared memory [M][K+8] bf16, applying RMSNorm exactly as
-// LlamaRMSNorm.forward (hf modeling_llama.py:62-67): fp32 x*rsqrt(mean(x^2)+eps) -> bf16 -> *w -> bf16.
-// A row is spread over K/8 threads (one 16-byte load each), 256*8/K rows per pass, so that even
-// a single sequence is loaded by all warps with one round trip to L2.
+// Rows of the phase input -> shared memory [M][K+8] bf16.  The input is an array of tagged words written
+// by the CTAs of phase P.src_ph.  Work item = 4 consecutive words (one 16-byte load); items are dealt
+// round-robin to the 256 compute threads, up to 8 loads in flight per thread, repeated until every word
+// carries the producer's tag -- the poll IS the load, one trip through L2 after the last producer's store.
+// RMSNorm exactly as LlamaRMSNorm.forward (hf modeling_llama.py:62-67): fp32 x*rsqrt(mean(x^2)+eps) ->
+// bf16 -> *w -> bf16.  Pass 1 stores the raw rows and per-warp partial sums of squares; after one CTA
+// barrier pass 2 scales the thread's own elements in place (fixed summation order: deterministic).
 __device__ __forceinline__ void stage_act(const StreamParams& p, const Phase& P, const Ctx& cx, int astride) {
   const int K = P.K, M = p.B;
-  const float eps = P.stack ? p.dec.eps : p.bb.eps;
   bf16* dst = reinterpret_cast<bf16*>(cx.actreg);
-  if (P.act_mode == ACT_GATHER) reduce_candidates(p, cx, P.cb);
-  if (P.act_mode == ACT_ATTN) {
-    // decoder attention of every (sequence, head), computed redundantly by every CTA straight into the
-    // activation rows of the o_proj that consumes it (small batches only: saves a phase and a barrier)
-    const int nh = p.dec.heads;
-    for (int unit = cx.warp; unit < M * nh; unit += CSM_COMPUTE_WARPS) {
-      const int b = unit / nh, head = unit - b * nh;
-      attn_dec_unit(p, P.layer, P.dec_pos, b, head, dst + (size_t)b * astride + head * p.dec.hd, cx.lane);
-    }
-    return;
-  }
-  if (K > 2048) {
-    // wide plain rows (the MLP activations when they fit in shared memory): straight 16-byte copies
-    const int cpr = K >> 3;
-    for (int m = 0; m < M; ++m) {
-      const uint4* src = reinterpret_cast<const uint4*>(P.act + (size_t)m * P.act_stride);
-      uint4* d4 = reinterpret_cast<uint4*>(dst + (size_t)m * astride);
-      for (int c0 = cx.tid; c0 < cpr; c0 += 4 * CSM_COMPUTE_THREADS) {
-        uint4 v[4];
+  if (P.act_mode == ACT_GATHER) {
+    // _embed_audio (modeling_csm.py:247-259): row tok + codebook*V of the audio table (plain bf16, read-only)
+    reduce_candidates(p, cx, P.cb, P.res_ph);
+    const int gpr = K >> 3;                      // 16-byte groups per row
+    const int total = M * gpr;
+    for (int i0 = cx.tid; i0 < total; i0 += 8 * CSM_COMPUTE_THREADS) {
+      uint4 v[8];
 #pragma unroll
-        for (int j = 0; j < 4; ++j) {
-          const int cc = c0 + j * CSM_COMPUTE_THREADS;
-          if (cc < cpr) v[j] = ldcg_u4(src + cc);
+      for (int j = 0; j < 8; ++j) {
+        const int i = i0 + j * CSM_COMPUTE_THREADS;
+        if (i < total) {
+          const int m = i / gpr, g = i - m * gpr;
+          v[j] = __ldg(reinterpret_cast<const uint4*>(P.act + (size_t)(cx.tok[m] + P.cb * p.V) * K) + g);
         }
+      }
 #pragma unroll
-        for (int j = 0; j < 4; ++j) {
-          const int cc = c0 + j * CSM_COMPUTE_THREADS;
-          if (cc < cpr) d4[cc] = v[j];
+      for (int j = 0; j < 8; ++j) {
+        const int i = i0 + j * CSM_COMPUTE_THREADS;
+        if (i < total) {
+          const int m = i / gpr, g = i - m * gpr;
+          *reinterpret_cast<uint4*>(dst + (size_t)m * astride + g * 8) = v[j];
         }
       }
     }
     return;
   }
-  const int tpr = K >> 3;                      // threads per row (K <= 2048 -> <= 256)
-  const int rpp = CSM_COMPUTE_THREADS / tpr;   // rows per pass
-  const int wpr = tpr >> 5;                    // warps per row (0 when a row is narrower than a warp)
-  const int rl = cx.tid / tpr, col = (cx.tid - rl * tpr) * 8;
-  uint4 wv = make_uint4(0, 0, 0, 0);
-  if (P.act_mode == ACT_NORM && rl < rpp) wv = __ldg(reinterpret_cast<const uint4*>(P.norm_w + col));
-  for (int m0 = 0; m0 < M; m0 += rpp) {
-    const int m = m0 + rl;
-    const bool on = rl < rpp && m < M;
-    uint4 v = make_uint4(0, 0, 0, 0);
-    if (on) {
-      const bf16* src;
-      if (P.act_mode == ACT_GATHER)   // _embed_audio (modeling_csm.py:247-259): row tok + codebook*V of the audio table
-        src = P.act + (size_t)(cx.tok[m] + P.cb * p.V) * K;
-      else
-        src = P.act + (size_t)m * P.act_stride;
-      v = ldcg_u4(src + col);
-    }
-    if (P.act_mode == ACT_NORM) {
-      const uint32_t* u = reinterpret_cast<const uint32_t*>(&v);
-      float ss = 0.f;
+  const uint32_t tag = tg(p, P.src_ph);
+  const uint32_t* base = reinterpret_cast<const uint32_t*>(P.act) + (size_t)cx.rep * p.Bmax * P.act_stride;
+  const bool norm = P.act_mode == ACT_NORM;
+  const int gpr = K >> 2;                        // 4-word groups per row (multiple of 32: a warp stays inside a row)
+  const int total = M * gpr;
+  const int ppr = gpr >> 5;                      // warp-sized pieces per row (<= 16 for K <= 2048)
+  // norm weights of this thread's (at most two) column groups, requested before the poll starts
+  uint2 nw0 = make_uint2(0, 0), nw1 = make_uint2(0, 0);
+  if (norm) {
+    nw0 = __ldg(reinterpret_cast<const uint2*>(P.norm_w) + (cx.tid % gpr));
+    nw1 = __ldg(reinterpret_cast<const uint2*>(P.norm_w) + ((cx.tid + CSM_COMPUTE_THREADS) % gpr));
+  }
+  bool first = true;
+  for (int i0 = cx.tid; i0 < total; i0 += 8 * CSM_COMPUTE_THREADS) {
+    uint4 w[8];
+    bool ok;
+    int iters = 0;
+    do {
+      ok = true;
 #pragma unroll
-      for (int q = 0; q < 4; ++q) {
-        float a = bf_lo(u[q]), b = bf_hi(u[q]);
-        ss += a * a + b * b;
-      }
-      // reduce over the threads of the row: inside the warp, then across the row's warps
-      if (wpr == 0) {
-        for (int o = tpr >> 1; o > 0; o >>= 1) ss += __shfl_xor_sync(0xffffffffu, ss, o);
-      } else {
-        ss = warp_sum(ss);
-        if (wpr > 1) {
-          if (cx.lane == 0) cx.scratch[cx.warp] = ss;
-          compute_sync();
-          const int w0 = (cx.warp / wpr) * wpr;
-          ss = 0.f;
-          for (int w = 0; w < wpr; ++w) ss += cx.scratch[w0 + w];
-          compute_sync();
+      for (int j = 0; j < 8; ++j) {
+        const int i = i0 + j * CSM_COMPUTE_THREADS;
+        if (i < total) {
+          const int m = i / gpr, g = i - m * gpr;
+          w[j] = ld_tag4(base + (size_t)m * P.act_stride + g * 4);
         }
       }
-      if (on) {
-        const float rstd = rsqrtf(ss / (float)K + eps);
-        const uint32_t* w = reinterpret_cast<const uint32_t*>(&wv);
-        uint4 o;
-        uint32_t* ou = reinterpret_cast<uint32_t*>(&o);
 #pragma unroll
-        for (int q = 0; q < 4; ++q) {
-          float y0 = bfround(bf_lo(u[q]) * rstd), y1 = bfround(bf_hi(u[q]) * rstd);
-          ou[q] = pack_bf16(bf_lo(w[q]) * y0, bf_hi(w[q]) * y1);
+      for (int j = 0; j < 8; ++j)
+        if (i0 + j * CSM_COMPUTE_THREADS < total) ok &= tw_ok4(w[j], tag);
+      ++iters;
+    } while (!__all_sync(0xffffffffu, ok));
+    if (first && cx.prof) { cx.prof[8] = clock64(); cx.prof[9] = (unsigned long long)iters; }
+    first = false;
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      const int i = i0 + j * CSM_COMPUTE_THREADS;   // warp-uniform validity and row (gpr % 32 == 0)
+      if (i < total) {
+        const int m = i / gpr, g = i - m * gpr;
+        *reinterpret_cast<uint2*>(dst + (size_t)m * astride + g * 4) =
+            make_uint2(tw_pair(w[j].x, w[j].y), tw_pair(w[j].z, w[j].w));
+        if (norm) {
+          const float a = tw_val(w[j].x), b = tw_val(w[j].y), c = tw_val(w[j].z), d = tw_val(w[j].w);
+          const float ss = warp_sum(a * a + b * b + c * c + d * d);
+          if (cx.lane == 0) cx.scratch[m * ppr + (g >> 5)] = ss;
         }
-        *reinterpret_cast<uint4*>(dst + (size_t)m * astride + col) = o;
-        if (P.norm_out != nullptr && (m % cx.G) == cx.c) *reinterpret_cast<uint4*>(P.norm_out + (size_t)m * K + col) = o;
       }
-    } else if (on) {
-      *reinterpret_cast<uint4*>(dst + (size_t)m * astride + col) = v;
     }
+  }
+  if (!norm) return;
+  compute_sync();
+  const float eps = P.stack ? p.dec.eps : p.bb.eps;
+  int jj = 0;
+  for (int i = cx.tid; i < total; i += CSM_COMPUTE_THREADS, ++jj) {
+    const int m = i / gpr, g = i - m * gpr;
+    float ss = 0.f;
+    for (int q = 0; q < ppr; ++q) ss += cx.scratch[m * ppr + q];
+    const float rstd = rsqrtf(ss / (float)K + eps);
+    const uint2 nw = (gpr > CSM_COMPUTE_THREADS && (jj & 1)) ? nw1 : nw0;
+    uint2* px = reinterpret_cast<uint2*>(dst + (size_t)m * astride + g * 4);
+    const uint2 x = *px;
+    const float y0 = bfround(bf_lo(x.x) * rstd), y1 = bfround(bf_hi(x.x) * rstd);
+    const float y2 = bfround(bf_lo(x.y) * rstd), y3 = bfround(bf_hi(x.y) * rstd);
+    const uint2 o = make_uint2(pack_bf16(bf_lo(nw.x) * y0, bf_hi(nw.x) * y1), pack_bf16(bf_lo(nw.y) * y2, bf_hi(nw.y) * y3));
+    *px = o;
+    if (P.norm_out != nullptr && (m % cx.G) == cx.c) *reinterpret_cast<uint2*>(P.norm_out + (size_t)m * K + g * 4) = o;
   }
 }
 
@@ -375,6 +419,7 @@ __device__ __forceinline__ void gemv_core(const StreamParams& p, const Phase& P,
     const int tiles = min(g.tpc, g.ntiles - T0);
     const uint32_t s = cx.slot;
     mbar_wait(&cx.full[s], cx.slot_par);
+    if (ch == 0) CSM_STAMP(cx, 7);   // first weight chunk of the phase is in shared memory
     uint32_t abase = act0;
     uint32_t as = 0;
     if (stream) {
@@ -426,6 +471,12 @@ __device__ __forceinline__ void gemv_core(const StreamParams& p, const Phase& P,
 }
 
 // ------------------------------------------------------------------ GEMV / skinny-GEMM phase
+__device__ __forceinline__ float resid_poll(const uint32_t* p, uint32_t tag) {
+  uint32_t w = ld_tag(p);
+  while ((w >> 16) != tag) w = ld_tag(p);
+  return tw_val(w);
+}
+
 template <int NB>
 __device__ __forceinline__ void gemv_phase(const StreamParams& p, const Phase& P, Ctx& cx) {
   const int M = p.B, K = P.K;
@@ -449,10 +500,16 @@ __device__ __forceinline__ void gemv_phase(const StreamParams& p, const Phase& P
   const int u = cx.tid & (up2 - 1);
   const int mstep = up2 >= CSM_COMPUTE_THREADS ? 1 : CSM_COMPUTE_THREADS >> ush;
   const int m_first = up2 >= CSM_COMPUTE_THREADS ? 0 : cx.tid >> ush;
-  // residual value of the first element this thread will update: fetched now, used after the MMAs
-  float resid0 = 0.f;
+  const uint32_t otag = tg(p, cx.ph);
+  uint32_t* outw = reinterpret_cast<uint32_t*>(P.out);
+  const size_t ors = (size_t)p.Bmax * P.out_stride;   // words between the copies of the output vector
+  const int R = p.repl;
+  // residual word of the first element this thread will update: requested now, used after the MMAs
+  // (own element of the previous residual phase, or the stream's first value written by another CTA)
+  uint32_t resid0 = 0;
+  const uint32_t rtag = tg(p, P.res_ph);
   if (P.epi == EPI_RESID && u < upc && m_first < M)
-    resid0 = ldcg_bf16(P.out + (size_t)m_first * P.out_stride + g.row0 + u);
+    resid0 = ld_tag(outw + cx.rep * ors + (size_t)m_first * P.out_stride + g.row0 + u);
   if (g.rows > 0) gemv_core<NB>(p, P, cx, g, stream, astride, rows_pad);
   CSM_STAMP(cx, 5);     // this warp's MMAs done
   compute_sync();
@@ -475,17 +532,20 @@ __device__ __forceinline__ void gemv_phase(const StreamParams& p, const Phase& P
       const int gn = g.row0 + n;   // packed row index
       switch (P.epi) {
         case EPI_STORE:
-          P.out[(size_t)m * P.out_stride + gn] = __float2bfloat16_rn(v0);
+          st_tag_r(outw + (size_t)m * P.out_stride + gn, tw_pack(v0, otag), R, ors);
           break;
         case EPI_RESID: {   // hf modeling_llama.py:325,331: residual + f(x), both bf16
-          bf16* o = P.out + (size_t)m * P.out_stride + gn;
-          const float r = m == m_first ? resid0 : ldcg_bf16(o);
-          *o = __float2bfloat16_rn(r + v0);
+          uint32_t* o = outw + (size_t)m * P.out_stride + gn;
+          float r;
+          if (m == m_first && (resid0 >> 16) == rtag) r = tw_val(resid0);
+          else r = resid_poll(o + cx.rep * ors, rtag);
+          st_tag_r(o, tw_pack(r + v0, otag), R, ors);
           break;
         }
         case EPI_SWIGLU: {  // hf modeling_llama.py:183: bf16(silu(gate)) * up -> bf16 ; rows (2j,2j+1)=(gate_j,up_j)
-          float sl = bfround(v0 / (1.f + expf(-v0)));
-          P.out[(size_t)m * P.out_stride + (gn >> 1)] = __float2bfloat16_rn(sl * v1);
+          const float sl = bfround(v0 / (1.f + expf(-v0)));
+          if (P.flags & CSM_PF_OUT_PLAIN) P.out[(size_t)m * P.out_stride + (gn >> 1)] = __float2bfloat16_rn(sl * v1);
+          else st_tag_r(outw + (size_t)m * P.out_stride + (gn >> 1), tw_pack(sl * v1, otag), R, ors);
           break;
         }
         case EPI_QKV: {     // rows (2j,2j+1) = RoPE pair (i, i+hd/2) of q/k, or two adjacent v features
@@ -495,6 +555,7 @@ __device__ __forceinline__ void gemv_phase(const StreamParams& p, const Phase& P
           const int cap = P.stack ? CSM_DEC_POS : p.Tcap;
           bf16* kc = P.stack ? p.kc_dec : p.kc_bb;
           bf16* vc = P.stack ? p.vc_dec : p.vc_bb;
+          uint32_t* qrow = outw + (size_t)m * P.out_stride;   // tagged q | k | v of this position
           if (pidx < nq + nk) {
             const bool isq = pidx < nq;
             const int pp = isq ? pidx : pidx - nq;
@@ -506,14 +567,18 @@ __device__ __forceinline__ void gemv_phase(const StreamParams& p, const Phase& P
             // apply_rotary_pos_emb (hf modeling_llama.py:146-168): every product and the sum round to bf16
             const float o1 = bfround(bfround(v0 * cs) + bfround(-v1 * sn));
             const float o2 = bfround(bfround(v1 * cs) + bfround(v0 * sn));
-            bf16* dstp;
-            if (isq) dstp = P.out + (size_t)m * P.out_stride + head * sd.hd + i;
-            else dstp = kc + ((((size_t)P.layer * p.Bmax + m) * sd.kv + head) * cap + pos) * sd.hd + i;
-            dstp[0] = __float2bfloat16_rn(o1);
-            dstp[half] = __float2bfloat16_rn(o2);
+            uint32_t* qd = qrow + (isq ? 0 : sd.heads * sd.hd) + head * sd.hd + i;
+            st_tag_r(qd, tw_pack(o1, otag), R, ors);
+            st_tag_r(qd + half, tw_pack(o2, otag), R, ors);
+            if (!isq) {   // DynamicCache.update (hf cache_utils.py:102-121) as an in-place write at `pos`
+              bf16* dstp = kc + ((((size_t)P.layer * p.Bmax + m) * sd.kv + head) * cap + pos) * sd.hd + i;
+              dstp[0] = __float2bfloat16_rn(o1);
+              dstp[half] = __float2bfloat16_rn(o2);
+            }
           } else {
             const int f = (pidx - nq - nk) * 2;
             const int head = f / sd.hd, d = f - head * sd.hd;
+            st_tag2_r(qrow + (sd.heads + sd.kv) * sd.hd + f, tw_pack(v0, otag), tw_pack(v1, otag), R, ors);
             bf16* dstp = vc + ((((size_t)P.layer * p.Bmax + m) * sd.kv + head) * cap + pos) * sd.hd + d;
             *reinterpret_cast<uint32_t*>(dstp) = pack_bf16(v0, v1);
           }
@@ -528,11 +593,11 @@ __device__ __forceinline__ void gemv_phase(const StreamParams& p, const Phase& P
     }
   }
   if (P.epi == EPI_HEAD) {
-    // publish this CTA's best (logit, id) per sequence; consumers reduce after the barrier
+    // publish this CTA's best (logit, id) per sequence as one tagged 64-bit word; consumers poll and reduce
     compute_sync();
     for (int m = cx.warp; m < M; m += CSM_COMPUTE_WARPS) {
       float best = -INFINITY;
-      int bi = 0x7fffffff;
+      int bi = 0xffff;
       for (int n = cx.lane; n < g.rows; n += 32) {
         float v = cx.red[(size_t)m * rows_pad + n];
         if (better(v, g.row0 + n, best, bi)) { best = v; bi = g.row0 + n; }
@@ -543,7 +608,10 @@ __device__ __forceinline__ void gemv_phase(const StreamParams& p, const Phase& P
         int oi = __shfl_xor_sync(0xffffffffu, bi, o);
         if (better(ov, oi, best, bi)) { best = ov; bi = oi; }
       }
-      if (cx.lane == 0) p.cand[(size_t)cx.c * p.Bmax + m] = make_float2(best, __int_as_float(bi));
+      if (cx.lane < R)   // one copy per lane
+        st_tag64(p.cand + ((size_t)cx.lane * cx.G + cx.c) * p.Bmax + m, ((unsigned long long)otag << 32) |
+                                                                          ((unsigned long long)(bi & 0xffff) << 16) |
+                                                                          (unsigned long long)float_to_bf16_bits(best));
     }
   }
 }
@@ -551,10 +619,10 @@ __device__ __forceinline__ void gemv_phase(const StreamParams& p, const Phase& P
 // ------------------------------------------------------------------ end of frame
 // After the last head: sample codebook 31, publish the 32 ids (modeling_csm.py:657-666) and evaluate
 // the stop rule torch.all(new_frame == 0) (:662).  CTA 0 only.
-__device__ __forceinline__ void finish_phase(const StreamParams& p, const Ctx& cx) {
+__device__ __forceinline__ void finish_phase(const StreamParams& p, const Phase& P, const Ctx& cx) {
   if (cx.c != 0) return;
   const int M = p.B;
-  reduce_candidates(p, cx, CSM_NQ - 1);
+  reduce_candidates(p, cx, CSM_NQ - 1, P.res_ph);
   __threadfence_block();
   if (cx.tid == 0) cx.sflag[1] = 0;
   compute_sync();
@@ -638,12 +706,11 @@ __device__ __forceinline__ void embed_phase(const StreamParams& p, const Ctx& cx
       }
     }
     if (incol) {
-      uint4 o;
-      o.x = pack_bf16(acc[0], acc[1]);
-      o.y = pack_bf16(acc[2], acc[3]);
-      o.z = pack_bf16(acc[4], acc[5]);
-      o.w = pack_bf16(acc[6], acc[7]);
-      *reinterpret_cast<uint4*>(p.h_bb + (size_t)m * H + col) = o;
+      const uint32_t otag = tg(p, cx.ph);
+      uint32_t* o = p.h_bb + (size_t)m * H + col;
+      const size_t rs = (size_t)p.Bmax * H;
+      st_tag4_r(o, tw_pack(acc[0], otag), tw_pack(acc[1], otag), tw_pack(acc[2], otag), tw_pack(acc[3], otag), p.repl, rs);
+      st_tag4_r(o + 4, tw_pack(acc[4], otag), tw_pack(acc[5], otag), tw_pack(acc[6], otag), tw_pack(acc[7], otag), p.repl, rs);
     }
   }
 }
@@ -651,8 +718,10 @@ __device__ __forceinline__ void embed_phase(const StreamParams& p, const Ctx& cx
 // ------------------------------------------------------------------ backbone decode attention (split-KV, GQA)
 // One unit = (sequence, kv-head, 128 cached positions); the 4 (rep) query heads of the group share
 // every K/V byte read.  Units write (max, sum, o[64]) partials; the last unit of a (sequence,
-// kv-head) merges them -- no extra grid barrier.  Softmax in fp32 (sdpa_attention_forward,
-// hf integrations/sdpa_attention.py:40-104; decode step attends to every cached position).
+// kv-head) merges them and publishes the head outputs as tagged words.  q and the K/V of the position
+// being processed are polled from the qkv phase's tagged output; older positions come from the cache.
+// Softmax in fp32 (sdpa_attention_forward, hf integrations/sdpa_attention.py:40-104; a decode step
+// attends to every cached position).
 template <int REP>
 __device__ __forceinline__ void attn_bb_phase(const StreamParams& p, const Phase& P, const Ctx& cx) {
   constexpr int HD = 64;
@@ -664,6 +733,9 @@ __device__ __forceinline__ void attn_bb_phase(const StreamParams& p, const Phase
   float* sm_m = cx.red + 8 * REP * HD;          // [8][REP]
   float* sm_l = sm_m + 8 * REP;                 // [8][REP]
   const int grp = cx.lane >> 3, dl = cx.lane & 7;   // 4 positions per load, 8 lanes x 8 dims each
+  const uint32_t qtag = tg(p, P.src_ph), otag = tg(p, cx.ph);
+  const int Wq = (p.bb.heads + 2 * nk) * HD;        // tagged q | k | v row
+  const uint32_t* qbase = p.q_bb + (size_t)cx.rep * p.Bmax * Wq;
   for (int unit = cx.c; unit < nunits; unit += cx.G) {
     const int sp = unit % nsplit;
     const int kvh = (unit / nsplit) % nk;
@@ -677,7 +749,7 @@ __device__ __forceinline__ void attn_bb_phase(const StreamParams& p, const Phase
 #pragma unroll
     for (int j = 0; j < 4; ++j) {
       const int pj = pbase + 4 * j + grp;
-      if (pj < Ttot) {
+      if (pj < p.pos) {
         kv4[j] = ldcg_u4(Kp + (size_t)pj * HD + dl * 8);
         vv4[j] = ldcg_u4(Vp + (size_t)pj * HD + dl * 8);
       } else {
@@ -685,18 +757,45 @@ __device__ __forceinline__ void attn_bb_phase(const StreamParams& p, const Phase
         vv4[j] = make_uint4(0, 0, 0, 0);
       }
     }
-    // q slice of this lane: REP heads x 8 dims, pre-scaled
+    // q slice of this lane: REP heads x 8 dims, pre-scaled (tagged words from the qkv phase)
     float q[REP][8];
+    {
+      const uint32_t* qw = qbase + (size_t)b * Wq + (kvh * REP) * HD + dl * 8;
+      uint4 qa[REP], qb[REP];
+      bool ok;
+      do {
+        ok = true;
 #pragma unroll
-    for (int h = 0; h < REP; ++h) {
-      uint4 qv = ldcg_u4(p.q_bb + (size_t)b * (p.bb.heads * HD) + (kvh * REP + h) * HD + dl * 8);
-      const uint32_t* u = reinterpret_cast<const uint32_t*>(&qv);
+        for (int h = 0; h < REP; ++h) {
+          qa[h] = ld_tag4(qw + h * HD);
+          qb[h] = ld_tag4(qw + h * HD + 4);
+          ok &= tw_ok4(qa[h], qtag) & tw_ok4(qb[h], qtag);
+        }
+      } while (!__all_sync(0xffffffffu, ok));
 #pragma unroll
-      for (int i = 0; i < 4; ++i) {
-        q[h][2 * i] = bf_lo(u[i]) * p.bb.scale;
-        q[h][2 * i + 1] = bf_hi(u[i]) * p.bb.scale;
+      for (int h = 0; h < REP; ++h) {
+        q[h][0] = tw_val(qa[h].x) * p.bb.scale; q[h][1] = tw_val(qa[h].y) * p.bb.scale;
+        q[h][2] = tw_val(qa[h].z) * p.bb.scale; q[h][3] = tw_val(qa[h].w) * p.bb.scale;
+        q[h][4] = tw_val(qb[h].x) * p.bb.scale; q[h][5] = tw_val(qb[h].y) * p.bb.scale;
+        q[h][6] = tw_val(qb[h].z) * p.bb.scale; q[h][7] = tw_val(qb[h].w) * p.bb.scale;
       }
     }
+    // the position being processed: its K/V are in flight to the cache, take them from the tagged row
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      if (pbase + 4 * j + grp == p.pos) {
+        const uint32_t* kw = qbase + (size_t)b * Wq + p.bb.heads * HD + kvh * HD + dl * 8;
+        const uint32_t* vw = kw + nk * HD;
+        uint4 k0, k1, v0, v1;
+        do {
+          k0 = ld_tag4(kw); k1 = ld_tag4(kw + 4);
+          v0 = ld_tag4(vw); v1 = ld_tag4(vw + 4);
+        } while (!(tw_ok4(k0, qtag) & tw_ok4(k1, qtag) & tw_ok4(v0, qtag) & tw_ok4(v1, qtag)));
+        kv4[j] = make_uint4(tw_pair(k0.x, k0.y), tw_pair(k0.z, k0.w), tw_pair(k1.x, k1.y), tw_pair(k1.z, k1.w));
+        vv4[j] = make_uint4(tw_pair(v0.x, v0.y), tw_pair(v0.z, v0.w), tw_pair(v1.x, v1.y), tw_pair(v1.z, v1.w));
+      }
+    }
+    __syncwarp();
     float s[REP][4];
 #pragma unroll
     for (int j = 0; j < 4; ++j) {
@@ -804,7 +903,8 @@ __device__ __forceinline__ void attn_bb_phase(const StreamParams& p, const Phase
           L += f * ldcg_f32(ps + 1);
           O += f * ldcg_f32(ps + 2 + d);
         }
-        p.attn_bb[(size_t)b * (p.bb.heads * HD) + (kvh * REP + h) * HD + d] = __float2bfloat16_rn(O / L);
+        st_tag_r(p.attn_bb + (size_t)b * (p.bb.heads * HD) + (kvh * REP + h) * HD + d, tw_pack(O / L, otag), p.repl,
+                 (size_t)p.Bmax * p.bb.heads * HD);
       }
       if (cx.tid == 0) p.attn_cnt[b * nk + kvh] = 0u;
     }
@@ -826,9 +926,10 @@ __global__ void __launch_bounds__(CSM_THREADS, 1) csm_stream_kernel(const Stream
   cx.afull = cx.empty + CSM_MAX_SLOTS;
   cx.aempty = cx.afull + 2;
   cx.sflag = reinterpret_cast<volatile int*>(cx.aempty + 2);
+  cx.sprog = reinterpret_cast<volatile unsigned int*>(cx.aempty + 3);
   cx.desc = reinterpret_cast<Phase*>(csm_smem + 256);
-  cx.scratch = reinterpret_cast<float*>(csm_smem + 512);
-  cx.tok = reinterpret_cast<int*>(csm_smem + 1536);
+  cx.scratch = reinterpret_cast<float*>(csm_smem + 512);    // 512 floats
+  cx.tok = reinterpret_cast<int*>(csm_smem + 2560);
   cx.rope = reinterpret_cast<bf16*>(csm_smem + CSM_SM_HDR_BYTES);
   cx.red = reinterpret_cast<float*>(csm_smem + CSM_SM_HDR_BYTES + p.rope_bytes);
   cx.actreg = csm_smem + CSM_SM_HDR_BYTES + p.rope_bytes + p.red_bytes;
@@ -839,6 +940,9 @@ __global__ void __launch_bounds__(CSM_THREADS, 1) csm_stream_kernel(const Stream
   cx.c = blockIdx.x;
   cx.G = gridDim.x;
   cx.slot = cx.slot_par = cx.aslot = cx.aslot_par = 0;
+  cx.ph = p.phase_begin;
+  cx.rep = blockIdx.x % p.repl;
+  cx.prof = nullptr;
 
   if (cx.tid == 0) {
     for (int s = 0; s < CSM_MAX_SLOTS; ++s) {
@@ -849,6 +953,7 @@ __global__ void __launch_bounds__(CSM_THREADS, 1) csm_stream_kernel(const Stream
       mbar_init(&cx.afull[s], 1);
       mbar_init(&cx.aempty[s], CSM_COMPUTE_WARPS);
     }
+    *cx.sprog = 0u;
     mbar_fence_init();
   }
   if (cx.tid < CSM_COMPUTE_THREADS) {
@@ -869,11 +974,13 @@ __global__ void __launch_bounds__(CSM_THREADS, 1) csm_stream_kernel(const Stream
           __ldg(reinterpret_cast<const uint4*>(p.phases + p.phase_begin) + cx.tid);
   }
   __syncthreads();
+  const int bar_base = p.phases[p.phase_begin].bar_idx;   // grid-barrier events before/at the first phase
 
   if (cx.warp == CSM_COMPUTE_WARPS) {
     // ===================== weight stream producer =====================
     if (cx.lane == 0) {
-      uint32_t s = 0, round = 0;
+      const uint64_t pol = l2_policy_evict_first();
+      uint32_t s = 0, round = 0, prog = 0;
       for (int ph = p.phase_begin; ph < p.phase_end; ++ph) {
         const Phase P = p.phases[ph];
         if (P.type != PH_GEMV) continue;
@@ -884,8 +991,11 @@ __global__ void __launch_bounds__(CSM_THREADS, 1) csm_stream_kernel(const Stream
           const uint32_t bytes = (uint32_t)tiles * g.rows * 32u;
           if (round > 0) mbar_wait(&cx.empty[s], (round - 1u) & 1u);
           mbar_expect_tx(&cx.full[s], bytes);
-          bulk_g2s(cx.ring + (size_t)s * p.slot_bytes, src, bytes, &cx.full[s]);
+          if (p.evict_first) bulk_g2s_hint(cx.ring + (size_t)s * p.slot_bytes, src, bytes, &cx.full[s], pol);
+          else bulk_g2s(cx.ring + (size_t)s * p.slot_bytes, src, bytes, &cx.full[s]);
           src += bytes;
+          prog += bytes;
+          *cx.sprog = prog;
           if (++s == (uint32_t)p.n_slots) { s = 0; ++round; }
         }
       }
@@ -893,7 +1003,7 @@ __global__ void __launch_bounds__(CSM_THREADS, 1) csm_stream_kernel(const Stream
     return;
   }
   if (cx.warp == CSM_COMPUTE_WARPS + 1) {
-    // ===================== activation stream producer (K=8192 phases) =====================
+    // ===================== activation stream producer (K=8192 phases at batch > 4) =====================
     if (cx.lane == 0) {
       uint32_t ait = 0;
       for (int ph = p.phase_begin; ph < p.phase_end; ++ph) {
@@ -903,7 +1013,7 @@ __global__ void __launch_bounds__(CSM_THREADS, 1) csm_stream_kernel(const Stream
         if (g.nchunks == 0) continue;
         const bf16* actp = P.act;
         const int act_stride = P.act_stride;
-        if (p.use_barrier && ph > p.phase_begin) grid_wait(p.bar_counter, (unsigned)(ph - p.phase_begin) * cx.G);
+        if (p.use_barrier && ph > p.phase_begin) grid_wait(p.bar_counter, (unsigned)(P.bar_idx - bar_base) * cx.G);
         fence_proxy_async();
         const int astride_b = (g.tpc * 16 + 8) * 2;
         for (int ch = 0; ch < g.nchunks; ++ch) {
@@ -922,20 +1032,66 @@ __global__ void __launch_bounds__(CSM_THREADS, 1) csm_stream_kernel(const Stream
     }
     return;
   }
+  if (cx.warp == CSM_COMPUTE_WARPS + 2) {
+    // ===================== L2 prefetcher =====================
+    // Issues HBM->L2 prefetches for this CTA's weight stream up to l2_ahead_bytes beyond what the ring
+    // has requested, so that DRAM never idles while the ring is full and the compute warps are inside
+    // a latency-bound stretch (staging, epilogue, attention).  Also: the norm weights of upcoming
+    // phases (one CTA each) and the K/V blocks of this CTA's first backbone attention units.
+    if (cx.lane == 0 && p.l2_ahead_bytes > 0) {
+      uint32_t pf = 0;
+      for (int ph = p.phase_begin; ph < p.phase_end; ++ph) {
+        const Phase P = p.phases[ph];
+        if (P.type == PH_ATTN_BB) {
+          const int Ttot = p.pos + 1, nk = p.bb.kv;
+          const int nsplit = (Ttot + CSM_ATT_SPLIT - 1) / CSM_ATT_SPLIT;
+          const int nunits = p.B * nk * nsplit;
+          int done = 0;
+          for (int unit = cx.c; unit < nunits && done < 4; unit += cx.G, ++done) {
+            const int sp = unit % nsplit, kvh = (unit / nsplit) % nk, b = unit / (nsplit * nk);
+            const size_t off = ((((size_t)P.layer * p.Bmax + b) * nk + kvh) * (size_t)p.Tcap + (size_t)sp * CSM_ATT_SPLIT) * 64;
+            const int npos = min(CSM_ATT_SPLIT, p.pos - sp * CSM_ATT_SPLIT);   // cached positions only
+            if (npos > 0) {
+              bulk_prefetch_l2(p.kc_bb + off, (uint32_t)npos * 128u);
+              bulk_prefetch_l2(p.vc_bb + off, (uint32_t)npos * 128u);
+            }
+          }
+          continue;
+        }
+        if (P.type != PH_GEMV) continue;
+        if (P.norm_w != nullptr && (ph % cx.G) == cx.c) bulk_prefetch_l2(P.norm_w, (uint32_t)P.K * 2u);
+        const Geom g = csm_geom(P, cx.c);
+        const unsigned char* src = reinterpret_cast<const unsigned char*>(P.w) + (size_t)g.row0 * P.K * 2;
+        const uint32_t total = (uint32_t)g.rows * (uint32_t)P.K * 2u;
+        for (uint32_t off = 0; off < total; off += 32768u) {
+          const uint32_t n = min(32768u, total - off);
+          uint32_t prog = *cx.sprog;
+          while ((int)(pf - prog) > p.l2_ahead_bytes) {
+            __nanosleep(500);
+            prog = *cx.sprog;
+          }
+          if ((int)(pf + n - prog) > 0) bulk_prefetch_l2(src + off, n);   // skip what the ring has already asked for
+          pf += n;
+        }
+      }
+    }
+    return;
+  }
 
   // ===================== compute warps =====================
   for (int ph = p.phase_begin; ph < p.phase_end; ++ph) {
     unsigned long long* prof = nullptr;   // debug stamps of the first and the last CTA: [cta][phase][8]
     if (p.prof != nullptr && cx.tid == 0 && (cx.c == 0 || cx.c == cx.G - 1))
-      prof = p.prof + ((size_t)(cx.c == 0 ? 0 : 1) * p.n_phases_total + ph) * 8;
+      prof = p.prof + ((size_t)(cx.c == 0 ? 0 : 1) * p.n_phases_total + ph) * 16;
     cx.prof = prof;
-    if (p.use_barrier && ph > p.phase_begin) {
-      if (cx.tid == 0) grid_wait(p.bar_counter, (unsigned)(ph - p.phase_begin) * cx.G);
-      if (prof) prof[0] = clock64();     // barrier observed
-      compute_sync();
-    }
+    cx.ph = ph;
     // descriptor of this phase is in shared memory; fetch the next one while this phase runs
     const Phase P = cx.desc[ph & 1];
+    if ((P.flags & CSM_PF_BAR_IN) && p.use_barrier && ph > p.phase_begin) {
+      if (cx.tid == 0) grid_wait(p.bar_counter, (unsigned)(P.bar_idx - bar_base) * cx.G);
+      compute_sync();
+    }
+    if (prof) prof[0] = clock64();       // (barrier observed)
     uint4 nxt = make_uint4(0, 0, 0, 0);
     const bool fetch = cx.warp == CSM_COMPUTE_WARPS - 1 && cx.lane < 8 && ph + 1 < p.phase_end;
     if (fetch) nxt = __ldg(reinterpret_cast<const uint4*>(p.phases + ph + 1) + cx.lane);
@@ -945,18 +1101,23 @@ __global__ void __launch_bounds__(CSM_THREADS, 1) csm_stream_kernel(const Stream
       case PH_GEMV: gemv_phase<NB>(p, P, cx); break;
       case PH_ATTN_BB: attn_bb_phase<REP>(p, P, cx); break;
       case PH_ATTN_DEC: attn_dec_phase(p, P, cx); break;
-      case PH_FINISH: finish_phase(p, cx); break;
+      case PH_FINISH: finish_phase(p, P, cx); break;
     }
     if (prof) prof[2] = clock64();       // this thread's share of the body done
     if (fetch) reinterpret_cast<uint4*>(&cx.desc[(ph + 1) & 1])[cx.lane] = nxt;
     if (ph + 1 < p.phase_end) {
-      compute_sync();
-      if (p.use_barrier && cx.tid == 0) {
+      compute_sync();                    // shared-memory reuse between phases; next descriptor visible
+      if ((P.flags & CSM_PF_BAR_OUT) && p.use_barrier && cx.tid == 0) {
         // release: everything this CTA wrote (ordered before by the CTA barrier) becomes visible before the count
         asm volatile("red.release.gpu.global.add.u32 [%0], 1;" ::"l"(p.bar_counter) : "memory");
       }
     }
-    if (prof) prof[3] = clock64();       // arrived at the grid barrier
+    if (prof) prof[3] = clock64();       // end of phase
+    if (p.prof != nullptr && cx.tid == 0) {   // wall-clock end of this phase for every CTA (skew between CTAs)
+      unsigned long long gt;
+      asm volatile("mov.u64 %0, %globaltimer;" : "=l"(gt));
+      p.prof[(size_t)32 * p.n_phases_total + (size_t)cx.c * p.n_phases_total + ph] = gt;
+    }
   }
 }
 

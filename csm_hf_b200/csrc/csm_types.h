@@ -8,20 +8,28 @@ typedef __nv_bfloat16 bf16;
 
 #define CSM_COMPUTE_WARPS 8
 #define CSM_COMPUTE_THREADS (CSM_COMPUTE_WARPS * 32)
-#define CSM_THREADS (CSM_COMPUTE_THREADS + 64)  // + weight-stream warp + activation-stream warp
+#define CSM_THREADS (CSM_COMPUTE_THREADS + 96)  // + weight-stream warp + activation-stream warp + L2-prefetch warp
 #define CSM_MAX_SLOTS 8
 #define CSM_NQ 32            // codebooks per frame (modeling_csm.py:66)
 #define CSM_DEC_POS 32       // decoder positions per frame: last_h + 31 codebook embeddings
 #define CSM_ATT_SPLIT 128    // backbone positions per split-KV unit
 #define CSM_MAX_ROWS 256     // at most 16 m-tiles of 16 weight rows per CTA per matrix
-#define CSM_SM_HDR_BYTES 2048   // mbarriers, phase-descriptor slots, small scratch
+#define CSM_SM_HDR_BYTES 4096   // mbarriers, phase-descriptor slots, 2 KB scratch, token slots
 
 enum PhaseType { PH_EMBED = 0, PH_GEMV = 1, PH_ATTN_BB = 2, PH_ATTN_DEC = 3, PH_FINISH = 4 };
 enum ActMode { ACT_NORM = 0, ACT_PLAIN = 1, ACT_GATHER = 2, ACT_STREAM = 3, ACT_ATTN = 4 };
 enum EpiMode { EPI_STORE = 0, EPI_RESID = 1, EPI_SWIGLU = 2, EPI_QKV = 3, EPI_HEAD = 4 };
 
+// Phase::flags
+#define CSM_PF_BAR_IN 1      // a grid barrier precedes this phase (its input is plain memory read by the TMA engine)
+#define CSM_PF_BAR_OUT 2     // arrive on the grid barrier after this phase (the next phase has BAR_IN)
+#define CSM_PF_OUT_PLAIN 4   // EPI_SWIGLU writes plain bf16 (consumer streams it with bulk copies) instead of tagged words
+
 // One step of the per-frame program.  A frame is ~800 of these executed in order by every
-// CTA of one persistent launch, with a grid-wide barrier between consecutive phases.
+// CTA of one persistent launch.  Phases are chained by DATAFLOW, not by barriers: every value that
+// crosses CTAs travels as a 32-bit "tagged word" (bf16 payload | 16-bit tag of the producing phase),
+// written with one relaxed store and polled by the consumer, so the hand-over costs one trip
+// through L2 and needs no fence (payload and flag are the same atomic word).
 // 128 bytes: the kernel copies the next descriptor into shared memory while a phase runs.
 struct __align__(16) Phase {
   int type;         // PhaseType
@@ -40,11 +48,14 @@ struct __align__(16) Phase {
   int q, r;
   int tpc[2];       // k16-tiles per ring chunk
   int nch[2];       // chunks per CTA
-  int pad_[4];
+  int src_ph;       // phase that produced `act` (tag to poll for); ATTN phases: the qkv phase
+  int res_ph;       // EPI_RESID: phase that last wrote the residual stream; ACT_GATHER / PH_FINISH: the head phase
+  int flags;        // CSM_PF_*
+  int bar_idx;      // number of BAR_IN phases in table[0..this]
   const bf16* w;        // packed weights, see csm_pack.cu
-  const bf16* act;      // activation rows (ACT_GATHER: embedding table)
+  const bf16* act;      // activation rows: tagged words (uint32) unless ACT_GATHER (embedding table, bf16) / ACT_STREAM (bf16)
   const bf16* norm_w;   // ACT_NORM weight
-  bf16* out;            // STORE/RESID/SWIGLU destination; QKV: q buffer; HEAD: logits (nullable)
+  bf16* out;            // STORE/RESID/SWIGLU/QKV destination (tagged words); HEAD: logits (plain bf16, nullable)
   bf16* norm_out;       // optional copy of the normalised rows (last_hidden_state)
 };
 static_assert(sizeof(Phase) == 128, "Phase must be 128 bytes");
@@ -59,6 +70,11 @@ struct StreamParams {
   const Phase* phases;
   int phase_begin, phase_end;
   int use_barrier;              // 0 in stepped mode (one launch per phase)
+  unsigned int tagbase;         // tag of phase ph = (tagbase + ph) & 0xffff, never 0 (0 = "never written")
+  int repl;                     // copies of every tagged vector (consumer CTA c polls copy c % repl): spreads the pollers
+                                // over repl x more L2 lines, so no line is hammered by all 148 CTAs at once
+  int evict_first;              // weight bulk copies carry an L2 evict-first hint
+  int l2_ahead_bytes;           // how far (bytes of this CTA's weight stream) the L2 prefetcher runs ahead of the ring
   int B;                        // sequences in this call
   int pos;                      // backbone position of the token being processed (= cached length)
   int Bmax, Tcap;
@@ -68,19 +84,19 @@ struct StreamParams {
   // KV caches: [L][Bmax][kv][cap][hd]
   bf16 *kc_bb, *vc_bb, *kc_dec, *vc_dec;
   const bf16 *cos_bb, *sin_bb, *cos_dec, *sin_dec;   // [n_pos][hd/2]
-  bf16 *q_bb, *q_dec;           // [Bmax][heads*hd]
-  bf16 *attn_bb, *attn_dec;     // attention outputs [Bmax][heads*hd]
+  uint32_t *q_bb, *q_dec;       // tagged [Bmax][(heads + 2 kv)*hd]: q | k | v of the position being processed
+  uint32_t *attn_bb, *attn_dec; // tagged attention outputs [Bmax][heads*hd]
   float* attn_part;             // [Bmax][heads_bb][nsplit_max][hd+2]
   int nsplit_max;
   unsigned int* attn_cnt;       // [Bmax][kv_bb]
-  float2* cand;                 // [grid][Bmax] per-CTA (best logit, index) of the last head phase
+  unsigned long long* cand;     // [grid][Bmax] per-CTA candidate of the last head phase: tag<<32 | index<<16 | bf16 logit
   int* samples;                 // [Bmax][32] argmax of every head
   int* fed;                     // [Bmax][32] tokens fed onward (== samples unless forced)
   int forced;
   const long long* ids;         // PH_EMBED: [B][33] or null (use `fed`, audio slots only)
   const int* mask;              // [B][33] or null
   const bf16 *text_emb, *audio_emb;
-  bf16* h_bb;                   // backbone residual stream [Bmax][Hb]
+  uint32_t* h_bb;               // backbone residual stream, tagged [Bmax][Hb]
   long long* out_frames;        // [B][out_stride] int64 or null; this frame at out_off
   long long out_stride, out_off;
   int* stop_flag;

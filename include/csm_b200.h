@@ -143,9 +143,11 @@ int csm_debug_copy(CsmCtx* ctx, int which, void* dst_device, int64_t max_bytes, 
 int csm_debug_run_phases(CsmCtx* ctx, const int64_t* ids, const int32_t* mask, int B, int ph_begin, int ph_end,
                          int forced, void* stream);
 int csm_debug_set_cache_len(CsmCtx* ctx, int len);
-/* One decode frame with per-phase clock64 stamps of the first and the last CTA:
- * clocks_host[2][phases][8] = (barrier observed, body start, body end, arrived at next barrier,
- *   activations staged, own MMAs done, all MMAs done, unused),
+/* One decode frame with per-phase stamps.  clocks_host holds (32 + grid) * phases uint64:
+ *   [2][phases][16] clock64 of the first and the last CTA: (phase top, body start, body end, phase end,
+ *     activations staged, own MMAs done, all MMAs done, first weight chunk resident, input poll succeeded,
+ *     poll iterations, unused...), then
+ *   [grid][phases] %globaltimer (ns) at the end of every phase of every CTA (skew between CTAs).
  * info_host[4*phases] = (type, epilogue, stack, act_mode) per phase. Synchronises. */
 int csm_debug_profile_frame(CsmCtx* ctx, int B, uint64_t* clocks_host, int32_t* info_host, void* stream);
 

@@ -5,5 +5,6 @@ timeout 900 python -m pytest tests -m gpu -x -q > gpurun_out/pytest_gpu.log 2>&1
 tail -15 gpurun_out/pytest_gpu.log
 for b in ${BATCHES:-1}; do
   timeout 300 python tools/phase_profile.py --batch $b > gpurun_out/phase_b$b.txt 2>&1
-  head -24 gpurun_out/phase_b$b.txt
+  head -${LINES_PER:-18} gpurun_out/phase_b$b.txt
 done
+if [ -n "$EXTRA" ]; then bash -c "$EXTRA"; fi

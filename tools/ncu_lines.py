@@ -1,34 +1,45 @@
-"""Rank CUDA source lines of an ncu --import-source report by warp-stall samples.
-usage: ncu -i X.ncu-rep --page source --print-source cuda,sass --csv > src.csv; python tools/ncu_lines.py src.csv [N]"""
+"""Join an ncu SASS-level source page (ncu -i X.ncu-rep --page source --csv) with nvdisasm -g -c line info
+and print the source lines with the most warp-stall samples.
+usage: python tools/ncu_lines.py src.csv dis.txt KERNEL_SUBSTR [topN]"""
 import csv
+import re
 import sys
+from collections import Counter
 
 rows = list(csv.reader(open(sys.argv[1])))
-top = int(sys.argv[2]) if len(sys.argv) > 2 else 40
-cur, hdr, out = None, None, []
-for r in rows:
-    if not r:
+hdr = rows[1]
+ia, isamp, iex = hdr.index("Address"), hdr.index("# Samples"), hdr.index("Instructions Executed")
+isrc = hdr.index("Source")
+sass = [(int(r[ia], 16), int(r[isamp] or 0), int(r[iex] or 0), r[isrc].strip()) for r in rows[2:] if len(r) > isamp and r[ia].startswith("0x")]
+base = sass[0][0]
+lines, cur, fn = {}, None, None
+for line in open(sys.argv[2]):
+    m = re.match(r'\s*//## File "([^"]+)", line (\d+)', line)
+    if m:
+        cur = (m.group(1).split('/')[-1], int(m.group(2)))
         continue
-    if r[0] == 'File Path':
-        cur = r[1].split('/')[-1]
+    m = re.match(r'\.text\.(\S+):', line)
+    if m:
+        fn = m.group(1)
         continue
-    if r[0] == 'Function Name':
-        continue
-    if r[0] == 'Line No':
-        hdr = r
-        continue
-    if hdr is None or r[2] != '-':
-        continue
-    try:
-        s = int(r[hdr.index('# Samples')])
-    except ValueError:
-        continue
-    out.append((s, cur, r))
-tot = sum(s for s, _, _ in out)
-print('total samples', tot)
-stall = [i for i, h in enumerate(hdr) if h.startswith('stall_') and 'Not Issued' not in h]
-ie = hdr.index('Instructions Executed')
-out.sort(key=lambda x: -x[0])
-for s, f, r in out[:top]:
-    st = sorted([(int(r[i] or 0), hdr[i][6:]) for i in stall], reverse=True)[:3]
-    print(f"{s:7d} {100 * s / tot:5.1f}% {f}:{r[0]:>4s} inst={int(r[ie]):>10d} {r[1].strip()[:84]:84s} {st}")
+    m = re.match(r'\s+/\*([0-9a-f]+)\*/\s+(\S.*)', line)
+    if fn and sys.argv[3] in fn and m:
+        lines[int(m.group(1), 16)] = cur
+samp, exe = Counter(), Counter()
+tot = 0
+for a, s, e, txt in sass:
+    k = lines.get(a - base)
+    samp[k] += s
+    exe[k] += e
+    tot += s
+top = int(sys.argv[4]) if len(sys.argv) > 4 else 40
+src = open('csm_hf_b200/csrc/csm_stream.cu').read().split('\n')
+com = open('csm_hf_b200/csrc/csm_common.cuh').read().split('\n')
+print("total samples", tot)
+for k, s in samp.most_common(top):
+    text = ""
+    if k and k[0] == 'csm_stream.cu':
+        text = src[k[1] - 1].strip()
+    elif k and k[0] == 'csm_common.cuh':
+        text = com[k[1] - 1].strip()
+    print(f"{100 * s / tot:5.1f}% {s:7d} exec {exe[k]:10d}  {k}  {text[:110]}")
