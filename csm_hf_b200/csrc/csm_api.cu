@@ -193,6 +193,7 @@ int build_stack(CsmCtx* ctx, Stack& S, const CsmLlamaShape& sh, const void* cons
   StackDims& d = S.d;
   d.H = sh.hidden; d.I = sh.inter; d.L = sh.layers; d.heads = sh.heads; d.kv = sh.kv_heads;
   d.hd = sh.hidden / sh.heads; d.eps = sh.eps; d.scale = 1.0f / sqrtf((float)d.hd);
+  d.hdl = d.hd == 128 ? 7 : 6;
   const int H = d.H, I = d.I, hd = d.hd, half = hd / 2;
   const int nq = d.heads * hd, nkv = d.kv * hd;
   S.layers.resize(d.L);
@@ -359,11 +360,25 @@ int plan_smem(CsmCtx* ctx) {
     const int U = P.N / P.gran;
     P.q = U / G;
     P.r = U % G;
-    for (int hi = 0; hi < 2; ++hi) {
-      const int rows = (P.q + (hi ? 1 : 0)) * P.gran;
-      if (rows == 0 || (hi && P.r == 0)) continue;
+    const int g4 = P.K / 4;
+    P.gsh = -1;
+    if ((g4 & (g4 - 1)) == 0) { P.gsh = 0; while ((1 << P.gsh) < g4) ++P.gsh; }
+    if (P.act_mode != ACT_STREAM && P.gsh < 6)
+      return fail(ctx, CSM_EINVAL, "reduction length %d: the staging path needs K/4 to be a power of two >= 64", P.K);
+    for (int cls = 0; cls < 2; ++cls) {
+      GeoC& gc = P.geo[cls];
+      memset(&gc, 0, sizeof gc);
+      const int rows = (P.q + (cls == 0 ? 1 : 0)) * P.gran;
+      gc.rows = rows;
       const int mt = (rows + 15) / 16;
       const int ns = mt >= 5 ? 8 : (mt >= 3 ? 4 : (mt >= 2 ? 2 : 1));
+      gc.mtiles = mt;
+      gc.ksl = ns == 8 ? 0 : (ns == 4 ? 1 : (ns == 2 ? 2 : 3));
+      gc.rows_pad = mt * 16 + 4;
+      gc.upc = rows / P.gran;
+      gc.ush = 0;
+      while ((1 << gc.ush) < gc.upc) ++gc.ush;
+      if (rows == 0 || (cls == 0 && P.r == 0)) continue;
       const int need = (8 / ns) * ctx->m_alloc * (mt * 16 + 4) * 4;
       if (need > red) red = need;
     }
@@ -373,6 +388,11 @@ int plan_smem(CsmCtx* ctx) {
   if (ctx->direct_mlp) {
     const int imax = ctx->bb.d.I > ctx->dec.d.I ? ctx->bb.d.I : ctx->dec.d.I;
     const int need = ctx->Bmax * (imax + 8) * 2;
+    if (need > ctx->act_region) ctx->act_region = need;
+  }
+  if (!ctx->direct_mlp) {
+    // TMA-streamed down_proj input: two slots of [m_alloc][tpc*16+8] bf16 with tpc >= 16 k-tiles
+    const int need = 2 * ctx->m_alloc * (16 * 16 + 8) * 2;
     if (need > ctx->act_region) ctx->act_region = need;
   }
   ctx->act_region = (ctx->act_region + 255) / 256 * 256;
@@ -395,19 +415,24 @@ int plan_smem(CsmCtx* ctx) {
   for (Phase& P : ctx->table) {
     if (P.type != PH_GEMV) continue;
     const int ntiles = P.K / 16;
-    for (int hi = 0; hi < 2; ++hi) {
-      const int rows = (P.q + (hi ? 0 : 1)) * P.gran;   // index 0 = larger share
+    for (int cls = 0; cls < 2; ++cls) {
+      GeoC& gc = P.geo[cls];
+      const int rows = gc.rows;
       int tpc = 0, nch = 0;
       if (rows > 0) {
         tpc = ctx->slot_bytes / (rows * 32);
         if (tpc > ntiles) tpc = ntiles;
         if (P.act_mode == ACT_STREAM && tpc > ctx->stream_tpc_max) tpc = ctx->stream_tpc_max;
-        if (tpc >= 8) tpc &= ~7;   // the 8 warps split a chunk's k-tiles evenly
-        if (tpc < 1) tpc = 1;
+        // every chunk must hold a multiple of 2*ks k16-tiles: each warp then consumes whole (tl, tl+ks) pairs
+        const int unit = 2 << gc.ksl;
+        tpc = tpc / unit * unit;
+        if (tpc < unit || ntiles % unit)
+          return fail(ctx, CSM_EINVAL, "matrix %dx%d: %d rows per CTA do not fit a ring slot in units of %d k-tiles", P.N,
+                      P.K, rows, unit);
         nch = (ntiles + tpc - 1) / tpc;
       }
-      P.tpc[hi] = tpc;
-      P.nch[hi] = nch;
+      gc.tpc = tpc;
+      gc.nch = nch;
     }
   }
   return 0;
@@ -638,11 +663,7 @@ int csm_create(const CsmShapes* sh, const CsmWeights* w, int max_batch, int max_
   DA(ctx->kc_dec, (size_t)d.L * B * d.kv * CSM_DEC_POS * d.hd);
   DA(ctx->vc_dec, (size_t)d.L * B * d.kv * CSM_DEC_POS * d.hd);
   // every tagged vector exists in `repl` copies so that no L2 line is polled by all CTAs at once
-  ctx->repl = 1;   // measured: replication does not pay on B200 (polls are one L2 trip either way)
-  if (const char* e = getenv("CSM_REPL")) ctx->repl = atoi(e);
-  if (ctx->repl < 1) ctx->repl = 1;
-  if (ctx->repl > 32) ctx->repl = 32;
-  if (ctx->repl > ctx->G) ctx->repl = ctx->G;
+  ctx->repl = 1;   // (replicating the vectors to spread the pollers was measured: no gain on B200)
   if (const char* e = getenv("CSM_EVICT_FIRST")) ctx->evict_first = atoi(e) != 0;
   const size_t R = ctx->repl;
   DA(ctx->h_bb, R * B * b.H); DA(ctx->h_dec, R * B * d.H);

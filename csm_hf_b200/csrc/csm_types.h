@@ -30,7 +30,19 @@ enum EpiMode { EPI_STORE = 0, EPI_RESID = 1, EPI_SWIGLU = 2, EPI_QKV = 3, EPI_HE
 // crosses CTAs travels as a 32-bit "tagged word" (bf16 payload | 16-bit tag of the producing phase),
 // written with one relaxed store and polled by the consumer, so the hand-over costs one trip
 // through L2 and needs no fence (payload and flag are the same atomic word).
-// 128 bytes: the kernel copies the next descriptor into shared memory while a phase runs.
+// 256 bytes: the kernel copies the next descriptor into shared memory while a phase runs.
+// Row split / chunking of one weight matrix for one class of CTAs, computed on the host (plan_smem) so that
+// the kernel's per-phase prologue is a handful of loads instead of divisions and loops.
+// Class 0: CTAs c < r (q+1 granules); class 1: the others (q granules).
+struct GeoC {
+  int rows;       // packed weight rows owned by a CTA of this class
+  int tpc, nch;   // k16-tiles per ring chunk, chunks per CTA
+  int mtiles;     // 16-row m-tiles
+  int ksl;        // log2 of the split-K ways over the 8 compute warps (ks = 1<<ksl, ns = 8>>ksl m-tile groups)
+  int rows_pad;   // mtiles*16+4: row stride of the split-K partial sums in shared memory
+  int upc, ush;   // epilogue granules per CTA, log2 of the next power of two
+};
+
 struct __align__(16) Phase {
   int type;         // PhaseType
   int act_mode;     // ActMode   (PH_GEMV)
@@ -44,24 +56,28 @@ struct __align__(16) Phase {
   int act_stride;   // elements between activation rows
   int out_stride;
   // row split over the grid, computed on the host for the launch grid G: CTAs c < r own q+1
-  // granules, the others q; [0] = values for the larger share, [1] for the smaller
+  // granules, the others q
   int q, r;
-  int tpc[2];       // k16-tiles per ring chunk
-  int nch[2];       // chunks per CTA
   int src_ph;       // phase that produced `act` (tag to poll for); ATTN phases: the qkv phase
   int res_ph;       // EPI_RESID: phase that last wrote the residual stream; ACT_GATHER / PH_FINISH: the head phase
   int flags;        // CSM_PF_*
   int bar_idx;      // number of BAR_IN phases in table[0..this]
+  int gsh;          // log2(K/4) when K/4 is a power of two (staging index math by shifts), else -1
+  int pad0_;
   const bf16* w;        // packed weights, see csm_pack.cu
   const bf16* act;      // activation rows: tagged words (uint32) unless ACT_GATHER (embedding table, bf16) / ACT_STREAM (bf16)
   const bf16* norm_w;   // ACT_NORM weight
   bf16* out;            // STORE/RESID/SWIGLU/QKV destination (tagged words); HEAD: logits (plain bf16, nullable)
   bf16* norm_out;       // optional copy of the normalised rows (last_hidden_state)
+  long long pad1_;
+  GeoC geo[2];
+  int pad2_[16];
 };
-static_assert(sizeof(Phase) == 128, "Phase must be 128 bytes");
+static_assert(sizeof(Phase) == 256, "Phase must be 256 bytes");
 
 struct StackDims {
   int H, I, L, heads, kv, hd;
+  int hdl;          // log2(hd) (head_dim is 64 or 128)
   float eps;
   float scale;      // hd^-0.5
 };
@@ -116,22 +132,16 @@ struct Geom {
   int ntiles;         // K/16
   int tpc;            // k16-tiles per ring slot
   int nchunks;
-  int mtiles;         // 16-row m-tiles
-  int ns, ks;         // m-tile split and k split over the 8 compute warps (ns*ks == 8)
 };
 
 __host__ __device__ inline Geom csm_geom(const Phase& P, int c) {
   Geom g;
   const int hi = c < P.r;
-  const int cnt = P.q + hi;
-  const int start = c * P.q + (hi ? c : P.r);
-  g.row0 = start * P.gran;
-  g.rows = cnt * P.gran;
+  const GeoC& gc = P.geo[hi ? 0 : 1];
+  g.row0 = (c * P.q + (hi ? c : P.r)) * P.gran;
+  g.rows = gc.rows;
   g.ntiles = P.K >> 4;
-  g.tpc = hi ? P.tpc[0] : P.tpc[1];
-  g.nchunks = hi ? P.nch[0] : P.nch[1];
-  g.mtiles = (g.rows + 15) >> 4;
-  g.ns = g.mtiles >= 5 ? 8 : (g.mtiles >= 3 ? 4 : (g.mtiles >= 2 ? 2 : 1));
-  g.ks = 8 / g.ns;
+  g.tpc = gc.tpc;
+  g.nchunks = gc.nch;
   return g;
 }
