@@ -275,12 +275,21 @@ void add_layer_phases(CsmCtx* ctx, Stack& S, int stack, int l, int dec_pos, bool
   P.dec_pos = dec_pos;
   ctx->table.push_back(P);
   if (kv_only) return;
-  const int ia = idx();
-  memset(&P, 0, sizeof P);
-  P.type = stack ? PH_ATTN_DEC : PH_ATTN_BB; P.stack = stack; P.layer = l; P.dec_pos = dec_pos; P.src_ph = iq;
-  ctx->table.push_back(P);
-  const int io = idx();
-  ctx->table.push_back(gemv(ACT_PLAIN, EPI_RESID, 1, d.H, nq, stack, l, L.p_o, at, nq, nullptr, h, d.H, ia, h_ph));
+  int io;
+  if (stack && ctx->fuse_attn) {
+    // small batch: every CTA computes the (tiny) decoder attention itself while staging o_proj's input
+    io = idx();
+    P = gemv(ACT_ATTN, EPI_RESID, 1, d.H, nq, stack, l, L.p_o, qb, nq + 2 * nkv, nullptr, h, d.H, iq, h_ph);
+    P.dec_pos = dec_pos;
+    ctx->table.push_back(P);
+  } else {
+    const int ia = idx();
+    memset(&P, 0, sizeof P);
+    P.type = stack ? PH_ATTN_DEC : PH_ATTN_BB; P.stack = stack; P.layer = l; P.dec_pos = dec_pos; P.src_ph = iq;
+    ctx->table.push_back(P);
+    io = idx();
+    ctx->table.push_back(gemv(ACT_PLAIN, EPI_RESID, 1, d.H, nq, stack, l, L.p_o, at, nq, nullptr, h, d.H, ia, h_ph));
+  }
   const int ig = idx();
   P = gemv(ACT_NORM, EPI_SWIGLU, 2, 2 * d.I, d.H, stack, l, L.p_gu, h, d.H, L.ln2, mlp, d.I, io);
   if (!ctx->direct_mlp) P.flags |= CSM_PF_OUT_PLAIN | CSM_PF_BAR_OUT;
@@ -388,6 +397,13 @@ int plan_smem(CsmCtx* ctx) {
   if (ctx->direct_mlp) {
     const int imax = ctx->bb.d.I > ctx->dec.d.I ? ctx->bb.d.I : ctx->dec.d.I;
     const int need = ctx->Bmax * (imax + 8) * 2;
+    if (need > ctx->act_region) ctx->act_region = need;
+  }
+  if (ctx->fuse_attn) {
+    // fused decoder attention: o_proj input rows + K|V of <= 32 cached positions (padded rows) + q scratch
+    const StackDims& d = ctx->dec.d;
+    const int need = ctx->m_alloc * (d.heads * d.hd + 8) * 2 + ctx->Bmax * 2 * d.kv * CSM_DEC_POS * (d.hd + 8) * 2 +
+                     CSM_COMPUTE_WARPS * d.hd * 4;
     if (need > ctx->act_region) ctx->act_region = need;
   }
   if (!ctx->direct_mlp) {
@@ -692,7 +708,7 @@ int csm_create(const CsmShapes* sh, const CsmWeights* w, int max_batch, int max_
   CK(cudaMemsetAsync(ctx->n_frames, 0, 16, st));
   CK(cudaMemsetAsync(ctx->samples, 0, B * CSM_NQ * sizeof(int), st));
   CK(cudaMemsetAsync(ctx->fed, 0, B * CSM_NQ * sizeof(int), st));
-  ctx->fuse_attn = 0;   // measured slower (148 CTAs re-reading the same K/V lines from L2); kept behind CSM_FUSE_ATTN
+  ctx->fuse_attn = max_batch <= 2;
   ctx->direct_mlp = max_batch <= 4;
   if (const char* e = getenv("CSM_FUSE_ATTN")) ctx->fuse_attn = atoi(e) != 0;
   if (const char* e = getenv("CSM_DIRECT_MLP")) ctx->direct_mlp = atoi(e) != 0;

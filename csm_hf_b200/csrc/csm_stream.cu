@@ -233,6 +233,107 @@ __device__ __forceinline__ void attn_dec_phase(const StreamParams& p, const Phas
   }
 }
 
+// Fused form (batch <= 2): the attention of every (sequence, head) is computed by EVERY CTA while it stages
+// the input of o_proj -- one phase and one hand-over less per layer.  The cached K/V rows (< 32 positions)
+// are first copied to shared memory by all threads (padded rows: conflict-free 16-byte reads by position),
+// then each warp takes (sequence, head) units; q | k | v of the position being processed are polled from the
+// qkv phase's tagged output.  Result: bf16 rows [M][astride] in the activation region = o_proj's input.
+__device__ __forceinline__ void stage_attn_dec(const StreamParams& p, const Phase& P, const Lane& L, int astride) {
+  constexpr int HD = 128, RS = HD + 8;
+  const int M = p.B, dec_pos = P.dec_pos, layer = P.layer;
+  const int nh = p.dec.heads, nk = p.dec.kv, rep = nh / nk;
+  const int W = (nh + 2 * nk) * HD;
+  const uint32_t qtag = tg(p, P.src_ph);
+  bf16* dst = reinterpret_cast<bf16*>(sm_act(p));
+  bf16* kvs = dst + (size_t)p.m_alloc * astride;                 // [b][K|V][kvh][32][RS]
+  float* qs = reinterpret_cast<float*>(kvs + (size_t)M * 2 * nk * CSM_DEC_POS * RS) + L.warp * HD;
+  // this warp's first unit: request q | k | v now, they are checked after the K/V copy
+  const uint32_t* qbase = p.q_dec;
+  int unit = L.warp;
+  uint4 q4 = make_uint4(0, 0, 0, 0), k4 = q4, v4 = q4;
+  if (unit < M * nh) {
+    const int b = unit / nh, head = unit - b * nh, kvh = head / rep;
+    q4 = ld_tag4(qbase + (size_t)b * W + head * HD + L.lane * 4);
+    k4 = ld_tag4(qbase + (size_t)b * W + nh * HD + kvh * HD + L.lane * 4);
+    v4 = ld_tag4(qbase + (size_t)b * W + (nh + nk) * HD + kvh * HD + L.lane * 4);
+  }
+  // cached rows -> shared memory: item = (x = (b, K|V, kvh), position t, 16-byte chunk)
+  {
+    const int total = M * 2 * nk * CSM_DEC_POS * (HD / 8);
+#pragma unroll 1
+    for (int i0 = L.tid; i0 < total; i0 += 4 * CSM_COMPUTE_THREADS) {
+      uint4 v[4];
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        const int i = i0 + j * CSM_COMPUTE_THREADS;
+        const int c16 = i & 15, t = (i >> 4) & (CSM_DEC_POS - 1), x = i >> 9;
+        if (i < total && t < dec_pos) {
+          const int kvh = x % nk, y = x / nk, b = y >> 1;
+          const bf16* src = ((y & 1) ? p.vc_dec : p.kc_dec) +
+                            ((((size_t)layer * p.Bmax + b) * nk + kvh) * CSM_DEC_POS + t) * HD + c16 * 8;
+          v[j] = ldcg_u4(src);
+        }
+      }
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        const int i = i0 + j * CSM_COMPUTE_THREADS;
+        const int c16 = i & 15, t = (i >> 4) & (CSM_DEC_POS - 1), x = i >> 9;
+        if (i < total && t < dec_pos) *reinterpret_cast<uint4*>(kvs + ((size_t)x * CSM_DEC_POS + t) * RS + c16 * 8) = v[j];
+      }
+    }
+  }
+  compute_sync();
+  const float sc = p.dec.scale;
+#pragma unroll 1
+  for (; unit < M * nh; unit += CSM_COMPUTE_WARPS) {
+    const int b = unit / nh, head = unit - b * nh, kvh = head / rep;
+    const uint32_t* qw = qbase + (size_t)b * W + head * HD + L.lane * 4;
+    const uint32_t* kw = qbase + (size_t)b * W + nh * HD + kvh * HD + L.lane * 4;
+    const uint32_t* vw = kw + nk * HD;
+    while (!__all_sync(0xffffffffu, tw_ok4(q4, qtag) & tw_ok4(k4, qtag) & tw_ok4(v4, qtag))) {
+      q4 = ld_tag4(qw);
+      k4 = ld_tag4(kw);
+      v4 = ld_tag4(vw);
+    }
+    const float4 qf = make_float4(tw_val(q4.x) * sc, tw_val(q4.y) * sc, tw_val(q4.z) * sc, tw_val(q4.w) * sc);
+    *reinterpret_cast<float4*>(qs + L.lane * 4) = qf;
+    float dcur = qf.x * tw_val(k4.x) + qf.y * tw_val(k4.y) + qf.z * tw_val(k4.z) + qf.w * tw_val(k4.w);
+    dcur = warp_sum(dcur);
+    __syncwarp();
+    const bf16* kb = kvs + (((size_t)(b * 2 + 0) * nk + kvh) * CSM_DEC_POS + L.lane) * RS;
+    float d = 0.f;
+    if (L.lane < dec_pos) {
+#pragma unroll 4
+      for (int ci = 0; ci < HD / 8; ++ci) {
+        const uint4 kv = *reinterpret_cast<const uint4*>(kb + ci * 8);
+        const float4 a = *reinterpret_cast<const float4*>(qs + ci * 8), c4 = *reinterpret_cast<const float4*>(qs + ci * 8 + 4);
+        d += a.x * bf_lo(kv.x) + a.y * bf_hi(kv.x) + a.z * bf_lo(kv.y) + a.w * bf_hi(kv.y);
+        d += c4.x * bf_lo(kv.z) + c4.y * bf_hi(kv.z) + c4.z * bf_lo(kv.w) + c4.w * bf_hi(kv.w);
+      }
+    }
+    if (L.lane == dec_pos) d = dcur;
+    const float sv = L.lane <= dec_pos ? d : -INFINITY;
+    const float mx = warp_max(sv);
+    const float pe = (L.lane <= dec_pos) ? __expf(sv - mx) : 0.f;
+    const float l = warp_sum(pe);
+    const float pc = __shfl_sync(0xffffffffu, pe, dec_pos);
+    float o0 = pc * tw_val(v4.x), o1 = pc * tw_val(v4.y), o2 = pc * tw_val(v4.z), o3 = pc * tw_val(v4.w);
+    const bf16* vb = kvs + (((size_t)(b * 2 + 1) * nk + kvh) * CSM_DEC_POS) * RS + L.lane * 4;
+#pragma unroll 4
+    for (int t = 0; t < dec_pos; ++t) {
+      const float pv = __shfl_sync(0xffffffffu, pe, t);
+      const uint2 vv = *reinterpret_cast<const uint2*>(vb + (size_t)t * RS);
+      o0 += pv * bf_lo(vv.x); o1 += pv * bf_hi(vv.x);
+      o2 += pv * bf_lo(vv.y); o3 += pv * bf_hi(vv.y);
+    }
+    const float inv = 1.f / l;
+    *reinterpret_cast<uint2*>(dst + (size_t)b * astride + head * HD + L.lane * 4) =
+        make_uint2(pack_bf16(o0 * inv, o1 * inv), pack_bf16(o2 * inv, o3 * inv));
+    q4 = k4 = v4 = make_uint4(0, 0, 0, 0);   // next unit: poll from scratch
+    __syncwarp();
+  }
+}
+
 // ------------------------------------------------------------------ activation staging
 // Rows of the phase input -> shared memory [M][K+8] bf16.  The input is an array of tagged words written
 // by the CTAs of phase P.src_ph.  Work item = 4 consecutive words (one 16-byte load); items are dealt
@@ -312,6 +413,10 @@ __device__ __forceinline__ void stage_act(const StreamParams& p, const Phase& P,
     }
     return;
   }
+  if (P.act_mode == ACT_ATTN) {
+    stage_attn_dec(p, P, L, astride);
+    return;
+  }
   const uint32_t tag = tg(p, P.src_ph);
   const uint32_t* base = reinterpret_cast<const uint32_t*>(P.act);
   const bool norm = P.act_mode == ACT_NORM;
@@ -326,7 +431,7 @@ __device__ __forceinline__ void stage_act(const StreamParams& p, const Phase& P,
   if (total <= CSM_COMPUTE_THREADS) {
     if (L.tid < total) stage_poll<1>(P, L, base, dst, astride, total, gsh, tag, norm);   // whole warps (total % 32 == 0)
   } else {
-    stage_poll<4>(P, L, base, dst, astride, total, gsh, tag, norm);
+    stage_poll<4>(P, L, base, dst, astride, total, gsh, tag, norm);   // (8 loads in flight per thread measured slower)
   }
   if (!norm) return;
   compute_sync();
