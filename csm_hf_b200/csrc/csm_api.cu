@@ -273,6 +273,7 @@ void add_layer_phases(CsmCtx* ctx, Stack& S, int stack, int l, int dec_pos, bool
   const int iq = idx();
   Phase P = gemv(ACT_NORM, EPI_QKV, 2, nq + 2 * nkv, d.H, stack, l, L.p_qkv, h, d.H, L.ln1, qb, nq + 2 * nkv, h_ph);
   P.dec_pos = dec_pos;
+  if (stack && ctx->fuse_attn && !kv_only) P.flags |= CSM_PF_KV_COPY;
   ctx->table.push_back(P);
   if (kv_only) return;
   int io;
@@ -492,6 +493,7 @@ int launch_frame(CsmCtx* ctx, int B, int ph_begin, int ph_end, const long long* 
   p.l2_ahead_bytes = ctx->l2_ahead;
   p.repl = ctx->repl;
   p.evict_first = ctx->evict_first;
+  p.small = ctx->fuse_attn;
   if (!ctx->stepped) {
     p.phase_begin = ph_begin; p.phase_end = ph_end; p.use_barrier = 1;
     CK(cudaMemsetAsync(ctx->bar_counter, 0, sizeof(unsigned int), st));
@@ -712,6 +714,7 @@ int csm_create(const CsmShapes* sh, const CsmWeights* w, int max_batch, int max_
   ctx->direct_mlp = max_batch <= 4;
   if (const char* e = getenv("CSM_FUSE_ATTN")) ctx->fuse_attn = atoi(e) != 0;
   if (const char* e = getenv("CSM_DIRECT_MLP")) ctx->direct_mlp = atoi(e) != 0;
+  if (!ctx->direct_mlp || max_batch > 4) ctx->fuse_attn = 0;   // the SMALL kernels have no streamed-activation path
   build_table(ctx);
   if ((r = plan_smem(ctx))) return r;
   DA(ctx->d_table, ctx->table.size());

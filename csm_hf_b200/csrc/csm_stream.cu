@@ -39,13 +39,27 @@
 //     word and the consumers reduce the 148 candidates themselves.
 #include "csm_common.cuh"
 
+// build-time experiment knobs (tools/gpu_variants.sh builds several libraries and times them in one GPU call)
+#ifndef CSM_MMA_UNROLL
+#define CSM_MMA_UNROLL 4
+#endif
+#ifndef CSM_KV_EARLY
+#define CSM_KV_EARLY 1
+#endif
+#ifndef CSM_NORM_SPLIT
+#define CSM_NORM_SPLIT 1
+#endif
+#define CSM_STR2(x) #x
+#define CSM_STR(x) CSM_STR2(x)
+
 extern __shared__ __align__(128) unsigned char csm_smem[];
 
 namespace {
 
 // ---- shared-memory header (CSM_SM_HDR_BYTES = 4096) ----
 //   [0,64) full[8] | [64,128) empty[8] | [128,144) afull[2] | [144,160) aempty[2] | [160,168) sflag[2] |
-//   [168,172) weight-stream progress | [256,768) 2 phase descriptors | [768,2816) 512 floats scratch | [2816,2944) tok[32]
+//   [168,172) weight-stream progress | [256,768) 2 phase descriptors | [768,2816) 512 floats scratch | [2816,2944) tok[32] |
+//   [2944,3072) rstd[32]
 __device__ __forceinline__ uint64_t* sm_full() { return reinterpret_cast<uint64_t*>(csm_smem); }
 __device__ __forceinline__ uint64_t* sm_empty() { return reinterpret_cast<uint64_t*>(csm_smem + 64); }
 __device__ __forceinline__ uint64_t* sm_afull() { return reinterpret_cast<uint64_t*>(csm_smem + 128); }
@@ -55,6 +69,7 @@ __device__ __forceinline__ volatile unsigned int* sm_prog() { return reinterpret
 __device__ __forceinline__ Phase* sm_desc() { return reinterpret_cast<Phase*>(csm_smem + 256); }
 __device__ __forceinline__ float* sm_scratch() { return reinterpret_cast<float*>(csm_smem + 768); }
 __device__ __forceinline__ int* sm_tok() { return reinterpret_cast<int*>(csm_smem + 2816); }
+__device__ __forceinline__ float* sm_rstd() { return reinterpret_cast<float*>(csm_smem + 2944); }   // 32 floats
 // cos_dec | sin_dec ([32][hd/2] each) | cos_bb[pos] | sin_bb[pos]
 __device__ __forceinline__ bf16* sm_rope() { return reinterpret_cast<bf16*>(csm_smem + CSM_SM_HDR_BYTES); }
 __device__ __forceinline__ float* sm_red(const StreamParams& p) {
@@ -235,66 +250,67 @@ __device__ __forceinline__ void attn_dec_phase(const StreamParams& p, const Phas
 
 // Fused form (batch <= 2): the attention of every (sequence, head) is computed by EVERY CTA while it stages
 // the input of o_proj -- one phase and one hand-over less per layer.  The cached K/V rows (< 32 positions)
-// are first copied to shared memory by all threads (padded rows: conflict-free 16-byte reads by position),
-// then each warp takes (sequence, head) units; q | k | v of the position being processed are polled from the
-// qkv phase's tagged output.  Result: bf16 rows [M][astride] in the activation region = o_proj's input.
+// are copied to shared memory by all threads at the END of the qkv phase (attn_kv_copy: the loads overlap
+// the hand-over of that phase's outputs; padded rows: conflict-free 16-byte reads by position), then in the
+// o_proj phase each warp takes (sequence, head) units; q | k | v of the position being processed are polled
+// from the qkv phase's tagged output.  Result: bf16 rows [M][astride] in the activation region = o_proj's input.
+__device__ __forceinline__ bf16* attn_kvs(const StreamParams& p) {   // [b][K|V][kvh][32][hd+8] after the o_proj input rows
+  return reinterpret_cast<bf16*>(sm_act(p)) + (size_t)p.m_alloc * (p.dec.heads * p.dec.hd + 8);
+}
+
+__device__ __forceinline__ void attn_kv_copy(const StreamParams& p, int layer, int dec_pos, int tid) {
+  constexpr int HD = 128, RS = HD + 8;
+  const int M = p.B, nk = p.dec.kv;
+  bf16* kvs = attn_kvs(p);
+  // item = (x = (b, K|V, kvh), position t, 16-byte chunk); asynchronous 16-byte copies (LDGSTS): the thread
+  // only issues them, the o_proj phase waits for them (cp.async.wait_all) before its first CTA barrier
+  // thread -> (position t0 + tid/16, chunk tid%16); loop over x and the two halves of the 32 positions
+  const int nx = M * 2 * nk, nkl = nk > 1 ? 1 : 0;   // (kv heads: 1 or 2)
+  const int c16 = tid & 15, tl = tid >> 4;
+#pragma unroll 1
+  for (int x = 0; x < nx; ++x) {
+    const int kvh = x & (nk - 1), y = x >> nkl, b = y >> 1;
+    const bf16* src = ((y & 1) ? p.vc_dec : p.kc_dec) + ((((size_t)layer * p.Bmax + b) * nk + kvh) * CSM_DEC_POS) * HD + c16 * 8;
+    const uint32_t dsts = smem_u32(kvs + ((size_t)x * CSM_DEC_POS) * RS + c16 * 8);
+#pragma unroll
+    for (int t0 = 0; t0 < CSM_DEC_POS; t0 += 16) {
+      const int t = t0 + tl;
+      if (t < dec_pos)
+        asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dsts + (uint32_t)t * (RS * 2)), "l"(src + (size_t)t * HD) : "memory");
+    }
+  }
+}
+
 __device__ __forceinline__ void stage_attn_dec(const StreamParams& p, const Phase& P, const Lane& L, int astride) {
   constexpr int HD = 128, RS = HD + 8;
-  const int M = p.B, dec_pos = P.dec_pos, layer = P.layer;
+  const int M = p.B, dec_pos = P.dec_pos;
   const int nh = p.dec.heads, nk = p.dec.kv, rep = nh / nk;
   const int W = (nh + 2 * nk) * HD;
   const uint32_t qtag = tg(p, P.src_ph);
   bf16* dst = reinterpret_cast<bf16*>(sm_act(p));
-  bf16* kvs = dst + (size_t)p.m_alloc * astride;                 // [b][K|V][kvh][32][RS]
-  float* qs = reinterpret_cast<float*>(kvs + (size_t)M * 2 * nk * CSM_DEC_POS * RS) + L.warp * HD;
-  // this warp's first unit: request q | k | v now, they are checked after the K/V copy
+  const bf16* kvs = attn_kvs(p);
+  float* qs = reinterpret_cast<float*>(attn_kvs(p) + (size_t)p.Bmax * 2 * nk * CSM_DEC_POS * RS) + L.warp * HD;
   const uint32_t* qbase = p.q_dec;
-  int unit = L.warp;
-  uint4 q4 = make_uint4(0, 0, 0, 0), k4 = q4, v4 = q4;
-  if (unit < M * nh) {
-    const int b = unit / nh, head = unit - b * nh, kvh = head / rep;
-    q4 = ld_tag4(qbase + (size_t)b * W + head * HD + L.lane * 4);
-    k4 = ld_tag4(qbase + (size_t)b * W + nh * HD + kvh * HD + L.lane * 4);
-    v4 = ld_tag4(qbase + (size_t)b * W + (nh + nk) * HD + kvh * HD + L.lane * 4);
-  }
-  // cached rows -> shared memory: item = (x = (b, K|V, kvh), position t, 16-byte chunk)
-  {
-    const int total = M * 2 * nk * CSM_DEC_POS * (HD / 8);
-#pragma unroll 1
-    for (int i0 = L.tid; i0 < total; i0 += 4 * CSM_COMPUTE_THREADS) {
-      uint4 v[4];
-#pragma unroll
-      for (int j = 0; j < 4; ++j) {
-        const int i = i0 + j * CSM_COMPUTE_THREADS;
-        const int c16 = i & 15, t = (i >> 4) & (CSM_DEC_POS - 1), x = i >> 9;
-        if (i < total && t < dec_pos) {
-          const int kvh = x % nk, y = x / nk, b = y >> 1;
-          const bf16* src = ((y & 1) ? p.vc_dec : p.kc_dec) +
-                            ((((size_t)layer * p.Bmax + b) * nk + kvh) * CSM_DEC_POS + t) * HD + c16 * 8;
-          v[j] = ldcg_u4(src);
-        }
-      }
-#pragma unroll
-      for (int j = 0; j < 4; ++j) {
-        const int i = i0 + j * CSM_COMPUTE_THREADS;
-        const int c16 = i & 15, t = (i >> 4) & (CSM_DEC_POS - 1), x = i >> 9;
-        if (i < total && t < dec_pos) *reinterpret_cast<uint4*>(kvs + ((size_t)x * CSM_DEC_POS + t) * RS + c16 * 8) = v[j];
-      }
-    }
-  }
-  compute_sync();
   const float sc = p.dec.scale;
+  // first phase of a launch (stepped / bisecting runs): the qkv phase ran in another launch, copy now
+  if (!CSM_KV_EARLY || L.ph == p.phase_begin) attn_kv_copy(p, P.layer, dec_pos, L.tid);
+  // the K/V copies were issued at the end of the qkv phase: wait for this thread's, then one CTA barrier
+  asm volatile("cp.async.wait_all;" ::: "memory");
+  compute_sync();
 #pragma unroll 1
-  for (; unit < M * nh; unit += CSM_COMPUTE_WARPS) {
+  for (int unit = L.warp; unit < M * nh; unit += CSM_COMPUTE_WARPS) {
     const int b = unit / nh, head = unit - b * nh, kvh = head / rep;
     const uint32_t* qw = qbase + (size_t)b * W + head * HD + L.lane * 4;
     const uint32_t* kw = qbase + (size_t)b * W + nh * HD + kvh * HD + L.lane * 4;
     const uint32_t* vw = kw + nk * HD;
-    while (!__all_sync(0xffffffffu, tw_ok4(q4, qtag) & tw_ok4(k4, qtag) & tw_ok4(v4, qtag))) {
+    uint4 q4, k4, v4;
+    bool ok;
+    do {
       q4 = ld_tag4(qw);
       k4 = ld_tag4(kw);
       v4 = ld_tag4(vw);
-    }
+      ok = tw_ok4(q4, qtag) & tw_ok4(k4, qtag) & tw_ok4(v4, qtag);
+    } while (!__all_sync(0xffffffffu, ok));
     const float4 qf = make_float4(tw_val(q4.x) * sc, tw_val(q4.y) * sc, tw_val(q4.z) * sc, tw_val(q4.w) * sc);
     *reinterpret_cast<float4*>(qs + L.lane * 4) = qf;
     float dcur = qf.x * tw_val(k4.x) + qf.y * tw_val(k4.y) + qf.z * tw_val(k4.z) + qf.w * tw_val(k4.w);
@@ -329,7 +345,6 @@ __device__ __forceinline__ void stage_attn_dec(const StreamParams& p, const Phas
     const float inv = 1.f / l;
     *reinterpret_cast<uint2*>(dst + (size_t)b * astride + head * HD + L.lane * 4) =
         make_uint2(pack_bf16(o0 * inv, o1 * inv), pack_bf16(o2 * inv, o3 * inv));
-    q4 = k4 = v4 = make_uint4(0, 0, 0, 0);   // next unit: poll from scratch
     __syncwarp();
   }
 }
@@ -386,6 +401,9 @@ __device__ __forceinline__ void stage_poll(const Phase& P, const Lane& L, const 
   }
 }
 
+// SMALL (engine built for <= 2 sequences): fused attention staging, 1-2 row RMSNorm, at most 4 loads in flight;
+// otherwise: many-row RMSNorm, 4 or 8 loads in flight, no fused attention.  Two kernels, each with half the code.
+template <bool SMALL>
 __device__ __forceinline__ void stage_act(const StreamParams& p, const Phase& P, const Lane& L, int astride) {
   const int K = P.K, M = p.B;
   bf16* dst = reinterpret_cast<bf16*>(sm_act(p));
@@ -413,7 +431,7 @@ __device__ __forceinline__ void stage_act(const StreamParams& p, const Phase& P,
     }
     return;
   }
-  if (P.act_mode == ACT_ATTN) {
+  if (SMALL && P.act_mode == ACT_ATTN) {
     stage_attn_dec(p, P, L, astride);
     return;
   }
@@ -430,32 +448,71 @@ __device__ __forceinline__ void stage_act(const StreamParams& p, const Phase& P,
   }
   if (total <= CSM_COMPUTE_THREADS) {
     if (L.tid < total) stage_poll<1>(P, L, base, dst, astride, total, gsh, tag, norm);   // whole warps (total % 32 == 0)
+  } else if (SMALL || total < 16 * CSM_COMPUTE_THREADS) {
+    stage_poll<4>(P, L, base, dst, astride, total, gsh, tag, norm);   // (8 in flight measured slower for few rows)
   } else {
-    stage_poll<4>(P, L, base, dst, astride, total, gsh, tag, norm);   // (8 loads in flight per thread measured slower)
+    stage_poll<8>(P, L, base, dst, astride, total, gsh, tag, norm);
   }
   if (!norm) return;
   compute_sync();
   const float eps = P.stack ? p.dec.eps : p.bb.eps;
   const int ppr = 1 << (gsh - 5);
   const float fK = (float)K;
-  const float* scratch = sm_scratch();
-  const bool wide = (1 << gsh) > CSM_COMPUTE_THREADS;   // two column groups per thread (K = 2048)
-  int jj = 0;
+  float* scratch = sm_scratch();
+  if (SMALL || M <= 2) {
+    // one or two rows: every thread derives its row's rstd itself (no further barrier)
+    const bool wide = (1 << gsh) > CSM_COMPUTE_THREADS;   // two column groups per thread (K = 2048)
+    int jj = 0;
 #pragma unroll 2
-  for (int i = L.tid; i < total; i += CSM_COMPUTE_THREADS, ++jj) {
-    const int m = i >> gsh, g = i & gmask;
-    // row sum: lane l reads partial l mod ppr, butterfly over the ppr-lane groups (fixed order: deterministic)
+    for (int i = L.tid; i < total; i += CSM_COMPUTE_THREADS, ++jj) {
+      const int m = i >> gsh, g = i & gmask;
+      // row sum: lane l reads partial l mod ppr, butterfly over the ppr-lane groups (fixed order: deterministic)
+      float ss = scratch[m * ppr + (L.lane & (ppr - 1))];
+      for (int o = ppr >> 1; o > 0; o >>= 1) ss += __shfl_xor_sync(0xffffffffu, ss, o);
+      const float rstd = rsqrtf(ss / fK + eps);   // mean = sum / K exactly as torch
+      const uint2 nw = (wide && (jj & 1)) ? nw1 : nw0;
+      uint2* px = reinterpret_cast<uint2*>(dst + (size_t)m * astride + g * 4);
+      const uint2 x = *px;
+      const float y0 = bfround(bf_lo(x.x) * rstd), y1 = bfround(bf_hi(x.x) * rstd);
+      const float y2 = bfround(bf_lo(x.y) * rstd), y3 = bfround(bf_hi(x.y) * rstd);
+      const uint2 o = make_uint2(pack_bf16(bf_lo(nw.x) * y0, bf_hi(nw.x) * y1), pack_bf16(bf_lo(nw.y) * y2, bf_hi(nw.y) * y3));
+      *px = o;
+      if (P.norm_out != nullptr && (m % L.G) == L.c) *reinterpret_cast<uint2*>(P.norm_out + (size_t)m * K + g * 4) = o;
+    }
+    return;
+  }
+  // many rows: rstd of every row once (same butterfly order as above, so a row's result does not depend on
+  // the batch it is in), then a wide scaling pass over 8-element groups
+  float* rstd_s = sm_rstd();
+  for (int m = L.warp; m < M; m += CSM_COMPUTE_WARPS) {
     float ss = scratch[m * ppr + (L.lane & (ppr - 1))];
     for (int o = ppr >> 1; o > 0; o >>= 1) ss += __shfl_xor_sync(0xffffffffu, ss, o);
-    const float rstd = rsqrtf(ss / fK + eps);   // mean = sum / K exactly as torch
-    const uint2 nw = (wide && (jj & 1)) ? nw1 : nw0;
-    uint2* px = reinterpret_cast<uint2*>(dst + (size_t)m * astride + g * 4);
-    const uint2 x = *px;
-    const float y0 = bfround(bf_lo(x.x) * rstd), y1 = bfround(bf_hi(x.x) * rstd);
-    const float y2 = bfround(bf_lo(x.y) * rstd), y3 = bfround(bf_hi(x.y) * rstd);
-    const uint2 o = make_uint2(pack_bf16(bf_lo(nw.x) * y0, bf_hi(nw.x) * y1), pack_bf16(bf_lo(nw.y) * y2, bf_hi(nw.y) * y3));
-    *px = o;
-    if (P.norm_out != nullptr && (m % L.G) == L.c) *reinterpret_cast<uint2*>(P.norm_out + (size_t)m * K + g * 4) = o;
+    if (L.lane == 0) rstd_s[m] = rsqrtf(ss / fK + eps);
+  }
+  compute_sync();
+  {
+    const int sh8 = gsh - 1, mask8 = (1 << sh8) - 1;   // 8-element groups per row
+    const int total8 = M << sh8;
+    const uint4 w8a = __ldg(reinterpret_cast<const uint4*>(P.norm_w) + (L.tid & mask8));
+    const uint4 w8b = __ldg(reinterpret_cast<const uint4*>(P.norm_w) + ((L.tid + CSM_COMPUTE_THREADS) & mask8));
+    const bool wide8 = (1 << sh8) > CSM_COMPUTE_THREADS;
+    const bool keep_any = P.norm_out != nullptr;
+    int jj = 0;
+#pragma unroll 4
+    for (int i = L.tid; i < total8; i += CSM_COMPUTE_THREADS, ++jj) {
+      const int m = i >> sh8, g = i & mask8;
+      const float rstd = rstd_s[m];
+      const uint4 nw = (wide8 && (jj & 1)) ? w8b : w8a;
+      uint4* px = reinterpret_cast<uint4*>(dst + (size_t)m * astride + g * 8);
+      const uint4 x = *px;
+      uint4 o;
+      o.x = pack_bf16(bf_lo(nw.x) * bfround(bf_lo(x.x) * rstd), bf_hi(nw.x) * bfround(bf_hi(x.x) * rstd));
+      o.y = pack_bf16(bf_lo(nw.y) * bfround(bf_lo(x.y) * rstd), bf_hi(nw.y) * bfround(bf_hi(x.y) * rstd));
+      o.z = pack_bf16(bf_lo(nw.z) * bfround(bf_lo(x.z) * rstd), bf_hi(nw.z) * bfround(bf_hi(x.z) * rstd));
+      o.w = pack_bf16(bf_lo(nw.w) * bfround(bf_lo(x.w) * rstd), bf_hi(nw.w) * bfround(bf_hi(x.w) * rstd));
+      *px = o;
+      if (keep_any && (m % L.G) == L.c) *reinterpret_cast<uint4*>(P.norm_out + (size_t)m * K + g * 8) = o;
+    }
   }
 }
 
@@ -475,9 +532,10 @@ __device__ __forceinline__ void ldsm_x4(uint32_t (&r)[4], uint32_t addr) {
 // The warp owns m-tiles mt0 (and mt1 when the CTA has more m-tiles than m-tile groups) and every ks-th
 // k16-tile; two k-tiles per iteration.  With a single m-tile the two k-tiles of an iteration feed the two
 // accumulator sets (two independent MMA chains); otherwise accumulator set j belongs to m-tile j.
-template <int NB>
-__device__ __forceinline__ void gemv_core(const StreamParams& p, const Phase& P, const GeoC& gc, Lane& L, bool stream,
+template <int NB, bool SMALL>
+__device__ __forceinline__ void gemv_core(const StreamParams& p, const Phase& P, const GeoC& gc, Lane& L, bool stream_,
                                           int astride) {
+  const bool stream = !SMALL && stream_;   // (engines for <= 4 sequences never stream the down_proj input)
   const int M = p.B;
   const int rows = gc.rows, mtiles = gc.mtiles, rows_pad = gc.rows_pad, ksl = gc.ksl;
   int tpc = gc.tpc, nchunks = gc.nch, ntiles = P.K >> 4;
@@ -540,7 +598,7 @@ __device__ __forceinline__ void gemv_core(const StreamParams& p, const Phase& P,
       uint32_t aoff = aadd;
       const int npairs = tiles >> (ksl + 1);
       if (single) {
-#pragma unroll 2
+_Pragma(CSM_STR(unroll CSM_MMA_UNROLL))
         for (int it = 0; it < npairs; ++it) {
           uint32_t aA[4], aC[4], b[NB][4];
           ldsm_x4(aA, wa0);
@@ -621,10 +679,10 @@ __device__ __forceinline__ float resid_poll(const uint32_t* p, uint32_t tag) {
 
 // Returns true when the next phase's descriptor has been published inside the phase (after its first CTA
 // barrier, made visible by the second), so that no barrier is needed at the end of the phase.
-template <int NB>
+template <int NB, bool SMALL>
 __device__ __forceinline__ bool gemv_phase(const StreamParams& p, const Phase& P, Lane& L, const uint4& nxt, bool fetch) {
   const int M = p.B, K = P.K;
-  const bool stream = (P.act_mode == ACT_STREAM);
+  const bool stream = !SMALL && (P.act_mode == ACT_STREAM);
   const bool hi = L.c < P.r;
   const GeoC& gc = P.geo[hi ? 0 : 1];
   const int row0 = (L.c * P.q + (hi ? L.c : P.r)) * P.gran;
@@ -632,7 +690,7 @@ __device__ __forceinline__ bool gemv_phase(const StreamParams& p, const Phase& P
   int astride;
   if (!stream) {
     astride = K + 8;
-    stage_act(p, P, L, astride);
+    stage_act<SMALL>(p, P, L, astride);
     compute_sync();
     CSM_STAMP(L, 4);   // activations staged
     // every warp is inside this phase now: the other descriptor slot is free for the next phase
@@ -652,7 +710,7 @@ __device__ __forceinline__ bool gemv_phase(const StreamParams& p, const Phase& P
   // (own element of the previous residual phase, or the stream's first value written by another CTA)
   uint32_t resid0 = 0;
   if (epi == EPI_RESID && u < upc && m_first < M) resid0 = ld_tag(outw + (size_t)m_first * out_stride + row0 + u);
-  if (rows > 0) gemv_core<NB>(p, P, gc, L, stream, astride);
+  if (rows > 0) gemv_core<NB, SMALL>(p, P, gc, L, stream, astride);
   CSM_STAMP(L, 5);     // this warp's MMAs done
   compute_sync();
   CSM_STAMP(L, 6);     // all warps' MMAs done
@@ -768,6 +826,7 @@ __device__ __forceinline__ bool gemv_phase(const StreamParams& p, const Phase& P
                                                         (unsigned long long)float_to_bf16_bits(best));
     }
   }
+  if (SMALL && CSM_KV_EARLY && (P.flags & CSM_PF_KV_COPY)) attn_kv_copy(p, P.layer, P.dec_pos, L.tid);
   return !stream;
 }
 
@@ -1075,7 +1134,7 @@ __device__ __noinline__ void attn_bb_phase(const StreamParams& p, int layer, int
 
 }  // namespace
 
-template <int NB, int REP>
+template <int NB, int REP, bool SMALL>
 __global__ void __launch_bounds__(CSM_THREADS, 1) csm_stream_kernel(const __grid_constant__ StreamParams p) {
   if (p.stop_flag != nullptr && *p.stop_flag) return;   // generation already ended (set by an earlier launch)
 
@@ -1155,7 +1214,7 @@ __global__ void __launch_bounds__(CSM_THREADS, 1) csm_stream_kernel(const __grid
   }
   if (L.warp == CSM_COMPUTE_WARPS + 1) {
     // ===================== activation stream producer (K=8192 phases at batch > 4) =====================
-    if (L.lane == 0) {
+    if (!SMALL && L.lane == 0) {
       uint32_t ait = 0;
       unsigned char* actreg = sm_act(p);
 #pragma unroll 1
@@ -1255,8 +1314,8 @@ __global__ void __launch_bounds__(CSM_THREADS, 1) csm_stream_kernel(const __grid
     if (prof) prof[1] = clock64();       // phase body starts
     const int type = P.type;
     bool published = false;
-    if (type == PH_GEMV) published = gemv_phase<NB>(p, P, L, nxt, fetch);
-    else if (type == PH_ATTN_DEC) attn_dec_phase(p, P, L);
+    if (type == PH_GEMV) published = gemv_phase<NB, SMALL>(p, P, L, nxt, fetch);
+    else if (!SMALL && type == PH_ATTN_DEC) attn_dec_phase(p, P, L);
     else if (type == PH_ATTN_BB) attn_bb_phase<REP>(p, P.layer, P.src_ph, ph);
     else if (type == PH_EMBED) embed_phase(p, ph);
     else finish_phase(p, P.res_ph);
@@ -1288,23 +1347,24 @@ __global__ void __launch_bounds__(CSM_THREADS, 1) csm_stream_kernel(const __grid
 // attention variant, which keeps its instruction footprint small.
 typedef void (*StreamKernel)(const StreamParams);
 
-static StreamKernel pick_kernel(int nb, int rep) {
-#define CSM_PICK(NBV)                                                    \
+static StreamKernel pick_kernel(int nb, int rep, bool small) {
+#define CSM_PICK(NBV, SM)                                                \
   switch (rep) {                                                         \
-    case 1: return csm_stream_kernel<NBV, 1>;                            \
-    case 2: return csm_stream_kernel<NBV, 2>;                            \
-    default: return csm_stream_kernel<NBV, 4>;                           \
+    case 1: return csm_stream_kernel<NBV, 1, SM>;                        \
+    case 2: return csm_stream_kernel<NBV, 2, SM>;                        \
+    default: return csm_stream_kernel<NBV, 4, SM>;                       \
   }
-  if (nb <= 1) { CSM_PICK(1) }
-  if (nb <= 2) { CSM_PICK(2) }
-  CSM_PICK(4)
+  if (small) { CSM_PICK(1, true) }
+  if (nb <= 1) { CSM_PICK(1, false) }
+  if (nb <= 2) { CSM_PICK(2, false) }
+  CSM_PICK(4, false)
 #undef CSM_PICK
 }
 
 extern "C" cudaError_t csm_launch_stream(const StreamParams* p, int grid, size_t smem, cudaStream_t stream,
                                          int cooperative) {
   const int nb = (p->B + 7) / 8, rep = p->bb.heads / p->bb.kv;
-  StreamKernel k = pick_kernel(nb, rep);
+  StreamKernel k = pick_kernel(nb, rep, p->small != 0);
   cudaError_t e = cudaFuncSetAttribute((const void*)k, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
   if (e != cudaSuccess) return e;
   if (cooperative) {

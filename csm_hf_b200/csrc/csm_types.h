@@ -24,6 +24,8 @@ enum EpiMode { EPI_STORE = 0, EPI_RESID = 1, EPI_SWIGLU = 2, EPI_QKV = 3, EPI_HE
 #define CSM_PF_BAR_IN 1      // a grid barrier precedes this phase (its input is plain memory read by the TMA engine)
 #define CSM_PF_BAR_OUT 2     // arrive on the grid barrier after this phase (the next phase has BAR_IN)
 #define CSM_PF_OUT_PLAIN 4   // EPI_SWIGLU writes plain bf16 (consumer streams it with bulk copies) instead of tagged words
+#define CSM_PF_KV_COPY 8     // decoder qkv phase, fused attention: copy this layer's cached K/V rows to shared memory
+                             // at the end of the phase (the o_proj phase that follows computes the attention from them)
 
 // One step of the per-frame program.  A frame is ~800 of these executed in order by every
 // CTA of one persistent launch.  Phases are chained by DATAFLOW, not by barriers: every value that
@@ -90,6 +92,7 @@ struct StreamParams {
   int repl;                     // copies of every tagged vector (consumer CTA c polls copy c % repl): spreads the pollers
                                 // over repl x more L2 lines, so no line is hammered by all 148 CTAs at once
   int evict_first;              // weight bulk copies carry an L2 evict-first hint
+  int small;                    // engine built for <= 2 sequences (fused decoder attention): selects the SMALL kernels
   int l2_ahead_bytes;           // how far (bytes of this CTA's weight stream) the L2 prefetcher runs ahead of the ring
   int B;                        // sequences in this call
   int pos;                      // backbone position of the token being processed (= cached length)

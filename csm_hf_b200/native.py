@@ -46,10 +46,11 @@ def load():
     global _lib
     if _lib is not None:
         return _lib
-    if not os.path.isfile(LIB_PATH):
-        raise RuntimeError(f"{LIB_PATH} not found: build it with `python csm_hf_b200/build.py` "
+    path = os.environ.get("CSM_LIB") or LIB_PATH   # experiment variants of the same library (tools/gpu_variants.sh)
+    if not os.path.isfile(path):
+        raise RuntimeError(f"{path} not found: build it with `python csm_hf_b200/build.py` "
                            "(there is no CPU or PyTorch fallback for the generation path)")
-    lib = C.CDLL(LIB_PATH)
+    lib = C.CDLL(path)
     vp, i32, i64p = C.c_void_p, C.c_int, C.c_void_p
     lib.csm_create.argtypes = [C.POINTER(Shapes), C.POINTER(Weights), i32, i32, vp, C.POINTER(vp)]
     lib.csm_create.restype = i32

@@ -1,9 +1,10 @@
 #!/bin/bash
-# Parity tests + per-phase profile + short decode timing (one gpurun call).
+# Parity tests + per-phase profile + decode timing over 100 frames (one gpurun call).
 mkdir -p gpurun_out
 timeout 900 python -m pytest tests -m gpu -x -q > gpurun_out/pytest_gpu.log 2>&1; echo "pytest rc=$?" >> gpurun_out/pytest_gpu.log
-tail -15 gpurun_out/pytest_gpu.log
+tail -4 gpurun_out/pytest_gpu.log
 for b in ${BATCHES:-1}; do
+  timeout 300 python tools/ncu_target.py --batch $b --frames 100 --reps 2
   timeout 300 python tools/phase_profile.py --batch $b > gpurun_out/phase_b$b.txt 2>&1
   head -${LINES_PER:-18} gpurun_out/phase_b$b.txt
 done

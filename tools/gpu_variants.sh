@@ -1,3 +1,4 @@
-for v in "CSM_L2_AHEAD_KB=256" "CSM_L2_AHEAD_KB=0" "CSM_L2_AHEAD_KB=1024" "CSM_RING_SLOTS=3" "CSM_RING_SLOTS=4 CSM_L2_AHEAD_KB=512" ; do
-  echo "=== $v"; env $v timeout 300 python tools/phase_profile.py --batch 1 2>&1 | head -8
+# time library variants built with different -D knobs (csm_hf_b200/build.py build(defines=..., out=...))
+for f in "" gpurun_variants/lib_*.so; do
+  echo "=== ${f:-default}"; CSM_LIB=${f:+$PWD/$f} python tools/ncu_target.py --batch ${B:-1} --frames 100 --reps 2 2>&1 | tail -1
 done
