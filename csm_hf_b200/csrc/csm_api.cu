@@ -89,6 +89,10 @@ struct CsmCtx {
   int *samples = nullptr, *fed = nullptr, *stop_flag = nullptr, *n_frames = nullptr;
   unsigned long long* prof = nullptr;
   int prof_on = 0;
+  int* abort_flag = nullptr; // [8], see StreamParams::abort_flag
+  int* progress = nullptr;   // [sms][4], see StreamParams::progress
+  int progress_on = 0;
+  int bar_all = 0;           // grid barrier between all phases (CSM_BAR_ALL=1)
   // prefill workspace (lazy)
   int pf_rows = 0;
   bf16 *pf_h = nullptr, *pf_hn = nullptr, *pf_qkv = nullptr, *pf_attn = nullptr, *pf_y = nullptr, *pf_gu = nullptr,
@@ -348,6 +352,13 @@ void build_table(CsmCtx* ctx) {
   P.type = PH_FINISH;
   P.res_ph = head_ph;
   ctx->table.push_back(P);
+  if (ctx->bar_all) {
+    // conservative mode: a grid barrier between every two phases, on top of the tagged hand-over
+    for (size_t i = 1; i < ctx->table.size(); ++i) {
+      ctx->table[i].flags |= CSM_PF_BAR_IN;
+      ctx->table[i - 1].flags |= CSM_PF_BAR_OUT;
+    }
+  }
   int nbar = 0;
   for (Phase& Q : ctx->table) {
     if (Q.flags & CSM_PF_BAR_IN) ++nbar;
@@ -466,6 +477,18 @@ int begin_epoch(CsmCtx* ctx, cudaStream_t st) {
 }
 void end_epoch(CsmCtx* ctx) { ctx->tagbase += (unsigned)ctx->table.size(); }
 
+// A wait inside a frame kernel timed out (hang guard, csm_stream.cu): report who waited for what.  Synchronises.
+int check_abort(CsmCtx* ctx, cudaStream_t st) {
+  int a[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+  CK(cudaMemcpyAsync(a, ctx->abort_flag, sizeof a, cudaMemcpyDeviceToHost, st));
+  CK(cudaStreamSynchronize(st));
+  if (a[0] == 0) return 0;
+  CK(cudaMemsetAsync(ctx->abort_flag, 0, sizeof a, st));   // the engine stays usable (reset + new generate)
+  return fail(ctx, CSM_ECUDA,
+              "frame kernel timed out: CTA %d, phase %d, wait kind %d (1 stage 2 cand 3 attn_dec 4/5 attn_bb 6 resid 7 grid "
+              "barrier 8/9 ring full 10/11 ring empty), detail %d / 0x%x, thread %d", a[1], a[2], a[3], a[4], a[5], a[6]);
+}
+
 int launch_frame(CsmCtx* ctx, int B, int ph_begin, int ph_end, const long long* ids, const int* mask, int forced,
                  long long* out_frames, long long out_stride, long long out_off, int stop_on_zeros, int pos,
                  cudaStream_t st) {
@@ -489,6 +512,8 @@ int launch_frame(CsmCtx* ctx, int B, int ph_begin, int ph_end, const long long* 
   p.rope_bytes = ctx->rope_bytes; p.act_region_bytes = ctx->act_region; p.red_bytes = ctx->red_bytes;
   p.prof = ctx->prof_on ? ctx->prof : nullptr;
   p.n_phases_total = (int)ctx->table.size();
+  p.progress = ctx->progress_on ? ctx->progress : nullptr;
+  p.abort_flag = ctx->abort_flag;
   p.tagbase = ctx->tagbase;
   p.l2_ahead_bytes = ctx->l2_ahead;
   p.repl = ctx->repl;
@@ -714,11 +739,17 @@ int csm_create(const CsmShapes* sh, const CsmWeights* w, int max_batch, int max_
   ctx->direct_mlp = max_batch <= 4;
   if (const char* e = getenv("CSM_FUSE_ATTN")) ctx->fuse_attn = atoi(e) != 0;
   if (const char* e = getenv("CSM_DIRECT_MLP")) ctx->direct_mlp = atoi(e) != 0;
+  if (const char* e = getenv("CSM_BAR_ALL")) ctx->bar_all = atoi(e) != 0;
   if (!ctx->direct_mlp || max_batch > 4) ctx->fuse_attn = 0;   // the SMALL kernels have no streamed-activation path
   build_table(ctx);
   if ((r = plan_smem(ctx))) return r;
   DA(ctx->d_table, ctx->table.size());
   DA(ctx->prof, (32 + (size_t)ctx->sms) * ctx->table.size());
+  DA(ctx->abort_flag, 8);
+  CK(cudaMemsetAsync(ctx->abort_flag, 0, 8 * sizeof(int), st));
+  DA(ctx->progress, (size_t)ctx->sms * 4);
+  CK(cudaMemsetAsync(ctx->progress, 0xff, (size_t)ctx->sms * 4 * sizeof(int), st));
+  if (const char* e = getenv("CSM_DEBUG_PROGRESS")) ctx->progress_on = atoi(e) != 0;
   CK(cudaMemcpyAsync(ctx->d_table, ctx->table.data(), ctx->table.size() * sizeof(Phase), cudaMemcpyHostToDevice, st));
   if (cublasCreate(&ctx->cublas) != CUBLAS_STATUS_SUCCESS) return fail(ctx, CSM_ECUDA, "cublasCreate failed");
   CK(cudaEventCreate(&ctx->ev0));
@@ -807,7 +838,8 @@ int csm_frames_done(CsmCtx* ctx, void* stream) {
   if (!ctx) return CSM_EINVAL;
   int n = 0;
   CK(cudaMemcpyAsync(&n, ctx->n_frames, sizeof(int), cudaMemcpyDeviceToHost, (cudaStream_t)stream));
-  CK(cudaStreamSynchronize((cudaStream_t)stream));
+  int r = check_abort(ctx, (cudaStream_t)stream);   // synchronises the stream
+  if (r) return r;
   return n;
 }
 
@@ -957,6 +989,15 @@ int csm_debug_profile_frame(CsmCtx* ctx, int B, uint64_t* clocks_host, int32_t* 
       info_host[4 * i + 0] = P.type; info_host[4 * i + 1] = P.type == PH_GEMV ? P.epi : -1;
       info_host[4 * i + 2] = P.stack; info_host[4 * i + 3] = P.type == PH_GEMV ? P.act_mode : -1;
     }
+  return CSM_OK;
+}
+
+int csm_debug_progress(CsmCtx* ctx, int32_t* host_out, void* side_stream) {
+  // copy the [grid][4] progress words on `side_stream` (a non-blocking stream: works while a frame kernel hangs)
+  if (!ctx || !host_out) return CSM_EINVAL;
+  CK(cudaMemcpyAsync(host_out, ctx->progress, (size_t)ctx->G * 4 * sizeof(int), cudaMemcpyDeviceToHost,
+                     (cudaStream_t)side_stream));
+  CK(cudaStreamSynchronize((cudaStream_t)side_stream));
   return CSM_OK;
 }
 

@@ -96,9 +96,59 @@ struct Lane {
   do {                                      \
     if ((L).prof) (L).prof[i] = clock64();  \
   } while (0)
+#define CSM_PROGRESS(p, c, tid, slot, v)                                      \
+  do {                                                                        \
+    if ((p).progress != nullptr && (tid) == 0) (p).progress[(c) * 4 + (slot)] = (v); \
+  } while (0)
 
-__device__ __forceinline__ void grid_wait(const unsigned int* counter, unsigned target) {
+// ---- hang guard ----
+// Every wait in this kernel is a spin on memory another CTA (or the TMA engine) will write.  A protocol bug or
+// a lost CTA would otherwise wedge the GPU for good; instead a wait that lasts longer than ~2 s records who waited
+// for what and raises the abort flag, which makes every wait in the grid give up and every later launch return at
+// once; the host reports it as an error (csm_frames_done / csm_generate_frame).  Cost: one counter increment
+// per failed poll.
+enum WaitId { W_STAGE = 1, W_CAND = 2, W_ATTN_DEC = 3, W_ATTN_BB_Q = 4, W_ATTN_BB_KV = 5, W_RESID = 6, W_GRID = 7,
+              W_FULL = 8, W_AFULL = 9, W_EMPTY = 10, W_AEMPTY = 11 };
+
+__device__ __noinline__ bool spin_slow(const StreamParams& p, unsigned& n, unsigned long long& t0, int ph, int id, unsigned a,
+                                       unsigned b) {
+  if (*reinterpret_cast<volatile int*>(p.abort_flag) != 0) return true;
+  unsigned long long now;
+  asm volatile("mov.u64 %0, %globaltimer;" : "=l"(now));
+  if (t0 == 0) { t0 = now; return false; }
+  if (now - t0 < 2000000000ull) return false;
+  if (atomicCAS(p.abort_flag, 0, 1) == 0) {
+    p.abort_flag[1] = (int)blockIdx.x; p.abort_flag[2] = ph; p.abort_flag[3] = id; p.abort_flag[4] = (int)a;
+    p.abort_flag[5] = (int)b; p.abort_flag[6] = (int)threadIdx.x;
+    __threadfence();
+  }
+  return true;
+}
+// Back-off between failed polls of the general (many-sequence) kernels: with 8-32 sequences a CTA re-reads 32-128 KB
+// per polling round; 148 CTAs doing that back to back saturate L2 and slow down the very producers they wait for
+// (observed as multi-second stalls at 24-32 sequences).  The <= 2-sequence kernels poll 4 KB and never sleep.
+__device__ __forceinline__ void poll_backoff(const StreamParams& p, unsigned n) {
+  if (!p.small) __nanosleep(n < 4u ? 100u : (n < 32u ? 400u : 1500u));
+}
+// call once per failed poll; true = give up
+__device__ __forceinline__ bool spin_giveup(const StreamParams& p, unsigned& n, unsigned long long& t0, int ph, int id,
+                                            unsigned a = 0, unsigned b = 0) {
+  if ((++n & 0x3ffu) != 0) return false;
+  return spin_slow(p, n, t0, ph, id, a, b);
+}
+
+__device__ __forceinline__ void grid_wait(const StreamParams& p, const unsigned int* counter, unsigned target, int ph) {
+  unsigned n = 0;
+  unsigned long long t0 = 0;
   while (ld_acquire_u32(counter) < target) {
+    if (spin_giveup(p, n, t0, ph, W_GRID, target)) break;
+  }
+}
+__device__ __forceinline__ void mbar_wait_g(const StreamParams& p, uint64_t* bar, uint32_t parity, int ph, int id) {
+  unsigned n = 0;
+  unsigned long long t0 = 0;
+  while (!mbar_try_wait(bar, parity)) {
+    if (spin_giveup(p, n, t0, ph, id, parity)) break;
   }
 }
 
@@ -122,6 +172,8 @@ __device__ __forceinline__ void reduce_candidates(const StreamParams& p, int war
   for (int m = warp; m < M; m += CSM_COMPUTE_WARPS) {
     unsigned long long w[5];
     bool ok;
+    unsigned spin = 0;
+    unsigned long long spin_t0 = 0;
     do {
       ok = true;
 #pragma unroll
@@ -133,6 +185,8 @@ __device__ __forceinline__ void reduce_candidates(const StreamParams& p, int war
           ok &= ((w[j] >> 32) & 0xffffull) == tag;
         }
       }
+      if (!ok) poll_backoff(p, spin);
+      if (!ok && spin_giveup(p, spin, spin_t0, head_ph, W_CAND, (unsigned)m, (unsigned)lane)) ok = true;
     } while (!__all_sync(0xffffffffu, ok));
     float best = -INFINITY;
     int bi = 0x7fffffff;
@@ -183,11 +237,15 @@ __device__ __forceinline__ void attn_dec_unit(const StreamParams& p, int layer, 
   const uint32_t* vw = kw + nk * HD;
   uint4 q4, k4, v4;
   bool ok;
+  unsigned spin = 0;
+  unsigned long long spin_t0 = 0;
   do {
     q4 = ld_tag4(qw);
     k4 = ld_tag4(kw);
     v4 = ld_tag4(vw);
     ok = tw_ok4(q4, qtag) & tw_ok4(k4, qtag) & tw_ok4(v4, qtag);
+    if (!ok) poll_backoff(p, spin);
+    if (!ok && spin_giveup(p, spin, spin_t0, layer, W_ATTN_DEC, (unsigned)(b * 256 + head), (unsigned)dec_pos)) ok = true;
   } while (!__all_sync(0xffffffffu, ok));
   const float sc = p.dec.scale;
   const float4 qf = make_float4(tw_val(q4.x) * sc, tw_val(q4.y) * sc, tw_val(q4.z) * sc, tw_val(q4.w) * sc);
@@ -305,11 +363,14 @@ __device__ __forceinline__ void stage_attn_dec(const StreamParams& p, const Phas
     const uint32_t* vw = kw + nk * HD;
     uint4 q4, k4, v4;
     bool ok;
+    unsigned spin = 0;
+    unsigned long long spin_t0 = 0;
     do {
       q4 = ld_tag4(qw);
       k4 = ld_tag4(kw);
       v4 = ld_tag4(vw);
       ok = tw_ok4(q4, qtag) & tw_ok4(k4, qtag) & tw_ok4(v4, qtag);
+      if (!ok && spin_giveup(p, spin, spin_t0, L.ph, W_ATTN_DEC, (unsigned)unit, (unsigned)dec_pos)) ok = true;
     } while (!__all_sync(0xffffffffu, ok));
     const float4 qf = make_float4(tw_val(q4.x) * sc, tw_val(q4.y) * sc, tw_val(q4.z) * sc, tw_val(q4.w) * sc);
     *reinterpret_cast<float4*>(qs + L.lane * 4) = qf;
@@ -359,8 +420,8 @@ __device__ __forceinline__ void stage_attn_dec(const StreamParams& p, const Phas
 // barrier pass 2 scales the thread's own elements in place (fixed summation order: deterministic).
 // K/4 is a power of two (checked at create time): item -> (row, group) is a shift and a mask.
 template <int U>
-__device__ __forceinline__ void stage_poll(const Phase& P, const Lane& L, const uint32_t* base, bf16* dst, int astride,
-                                           int total, int gsh, uint32_t tag, bool norm) {
+__device__ __forceinline__ void stage_poll(const StreamParams& p, const Phase& P, const Lane& L, const uint32_t* base,
+                                           bf16* dst, int astride, int total, int gsh, uint32_t tag, bool norm) {
   const int gmask = (1 << gsh) - 1, ppr = 1 << (gsh - 5);
   const int act_stride = P.act_stride;
   float* scratch = sm_scratch();
@@ -370,6 +431,8 @@ __device__ __forceinline__ void stage_poll(const Phase& P, const Lane& L, const 
     uint4 w[U];
     bool ok;
     int iters = 0;
+    unsigned spin = 0;
+    unsigned long long spin_t0 = 0;
     do {
       ok = true;
 #pragma unroll
@@ -381,6 +444,8 @@ __device__ __forceinline__ void stage_poll(const Phase& P, const Lane& L, const 
         }
       }
       ++iters;
+      if (!ok) poll_backoff(p, spin);
+      if (!ok && spin_giveup(p, spin, spin_t0, L.ph, W_STAGE, (unsigned)i0, w[0].x)) ok = true;
     } while (!__all_sync(0xffffffffu, ok));
     if (first && L.prof) { L.prof[8] = clock64(); L.prof[9] = (unsigned long long)iters; }
     first = false;
@@ -447,11 +512,11 @@ __device__ __forceinline__ void stage_act(const StreamParams& p, const Phase& P,
     nw1 = __ldg(reinterpret_cast<const uint2*>(P.norm_w) + ((L.tid + CSM_COMPUTE_THREADS) & gmask));
   }
   if (total <= CSM_COMPUTE_THREADS) {
-    if (L.tid < total) stage_poll<1>(P, L, base, dst, astride, total, gsh, tag, norm);   // whole warps (total % 32 == 0)
+    if (L.tid < total) stage_poll<1>(p, P, L, base, dst, astride, total, gsh, tag, norm);   // whole warps (total % 32 == 0)
   } else if (SMALL || total < 16 * CSM_COMPUTE_THREADS) {
-    stage_poll<4>(P, L, base, dst, astride, total, gsh, tag, norm);   // (8 in flight measured slower for few rows)
+    stage_poll<4>(p, P, L, base, dst, astride, total, gsh, tag, norm);   // (8 in flight measured slower for few rows)
   } else {
-    stage_poll<8>(P, L, base, dst, astride, total, gsh, tag, norm);
+    stage_poll<8>(p, P, L, base, dst, astride, total, gsh, tag, norm);
   }
   if (!norm) return;
   compute_sync();
@@ -579,13 +644,13 @@ __device__ __forceinline__ void gemv_core(const StreamParams& p, const Phase& P,
     const int T0 = ch * tpc;
     const int tiles = min(tpc, ntiles - T0);
     const uint32_t s = L.slot;
-    mbar_wait(&full[s], L.slot_par);
+    mbar_wait_g(p, &full[s], L.slot_par, L.ph, W_FULL);
     if (ch == 0) CSM_STAMP(L, 7);   // first weight chunk of the phase is in shared memory
     uint32_t aadd;
     uint32_t as = 0;
     if (stream) {
       as = L.aslot;
-      mbar_wait(&sm_afull()[as], L.aslot_par);
+      mbar_wait_g(p, &sm_afull()[as], L.aslot_par, L.ph, W_AFULL);
       aadd = as * (uint32_t)(p.act_region_bytes / 2);
     } else {
       aadd = (uint32_t)T0 * 32u;
@@ -671,9 +736,14 @@ _Pragma(CSM_STR(unroll CSM_MMA_UNROLL))
 }
 
 // ------------------------------------------------------------------ GEMV / skinny-GEMM phase
-__device__ __forceinline__ float resid_poll(const uint32_t* p, uint32_t tag) {
-  uint32_t w = ld_tag(p);
-  while ((w >> 16) != tag) w = ld_tag(p);
+__device__ __forceinline__ float resid_poll(const StreamParams& p, const uint32_t* q, uint32_t tag, int ph) {
+  uint32_t w = ld_tag(q);
+  unsigned n = 0;
+  unsigned long long t0 = 0;
+  while ((w >> 16) != tag) {
+    if (spin_giveup(p, n, t0, ph, W_RESID, w, tag)) break;
+    w = ld_tag(q);
+  }
   return tw_val(w);
 }
 
@@ -693,6 +763,7 @@ __device__ __forceinline__ bool gemv_phase(const StreamParams& p, const Phase& P
     stage_act<SMALL>(p, P, L, astride);
     compute_sync();
     CSM_STAMP(L, 4);   // activations staged
+    CSM_PROGRESS(p, L.c, L.tid, 1, 1);
     // every warp is inside this phase now: the other descriptor slot is free for the next phase
     if (fetch) reinterpret_cast<uint4*>(&sm_desc()[(L.ph + 1) & 1])[L.lane] = nxt;
   } else {
@@ -714,6 +785,7 @@ __device__ __forceinline__ bool gemv_phase(const StreamParams& p, const Phase& P
   CSM_STAMP(L, 5);     // this warp's MMAs done
   compute_sync();
   CSM_STAMP(L, 6);     // all warps' MMAs done
+  CSM_PROGRESS(p, L.c, L.tid, 1, 2);
 
   // ---- fused epilogues
   if (u < upc) {
@@ -748,7 +820,7 @@ __device__ __forceinline__ bool gemv_phase(const StreamParams& p, const Phase& P
         uint32_t* o = outw + (size_t)m * out_stride + gn;
         float r;
         if (m == m_first && (resid0 >> 16) == rtag) r = tw_val(resid0);
-        else r = resid_poll(o, rtag);
+        else r = resid_poll(p, o, rtag, L.ph);
         st_tag(o, tw_pack(r + v0, otag));
       } else if (epi == EPI_SWIGLU) {  // hf modeling_llama.py:183: bf16(silu(gate)) * up -> bf16 ; rows (2j,2j+1)=(gate_j,up_j)
         const float sl = bfround(v0 / (1.f + expf(-v0)));
@@ -984,6 +1056,8 @@ __device__ __noinline__ void attn_bb_phase(const StreamParams& p, int layer, int
       const uint32_t* qw = p.q_bb + (size_t)b * Wq + (kvh * REP) * HD + dl * 8;
       uint4 qa[REP], qb[REP];
       bool ok;
+      unsigned spin = 0;
+      unsigned long long spin_t0 = 0;
       do {
         ok = true;
 #pragma unroll
@@ -992,6 +1066,8 @@ __device__ __noinline__ void attn_bb_phase(const StreamParams& p, int layer, int
           qb[h] = ld_tag4(qw + h * HD + 4);
           ok &= tw_ok4(qa[h], qtag) & tw_ok4(qb[h], qtag);
         }
+        if (!ok) poll_backoff(p, spin);
+        if (!ok && spin_giveup(p, spin, spin_t0, ph, W_ATTN_BB_Q, (unsigned)unit)) ok = true;
       } while (!__all_sync(0xffffffffu, ok));
 #pragma unroll
       for (int h = 0; h < REP; ++h) {
@@ -1008,9 +1084,12 @@ __device__ __noinline__ void attn_bb_phase(const StreamParams& p, int layer, int
         const uint32_t* kw = p.q_bb + (size_t)b * Wq + p.bb.heads * HD + kvh * HD + dl * 8;
         const uint32_t* vw = kw + nk * HD;
         uint4 k0, k1, v0, v1;
+        unsigned spin = 0;
+        unsigned long long spin_t0 = 0;
         do {
           k0 = ld_tag4(kw); k1 = ld_tag4(kw + 4);
           v0 = ld_tag4(vw); v1 = ld_tag4(vw + 4);
+          if (spin_giveup(p, spin, spin_t0, ph, W_ATTN_BB_KV, (unsigned)unit)) break;
         } while (!(tw_ok4(k0, qtag) & tw_ok4(k1, qtag) & tw_ok4(v0, qtag) & tw_ok4(v1, qtag)));
         kv4[j] = make_uint4(tw_pair(k0.x, k0.y), tw_pair(k0.z, k0.w), tw_pair(k1.x, k1.y), tw_pair(k1.z, k1.w));
         vv4[j] = make_uint4(tw_pair(v0.x, v0.y), tw_pair(v0.z, v0.w), tw_pair(v1.x, v1.y), tw_pair(v1.z, v1.w));
@@ -1137,6 +1216,7 @@ __device__ __noinline__ void attn_bb_phase(const StreamParams& p, int layer, int
 template <int NB, int REP, bool SMALL>
 __global__ void __launch_bounds__(CSM_THREADS, 1) csm_stream_kernel(const __grid_constant__ StreamParams p) {
   if (p.stop_flag != nullptr && *p.stop_flag) return;   // generation already ended (set by an earlier launch)
+  if (*reinterpret_cast<volatile int*>(p.abort_flag) != 0) return;   // an earlier launch timed out
 
   Lane L;
   L.tid = threadIdx.x;
@@ -1193,13 +1273,14 @@ __global__ void __launch_bounds__(CSM_THREADS, 1) csm_stream_kernel(const __grid
       for (int ph = p.phase_begin; ph < p.phase_end; ++ph) {
         const Phase& P = p.phases[ph];
         if (P.type != PH_GEMV) continue;
+        if (p.progress != nullptr) p.progress[L.c * 4 + 2] = ph;
         const Geom g = csm_geom(P, L.c);
         const unsigned char* src = reinterpret_cast<const unsigned char*>(P.w) + (size_t)g.row0 * P.K * 2;
 #pragma unroll 1
         for (int ch = 0; ch < g.nchunks; ++ch) {
           const int tiles = min(g.tpc, g.ntiles - ch * g.tpc);
           const uint32_t bytes = (uint32_t)tiles * g.rows * 32u;
-          if (round > 0) mbar_wait(&empty[s], (round - 1u) & 1u);
+          if (round > 0) mbar_wait_g(p, &empty[s], (round - 1u) & 1u, ph, W_EMPTY);
           mbar_expect_tx(&full[s], bytes);
           if (p.evict_first) bulk_g2s_hint(ring + (size_t)s * p.slot_bytes, src, bytes, &full[s], pol);
           else bulk_g2s(ring + (size_t)s * p.slot_bytes, src, bytes, &full[s]);
@@ -1225,7 +1306,7 @@ __global__ void __launch_bounds__(CSM_THREADS, 1) csm_stream_kernel(const __grid
         if (g.nchunks == 0) continue;
         const bf16* actp = P.act;
         const int act_stride = P.act_stride;
-        if (p.use_barrier && ph > p.phase_begin) grid_wait(p.bar_counter, (unsigned)(P.bar_idx - bar_base) * L.G);
+        if (p.use_barrier && ph > p.phase_begin) grid_wait(p, p.bar_counter, (unsigned)(P.bar_idx - bar_base) * L.G, ph);
         fence_proxy_async();
         const int astride_b = (g.tpc * 16 + 8) * 2;
 #pragma unroll 1
@@ -1233,7 +1314,7 @@ __global__ void __launch_bounds__(CSM_THREADS, 1) csm_stream_kernel(const __grid
           const int tiles = min(g.tpc, g.ntiles - ch * g.tpc);
           const uint32_t rowbytes = (uint32_t)tiles * 32u;
           const uint32_t s = ait & 1u;
-          if (ait >= 2u) mbar_wait(&sm_aempty()[s], ((ait >> 1) - 1u) & 1u);
+          if (ait >= 2u) mbar_wait_g(p, &sm_aempty()[s], ((ait >> 1) - 1u) & 1u, ph, W_AEMPTY);
           mbar_expect_tx(&sm_afull()[s], rowbytes * (uint32_t)p.B);
           unsigned char* dst = actreg + (size_t)s * (p.act_region_bytes / 2);
           const unsigned char* src = reinterpret_cast<const unsigned char*>(actp) + (size_t)ch * g.tpc * 32;
@@ -1273,6 +1354,7 @@ __global__ void __launch_bounds__(CSM_THREADS, 1) csm_stream_kernel(const __grid
           continue;
         }
         if (P.type != PH_GEMV) continue;
+        if (p.progress != nullptr) p.progress[L.c * 4 + 3] = ph;
         if (P.norm_w != nullptr && (ph % L.G) == L.c) bulk_prefetch_l2(P.norm_w, (uint32_t)P.K * 2u);
         const Geom g = csm_geom(P, L.c);
         const unsigned char* src = reinterpret_cast<const unsigned char*>(P.w) + (size_t)g.row0 * P.K * 2;
@@ -1284,6 +1366,7 @@ __global__ void __launch_bounds__(CSM_THREADS, 1) csm_stream_kernel(const __grid
           while ((int)(pf - prog) > p.l2_ahead_bytes) {
             __nanosleep(500);
             prog = *sm_prog();
+            if (*reinterpret_cast<volatile int*>(p.abort_flag) != 0) return;
           }
           if ((int)(pf + n - prog) > 0) bulk_prefetch_l2(src + off, n);   // skip what the ring has already asked for
           pf += n;
@@ -1301,10 +1384,12 @@ __global__ void __launch_bounds__(CSM_THREADS, 1) csm_stream_kernel(const __grid
       prof = p.prof + ((size_t)(L.c == 0 ? 0 : 1) * p.n_phases_total + ph) * 16;
     L.prof = prof;
     L.ph = ph;
+    CSM_PROGRESS(p, L.c, L.tid, 0, ph);
+    CSM_PROGRESS(p, L.c, L.tid, 1, 0);
     // descriptor of this phase is in shared memory (read in place); fetch the next one while this phase runs
     const Phase& P = sm_desc()[ph & 1];
     if ((P.flags & CSM_PF_BAR_IN) && p.use_barrier && ph > p.phase_begin) {
-      if (L.tid == 0) grid_wait(p.bar_counter, (unsigned)(P.bar_idx - bar_base) * L.G);
+      if (L.tid == 0) grid_wait(p, p.bar_counter, (unsigned)(P.bar_idx - bar_base) * L.G, ph);
       compute_sync();
     }
     if (prof) prof[0] = clock64();       // (barrier observed)

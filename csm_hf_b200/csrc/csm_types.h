@@ -127,6 +127,10 @@ struct StreamParams {
   int rope_bytes, act_region_bytes, red_bytes;
   unsigned long long* prof;     // debug: clock64 stamps [2 CTAs (first,last)][n_phases_total][4], see csm_stream.cu
   int n_phases_total;
+  int* abort_flag;              // [0] != 0: a wait inside a frame kernel timed out (or an earlier launch did): every wait
+                                // gives up, later launches return at once; [1..7] = (cta, phase, wait id, detail...)
+  int* progress;                // debug (CSM_DEBUG_PROGRESS=1): [grid][4] = phase of the compute warps, step inside it,
+                                // phase of the weight stream, phase of the L2 prefetcher -- read by a watchdog on a hang
 };
 
 // Row split and chunking of one weight matrix for one CTA.

@@ -143,6 +143,10 @@ int csm_debug_copy(CsmCtx* ctx, int which, void* dst_device, int64_t max_bytes, 
 int csm_debug_run_phases(CsmCtx* ctx, const int64_t* ids, const int32_t* mask, int B, int ph_begin, int ph_end,
                          int forced, void* stream);
 int csm_debug_set_cache_len(CsmCtx* ctx, int len);
+/* Watchdog aid (engine created with CSM_DEBUG_PROGRESS=1): host_out[grid][4] = (phase of the compute warps, step
+ * inside it, phase of the weight stream, phase of the L2 prefetcher) of every CTA, copied on `side_stream`
+ * (must be a non-blocking stream) so that it can be read while a frame kernel is still running. */
+int csm_debug_progress(CsmCtx* ctx, int32_t* host_out, void* side_stream);
 /* One decode frame with per-phase stamps.  clocks_host holds (32 + grid) * phases uint64:
  *   [2][phases][16] clock64 of the first and the last CTA: (phase top, body start, body end, phase end,
  *     activations staged, own MMAs done, all MMAs done, first weight chunk resident, input poll succeeded,
