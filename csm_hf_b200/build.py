@@ -26,7 +26,8 @@ def needs_build() -> bool:
     if not os.path.isfile(LIB):
         return True
     t = os.path.getmtime(LIB)
-    deps = sources() + glob.glob(os.path.join(CSRC, "*.h")) + glob.glob(os.path.join(CSRC, "*.cuh")) + [
+    deps = sources() + glob.glob(os.path.join(CSRC, "*.h")) + glob.glob(os.path.join(CSRC, "*.cuh")) + glob.glob(
+        os.path.join(CSRC, "*.inl")) + [
         os.path.join(os.path.dirname(HERE), "include", "csm_b200.h")]
     return any(os.path.getmtime(d) > t for d in deps)
 

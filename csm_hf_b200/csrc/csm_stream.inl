@@ -37,7 +37,14 @@
 //   * every cross-CTA read is issued as one batch of independent loads (one L2 round trip);
 //   * greedy sampling needs no extra synchronisation: every CTA publishes its best (logit, id) as a tagged
 //     word and the consumers reduce the 148 candidates themselves.
+//
+// This file is compiled twice (csm_stream_small.cu: engines for <= 2 sequences, nothing on the hot path that is
+// not needed there -- no hang guard, no debug hooks, no poll back-off; csm_stream_general.cu: everything else).
 #include "csm_common.cuh"
+
+#ifndef CSM_BUILD_SMALL
+#error "include this file from csm_stream_small.cu / csm_stream_general.cu"
+#endif
 
 // build-time experiment knobs (tools/gpu_variants.sh builds several libraries and times them in one GPU call)
 #ifndef CSM_MMA_UNROLL
@@ -48,6 +55,12 @@
 #endif
 #ifndef CSM_NORM_SPLIT
 #define CSM_NORM_SPLIT 1
+#endif
+#ifndef CSM_GUARD
+#define CSM_GUARD (!CSM_BUILD_SMALL)
+#endif
+#ifndef CSM_PROGRESS_HOOKS
+#define CSM_PROGRESS_HOOKS (!CSM_BUILD_SMALL)
 #endif
 #define CSM_STR2(x) #x
 #define CSM_STR(x) CSM_STR2(x)
@@ -98,7 +111,7 @@ struct Lane {
   } while (0)
 #define CSM_PROGRESS(p, c, tid, slot, v)                                      \
   do {                                                                        \
-    if ((p).progress != nullptr && (tid) == 0) (p).progress[(c) * 4 + (slot)] = (v); \
+    if (CSM_PROGRESS_HOOKS && (p).progress != nullptr && (tid) == 0) (p).progress[(c) * 4 + (slot)] = (v); \
   } while (0)
 
 // ---- hang guard ----
@@ -110,13 +123,9 @@ struct Lane {
 enum WaitId { W_STAGE = 1, W_CAND = 2, W_ATTN_DEC = 3, W_ATTN_BB_Q = 4, W_ATTN_BB_KV = 5, W_RESID = 6, W_GRID = 7,
               W_FULL = 8, W_AFULL = 9, W_EMPTY = 10, W_AEMPTY = 11 };
 
-__device__ __noinline__ bool spin_slow(const StreamParams& p, unsigned& n, unsigned long long& t0, int ph, int id, unsigned a,
-                                       unsigned b) {
+__device__ __noinline__ bool spin_slow(const StreamParams& p, unsigned n, int ph, int id, unsigned a, unsigned b) {
   if (*reinterpret_cast<volatile int*>(p.abort_flag) != 0) return true;
-  unsigned long long now;
-  asm volatile("mov.u64 %0, %globaltimer;" : "=l"(now));
-  if (t0 == 0) { t0 = now; return false; }
-  if (now - t0 < 2000000000ull) return false;
+  if (n < (1u << 22)) return false;            // >= 4M failed polls of >= 0.15-0.5 us each: seconds
   if (atomicCAS(p.abort_flag, 0, 1) == 0) {
     p.abort_flag[1] = (int)blockIdx.x; p.abort_flag[2] = ph; p.abort_flag[3] = id; p.abort_flag[4] = (int)a;
     p.abort_flag[5] = (int)b; p.abort_flag[6] = (int)threadIdx.x;
@@ -126,29 +135,28 @@ __device__ __noinline__ bool spin_slow(const StreamParams& p, unsigned& n, unsig
 }
 // Back-off between failed polls of the general (many-sequence) kernels: with 8-32 sequences a CTA re-reads 32-128 KB
 // per polling round; 148 CTAs doing that back to back saturate L2 and slow down the very producers they wait for
-// (observed as multi-second stalls at 24-32 sequences).  The <= 2-sequence kernels poll 4 KB and never sleep.
+// (observed as multi-second stalls at 24-32 sequences).  Below 16 sequences nobody sleeps.
 __device__ __forceinline__ void poll_backoff(const StreamParams& p, unsigned n) {
-  if (!p.small) __nanosleep(n < 4u ? 100u : (n < 32u ? 400u : 1500u));
+  if (!CSM_BUILD_SMALL && p.B >= 16) __nanosleep(n < 4u ? 100u : (n < 32u ? 400u : 1500u));
 }
-// call once per failed poll; true = give up
-__device__ __forceinline__ bool spin_giveup(const StreamParams& p, unsigned& n, unsigned long long& t0, int ph, int id,
-                                            unsigned a = 0, unsigned b = 0) {
-  if ((++n & 0x3ffu) != 0) return false;
-  return spin_slow(p, n, t0, ph, id, a, b);
+// call once per failed poll (one add and one test on the fast path); true = give up
+__device__ __forceinline__ bool spin_giveup(const StreamParams& p, unsigned& n, int ph, int id, unsigned a = 0,
+                                            unsigned b = 0) {
+  if (!CSM_GUARD) return false;
+  if ((++n & 0xffffu) != 0) return false;
+  return spin_slow(p, n, ph, id, a, b);
 }
 
 __device__ __forceinline__ void grid_wait(const StreamParams& p, const unsigned int* counter, unsigned target, int ph) {
   unsigned n = 0;
-  unsigned long long t0 = 0;
   while (ld_acquire_u32(counter) < target) {
-    if (spin_giveup(p, n, t0, ph, W_GRID, target)) break;
+    if (spin_giveup(p, n, ph, W_GRID, target)) break;
   }
 }
 __device__ __forceinline__ void mbar_wait_g(const StreamParams& p, uint64_t* bar, uint32_t parity, int ph, int id) {
   unsigned n = 0;
-  unsigned long long t0 = 0;
   while (!mbar_try_wait(bar, parity)) {
-    if (spin_giveup(p, n, t0, ph, id, parity)) break;
+    if (spin_giveup(p, n, ph, id, parity)) break;
   }
 }
 
@@ -173,7 +181,6 @@ __device__ __forceinline__ void reduce_candidates(const StreamParams& p, int war
     unsigned long long w[5];
     bool ok;
     unsigned spin = 0;
-    unsigned long long spin_t0 = 0;
     do {
       ok = true;
 #pragma unroll
@@ -186,7 +193,7 @@ __device__ __forceinline__ void reduce_candidates(const StreamParams& p, int war
         }
       }
       if (!ok) poll_backoff(p, spin);
-      if (!ok && spin_giveup(p, spin, spin_t0, head_ph, W_CAND, (unsigned)m, (unsigned)lane)) ok = true;
+      if (!ok && spin_giveup(p, spin, head_ph, W_CAND, (unsigned)m, (unsigned)lane)) ok = true;
     } while (!__all_sync(0xffffffffu, ok));
     float best = -INFINITY;
     int bi = 0x7fffffff;
@@ -238,14 +245,13 @@ __device__ __forceinline__ void attn_dec_unit(const StreamParams& p, int layer, 
   uint4 q4, k4, v4;
   bool ok;
   unsigned spin = 0;
-  unsigned long long spin_t0 = 0;
   do {
     q4 = ld_tag4(qw);
     k4 = ld_tag4(kw);
     v4 = ld_tag4(vw);
     ok = tw_ok4(q4, qtag) & tw_ok4(k4, qtag) & tw_ok4(v4, qtag);
     if (!ok) poll_backoff(p, spin);
-    if (!ok && spin_giveup(p, spin, spin_t0, layer, W_ATTN_DEC, (unsigned)(b * 256 + head), (unsigned)dec_pos)) ok = true;
+    if (!ok && spin_giveup(p, spin, layer, W_ATTN_DEC, (unsigned)(b * 256 + head), (unsigned)dec_pos)) ok = true;
   } while (!__all_sync(0xffffffffu, ok));
   const float sc = p.dec.scale;
   const float4 qf = make_float4(tw_val(q4.x) * sc, tw_val(q4.y) * sc, tw_val(q4.z) * sc, tw_val(q4.w) * sc);
@@ -364,13 +370,12 @@ __device__ __forceinline__ void stage_attn_dec(const StreamParams& p, const Phas
     uint4 q4, k4, v4;
     bool ok;
     unsigned spin = 0;
-    unsigned long long spin_t0 = 0;
     do {
       q4 = ld_tag4(qw);
       k4 = ld_tag4(kw);
       v4 = ld_tag4(vw);
       ok = tw_ok4(q4, qtag) & tw_ok4(k4, qtag) & tw_ok4(v4, qtag);
-      if (!ok && spin_giveup(p, spin, spin_t0, L.ph, W_ATTN_DEC, (unsigned)unit, (unsigned)dec_pos)) ok = true;
+      if (!ok && spin_giveup(p, spin, L.ph, W_ATTN_DEC, (unsigned)unit, (unsigned)dec_pos)) ok = true;
     } while (!__all_sync(0xffffffffu, ok));
     const float4 qf = make_float4(tw_val(q4.x) * sc, tw_val(q4.y) * sc, tw_val(q4.z) * sc, tw_val(q4.w) * sc);
     *reinterpret_cast<float4*>(qs + L.lane * 4) = qf;
@@ -432,7 +437,6 @@ __device__ __forceinline__ void stage_poll(const StreamParams& p, const Phase& P
     bool ok;
     int iters = 0;
     unsigned spin = 0;
-    unsigned long long spin_t0 = 0;
     do {
       ok = true;
 #pragma unroll
@@ -445,7 +449,7 @@ __device__ __forceinline__ void stage_poll(const StreamParams& p, const Phase& P
       }
       ++iters;
       if (!ok) poll_backoff(p, spin);
-      if (!ok && spin_giveup(p, spin, spin_t0, L.ph, W_STAGE, (unsigned)i0, w[0].x)) ok = true;
+      if (!ok && spin_giveup(p, spin, L.ph, W_STAGE, (unsigned)i0, w[0].x)) ok = true;
     } while (!__all_sync(0xffffffffu, ok));
     if (first && L.prof) { L.prof[8] = clock64(); L.prof[9] = (unsigned long long)iters; }
     first = false;
@@ -739,9 +743,8 @@ _Pragma(CSM_STR(unroll CSM_MMA_UNROLL))
 __device__ __forceinline__ float resid_poll(const StreamParams& p, const uint32_t* q, uint32_t tag, int ph) {
   uint32_t w = ld_tag(q);
   unsigned n = 0;
-  unsigned long long t0 = 0;
   while ((w >> 16) != tag) {
-    if (spin_giveup(p, n, t0, ph, W_RESID, w, tag)) break;
+    if (spin_giveup(p, n, ph, W_RESID, w, tag)) break;
     w = ld_tag(q);
   }
   return tw_val(w);
@@ -1057,8 +1060,7 @@ __device__ __noinline__ void attn_bb_phase(const StreamParams& p, int layer, int
       uint4 qa[REP], qb[REP];
       bool ok;
       unsigned spin = 0;
-      unsigned long long spin_t0 = 0;
-      do {
+        do {
         ok = true;
 #pragma unroll
         for (int h = 0; h < REP; ++h) {
@@ -1067,7 +1069,7 @@ __device__ __noinline__ void attn_bb_phase(const StreamParams& p, int layer, int
           ok &= tw_ok4(qa[h], qtag) & tw_ok4(qb[h], qtag);
         }
         if (!ok) poll_backoff(p, spin);
-        if (!ok && spin_giveup(p, spin, spin_t0, ph, W_ATTN_BB_Q, (unsigned)unit)) ok = true;
+        if (!ok && spin_giveup(p, spin, ph, W_ATTN_BB_Q, (unsigned)unit)) ok = true;
       } while (!__all_sync(0xffffffffu, ok));
 #pragma unroll
       for (int h = 0; h < REP; ++h) {
@@ -1085,11 +1087,10 @@ __device__ __noinline__ void attn_bb_phase(const StreamParams& p, int layer, int
         const uint32_t* vw = kw + nk * HD;
         uint4 k0, k1, v0, v1;
         unsigned spin = 0;
-        unsigned long long spin_t0 = 0;
-        do {
+            do {
           k0 = ld_tag4(kw); k1 = ld_tag4(kw + 4);
           v0 = ld_tag4(vw); v1 = ld_tag4(vw + 4);
-          if (spin_giveup(p, spin, spin_t0, ph, W_ATTN_BB_KV, (unsigned)unit)) break;
+          if (spin_giveup(p, spin, ph, W_ATTN_BB_KV, (unsigned)unit)) break;
         } while (!(tw_ok4(k0, qtag) & tw_ok4(k1, qtag) & tw_ok4(v0, qtag) & tw_ok4(v1, qtag)));
         kv4[j] = make_uint4(tw_pair(k0.x, k0.y), tw_pair(k0.z, k0.w), tw_pair(k1.x, k1.y), tw_pair(k1.z, k1.w));
         vv4[j] = make_uint4(tw_pair(v0.x, v0.y), tw_pair(v0.z, v0.w), tw_pair(v1.x, v1.y), tw_pair(v1.z, v1.w));
@@ -1216,7 +1217,7 @@ __device__ __noinline__ void attn_bb_phase(const StreamParams& p, int layer, int
 template <int NB, int REP, bool SMALL>
 __global__ void __launch_bounds__(CSM_THREADS, 1) csm_stream_kernel(const __grid_constant__ StreamParams p) {
   if (p.stop_flag != nullptr && *p.stop_flag) return;   // generation already ended (set by an earlier launch)
-  if (*reinterpret_cast<volatile int*>(p.abort_flag) != 0) return;   // an earlier launch timed out
+  if (CSM_GUARD && *reinterpret_cast<volatile int*>(p.abort_flag) != 0) return;   // an earlier launch timed out
 
   Lane L;
   L.tid = threadIdx.x;
@@ -1432,24 +1433,38 @@ __global__ void __launch_bounds__(CSM_THREADS, 1) csm_stream_kernel(const __grid
 // attention variant, which keeps its instruction footprint small.
 typedef void (*StreamKernel)(const StreamParams);
 
-static StreamKernel pick_kernel(int nb, int rep, bool small) {
-#define CSM_PICK(NBV, SM)                                                \
-  switch (rep) {                                                         \
-    case 1: return csm_stream_kernel<NBV, 1, SM>;                        \
-    case 2: return csm_stream_kernel<NBV, 2, SM>;                        \
-    default: return csm_stream_kernel<NBV, 4, SM>;                       \
+#if CSM_BUILD_SMALL
+extern "C" cudaError_t csm_launch_stream_small(const StreamParams* p, int grid, size_t smem, cudaStream_t stream,
+                                               int cooperative) {
+  StreamKernel k;
+  switch (p->bb.heads / p->bb.kv) {
+    case 1: k = csm_stream_kernel<1, 1, true>; break;
+    case 2: k = csm_stream_kernel<1, 2, true>; break;
+    default: k = csm_stream_kernel<1, 4, true>; break;
   }
-  if (small) { CSM_PICK(1, true) }
-  if (nb <= 1) { CSM_PICK(1, false) }
-  if (nb <= 2) { CSM_PICK(2, false) }
-  CSM_PICK(4, false)
+#else
+extern "C" cudaError_t csm_launch_stream_small(const StreamParams* p, int grid, size_t smem, cudaStream_t stream,
+                                               int cooperative);
+
+static StreamKernel pick_kernel(int nb, int rep) {
+#define CSM_PICK(NBV)                                                    \
+  switch (rep) {                                                         \
+    case 1: return csm_stream_kernel<NBV, 1, false>;                     \
+    case 2: return csm_stream_kernel<NBV, 2, false>;                     \
+    default: return csm_stream_kernel<NBV, 4, false>;                    \
+  }
+  if (nb <= 1) { CSM_PICK(1) }
+  if (nb <= 2) { CSM_PICK(2) }
+  CSM_PICK(4)
 #undef CSM_PICK
 }
 
 extern "C" cudaError_t csm_launch_stream(const StreamParams* p, int grid, size_t smem, cudaStream_t stream,
                                          int cooperative) {
+  if (p->small) return csm_launch_stream_small(p, grid, smem, stream, cooperative);
   const int nb = (p->B + 7) / 8, rep = p->bb.heads / p->bb.kv;
-  StreamKernel k = pick_kernel(nb, rep, p->small != 0);
+  StreamKernel k = pick_kernel(nb, rep);
+#endif
   cudaError_t e = cudaFuncSetAttribute((const void*)k, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
   if (e != cudaSuccess) return e;
   if (cooperative) {

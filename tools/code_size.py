@@ -5,7 +5,7 @@ import re
 import sys
 from collections import Counter
 
-src = open('csm_hf_b200/csrc/csm_stream.cu').read().split('\n')
+src = open('csm_hf_b200/csrc/csm_stream.inl').read().split('\n')
 marks = [(1, 'top')]
 for i, l in enumerate(src, 1):
     m = re.match(r'(?:__device__ __forceinline__|__global__).*?(\w+)\(', l)

@@ -33,7 +33,7 @@ for a, s, e, txt in sass:
     exe[k] += e
     tot += s
 top = int(sys.argv[4]) if len(sys.argv) > 4 else 40
-src = open('csm_hf_b200/csrc/csm_stream.cu').read().split('\n')
+src = open('csm_hf_b200/csrc/csm_stream.inl').read().split('\n')
 com = open('csm_hf_b200/csrc/csm_common.cuh').read().split('\n')
 print("total samples", tot)
 for k, s in samp.most_common(top):
