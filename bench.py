@@ -139,7 +139,7 @@ def main():
                   f"({statistics.mean(x[1] for x in vals):.2f} s) + {a.cpu_sample_frames} decode frames "
                   f"({statistics.mean(x[2] for x in vals):.3f} s each), projected to {a.frames} frames, batch 1")
         print(json.dumps({
-            "impl": "reference", "metric": "audio_frames_per_s", "value": v, "unit": "frames/s", "n_gpus": 0,
+            "impl": "reference", "metric": "audio_frames_per_s", "value": v, "unit": "frames/s", "n_gpus": a.gpus,
             "steps": a.steps, "warmup": a.warmup, "ms_per_step": 1000.0 * a.frames / v, "higher_is_better": True,
             "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
             "config": {"workload": workload.replace(f"batch={a.batch} per GPU", "batch=1")},

@@ -70,6 +70,7 @@ struct CsmCtx {
   Stack bb, dec;
   bf16 *text_emb = nullptr, *audio_emb = nullptr;
   bf16 *p_proj = nullptr, *p_c0 = nullptr;
+  bf16* proj_table = nullptr;   // projection(audio_embeddings) [32*V][Hd]: the decoder input of positions 1..31 is a row gather
   std::vector<bf16*> p_heads;
   // workspace
   bf16 *kc_bb = nullptr, *vc_bb = nullptr, *kc_dec = nullptr, *vc_dec = nullptr;
@@ -265,7 +266,11 @@ Phase gemv(int act_mode, int epi, int gran, int N, int K, int stack, int layer, 
 }
 
 // One transformer layer.  h_ph: index of the phase that last wrote the residual stream (in/out).
-void add_layer_phases(CsmCtx* ctx, Stack& S, int stack, int l, int dec_pos, bool kv_only, int& h_ph) {
+// gather_cb >= 0 (decoder layer 0 of positions 1..31): the layer input is not read from the residual stream but
+// gathered from the pre-projected embedding table with the token sampled by head phase `head_ph`; the qkv phase
+// also starts the residual stream (one CTA per sequence writes the gathered row as tagged words).
+void add_layer_phases(CsmCtx* ctx, Stack& S, int stack, int l, int dec_pos, bool kv_only, int& h_ph, int gather_cb = -1,
+                      int head_ph = 0) {
   const StackDims& d = S.d;
   LayerW& L = S.layers[l];
   uint32_t* h = stack ? ctx->h_dec : ctx->h_bb;
@@ -276,6 +281,14 @@ void add_layer_phases(CsmCtx* ctx, Stack& S, int stack, int l, int dec_pos, bool
   auto idx = [&]() { return (int)ctx->table.size(); };
   const int iq = idx();
   Phase P = gemv(ACT_NORM, EPI_QKV, 2, nq + 2 * nkv, d.H, stack, l, L.p_qkv, h, d.H, L.ln1, qb, nq + 2 * nkv, h_ph);
+  if (gather_cb >= 0) {
+    P.act_mode = ACT_GATHER;
+    P.act = ctx->proj_table;
+    P.cb = gather_cb;
+    P.res_ph = head_ph;                 // candidates to reduce
+    P.norm_out = (bf16*)h;              // tagged residual stream to start
+    h_ph = iq;
+  }
   P.dec_pos = dec_pos;
   if (stack && ctx->fuse_attn && !kv_only) P.flags |= CSM_PF_KV_COPY;
   ctx->table.push_back(P);
@@ -331,13 +344,12 @@ void build_table(CsmCtx* ctx) {
     int hd_ph = (int)ctx->table.size();
     if (pos == 0) {
       P = gemv(ACT_NORM, EPI_STORE, 1, d.H, b.H, 0, 0, ctx->p_proj, ctx->h_bb, b.H, ctx->bb.norm, ctx->h_dec, d.H, hb_ph);
-    } else {
-      P = gemv(ACT_GATHER, EPI_STORE, 1, d.H, b.H, 1, 0, ctx->p_proj, ctx->audio_emb, b.H, nullptr, ctx->h_dec, d.H, 0,
-               head_ph);
-      P.cb = pos - 1;
+      ctx->table.push_back(P);
     }
-    ctx->table.push_back(P);
-    for (int l = 0; l < d.L; ++l) add_layer_phases(ctx, ctx->dec, 1, l, pos, pos == 0 && l == d.L - 1, hd_ph);
+    // positions 1..31: projection(embedding(token)) is a row of proj_table, gathered by layer 0's qkv phase
+    for (int l = 0; l < d.L; ++l)
+      add_layer_phases(ctx, ctx->dec, 1, l, pos, pos == 0 && l == d.L - 1, hd_ph, (pos >= 1 && l == 0) ? pos - 1 : -1,
+                       head_ph);
     if (pos >= 1) {
       // audio_head[pos-1] on the decoder's final-norm output, greedy sample (modeling_csm.py:557-560)
       head_ph = (int)ctx->table.size();
@@ -689,6 +701,12 @@ int csm_create(const CsmShapes* sh, const CsmWeights* w, int max_batch, int max_
   if ((r = build_stack(ctx, ctx->bb, sh->backbone, w->backbone_layers, w->backbone_norm, true, st))) return r;
   if ((r = build_stack(ctx, ctx->dec, sh->decoder, w->decoder_layers, w->decoder_norm, false, st))) return r;
   if ((r = pack_matrix(ctx, &ctx->p_proj, one_src((const bf16*)w->projection, Hd, Hb, 1), nullptr, Hd, Hb, 1, st))) return r;
+  // projection applied once to the whole audio table (modeling_csm.py:564-565 applies it to one gathered row per
+  // codebook and frame: the same function of the same row, so it is folded into a [32*V, Hd] table)
+  if (cublasCreate(&ctx->cublas) != CUBLAS_STATUS_SUCCESS) return fail(ctx, CSM_ECUDA, "cublasCreate failed");
+  DA(ctx->proj_table, (size_t)sh->audio_vocab * CSM_NQ * Hd);
+  if ((r = gemm_bf16(ctx, ctx->audio_emb, Hb, (const bf16*)w->projection, Hd, Hb, ctx->proj_table, Hd, sh->audio_vocab * CSM_NQ, st)))
+    return r;
   if ((r = pack_matrix(ctx, &ctx->p_c0, one_src((const bf16*)w->codebook0_head, ctx->V, Hb, 1), nullptr, ctx->V, Hb, 1, st)))
     return r;
   ctx->p_heads.resize(CSM_NQ - 1);
@@ -751,7 +769,6 @@ int csm_create(const CsmShapes* sh, const CsmWeights* w, int max_batch, int max_
   CK(cudaMemsetAsync(ctx->progress, 0xff, (size_t)ctx->sms * 4 * sizeof(int), st));
   if (const char* e = getenv("CSM_DEBUG_PROGRESS")) ctx->progress_on = atoi(e) != 0;
   CK(cudaMemcpyAsync(ctx->d_table, ctx->table.data(), ctx->table.size() * sizeof(Phase), cudaMemcpyHostToDevice, st));
-  if (cublasCreate(&ctx->cublas) != CUBLAS_STATUS_SUCCESS) return fail(ctx, CSM_ECUDA, "cublasCreate failed");
   CK(cudaEventCreate(&ctx->ev0));
   CK(cudaEventCreate(&ctx->ev1));
   CK(cudaStreamSynchronize(st));

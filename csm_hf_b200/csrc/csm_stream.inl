@@ -477,36 +477,7 @@ __device__ __forceinline__ void stage_act(const StreamParams& p, const Phase& P,
   const int K = P.K, M = p.B;
   bf16* dst = reinterpret_cast<bf16*>(sm_act(p));
   const int gsh = P.gsh;                         // log2(K/4)
-  if (P.act_mode == ACT_GATHER) {
-    // _embed_audio (modeling_csm.py:247-259): row tok + codebook*V of the audio table (plain bf16, read-only)
-    reduce_candidates(p, L.warp, L.lane, L.c, L.G, P.cb, P.res_ph);
-    const int sh = gsh - 1, mask = (1 << sh) - 1;   // 16-byte groups (8 bf16) per row = K/8
-    const int total = M << sh;
-    const int* tok = sm_tok();
-    const bf16* tab = P.act + (size_t)(P.cb * p.V) * K;
-#pragma unroll 1
-    for (int i0 = L.tid; i0 < total; i0 += 4 * CSM_COMPUTE_THREADS) {
-      uint4 v[4];
-#pragma unroll
-      for (int j = 0; j < 4; ++j) {
-        const int i = i0 + j * CSM_COMPUTE_THREADS;
-        if (i < total) v[j] = __ldg(reinterpret_cast<const uint4*>(tab + (size_t)tok[i >> sh] * K) + (i & mask));
-      }
-#pragma unroll
-      for (int j = 0; j < 4; ++j) {
-        const int i = i0 + j * CSM_COMPUTE_THREADS;
-        if (i < total) *reinterpret_cast<uint4*>(dst + (size_t)(i >> sh) * astride + (i & mask) * 8) = v[j];
-      }
-    }
-    return;
-  }
-  if (SMALL && P.act_mode == ACT_ATTN) {
-    stage_attn_dec(p, P, L, astride);
-    return;
-  }
-  const uint32_t tag = tg(p, P.src_ph);
-  const uint32_t* base = reinterpret_cast<const uint32_t*>(P.act);
-  const bool norm = P.act_mode == ACT_NORM;
+  const bool norm = P.act_mode == ACT_NORM || P.act_mode == ACT_GATHER;
   const int gmask = (1 << gsh) - 1;
   const int total = M << gsh;
   // norm weights of this thread's (at most two) column groups, requested before the poll starts
@@ -515,6 +486,47 @@ __device__ __forceinline__ void stage_act(const StreamParams& p, const Phase& P,
     nw0 = __ldg(reinterpret_cast<const uint2*>(P.norm_w) + (L.tid & gmask));
     nw1 = __ldg(reinterpret_cast<const uint2*>(P.norm_w) + ((L.tid + CSM_COMPUTE_THREADS) & gmask));
   }
+  if (P.act_mode == ACT_GATHER) {
+    // decoder input of positions 1..31: projection(_embed_audio(codebook, token)) (modeling_csm.py:247-259,
+    // 564-565) = row token + codebook*V of the pre-projected table (plain bf16, read-only).  The token is the
+    // greedy sample of the previous head phase.  One CTA per sequence also starts the residual stream with it.
+    reduce_candidates(p, L.warp, L.lane, L.c, L.G, P.cb, P.res_ph);
+    const int* tok = sm_tok();
+    const bf16* tab = P.act + (size_t)(P.cb * p.V) * K;
+    const int ppr = 1 << (gsh - 5);
+    float* scratch = sm_scratch();
+    uint32_t* hres = reinterpret_cast<uint32_t*>(P.norm_out);
+    const uint32_t otag = tg(p, L.ph);
+#pragma unroll 1
+    for (int i0 = L.tid; i0 < total; i0 += 4 * CSM_COMPUTE_THREADS) {
+      uint2 v[4];
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        const int i = i0 + j * CSM_COMPUTE_THREADS;
+        if (i < total) v[j] = __ldg(reinterpret_cast<const uint2*>(tab + (size_t)tok[i >> gsh] * K) + (i & gmask));
+      }
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        const int i = i0 + j * CSM_COMPUTE_THREADS;
+        if (i < total) {   // warp-uniform
+          const int m = i >> gsh, g = i & gmask;
+          *reinterpret_cast<uint2*>(dst + (size_t)m * astride + g * 4) = v[j];
+          const float a = bf_lo(v[j].x), b = bf_hi(v[j].x), c = bf_lo(v[j].y), d = bf_hi(v[j].y);
+          const float ss = warp_sum(a * a + b * b + c * c + d * d);
+          if (L.lane == 0) scratch[m * ppr + (g >> 5)] = ss;
+          if ((m % L.G) == L.c)
+            st_tag4(hres + (size_t)m * K + g * 4, (otag << 16) | (v[j].x & 0xffffu), (otag << 16) | (v[j].x >> 16),
+                    (otag << 16) | (v[j].y & 0xffffu), (otag << 16) | (v[j].y >> 16));
+        }
+      }
+    }
+  } else
+  if (SMALL && P.act_mode == ACT_ATTN) {
+    stage_attn_dec(p, P, L, astride);
+    return;
+  } else {
+  const uint32_t tag = tg(p, P.src_ph);
+  const uint32_t* base = reinterpret_cast<const uint32_t*>(P.act);
   if (total <= CSM_COMPUTE_THREADS) {
     if (L.tid < total) stage_poll<1>(p, P, L, base, dst, astride, total, gsh, tag, norm);   // whole warps (total % 32 == 0)
   } else if (SMALL || total < 16 * CSM_COMPUTE_THREADS) {
@@ -522,12 +534,14 @@ __device__ __forceinline__ void stage_act(const StreamParams& p, const Phase& P,
   } else {
     stage_poll<8>(p, P, L, base, dst, astride, total, gsh, tag, norm);
   }
+  }
   if (!norm) return;
   compute_sync();
   const float eps = P.stack ? p.dec.eps : p.bb.eps;
   const int ppr = 1 << (gsh - 5);
   const float fK = (float)K;
   float* scratch = sm_scratch();
+  const bool keep_norm = P.norm_out != nullptr && P.act_mode == ACT_NORM;   // copy of the normalised rows (last_hidden_state)
   if (SMALL || M <= 2) {
     // one or two rows: every thread derives its row's rstd itself (no further barrier)
     const bool wide = (1 << gsh) > CSM_COMPUTE_THREADS;   // two column groups per thread (K = 2048)
@@ -546,7 +560,7 @@ __device__ __forceinline__ void stage_act(const StreamParams& p, const Phase& P,
       const float y2 = bfround(bf_lo(x.y) * rstd), y3 = bfround(bf_hi(x.y) * rstd);
       const uint2 o = make_uint2(pack_bf16(bf_lo(nw.x) * y0, bf_hi(nw.x) * y1), pack_bf16(bf_lo(nw.y) * y2, bf_hi(nw.y) * y3));
       *px = o;
-      if (P.norm_out != nullptr && (m % L.G) == L.c) *reinterpret_cast<uint2*>(P.norm_out + (size_t)m * K + g * 4) = o;
+      if (keep_norm && (m % L.G) == L.c) *reinterpret_cast<uint2*>(P.norm_out + (size_t)m * K + g * 4) = o;
     }
     return;
   }
@@ -565,7 +579,7 @@ __device__ __forceinline__ void stage_act(const StreamParams& p, const Phase& P,
     const uint4 w8a = __ldg(reinterpret_cast<const uint4*>(P.norm_w) + (L.tid & mask8));
     const uint4 w8b = __ldg(reinterpret_cast<const uint4*>(P.norm_w) + ((L.tid + CSM_COMPUTE_THREADS) & mask8));
     const bool wide8 = (1 << sh8) > CSM_COMPUTE_THREADS;
-    const bool keep_any = P.norm_out != nullptr;
+    const bool keep_any = keep_norm;
     int jj = 0;
 #pragma unroll 4
     for (int i = L.tid; i < total8; i += CSM_COMPUTE_THREADS, ++jj) {

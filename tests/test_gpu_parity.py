@@ -217,6 +217,48 @@ def test_generate_contract(tiny):
     assert tuple(model.generate(ids, mask, max_new_frames=3, temperature=0, stop_on_all_zeros=True).shape) == (2, 3, 32)
 
 
+def test_small_and_general_kernel_families_agree(tiny, dev):
+    """An engine built for <= 2 sequences runs the SMALL kernels (decoder attention fused into o_proj, no separate
+    attention phase); one built for more runs the general kernels.  Same arithmetic in the same order: the ids and
+    the logits must be bit-identical."""
+    from csm_hf_b200.modeling import CSMModel
+    cfg, big, oracle = tiny
+    small = CSMModel(cfg, make_state_dict(cfg, seed=0, norm_jitter=0.1), device=dev, max_batch=2, max_ctx=320)
+    ids, mask = make_context(cfg, 2, 7, seed=5, text_frames=2)
+    fa = small.generate(ids, mask, max_new_frames=12, temperature=0, stop_on_all_zeros=False)
+    fb = big.generate(ids, mask, max_new_frames=12, temperature=0, stop_on_all_zeros=False)
+    assert torch.equal(fa, fb)
+    oa = small.generate_frame(ids, mask, temperature=0, return_codebook_logits=True)
+    ob = big.generate_frame(ids, mask, temperature=0, return_codebook_logits=True)
+    assert torch.equal(oa.codebook_logits.cpu(), ob.codebook_logits.cpu())
+    assert torch.equal(oa.last_hidden_state.cpu(), ob.last_hidden_state.cpu())
+
+
+@pytest.mark.parametrize("small", [False, True])
+def test_long_generate_crosses_tag_epoch(tiny, dev, small):
+    """The hand-over tags are 16 bits: a generate() longer than one tag epoch (65535 / phases-per-frame ~ 83 frames)
+    makes the engine clear its tagged buffers and restart the epoch in the middle of a run.  The result must not
+    depend on where the epoch boundary falls: two consecutive runs (different starting epochs) agree, and agree
+    with a frame-by-frame generate_frame loop."""
+    cfg, model, oracle = tiny
+    B = 3
+    if small:   # engine for <= 2 sequences: the SMALL kernel family (fused decoder attention)
+        from csm_hf_b200.modeling import CSMModel
+        model = CSMModel(cfg, make_state_dict(cfg, seed=0, norm_jitter=0.1), device=dev, max_batch=2, max_ctx=320)
+        B = 2
+    ids, mask = make_context(cfg, B, 5, seed=31)
+    a = model.generate(ids, mask, max_new_frames=100, temperature=0, stop_on_all_zeros=False)
+    b = model.generate(ids, mask, max_new_frames=100, temperature=0, stop_on_all_zeros=False)
+    assert tuple(a.shape) == (B, 100, 32) and torch.equal(a, b)
+    kv, run_ids, run_mask, frames = None, ids, mask, []
+    for _ in range(100):
+        out = model.generate_frame(run_ids, run_mask, temperature=0, past_key_values=kv)
+        kv = out.past_key_values
+        frames.append(out.samples.cpu())
+        run_ids, run_mask = next_row(frames[-1])
+    assert torch.equal(torch.stack(frames, dim=1), a)
+
+
 def test_stop_on_all_zeros(dev):
     """A model whose heads always pick id 0 stops at once and returns [B,0,32] (modeling_csm.py:662-663,698-700)."""
     from csm_hf_b200.modeling import CSMModel
