@@ -35,6 +35,8 @@ cudaError_t csm_swiglu_rows_launch(const bf16* gu, int I, bf16* act, long long r
 cudaError_t csm_add_rows_launch(bf16* h, const bf16* y, long long n, cudaStream_t st);
 cudaError_t csm_take_last_rows_launch(const bf16* h, int S, int H, uint32_t* dst, int b0, int nseq, uint32_t tag,
                                       cudaStream_t st);
+cudaError_t csm_sample_rows_launch(const bf16* logits, int rows, int V, int topk, float inv_temp, unsigned long long seed,
+                                   long long* out, cudaStream_t st);
 cudaError_t csm_untag_rows_launch(const uint32_t* src, long long src_stride, int cols, int rows, bf16* dst, cudaStream_t st);
 cudaError_t csm_i64_to_i32_launch(const long long* src, int* dst, int n, cudaStream_t st);
 cudaError_t csm_i32_to_i64_launch(const int* src, long long* dst, int n, cudaStream_t st);
@@ -94,6 +96,14 @@ struct CsmCtx {
   int* progress = nullptr;   // [sms][4], see StreamParams::progress
   int progress_on = 0;
   int bar_all = 0;           // grid barrier between all phases (CSM_BAR_ALL=1)
+  // sampling (csm_set_sampling); topk <= 1 = greedy
+  int topk = 1;
+  float inv_temp = 1.f;
+  unsigned long long rng_seed = 0;
+  unsigned int rng_frame = 0;
+  int seq_base = 0;
+  uint32_t* lgt = nullptr;
+  int lgt_stride = 0;
   // prefill workspace (lazy)
   int pf_rows = 0;
   bf16 *pf_h = nullptr, *pf_hn = nullptr, *pf_qkv = nullptr, *pf_attn = nullptr, *pf_y = nullptr, *pf_gu = nullptr,
@@ -526,6 +536,8 @@ int launch_frame(CsmCtx* ctx, int B, int ph_begin, int ph_end, const long long* 
   p.n_phases_total = (int)ctx->table.size();
   p.progress = ctx->progress_on ? ctx->progress : nullptr;
   p.abort_flag = ctx->abort_flag;
+  p.topk = ctx->topk; p.inv_temp = ctx->inv_temp; p.rng_seed = ctx->rng_seed; p.rng_frame = ctx->rng_frame;
+  p.seq_base = ctx->seq_base; p.lgt = ctx->lgt; p.lgt_stride = ctx->lgt_stride;
   p.tagbase = ctx->tagbase;
   p.l2_ahead_bytes = ctx->l2_ahead;
   p.repl = ctx->repl;
@@ -645,6 +657,7 @@ int frame_impl(CsmCtx* ctx, const long long* ids, const int* mask, int B, int S,
   }
   if (r) return r;
   end_epoch(ctx);
+  ctx->rng_frame += 1;
   ctx->cache_len += S;
   return 0;
 }
@@ -740,6 +753,9 @@ int csm_create(const CsmShapes* sh, const CsmWeights* w, int max_batch, int max_
   DA(ctx->attn_part, B * b.heads * ctx->nsplit_max * (b.hd + 2));
   DA(ctx->attn_cnt, B * b.kv);
   DA(ctx->bar_counter, 4);
+  ctx->lgt_stride = (ctx->V + 3) / 4 * 4;
+  DA(ctx->lgt, B * ctx->lgt_stride);
+  ctx->tagged.push_back({ctx->lgt, B * ctx->lgt_stride * sizeof(uint32_t)});
   DA(ctx->cand, R * ctx->sms * B);
   ctx->tagged.push_back({ctx->cand, R * ctx->sms * B * sizeof(unsigned long long)});
   for (auto& t : ctx->tagged) CK(cudaMemsetAsync(t.first, 0, t.second, st));
@@ -796,6 +812,26 @@ int csm_reset(CsmCtx* ctx) {
 }
 
 int csm_cache_len(const CsmCtx* ctx) { return ctx ? ctx->cache_len : CSM_EINVAL; }
+
+int csm_set_sampling(CsmCtx* ctx, int topk, float temperature, uint64_t seed, int seq_base) {
+  if (!ctx) return CSM_EINVAL;
+  if (topk <= 1 || temperature == 0.f) {   // greedy (the reference's spelling: topk=1)
+    ctx->topk = 1;
+    ctx->inv_temp = 1.f;
+    return CSM_OK;
+  }
+  if (!(temperature > 0.f)) return fail(ctx, CSM_EINVAL, "temperature must be >= 0 (got %g)", (double)temperature);
+  // sample_tokens keeps one 16-bit key per logit of every sequence in the activation region
+  if ((size_t)ctx->Bmax * ctx->lgt_stride * 2 > (size_t)ctx->act_region)
+    return fail(ctx, CSM_ECAPACITY, "top-k sampling of %d sequences needs %d bytes of shared memory (have %d)", ctx->Bmax,
+                ctx->Bmax * ctx->lgt_stride * 2, ctx->act_region);
+  ctx->topk = topk > ctx->V ? ctx->V : topk;
+  ctx->inv_temp = 1.f / temperature;
+  ctx->rng_seed = seed;
+  ctx->rng_frame = 0;     // frames are counted from the call that set the seed: (seed, call) reproduces its output
+  ctx->seq_base = seq_base;
+  return CSM_OK;
+}
 
 int csm_embed_sum(CsmCtx* ctx, const int64_t* ids, const int32_t* mask, int B, int S, void* out, void* stream) {
   if (!ctx || !ids || !out) return fail(ctx, CSM_EINVAL, "null argument");
@@ -1007,6 +1043,15 @@ int csm_debug_profile_frame(CsmCtx* ctx, int B, uint64_t* clocks_host, int32_t* 
       info_host[4 * i + 2] = P.stack; info_host[4 * i + 3] = P.type == PH_GEMV ? P.act_mode : -1;
     }
   return CSM_OK;
+}
+
+int csm_sample_topk(const void* logits, int rows, int V, int topk, float temperature, uint64_t seed, int64_t* out,
+                    void* stream) {
+  if (!logits || !out || rows < 0 || V < 1 || topk < 1 || !(temperature > 0.f)) return CSM_EINVAL;
+  if (rows == 0) return CSM_OK;
+  cudaError_t e = csm_sample_rows_launch((const bf16*)logits, rows, V, topk, 1.f / temperature, seed, (long long*)out,
+                                         (cudaStream_t)stream);
+  return e == cudaSuccess ? CSM_OK : CSM_ECUDA;
 }
 
 int csm_debug_progress(CsmCtx* ctx, int32_t* host_out, void* side_stream) {

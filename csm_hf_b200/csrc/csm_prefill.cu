@@ -4,6 +4,7 @@
 // mma.sync tensor cores, SwiGLU, residual add.  The projections themselves are plain GEMMs
 // (csm_api.cu: csm_gemm_bf16).
 #include "csm_common.cuh"
+#include "csm_sample.cuh"
 
 // ---------------------------------------------------------------- K1: masked 33-way gather-sum
 // out[r] = sum_slot mask[r][slot] * emb(slot, ids[r][slot])   (modeling_csm.py:261-282, 327-334)
@@ -313,8 +314,37 @@ __global__ void __launch_bounds__(128) csm_flash_prefill_kernel(const bf16* __re
   }
 }
 
+// ---------------------------------------------------------------- stand-alone top-k sampler (tests)
+// One warp per logits row, the same device code the frame kernel runs (csm_sample.cuh): row r is drawn with the
+// noise key (seed, frame 0, codebook 0, sequence r).
+__global__ void __launch_bounds__(256) csm_sample_rows_kernel(const bf16* __restrict__ logits, int rows, int V, int Vs,
+                                                              int topk, float inv_temp, unsigned long long seed,
+                                                              long long* __restrict__ out) {
+  extern __shared__ __align__(16) unsigned char smem[];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  unsigned short* keys = reinterpret_cast<unsigned short*>(smem) + (size_t)warp * Vs;
+  int* hist = reinterpret_cast<int*>(smem + (size_t)8 * Vs * 2) + warp * 256;
+  const int r = blockIdx.x * 8 + warp;
+  if (r >= rows) return;
+  const unsigned short* src = reinterpret_cast<const unsigned short*>(logits + (size_t)r * V);
+  for (int i = lane; i < V; i += 32) keys[i] = (unsigned short)bf16_sort_key(src[i]);
+  __syncwarp();
+  const int idx = warp_sample_topk(keys, V, topk < V ? topk : V, inv_temp, draw_key(seed, 0u, 0, r), lane, hist);
+  if (lane == 0) out[r] = idx;
+}
+
 // ---------------------------------------------------------------- host launchers
 extern "C" {
+
+cudaError_t csm_sample_rows_launch(const bf16* logits, int rows, int V, int topk, float inv_temp, unsigned long long seed,
+                                   long long* out, cudaStream_t st) {
+  const int Vs = (V + 3) / 4 * 4;
+  const size_t smem = (size_t)8 * Vs * 2 + 8 * 256 * sizeof(int);
+  cudaError_t e = cudaFuncSetAttribute((const void*)csm_sample_rows_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  if (e != cudaSuccess) return e;
+  csm_sample_rows_kernel<<<(rows + 7) / 8, 256, smem, st>>>(logits, rows, V, Vs, topk, inv_temp, seed, out);
+  return cudaGetLastError();
+}
 
 cudaError_t csm_embed_sum_launch(const long long* ids, const int* mask, int default_mask, const bf16* audio_emb,
                                  const bf16* text_emb, int V, int H, bf16* out, int rows, cudaStream_t st) {

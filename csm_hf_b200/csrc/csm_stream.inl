@@ -38,12 +38,15 @@
 //   * greedy sampling needs no extra synchronisation: every CTA publishes its best (logit, id) as a tagged
 //     word and the consumers reduce the 148 candidates themselves.
 //
-// This file is compiled twice (csm_stream_small.cu: engines for <= 2 sequences, nothing on the hot path that is
-// not needed there -- no hang guard, no debug hooks, no poll back-off; csm_stream_general.cu: everything else).
+// This file is compiled four times: {SMALL: engines for <= 2 sequences, nothing on the hot path that is not needed
+// there -- no hang guard, no debug hooks, no poll back-off; general: everything else} x {greedy; STOCH: stochastic
+// top-k sampling}.  Separate translation units, because the small-batch greedy kernel is bound by the instruction
+// count and register pressure of its hot path: code it never executes still costs it 10-20 % when compiled in.
 #include "csm_common.cuh"
+#include "csm_sample.cuh"
 
-#ifndef CSM_BUILD_SMALL
-#error "include this file from csm_stream_small.cu / csm_stream_general.cu"
+#if !defined(CSM_BUILD_SMALL) || !defined(CSM_BUILD_STOCH)
+#error "include this file from csm_stream_{small,general}{,_stoch}.cu"
 #endif
 
 // build-time experiment knobs (tools/gpu_variants.sh builds several libraries and times them in one GPU call)
@@ -223,6 +226,76 @@ __device__ __forceinline__ void reduce_candidates(const StreamParams& p, int war
   }
   compute_sync();
 }
+
+#if CSM_BUILD_STOCH
+// ------------------------------------------------------------------ stochastic top-k sample of a finished head phase
+// sample_topk(logits, topk, temperature) (modeling_csm.py:179-189) for codebook `cb`: every CTA polls the tagged
+// logits the head phase published, keeps them as 16-bit sort keys in shared memory (the activation region, free
+// at this point), and one warp per sequence selects the k-th largest and draws by Gumbel-max with hashed noise
+// (csm_sample.cuh) -- every CTA draws the same token.  Out of line: only stochastic runs execute it.
+__device__ __noinline__ void sample_tokens(const StreamParams& p, int cb, int head_ph) {
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31, c = blockIdx.x;
+  const int M = p.B, V = p.V, Vs = p.lgt_stride;
+  unsigned short* keys = reinterpret_cast<unsigned short*>(sm_act(p));   // [M][Vs]
+  const uint32_t tag = tg(p, head_ph);
+  const int gpr = Vs >> 2, total = M * gpr;
+  unsigned spin = 0;
+#pragma unroll 1
+  for (int i0 = tid; i0 - lane < total; i0 += 4 * CSM_COMPUTE_THREADS) {   // whole warps iterate (the poll votes)
+    uint4 w[4];
+    int mm[4], gg[4];
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const int i = i0 + j * CSM_COMPUTE_THREADS;
+      mm[j] = i / gpr;
+      gg[j] = i - mm[j] * gpr;
+    }
+    bool ok;
+    do {
+      ok = true;
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        if (i0 + j * CSM_COMPUTE_THREADS < total) {
+          w[j] = ld_tag4(p.lgt + (size_t)mm[j] * Vs + gg[j] * 4);
+          const int nv = V - gg[j] * 4;   // valid words of this group (the row is padded to a multiple of 4)
+          ok &= (w[j].x >> 16) == tag && (nv < 2 || (w[j].y >> 16) == tag) && (nv < 3 || (w[j].z >> 16) == tag) &&
+                (nv < 4 || (w[j].w >> 16) == tag);
+        }
+      }
+      if (!ok) poll_backoff(p, spin);
+      if (!ok && spin_giveup(p, spin, head_ph, W_CAND, (unsigned)i0, 1u)) ok = true;
+    } while (!__all_sync(0xffffffffu, ok));
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      if (i0 + j * CSM_COMPUTE_THREADS < total) {
+        const uint32_t k0 = bf16_sort_key(w[j].x & 0xffffu), k1 = bf16_sort_key(w[j].y & 0xffffu);
+        const uint32_t k2 = bf16_sort_key(w[j].z & 0xffffu), k3 = bf16_sort_key(w[j].w & 0xffffu);
+        *reinterpret_cast<uint2*>(keys + (size_t)mm[j] * Vs + gg[j] * 4) = make_uint2(k0 | (k1 << 16), k2 | (k3 << 16));
+      }
+    }
+  }
+  compute_sync();
+  int* hist = reinterpret_cast<int*>(sm_red(p)) + warp * 256;
+  int* tok = sm_tok();
+  const int k = p.topk < V ? p.topk : V;
+#pragma unroll 1
+  for (int m = warp; m < M; m += CSM_COMPUTE_WARPS) {
+    const int idx = warp_sample_topk(keys + (size_t)m * Vs, V, k, p.inv_temp,
+                                     draw_key(p.rng_seed, p.rng_frame, cb, p.seq_base + m), lane, hist);
+    if (lane == 0) {
+      int fedtok = idx;
+      if (p.forced) fedtok = ldcg_i32(p.fed + m * CSM_NQ + cb);
+      tok[m] = fedtok;
+      if (c == 0) {
+        p.samples[m * CSM_NQ + cb] = idx;
+        if (!p.forced) p.fed[m * CSM_NQ + cb] = idx;
+      }
+    }
+    __syncwarp();
+  }
+  compute_sync();
+}
+#endif
 
 // ------------------------------------------------------------------ decoder attention (<= 32 positions, hd 128)
 // One warp per (sequence, query head).  Lane t owns cached position t for the scores and output dims
@@ -490,7 +563,11 @@ __device__ __forceinline__ void stage_act(const StreamParams& p, const Phase& P,
     // decoder input of positions 1..31: projection(_embed_audio(codebook, token)) (modeling_csm.py:247-259,
     // 564-565) = row token + codebook*V of the pre-projected table (plain bf16, read-only).  The token is the
     // greedy sample of the previous head phase.  One CTA per sequence also starts the residual stream with it.
+#if CSM_BUILD_STOCH
+    sample_tokens(p, P.cb, P.res_ph);
+#else
     reduce_candidates(p, L.warp, L.lane, L.c, L.G, P.cb, P.res_ph);
+#endif
     const int* tok = sm_tok();
     const bf16* tab = P.act + (size_t)(P.cb * p.V) * K;
     const int ppr = 1 << (gsh - 5);
@@ -884,6 +961,7 @@ __device__ __forceinline__ bool gemv_phase(const StreamParams& p, const Phase& P
         st_tag(outw + (size_t)m * out_stride + gn, tw_pack(v0, otag));
       } else {   // EPI_HEAD
         if (P.out) P.out[(size_t)m * out_stride + gn] = __float2bfloat16_rn(v0);
+        if (CSM_BUILD_STOCH) st_tag(p.lgt + (size_t)m * p.lgt_stride + gn, tw_pack(v0, otag));   // for sample_tokens
         red[(size_t)m * rows_pad + n] = v0;   // kk = 0 plane, own element only
       }
     }
@@ -928,7 +1006,11 @@ __device__ __noinline__ void finish_phase(const StreamParams& p, int head_ph) {
   const int M = p.B;
   volatile int* sflag = sm_flag();
   compute_sync();   // (the previous phase ended without a CTA barrier)
+#if CSM_BUILD_STOCH
+  sample_tokens(p, CSM_NQ - 1, head_ph);
+#else
   reduce_candidates(p, tid >> 5, tid & 31, c, gridDim.x, CSM_NQ - 1, head_ph);
+#endif
   __threadfence_block();
   if (tid == 0) sflag[1] = 0;
   compute_sync();
@@ -1228,7 +1310,9 @@ __device__ __noinline__ void attn_bb_phase(const StreamParams& p, int layer, int
 
 }  // namespace
 
-template <int NB, int REP, bool SMALL>
+// STOCH only makes the kernel's NAME unique per translation unit: template instantiations have weak linkage, two
+// units instantiating csm_stream_kernel<1,4,true> with different bodies would be merged into one by the linker.
+template <int NB, int REP, bool SMALL, bool STOCH>
 __global__ void __launch_bounds__(CSM_THREADS, 1) csm_stream_kernel(const __grid_constant__ StreamParams p) {
   if (p.stop_flag != nullptr && *p.stop_flag) return;   // generation already ended (set by an earlier launch)
   if (CSM_GUARD && *reinterpret_cast<volatile int*>(p.abort_flag) != 0) return;   // an earlier launch timed out
@@ -1447,37 +1531,44 @@ __global__ void __launch_bounds__(CSM_THREADS, 1) csm_stream_kernel(const __grid
 // attention variant, which keeps its instruction footprint small.
 typedef void (*StreamKernel)(const StreamParams);
 
-#if CSM_BUILD_SMALL
-extern "C" cudaError_t csm_launch_stream_small(const StreamParams* p, int grid, size_t smem, cudaStream_t stream,
-                                               int cooperative) {
-  StreamKernel k;
-  switch (p->bb.heads / p->bb.kv) {
-    case 1: k = csm_stream_kernel<1, 1, true>; break;
-    case 2: k = csm_stream_kernel<1, 2, true>; break;
-    default: k = csm_stream_kernel<1, 4, true>; break;
+template <int NB, bool SMALL>
+static StreamKernel pick_rep(int rep) {
+  switch (rep) {
+    case 1: return csm_stream_kernel<NB, 1, SMALL, CSM_BUILD_STOCH != 0>;
+    case 2: return csm_stream_kernel<NB, 2, SMALL, CSM_BUILD_STOCH != 0>;
+    default: return csm_stream_kernel<NB, 4, SMALL, CSM_BUILD_STOCH != 0>;
   }
-#else
-extern "C" cudaError_t csm_launch_stream_small(const StreamParams* p, int grid, size_t smem, cudaStream_t stream,
-                                               int cooperative);
-
-static StreamKernel pick_kernel(int nb, int rep) {
-#define CSM_PICK(NBV)                                                    \
-  switch (rep) {                                                         \
-    case 1: return csm_stream_kernel<NBV, 1, false>;                     \
-    case 2: return csm_stream_kernel<NBV, 2, false>;                     \
-    default: return csm_stream_kernel<NBV, 4, false>;                    \
-  }
-  if (nb <= 1) { CSM_PICK(1) }
-  if (nb <= 2) { CSM_PICK(2) }
-  CSM_PICK(4)
-#undef CSM_PICK
 }
 
-extern "C" cudaError_t csm_launch_stream(const StreamParams* p, int grid, size_t smem, cudaStream_t stream,
-                                         int cooperative) {
-  if (p->small) return csm_launch_stream_small(p, grid, smem, stream, cooperative);
-  const int nb = (p->B + 7) / 8, rep = p->bb.heads / p->bb.kv;
-  StreamKernel k = pick_kernel(nb, rep);
+// Four launchers, one per translation unit; csm_launch_stream (greedy general unit) dispatches.
+extern "C" {
+cudaError_t csm_launch_stream_small(const StreamParams* p, int grid, size_t smem, cudaStream_t stream, int cooperative);
+cudaError_t csm_launch_stream_small_stoch(const StreamParams* p, int grid, size_t smem, cudaStream_t stream, int cooperative);
+cudaError_t csm_launch_stream_general_stoch(const StreamParams* p, int grid, size_t smem, cudaStream_t stream, int cooperative);
+}
+
+#if CSM_BUILD_SMALL && CSM_BUILD_STOCH
+#define CSM_LAUNCHER csm_launch_stream_small_stoch
+#elif CSM_BUILD_SMALL
+#define CSM_LAUNCHER csm_launch_stream_small
+#elif CSM_BUILD_STOCH
+#define CSM_LAUNCHER csm_launch_stream_general_stoch
+#else
+#define CSM_LAUNCHER csm_launch_stream
+#endif
+
+extern "C" cudaError_t CSM_LAUNCHER(const StreamParams* p, int grid, size_t smem, cudaStream_t stream, int cooperative) {
+#if !CSM_BUILD_SMALL && !CSM_BUILD_STOCH
+  if (p->small) return p->topk > 1 ? csm_launch_stream_small_stoch(p, grid, smem, stream, cooperative)
+                                   : csm_launch_stream_small(p, grid, smem, stream, cooperative);
+  if (p->topk > 1) return csm_launch_stream_general_stoch(p, grid, smem, stream, cooperative);
+#endif
+  const int rep = p->bb.heads / p->bb.kv;
+#if CSM_BUILD_SMALL
+  StreamKernel k = pick_rep<1, true>(rep);
+#else
+  const int nb = (p->B + 7) / 8;
+  StreamKernel k = nb <= 1 ? pick_rep<1, false>(rep) : (nb <= 2 ? pick_rep<2, false>(rep) : pick_rep<4, false>(rep));
 #endif
   cudaError_t e = cudaFuncSetAttribute((const void*)k, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
   if (e != cudaSuccess) return e;

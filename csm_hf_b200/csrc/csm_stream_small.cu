@@ -1,4 +1,4 @@
-// Frame kernels of engines built for <= 2 sequences (SMALL): the leanest hot path -- fused decoder attention,
-// no hang guard, no debug hooks, no poll back-off.  See csm_stream.inl.
+// Frame kernels: engines for <= 2 sequences, greedy.  See csm_stream.inl.
 #define CSM_BUILD_SMALL 1
+#define CSM_BUILD_STOCH 0
 #include "csm_stream.inl"

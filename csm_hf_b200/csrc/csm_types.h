@@ -127,6 +127,14 @@ struct StreamParams {
   int rope_bytes, act_region_bytes, red_bytes;
   unsigned long long* prof;     // debug: clock64 stamps [2 CTAs (first,last)][n_phases_total][4], see csm_stream.cu
   int n_phases_total;
+  // stochastic top-k sampling (topk <= 1: greedy).  lgt: tagged logits of the last head phase [Bmax][lgt_stride]
+  int topk;
+  float inv_temp;
+  unsigned long long rng_seed;
+  unsigned int rng_frame;       // frame counter of this context (part of the noise key)
+  int seq_base;                 // global index of sequence 0 (batch sharding: ranks draw independent noise)
+  uint32_t* lgt;
+  int lgt_stride;               // V rounded up to a multiple of 4 words
   int* abort_flag;              // [0] != 0: a wait inside a frame kernel timed out (or an earlier launch did): every wait
                                 // gives up, later launches return at once; [1..7] = (cta, phase, wait id, detail...)
   int* progress;                // debug (CSM_DEBUG_PROGRESS=1): [grid][4] = phase of the compute warps, step inside it,

@@ -62,6 +62,7 @@ def generate_sharded(model, input_ids: torch.Tensor, attention_mask: Optional[to
     B = input_ids.shape[0]
     lo, hi = shard_bounds(B, rank, world)
     if hi > lo:
+        model.seq_base = lo      # sampling noise is keyed by the global sequence index: sharding does not change a sequence's draw
         mask = attention_mask[lo:hi] if attention_mask is not None else None
         local = model.generate(input_ids[lo:hi], mask, max_new_frames=max_new_frames, temperature=temperature,
                                topk=topk, use_cache=use_cache, stop_on_all_zeros=False)

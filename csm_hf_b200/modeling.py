@@ -8,9 +8,10 @@ include/csm_b200.h).  There is no CPU or eager fallback: without the library or 
 constructor of the engine raises.
 
 Differences from the reference, all deliberate and documented in DESIGN.md:
-  * greedy only: `temperature == 0` (or the reference's own spelling, `topk == 1`) is
-    required; stochastic top-k raises NotImplementedError (SURVEY.md §8f N2);
-  * ties break to the lowest index (the reference breaks them randomly);
+  * `temperature == 0` (or the reference's own spelling, `topk == 1`) is greedy decoding with
+    ties broken to the lowest index (the reference breaks them randomly);
+  * stochastic top-k sampling draws with counter-based noise seeded from `torch.initial_seed()`
+    instead of torch's global generator: same distribution, different stream;
   * padded (left-padded) batches raise NotImplementedError (N3);
   * `past_key_values` is an opaque handle to the engine's in-place KV cache;
   * `labels` (training) raises NotImplementedError (N1).
@@ -286,12 +287,18 @@ class CSMModel:
             mask = mask.to(device=self.device, dtype=torch.int32).contiguous()
         return ids, mask
 
-    @staticmethod
-    def _require_greedy(temperature, topk):
-        if not (temperature == 0 or topk == 1):
-            raise NotImplementedError(
-                "only greedy decoding (temperature=0, or the reference's topk=1) runs on the B200 path; "
-                "stochastic top-k sampling is the next row (SURVEY.md §8f N2)")
+    def _set_sampling(self, e, temperature, topk, seq_base: int = 0):
+        """sample_topk's arguments (modeling_csm.py:179-189) -> engine sampling mode.  Greedy when
+        temperature == 0 or topk == 1; otherwise top-k + temperature sampling, reproducible for a given
+        torch.manual_seed() and call sequence."""
+        if temperature is None or topk is None or temperature < 0 or topk < 1:
+            raise ValueError(f"invalid sampling arguments temperature={temperature}, topk={topk}")
+        if temperature == 0 or topk == 1:
+            e.call(e.lib.csm_set_sampling, 1, 1.0, 0, 0)
+            return
+        self._sample_calls = getattr(self, "_sample_calls", 0) + 1
+        seed = (int(torch.initial_seed()) * 0x9E3779B97F4A7C15 + self._sample_calls) & 0xFFFFFFFFFFFFFFFF
+        e.call(e.lib.csm_set_sampling, int(topk), float(temperature), seed, int(seq_base))
 
     # ------------------------------------------------------------------ generate_frame / forward
     def generate_frame(self, input_ids, attention_mask, position_ids=None, temperature=1.0, topk=50,
@@ -299,7 +306,6 @@ class CSMModel:
                        return_dict=None, force_tokens: Optional[torch.Tensor] = None, return_codebook_logits=False):
         """modeling_csm.py:484-589.  `force_tokens` [B,32] (extension) teacher-forces the decoder;
         `return_codebook_logits` adds `.codebook_logits` [B,31,V] to the output."""
-        self._require_greedy(temperature, topk)
         if position_ids is not None:
             raise NotImplementedError("explicit position_ids are not supported (the reference passes None)")
         if output_attentions or output_hidden_states:
@@ -308,6 +314,7 @@ class CSMModel:
         ids, mask = self._prep_inputs(input_ids, attention_mask)
         B, S = ids.shape[:2]
         e = self.engine(B, 0)
+        self._set_sampling(e, temperature, topk, getattr(self, "seq_base", 0))
         if past_key_values is None:
             e.call(e.lib.csm_reset)          # a call without a cache starts a new context
         elif not isinstance(past_key_values, KVHandle) or past_key_values.model is not self:
@@ -361,12 +368,12 @@ class CSMModel:
 
         CPU inputs take the host-buffer C-ABI call (csm_generate_host: pinned H2D copy, all
         frames on the device, one D2H copy); CUDA inputs are consumed in place."""
-        self._require_greedy(temperature, topk)
         if not use_cache:
             raise NotImplementedError("use_cache=False loses the context in the reference itself (SURVEY.md fact 6)")
         ids, mask = self._prep_inputs(input_ids, attention_mask) if input_ids.device.type == "cuda" else (None, None)
         B, T = input_ids.shape[:2]
         e = self.engine(B, T + max_new_frames)
+        self._set_sampling(e, temperature, topk, getattr(self, "seq_base", 0))
         if max_new_frames <= 0:
             return torch.zeros(B, 0, 32, dtype=torch.long, device=input_ids.device)
         if input_ids.device.type == "cuda":

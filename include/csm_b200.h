@@ -133,6 +133,32 @@ int csm_last_decode_ms(CsmCtx* ctx, float* ms, int* n);
 
 const char* csm_last_error(const CsmCtx* ctx);
 
+/* Sampling mode of the following csm_generate_frame / csm_generate calls (sample_topk, modeling_csm.py:179-189).
+ * topk <= 1 or temperature == 0: greedy, lowest index on ties (the default).  Otherwise: keep the logits >= the
+ * k-th largest of logits/temperature, softmax, draw -- by Gumbel-max with counter-based noise keyed by
+ * (seed, frames generated since this call, codebook, seq_base + sequence index, vocabulary index); the reference
+ * draws from torch's global generator, so parity is distributional.  seq_base: global index of this context's
+ * sequence 0 when a batch is sharded over several contexts. */
+int csm_set_sampling(CsmCtx* ctx, int topk, float temperature, uint64_t seed, int seq_base);
+
+/* The same sampler on stand-alone rows (no context): logits [rows][V] bf16 on the device -> out[rows] int64;
+ * row r uses the noise key (seed, 0, 0, r).  Used by the distribution tests. */
+int csm_sample_topk(const void* logits, int rows, int V, int topk, float temperature, uint64_t seed, int64_t* out,
+                    void* stream);
+
+/* Sampling mode of the following csm_generate_frame / csm_generate calls (sample_topk, modeling_csm.py:179-189).
+ * topk <= 1 or temperature == 0: greedy, lowest index on ties (the default).  Otherwise: keep the logits >= the
+ * k-th largest of logits/temperature, softmax, draw -- by Gumbel-max with counter-based noise keyed by
+ * (seed, frames generated since this call, codebook, seq_base + sequence index, vocabulary index); the reference
+ * draws from torch's global generator, so parity is distributional.  seq_base: global index of this context's
+ * sequence 0 when a batch is sharded over several contexts. */
+int csm_set_sampling(CsmCtx* ctx, int topk, float temperature, uint64_t seed, int seq_base);
+
+/* The same sampler on stand-alone rows (no context): logits [rows][V] bf16 on the device -> out[rows] int64;
+ * row r uses the noise key (seed, 0, 0, r).  Used by the distribution tests. */
+int csm_sample_topk(const void* logits, int rows, int V, int topk, float temperature, uint64_t seed, int64_t* out,
+                    void* stream);
+
 /* ---- debug / test hooks: not part of the drop-in surface ------------------------------------
  * csm_debug_copy: device-to-device copy of an internal buffer (0 h_bb, 1 h_dec, 2 q_bb, 3 q_dec,
  *   4 attn_bb, 5 attn_dec, 6 mlp_bb, 7 mlp_dec, 8 last_h, 9 c0_logits, 10 cb_logits, 11 samples(i32),

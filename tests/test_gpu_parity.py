@@ -293,8 +293,10 @@ def test_argmax_ties_break_low(dev):
 def test_errors_are_loud(tiny):
     cfg, model, oracle = tiny
     ids, mask = make_context(cfg, 1, 4)
-    with pytest.raises(NotImplementedError):
-        model.generate(ids, mask, max_new_frames=2, temperature=1.0, topk=50)
+    with pytest.raises(ValueError):
+        model.generate(ids, mask, max_new_frames=2, temperature=1.0, topk=0)
+    with pytest.raises(ValueError):
+        model.generate(ids, mask, max_new_frames=2, temperature=-1.0, topk=5)
     with pytest.raises(ValueError):
         model.generate(ids, mask.float(), max_new_frames=2, temperature=0)
     with pytest.raises(NotImplementedError):
@@ -309,3 +311,87 @@ def test_errors_are_loud(tiny):
         model.generate(ids, padded, max_new_frames=2, temperature=0)
     with pytest.raises(ValueError):
         model.generate_frame(torch.zeros(40, 1, 33, dtype=torch.long), None, temperature=0)
+
+
+# ------------------------------------------------------------------ stochastic top-k sampling (sample_topk, modeling_csm.py:170-189)
+def _sample_rows(logits_bf16, topk, temperature, seed):
+    import ctypes as C
+    from csm_hf_b200 import native
+    lib = native.load()
+    rows, V = logits_bf16.shape
+    out = torch.empty(rows, dtype=torch.int64, device=logits_bf16.device)
+    rc = lib.csm_sample_topk(C.c_void_p(logits_bf16.data_ptr()), rows, V, topk, temperature, seed, C.c_void_p(out.data_ptr()),
+                             C.c_void_p(torch.cuda.current_stream().cuda_stream))
+    assert rc == 0
+    torch.cuda.synchronize()
+    return out.cpu()
+
+
+def test_topk_sampling_distribution(dev):
+    """The sampler draws from softmax(top-k(logits / T)) -- the distribution of the reference's sample_topk.
+    40 000 draws of one 2051-entry row against the exact probabilities: every draw inside the top-k set, and every
+    frequency within 5 standard deviations."""
+    g = torch.Generator().manual_seed(3)
+    V, k, T, n = 2051, 50, 0.8, 40000
+    row = (torch.randn(V, generator=g) * 2.0).to(torch.bfloat16)
+    ids = _sample_rows(row.unsqueeze(0).repeat(n, 1).contiguous().to(dev), k, T, seed=1234)
+    scaled = row.double() / T
+    kth = torch.topk(scaled, k).values[-1]
+    keep = scaled >= kth
+    probs = torch.softmax(scaled.masked_fill(~keep, float("-inf")), dim=0)
+    counts = torch.bincount(ids, minlength=V).double()
+    assert int(counts[~keep].sum()) == 0                                  # nothing outside the top-k set
+    sd = torch.sqrt(n * probs * (1 - probs)).clamp_min(1.0)
+    z = ((counts - n * probs).abs() / sd)[keep]
+    assert float(z.max()) < 5.0, float(z.max())
+    # a different seed gives different draws, the same seed the same draws
+    again = _sample_rows(row.unsqueeze(0).repeat(64, 1).contiguous().to(dev), k, T, seed=1234)
+    assert torch.equal(again, ids[:64])
+    other = _sample_rows(row.unsqueeze(0).repeat(64, 1).contiguous().to(dev), k, T, seed=99)
+    assert not torch.equal(other, ids[:64])
+
+
+def test_topk_sampling_edge_cases(dev):
+    g = torch.Generator().manual_seed(4)
+    V = 67
+    rows = (torch.randn(200, V, generator=g) * 3).to(torch.bfloat16)
+    # k = 1 returns a maximum (exact ties are all kept, like the reference, and drawn among)
+    ids = _sample_rows(rows.to(dev), 1, 1.0, 7)
+    assert torch.equal(rows.float().gather(1, ids.unsqueeze(1)).squeeze(1), rows.float().max(-1).values)
+    # ties with the k-th value are all kept (reference: `logits < kth` is what gets masked)
+    row = torch.full((V,), -5.0)
+    row[3], row[10], row[20], row[30] = 4.0, 2.0, 2.0, 2.0                # k = 2: the k-th value 2.0 appears three times
+    ids = _sample_rows(row.to(torch.bfloat16).unsqueeze(0).repeat(4000, 1).contiguous().to(dev), 2, 1.0, 5)
+    assert set(ids.tolist()) == {3, 10, 20, 30}
+    # k >= V keeps everything; a very low temperature concentrates on the maximum
+    ids = _sample_rows(rows.to(dev), 1000, 1e-3, 11)
+    assert torch.equal(rows.float().gather(1, ids.unsqueeze(1)).squeeze(1), rows.float().max(-1).values)
+
+
+def test_generate_with_topk_sampling(tiny, dev):
+    """In-kernel sampling: every sampled id lies in the top-k set of the logits the engine returns for that
+    codebook; runs are reproducible under torch.manual_seed; both kernel families draw the same tokens."""
+    from csm_hf_b200.modeling import CSMModel
+    cfg, big, oracle = tiny
+    ids, mask = make_context(cfg, 2, 6, seed=8)
+    k = 5
+
+    def run(model, seed):
+        torch.manual_seed(seed)
+        model._sample_calls = 0
+        out = model.generate_frame(ids, mask, temperature=0.7, topk=k, return_codebook_logits=True)
+        frames = model.generate(ids, mask, max_new_frames=6, temperature=0.7, topk=k, stop_on_all_zeros=False)
+        return out, frames
+
+    out, frames = run(big, 11)
+    lg = torch.cat([out.logits.unsqueeze(1), out.codebook_logits], dim=1).float().cpu()          # [B,32,V]
+    kth = torch.topk(lg, k, dim=-1).values[..., -1]
+    picked = torch.gather(lg, 2, out.samples.cpu().unsqueeze(-1)).squeeze(-1)
+    assert bool((picked >= kth).all())
+    greedy = big.generate_frame(ids, mask, temperature=0).samples.cpu()
+    assert not torch.equal(greedy, out.samples.cpu())                                            # it does sample
+    out2, frames2 = run(big, 11)
+    assert torch.equal(out2.samples.cpu(), out.samples.cpu()) and torch.equal(frames2.cpu(), frames.cpu())
+    out3, frames3 = run(big, 12)
+    assert not torch.equal(frames3.cpu(), frames.cpu())
+    assert tuple(frames.shape) == (2, 6, 32) and int(frames.min()) >= 0 and int(frames.max()) < cfg.audio_vocab_size

@@ -1,7 +1,7 @@
 #!/bin/bash
 # Parity tests + per-phase profile + decode timing over 100 frames (one gpurun call).
 mkdir -p gpurun_out
-timeout 900 python -m pytest tests -m gpu -x -q > gpurun_out/pytest_gpu.log 2>&1; echo "pytest rc=$?" >> gpurun_out/pytest_gpu.log
+timeout 300 python -m pytest tests -m gpu -x -q --timeout 90 > gpurun_out/pytest_gpu.log 2>&1; echo "pytest rc=$?" >> gpurun_out/pytest_gpu.log
 tail -4 gpurun_out/pytest_gpu.log
 for b in ${BATCHES:-1}; do
   timeout 300 python tools/ncu_target.py --batch $b --frames 100 --reps 2

@@ -3,7 +3,7 @@
 # capture of the frame kernel.  Outputs under gpurun_out/ (copied to profiles/ by hand).
 mkdir -p gpurun_out
 nvidia-smi --query-gpu=name,clocks.sm,clocks.max.sm,power.draw --format=csv > gpurun_out/smi.txt 2>&1
-timeout 900 python -m pytest tests -m gpu -x -q > gpurun_out/pytest_gpu.log 2>&1; echo "pytest rc=$?" >> gpurun_out/pytest_gpu.log
+timeout 300 python -m pytest tests -m gpu -x -q --timeout 90 > gpurun_out/pytest_gpu.log 2>&1; echo "pytest rc=$?" >> gpurun_out/pytest_gpu.log
 tail -4 gpurun_out/pytest_gpu.log
 timeout 900 python bench.py --steps 3 --warmup 3 > gpurun_out/bench_b1.json 2> gpurun_out/bench_b1.err
 cat gpurun_out/bench_b1.json
