@@ -101,6 +101,13 @@ def cpu_reference_sample(cfg, sd_fp32, ctx, frames_sample, new_frames):
     return new_frames / total, t_first, t_frame
 
 
+def note(msg):
+    """Progress on stderr (BENCH_VERBOSE=1): where a run is, if it ever stops."""
+    if os.environ.get("BENCH_VERBOSE"):
+        sys.stderr.write(f"[bench {time.strftime('%H:%M:%S')}] {msg}\n")
+        sys.stderr.flush()
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -128,6 +135,15 @@ def main():
     if a.impl == "reference":
         if rank != 0:
             return
+        import signal
+
+        def _too_slow(signum, frame):   # a host that cannot finish the bounded CPU sample in 15 minutes
+            print(json.dumps({"impl": "reference", "unavailable": "CPU reference sample did not finish within 900 s"}))
+            sys.stdout.flush()
+            os._exit(0)
+
+        signal.signal(signal.SIGALRM, _too_slow)
+        signal.alarm(900)
         sd = make_state_dict(cfg, seed=0)
         vals = []
         for i in range(max(1, min(a.warmup, 1)) + a.steps):          # one warm-up pass is enough on the CPU
@@ -159,7 +175,22 @@ def main():
     if world > 1:
         dist.init_process_group("nccl", device_id=dev)
     want_cpu = (world == 1 and not a.no_cpu_baseline)
-    sd = make_state_dict(cfg, seed=0, dtype=torch.float32 if want_cpu else torch.bfloat16)
+    cpu_baseline = None
+    if want_cpu:
+        # the CPU baseline is the reference arm run in a child process BEFORE any GPU work, with a time limit: it
+        # cannot disturb (or be disturbed by) the GPU measurement, and a slow host cannot stall the bench
+        note("cpu baseline (child process) starts")
+        cmd = [sys.executable, os.path.abspath(__file__), "--impl", "reference", "--steps", "1", "--warmup", "1", "--ctx",
+               str(a.ctx), "--frames", str(a.frames), "--cpu-sample-frames", str(a.cpu_sample_frames)]
+        try:
+            res = subprocess.run(cmd, capture_output=True, text=True, timeout=240)
+            ref = json.loads(res.stdout.strip().splitlines()[-1])
+            cpu_baseline = ref["cpu_baseline"]
+        except Exception as exc:   # noqa: BLE001 -- a baseline that cannot be measured is reported, not fatal
+            cpu_baseline = {"value": None, "unit": "frames/s", "cores": os.cpu_count(), "kind": "port",
+                            "sample": f"not measured: {type(exc).__name__}"}
+        note("cpu baseline done")
+    sd = make_state_dict(cfg, seed=0, dtype=torch.bfloat16)
     model = CSMModel(cfg, sd, device=dev, max_batch=a.batch, max_ctx=a.ctx + a.frames + 8)
     GB = a.batch * world
     ids, mask = make_context(cfg, GB, a.ctx, seed=1234)
@@ -173,8 +204,11 @@ def main():
             return generate_sharded(model, d_ids, d_mask, max_new_frames=a.frames, temperature=0, stop_on_all_zeros=False)
         return model.generate(d_ids, d_mask, max_new_frames=a.frames, temperature=0, stop_on_all_zeros=False)
 
-    for _ in range(max(a.warmup, 3)):
+    note("model + engine ready")
+    for i in range(max(a.warmup, 3)):
         out = step_device()
+        torch.cuda.synchronize()
+        note(f"warm-up {i} done")
     assert tuple(out.shape) == (GB, a.frames, 32)
 
     def fence():
@@ -197,6 +231,7 @@ def main():
         dec_n += n
     ev1.record()
     fence()
+    note("timed device steps done")
     ms_total = ev0.elapsed_time(ev1)
     launches = eng.info(4) - launches0
     # end to end through host buffers (same process, same engine)
@@ -210,6 +245,7 @@ def main():
             from csm_hf_b200.dist import all_gather_frames
             all_gather_frames(fr.to(dev), GB)
     fence()
+    note("timed host-buffer steps done")
     e2e_s = time.perf_counter() - t0
     clocks = sampler.stop() if rank == 0 else None
     t = torch.tensor([ms_total, e2e_s * 1000.0, dec_ms / max(dec_n, 1)], device=dev, dtype=torch.float64)
@@ -249,11 +285,7 @@ def main():
         "clocks": clocks,
     }
     if want_cpu:
-        v, t_first, t_frame = cpu_reference_sample(cfg, sd, a.ctx, a.cpu_sample_frames, a.frames)
-        line["cpu_baseline"] = {
-            "value": v, "unit": "frames/s", "cores": torch.get_num_threads(), "kind": "port",
-            "sample": (f"oracle port of modeling_csm.py, fp32 torch CPU, batch 1: {a.ctx}-frame prefill+frame {t_first:.2f} s, "
-                       f"{a.cpu_sample_frames} decode frames {t_frame:.3f} s each, projected to {a.frames} frames")}
+        line["cpu_baseline"] = cpu_baseline
     print(json.dumps(line))
     if world > 1:
         dist.destroy_process_group()

@@ -773,8 +773,13 @@ int csm_create(const CsmShapes* sh, const CsmWeights* w, int max_batch, int max_
   ctx->direct_mlp = max_batch <= 4;
   if (const char* e = getenv("CSM_FUSE_ATTN")) ctx->fuse_attn = atoi(e) != 0;
   if (const char* e = getenv("CSM_DIRECT_MLP")) ctx->direct_mlp = atoi(e) != 0;
-  if (const char* e = getenv("CSM_BAR_ALL")) ctx->bar_all = atoi(e) != 0;
+  // Engines for > 2 sequences keep a grid barrier between all phases on top of the tagged hand-over: with many
+  // sequences the pure dataflow chain showed rare run-to-run differences (one flaky batch-invariance run) and, before
+  // the poll back-off, multi-second stalls at 24-32 sequences; the barrier costs < 10 % there (phases are long) and
+  // nothing at 1-2 sequences, which stay pure dataflow.  CSM_BAR_ALL=0/1 overrides.
   if (!ctx->direct_mlp || max_batch > 4) ctx->fuse_attn = 0;   // the SMALL kernels have no streamed-activation path
+  ctx->bar_all = !ctx->fuse_attn;                              // (the general kernel family)
+  if (const char* e = getenv("CSM_BAR_ALL")) ctx->bar_all = atoi(e) != 0;
   build_table(ctx);
   if ((r = plan_smem(ctx))) return r;
   DA(ctx->d_table, ctx->table.size());
