@@ -131,3 +131,46 @@ def test_sharded_generate_two_ranks_gloo(tmp_path):
     outs = [p.communicate(timeout=180)[0] for p in procs]
     for p, o in zip(procs, outs):
         assert p.returncode == 0 and "ok" in o, o
+
+
+def test_ctypes_structs_match_the_header(tmp_path):
+    """The ctypes mirror of CsmLlamaShape / CsmShapes / CsmWeights has the C compiler's size and field offsets."""
+    import ctypes as C
+    from csm_hf_b200 import native
+    src = tmp_path / "layout.c"
+    src.write_text(r"""
+#include <stdio.h>
+#include <stddef.h>
+#include "csm_b200.h"
+int main(void) {
+  printf("%zu %zu %zu %zu %zu\n", sizeof(CsmLlamaShape), offsetof(CsmLlamaShape, eps), offsetof(CsmLlamaShape, rope_cos),
+         offsetof(CsmLlamaShape, rope_sin), offsetof(CsmLlamaShape, n_pos));
+  printf("%zu %zu %zu\n", sizeof(CsmShapes), offsetof(CsmShapes, backbone), offsetof(CsmShapes, decoder));
+  printf("%zu %zu %zu %zu\n", sizeof(CsmWeights), offsetof(CsmWeights, audio_head), offsetof(CsmWeights, backbone_layers),
+         offsetof(CsmWeights, decoder_layers));
+  return 0;
+}
+""")
+    exe = tmp_path / "layout"
+    subprocess.run(["gcc", "-I", os.path.join(ROOT, "include"), str(src), "-o", str(exe)], check=True)
+    out = subprocess.run([str(exe)], capture_output=True, text=True, check=True).stdout.split()
+    got = [int(x) for x in out]
+    L, S, W = native.LlamaShape, native.Shapes, native.Weights
+    want = [C.sizeof(L), L.eps.offset, L.rope_cos.offset, L.rope_sin.offset, L.n_pos.offset,
+            C.sizeof(S), S.backbone.offset, S.decoder.offset,
+            C.sizeof(W), W.audio_head.offset, W.backbone_layers.offset, W.decoder_layers.offset]
+    assert got == want
+
+
+def test_reference_arm_prints_the_contract_line():
+    """bench.py --impl reference (the oracle port timed on the host cores) at BASELINE.json configs[0] size."""
+    import json
+    res = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--impl", "reference", "--steps", "1", "--warmup", "0",
+                          "--ctx", "16", "--frames", "8", "--cpu-sample-frames", "1"], capture_output=True, text=True,
+                         timeout=600)
+    assert res.returncode == 0, res.stderr[-2000:]
+    line = json.loads(res.stdout.strip().splitlines()[-1])
+    assert line["impl"] == "reference" and line["metric"] == "audio_frames_per_s" and line["unit"] == "frames/s"
+    assert line["value"] > 0 and line["higher_is_better"] is True
+    assert line["cpu_baseline"]["kind"] == "port" and line["cpu_baseline"]["cores"] >= 1
+    assert line["e2e"]["value"] == line["value"] and line["e2e"]["h2d_bytes_per_step"] == 0
