@@ -351,6 +351,23 @@ def test_topk_sampling_distribution(dev):
     assert not torch.equal(other, ids[:64])
 
 
+def test_topk_sampling_matches_reference_histograms(dev):
+    """Histograms of the REFERENCE's own sample_topk (minted on CPU by oracle/make_golden_sampling.py from
+    /root/reference/modeling_csm.py) against the CUDA sampler on the same logits rows: same support (incl. the
+    ties with the k-th value the reference keeps) and frequencies within 5 sigma of each other."""
+    import os
+    g = torch.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "sample_topk.pt"), weights_only=False)
+    n = g["n"]
+    for name, c in g["cases"].items():
+        row = c["row"]
+        ids = _sample_rows(row.unsqueeze(0).repeat(n, 1).contiguous().to(dev), c["topk"], c["temperature"], seed=77)
+        mine = torch.bincount(ids, minlength=row.numel()).double()
+        ref = c["counts"].double()
+        assert torch.equal(mine > 0, ref > 0) or float((mine + ref)[(mine > 0) != (ref > 0)].max()) < 12, name
+        z = (mine - ref).abs() / torch.sqrt((mine + ref).clamp_min(1.0))
+        assert float(z.max()) < 5.0, (name, float(z.max()))
+
+
 def test_topk_sampling_edge_cases(dev):
     g = torch.Generator().manual_seed(4)
     V = 67
