@@ -53,3 +53,24 @@ def test_csm1b_config1_fp32_tokens():
     assert torch.equal(frames, g["frames"])
     c0 = torch.stack([t["c0_logits"] for t in tr])
     assert (c0 - g["c0_logits"]).abs().max() < 5e-5
+
+
+def test_reference_sampler_histograms_follow_topk_softmax():
+    """The reference's sample_topk (histograms minted by oracle/make_golden_sampling.py) draws from
+    softmax(logits/T restricted to the entries >= the k-th largest) -- ties with the k-th value included.
+    This is the definition the CUDA sampler implements (csm_sample.cuh)."""
+    import os
+    import torch
+    g = torch.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "sample_topk.pt"), weights_only=False)
+    n = g["n"]
+    for name, c in g["cases"].items():
+        scaled = c["row"].double() / c["temperature"]
+        kth = torch.topk(scaled, c["topk"]).values[-1]
+        keep = scaled >= kth
+        probs = torch.softmax(scaled.masked_fill(~keep, float("-inf")), dim=0)
+        counts = c["counts"].double()
+        assert int(counts[~keep].sum()) == 0, name
+        if "ties" in name:
+            assert int(keep.sum()) == c["topk"] + 2          # the k-th value appears three times: all kept
+        z = (counts - n * probs).abs() / torch.sqrt(n * probs * (1 - probs)).clamp_min(1.0)
+        assert float(z[keep].max()) < 5.0, (name, float(z[keep].max()))
