@@ -12,7 +12,7 @@ LIB = os.path.join(HERE, "libcsm_b200.so")
 
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a",
-    "-O3", "-lineinfo", "-std=c++17",
+    "-O3", "-lineinfo", "-std=c++17", "-t", "0",
     "-Xptxas=-v",
     "-Xcompiler", "-fPIC", "-shared",
 ]
