@@ -163,6 +163,10 @@ __device__ __forceinline__ void mbar_wait_g(const StreamParams& p, uint64_t* bar
   }
 }
 
+// split-KV units of a backbone attention phase: (sequence, kv-head, 128 cached positions)
+__device__ __forceinline__ int attn_bb_units(const StreamParams& p) {
+  return p.B * p.bb.kv * ((p.pos + CSM_ATT_SPLIT) / CSM_ATT_SPLIT);
+}
 __device__ __forceinline__ bool better(float v, int i, float bv, int bi) { return v > bv || (v == bv && i < bi); }
 __device__ __forceinline__ uint32_t tg(const StreamParams& p, int ph) { return (p.tagbase + (uint32_t)ph) & 0xffffu; }
 // Keep a loop-invariant value in its register: stops the optimiser from re-deriving it inside a loop.
@@ -1308,6 +1312,271 @@ __device__ __noinline__ void attn_bb_phase(const StreamParams& p, int layer, int
   }
 }
 
+#if !CSM_BUILD_SMALL
+// Many-unit form of the same phase (general kernels, once there are more than ~2 units per CTA: 8+ sequences at a
+// 2048-frame context): ONE WARP per (sequence, kv-head, 128 positions) unit and no CTA barrier inside the phase.
+// The CTA-per-unit form above spends four CTA barriers and one exposed load round trip per unit, which at 32
+// sequences (31 units per CTA, one after the other) made this phase 14x slower than its K/V bytes take to stream.
+//
+// The arithmetic is attn_bb_phase's, operation for operation, so a sequence's result does not depend on which form
+// ran (batch invariance, and the two kernel families stay bit-identical): the unit is still eight 16-position
+// chunks, each reduced to (max, sum, o[64]) on its own exactly as one warp of the CTA form does, and the eight
+// chunk results are merged in chunk order with the same expressions.  What the CTA form does in parallel over its
+// warps this form does in two passes over the chunks: pass 1 reads K, leaves exp(s - chunk max) per position and
+// (max, sum) per chunk in shared memory and finds the unit's max; pass 2 reads V and accumulates
+// exp(chunk max - unit max) * o_chunk.  K (pass 1) and V (pass 2) of the next chunk are requested before the
+// current one is used.  Out of line.
+template <int REP>
+__device__ __noinline__ void attn_bb_phase_warp(const StreamParams& p, int layer, int src_ph, int ph) {
+  constexpr int HD = 64, NCH = CSM_ATT_SPLIT / 16;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, c = blockIdx.x, G = gridDim.x;
+  const int Ttot = p.pos + 1;
+  const int nsplit = (Ttot + CSM_ATT_SPLIT - 1) / CSM_ATT_SPLIT;
+  const int nk = p.bb.kv;
+  const int nunits = p.B * nk * nsplit;
+  const int grp = lane >> 3, dl = lane & 7;   // 4 positions per load, 8 lanes x 8 dims each
+  const uint32_t qtag = tg(p, src_ph), otag = tg(p, ph);
+  const int Wq = (p.bb.heads + 2 * nk) * HD;        // tagged q | k | v row
+  // this warp's scratch (host: plan_smem reserves CSM_ATT_WARP_SCRATCH floats per compute warp in the split-K region)
+  float* s_pv = sm_red(p) + warp * CSM_ATT_WARP_SCRATCH;   // [NCH][REP][4 loads][4 positions]
+  float* s_m = s_pv + NCH * 4 * 16;                        // [NCH][REP]
+  float* s_l = s_m + NCH * 4;                              // [NCH][REP]
+  compute_sync();   // (the previous phase ended without a CTA barrier; this one reuses its shared memory)
+#pragma unroll 1
+  for (int unit = warp * G + c; unit < nunits; unit += CSM_COMPUTE_WARPS * G) {
+    const int sp = unit % nsplit;
+    const int kvh = (unit / nsplit) % nk;
+    const int b = unit / (nsplit * nk);
+    const size_t kvbase = (((size_t)layer * p.Bmax + b) * nk + kvh) * (size_t)p.Tcap * HD;
+    const bf16* Kp = p.kc_bb + kvbase + dl * 8;
+    const bf16* Vp = p.vc_bb + kvbase + dl * 8;
+    const int p0 = sp * CSM_ATT_SPLIT + grp;
+    const int nch = min(NCH, (Ttot - sp * CSM_ATT_SPLIT + 15) >> 4);   // chunks with at least one position (>= 1)
+    const uint32_t* kw = p.q_bb + (size_t)b * Wq + p.bb.heads * HD + kvh * HD + dl * 8;   // tagged K of position `pos`
+    const uint32_t* vw = kw + nk * HD;
+    uint4 cur[4], nxt[4];
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const int pj = p0 + 4 * j;
+      cur[j] = pj < p.pos ? ldcg_u4(Kp + (size_t)pj * HD) : make_uint4(0, 0, 0, 0);
+    }
+    // q slice of this lane: REP heads x 8 dims, pre-scaled (tagged words from the qkv phase)
+    float q[REP][8];
+    {
+      const uint32_t* qw = p.q_bb + (size_t)b * Wq + (kvh * REP) * HD + dl * 8;
+      uint4 qa[REP], qb[REP];
+      bool ok;
+      unsigned spin = 0;
+      do {
+        ok = true;
+#pragma unroll
+        for (int h = 0; h < REP; ++h) {
+          qa[h] = ld_tag4(qw + h * HD);
+          qb[h] = ld_tag4(qw + h * HD + 4);
+          ok &= tw_ok4(qa[h], qtag) & tw_ok4(qb[h], qtag);
+        }
+        if (!ok) poll_backoff(p, spin);
+        if (!ok && spin_giveup(p, spin, ph, W_ATTN_BB_Q, (unsigned)unit)) ok = true;
+      } while (!__all_sync(0xffffffffu, ok));
+#pragma unroll
+      for (int h = 0; h < REP; ++h) {
+        q[h][0] = tw_val(qa[h].x) * p.bb.scale; q[h][1] = tw_val(qa[h].y) * p.bb.scale;
+        q[h][2] = tw_val(qa[h].z) * p.bb.scale; q[h][3] = tw_val(qa[h].w) * p.bb.scale;
+        q[h][4] = tw_val(qb[h].x) * p.bb.scale; q[h][5] = tw_val(qb[h].y) * p.bb.scale;
+        q[h][6] = tw_val(qb[h].z) * p.bb.scale; q[h][7] = tw_val(qb[h].w) * p.bb.scale;
+      }
+    }
+    // ---- pass 1: scores of every chunk
+    float Mx[REP];
+#pragma unroll
+    for (int h = 0; h < REP; ++h) Mx[h] = -INFINITY;
+#pragma unroll 1
+    for (int w = 0; w < nch; ++w) {
+      const int pw = p0 + 16 * w;
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        const int pj = pw + 16 + 4 * j;
+        nxt[j] = (w + 1 < nch && pj < p.pos) ? ldcg_u4(Kp + (size_t)pj * HD) : make_uint4(0, 0, 0, 0);
+      }
+      // the position being processed: its K is in flight to the cache, take it from the tagged row
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        if (pw + 4 * j == p.pos) {
+          uint4 k0, k1;
+          unsigned spin = 0;
+          do {
+            k0 = ld_tag4(kw); k1 = ld_tag4(kw + 4);
+            if (spin_giveup(p, spin, ph, W_ATTN_BB_KV, (unsigned)unit)) break;
+          } while (!(tw_ok4(k0, qtag) & tw_ok4(k1, qtag)));
+          cur[j] = make_uint4(tw_pair(k0.x, k0.y), tw_pair(k0.z, k0.w), tw_pair(k1.x, k1.y), tw_pair(k1.z, k1.w));
+        }
+      }
+      __syncwarp();
+      float s[REP][4];
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        const int pj = pw + 4 * j;
+        const uint32_t* u = reinterpret_cast<const uint32_t*>(&cur[j]);
+        float kf[8];
+#pragma unroll
+        for (int i = 0; i < 4; ++i) { kf[2 * i] = bf_lo(u[i]); kf[2 * i + 1] = bf_hi(u[i]); }
+#pragma unroll
+        for (int h = 0; h < REP; ++h) {
+          float d = 0.f;
+#pragma unroll
+          for (int i = 0; i < 8; ++i) d += q[h][i] * kf[i];
+          d += __shfl_xor_sync(0xffffffffu, d, 1);
+          d += __shfl_xor_sync(0xffffffffu, d, 2);
+          d += __shfl_xor_sync(0xffffffffu, d, 4);
+          s[h][j] = (pj < Ttot) ? d : -INFINITY;
+        }
+      }
+#pragma unroll
+      for (int h = 0; h < REP; ++h) {
+        float m = fmaxf(fmaxf(s[h][0], s[h][1]), fmaxf(s[h][2], s[h][3]));
+        m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, 8));
+        m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, 16));
+        float l = 0.f;
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          float pv = (m == -INFINITY) ? 0.f : __expf(s[h][j] - m);
+          s[h][j] = pv;
+          l += pv;
+        }
+        l += __shfl_xor_sync(0xffffffffu, l, 8);
+        l += __shfl_xor_sync(0xffffffffu, l, 16);
+        Mx[h] = fmaxf(Mx[h], m);
+        if (dl == 0) {
+#pragma unroll
+          for (int j = 0; j < 4; ++j) s_pv[((w * 4 + h) * 4 + j) * 4 + grp] = s[h][j];
+          if (grp == 0) { s_m[w * 4 + h] = m; s_l[w * 4 + h] = l; }
+        }
+      }
+#pragma unroll
+      for (int j = 0; j < 4; ++j) cur[j] = nxt[j];
+    }
+    __syncwarp();
+    // ---- pass 2: P.V of every chunk, merged in chunk order
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const int pj = p0 + 4 * j;
+      cur[j] = pj < p.pos ? ldcg_u4(Vp + (size_t)pj * HD) : make_uint4(0, 0, 0, 0);
+    }
+    float Ls[REP], O[REP][8];
+#pragma unroll
+    for (int h = 0; h < REP; ++h) {
+      Ls[h] = 0.f;
+#pragma unroll
+      for (int i = 0; i < 8; ++i) O[h][i] = 0.f;
+    }
+#pragma unroll 1
+    for (int w = 0; w < nch; ++w) {
+      const int pw = p0 + 16 * w;
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        const int pj = pw + 16 + 4 * j;
+        nxt[j] = (w + 1 < nch && pj < p.pos) ? ldcg_u4(Vp + (size_t)pj * HD) : make_uint4(0, 0, 0, 0);
+      }
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        if (pw + 4 * j == p.pos) {
+          uint4 v0, v1;
+          unsigned spin = 0;
+          do {
+            v0 = ld_tag4(vw); v1 = ld_tag4(vw + 4);
+            if (spin_giveup(p, spin, ph, W_ATTN_BB_KV, (unsigned)unit)) break;
+          } while (!(tw_ok4(v0, qtag) & tw_ok4(v1, qtag)));
+          cur[j] = make_uint4(tw_pair(v0.x, v0.y), tw_pair(v0.z, v0.w), tw_pair(v1.x, v1.y), tw_pair(v1.z, v1.w));
+        }
+      }
+      __syncwarp();
+      float o[REP][8];
+#pragma unroll
+      for (int h = 0; h < REP; ++h)
+#pragma unroll
+        for (int i = 0; i < 8; ++i) o[h][i] = 0.f;
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        const uint32_t* u = reinterpret_cast<const uint32_t*>(&cur[j]);
+        float vf[8];
+#pragma unroll
+        for (int i = 0; i < 4; ++i) { vf[2 * i] = bf_lo(u[i]); vf[2 * i + 1] = bf_hi(u[i]); }
+#pragma unroll
+        for (int h = 0; h < REP; ++h) {
+          const float pv = s_pv[((w * 4 + h) * 4 + j) * 4 + grp];
+#pragma unroll
+          for (int i = 0; i < 8; ++i) o[h][i] += pv * vf[i];
+        }
+      }
+#pragma unroll
+      for (int h = 0; h < REP; ++h) {
+        const float mw = s_m[w * 4 + h];
+        const float f = (mw == -INFINITY) ? 0.f : __expf(mw - Mx[h]);
+        Ls[h] += f * s_l[w * 4 + h];
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+          float v = o[h][i];
+          v += __shfl_xor_sync(0xffffffffu, v, 8);
+          v += __shfl_xor_sync(0xffffffffu, v, 16);
+          O[h][i] += f * v;
+        }
+      }
+#pragma unroll
+      for (int j = 0; j < 4; ++j) cur[j] = nxt[j];
+    }
+    if (nch < NCH) {   // (the CTA form adds 0 * 0 for chunks past the end: -0 + 0 = +0)
+#pragma unroll
+      for (int h = 0; h < REP; ++h)
+#pragma unroll
+        for (int i = 0; i < 8; ++i) O[h][i] += 0.f;
+    }
+    // partial (max, sum, o[64]) of this unit: head h is written by the lanes of position group h % 4
+#pragma unroll
+    for (int h = 0; h < REP; ++h) {
+      if ((h & 3) == grp) {
+        float* part = p.attn_part + (((size_t)b * p.bb.heads + kvh * REP + h) * p.nsplit_max + sp) * (HD + 2);
+#pragma unroll
+        for (int i = 0; i < 8; ++i) part[2 + dl * 8 + i] = O[h][i];
+        if (dl == 0) { part[0] = Mx[h]; part[1] = Ls[h]; }
+      }
+    }
+    __threadfence();
+    __syncwarp();
+    int last = 0;
+    if (lane == 0) last = atomicAdd(p.attn_cnt + b * nk + kvh, 1u) == (unsigned)nsplit - 1u;
+    last = __shfl_sync(0xffffffffu, last, 0);
+    if (last) {
+      // last unit of this (sequence, kv-head): merge the splits and publish the head outputs
+      __threadfence();
+#pragma unroll
+      for (int h = 0; h < REP; ++h) {
+        if ((h & 3) == grp) {
+          const float* part = p.attn_part + (((size_t)b * p.bb.heads + kvh * REP + h) * p.nsplit_max) * (HD + 2);
+          float M2 = -INFINITY;
+          for (int s2 = 0; s2 < nsplit; ++s2) M2 = fmaxf(M2, ldcg_f32(part + (size_t)s2 * (HD + 2)));
+          float L2 = 0.f, O2[8];
+#pragma unroll
+          for (int i = 0; i < 8; ++i) O2[i] = 0.f;
+          for (int s2 = 0; s2 < nsplit; ++s2) {
+            const float* ps = part + (size_t)s2 * (HD + 2);
+            const float f = __expf(ldcg_f32(ps) - M2);
+            L2 += f * ldcg_f32(ps + 1);
+#pragma unroll
+            for (int i = 0; i < 8; ++i) O2[i] += f * ldcg_f32(ps + 2 + dl * 8 + i);
+          }
+          uint32_t* o = p.attn_bb + (size_t)b * (p.bb.heads * HD) + (kvh * REP + h) * HD + dl * 8;
+          st_tag4(o, tw_pack(O2[0] / L2, otag), tw_pack(O2[1] / L2, otag), tw_pack(O2[2] / L2, otag), tw_pack(O2[3] / L2, otag));
+          st_tag4(o + 4, tw_pack(O2[4] / L2, otag), tw_pack(O2[5] / L2, otag), tw_pack(O2[6] / L2, otag),
+                  tw_pack(O2[7] / L2, otag));
+        }
+      }
+      if (lane == 0) p.attn_cnt[b * nk + kvh] = 0u;
+    }
+    __syncwarp();
+  }
+}
+#endif
+
 }  // namespace
 
 // STOCH only makes the kernel's NAME unique per translation unit: template instantiations have weak linkage, two
@@ -1441,7 +1710,9 @@ __global__ void __launch_bounds__(CSM_THREADS, 1) csm_stream_kernel(const __grid
           const int nsplit = (Ttot + CSM_ATT_SPLIT - 1) / CSM_ATT_SPLIT;
           const int nunits = p.B * nk * nsplit;
           int done = 0;
-          for (int unit = L.c; unit < nunits && done < 4; unit += L.G, ++done) {
+          // (warp-per-unit form: the first round of this CTA's eight warps are units c, G + c, ... as well)
+          const int maxdone = (!SMALL && nunits > p.attn_warp_units) ? CSM_COMPUTE_WARPS : 4;
+          for (int unit = L.c; unit < nunits && done < maxdone; unit += L.G, ++done) {
             const int sp = unit % nsplit, kvh = (unit / nsplit) % nk, b = unit / (nsplit * nk);
             const size_t off = ((((size_t)P.layer * p.Bmax + b) * nk + kvh) * (size_t)p.Tcap + (size_t)sp * CSM_ATT_SPLIT) * 64;
             const int npos = min(CSM_ATT_SPLIT, p.pos - sp * CSM_ATT_SPLIT);   // cached positions only
@@ -1500,7 +1771,13 @@ __global__ void __launch_bounds__(CSM_THREADS, 1) csm_stream_kernel(const __grid
     bool published = false;
     if (type == PH_GEMV) published = gemv_phase<NB, SMALL>(p, P, L, nxt, fetch);
     else if (!SMALL && type == PH_ATTN_DEC) attn_dec_phase(p, P, L);
-    else if (type == PH_ATTN_BB) attn_bb_phase<REP>(p, P.layer, P.src_ph, ph);
+    else if (type == PH_ATTN_BB) {
+#if !CSM_BUILD_SMALL
+      if (attn_bb_units(p) > p.attn_warp_units) attn_bb_phase_warp<REP>(p, P.layer, P.src_ph, ph);
+      else
+#endif
+        attn_bb_phase<REP>(p, P.layer, P.src_ph, ph);
+    }
     else if (type == PH_EMBED) embed_phase(p, ph);
     else finish_phase(p, P.res_ph);
     if (prof) prof[2] = clock64();       // this thread's share of the body done

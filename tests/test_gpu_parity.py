@@ -234,6 +234,38 @@ def test_small_and_general_kernel_families_agree(tiny, dev):
     assert torch.equal(oa.last_hidden_state.cpu(), ob.last_hidden_state.cpu())
 
 
+@pytest.mark.parametrize("rep,grid", [(2, None), (2, "4"), (4, None), (4, "5")])
+def test_backbone_attention_warp_form_is_bit_identical(dev, monkeypatch, rep, grid):
+    """The general kernels run the backbone decode attention one CTA per split-KV unit while there are few units and
+    one WARP per unit once there are many (8+ sequences at a 2048-frame context).  Both forms do the same arithmetic
+    in the same order, so forcing one or the other (CSM_ATTN_WARP_UNITS, read at engine creation) must not change a
+    bit: ids, codebook logits and hidden state, over a context of three split-KV units, with 2 and 4 query heads per
+    kv head, and on a small grid where a warp owns several units in turn."""
+    from csm_hf_b200.config import LlamaDims
+    from csm_hf_b200.modeling import CSMModel
+    cfg = tiny_config()
+    if rep == 4:
+        cfg = tiny_config(backbone_config=LlamaDims(hidden_size=512, intermediate_size=512, num_hidden_layers=2,
+                                                    num_attention_heads=8, num_key_value_heads=2))
+    sd = make_state_dict(cfg, seed=3, norm_jitter=0.1)
+    ids, mask = make_context(cfg, 8, 300, seed=21, text_frames=3)   # 8 x 2 kv-heads x 3 splits = 48 units
+    if grid is not None:                                            # 4-5 CTAs = 32-40 warps: some warps take two units
+        monkeypatch.setenv("CSM_GRID", grid)
+    res = []
+    for units in ("0", "1000000"):   # always one warp per unit / never
+        monkeypatch.setenv("CSM_ATTN_WARP_UNITS", units)
+        model = CSMModel(cfg, sd, device=dev, max_batch=8, max_ctx=320)
+        frames = model.generate(ids, mask, max_new_frames=6, temperature=0, stop_on_all_zeros=False).cpu()
+        out = model.generate_frame(ids, mask, temperature=0, return_codebook_logits=True)
+        out2 = model.generate_frame(*next_row(out.samples.cpu()), temperature=0, past_key_values=out.past_key_values,
+                                    return_codebook_logits=True)
+        res.append((frames, out2.samples.cpu(), out2.codebook_logits.cpu(), out2.logits.cpu(), out2.last_hidden_state.cpu()))
+        model._drop_engine()
+    assert tuple(res[0][0].shape) == (8, 6, 32)
+    for a, b in zip(*res):
+        assert torch.equal(a, b)
+
+
 @pytest.mark.parametrize("small", [False, True])
 def test_long_generate_crosses_tag_epoch(tiny, dev, small):
     """The hand-over tags are 16 bits: a generate() longer than one tag epoch (65535 / phases-per-frame ~ 83 frames)
