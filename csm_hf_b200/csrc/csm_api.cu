@@ -96,7 +96,6 @@ struct CsmCtx {
   int* progress = nullptr;   // [sms][4], see StreamParams::progress
   int progress_on = 0;
   int bar_all = 0;           // grid barrier between all phases (CSM_BAR_ALL=1)
-  int attn_warp_units = 0;   // StreamParams::attn_warp_units (default 2 x grid; CSM_ATTN_WARP_UNITS overrides)
   // sampling (csm_set_sampling); topk <= 1 = greedy
   int topk = 1;
   float inv_temp = 1.f;
@@ -399,8 +398,6 @@ int plan_smem(CsmCtx* ctx) {
   ctx->rope_bytes = (ctx->rope_bytes + 255) / 256 * 256;
   // split-K partial sums: red[ks][m_alloc][mtiles*16+4] floats; attention scratch needs 9216 bytes
   int red = 9216;
-  // (general kernels: per-warp scratch of the warp-per-unit backbone attention)
-  if (!ctx->fuse_attn && red < CSM_COMPUTE_WARPS * CSM_ATT_WARP_SCRATCH * 4) red = CSM_COMPUTE_WARPS * CSM_ATT_WARP_SCRATCH * 4;
   for (Phase& P : ctx->table) {
     if (P.type != PH_GEMV) continue;
     const int U = P.N / P.gran;
@@ -546,7 +543,6 @@ int launch_frame(CsmCtx* ctx, int B, int ph_begin, int ph_end, const long long* 
   p.repl = ctx->repl;
   p.evict_first = ctx->evict_first;
   p.small = ctx->fuse_attn;
-  p.attn_warp_units = ctx->attn_warp_units;
   if (!ctx->stepped) {
     p.phase_begin = ph_begin; p.phase_end = ph_end; p.use_barrier = 1;
     CK(cudaMemsetAsync(ctx->bar_counter, 0, sizeof(unsigned int), st));
@@ -753,7 +749,7 @@ int csm_create(const CsmShapes* sh, const CsmWeights* w, int max_batch, int max_
                  {ctx->attn_bb, R * B * b.heads * b.hd * 4}, {ctx->attn_dec, R * B * d.heads * d.hd * 4},
                  {ctx->mlp_bb, R * B * b.I * 4}, {ctx->mlp_dec, R * B * d.I * 4}};
   DA(ctx->last_h, B * b.H); DA(ctx->c0_logits, B * ctx->V); DA(ctx->cb_logits, B * (CSM_NQ - 1) * ctx->V);
-  ctx->nsplit_max = (max_ctx + CSM_ATT_SPLIT - 1) / CSM_ATT_SPLIT;
+  ctx->nsplit_max = (max_ctx + CSM_ATT_SPLIT_MMA - 1) / CSM_ATT_SPLIT_MMA;   // (sized for the smaller unit of the two kernel families)
   DA(ctx->attn_part, B * b.heads * ctx->nsplit_max * (b.hd + 2));
   DA(ctx->attn_cnt, B * b.kv);
   DA(ctx->bar_counter, 4);
@@ -784,10 +780,6 @@ int csm_create(const CsmShapes* sh, const CsmWeights* w, int max_batch, int max_
   if (!ctx->direct_mlp || max_batch > 4) ctx->fuse_attn = 0;   // the SMALL kernels have no streamed-activation path
   ctx->bar_all = !ctx->fuse_attn;                              // (the general kernel family)
   if (const char* e = getenv("CSM_BAR_ALL")) ctx->bar_all = atoi(e) != 0;
-  // backbone decode attention: one CTA per split-KV unit while every CTA has at most two of them (lowest latency),
-  // one warp per unit beyond that (csm_stream.inl: attn_bb_phase_warp; general kernels only, same results)
-  ctx->attn_warp_units = 2 * ctx->G;
-  if (const char* e = getenv("CSM_ATTN_WARP_UNITS")) ctx->attn_warp_units = atoi(e);
   build_table(ctx);
   if ((r = plan_smem(ctx))) return r;
   DA(ctx->d_table, ctx->table.size());

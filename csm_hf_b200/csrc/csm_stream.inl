@@ -50,6 +50,15 @@
 #endif
 
 // build-time experiment knobs (tools/gpu_variants.sh builds several libraries and times them in one GPU call)
+#ifndef CSM_ATT_INLINE
+#define CSM_ATT_INLINE __noinline__
+#endif
+#ifndef CSM_ATT_KBUF
+#define CSM_ATT_KBUF 2   // K / V chunks in flight per warp in the tensor-core backbone attention (register budget)
+#endif
+#ifndef CSM_ATT_VBUF
+#define CSM_ATT_VBUF 2
+#endif
 #ifndef CSM_MMA_UNROLL
 #define CSM_MMA_UNROLL 4
 #endif
@@ -163,10 +172,6 @@ __device__ __forceinline__ void mbar_wait_g(const StreamParams& p, uint64_t* bar
   }
 }
 
-// split-KV units of a backbone attention phase: (sequence, kv-head, 128 cached positions)
-__device__ __forceinline__ int attn_bb_units(const StreamParams& p) {
-  return p.B * p.bb.kv * ((p.pos + CSM_ATT_SPLIT) / CSM_ATT_SPLIT);
-}
 __device__ __forceinline__ bool better(float v, int i, float bv, int bi) { return v > bv || (v == bv && i < bi); }
 __device__ __forceinline__ uint32_t tg(const StreamParams& p, int ph) { return (p.tagbase + (uint32_t)ph) & 0xffffu; }
 // Keep a loop-invariant value in its register: stops the optimiser from re-deriving it inside a loop.
@@ -1313,232 +1318,263 @@ __device__ __noinline__ void attn_bb_phase(const StreamParams& p, int layer, int
 }
 
 #if !CSM_BUILD_SMALL
-// Many-unit form of the same phase (general kernels, once there are more than ~2 units per CTA: 8+ sequences at a
-// 2048-frame context): ONE WARP per (sequence, kv-head, 128 positions) unit and no CTA barrier inside the phase.
-// The CTA-per-unit form above spends four CTA barriers and one exposed load round trip per unit, which at 32
-// sequences (31 units per CTA, one after the other) made this phase 14x slower than its K/V bytes take to stream.
+// Tensor-core form of the same phase (all general kernels): ONE WARP per (sequence, kv-head, 128 positions) unit, no
+// CTA barrier inside the phase, Q.K^T and P.V on mma.sync.m16n8k16.  The scalar form above costs ~1400 instructions
+// per 16 positions (fp32 dot products spread over 8 lanes, butterfly reductions); at 8-32 sequences that made this
+// phase instruction-bound, 14x slower than its K/V bytes take to stream (profiles/r01_phase_profile_b32_v9.txt).
 //
-// The arithmetic is attn_bb_phase's, operation for operation, so a sequence's result does not depend on which form
-// ran (batch invariance, and the two kernel families stay bit-identical): the unit is still eight 16-position
-// chunks, each reduced to (max, sum, o[64]) on its own exactly as one warp of the CTA form does, and the eight
-// chunk results are merged in chunk order with the same expressions.  What the CTA form does in parallel over its
-// warps this form does in two passes over the chunks: pass 1 reads K, leaves exp(s - chunk max) per position and
-// (max, sum) per chunk in shared memory and finds the unit's max; pass 2 reads V and accumulates
-// exp(chunk max - unit max) * o_chunk.  K (pass 1) and V (pass 2) of the next chunk are requested before the
-// current one is used.  Out of line.
+//   S = Q K^T : A = the REP query heads of the group (rows >= REP are zero), B = 8 cached positions per n-tile, k = the
+//               64 head dims in 4 steps.  The k index of an MMA is a free permutation as long as A and B agree: lane
+//               (g, t) supplies dims 8t..8t+7 and 32+8t..32+8t+7, i.e. two 16-byte loads per K row, and the four
+//               lanes of a row read 64 contiguous bytes per load instruction.
+//   softmax   : the scores of the whole unit (8 chunks x 2 n-tiles x 2) stay in registers; max and sum over the unit
+//               in fp32 (sdpa_attention_forward computes its softmax in fp32), no online rescaling.
+//   O = P V   : the S accumulator fragments of a chunk are the A fragment of P (positions as k).  P is split into
+//               bf16 hi + lo parts (two MMAs), which keeps ~16 mantissa bits of the fp32 probabilities.  B = V with the
+//               output dims permuted (column g of n-tile j is dim 8g + j), so that lane (g, t) reads V as one 16-byte
+//               load per position and builds the fragments with byte permutes.
+// The unit's partial (max, sum, o[64]) and the last-arriver merge over the splits are those of the scalar form.
+// A sequence's result does not depend on the batch it is in (same unit decomposition, same arithmetic).  Out of line.
 template <int REP>
-__device__ __noinline__ void attn_bb_phase_warp(const StreamParams& p, int layer, int src_ph, int ph) {
-  constexpr int HD = 64, NCH = CSM_ATT_SPLIT / 16;
+__device__ CSM_ATT_INLINE void attn_bb_phase_mma(const StreamParams& p, int layer, int src_ph, int ph) {
+  constexpr int HD = 64, SPLIT = CSM_ATT_SPLIT_MMA, NCH = SPLIT / 16;
+  static_assert(REP <= 8, "query heads per kv head");
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, c = blockIdx.x, G = gridDim.x;
   const int Ttot = p.pos + 1;
-  const int nsplit = (Ttot + CSM_ATT_SPLIT - 1) / CSM_ATT_SPLIT;
+  const int nsplit = (Ttot + SPLIT - 1) / SPLIT;
   const int nk = p.bb.kv;
   const int nunits = p.B * nk * nsplit;
-  const int grp = lane >> 3, dl = lane & 7;   // 4 positions per load, 8 lanes x 8 dims each
+  const int g = lane >> 2, t = lane & 3;        // MMA fragment coordinates
+  const int grp = lane >> 3, dl = lane & 7;     // merge coordinates: head grp, dims 8*dl..
   const uint32_t qtag = tg(p, src_ph), otag = tg(p, ph);
-  const int Wq = (p.bb.heads + 2 * nk) * HD;        // tagged q | k | v row
-  // this warp's scratch (host: plan_smem reserves CSM_ATT_WARP_SCRATCH floats per compute warp in the split-K region)
-  float* s_pv = sm_red(p) + warp * CSM_ATT_WARP_SCRATCH;   // [NCH][REP][4 loads][4 positions]
-  float* s_m = s_pv + NCH * 4 * 16;                        // [NCH][REP]
-  float* s_l = s_m + NCH * 4;                              // [NCH][REP]
-  compute_sync();   // (the previous phase ended without a CTA barrier; this one reuses its shared memory)
+  const int Wq = (p.bb.heads + 2 * nk) * HD;    // tagged q | k | v row
+  const float scale = p.bb.scale;
+  compute_sync();   // (the previous phase ended without a CTA barrier)
 #pragma unroll 1
   for (int unit = warp * G + c; unit < nunits; unit += CSM_COMPUTE_WARPS * G) {
     const int sp = unit % nsplit;
     const int kvh = (unit / nsplit) % nk;
     const int b = unit / (nsplit * nk);
     const size_t kvbase = (((size_t)layer * p.Bmax + b) * nk + kvh) * (size_t)p.Tcap * HD;
-    const bf16* Kp = p.kc_bb + kvbase + dl * 8;
-    const bf16* Vp = p.vc_bb + kvbase + dl * 8;
-    const int p0 = sp * CSM_ATT_SPLIT + grp;
-    const int nch = min(NCH, (Ttot - sp * CSM_ATT_SPLIT + 15) >> 4);   // chunks with at least one position (>= 1)
-    const uint32_t* kw = p.q_bb + (size_t)b * Wq + p.bb.heads * HD + kvh * HD + dl * 8;   // tagged K of position `pos`
+    const bf16* Kp = p.kc_bb + kvbase;
+    const bf16* Vp = p.vc_bb + kvbase;
+    const int p0 = sp * SPLIT;
+    const int nch = min(NCH, (Ttot - p0 + 15) >> 4);   // chunks with at least one position (>= 1)
+    const uint32_t* kw = p.q_bb + (size_t)b * Wq + p.bb.heads * HD + kvh * HD;   // tagged K / V of position `pos`
     const uint32_t* vw = kw + nk * HD;
-    uint4 cur[4], nxt[4];
-#pragma unroll
-    for (int j = 0; j < 4; ++j) {
-      const int pj = p0 + 4 * j;
-      cur[j] = pj < p.pos ? ldcg_u4(Kp + (size_t)pj * HD) : make_uint4(0, 0, 0, 0);
+    if (lane == 0) {   // HBM -> L2: this unit's V (read in the second pass) and the next unit of this warp
+      {
+        const int npos = min(SPLIT, p.pos - p0);
+        if (npos > 0) bulk_prefetch_l2(Vp + (size_t)p0 * HD, (uint32_t)npos * 128u);
+      }
+      const int nu = unit + CSM_COMPUTE_WARPS * G;
+      if (nu < nunits) {
+        const int sp2 = nu % nsplit, kvh2 = (nu / nsplit) % nk, b2 = nu / (nsplit * nk);
+        const size_t off = ((((size_t)layer * p.Bmax + b2) * nk + kvh2) * (size_t)p.Tcap + (size_t)sp2 * SPLIT) * HD;
+        const int npos = min(SPLIT, p.pos - sp2 * SPLIT);   // cached positions only
+        if (npos > 0) {
+          bulk_prefetch_l2(p.kc_bb + off, (uint32_t)npos * 128u);
+          bulk_prefetch_l2(p.vc_bb + off, (uint32_t)npos * 128u);
+        }
+      }
     }
-    // q slice of this lane: REP heads x 8 dims, pre-scaled (tagged words from the qkv phase)
-    float q[REP][8];
+    // K rows of a chunk for this lane: positions pc + g and pc + 8 + g (j = 0, 1), dims 8t.. (words 0-3) and 32+8t..
+    // (words 4-7).  Plain word arrays with compile-time indices only (everything below is fully unrolled): an array
+    // of uint4 read through pointer casts stayed in local memory, and a spilled load result is a wait for that load.
+    uint32_t kq[CSM_ATT_KBUF][16];   // chunks in flight: the unit is latency-bound, not instruction-bound
+#define CSM_LOAD_K(bf, ch)                                                                          \
+    do {                                                                                              \
+      _Pragma("unroll") for (int j = 0; j < 2; ++j) {                                                 \
+        const int pj = p0 + 16 * (ch) + 8 * j + g;                                                    \
+        uint4 x0 = make_uint4(0, 0, 0, 0), x1 = make_uint4(0, 0, 0, 0);                               \
+        if (pj < p.pos) {                                                                             \
+          x0 = ldcg_u4(Kp + (size_t)pj * HD + 8 * t);                                                 \
+          x1 = ldcg_u4(Kp + (size_t)pj * HD + 32 + 8 * t);                                            \
+        }                                                                                             \
+        kq[bf][8 * j + 0] = x0.x; kq[bf][8 * j + 1] = x0.y; kq[bf][8 * j + 2] = x0.z; kq[bf][8 * j + 3] = x0.w; \
+        kq[bf][8 * j + 4] = x1.x; kq[bf][8 * j + 5] = x1.y; kq[bf][8 * j + 6] = x1.z; kq[bf][8 * j + 7] = x1.w; \
+      }                                                                                               \
+    } while (0)
+    // Q fragment: head g (rows >= REP are zero), this lane's 16 dims as 8 packed pairs (tagged words from the qkv phase)
+    uint32_t qf[8];
     {
-      const uint32_t* qw = p.q_bb + (size_t)b * Wq + (kvh * REP) * HD + dl * 8;
-      uint4 qa[REP], qb[REP];
+      const uint32_t* qw = p.q_bb + (size_t)b * Wq + (kvh * REP + (g < REP ? g : 0)) * HD;
+      uint4 q0, q1, q2, q3;
       bool ok;
       unsigned spin = 0;
       do {
-        ok = true;
-#pragma unroll
-        for (int h = 0; h < REP; ++h) {
-          qa[h] = ld_tag4(qw + h * HD);
-          qb[h] = ld_tag4(qw + h * HD + 4);
-          ok &= tw_ok4(qa[h], qtag) & tw_ok4(qb[h], qtag);
-        }
+        q0 = ld_tag4(qw + 8 * t); q1 = ld_tag4(qw + 8 * t + 4);
+        q2 = ld_tag4(qw + 32 + 8 * t); q3 = ld_tag4(qw + 32 + 8 * t + 4);
+        ok = tw_ok4(q0, qtag) & tw_ok4(q1, qtag) & tw_ok4(q2, qtag) & tw_ok4(q3, qtag);
         if (!ok) poll_backoff(p, spin);
         if (!ok && spin_giveup(p, spin, ph, W_ATTN_BB_Q, (unsigned)unit)) ok = true;
       } while (!__all_sync(0xffffffffu, ok));
+      qf[0] = tw_pair(q0.x, q0.y); qf[1] = tw_pair(q0.z, q0.w); qf[2] = tw_pair(q1.x, q1.y); qf[3] = tw_pair(q1.z, q1.w);
+      qf[4] = tw_pair(q2.x, q2.y); qf[5] = tw_pair(q2.z, q2.w); qf[6] = tw_pair(q3.x, q3.y); qf[7] = tw_pair(q3.z, q3.w);
+      if (g >= REP) {
 #pragma unroll
-      for (int h = 0; h < REP; ++h) {
-        q[h][0] = tw_val(qa[h].x) * p.bb.scale; q[h][1] = tw_val(qa[h].y) * p.bb.scale;
-        q[h][2] = tw_val(qa[h].z) * p.bb.scale; q[h][3] = tw_val(qa[h].w) * p.bb.scale;
-        q[h][4] = tw_val(qb[h].x) * p.bb.scale; q[h][5] = tw_val(qb[h].y) * p.bb.scale;
-        q[h][6] = tw_val(qb[h].z) * p.bb.scale; q[h][7] = tw_val(qb[h].w) * p.bb.scale;
+        for (int i = 0; i < 8; ++i) qf[i] = 0u;
       }
     }
-    // ---- pass 1: scores of every chunk
-    float Mx[REP];
+    // The position being processed (`pos`, in the last split only): its K / V are still in flight to the cache, so the
+    // chunks below cover the CACHED positions (< pos) and `pos` is one extra score / one extra P.V step taken from the
+    // tagged row after each pass -- nothing of it is live inside the loops (register budget of this out-of-line
+    // function: ~100; a load result that gets spilled is a wait for that load).
+    const bool has_cur = p.pos >= p0 && p.pos < p0 + SPLIT;   // (warp-uniform)
+    CSM_LOAD_K(0, 0);
 #pragma unroll
-    for (int h = 0; h < REP; ++h) Mx[h] = -INFINITY;
-#pragma unroll 1
-    for (int w = 0; w < nch; ++w) {
-      const int pw = p0 + 16 * w;
+    for (int a = 1; a < CSM_ATT_KBUF - 1; ++a)
+      if (a < nch) CSM_LOAD_K(a, a);
+    // ---- S = Q K^T for the whole unit; s[ch][j][e]: head g, position p0 + 16 ch + 8 j + 2 t + e
+    float s[NCH][2][2];
 #pragma unroll
-      for (int j = 0; j < 4; ++j) {
-        const int pj = pw + 16 + 4 * j;
-        nxt[j] = (w + 1 < nch && pj < p.pos) ? ldcg_u4(Kp + (size_t)pj * HD) : make_uint4(0, 0, 0, 0);
-      }
-      // the position being processed: its K is in flight to the cache, take it from the tagged row
+    for (int ch = 0; ch < NCH; ++ch) {
+      if (ch + CSM_ATT_KBUF - 1 < nch) CSM_LOAD_K((ch + CSM_ATT_KBUF - 1) % CSM_ATT_KBUF, ch + CSM_ATT_KBUF - 1);
+      if (ch < nch) {
 #pragma unroll
-      for (int j = 0; j < 4; ++j) {
-        if (pw + 4 * j == p.pos) {
-          uint4 k0, k1;
-          unsigned spin = 0;
-          do {
-            k0 = ld_tag4(kw); k1 = ld_tag4(kw + 4);
-            if (spin_giveup(p, spin, ph, W_ATTN_BB_KV, (unsigned)unit)) break;
-          } while (!(tw_ok4(k0, qtag) & tw_ok4(k1, qtag)));
-          cur[j] = make_uint4(tw_pair(k0.x, k0.y), tw_pair(k0.z, k0.w), tw_pair(k1.x, k1.y), tw_pair(k1.z, k1.w));
+        for (int j = 0; j < 2; ++j) {
+          float acc[4] = {0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+          for (int i = 0; i < 4; ++i) {
+            const uint32_t a[4] = {qf[2 * i], 0u, qf[2 * i + 1], 0u};
+            mma16816(acc, a, kq[ch % CSM_ATT_KBUF][8 * j + 2 * i], kq[ch % CSM_ATT_KBUF][8 * j + 2 * i + 1]);
+          }
+          const int pj = p0 + 16 * ch + 8 * j + 2 * t;
+          s[ch][j][0] = (pj < p.pos) ? acc[0] * scale : -INFINITY;
+          s[ch][j][1] = (pj + 1 < p.pos) ? acc[1] * scale : -INFINITY;
         }
+      } else {
+        s[ch][0][0] = s[ch][0][1] = s[ch][1][0] = s[ch][1][1] = -INFINITY;
       }
-      __syncwarp();
-      float s[REP][4];
-#pragma unroll
-      for (int j = 0; j < 4; ++j) {
-        const int pj = pw + 4 * j;
-        const uint32_t* u = reinterpret_cast<const uint32_t*>(&cur[j]);
-        float kf[8];
-#pragma unroll
-        for (int i = 0; i < 4; ++i) { kf[2 * i] = bf_lo(u[i]); kf[2 * i + 1] = bf_hi(u[i]); }
-#pragma unroll
-        for (int h = 0; h < REP; ++h) {
-          float d = 0.f;
-#pragma unroll
-          for (int i = 0; i < 8; ++i) d += q[h][i] * kf[i];
-          d += __shfl_xor_sync(0xffffffffu, d, 1);
-          d += __shfl_xor_sync(0xffffffffu, d, 2);
-          d += __shfl_xor_sync(0xffffffffu, d, 4);
-          s[h][j] = (pj < Ttot) ? d : -INFINITY;
-        }
-      }
-#pragma unroll
-      for (int h = 0; h < REP; ++h) {
-        float m = fmaxf(fmaxf(s[h][0], s[h][1]), fmaxf(s[h][2], s[h][3]));
-        m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, 8));
-        m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, 16));
-        float l = 0.f;
-#pragma unroll
-        for (int j = 0; j < 4; ++j) {
-          float pv = (m == -INFINITY) ? 0.f : __expf(s[h][j] - m);
-          s[h][j] = pv;
-          l += pv;
-        }
-        l += __shfl_xor_sync(0xffffffffu, l, 8);
-        l += __shfl_xor_sync(0xffffffffu, l, 16);
-        Mx[h] = fmaxf(Mx[h], m);
-        if (dl == 0) {
-#pragma unroll
-          for (int j = 0; j < 4; ++j) s_pv[((w * 4 + h) * 4 + j) * 4 + grp] = s[h][j];
-          if (grp == 0) { s_m[w * 4 + h] = m; s_l[w * 4 + h] = l; }
-        }
-      }
-#pragma unroll
-      for (int j = 0; j < 4; ++j) cur[j] = nxt[j];
     }
-    __syncwarp();
-    // ---- pass 2: P.V of every chunk, merged in chunk order
+#undef CSM_LOAD_K
+    // score of `pos`: one more n-tile whose column 0 is the tagged K row (lanes g == 0 supply it), valid in c0 of t == 0
+    float s_cur = -INFINITY;
+    if (has_cur) {
+      uint4 a0, a1, a2, a3;
+      bool ok;
+      unsigned spin = 0;
+      do {
+        a0 = ld_tag4(kw + 8 * t); a1 = ld_tag4(kw + 8 * t + 4);
+        a2 = ld_tag4(kw + 32 + 8 * t); a3 = ld_tag4(kw + 32 + 8 * t + 4);
+        ok = tw_ok4(a0, qtag) & tw_ok4(a1, qtag) & tw_ok4(a2, qtag) & tw_ok4(a3, qtag);
+        if (!ok) poll_backoff(p, spin);
+        if (!ok && spin_giveup(p, spin, ph, W_ATTN_BB_KV, (unsigned)unit)) ok = true;
+      } while (!__all_sync(0xffffffffu, ok));
+      uint32_t kc[8] = {tw_pair(a0.x, a0.y), tw_pair(a0.z, a0.w), tw_pair(a1.x, a1.y), tw_pair(a1.z, a1.w),
+                        tw_pair(a2.x, a2.y), tw_pair(a2.z, a2.w), tw_pair(a3.x, a3.y), tw_pair(a3.z, a3.w)};
+      if (g != 0) {
 #pragma unroll
-    for (int j = 0; j < 4; ++j) {
-      const int pj = p0 + 4 * j;
-      cur[j] = pj < p.pos ? ldcg_u4(Vp + (size_t)pj * HD) : make_uint4(0, 0, 0, 0);
-    }
-    float Ls[REP], O[REP][8];
-#pragma unroll
-    for (int h = 0; h < REP; ++h) {
-      Ls[h] = 0.f;
-#pragma unroll
-      for (int i = 0; i < 8; ++i) O[h][i] = 0.f;
-    }
-#pragma unroll 1
-    for (int w = 0; w < nch; ++w) {
-      const int pw = p0 + 16 * w;
-#pragma unroll
-      for (int j = 0; j < 4; ++j) {
-        const int pj = pw + 16 + 4 * j;
-        nxt[j] = (w + 1 < nch && pj < p.pos) ? ldcg_u4(Vp + (size_t)pj * HD) : make_uint4(0, 0, 0, 0);
+        for (int i = 0; i < 8; ++i) kc[i] = 0u;
       }
+      float acc[4] = {0.f, 0.f, 0.f, 0.f};
 #pragma unroll
-      for (int j = 0; j < 4; ++j) {
-        if (pw + 4 * j == p.pos) {
-          uint4 v0, v1;
-          unsigned spin = 0;
-          do {
-            v0 = ld_tag4(vw); v1 = ld_tag4(vw + 4);
-            if (spin_giveup(p, spin, ph, W_ATTN_BB_KV, (unsigned)unit)) break;
-          } while (!(tw_ok4(v0, qtag) & tw_ok4(v1, qtag)));
-          cur[j] = make_uint4(tw_pair(v0.x, v0.y), tw_pair(v0.z, v0.w), tw_pair(v1.x, v1.y), tw_pair(v1.z, v1.w));
+      for (int i = 0; i < 4; ++i) {
+        const uint32_t a[4] = {qf[2 * i], 0u, qf[2 * i + 1], 0u};
+        mma16816(acc, a, kc[2 * i], kc[2 * i + 1]);
+      }
+      if (t == 0) s_cur = acc[0] * scale;
+    }
+    // ---- softmax over the unit (fp32): lanes t = 0..3 of a row share a head
+    float mx = s_cur;
+#pragma unroll
+    for (int ch = 0; ch < NCH; ++ch) mx = fmaxf(mx, fmaxf(fmaxf(s[ch][0][0], s[ch][0][1]), fmaxf(s[ch][1][0], s[ch][1][1])));
+    mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, 1));
+    mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, 2));
+    float ls = 0.f;
+#pragma unroll
+    for (int ch = 0; ch < NCH; ++ch)
+#pragma unroll
+      for (int j = 0; j < 2; ++j)
+#pragma unroll
+        for (int e = 0; e < 2; ++e) {
+          const float pv = __expf(s[ch][j][e] - mx);   // (every unit holds at least one position: mx is finite)
+          s[ch][j][e] = pv;
+          ls += pv;
+        }
+    const float p_cur = __expf(s_cur - mx);   // (0 unless this lane holds the score of `pos`)
+    ls += p_cur;
+    ls += __shfl_xor_sync(0xffffffffu, ls, 1);
+    ls += __shfl_xor_sync(0xffffffffu, ls, 2);
+    // ---- O = P V; o[jn][e]: head g, dim 8 (2 t + e) + jn
+    float o[8][4];
+#pragma unroll
+    for (int jn = 0; jn < 8; ++jn) o[jn][0] = o[jn][1] = o[jn][2] = o[jn][3] = 0.f;
+    // V rows of a chunk for this lane: positions pc + {2t, 2t+1, 2t+8, 2t+9} (j = 0..3), dims 8g..8g+7 (4 words)
+    uint32_t vq[CSM_ATT_VBUF][16];   // chunks in flight (the unit's V was prefetched into L2 when the unit started)
+#define CSM_LOAD_V(bf, ch)                                                                           \
+    do {                                                                                              \
+      _Pragma("unroll") for (int j = 0; j < 4; ++j) {                                                 \
+        const int pj = p0 + 16 * (ch) + 2 * t + (j & 1) + 8 * (j >> 1);                               \
+        uint4 x = make_uint4(0, 0, 0, 0);                                                             \
+        if (pj < p.pos) x = ldcg_u4(Vp + (size_t)pj * HD + 8 * g);                                    \
+        vq[bf][4 * j + 0] = x.x; vq[bf][4 * j + 1] = x.y; vq[bf][4 * j + 2] = x.z; vq[bf][4 * j + 3] = x.w; \
+      }                                                                                               \
+    } while (0)
+    CSM_LOAD_V(0, 0);
+#pragma unroll
+    for (int a = 1; a < CSM_ATT_VBUF - 1; ++a)
+      if (a < nch) CSM_LOAD_V(a, a);
+#pragma unroll
+    for (int ch = 0; ch < NCH; ++ch) {
+      if (ch + CSM_ATT_VBUF - 1 < nch) CSM_LOAD_V((ch + CSM_ATT_VBUF - 1) % CSM_ATT_VBUF, ch + CSM_ATT_VBUF - 1);
+      if (ch < nch) {
+        // A fragments of P: (a0, a2) = positions (2t, 2t+1), (2t+8, 2t+9); bf16 hi + lo parts
+        const float h00 = bfround(s[ch][0][0]), h01 = bfround(s[ch][0][1]), h10 = bfround(s[ch][1][0]), h11 = bfround(s[ch][1][1]);
+        const uint32_t ahi[4] = {pack_bf16(h00, h01), 0u, pack_bf16(h10, h11), 0u};
+        const uint32_t alo[4] = {pack_bf16(s[ch][0][0] - h00, s[ch][0][1] - h01), 0u,
+                                 pack_bf16(s[ch][1][0] - h10, s[ch][1][1] - h11), 0u};
+#pragma unroll
+        for (int wd = 0; wd < 4; ++wd) {   // word wd of the four rows = dims 8g + 2 wd, +1
+          const uint32_t w0 = vq[ch % CSM_ATT_VBUF][0 + wd];    // position 2t
+          const uint32_t w1 = vq[ch % CSM_ATT_VBUF][4 + wd];    // 2t+1
+          const uint32_t w2 = vq[ch % CSM_ATT_VBUF][8 + wd];    // 2t+8
+          const uint32_t w3 = vq[ch % CSM_ATT_VBUF][12 + wd];   // 2t+9
+#pragma unroll
+          for (int e = 0; e < 2; ++e) {
+            const int jn = 2 * wd + e;
+            const uint32_t sel = e ? 0x7632u : 0x5410u;
+            const uint32_t b0 = __byte_perm(w0, w1, sel);
+            const uint32_t b1 = __byte_perm(w2, w3, sel);
+            mma16816(o[jn], ahi, b0, b1);
+            mma16816(o[jn], alo, b0, b1);
+          }
         }
       }
-      __syncwarp();
-      float o[REP][8];
-#pragma unroll
-      for (int h = 0; h < REP; ++h)
-#pragma unroll
-        for (int i = 0; i < 8; ++i) o[h][i] = 0.f;
-#pragma unroll
-      for (int j = 0; j < 4; ++j) {
-        const uint32_t* u = reinterpret_cast<const uint32_t*>(&cur[j]);
-        float vf[8];
-#pragma unroll
-        for (int i = 0; i < 4; ++i) { vf[2 * i] = bf_lo(u[i]); vf[2 * i + 1] = bf_hi(u[i]); }
-#pragma unroll
-        for (int h = 0; h < REP; ++h) {
-          const float pv = s_pv[((w * 4 + h) * 4 + j) * 4 + grp];
-#pragma unroll
-          for (int i = 0; i < 8; ++i) o[h][i] += pv * vf[i];
-        }
-      }
-#pragma unroll
-      for (int h = 0; h < REP; ++h) {
-        const float mw = s_m[w * 4 + h];
-        const float f = (mw == -INFINITY) ? 0.f : __expf(mw - Mx[h]);
-        Ls[h] += f * s_l[w * 4 + h];
-#pragma unroll
-        for (int i = 0; i < 8; ++i) {
-          float v = o[h][i];
-          v += __shfl_xor_sync(0xffffffffu, v, 8);
-          v += __shfl_xor_sync(0xffffffffu, v, 16);
-          O[h][i] += f * v;
-        }
-      }
-#pragma unroll
-      for (int j = 0; j < 4; ++j) cur[j] = nxt[j];
     }
-    if (nch < NCH) {   // (the CTA form adds 0 * 0 for chunks past the end: -0 + 0 = +0)
+#undef CSM_LOAD_V
+    // P.V of `pos`: k slot 0 of one more step -- A holds p_cur in lanes t == 0, B the tagged V row in lanes t == 0
+    if (has_cur) {
+      uint4 b0, b1;
+      bool ok;
+      unsigned spin = 0;
+      do {
+        b0 = ld_tag4(vw + 8 * g); b1 = ld_tag4(vw + 8 * g + 4);
+        ok = tw_ok4(b0, qtag) & tw_ok4(b1, qtag);
+        if (!ok) poll_backoff(p, spin);
+        if (!ok && spin_giveup(p, spin, ph, W_ATTN_BB_KV, (unsigned)unit)) ok = true;
+      } while (!__all_sync(0xffffffffu, ok));
+      uint32_t vc[4] = {tw_pair(b0.x, b0.y), tw_pair(b0.z, b0.w), tw_pair(b1.x, b1.y), tw_pair(b1.z, b1.w)};
+      if (t != 0) vc[0] = vc[1] = vc[2] = vc[3] = 0u;
+      const float hc = bfround(p_cur);
+      const uint32_t ahi[4] = {pack_bf16(hc, 0.f), 0u, 0u, 0u};
+      const uint32_t alo[4] = {pack_bf16(p_cur - hc, 0.f), 0u, 0u, 0u};
 #pragma unroll
-      for (int h = 0; h < REP; ++h)
-#pragma unroll
-        for (int i = 0; i < 8; ++i) O[h][i] += 0.f;
-    }
-    // partial (max, sum, o[64]) of this unit: head h is written by the lanes of position group h % 4
-#pragma unroll
-    for (int h = 0; h < REP; ++h) {
-      if ((h & 3) == grp) {
-        float* part = p.attn_part + (((size_t)b * p.bb.heads + kvh * REP + h) * p.nsplit_max + sp) * (HD + 2);
-#pragma unroll
-        for (int i = 0; i < 8; ++i) part[2 + dl * 8 + i] = O[h][i];
-        if (dl == 0) { part[0] = Mx[h]; part[1] = Ls[h]; }
+      for (int jn = 0; jn < 8; ++jn) {
+        const uint32_t bb0 = (vc[jn >> 1] >> (16 * (jn & 1))) & 0xffffu;   // dim 8g + jn of `pos` in k slot 0
+        mma16816(o[jn], ahi, bb0, 0u);
+        mma16816(o[jn], alo, bb0, 0u);
       }
+    }
+    // partial (max, sum, o[64]) of this unit: lane (g < REP, t) holds dims 16t..16t+7 (e = 0) and 16t+8.. (e = 1)
+    if (g < REP) {
+      float* part = p.attn_part + (((size_t)b * p.bb.heads + kvh * REP + g) * p.nsplit_max + sp) * (HD + 2);
+#pragma unroll
+      for (int jn = 0; jn < 8; ++jn) {
+        part[2 + 16 * t + jn] = o[jn][0];
+        part[2 + 16 * t + 8 + jn] = o[jn][1];
+      }
+      if (t == 0) { part[0] = mx; part[1] = ls; }
     }
     __threadfence();
     __syncwarp();
@@ -1549,14 +1585,18 @@ __device__ __noinline__ void attn_bb_phase_warp(const StreamParams& p, int layer
       // last unit of this (sequence, kv-head): merge the splits and publish the head outputs
       __threadfence();
 #pragma unroll
-      for (int h = 0; h < REP; ++h) {
-        if ((h & 3) == grp) {
+      for (int h0 = 0; h0 < REP; h0 += 4) {
+        const int h = h0 + grp;
+        if (h < REP) {
           const float* part = p.attn_part + (((size_t)b * p.bb.heads + kvh * REP + h) * p.nsplit_max) * (HD + 2);
+          // (the loads of several splits are independent: unrolled so that they are in flight together)
           float M2 = -INFINITY;
+#pragma unroll 6
           for (int s2 = 0; s2 < nsplit; ++s2) M2 = fmaxf(M2, ldcg_f32(part + (size_t)s2 * (HD + 2)));
           float L2 = 0.f, O2[8];
 #pragma unroll
           for (int i = 0; i < 8; ++i) O2[i] = 0.f;
+#pragma unroll 3
           for (int s2 = 0; s2 < nsplit; ++s2) {
             const float* ps = part + (size_t)s2 * (HD + 2);
             const float f = __expf(ldcg_f32(ps) - M2);
@@ -1564,9 +1604,9 @@ __device__ __noinline__ void attn_bb_phase_warp(const StreamParams& p, int layer
 #pragma unroll
             for (int i = 0; i < 8; ++i) O2[i] += f * ldcg_f32(ps + 2 + dl * 8 + i);
           }
-          uint32_t* o = p.attn_bb + (size_t)b * (p.bb.heads * HD) + (kvh * REP + h) * HD + dl * 8;
-          st_tag4(o, tw_pack(O2[0] / L2, otag), tw_pack(O2[1] / L2, otag), tw_pack(O2[2] / L2, otag), tw_pack(O2[3] / L2, otag));
-          st_tag4(o + 4, tw_pack(O2[4] / L2, otag), tw_pack(O2[5] / L2, otag), tw_pack(O2[6] / L2, otag),
+          uint32_t* od = p.attn_bb + (size_t)b * (p.bb.heads * HD) + (kvh * REP + h) * HD + dl * 8;
+          st_tag4(od, tw_pack(O2[0] / L2, otag), tw_pack(O2[1] / L2, otag), tw_pack(O2[2] / L2, otag), tw_pack(O2[3] / L2, otag));
+          st_tag4(od + 4, tw_pack(O2[4] / L2, otag), tw_pack(O2[5] / L2, otag), tw_pack(O2[6] / L2, otag),
                   tw_pack(O2[7] / L2, otag));
         }
       }
@@ -1707,15 +1747,17 @@ __global__ void __launch_bounds__(CSM_THREADS, 1) csm_stream_kernel(const __grid
         const Phase& P = p.phases[ph];
         if (P.type == PH_ATTN_BB) {
           const int Ttot = p.pos + 1, nk = p.bb.kv;
-          const int nsplit = (Ttot + CSM_ATT_SPLIT - 1) / CSM_ATT_SPLIT;
+          constexpr int CSM_ATT_SPLIT_K = SMALL ? CSM_ATT_SPLIT : CSM_ATT_SPLIT_MMA;   // positions per unit of this kernel family
+          const int nsplit = (Ttot + CSM_ATT_SPLIT_K - 1) / CSM_ATT_SPLIT_K;
           const int nunits = p.B * nk * nsplit;
           int done = 0;
-          // (warp-per-unit form: the first round of this CTA's eight warps are units c, G + c, ... as well)
-          const int maxdone = (!SMALL && nunits > p.attn_warp_units) ? CSM_COMPUTE_WARPS : 4;
+          // (general kernels: one warp per unit, the first round of this CTA's eight warps are units c, G + c, ...
+          // as well; later rounds are prefetched by the warps themselves)
+          const int maxdone = SMALL ? 4 : CSM_COMPUTE_WARPS;
           for (int unit = L.c; unit < nunits && done < maxdone; unit += L.G, ++done) {
             const int sp = unit % nsplit, kvh = (unit / nsplit) % nk, b = unit / (nsplit * nk);
-            const size_t off = ((((size_t)P.layer * p.Bmax + b) * nk + kvh) * (size_t)p.Tcap + (size_t)sp * CSM_ATT_SPLIT) * 64;
-            const int npos = min(CSM_ATT_SPLIT, p.pos - sp * CSM_ATT_SPLIT);   // cached positions only
+            const size_t off = ((((size_t)P.layer * p.Bmax + b) * nk + kvh) * (size_t)p.Tcap + (size_t)sp * CSM_ATT_SPLIT_K) * 64;
+            const int npos = min(CSM_ATT_SPLIT_K, p.pos - sp * CSM_ATT_SPLIT_K);   // cached positions only
             if (npos > 0) {
               bulk_prefetch_l2(p.kc_bb + off, (uint32_t)npos * 128u);
               bulk_prefetch_l2(p.vc_bb + off, (uint32_t)npos * 128u);
@@ -1772,11 +1814,11 @@ __global__ void __launch_bounds__(CSM_THREADS, 1) csm_stream_kernel(const __grid
     if (type == PH_GEMV) published = gemv_phase<NB, SMALL>(p, P, L, nxt, fetch);
     else if (!SMALL && type == PH_ATTN_DEC) attn_dec_phase(p, P, L);
     else if (type == PH_ATTN_BB) {
-#if !CSM_BUILD_SMALL
-      if (attn_bb_units(p) > p.attn_warp_units) attn_bb_phase_warp<REP>(p, P.layer, P.src_ph, ph);
-      else
+#if CSM_BUILD_SMALL
+      attn_bb_phase<REP>(p, P.layer, P.src_ph, ph);
+#else
+      attn_bb_phase_mma<REP>(p, P.layer, P.src_ph, ph);
 #endif
-        attn_bb_phase<REP>(p, P.layer, P.src_ph, ph);
     }
     else if (type == PH_EMBED) embed_phase(p, ph);
     else finish_phase(p, P.res_ph);

@@ -12,9 +12,8 @@ typedef __nv_bfloat16 bf16;
 #define CSM_MAX_SLOTS 8
 #define CSM_NQ 32            // codebooks per frame (modeling_csm.py:66)
 #define CSM_DEC_POS 32       // decoder positions per frame: last_h + 31 codebook embeddings
-#define CSM_ATT_SPLIT 128    // backbone positions per split-KV unit
-#define CSM_ATT_WARP_SCRATCH 576   // floats of shared memory per compute warp for the warp-per-unit backbone attention:
-                                   // exp(s - max) of 128 positions x 4 query heads + (max, sum) of 8 chunks x 4 heads
+#define CSM_ATT_SPLIT 128    // backbone positions per split-KV unit (SMALL kernels: one CTA per unit, 8 warps x 16)
+#define CSM_ATT_SPLIT_MMA 128 // ... of the general kernels (one warp per unit on tensor cores; the scores of a unit stay in registers)
 #define CSM_MAX_ROWS 256     // at most 16 m-tiles of 16 weight rows per CTA per matrix
 #define CSM_SM_HDR_BYTES 4096   // mbarriers, phase-descriptor slots, 2 KB scratch, token slots
 
@@ -95,8 +94,6 @@ struct StreamParams {
                                 // over repl x more L2 lines, so no line is hammered by all 148 CTAs at once
   int evict_first;              // weight bulk copies carry an L2 evict-first hint
   int small;                    // engine built for <= 2 sequences (fused decoder attention): selects the SMALL kernels
-  int attn_warp_units;          // general kernels: backbone attention phases with more split-KV units than this run one
-                                // warp per unit instead of one CTA per unit (same arithmetic, bit-identical results)
   int l2_ahead_bytes;           // how far (bytes of this CTA's weight stream) the L2 prefetcher runs ahead of the ring
   int B;                        // sequences in this call
   int pos;                      // backbone position of the token being processed (= cached length)

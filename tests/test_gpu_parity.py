@@ -218,31 +218,39 @@ def test_generate_contract(tiny):
 
 
 def test_small_and_general_kernel_families_agree(tiny, dev):
-    """An engine built for <= 2 sequences runs the SMALL kernels (decoder attention fused into o_proj, no separate
-    attention phase); one built for more runs the general kernels.  Same arithmetic in the same order: the ids and
-    the logits must be bit-identical."""
+    """An engine built for <= 2 sequences runs the SMALL kernels (decoder attention fused into o_proj, scalar fp32
+    backbone attention spread over all CTAs); one built for more runs the general kernels (separate attention
+    phases, backbone attention on tensor cores with P split into bf16 hi + lo parts).  Everything else is the same
+    arithmetic in the same order, so teacher-forced with the same ids the two agree to accumulation-order accuracy:
+    logits within 2 % of their range over six frames (a one-ulp difference in a bf16 hidden state is amplified by the
+    layers that follow; measured 0.9 %), ids identical wherever the margin decides them."""
     from csm_hf_b200.modeling import CSMModel
     cfg, big, oracle = tiny
     small = CSMModel(cfg, make_state_dict(cfg, seed=0, norm_jitter=0.1), device=dev, max_batch=2, max_ctx=320)
-    ids, mask = make_context(cfg, 2, 7, seed=5, text_frames=2)
-    fa = small.generate(ids, mask, max_new_frames=12, temperature=0, stop_on_all_zeros=False)
-    fb = big.generate(ids, mask, max_new_frames=12, temperature=0, stop_on_all_zeros=False)
-    assert torch.equal(fa, fb)
-    oa = small.generate_frame(ids, mask, temperature=0, return_codebook_logits=True)
-    ob = big.generate_frame(ids, mask, temperature=0, return_codebook_logits=True)
-    assert torch.equal(oa.codebook_logits.cpu(), ob.codebook_logits.cpu())
-    assert torch.equal(oa.last_hidden_state.cpu(), ob.last_hidden_state.cpu())
+    ids, mask = make_context(cfg, 2, 150, seed=5, text_frames=2)   # two split-KV units
+    frames = small.generate(ids, mask, max_new_frames=6, temperature=0, stop_on_all_zeros=False).cpu()
+    oa = teacher_forced(small, ids, mask, frames)
+    ob = teacher_forced(big, ids, mask, frames)
+    rel = 0.02
+    for f, (a, b) in enumerate(zip(oa, ob)):
+        assert torch.equal(a.samples.cpu(), frames[:, f])
+        assert_logits_close(b.last_hidden_state.cpu(), a.last_hidden_state.cpu(), rel, f"last_h f{f}")
+        assert_logits_close(b.logits.cpu(), a.logits.cpu(), rel, f"c0 f{f}")
+        assert_logits_close(b.codebook_logits.cpu(), a.codebook_logits.cpu(), rel, f"cb f{f}")
+        logits = torch.cat([a.logits.cpu().unsqueeze(1), a.codebook_logits.cpu()], dim=1)
+        tol = rel * float(logits.float().abs().max())
+        assert_tokens_match_where_decided(b.samples.cpu(), a.samples.cpu(), logits, tol, f"ids f{f}")
 
 
-@pytest.mark.parametrize("rep,grid", [(2, None), (2, "4"), (4, None), (4, "5")])
-def test_backbone_attention_warp_form_is_bit_identical(dev, monkeypatch, rep, grid):
-    """The general kernels run the backbone decode attention one CTA per split-KV unit while there are few units and
-    one WARP per unit once there are many (8+ sequences at a 2048-frame context).  Both forms do the same arithmetic
-    in the same order, so forcing one or the other (CSM_ATTN_WARP_UNITS, read at engine creation) must not change a
-    bit: ids, codebook logits and hidden state, over a context of three split-KV units, with 2 and 4 query heads per
-    kv head, and on a small grid where a warp owns several units in turn."""
+@pytest.mark.parametrize("rep,grid", [(2, "4"), (4, None), (4, "5")])
+def test_backbone_attention_tensor_core_form_vs_oracle(dev, monkeypatch, rep, grid):
+    """The general kernels (engines for > 2 sequences) run the backbone decode attention on tensor cores, one warp per
+    (sequence, kv-head, 128 positions) unit.  Against the oracle over a context of three units, with 2 and 4 query
+    heads per kv head, 8 sequences, and on a small grid (CSM_GRID, read at engine creation) where a warp owns several
+    units in turn and prefetches its next one."""
     from csm_hf_b200.config import LlamaDims
     from csm_hf_b200.modeling import CSMModel
+    from oracle.csm_oracle import CSMOracle
     cfg = tiny_config()
     if rep == 4:
         cfg = tiny_config(backbone_config=LlamaDims(hidden_size=512, intermediate_size=512, num_hidden_layers=2,
@@ -251,19 +259,19 @@ def test_backbone_attention_warp_form_is_bit_identical(dev, monkeypatch, rep, gr
     ids, mask = make_context(cfg, 8, 300, seed=21, text_frames=3)   # 8 x 2 kv-heads x 3 splits = 48 units
     if grid is not None:                                            # 4-5 CTAs = 32-40 warps: some warps take two units
         monkeypatch.setenv("CSM_GRID", grid)
-    res = []
-    for units in ("0", "1000000"):   # always one warp per unit / never
-        monkeypatch.setenv("CSM_ATTN_WARP_UNITS", units)
-        model = CSMModel(cfg, sd, device=dev, max_batch=8, max_ctx=320)
-        frames = model.generate(ids, mask, max_new_frames=6, temperature=0, stop_on_all_zeros=False).cpu()
-        out = model.generate_frame(ids, mask, temperature=0, return_codebook_logits=True)
-        out2 = model.generate_frame(*next_row(out.samples.cpu()), temperature=0, past_key_values=out.past_key_values,
-                                    return_codebook_logits=True)
-        res.append((frames, out2.samples.cpu(), out2.codebook_logits.cpu(), out2.logits.cpu(), out2.last_hidden_state.cpu()))
-        model._drop_engine()
-    assert tuple(res[0][0].shape) == (8, 6, 32)
-    for a, b in zip(*res):
-        assert torch.equal(a, b)
+    model = CSMModel(cfg, sd, device=dev, max_batch=8, max_ctx=320)
+    tr = []
+    want = CSMOracle(cfg, sd, torch.bfloat16).generate(ids, mask, 3, traces=tr)
+    outs = teacher_forced(model, ids, mask, want)
+    for f, out in enumerate(outs):
+        assert_logits_close(out.last_hidden_state.cpu(), tr[f]["last_h"], 0.03, f"last_h f{f}")
+        assert_logits_close(out.logits.cpu(), tr[f]["c0_logits"], 0.03, f"c0 f{f}")
+        assert_logits_close(out.codebook_logits.cpu(), tr[f]["cb_logits"], 0.03, f"cb f{f}")
+    # and a sequence's result does not depend on the rest of the batch (same units, same arithmetic)
+    full = model.generate(ids, mask, max_new_frames=4, temperature=0, stop_on_all_zeros=False).cpu()
+    part = model.generate(ids[2:5], mask[2:5], max_new_frames=4, temperature=0, stop_on_all_zeros=False).cpu()
+    assert torch.equal(part, full[2:5])
+    model._drop_engine()
 
 
 @pytest.mark.parametrize("small", [False, True])
