@@ -445,6 +445,13 @@ int plan_smem(CsmCtx* ctx) {
     const int need = 2 * ctx->m_alloc * (16 * 16 + 8) * 2;
     if (need > ctx->act_region) ctx->act_region = need;
   }
+#if defined(CSM_ATT_RING) && CSM_ATT_RING
+  if (!ctx->fuse_attn) {
+    // experiment (csm_stream.inl: attn_bb_phase_ring): per-warp cp.async K/V ring of the backbone attention
+    const int need = CSM_COMPUTE_WARPS * CSM_ATT_RING * 16 * 144;
+    if (need > ctx->act_region) ctx->act_region = need;
+  }
+#endif
   ctx->act_region = (ctx->act_region + 255) / 256 * 256;
   const int limit = 227 * 1024;
   const int avail = limit - CSM_SM_HDR_BYTES - ctx->rope_bytes - ctx->red_bytes - ctx->act_region;

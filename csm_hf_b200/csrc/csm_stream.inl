@@ -50,6 +50,13 @@
 #endif
 
 // build-time experiment knobs (tools/gpu_variants.sh builds several libraries and times them in one GPU call)
+#ifndef CSM_ATT_RING
+#define CSM_ATT_RING 0   // experiment: stages of a per-warp cp.async K/V ring in the tensor-core backbone attention (0: off)
+#endif
+#if CSM_BUILD_SMALL
+#undef CSM_ATT_RING
+#define CSM_ATT_RING 0
+#endif
 #ifndef CSM_ATT_INLINE
 #define CSM_ATT_INLINE __noinline__
 #endif
@@ -1617,6 +1624,286 @@ __device__ CSM_ATT_INLINE void attn_bb_phase_mma(const StreamParams& p, int laye
 }
 #endif
 
+#if CSM_ATT_RING
+// EXPERIMENT (compile with -DCSM_ATT_RING=2 or 3; default off, not validated on a GPU yet -- DESIGN.md section 7): the same
+// phase with the K / V chunks staged in a per-warp shared-memory ring by cp.async instead of registers, so that
+// CSM_ATT_RING - 1 chunks are really in flight (ptxas spills the register prefetch of attn_bb_phase_mma, which makes
+// those loads synchronous).  One stream of 2 * nch chunk copies per unit: K chunks, then V chunks, 16 rows of 128
+// bytes each, padded to 144-byte rows (conflict-free ldmatrix).  Fragments: K with ldmatrix.x4 (natural dim order,
+// so q is read as 8-byte pairs), V with ldmatrix.x4.trans (natural output dims).  The ring lives in the activation
+// region, which no one uses during this phase (host: plan_smem reserves 8 warps x CSM_ATT_RING x 2304 bytes).
+__device__ __forceinline__ uint2 ld_tag2(const uint32_t* q) {
+  uint2 v;
+  asm volatile("ld.relaxed.gpu.global.v2.u32 {%0,%1}, [%2];" : "=r"(v.x), "=r"(v.y) : "l"(q) : "memory");
+  return v;
+}
+__device__ __forceinline__ void ldsm_x4_t(uint32_t (&r)[4], uint32_t addr) {
+  asm volatile("ldmatrix.sync.aligned.m8n8.x4.trans.shared.b16 {%0,%1,%2,%3}, [%4];"
+               : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3])
+               : "r"(addr));
+}
+
+template <int REP>
+__device__ __noinline__ void attn_bb_phase_ring(const StreamParams& p, int layer, int src_ph, int ph) {
+  constexpr int HD = 64, SPLIT = CSM_ATT_SPLIT_MMA, NCH = SPLIT / 16, ST = CSM_ATT_RING, RS = 144, STB = 16 * RS;
+  static_assert(REP <= 8, "query heads per kv head");
+  static_assert(ST >= 2 && ST <= 4, "ring stages");
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, c = blockIdx.x, G = gridDim.x;
+  const int Ttot = p.pos + 1;
+  const int nsplit = (Ttot + SPLIT - 1) / SPLIT;
+  const int nk = p.bb.kv;
+  const int nunits = p.B * nk * nsplit;
+  const int g = lane >> 2, t = lane & 3;        // MMA fragment coordinates
+  const int grp = lane >> 3, dl = lane & 7;     // copy / merge coordinates
+  const uint32_t qtag = tg(p, src_ph), otag = tg(p, ph);
+  const int Wq = (p.bb.heads + 2 * nk) * HD;    // tagged q | k | v row
+  const float scale = p.bb.scale;
+  const uint32_t ring = smem_u32(sm_act(p)) + (uint32_t)warp * (ST * STB);
+  compute_sync();   // (the previous phase ended without a CTA barrier; this one reuses its activation region)
+#pragma unroll 1
+  for (int unit = warp * G + c; unit < nunits; unit += CSM_COMPUTE_WARPS * G) {
+    const int sp = unit % nsplit;
+    const int kvh = (unit / nsplit) % nk;
+    const int b = unit / (nsplit * nk);
+    const size_t kvbase = (((size_t)layer * p.Bmax + b) * nk + kvh) * (size_t)p.Tcap * HD;
+    const bf16* Kp = p.kc_bb + kvbase;
+    const bf16* Vp = p.vc_bb + kvbase;
+    const int p0 = sp * SPLIT;
+    const int nch = min(NCH, (Ttot - p0 + 15) >> 4);   // chunks with at least one position (>= 1)
+    const uint32_t* kw = p.q_bb + (size_t)b * Wq + p.bb.heads * HD + kvh * HD;   // tagged K / V of position `pos`
+    const uint32_t* vw = kw + nk * HD;
+    const bool has_cur = p.pos >= p0 && p.pos < p0 + SPLIT;   // (warp-uniform)
+    if (lane == 0) {   // next unit of this warp: HBM -> L2 while this one is computed
+      const int nu = unit + CSM_COMPUTE_WARPS * G;
+      if (nu < nunits) {
+        const int sp2 = nu % nsplit, kvh2 = (nu / nsplit) % nk, b2 = nu / (nsplit * nk);
+        const size_t off = ((((size_t)layer * p.Bmax + b2) * nk + kvh2) * (size_t)p.Tcap + (size_t)sp2 * SPLIT) * HD;
+        const int npos = min(SPLIT, p.pos - sp2 * SPLIT);   // cached positions only
+        if (npos > 0) {
+          bulk_prefetch_l2(p.kc_bb + off, (uint32_t)npos * 128u);
+          bulk_prefetch_l2(p.vc_bb + off, (uint32_t)npos * 128u);
+        }
+      }
+    }
+    // copy i of the unit's stream (i < nch: K chunk i, else V chunk i - nch) into slot i % ST: lane -> rows grp + 4 r,
+    // 16-byte column dl; rows that are not cached yet (>= pos) are zero-filled.  One cp.async group per copy, also when
+    // there is nothing left to copy (uniform group counting).
+    __syncwarp();   // (the previous unit's last reads of the ring are done)
+#define CSM_RING_ISSUE(i)                                                                                       \
+    do {                                                                                                          \
+      if ((i) < 2 * nch) {                                                                                        \
+        const bf16* src_ = ((i) < nch ? Kp : Vp) + dl * 8;                                                        \
+        const int pc_ = p0 + 16 * ((i) < nch ? (i) : (i) - nch);                                                  \
+        const uint32_t dst_ = ring + (uint32_t)((i) % ST) * STB + (uint32_t)dl * 16u;                             \
+        _Pragma("unroll") for (int r_ = 0; r_ < 4; ++r_) {                                                        \
+          const int row_ = grp + 4 * r_;                                                                          \
+          if (pc_ + row_ < p.pos)                                                                                 \
+            asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst_ + (uint32_t)row_ * RS),            \
+                         "l"(src_ + (size_t)(pc_ + row_) * HD) : "memory");                                      \
+          else                                                                                                    \
+            asm volatile("st.shared.v4.u32 [%0], {%1,%1,%1,%1};" ::"r"(dst_ + (uint32_t)row_ * RS), "r"(0u) : "memory"); \
+        }                                                                                                         \
+      }                                                                                                           \
+      asm volatile("cp.async.commit_group;" ::: "memory");                                                       \
+    } while (0)
+#pragma unroll
+    for (int i = 0; i < ST - 1; ++i) CSM_RING_ISSUE(i);
+    // Q fragments, natural dim order: k-step i, a0 = dims 16 i + 2 t (+1), a2 = dims 16 i + 8 + 2 t (+1)
+    uint32_t qf[8];
+    {
+      const uint32_t* qw = p.q_bb + (size_t)b * Wq + (kvh * REP + (g < REP ? g : 0)) * HD + 2 * t;
+      uint2 q2[8];
+      bool ok;
+      unsigned spin = 0;
+      do {
+        ok = true;
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+          q2[i] = ld_tag2(qw + 8 * i);
+          ok &= ((q2[i].x >> 16) == qtag) & ((q2[i].y >> 16) == qtag);
+        }
+        if (!ok) poll_backoff(p, spin);
+        if (!ok && spin_giveup(p, spin, ph, W_ATTN_BB_Q, (unsigned)unit)) ok = true;
+      } while (!__all_sync(0xffffffffu, ok));
+#pragma unroll
+      for (int i = 0; i < 8; ++i) qf[i] = g < REP ? tw_pair(q2[i].x, q2[i].y) : 0u;
+    }
+    // ---- S = Q K^T; s[ch][j][e]: head g, position p0 + 16 ch + 8 j + 2 t + e
+    float s[NCH][2][2];
+#pragma unroll
+    for (int ch = 0; ch < NCH; ++ch) {
+      if (ch < nch) {
+        __syncwarp();                                          // slot (ch - 1) % ST has been read by every lane
+        CSM_RING_ISSUE(ch + ST - 1);
+        asm volatile("cp.async.wait_group %0;" ::"n"(ST - 1) : "memory");   // this lane's part of copy `ch` has landed
+        __syncwarp();                                          // ... and every other lane's
+        const uint32_t slot = ring + (uint32_t)(ch % ST) * STB;
+#pragma unroll
+        for (int j = 0; j < 2; ++j) {
+          float acc[4] = {0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+          for (int hf = 0; hf < 2; ++hf) {   // 32 dims per ldmatrix.x4: matrices = dims 0-7 | 8-15 | 16-23 | 24-31 of rows 8j..8j+7
+            uint32_t kf[4];
+            ldsm_x4(kf, slot + (uint32_t)(8 * j + dl) * RS + (uint32_t)grp * 16u + (uint32_t)hf * 64u);
+            const uint32_t a0[4] = {qf[4 * hf], 0u, qf[4 * hf + 1], 0u};
+            const uint32_t a1[4] = {qf[4 * hf + 2], 0u, qf[4 * hf + 3], 0u};
+            mma16816(acc, a0, kf[0], kf[1]);
+            mma16816(acc, a1, kf[2], kf[3]);
+          }
+          const int pj = p0 + 16 * ch + 8 * j + 2 * t;
+          s[ch][j][0] = (pj < p.pos) ? acc[0] * scale : -INFINITY;
+          s[ch][j][1] = (pj + 1 < p.pos) ? acc[1] * scale : -INFINITY;
+        }
+      } else {
+        s[ch][0][0] = s[ch][0][1] = s[ch][1][0] = s[ch][1][1] = -INFINITY;
+      }
+    }
+    // score of `pos`: one more n-tile whose column 0 is the tagged K row (lanes g == 0 supply it), valid in c0 of t == 0
+    float s_cur = -INFINITY;
+    if (has_cur) {
+      uint2 k2[8];
+      bool ok;
+      unsigned spin = 0;
+      do {
+        ok = true;
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+          k2[i] = ld_tag2(kw + 2 * t + 8 * i);
+          ok &= ((k2[i].x >> 16) == qtag) & ((k2[i].y >> 16) == qtag);
+        }
+        if (!ok) poll_backoff(p, spin);
+        if (!ok && spin_giveup(p, spin, ph, W_ATTN_BB_KV, (unsigned)unit)) ok = true;
+      } while (!__all_sync(0xffffffffu, ok));
+      float acc[4] = {0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        const uint32_t a[4] = {qf[2 * i], 0u, qf[2 * i + 1], 0u};
+        mma16816(acc, a, g == 0 ? tw_pair(k2[2 * i].x, k2[2 * i].y) : 0u, g == 0 ? tw_pair(k2[2 * i + 1].x, k2[2 * i + 1].y) : 0u);
+      }
+      if (t == 0) s_cur = acc[0] * scale;
+    }
+    // ---- softmax over the unit (fp32): lanes t = 0..3 of a row share a head
+    float mx = s_cur;
+#pragma unroll
+    for (int ch = 0; ch < NCH; ++ch) mx = fmaxf(mx, fmaxf(fmaxf(s[ch][0][0], s[ch][0][1]), fmaxf(s[ch][1][0], s[ch][1][1])));
+    mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, 1));
+    mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, 2));
+    float ls = 0.f;
+#pragma unroll
+    for (int ch = 0; ch < NCH; ++ch)
+#pragma unroll
+      for (int j = 0; j < 2; ++j)
+#pragma unroll
+        for (int e = 0; e < 2; ++e) {
+          const float pv = __expf(s[ch][j][e] - mx);
+          s[ch][j][e] = pv;
+          ls += pv;
+        }
+    const float p_cur = __expf(s_cur - mx);   // (0 unless this lane holds the score of `pos`)
+    ls += p_cur;
+    ls += __shfl_xor_sync(0xffffffffu, ls, 1);
+    ls += __shfl_xor_sync(0xffffffffu, ls, 2);
+    // ---- O = P V; o[jn][e]: head g, dim 8 jn + 2 t + e
+    float o[8][4];
+#pragma unroll
+    for (int jn = 0; jn < 8; ++jn) o[jn][0] = o[jn][1] = o[jn][2] = o[jn][3] = 0.f;
+#pragma unroll
+    for (int ch = 0; ch < NCH; ++ch) {
+      if (ch < nch) {
+        __syncwarp();
+        CSM_RING_ISSUE(nch + ch + ST - 1);
+        asm volatile("cp.async.wait_group %0;" ::"n"(ST - 1) : "memory");
+        __syncwarp();
+        const uint32_t slot = ring + (uint32_t)((nch + ch) % ST) * STB;
+        const float h00 = bfround(s[ch][0][0]), h01 = bfround(s[ch][0][1]), h10 = bfround(s[ch][1][0]), h11 = bfround(s[ch][1][1]);
+        const uint32_t ahi[4] = {pack_bf16(h00, h01), 0u, pack_bf16(h10, h11), 0u};
+        const uint32_t alo[4] = {pack_bf16(s[ch][0][0] - h00, s[ch][0][1] - h01), 0u,
+                                 pack_bf16(s[ch][1][0] - h10, s[ch][1][1] - h11), 0u};
+#pragma unroll
+        for (int jp = 0; jp < 4; ++jp) {   // two n-tiles per ldmatrix.x4.trans: matrices = (rows 0-7 | 8-15) x (dims 16 jp.. | 16 jp + 8..)
+          uint32_t vf[4];
+          ldsm_x4_t(vf, slot + (uint32_t)(dl + 8 * (grp & 1)) * RS + (uint32_t)(16 * jp + 8 * (grp >> 1)) * 2u);
+          mma16816(o[2 * jp], ahi, vf[0], vf[1]);
+          mma16816(o[2 * jp], alo, vf[0], vf[1]);
+          mma16816(o[2 * jp + 1], ahi, vf[2], vf[3]);
+          mma16816(o[2 * jp + 1], alo, vf[2], vf[3]);
+        }
+      }
+    }
+    asm volatile("cp.async.wait_group 0;" ::: "memory");
+#undef CSM_RING_ISSUE
+    // P.V of `pos`: k slot 0 of one more step -- A holds p_cur in lanes t == 0, B the tagged V row (dim 8 jn + g) in lanes t == 0
+    if (has_cur) {
+      uint32_t vv[8];
+      bool ok;
+      unsigned spin = 0;
+      do {
+        ok = true;
+#pragma unroll
+        for (int jn = 0; jn < 8; ++jn) {
+          vv[jn] = ld_tag(vw + 8 * jn + g);
+          ok &= (vv[jn] >> 16) == qtag;
+        }
+        if (!ok) poll_backoff(p, spin);
+        if (!ok && spin_giveup(p, spin, ph, W_ATTN_BB_KV, (unsigned)unit)) ok = true;
+      } while (!__all_sync(0xffffffffu, ok));
+      const float hc = bfround(p_cur);
+      const uint32_t ahi[4] = {pack_bf16(hc, 0.f), 0u, 0u, 0u};
+      const uint32_t alo[4] = {pack_bf16(p_cur - hc, 0.f), 0u, 0u, 0u};
+#pragma unroll
+      for (int jn = 0; jn < 8; ++jn) {
+        const uint32_t bb0 = t == 0 ? (vv[jn] & 0xffffu) : 0u;
+        mma16816(o[jn], ahi, bb0, 0u);
+        mma16816(o[jn], alo, bb0, 0u);
+      }
+    }
+    // partial (max, sum, o[64]) of this unit: lane (g < REP, t) holds dims 8 jn + 2 t, + 1
+    if (g < REP) {
+      float* part = p.attn_part + (((size_t)b * p.bb.heads + kvh * REP + g) * p.nsplit_max + sp) * (HD + 2);
+#pragma unroll
+      for (int jn = 0; jn < 8; ++jn) *reinterpret_cast<float2*>(part + 2 + 8 * jn + 2 * t) = make_float2(o[jn][0], o[jn][1]);
+      if (t == 0) { part[0] = mx; part[1] = ls; }
+    }
+    __threadfence();
+    __syncwarp();
+    int last = 0;
+    if (lane == 0) last = atomicAdd(p.attn_cnt + b * nk + kvh, 1u) == (unsigned)nsplit - 1u;
+    last = __shfl_sync(0xffffffffu, last, 0);
+    if (last) {
+      // last unit of this (sequence, kv-head): merge the splits and publish the head outputs
+      __threadfence();
+#pragma unroll
+      for (int h0 = 0; h0 < REP; h0 += 4) {
+        const int h = h0 + grp;
+        if (h < REP) {
+          const float* part = p.attn_part + (((size_t)b * p.bb.heads + kvh * REP + h) * p.nsplit_max) * (HD + 2);
+          float M2 = -INFINITY;
+#pragma unroll 6
+          for (int s2 = 0; s2 < nsplit; ++s2) M2 = fmaxf(M2, ldcg_f32(part + (size_t)s2 * (HD + 2)));
+          float L2 = 0.f, O2[8];
+#pragma unroll
+          for (int i = 0; i < 8; ++i) O2[i] = 0.f;
+#pragma unroll 3
+          for (int s2 = 0; s2 < nsplit; ++s2) {
+            const float* ps = part + (size_t)s2 * (HD + 2);
+            const float f = __expf(ldcg_f32(ps) - M2);
+            L2 += f * ldcg_f32(ps + 1);
+#pragma unroll
+            for (int i = 0; i < 8; ++i) O2[i] += f * ldcg_f32(ps + 2 + dl * 8 + i);
+          }
+          uint32_t* od = p.attn_bb + (size_t)b * (p.bb.heads * HD) + (kvh * REP + h) * HD + dl * 8;
+          st_tag4(od, tw_pack(O2[0] / L2, otag), tw_pack(O2[1] / L2, otag), tw_pack(O2[2] / L2, otag), tw_pack(O2[3] / L2, otag));
+          st_tag4(od + 4, tw_pack(O2[4] / L2, otag), tw_pack(O2[5] / L2, otag), tw_pack(O2[6] / L2, otag),
+                  tw_pack(O2[7] / L2, otag));
+        }
+      }
+      if (lane == 0) p.attn_cnt[b * nk + kvh] = 0u;
+    }
+    __syncwarp();
+  }
+}
+#endif   // CSM_ATT_RING
+
 }  // namespace
 
 // STOCH only makes the kernel's NAME unique per translation unit: template instantiations have weak linkage, two
@@ -1816,6 +2103,8 @@ __global__ void __launch_bounds__(CSM_THREADS, 1) csm_stream_kernel(const __grid
     else if (type == PH_ATTN_BB) {
 #if CSM_BUILD_SMALL
       attn_bb_phase<REP>(p, P.layer, P.src_ph, ph);
+#elif CSM_ATT_RING
+      attn_bb_phase_ring<REP>(p, P.layer, P.src_ph, ph);
 #else
       attn_bb_phase_mma<REP>(p, P.layer, P.src_ph, ph);
 #endif
