@@ -27,7 +27,7 @@ tot = sum(cnt.values())
 print('total', tot, 'instr', tot * 16 // 1024, 'KB')
 b = Counter()
 for (f, l), n in cnt.items():
-    if f != 'csm_stream.cu':
+    if f not in ('csm_stream.cu', 'csm_stream.inl'):
         b[f] += n
         continue
     i = bisect.bisect_right([m[0] for m in marks], l) - 1

@@ -38,7 +38,7 @@ com = open('csm_hf_b200/csrc/csm_common.cuh').read().split('\n')
 print("total samples", tot)
 for k, s in samp.most_common(top):
     text = ""
-    if k and k[0] == 'csm_stream.cu':
+    if k and k[0] in ('csm_stream.cu', 'csm_stream.inl'):
         text = src[k[1] - 1].strip()
     elif k and k[0] == 'csm_common.cuh':
         text = com[k[1] - 1].strip()
