@@ -5,13 +5,23 @@ A "step" is one CSMModel.generate() of `--frames` new frames after a `--ctx`-fra
 `--batch` sequences per GPU (default: BASELINE.json configs[1] = csm-1b bf16, 2048-frame
 context, 200 new frames, batch 1, one B200).  Prints ONE JSON line (rank 0).
 
-  value   whole-job frames/s (all ranks), inputs resident in HBM, prefill included
-  e2e     the same call through the host-buffer C-ABI entry (csm_generate_host): pinned H2D of
-          ids+mask and D2H of the frames inside the timed region
+  value     whole-job frames/s (all ranks), inputs resident in HBM, prefill included
+  e2e       the same call through the host-buffer C-ABI entry (csm_generate_host): pinned H2D of
+            ids+mask and D2H of the frames inside the timed region
   roofline  the persistent decode-frame kernel (csm_stream_kernel): algorithmic bytes per
-          launch / CUDA-event time per launch, against MEASURED_PEAKS.json
-  cpu_baseline / --impl reference: the oracle port of the reference's CPU path (the Python
-          reference cannot travel to the GPU box), fp32, all host threads, bounded sample
+            launch / CUDA-event time per launch, against MEASURED_PEAKS.json
+  config.points   the other batch sizes of the metric ("batch 1/8/32"), measured in the same
+            invocation with the same engine code: frames/s, decode ms/frame, roofline fraction,
+            prefill time against the tensor roofline.  Under torchrun with N ranks the batch-8
+            point is BASELINE.json configs[3] scaled to N GPUs (8 sequences per GPU, N x 8 total).
+  verified  after the timed region the SAME engine is checked, teacher-forced, against the
+            committed fixture minted from the reference at this configuration
+            (tests/golden/csm1b_t2048_b1_fp32.pt): logits within the stated tolerance, greedy ids
+            identical wherever the reference's margin decides them
+  cpu_baseline / --impl reference: the reference's own CPU path (modeling_csm.py staged under
+            oracle/_ref by oracle/stage_ref.py; the oracle port if that copy is absent), fp32, all
+            host threads, on a bounded sample (prefill + a few decode frames) PROJECTED to the
+            200-frame workload -- the JSON says so
 """
 import argparse
 import json
@@ -35,12 +45,19 @@ def algorithmic_bytes(B, T):
     return 2 * (P_BB + P_C0 + 31 * P_DEC + P_AH + P_PROJ) + B * T * 32768 + B * 65 * 4096
 
 
+def prefill_flops(B, T):
+    """2*B*T*P_bb + causal attention + last-position head."""
+    return 2.0 * B * T * P_BB + B * 16 * 4 * 32 * 64 * T * T / 2.0 + 2.0 * B * P_C0
+
+
 def measured_peaks():
     p = os.path.join(ROOT, "MEASURED_PEAKS.json")
     if os.path.isfile(p):
         with open(p) as f:
-            return float(json.load(f)["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
-    return 6650.0, "fallback (B200_PROFILING.md 6.65 TB/s)"
+            j = json.load(f)
+        return (float(j["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)",
+                float(j.get("bf16_tflops_sustained", 1400.0)), "measured (MEASURED_PEAKS.json bf16_tflops_sustained)")
+    return 6650.0, "fallback (B200_PROFILING.md 6.65 TB/s)", 1400.0, "fallback (B200_PROFILING.md ~1.4 PFLOP/s sustained)"
 
 
 class ClockSampler:
@@ -76,29 +93,63 @@ class ClockSampler:
                 "reasons": reasons, "samples": len(sm)}
 
 
-def cpu_reference_sample(cfg, sd_fp32, ctx, frames_sample, new_frames):
-    """Oracle port of the reference CPU path (fp32, all threads): prefill `ctx` frames + a few
-    decode frames, projected to the full `new_frames` workload."""
+def next_row(toks):
     import torch
-    from csm_hf_b200.synthetic import make_context
-    from oracle.csm_oracle import CSMOracle   # the one place bench.py executes oracle/: as the timed CPU baseline
-    torch.set_num_threads(os.cpu_count() or 1)
-    oracle = CSMOracle(cfg, sd_fp32, torch.float32)
-    ids, mask = make_context(cfg, 1, ctx, seed=1234)
-    with torch.inference_mode():
-        cache = oracle.new_cache(1, ctx + frames_sample + 1)
-        t0 = time.perf_counter()
-        toks, _, _ = oracle.generate_frame(ids, mask, cache)
-        t_first = time.perf_counter() - t0
-        t1 = time.perf_counter()
-        for _ in range(frames_sample):
-            row = torch.cat([toks, torch.zeros(1, 1, dtype=torch.long)], dim=1).unsqueeze(1)
-            m = torch.zeros(1, 1, 33, dtype=torch.int32)
-            m[:, :, :32] = 1
-            toks, _, _ = oracle.generate_frame(row, m, cache)
-        t_frame = (time.perf_counter() - t1) / frames_sample
-    total = t_first + (new_frames - 1) * t_frame
-    return new_frames / total, t_first, t_frame
+    B = toks.shape[0]
+    ids = torch.cat([toks.to(torch.long), torch.zeros(B, 1, dtype=torch.long)], dim=1).unsqueeze(1)
+    m = torch.zeros(B, 1, 33, dtype=torch.int32)
+    m[:, :, :32] = 1
+    return ids, m
+
+
+class CpuReference:
+    """The reference's CPU path for the bounded sample: the real modeling_csm.py (oracle/_ref or /root/reference)
+    behind the harness shims of oracle/ref_harness.py, else the oracle port."""
+
+    def __init__(self, cfg, sd_fp32):
+        import torch
+        from oracle import ref_harness as R   # bench.py executes oracle/ only here: as the timed CPU baseline
+        torch.set_num_threads(os.cpu_count() or 1)
+        self.kind = "port"
+        self.model = None
+        if R.reference_available() and not os.environ.get("BENCH_CPU_PORT"):
+            try:
+                self.model = R.build_reference_model(cfg, sd_fp32, torch.float32)
+                self.kind = "reference"
+            except Exception as exc:  # noqa: BLE001 -- e.g. a transformers version the reference cannot import under
+                sys.stderr.write(f"[bench] reference import failed ({type(exc).__name__}: {exc}); timing the oracle port\n")
+        if self.model is None:
+            from oracle.csm_oracle import CSMOracle
+            self.oracle = CSMOracle(cfg, sd_fp32, torch.float32)
+
+    def sample(self, ids, mask, frames_sample):
+        """-> (seconds of prefill + first frame, seconds per decode frame)"""
+        import torch
+        import warnings
+        with torch.inference_mode(), warnings.catch_warnings():
+            warnings.simplefilter("ignore")
+            if self.model is not None:
+                t0 = time.perf_counter()
+                out = self.model.generate_frame(ids, mask, temperature=1.0, topk=1, past_key_values=None, use_cache=True,
+                                                return_dict=True)
+                t_first = time.perf_counter() - t0
+                kv, toks = out.past_key_values, out.samples
+                t1 = time.perf_counter()
+                for _ in range(frames_sample):
+                    rid, rm = next_row(toks)
+                    out = self.model.generate_frame(rid, rm, temperature=1.0, topk=1, past_key_values=kv, use_cache=True,
+                                                    return_dict=True)
+                    kv, toks = out.past_key_values, out.samples
+                return t_first, (time.perf_counter() - t1) / frames_sample
+            cache = self.oracle.new_cache(1, ids.shape[1] + frames_sample + 1)
+            t0 = time.perf_counter()
+            toks, _, _ = self.oracle.generate_frame(ids, mask, cache)
+            t_first = time.perf_counter() - t0
+            t1 = time.perf_counter()
+            for _ in range(frames_sample):
+                rid, rm = next_row(toks)
+                toks, _, _ = self.oracle.generate_frame(rid, rm, cache)
+            return t_first, (time.perf_counter() - t1) / frames_sample
 
 
 def note(msg):
@@ -108,16 +159,92 @@ def note(msg):
         sys.stderr.flush()
 
 
+def reference_arm(a, cfg, workload):
+    import signal
+    import torch
+    from csm_hf_b200.synthetic import make_context, make_state_dict
+
+    def _too_slow(signum, frame):   # a host that cannot finish the bounded CPU sample in 15 minutes
+        print(json.dumps({"impl": "reference", "unavailable": "CPU reference sample did not finish within 900 s"}))
+        sys.stdout.flush()
+        os._exit(0)
+
+    signal.signal(signal.SIGALRM, _too_slow)
+    signal.alarm(900)
+    t_start = time.perf_counter()
+    ref = CpuReference(cfg, make_state_dict(cfg, seed=0))
+    ids, mask = make_context(cfg, 1, a.ctx, seed=1234)
+    vals = []
+    n_warm = 1                                                    # one warm-up pass is enough on the CPU
+    budget_s = float(os.environ.get("BENCH_REF_BUDGET_S", "420"))  # the whole arm ends within a few minutes
+    for i in range(n_warm + a.steps):
+        t_first, t_frame = ref.sample(ids, mask, a.cpu_sample_frames)
+        if i >= n_warm:
+            vals.append((a.frames / (t_first + (a.frames - 1) * t_frame), t_first, t_frame))
+        if vals and time.perf_counter() - t_start > budget_s:
+            break
+    v = statistics.mean(x[0] for x in vals)
+    src = "modeling_csm.py (the reference itself, staged copy)" if ref.kind == "reference" else "oracle port of modeling_csm.py"
+    sample = (f"{src}, fp32, torch CPU: {a.ctx}-frame prefill+frame ({statistics.mean(x[1] for x in vals):.2f} s) + "
+              f"{a.cpu_sample_frames} decode frames ({statistics.mean(x[2] for x in vals):.3f} s each), PROJECTED to "
+              f"{a.frames} frames, batch 1; {len(vals)} samples")
+    print(json.dumps({
+        "impl": "reference", "metric": "audio_frames_per_s", "value": v, "unit": "frames/s", "n_gpus": a.gpus,
+        "steps": len(vals), "warmup": n_warm, "ms_per_step": 1000.0 * a.frames / v, "higher_is_better": True,
+        "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic", "projected": True,
+        "config": {"workload": workload.replace(f"batch={a.batch} per GPU", "batch=1"),
+                   "note": "ms_per_step is the projected time of one 200-frame generate(): each timed sample runs the "
+                           "prefill and a few decode frames of it"},
+        "cpu_baseline": {"value": v, "unit": "frames/s", "cores": torch.get_num_threads(), "kind": ref.kind,
+                         "sample": sample, "projected": True},
+        "e2e": {"value": v, "unit": "frames/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+    }))
+
+
+def verify_against_fixture(model, dev):
+    """Teacher-forced check of the engine that was just timed against the reference-minted fixture of this
+    configuration (csm-1b, 2048-frame context, batch 1): -> dict for the JSON line."""
+    import torch
+    path = os.path.join(ROOT, "tests", "golden", "csm1b_t2048_b1_fp32.pt")
+    if not os.path.isfile(path):
+        return {"ok": False, "why": "fixture missing"}
+    from csm_hf_b200.synthetic import make_context
+    g = torch.load(path, weights_only=False)
+    r = g["recipe"]
+    ids, mask = make_context(model.config, r["batch"], r["ctx_frames"], seed=r["ctx_seed"])
+    rel, worst, ok = 0.05, 0.0, True
+    kv, rid, rm = None, ids, mask
+    for f in range(g["frames"].shape[1]):
+        out = model.generate_frame(rid, rm, temperature=0, past_key_values=kv, force_tokens=g["frames"][:, f],
+                                   return_codebook_logits=True)
+        kv = out.past_key_values
+        for got, want in ((out.logits.cpu(), g["c0_logits"][f]), (out.codebook_logits.cpu(), g["cb_logits"][f])):
+            want = want.float()
+            scale = float(want.abs().max())
+            err = float((got.float() - want).abs().max()) / scale
+            worst = max(worst, err)
+            top2 = torch.topk(want, 2, dim=-1).values
+            decided = (top2[..., 0] - top2[..., 1]) > 2 * rel * scale
+            ok = ok and err <= rel and not bool(((got.float().argmax(-1) != want.argmax(-1)) & decided).any())
+        rid, rm = next_row(g["frames"][:, f])
+    return {"ok": bool(ok), "fixture": "tests/golden/csm1b_t2048_b1_fp32.pt (reference fp32 CPU run)",
+            "frames": int(g["frames"].shape[1]), "max_err_of_logit_range": worst, "tolerance": rel,
+            "how": "teacher-forced with the reference's ids after the timed region, same engine"}
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=3)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--batch", type=int, default=1, help="sequences per GPU")
+    ap.add_argument("--batch", type=int, default=1, help="sequences per GPU of the headline value")
     ap.add_argument("--ctx", type=int, default=2048)
     ap.add_argument("--frames", type=int, default=200)
+    ap.add_argument("--points", default="1,8,32", help="batch sizes per GPU reported under config.points ('' = none)")
+    ap.add_argument("--point-steps", type=int, default=2)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-verify", action="store_true")
     ap.add_argument("--cpu-sample-frames", type=int, default=4)
     a = ap.parse_args()
 
@@ -133,41 +260,13 @@ def main():
     cfg = CSMConfig()
 
     if a.impl == "reference":
-        if rank != 0:
-            return
-        import signal
-
-        def _too_slow(signum, frame):   # a host that cannot finish the bounded CPU sample in 15 minutes
-            print(json.dumps({"impl": "reference", "unavailable": "CPU reference sample did not finish within 900 s"}))
-            sys.stdout.flush()
-            os._exit(0)
-
-        signal.signal(signal.SIGALRM, _too_slow)
-        signal.alarm(900)
-        sd = make_state_dict(cfg, seed=0)
-        vals = []
-        for i in range(max(1, min(a.warmup, 1)) + a.steps):          # one warm-up pass is enough on the CPU
-            v, t_first, t_frame = cpu_reference_sample(cfg, sd, a.ctx, a.cpu_sample_frames, a.frames)
-            if i >= max(1, min(a.warmup, 1)):
-                vals.append((v, t_first, t_frame))
-        v = statistics.mean(x[0] for x in vals)
-        sample = (f"oracle port of modeling_csm.py (fp32, torch CPU): {a.ctx}-frame prefill+frame "
-                  f"({statistics.mean(x[1] for x in vals):.2f} s) + {a.cpu_sample_frames} decode frames "
-                  f"({statistics.mean(x[2] for x in vals):.3f} s each), projected to {a.frames} frames, batch 1")
-        print(json.dumps({
-            "impl": "reference", "metric": "audio_frames_per_s", "value": v, "unit": "frames/s", "n_gpus": a.gpus,
-            "steps": a.steps, "warmup": a.warmup, "ms_per_step": 1000.0 * a.frames / v, "higher_is_better": True,
-            "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-            "config": {"workload": workload.replace(f"batch={a.batch} per GPU", "batch=1")},
-            "cpu_baseline": {"value": v, "unit": "frames/s", "cores": torch.get_num_threads(), "kind": "port",
-                             "sample": sample},
-            "e2e": {"value": v, "unit": "frames/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
-        }))
+        if rank == 0:
+            reference_arm(a, cfg, workload)
         return
 
     # ------------------------------------------------------------------ our arm
     import torch.distributed as dist
-    from csm_hf_b200.dist import generate_sharded
+    from csm_hf_b200.dist import all_gather_frames, generate_sharded
     from csm_hf_b200.modeling import CSMModel
     assert torch.cuda.is_available(), "bench.py needs a GPU (no CPU fallback)"
     dev = torch.device("cuda", local_rank)
@@ -183,58 +282,80 @@ def main():
         cmd = [sys.executable, os.path.abspath(__file__), "--impl", "reference", "--steps", "1", "--warmup", "1", "--ctx",
                str(a.ctx), "--frames", str(a.frames), "--cpu-sample-frames", str(a.cpu_sample_frames)]
         try:
-            res = subprocess.run(cmd, capture_output=True, text=True, timeout=240)
+            res = subprocess.run(cmd, capture_output=True, text=True, timeout=300)
             ref = json.loads(res.stdout.strip().splitlines()[-1])
             cpu_baseline = ref["cpu_baseline"]
         except Exception as exc:   # noqa: BLE001 -- a baseline that cannot be measured is reported, not fatal
             cpu_baseline = {"value": None, "unit": "frames/s", "cores": os.cpu_count(), "kind": "port",
                             "sample": f"not measured: {type(exc).__name__}"}
         note("cpu baseline done")
-    sd = make_state_dict(cfg, seed=0, dtype=torch.bfloat16)
-    model = CSMModel(cfg, sd, device=dev, max_batch=a.batch, max_ctx=a.ctx + a.frames + 8)
-    GB = a.batch * world
-    ids, mask = make_context(cfg, GB, a.ctx, seed=1234)
-    lo = rank * a.batch
-    d_ids, d_mask = ids.to(dev), mask.to(dev)
-    h_ids, h_mask = ids[lo:lo + a.batch].contiguous().pin_memory(), mask[lo:lo + a.batch].contiguous().pin_memory()
-    eng = model.engine(a.batch, a.ctx + a.frames)
-
-    def step_device():
-        if world > 1:
-            return generate_sharded(model, d_ids, d_mask, max_new_frames=a.frames, temperature=0, stop_on_all_zeros=False)
-        return model.generate(d_ids, d_mask, max_new_frames=a.frames, temperature=0, stop_on_all_zeros=False)
-
-    note("model + engine ready")
-    for i in range(max(a.warmup, 3)):
-        out = step_device()
-        torch.cuda.synchronize()
-        note(f"warm-up {i} done")
-    assert tuple(out.shape) == (GB, a.frames, 32)
+    sd = {k: v.to(dev) for k, v in make_state_dict(cfg, seed=0, dtype=torch.bfloat16).items()}
+    peak, peak_src, tpeak, tpeak_src = measured_peaks()
+    t_mean = a.ctx + (a.frames + 1) / 2.0                     # mean cached length over the decode frames
 
     def fence():
         if world > 1:
             dist.barrier()
         torch.cuda.synchronize()
 
+    def measure(batch, steps, warmup):
+        """Device-resident inputs, `steps` timed generate() calls after `warmup`: -> (model, dict)."""
+        model = CSMModel(cfg, sd, device=dev, max_batch=batch, max_ctx=a.ctx + a.frames + 8)
+        GB = batch * world
+        ids, mask = make_context(cfg, GB, a.ctx, seed=1234)
+        d_ids, d_mask = ids.to(dev), mask.to(dev)
+        eng = model.engine(batch, a.ctx + a.frames)
+
+        def step():
+            if world > 1:
+                return generate_sharded(model, d_ids, d_mask, max_new_frames=a.frames, temperature=0, stop_on_all_zeros=False)
+            return model.generate(d_ids, d_mask, max_new_frames=a.frames, temperature=0, stop_on_all_zeros=False)
+
+        for i in range(warmup):
+            out = step()
+            torch.cuda.synchronize()
+        assert tuple(out.shape) == (GB, a.frames, 32)
+        launches0 = eng.info(4)
+        ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        dec_ms, dec_n = 0.0, 0
+        fence()
+        ev0.record()
+        for _ in range(steps):
+            out = step()
+            ms, n = model.last_decode_ms()
+            dec_ms += ms
+            dec_n += n
+        ev1.record()
+        fence()
+        t = torch.tensor([ev0.elapsed_time(ev1), dec_ms / max(dec_n, 1)], device=dev, dtype=torch.float64)
+        if world > 1:
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms_total, dec_per = [float(x) for x in t.cpu()]
+        ms_step = ms_total / steps
+        abytes = algorithmic_bytes(batch, t_mean)
+        achieved = abytes / (dec_per / 1000.0) / 1e9 if dec_per > 0 else 0.0
+        pre_ms = max(ms_step - dec_per * (a.frames - 1), 1e-6)       # prefill + the first frame's launch
+        ptf = prefill_flops(batch, a.ctx) / (pre_ms / 1000.0) / 1e12
+        res = {"batch_per_gpu": batch, "global_batch": GB, "value": GB * a.frames / (ms_step / 1000.0), "unit": "frames/s",
+               "ms_per_step": ms_step, "steps": steps, "decode_ms_per_frame": dec_per,
+               "decode_frames_per_s_per_gpu": batch * 1000.0 / dec_per if dec_per > 0 else 0.0,
+               "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
+                            "algorithmic_bytes_per_launch": abytes},
+               "prefill": {"ms_incl_first_frame": pre_ms, "bound": "tensor", "achieved": ptf, "peak": tpeak,
+                           "unit": "TFLOP/s", "frac": ptf / tpeak},
+               "launches": int(eng.info(4) - launches0), "out0": out[0, :3].cpu() if rank == 0 else None}
+        return model, res, (ids, mask)
+
     sampler = ClockSampler(local_rank)
     if rank == 0:
         sampler.start()
-    launches0 = eng.info(4)
-    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    dec_ms, dec_n = 0.0, 0
-    fence()
-    ev0.record()
-    for _ in range(a.steps):
-        step_device()
-        ms, n = model.last_decode_ms()
-        dec_ms += ms
-        dec_n += n
-    ev1.record()
-    fence()
+    note("headline point starts")
+    model, head, (ids, mask) = measure(a.batch, a.steps, max(a.warmup, 3))
     note("timed device steps done")
-    ms_total = ev0.elapsed_time(ev1)
-    launches = eng.info(4) - launches0
     # end to end through host buffers (same process, same engine)
+    lo = rank * a.batch
+    h_ids, h_mask = ids[lo:lo + a.batch].contiguous().pin_memory(), mask[lo:lo + a.batch].contiguous().pin_memory()
+    GB = a.batch * world
     for _ in range(2):
         model.generate(h_ids, h_mask, max_new_frames=a.frames, temperature=0, stop_on_all_zeros=False)
     fence()
@@ -242,47 +363,67 @@ def main():
     for _ in range(a.steps):
         fr = model.generate(h_ids, h_mask, max_new_frames=a.frames, temperature=0, stop_on_all_zeros=False)
         if world > 1:
-            from csm_hf_b200.dist import all_gather_frames
             all_gather_frames(fr.to(dev), GB)
     fence()
     note("timed host-buffer steps done")
     e2e_s = time.perf_counter() - t0
     clocks = sampler.stop() if rank == 0 else None
-    t = torch.tensor([ms_total, e2e_s * 1000.0, dec_ms / max(dec_n, 1)], device=dev, dtype=torch.float64)
+    t = torch.tensor([e2e_s * 1000.0], device=dev, dtype=torch.float64)
     if world > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
-    ms_total, e2e_ms, dec_ms_per = [float(x) for x in t.cpu()]
+    e2e_ms = float(t.cpu()[0])
+    verified = None
+    if rank == 0 and not a.no_verify and a.ctx == 2048:
+        vm = model if a.batch == 1 else None
+        if vm is not None:
+            verified = verify_against_fixture(vm, dev)
+            note(f"verified: {verified}")
+    # the other batch sizes of the metric, same invocation
+    points = []
+    want_points = [int(x) for x in a.points.split(",") if x.strip()]
+    for b in want_points:
+        if b == a.batch:
+            pt = dict(head)
+        else:
+            model._drop_engine()
+            note(f"point batch {b} starts")
+            pm, pt, _ = measure(b, a.point_steps, 3)
+            if rank == 0 and verified is None and not a.no_verify and a.ctx == 2048 and b == 1:
+                verified = verify_against_fixture(pm, dev)
+            pm._drop_engine()
+            del pm
+        pt.pop("out0", None)
+        points.append(pt)
     if rank != 0:
         if world > 1:
             dist.destroy_process_group()
         return
-    ms_per_step = ms_total / a.steps
-    value = GB * a.frames / (ms_per_step / 1000.0)
     e2e_value = GB * a.frames / (e2e_ms / 1000.0 / a.steps)
-    peak, peak_src = measured_peaks()
-    t_mean = a.ctx + (a.frames + 1) / 2.0                     # mean cached length over the decode frames
-    abytes = algorithmic_bytes(a.batch, t_mean)
-    achieved = abytes / (dec_ms_per / 1000.0) / 1e9 if dec_ms_per > 0 else 0.0
     traffic = None
     tp = os.path.join(ROOT, "profiles", "traffic.json")
     if os.path.isfile(tp):
         with open(tp) as f:
             traffic = json.load(f).get(f"b{a.batch}")
+    rl = dict(head["roofline"])
+    rl.update({"kernel": "csm_stream_kernel (one launch = one frame for the whole batch)", "peak_source": peak_src,
+               "traffic": traffic})
     line = {
-        "metric": "audio_frames_per_s", "value": value, "unit": "frames/s", "n_gpus": world, "steps": a.steps,
-        "warmup": max(a.warmup, 3), "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak",
+        "metric": "audio_frames_per_s", "value": head["value"], "unit": "frames/s", "n_gpus": world, "steps": a.steps,
+        "warmup": max(a.warmup, 3), "ms_per_step": head["ms_per_step"], "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
         "config": {"workload": workload, "batch_per_gpu": a.batch, "global_batch": GB, "ctx_frames": a.ctx,
                    "new_frames": a.frames, "parallelism": f"batch-sharded x{world}, weights replicated",
                    "l2": "inputs larger than L2: 3.1 GB of weights are streamed every frame",
-                   "decode_ms_per_frame": dec_ms_per, "decode_frames_per_s_per_gpu": a.batch * 1000.0 / dec_ms_per},
-        "roofline": {"bound": "hbm", "kernel": "csm_stream_kernel (one launch = one frame for the whole batch)",
-                     "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                     "peak_source": peak_src, "algorithmic_bytes_per_launch": abytes, "traffic": traffic},
+                   "decode_ms_per_frame": head["decode_ms_per_frame"],
+                   "decode_frames_per_s_per_gpu": head["decode_frames_per_s_per_gpu"],
+                   "prefill": dict(head["prefill"], peak_source=tpeak_src),
+                   "points": points},
+        "roofline": rl,
         "e2e": {"value": e2e_value, "unit": "frames/s", "h2d_bytes_per_step": int(h_ids.numel() * 8 + h_mask.numel() * 4),
                 "d2h_bytes_per_step": int(a.batch * a.frames * 32 * 8)},
-        "gpu_launches": int(launches),
+        "gpu_launches": head["launches"],
         "clocks": clocks,
+        "verified": verified,
     }
     if want_cpu:
         line["cpu_baseline"] = cpu_baseline

@@ -1,6 +1,6 @@
 // C ABI of libcsm_b200.so (include/csm_b200.h): context creation (weight packing, workspace,
 // phase table), prefill orchestration, per-frame persistent launches, generate loop.
-#include <cublas_v2.h>
+#include <cuda.h>
 #include <cuda_runtime.h>
 #include <math.h>
 #include <stdarg.h>
@@ -25,14 +25,14 @@ extern "C" {
 cudaError_t csm_launch_stream(const StreamParams* p, int grid, size_t smem, cudaStream_t stream, int cooperative);
 cudaError_t csm_pack_launch(const PackSrc* src, const int* row_map_dev, int N, int K, int gran, int G, bf16* dst,
                             cudaStream_t stream);
+cudaError_t csm_gemm_launch(const void* map_a, const void* map_w, const GemmParams* p, int sms, cudaStream_t st);
+int csm_tmap_2d(void* out, const void* base, long long rows, int K, long long pitch, int box_rows);
+int csm_gemm_box_rows_a();
+int csm_gemm_box_rows_w();
+cudaError_t csm_interleave_rows_launch(const bf16* a, const bf16* b, int rows, int K, bf16* dst, cudaStream_t st);
 cudaError_t csm_embed_sum_launch(const long long* ids, const int* mask, int default_mask, const bf16* audio_emb,
                                  const bf16* text_emb, int V, int H, bf16* out, int rows, cudaStream_t st);
 cudaError_t csm_rmsnorm_rows_launch(const bf16* x, const bf16* w, float eps, int H, bf16* y, int rows, cudaStream_t st);
-cudaError_t csm_rope_kv_rows_launch(bf16* qkv, int S, int pos0, int b0, int heads, int kv, int hd, const bf16* cos_t,
-                                    const bf16* sin_t, bf16* kc, bf16* vc, int layer, int Bmax, int Tcap, int rows,
-                                    cudaStream_t st);
-cudaError_t csm_swiglu_rows_launch(const bf16* gu, int I, bf16* act, long long rows, cudaStream_t st);
-cudaError_t csm_add_rows_launch(bf16* h, const bf16* y, long long n, cudaStream_t st);
 cudaError_t csm_take_last_rows_launch(const bf16* h, int S, int H, uint32_t* dst, int b0, int nseq, uint32_t tag,
                                       cudaStream_t st);
 cudaError_t csm_sample_rows_launch(const bf16* logits, int rows, int V, int topk, float inv_temp, unsigned long long seed,
@@ -42,14 +42,17 @@ cudaError_t csm_i64_to_i32_launch(const long long* src, int* dst, int n, cudaStr
 cudaError_t csm_i32_to_i64_launch(const int* src, long long* dst, int n, cudaStream_t st);
 cudaError_t csm_flash_prefill_launch(const bf16* qkv, int S, int pos0, int b0, int nseq, int heads, int kv,
                                      const bf16* kc, const bf16* vc, int layer, int Bmax, int Tcap, float scale,
-                                     bf16* out, cudaStream_t st);
+                                     const unsigned char* valid, bf16* out, cudaStream_t st);
+cudaError_t csm_frame_valid_launch(const int* mask, int rows, unsigned char* valid, int* any_pad, cudaStream_t st);
 }
 
 namespace {
 
 struct LayerW {
-  // natural-layout copies for the prefill GEMMs (backbone only)
-  bf16 *q = nullptr, *k = nullptr, *v = nullptr, *o = nullptr, *gate = nullptr, *up = nullptr, *down = nullptr;
+  // natural-layout [out, in] copies for the prefill GEMMs (backbone only): q|k|v rows concatenated, gate/up rows
+  // interleaved (gate_j, up_j) so that SwiGLU is a tail of the GEMM tile; TMA tensor maps of each (csm_gemm.cu)
+  bf16 *qkv = nullptr, *o = nullptr, *gu = nullptr, *down = nullptr;
+  CUtensorMap tm_qkv, tm_o, tm_gu, tm_down;
   bf16 *ln1 = nullptr, *ln2 = nullptr;
   // packed for the frame engine
   bf16 *p_qkv = nullptr, *p_o = nullptr, *p_gu = nullptr, *p_down = nullptr;
@@ -106,8 +109,8 @@ struct CsmCtx {
   int lgt_stride = 0;
   // prefill workspace (lazy)
   int pf_rows = 0;
-  bf16 *pf_h = nullptr, *pf_hn = nullptr, *pf_qkv = nullptr, *pf_attn = nullptr, *pf_y = nullptr, *pf_gu = nullptr,
-       *pf_act = nullptr;
+  bf16 *pf_h = nullptr, *pf_hn = nullptr, *pf_qkv = nullptr, *pf_attn = nullptr, *pf_act = nullptr;
+  unsigned char* pf_valid = nullptr;   // [rows] frame-valid bytes of a padded prefill
   // host staging for csm_generate_host
   long long* st_ids = nullptr;
   int* st_mask = nullptr;
@@ -125,7 +128,6 @@ struct CsmCtx {
   int m_alloc = 0, slot_bytes = 0, n_slots = 0, rope_bytes = 0, act_region = 0, red_bytes = 0, stream_tpc_max = 0;
   size_t smem_total = 0;
   long long launches = 0;
-  cublasHandle_t cublas = nullptr;
   cudaEvent_t ev0 = nullptr, ev1 = nullptr;
   int ev_frames = 0;
   std::vector<void*> allocs;
@@ -230,13 +232,18 @@ int build_stack(CsmCtx* ctx, Stack& S, const CsmLlamaShape& sh, const void* cons
     if ((r = copy_weight(ctx, &L.ln1, w[CSM_W_LN1], H, st))) return r;
     if ((r = copy_weight(ctx, &L.ln2, w[CSM_W_LN2], H, st))) return r;
     if (keep_natural) {
-      if ((r = copy_weight(ctx, &L.q, w[CSM_W_Q], (size_t)nq * H, st))) return r;
-      if ((r = copy_weight(ctx, &L.k, w[CSM_W_K], (size_t)nkv * H, st))) return r;
-      if ((r = copy_weight(ctx, &L.v, w[CSM_W_V], (size_t)nkv * H, st))) return r;
+      DA(L.qkv, (size_t)(nq + 2 * nkv) * H);
+      CK(cudaMemcpyAsync(L.qkv, w[CSM_W_Q], (size_t)nq * H * 2, cudaMemcpyDeviceToDevice, st));
+      CK(cudaMemcpyAsync(L.qkv + (size_t)nq * H, w[CSM_W_K], (size_t)nkv * H * 2, cudaMemcpyDeviceToDevice, st));
+      CK(cudaMemcpyAsync(L.qkv + (size_t)(nq + nkv) * H, w[CSM_W_V], (size_t)nkv * H * 2, cudaMemcpyDeviceToDevice, st));
       if ((r = copy_weight(ctx, &L.o, w[CSM_W_O], (size_t)H * nq, st))) return r;
-      if ((r = copy_weight(ctx, &L.gate, w[CSM_W_GATE], (size_t)I * H, st))) return r;
-      if ((r = copy_weight(ctx, &L.up, w[CSM_W_UP], (size_t)I * H, st))) return r;
+      DA(L.gu, (size_t)2 * I * H);
+      CK(csm_interleave_rows_launch((const bf16*)w[CSM_W_GATE], (const bf16*)w[CSM_W_UP], I, H, L.gu, st));
       if ((r = copy_weight(ctx, &L.down, w[CSM_W_DOWN], (size_t)H * I, st))) return r;
+      const int bw = csm_gemm_box_rows_w();
+      if (csm_tmap_2d(&L.tm_qkv, L.qkv, nq + 2 * nkv, H, H, bw) || csm_tmap_2d(&L.tm_o, L.o, H, nq, nq, bw) ||
+          csm_tmap_2d(&L.tm_gu, L.gu, 2 * I, H, H, bw) || csm_tmap_2d(&L.tm_down, L.down, H, I, I, bw))
+        return fail(ctx, CSM_ECUDA, "cuTensorMapEncodeTiled failed for the layer %d weights", l);
     }
     PackSrc s;
     memset(&s, 0, sizeof s);
@@ -566,39 +573,53 @@ int launch_frame(CsmCtx* ctx, int B, int ph_begin, int ph_end, const long long* 
   return 0;
 }
 
-int gemm_bf16(CsmCtx* ctx, const bf16* x, int lda, const bf16* W, int N, int K, bf16* y, int ldc, int R,
-              cudaStream_t st) {
-  // row-major y[R,N] = x[R,K] * W[N,K]^T, fp32 accumulation, bf16 output (nn.Linear, no bias)
-  const float alpha = 1.f, beta = 0.f;
-  cublasStatus_t s = cublasSetStream(ctx->cublas, st);
-  if (s != CUBLAS_STATUS_SUCCESS) return fail(ctx, CSM_ECUDA, "cublasSetStream: %d", (int)s);
-  s = cublasGemmEx(ctx->cublas, CUBLAS_OP_T, CUBLAS_OP_N, N, R, K, &alpha, W, CUDA_R_16BF, K, x, CUDA_R_16BF, lda, &beta,
-                   y, CUDA_R_16BF, ldc, CUBLAS_COMPUTE_32F, CUBLAS_GEMM_DEFAULT);
-  if (s != CUBLAS_STATUS_SUCCESS) return fail(ctx, CSM_ECUDA, "cublasGemmEx(%d,%d,%d): %d", N, R, K, (int)s);
-  return 0;   // library kernels are not counted in ctx->launches (that counter is OUR kernels only)
+// C[R,N] = A[R,K] * W[N,K]^T on the tcgen05 path (csm_gemm.cu).  `map_w`: tensor map of W made at create time;
+// the map of A is encoded here (host-side, no driver call that touches the device).
+int gemm_tc(CsmCtx* ctx, const bf16* A, int lda, const CUtensorMap* map_w, GemmParams g, cudaStream_t st) {
+  CUtensorMap map_a;
+  if (csm_tmap_2d(&map_a, A, g.R, g.K, lda, csm_gemm_box_rows_a()))
+    return fail(ctx, CSM_ECUDA, "cuTensorMapEncodeTiled failed for an activation matrix [%d,%d]", g.R, g.K);
+  CK(csm_gemm_launch(&map_a, map_w, &g, ctx->sms, st));
+  ctx->launches += 1;
+  return 0;
 }
 
 int ensure_prefill_ws(CsmCtx* ctx, int rows) {
   if (rows <= ctx->pf_rows) return 0;
   const StackDims& d = ctx->bb.d;
   const size_t W = (size_t)(d.heads + 2 * d.kv) * d.hd;
-  // (old buffers stay in ctx->allocs and are released at destroy; growth happens at most a few times)
+  // growth: the outgrown buffers are released first (nothing is in flight on them: prefill calls are stream-ordered
+  // and the previous call's kernels were enqueued before this cudaFree, which synchronises)
+  bf16** bufs[] = {&ctx->pf_h, &ctx->pf_hn, &ctx->pf_qkv, &ctx->pf_attn, &ctx->pf_act};
+  for (bf16** b : bufs) {
+    if (*b) CK(cudaFree(*b));
+    *b = nullptr;
+  }
+  if (ctx->pf_valid) CK(cudaFree(ctx->pf_valid));
+  ctx->pf_valid = nullptr;
+  ctx->pf_rows = 0;
+  CK(cudaMalloc(&ctx->pf_h, (size_t)rows * d.H * 2));
+  CK(cudaMalloc(&ctx->pf_hn, (size_t)rows * d.H * 2));
+  CK(cudaMalloc(&ctx->pf_qkv, (size_t)rows * W * 2));
+  CK(cudaMalloc(&ctx->pf_attn, (size_t)rows * d.heads * d.hd * 2));
+  CK(cudaMalloc(&ctx->pf_act, (size_t)rows * d.I * 2));
+  CK(cudaMalloc(&ctx->pf_valid, (size_t)rows));
   ctx->pf_rows = rows;
-  DA(ctx->pf_h, (size_t)rows * d.H);
-  DA(ctx->pf_hn, (size_t)rows * d.H);
-  DA(ctx->pf_qkv, (size_t)rows * W);
-  DA(ctx->pf_attn, (size_t)rows * d.heads * d.hd);
-  DA(ctx->pf_y, (size_t)rows * d.H);
-  DA(ctx->pf_gu, (size_t)rows * 2 * d.I);
-  DA(ctx->pf_act, (size_t)rows * d.I);
   return 0;
 }
 
 // Backbone over S new positions for sequences [0,B): fills the KV cache and leaves the last position's
-// residual-stream row (pre final-norm) in h_bb[b].
+// residual-stream row (pre final-norm) in h_bb[b].  Per layer: RMSNorm rows, q|k|v GEMM with the RoPE + KV-cache
+// write tail, causal GQA flash attention, o_proj GEMM with the residual tail, RMSNorm rows, gate|up GEMM with the
+// SwiGLU tail, down_proj GEMM with the residual tail -- seven launches, all of them kernels of this library
+// (hf LlamaDecoderLayer.forward, modeling_llama.py:303-332).
+// Padding (modeling_csm.py:337-342): frames whose 33 mask entries are all zero are hidden as KEYS in this call
+// (a query that sees no key gets a zero attention output, so a padded position stays exactly zero through every
+// layer and caches K = V = 0); decode steps attend to every cached position, padded ones included -- the reference's
+// behaviour.  Honoured for a prefill into an empty cache, which is how generate() runs it.
 int prefill(CsmCtx* ctx, const long long* ids, const int* mask, int B, int S, cudaStream_t st) {
   const StackDims& d = ctx->bb.d;
-  const int W = (d.heads + 2 * d.kv) * d.hd, nq = d.heads * d.hd, nkv = d.kv * d.hd;
+  const int W = (d.heads + 2 * d.kv) * d.hd, nq = d.heads * d.hd;
   int group = 16384 / S;
   if (group < 1) group = 1;
   if (group > B) group = B;
@@ -610,32 +631,40 @@ int prefill(CsmCtx* ctx, const long long* ids, const int* mask, int B, int S, cu
     const int R = nseq * S;
     const long long* gi = ids + (size_t)b0 * S * (CSM_NQ + 1);
     const int* gm = mask ? mask + (size_t)b0 * S * (CSM_NQ + 1) : nullptr;
+    const unsigned char* valid = nullptr;
+    if (gm && pos0 == 0) {
+      CK(csm_frame_valid_launch(gm, R, ctx->pf_valid, nullptr, st));
+      valid = ctx->pf_valid;
+      ctx->launches += 1;
+    }
     CK(csm_embed_sum_launch(gi, gm, 2, ctx->audio_emb, ctx->text_emb, ctx->V, d.H, ctx->pf_h, R, st));
+    ctx->launches += 1;
+    GemmParams g;
+    memset(&g, 0, sizeof g);
+    g.R = R;
     for (int l = 0; l < d.L; ++l) {
       LayerW& L = ctx->bb.layers[l];
       CK(csm_rmsnorm_rows_launch(ctx->pf_h, L.ln1, d.eps, d.H, ctx->pf_hn, R, st));
-      if ((r = gemm_bf16(ctx, ctx->pf_hn, d.H, L.q, nq, d.H, ctx->pf_qkv, W, R, st))) return r;
-      if ((r = gemm_bf16(ctx, ctx->pf_hn, d.H, L.k, nkv, d.H, ctx->pf_qkv + nq, W, R, st))) return r;
-      if ((r = gemm_bf16(ctx, ctx->pf_hn, d.H, L.v, nkv, d.H, ctx->pf_qkv + nq + nkv, W, R, st))) return r;
-      CK(csm_rope_kv_rows_launch(ctx->pf_qkv, S, pos0, b0, d.heads, d.kv, d.hd, ctx->bb.cos_t, ctx->bb.sin_t, ctx->kc_bb,
-                                 ctx->vc_bb, l, ctx->Bmax, ctx->Tcap, R, st));
+      g.N = W; g.K = d.H; g.epi = EPI_QKV; g.C = ctx->pf_qkv; g.ldc = W;
+      g.S = S; g.pos0 = pos0; g.b0 = b0; g.heads = d.heads; g.kv = d.kv; g.layer = l; g.Bmax = ctx->Bmax; g.Tcap = ctx->Tcap;
+      g.kc = ctx->kc_bb; g.vc = ctx->vc_bb; g.cos_t = ctx->bb.cos_t; g.sin_t = ctx->bb.sin_t;
+      if ((r = gemm_tc(ctx, ctx->pf_hn, d.H, &L.tm_qkv, g, st))) return r;
       CK(csm_flash_prefill_launch(ctx->pf_qkv, S, pos0, b0, nseq, d.heads, d.kv, ctx->kc_bb, ctx->vc_bb, l, ctx->Bmax,
-                                  ctx->Tcap, d.scale, ctx->pf_attn, st));
-      if ((r = gemm_bf16(ctx, ctx->pf_attn, nq, L.o, d.H, nq, ctx->pf_y, d.H, R, st))) return r;
-      CK(csm_add_rows_launch(ctx->pf_h, ctx->pf_y, (long long)R * d.H, st));
+                                  ctx->Tcap, d.scale, valid, ctx->pf_attn, st));
+      g.N = d.H; g.K = nq; g.epi = EPI_RESID; g.C = ctx->pf_h; g.ldc = d.H;
+      if ((r = gemm_tc(ctx, ctx->pf_attn, nq, &L.tm_o, g, st))) return r;
       CK(csm_rmsnorm_rows_launch(ctx->pf_h, L.ln2, d.eps, d.H, ctx->pf_hn, R, st));
-      if ((r = gemm_bf16(ctx, ctx->pf_hn, d.H, L.gate, d.I, d.H, ctx->pf_gu, 2 * d.I, R, st))) return r;
-      if ((r = gemm_bf16(ctx, ctx->pf_hn, d.H, L.up, d.I, d.H, ctx->pf_gu + d.I, 2 * d.I, R, st))) return r;
-      CK(csm_swiglu_rows_launch(ctx->pf_gu, d.I, ctx->pf_act, R, st));
-      if ((r = gemm_bf16(ctx, ctx->pf_act, d.I, L.down, d.H, d.I, ctx->pf_y, d.H, R, st))) return r;
-      CK(csm_add_rows_launch(ctx->pf_h, ctx->pf_y, (long long)R * d.H, st));
-      ctx->launches += 7;
+      g.N = 2 * d.I; g.K = d.H; g.epi = EPI_SWIGLU; g.C = ctx->pf_act; g.ldc = d.I;
+      if ((r = gemm_tc(ctx, ctx->pf_hn, d.H, &L.tm_gu, g, st))) return r;
+      g.N = d.H; g.K = d.I; g.epi = EPI_RESID; g.C = ctx->pf_h; g.ldc = d.H;
+      if ((r = gemm_tc(ctx, ctx->pf_act, d.I, &L.tm_down, g, st))) return r;
+      ctx->launches += 3;
     }
     // hand the last position's residual row to the frame kernel as tagged words of the last backbone phase
     for (int rr = 0; rr < ctx->repl; ++rr)
       CK(csm_take_last_rows_launch(ctx->pf_h, S, d.H, ctx->h_bb + (size_t)rr * ctx->Bmax * d.H, b0, nseq,
                                    (ctx->tagbase + (unsigned)(ctx->ph_head_c0 - 1)) & 0xffffu, st));
-    ctx->launches += 2;
+    ctx->launches += 1;
   }
   return 0;
 }
@@ -723,10 +752,17 @@ int csm_create(const CsmShapes* sh, const CsmWeights* w, int max_batch, int max_
   if ((r = pack_matrix(ctx, &ctx->p_proj, one_src((const bf16*)w->projection, Hd, Hb, 1), nullptr, Hd, Hb, 1, st))) return r;
   // projection applied once to the whole audio table (modeling_csm.py:564-565 applies it to one gathered row per
   // codebook and frame: the same function of the same row, so it is folded into a [32*V, Hd] table)
-  if (cublasCreate(&ctx->cublas) != CUBLAS_STATUS_SUCCESS) return fail(ctx, CSM_ECUDA, "cublasCreate failed");
   DA(ctx->proj_table, (size_t)sh->audio_vocab * CSM_NQ * Hd);
-  if ((r = gemm_bf16(ctx, ctx->audio_emb, Hb, (const bf16*)w->projection, Hd, Hb, ctx->proj_table, Hd, sh->audio_vocab * CSM_NQ, st)))
-    return r;
+  {
+    CUtensorMap tm_proj;
+    if (csm_tmap_2d(&tm_proj, w->projection, Hd, Hb, Hb, csm_gemm_box_rows_w()))
+      return fail(ctx, CSM_ECUDA, "cuTensorMapEncodeTiled failed for the projection weight");
+    GemmParams g;
+    memset(&g, 0, sizeof g);
+    g.R = sh->audio_vocab * CSM_NQ; g.N = Hd; g.K = Hb; g.epi = EPI_STORE; g.C = ctx->proj_table; g.ldc = Hd;
+    if ((r = gemm_tc(ctx, ctx->audio_emb, Hb, &tm_proj, g, st))) return r;
+    CK(cudaStreamSynchronize(st));   // (tm_proj lives on this stack frame)
+  }
   if ((r = pack_matrix(ctx, &ctx->p_c0, one_src((const bf16*)w->codebook0_head, ctx->V, Hb, 1), nullptr, ctx->V, Hb, 1, st)))
     return r;
   ctx->p_heads.resize(CSM_NQ - 1);
@@ -810,7 +846,9 @@ int csm_destroy(CsmCtx* ctx) {
   if (ctx->st_ids) cudaFree(ctx->st_ids);
   if (ctx->st_mask) cudaFree(ctx->st_mask);
   if (ctx->st_frames) cudaFree(ctx->st_frames);
-  if (ctx->cublas) cublasDestroy(ctx->cublas);
+  bf16* pf[] = {ctx->pf_h, ctx->pf_hn, ctx->pf_qkv, ctx->pf_attn, ctx->pf_act};
+  for (bf16* b : pf) if (b) cudaFree(b);
+  if (ctx->pf_valid) cudaFree(ctx->pf_valid);
   if (ctx->ev0) cudaEventDestroy(ctx->ev0);
   if (ctx->ev1) cudaEventDestroy(ctx->ev1);
   delete ctx;
@@ -1064,6 +1102,22 @@ int csm_sample_topk(const void* logits, int rows, int V, int topk, float tempera
   cudaError_t e = csm_sample_rows_launch((const bf16*)logits, rows, V, topk, 1.f / temperature, seed, (long long*)out,
                                          (cudaStream_t)stream);
   return e == cudaSuccess ? CSM_OK : CSM_ECUDA;
+}
+
+int csm_linear(const void* x, int ldx, const void* W, int R, int N, int K, int tail, void* C, int ldc, void* stream) {
+  if (!x || !W || !C || R < 0 || N < 64 || K < 64 || (N % 64) || (K % 64) || tail < 0 || tail > 2) return CSM_EINVAL;
+  if (R == 0) return CSM_OK;
+  int dev = 0, sms = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess || cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess)
+    return CSM_ECUDA;
+  CUtensorMap ma, mw;
+  if (csm_tmap_2d(&ma, x, R, K, ldx, csm_gemm_box_rows_a()) || csm_tmap_2d(&mw, W, N, K, K, csm_gemm_box_rows_w()))
+    return CSM_ECUDA;
+  GemmParams g;
+  memset(&g, 0, sizeof g);
+  g.R = R; g.N = N; g.K = K; g.epi = tail == 0 ? EPI_STORE : (tail == 1 ? EPI_RESID : EPI_SWIGLU);
+  g.C = (bf16*)C; g.ldc = ldc;
+  return csm_gemm_launch(&ma, &mw, &g, sms, (cudaStream_t)stream) == cudaSuccess ? CSM_OK : CSM_ECUDA;
 }
 
 int csm_debug_progress(CsmCtx* ctx, int32_t* host_out, void* side_stream) {

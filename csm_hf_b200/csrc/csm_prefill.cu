@@ -1,8 +1,8 @@
 // Context prefill kernels: the first CSMModel.forward call of generate() (modeling_csm.py:508-517 with
 // S = T context frames).  Row-parallel kernels around the dense projections: masked 33-way
-// embedding gather-sum, RMSNorm, RoPE + KV-cache write, causal GQA flash attention on
-// mma.sync tensor cores, SwiGLU, residual add.  The projections themselves are plain GEMMs
-// (csm_api.cu: csm_gemm_bf16).
+// embedding gather-sum, RMSNorm, causal GQA flash attention on mma.sync tensor cores (padding-aware).
+// The projections themselves, with RoPE + KV-cache write, SwiGLU and the residual adds fused into their
+// tails, are the tcgen05 GEMMs of csm_gemm.cu.
 #include "csm_common.cuh"
 #include "csm_sample.cuh"
 
@@ -91,64 +91,27 @@ __global__ void csm_rmsnorm_rows_kernel(const bf16* __restrict__ x, const bf16* 
   }
 }
 
-// ---------------------------------------------------------------- RoPE + KV-cache write for prefill rows
-// qkv rows [(b,s)][q | k | v] in natural feature order.  q is rotated in place, k rotated into the
-// cache, v copied (apply_rotary_pos_emb, hf modeling_llama.py:146-168; DynamicCache.update,
-// hf cache_utils.py:102-121 -- here a write at the position instead of a concat).
-__global__ void csm_rope_kv_rows_kernel(bf16* __restrict__ qkv, int S, int pos0, int b0, int heads, int kv, int hd,
-                                        const bf16* __restrict__ cos_t, const bf16* __restrict__ sin_t,
-                                        bf16* __restrict__ kc, bf16* __restrict__ vc, int layer, int Bmax, int Tcap,
-                                        int rows) {
-  const int r = blockIdx.x;
+// ---------------------------------------------------------------- gate / up rows interleaved (create time)
+// dst row 2j = a row j (gate_j), dst row 2j+1 = b row j (up_j): a GEMM tile of the interleaved matrix holds both halves
+// of SwiGLU for its columns (csm_gemm.cu, EPI_SWIGLU).
+__global__ void csm_interleave_rows_kernel(const bf16* __restrict__ a, const bf16* __restrict__ b, int K,
+                                           bf16* __restrict__ dst) {
+  const int j = blockIdx.x;
+  const uint4* sa = reinterpret_cast<const uint4*>(a + (size_t)j * K);
+  const uint4* sb = reinterpret_cast<const uint4*>(b + (size_t)j * K);
+  uint4* da = reinterpret_cast<uint4*>(dst + (size_t)(2 * j) * K);
+  uint4* db = reinterpret_cast<uint4*>(dst + (size_t)(2 * j + 1) * K);
+  for (int i = threadIdx.x; i < K / 8; i += blockDim.x) { da[i] = sa[i]; db[i] = sb[i]; }
+}
+
+// ---------------------------------------------------------------- frame-valid bytes of a padded batch
+// valid[r] = any(mask[r][0..32] != 0)  (modeling_csm.py:337-342: hf_attention_mask = mask.sum(-1) > 0)
+__global__ void csm_frame_valid_kernel(const int* __restrict__ mask, int rows, unsigned char* __restrict__ valid) {
+  const int r = blockIdx.x * blockDim.x + threadIdx.x;
   if (r >= rows) return;
-  const int b = b0 + r / S, s = r % S, pos = pos0 + s;
-  const int half = hd / 2;
-  const int width = (heads + 2 * kv) * hd;
-  bf16* row = qkv + (size_t)r * width;
-  const int npairs = (heads + kv) * half;
-  for (int pidx = threadIdx.x; pidx < npairs + kv * half; pidx += blockDim.x) {
-    if (pidx < npairs) {
-      const bool isq = pidx < heads * half;
-      const int pp = isq ? pidx : pidx - heads * half;
-      const int head = pp / half, i = pp % half;
-      bf16* src = row + (isq ? 0 : heads * hd) + head * hd + i;
-      const float x1 = __bfloat162float(src[0]), x2 = __bfloat162float(src[half]);
-      const float cs = __bfloat162float(cos_t[(size_t)pos * half + i]);
-      const float sn = __bfloat162float(sin_t[(size_t)pos * half + i]);
-      const float o1 = bfround(bfround(x1 * cs) + bfround(-x2 * sn));
-      const float o2 = bfround(bfround(x2 * cs) + bfround(x1 * sn));
-      bf16* dst = isq ? src : kc + ((((size_t)layer * Bmax + b) * kv + head) * Tcap + pos) * hd + i;
-      dst[0] = __float2bfloat16_rn(o1);
-      dst[half] = __float2bfloat16_rn(o2);
-    } else {
-      const int f = (pidx - npairs) * 2;
-      const int head = f / hd, d = f % hd;
-      const uint32_t v = *reinterpret_cast<const uint32_t*>(row + (heads + kv) * hd + f);
-      *reinterpret_cast<uint32_t*>(vc + ((((size_t)layer * Bmax + b) * kv + head) * Tcap + pos) * hd + d) = v;
-    }
-  }
-}
-
-// ---------------------------------------------------------------- SwiGLU rows: act = bf16(silu(gate)) * up
-__global__ void csm_swiglu_rows_kernel(const bf16* __restrict__ gu, int I, bf16* __restrict__ act, long long n2) {
-  // gu rows are [gate(I) | up(I)]; n2 = rows * I / 2 pairs
-  for (long long e = (long long)blockIdx.x * blockDim.x + threadIdx.x; e < n2; e += (long long)gridDim.x * blockDim.x) {
-    const long long r = e / (I / 2);
-    const int j2 = (int)(e % (I / 2));
-    const uint32_t g = reinterpret_cast<const uint32_t*>(gu + (size_t)r * 2 * I)[j2];
-    const uint32_t u = reinterpret_cast<const uint32_t*>(gu + (size_t)r * 2 * I + I)[j2];
-    const float g0 = bf_lo(g), g1 = bf_hi(g);
-    const float s0 = bfround(g0 / (1.f + expf(-g0))), s1 = bfround(g1 / (1.f + expf(-g1)));
-    reinterpret_cast<uint32_t*>(act + (size_t)r * I)[j2] = pack_bf16(s0 * bf_lo(u), s1 * bf_hi(u));
-  }
-}
-
-// ---------------------------------------------------------------- residual add: h = bf16(h + y)
-__global__ void csm_add_rows_kernel(bf16* __restrict__ h, const bf16* __restrict__ y, long long n2) {
-  for (long long e = (long long)blockIdx.x * blockDim.x + threadIdx.x; e < n2; e += (long long)gridDim.x * blockDim.x) {
-    const uint32_t a = reinterpret_cast<const uint32_t*>(h)[e], b = reinterpret_cast<const uint32_t*>(y)[e];
-    reinterpret_cast<uint32_t*>(h)[e] = pack_bf16(bf_lo(a) + bf_lo(b), bf_hi(a) + bf_hi(b));
-  }
+  int any = 0;
+  for (int s = 0; s <= CSM_NQ; ++s) any |= mask[(size_t)r * (CSM_NQ + 1) + s];
+  valid[r] = any != 0;
 }
 
 // ---------------------------------------------------------------- the last position's hidden row per sequence,
@@ -191,10 +154,13 @@ __device__ __forceinline__ void ldmatrix_x2_trans(uint32_t& r0, uint32_t& r1, co
 __global__ void __launch_bounds__(128) csm_flash_prefill_kernel(const bf16* __restrict__ qkv, int S, int pos0, int b0,
                                                                 int heads, int kv, const bf16* __restrict__ kc,
                                                                 const bf16* __restrict__ vc, int layer, int Bmax,
-                                                                int Tcap, float scale, bf16* __restrict__ out) {
+                                                                int Tcap, float scale,
+                                                                const unsigned char* __restrict__ valid,
+                                                                bf16* __restrict__ out) {
   constexpr int HD = 64, BQ = 64, BK = 64, LDS = 72;
   __shared__ __align__(16) bf16 sK[BK * LDS];
   __shared__ __align__(16) bf16 sV[BK * LDS];
+  __shared__ unsigned char sOk[BK];   // padded batches: key of this block visible (valid == null: all visible)
   const int qt = blockIdx.x, head = blockIdx.y, bl = blockIdx.z;
   const int b = b0 + bl;
   const int kvh = head / (heads / kv);
@@ -238,6 +204,10 @@ __global__ void __launch_bounds__(128) csm_flash_prefill_kernel(const bf16* __re
       *reinterpret_cast<uint4*>(sK + kr * LDS + c8 * 8) = kv4;
       *reinterpret_cast<uint4*>(sV + kr * LDS + c8 * 8) = vv4;
     }
+    if (threadIdx.x < BK) {
+      const int kk = k0 + (int)threadIdx.x - pos0;   // sequence-local index of the key (valid covers this call's rows)
+      sOk[threadIdx.x] = (valid == nullptr || kk < 0 || kk >= S) ? 1 : valid[(size_t)bl * S + kk];
+    }
     __syncthreads();
     if (k0 > pos0 + q0 + 15) continue;   // whole block is in this warp's future
     float sc[8][4];
@@ -258,10 +228,11 @@ __global__ void __launch_bounds__(128) csm_flash_prefill_kernel(const bf16* __re
 #pragma unroll
     for (int j = 0; j < 8; ++j) {
       const int key = k0 + 8 * j + 2 * t;
-      if (key > p_lo) sc[j][0] = -INFINITY;
-      if (key + 1 > p_lo) sc[j][1] = -INFINITY;
-      if (key > p_hi) sc[j][2] = -INFINITY;
-      if (key + 1 > p_hi) sc[j][3] = -INFINITY;
+      const bool ok0 = sOk[8 * j + 2 * t] != 0, ok1 = sOk[8 * j + 2 * t + 1] != 0;
+      if (key > p_lo || !ok0) sc[j][0] = -INFINITY;
+      if (key + 1 > p_lo || !ok1) sc[j][1] = -INFINITY;
+      if (key > p_hi || !ok0) sc[j][2] = -INFINITY;
+      if (key + 1 > p_hi || !ok1) sc[j][3] = -INFINITY;
       mx_lo = fmaxf(mx_lo, fmaxf(sc[j][0], sc[j][1]));
       mx_hi = fmaxf(mx_hi, fmaxf(sc[j][2], sc[j][3]));
     }
@@ -303,7 +274,8 @@ __global__ void __launch_bounds__(128) csm_flash_prefill_kernel(const bf16* __re
   l_lo += __shfl_xor_sync(0xffffffffu, l_lo, 2);
   l_hi += __shfl_xor_sync(0xffffffffu, l_hi, 1);
   l_hi += __shfl_xor_sync(0xffffffffu, l_hi, 2);
-  const float i_lo = 1.f / l_lo, i_hi = 1.f / l_hi;
+  // a query that saw no key at all (a padded frame) gets a zero output, as torch's SDPA returns for a fully masked row
+  const float i_lo = l_lo > 0.f ? 1.f / l_lo : 0.f, i_hi = l_hi > 0.f ? 1.f / l_hi : 0.f;
   bf16* olo = out + ((size_t)bl * S + r_lo) * (heads * HD) + head * HD;
   bf16* ohi = out + ((size_t)bl * S + r_hi) * (heads * HD) + head * HD;
 #pragma unroll
@@ -356,25 +328,13 @@ cudaError_t csm_rmsnorm_rows_launch(const bf16* x, const bf16* w, float eps, int
   csm_rmsnorm_rows_kernel<<<(rows + 7) / 8, 256, 0, st>>>(x, w, eps, H, y, rows);
   return cudaGetLastError();
 }
-cudaError_t csm_rope_kv_rows_launch(bf16* qkv, int S, int pos0, int b0, int heads, int kv, int hd, const bf16* cos_t,
-                                    const bf16* sin_t, bf16* kc, bf16* vc, int layer, int Bmax, int Tcap, int rows,
-                                    cudaStream_t st) {
-  csm_rope_kv_rows_kernel<<<rows, 256, 0, st>>>(qkv, S, pos0, b0, heads, kv, hd, cos_t, sin_t, kc, vc, layer, Bmax, Tcap,
-                                                rows);
+cudaError_t csm_interleave_rows_launch(const bf16* a, const bf16* b, int rows, int K, bf16* dst, cudaStream_t st) {
+  csm_interleave_rows_kernel<<<rows, 256, 0, st>>>(a, b, K, dst);
   return cudaGetLastError();
 }
-cudaError_t csm_swiglu_rows_launch(const bf16* gu, int I, bf16* act, long long rows, cudaStream_t st) {
-  long long n2 = rows * (I / 2);
-  long long blocks = (n2 + 255) / 256;
-  if (blocks > 148 * 32) blocks = 148 * 32;
-  csm_swiglu_rows_kernel<<<(int)blocks, 256, 0, st>>>(gu, I, act, n2);
-  return cudaGetLastError();
-}
-cudaError_t csm_add_rows_launch(bf16* h, const bf16* y, long long n, cudaStream_t st) {
-  long long n2 = n / 2;
-  long long blocks = (n2 + 255) / 256;
-  if (blocks > 148 * 32) blocks = 148 * 32;
-  csm_add_rows_kernel<<<(int)blocks, 256, 0, st>>>(h, y, n2);
+cudaError_t csm_frame_valid_launch(const int* mask, int rows, unsigned char* valid, int* any_pad, cudaStream_t st) {
+  (void)any_pad;
+  csm_frame_valid_kernel<<<(rows + 255) / 256, 256, 0, st>>>(mask, rows, valid);
   return cudaGetLastError();
 }
 cudaError_t csm_take_last_rows_launch(const bf16* h, int S, int H, uint32_t* dst, int b0, int nseq, uint32_t tag,
@@ -396,9 +356,9 @@ cudaError_t csm_i32_to_i64_launch(const int* src, long long* dst, int n, cudaStr
 }
 cudaError_t csm_flash_prefill_launch(const bf16* qkv, int S, int pos0, int b0, int nseq, int heads, int kv,
                                      const bf16* kc, const bf16* vc, int layer, int Bmax, int Tcap, float scale,
-                                     bf16* out, cudaStream_t st) {
+                                     const unsigned char* valid, bf16* out, cudaStream_t st) {
   dim3 grid((S + 63) / 64, heads, nseq);
-  csm_flash_prefill_kernel<<<grid, 128, 0, st>>>(qkv, S, pos0, b0, heads, kv, kc, vc, layer, Bmax, Tcap, scale, out);
+  csm_flash_prefill_kernel<<<grid, 128, 0, st>>>(qkv, S, pos0, b0, heads, kv, kc, vc, layer, Bmax, Tcap, scale, valid, out);
   return cudaGetLastError();
 }
 

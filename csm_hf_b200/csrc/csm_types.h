@@ -142,6 +142,18 @@ struct StreamParams {
                                 // phase of the weight stream, phase of the L2 prefetcher -- read by a watchdog on a hang
 };
 
+// One dense projection of the context prefill on the tcgen05 path (csm_gemm.cu): C[R,N] = A[R,K] * W[N,K]^T + fused tail.
+struct GemmParams {
+  int R, N, K;
+  int epi;                      // EPI_STORE / EPI_RESID / EPI_SWIGLU / EPI_QKV
+  bf16* C;                      // STORE / RESID: [R, ldc]; SWIGLU: [R, ldc] with N/2 columns; QKV: rotated q rows [R, ldc]
+  int ldc;
+  // EPI_QKV: row r = (sequence b0 + r / S, position pos0 + r % S); k and v go to the cache [L][Bmax][kv][Tcap][64]
+  int S, pos0, b0, heads, kv, layer, Bmax, Tcap;
+  bf16 *kc, *vc;
+  const bf16 *cos_t, *sin_t;    // [n_pos][32]
+};
+
 // Row split and chunking of one weight matrix for one CTA.
 struct Geom {
   int row0, rows;     // packed rows owned by this CTA

@@ -7,12 +7,19 @@ and streams only; every arithmetic step of the path runs in libcsm_b200.so (ctyp
 include/csm_b200.h).  There is no CPU or eager fallback: without the library or a B200 the
 constructor of the engine raises.
 
+`CSMModel` is an `nn.Module` whose parameter tree has the reference's attribute names
+(`backbone.layers[i].self_attn.q_proj.weight`, `text_embeddings.weight`, `audio_head`, ... --
+modeling_csm.py:222-240) and therefore the reference's 187 `state_dict()` keys; the sub-modules hold
+parameters only (their arithmetic lives in the engine), so `.to()`, `.parameters()`,
+`load_state_dict()` and `state_dict()` behave as on the reference.
+
 Differences from the reference, all deliberate and documented in DESIGN.md:
   * `temperature == 0` (or the reference's own spelling, `topk == 1`) is greedy decoding with
     ties broken to the lowest index (the reference breaks them randomly);
   * stochastic top-k sampling draws with counter-based noise seeded from `torch.initial_seed()`
     instead of torch's global generator: same distribution, different stream;
-  * padded (left-padded) batches raise NotImplementedError (N3);
+  * a float32 attention mask (what CSMProcessor emits when it pads, processor.py:148) is accepted with a
+    bf16 model (the reference raises a dtype error there, SURVEY.md fact 5);
   * `past_key_values` is an opaque handle to the engine's in-place KV cache;
   * `labels` (training) raises NotImplementedError (N1).
 """
@@ -35,13 +42,33 @@ _LAYER_KEYS = ["self_attn.q_proj.weight", "self_attn.k_proj.weight", "self_attn.
 
 
 class KVHandle:
-    """What `past_key_values` is on this path: a token for the engine-owned cache."""
+    """What `past_key_values` is on this path: a token for the engine-owned cache.  It is valid for the next
+    call only: the cache it names is overwritten in place (the reference returns a new DynamicCache state
+    each step, modeling_csm.py:653,659)."""
 
-    def __init__(self, model: "CSMModel", length: int, batch: int):
-        self.model, self.length, self.batch = model, length, batch
+    def __init__(self, model: "CSMModel", length: int, batch: int, serial: int):
+        self.model, self.length, self.batch, self.serial = model, length, batch, serial
 
     def get_seq_length(self) -> int:
         return self.length
+
+
+class _Params(torch.nn.Module):
+    """A node of the reference's module tree that only holds parameters (`backbone`, `layers[i]`, `self_attn`,
+    `q_proj`, ... -- modeling_csm.py:156-167,222-240).  Indexable where the reference has a ModuleList."""
+
+    def __getitem__(self, i):
+        return getattr(self, str(i))
+
+    def __len__(self):
+        return len(self._modules)
+
+    def __iter__(self):
+        return iter(self._modules.values())
+
+    def forward(self, *a, **k):
+        raise NotImplementedError("sub-modules of the B200 CSMModel hold parameters only; call generate / "
+                                  "generate_frame / forward on the model (the arithmetic runs in libcsm_b200.so)")
 
 
 class _Engine:
@@ -127,7 +154,7 @@ class _Engine:
         return int(self.lib.csm_info(self.ctx, what))
 
 
-class CSMModel:
+class CSMModel(torch.nn.Module):
     """Drop-in for the reference CSMModel on the generation path."""
 
     config_class = CSMConfig
@@ -135,20 +162,39 @@ class CSMModel:
 
     def __init__(self, config: CSMConfig, state_dict: Optional[Dict[str, torch.Tensor]] = None,
                  device: Optional[torch.device] = None, max_batch: int = 1, max_ctx: Optional[int] = None):
+        super().__init__()
         self.config = config
-        self.device = torch.device(device) if device is not None else torch.device("cuda", 0)
-        self.dtype = torch.bfloat16
-        self._sd: Dict[str, torch.Tensor] = {}
+        self._device = torch.device(device) if device is not None else torch.device("cuda", 0)
         self._engine: Optional[_Engine] = None
         self._max_batch = max_batch
         self._max_ctx = max_ctx or max(4096, config.max_seq_len + 512)
         self._using_kv_cache = False
         self._kv: Optional[KVHandle] = None
+        self._kv_serial = 0
+        self._loaded = False
         if state_dict is not None:
             self.load_state_dict(state_dict)
 
     # ------------------------------------------------------------------ weights
-    def load_state_dict(self, state_dict: Dict[str, torch.Tensor], strict: bool = True):
+    @property
+    def device(self) -> torch.device:
+        return self._device
+
+    @property
+    def dtype(self) -> torch.dtype:
+        return torch.bfloat16
+
+    def _set_param(self, key: str, t: torch.Tensor):
+        node = self
+        parts = key.split(".")
+        for name in parts[:-1]:
+            if name not in node._modules:
+                node.add_module(name, _Params())
+            node = node._modules[name]
+        node._parameters[parts[-1]] = torch.nn.Parameter(t, requires_grad=False)
+
+    def load_state_dict(self, state_dict: Dict[str, torch.Tensor], strict: bool = True, assign: bool = False):
+        """The reference's 187 keys; tensors are converted to bf16 on the model's device."""
         want = state_dict_shapes(self.config)
         missing = [k for k in want if k not in state_dict]
         unexpected = [k for k in state_dict if k not in want and "rotary_emb" not in k]
@@ -159,12 +205,19 @@ class CSMModel:
                 t = state_dict[k]
                 if tuple(t.shape) != tuple(shape):
                     raise RuntimeError(f"size mismatch for {k}: {tuple(t.shape)} vs {tuple(shape)}")
-                self._sd[k] = t.detach().to(device=self.device, dtype=torch.bfloat16).contiguous()
+                self._set_param(k, t.detach().to(device=self._device, dtype=torch.bfloat16).contiguous())
+        self._loaded = len(dict(self.named_parameters())) == len(want)
         self._drop_engine()
-        return missing, unexpected
+        return torch.nn.modules.module._IncompatibleKeys(missing, unexpected)
 
-    def state_dict(self) -> Dict[str, torch.Tensor]:
-        return dict(self._sd)
+    def _apply(self, fn, *a, **k):
+        """.to() / .cuda() / .bfloat16(): move the parameters, then rebuild the engine lazily on the new device."""
+        out = super()._apply(fn, *a, **k)
+        for p in self.parameters():
+            self._device = p.device
+            break
+        self._drop_engine()
+        return out
 
     @classmethod
     def from_reference(cls, ref_model, device=None, **kw) -> "CSMModel":
@@ -194,22 +247,15 @@ class CSMModel:
         with open(os.path.join(path, "config.json"), "w") as f:
             json.dump(self.config.to_dict(), f, indent=1)
         from safetensors.torch import save_file
-        save_file({k: v.cpu().contiguous() for k, v in self._sd.items()}, os.path.join(path, "model.safetensors"))
-
-    def to(self, *a, **k):
-        return self
-
-    def eval(self):
-        return self
-
-    def parameters(self):
-        return iter(self._sd.values())
+        save_file({k: v.detach().cpu().contiguous() for k, v in self.state_dict().items()},
+                  os.path.join(path, "model.safetensors"))
 
     # ------------------------------------------------------------------ engine
     def _drop_engine(self):
-        if self._engine is not None:
+        if getattr(self, "_engine", None) is not None:
             self._engine.close()
         self._engine, self._kv = None, None
+        self._kv_serial = getattr(self, "_kv_serial", 0) + 1     # handles issued by the old engine are dead
 
     def engine(self, batch: int = 1, ctx_len: int = 0) -> _Engine:
         need_b, need_t = max(batch, self._max_batch), max(ctx_len, self._max_ctx)
@@ -217,11 +263,11 @@ class CSMModel:
             raise ValueError(f"batch {need_b} > 32 sequences per GPU: shard the batch (csm_hf_b200.dist.generate_sharded)")
         e = self._engine
         if e is None or e.max_batch < need_b or e.max_ctx < need_t:
-            if len(self._sd) != len(state_dict_shapes(self.config)):
+            if not self._loaded:
                 raise RuntimeError("CSMModel has no weights: load_state_dict / from_pretrained first")
             self._drop_engine()
             self._max_batch, self._max_ctx = need_b, need_t
-            self._engine = _Engine(self.config, self._sd, self.device, need_b, need_t)
+            self._engine = _Engine(self.config, dict(self.state_dict()), self.device, need_b, need_t)
         return self._engine
 
     def setup_caches(self, max_batch_size: int):
@@ -234,23 +280,24 @@ class CSMModel:
         if self._engine is not None:
             self._engine.call(self._engine.lib.csm_reset)
         self._kv = None
+        self._kv_serial += 1
 
     # ------------------------------------------------------------------ small gathers (API parity; not hot)
     def _embed_audio(self, codebook: int, tokens: torch.Tensor) -> torch.Tensor:
         """modeling_csm.py:247-259."""
-        return self._sd["audio_embeddings.weight"][tokens.to(self.device) + codebook * self.config.audio_vocab_size]
+        return self.audio_embeddings.weight[tokens.to(self.device) + codebook * self.config.audio_vocab_size]
 
     def _embed_tokens(self, tokens: torch.Tensor) -> torch.Tensor:
         """modeling_csm.py:261-282 -> [B,S,33,H]."""
         tokens = tokens.to(self.device)
         nq, V = self.config.audio_num_codebooks, self.config.audio_vocab_size
-        text = self._sd["text_embeddings.weight"][tokens[:, :, -1]].unsqueeze(-2)
-        aud = self._sd["audio_embeddings.weight"][tokens[:, :, :-1] + V * torch.arange(nq, device=self.device)]
+        text = self.text_embeddings.weight[tokens[:, :, -1]].unsqueeze(-2)
+        aud = self.audio_embeddings.weight[tokens[:, :, :-1] + V * torch.arange(nq, device=self.device)]
         return torch.cat([aud, text], dim=-2)
 
     def embed_sum(self, input_ids: torch.Tensor, attention_mask: Optional[torch.Tensor]) -> torch.Tensor:
         """Fused K1 kernel: sum over the 33 slots of mask*embedding (modeling_csm.py:327-334) -> [B,S,H] bf16."""
-        ids, mask = self._prep_inputs(input_ids, attention_mask, check=False)
+        ids, mask, _ = self._prep_inputs(input_ids, attention_mask, check=False, none_is_ones=False)
         B, S = ids.shape[:2]
         e = self.engine(B, 0)
         out = torch.empty(B, S, self.config.backbone_config.hidden_size, dtype=torch.bfloat16, device=self.device)
@@ -259,7 +306,10 @@ class CSMModel:
         return out
 
     # ------------------------------------------------------------------ input checks
-    def _prep_inputs(self, input_ids, attention_mask, check=True):
+    def _prep_inputs(self, input_ids, attention_mask, check=True, none_is_ones=True):
+        """-> (ids int64, mask int32, padded?) on the device.  attention_mask=None means "all 33 slots present", as
+        in the reference (modeling_csm.py:328-332: the mask multiply is skipped); the engine's own NULL convention
+        (audio slots only) is used for the decode rows generate() builds itself, never for a caller's None."""
         nq = self.config.audio_num_codebooks
         if input_ids.dim() != 3 or input_ids.shape[-1] != nq + 1:
             raise ValueError(f"input_ids must be [B, S, {nq + 1}]")
@@ -269,9 +319,14 @@ class CSMModel:
         if mask is not None:
             if mask.shape != input_ids.shape:
                 raise ValueError("attention_mask must have the shape of input_ids")
-            if mask.dtype.is_floating_point and mask.dtype != torch.bfloat16:
-                # the reference promotes embeds*mask to fp32 and its bf16 backbone raises
-                raise ValueError("attention_mask must be an integer (or bf16) mask for a bf16 model")
+            if mask.dtype.is_floating_point:
+                # CSMProcessor pads with a float32 zero mask (processor.py:148); the mask is a 0/1 indicator
+                if check and not bool(((mask == 0) | (mask == 1)).all()):
+                    raise ValueError("a floating-point attention_mask must hold 0 / 1 only")
+                mask = mask != 0
+        elif none_is_ones:
+            mask = torch.ones(input_ids.shape, dtype=torch.int32, device=input_ids.device)
+        padded = False
         if check:
             V, TV = self.config.audio_vocab_size, self.config.text_vocab_size
             m = torch.ones_like(input_ids) if mask is None else (mask != 0)
@@ -280,12 +335,12 @@ class CSMModel:
             badt = ((t < 0) | (t >= TV)) & (m[..., nq] != 0)
             if bool(bad.any()) or bool(badt.any()):
                 raise IndexError("token id out of range of the embedding tables")
-            if mask is not None and input_ids.shape[1] > 1 and not bool((mask != 0).any(dim=-1).all()):
-                raise NotImplementedError("padded frames (all-zero mask rows) are not on the accelerated path yet")
+            if mask is not None:
+                padded = not bool((mask != 0).any(dim=-1).all())
         ids = input_ids.to(device=self.device, dtype=torch.int64).contiguous()
         if mask is not None:
             mask = mask.to(device=self.device, dtype=torch.int32).contiguous()
-        return ids, mask
+        return ids, mask, padded
 
     def _set_sampling(self, e, temperature, topk, seq_base: int = 0):
         """sample_topk's arguments (modeling_csm.py:179-189) -> engine sampling mode.  Greedy when
@@ -311,7 +366,7 @@ class CSMModel:
         if output_attentions or output_hidden_states:
             raise NotImplementedError("output_attentions / output_hidden_states are not available on the fused path")
         return_dict = True if return_dict is None else return_dict
-        ids, mask = self._prep_inputs(input_ids, attention_mask)
+        ids, mask, padded = self._prep_inputs(input_ids, attention_mask)
         B, S = ids.shape[:2]
         e = self.engine(B, 0)
         self._set_sampling(e, temperature, topk, getattr(self, "seq_base", 0))
@@ -319,6 +374,14 @@ class CSMModel:
             e.call(e.lib.csm_reset)          # a call without a cache starts a new context
         elif not isinstance(past_key_values, KVHandle) or past_key_values.model is not self:
             raise ValueError("past_key_values must be the handle returned by this model's generate_frame")
+        else:
+            kv = past_key_values
+            if kv.serial != self._kv_serial or kv.batch != B or kv.length != e.call(e.lib.csm_cache_len):
+                raise ValueError("stale past_key_values: the engine's cache has moved on since this handle was issued "
+                                 "(another generate / generate_frame / reset_caches call, or a different batch size)")
+            if padded:
+                raise NotImplementedError("padding is only honoured in the first (prefill) call of a context, as in "
+                                          "the reference's generate()")
         start = e.call(e.lib.csm_cache_len)
         if start + S > e.max_ctx:
             e = self._grow_ctx(e, start + S)
@@ -333,7 +396,8 @@ class CSMModel:
         e.call(e.lib.csm_generate_frame, ids.data_ptr(), mask.data_ptr() if mask is not None else None, B, S,
                ft.data_ptr() if ft is not None else None, samples.data_ptr(), last_h.data_ptr(), c0.data_ptr(),
                cb.data_ptr() if cb is not None else None, e._stream())
-        self._kv = KVHandle(self, start + S, B)
+        self._kv_serial += 1
+        self._kv = KVHandle(self, start + S, B, self._kv_serial)
         if input_ids.device.type != "cuda":
             samples = samples.to(input_ids.device)
         if not return_dict:
@@ -359,7 +423,6 @@ class CSMModel:
             return (out.last_hidden_state, out.logits, out.past_key_values)
         return CSMOutput(last_hidden_state=out.last_hidden_state, logits=out.logits, past_key_values=out.past_key_values)
 
-    __call__ = forward
 
     # ------------------------------------------------------------------ generate
     def generate(self, input_ids: torch.Tensor, attention_mask: torch.Tensor, max_new_frames: int = 100,
@@ -370,7 +433,7 @@ class CSMModel:
         frames on the device, one D2H copy); CUDA inputs are consumed in place."""
         if not use_cache:
             raise NotImplementedError("use_cache=False loses the context in the reference itself (SURVEY.md fact 6)")
-        ids, mask = self._prep_inputs(input_ids, attention_mask) if input_ids.device.type == "cuda" else (None, None)
+        ids, mask, _ = self._prep_inputs(input_ids, attention_mask) if input_ids.device.type == "cuda" else (None, None, None)
         B, T = input_ids.shape[:2]
         e = self.engine(B, T + max_new_frames)
         self._set_sampling(e, temperature, topk, getattr(self, "seq_base", 0))
@@ -384,7 +447,8 @@ class CSMModel:
         else:
             self._prep_inputs(input_ids, attention_mask)   # validation only (host tensors)
             hi = input_ids.to(torch.int64).contiguous()
-            hm = attention_mask.to(torch.int32).contiguous() if attention_mask is not None else None
+            am = attention_mask if attention_mask is not None else torch.ones(input_ids.shape, dtype=torch.int32)
+            hm = (am != 0).to(torch.int32).contiguous() if am.dtype.is_floating_point else am.to(torch.int32).contiguous()
             if not hi.is_pinned():
                 hi = hi.pin_memory()
             if hm is not None and not hm.is_pinned():
@@ -395,6 +459,7 @@ class CSMModel:
                    max_new_frames, int(bool(stop_on_all_zeros)), frames.data_ptr(), C.byref(n_out), e._stream())
             n = n_out.value
         self._kv = None
+        self._kv_serial += 1
         return frames[:, :n].contiguous()
 
     def last_decode_ms(self):

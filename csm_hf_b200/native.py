@@ -16,7 +16,7 @@ EXPORTS = [
     "csm_create", "csm_destroy", "csm_reset", "csm_cache_len", "csm_embed_sum", "csm_generate_frame",
     "csm_generate", "csm_frames_done", "csm_generate_host", "csm_info", "csm_set_stepped",
     "csm_last_decode_ms", "csm_last_error", "csm_debug_copy", "csm_debug_run_phases", "csm_debug_set_cache_len",
-    "csm_debug_profile_frame", "csm_debug_progress", "csm_set_sampling", "csm_sample_topk",
+    "csm_debug_profile_frame", "csm_debug_progress", "csm_set_sampling", "csm_sample_topk", "csm_linear",
 ]
 
 
@@ -76,6 +76,7 @@ def load():
     lib.csm_debug_progress.argtypes = [vp, vp, vp]; lib.csm_debug_progress.restype = i32
     lib.csm_set_sampling.argtypes = [vp, i32, C.c_float, C.c_uint64, i32]; lib.csm_set_sampling.restype = i32
     lib.csm_sample_topk.argtypes = [vp, i32, i32, i32, C.c_float, C.c_uint64, vp, vp]; lib.csm_sample_topk.restype = i32
+    lib.csm_linear.argtypes = [vp, i32, vp, i32, i32, i32, i32, vp, i32, vp]; lib.csm_linear.restype = i32
     _lib = lib
     return lib
 

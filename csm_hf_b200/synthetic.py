@@ -93,3 +93,30 @@ def make_context(cfg: CSMConfig, batch: int, frames: int, seed: int = 1234,
         mask[:, :text_frames, :] = 0
         mask[:, :text_frames, nq] = 1
     return ids, mask
+
+
+def make_padded_context(cfg: CSMConfig, lengths, frames: int, seed: int = 1234, text_frames: int = 0,
+                        pad_text_id: int = 0, mask_dtype: torch.dtype = torch.int32):
+    """A variable-length batch left-padded to `frames` the way CSMProcessor pads it (processor.py:137-169):
+    sequence b keeps its last lengths[b] frames, the frames before them are padding -- ids 0 (text column
+    `pad_text_id`), all 33 mask entries 0.  `mask_dtype=torch.float32` reproduces the dtype the processor's
+    padding path emits (processor.py:148)."""
+    B = len(lengths)
+    ids, mask = make_context(cfg, B, frames, seed=seed, text_frames=0)
+    nq = cfg.audio_num_codebooks
+    g = torch.Generator().manual_seed(seed + 977)
+    for b, n in enumerate(lengths):
+        if not 1 <= n <= frames:
+            raise ValueError("every sequence needs between 1 and `frames` real frames")
+        npad = frames - n
+        if text_frames:
+            tf = min(text_frames, n)
+            tt = torch.randint(0, cfg.text_vocab_size, (tf,), generator=g, dtype=torch.int64)
+            ids[b, npad:npad + tf, :] = 0
+            ids[b, npad:npad + tf, nq] = tt
+            mask[b, npad:npad + tf, :] = 0
+            mask[b, npad:npad + tf, nq] = 1
+        ids[b, :npad, :] = 0
+        ids[b, :npad, nq] = pad_text_id
+        mask[b, :npad, :] = 0
+    return ids, mask.to(mask_dtype)

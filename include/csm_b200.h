@@ -95,7 +95,11 @@ int csm_embed_sum(CsmCtx* ctx, const int64_t* ids, const int32_t* mask, int B, i
 /* CSMModel.generate_frame (modeling_csm.py:484-589) at temperature 0 (reference:
  * topk=1, ties -> lowest index).  S == cached-context continuation: S > 1 is the
  * prefill call (causal), S == 1 a decode step attending to every cached position.
- *   ids int64 [B,S,33], mask int32 [B,S,33] (NULL = audio columns set, text clear)
+ *   ids int64 [B,S,33], mask int32 [B,S,33].  mask NULL means "audio columns set, text column clear" (the row
+ *       generate() builds for a decode step, modeling_csm.py:684-687) -- NOT the reference's attention_mask=None,
+ *       which sums all 33 slots (:328-332); the Python mirror passes an explicit all-ones mask for that case.
+ *       A prefill into an empty cache honours padding: frames whose 33 mask entries are all zero are hidden as
+ *       keys (modeling_csm.py:337-342); decode steps attend to every cached position, as the reference does.
  *   force_tokens int64 [B,32] or NULL: teacher forcing -- the decoder is fed these
  *       tokens instead of its own argmax (samples still report the argmax)
  *   samples int64 [B,32]; last_h bf16 [B,Hb]; c0_logits bf16 [B,V];
@@ -146,18 +150,13 @@ int csm_set_sampling(CsmCtx* ctx, int topk, float temperature, uint64_t seed, in
 int csm_sample_topk(const void* logits, int rows, int V, int topk, float temperature, uint64_t seed, int64_t* out,
                     void* stream);
 
-/* Sampling mode of the following csm_generate_frame / csm_generate calls (sample_topk, modeling_csm.py:179-189).
- * topk <= 1 or temperature == 0: greedy, lowest index on ties (the default).  Otherwise: keep the logits >= the
- * k-th largest of logits/temperature, softmax, draw -- by Gumbel-max with counter-based noise keyed by
- * (seed, frames generated since this call, codebook, seq_base + sequence index, vocabulary index); the reference
- * draws from torch's global generator, so parity is distributional.  seq_base: global index of this context's
- * sequence 0 when a batch is sharded over several contexts. */
-int csm_set_sampling(CsmCtx* ctx, int topk, float temperature, uint64_t seed, int seq_base);
-
-/* The same sampler on stand-alone rows (no context): logits [rows][V] bf16 on the device -> out[rows] int64;
- * row r uses the noise key (seed, 0, 0, r).  Used by the distribution tests. */
-int csm_sample_topk(const void* logits, int rows, int V, int topk, float temperature, uint64_t seed, int64_t* out,
-                    void* stream);
+/* One nn.Linear (no bias) on the tcgen05 tensor cores, the kernel the context prefill runs its projections on
+ * (hf modeling_llama.py:183,262-264,288): C[R,N] = x[R,K] * W[N,K]^T, bf16 in, fp32 accumulate, bf16 out, with the
+ * element-wise tail that follows the projection in the reference fused in:
+ *   tail 0: none; tail 1: C += y (residual add, C holds the residual on entry); tail 2: SwiGLU -- W rows interleaved
+ *   (gate_j, up_j), C [R, N/2] = bf16(silu(gate)) * up.
+ * x row pitch ldx, C row pitch ldc (elements); K % 64 == 0, N % 64 == 0; all device pointers, 16-byte aligned. */
+int csm_linear(const void* x, int ldx, const void* W, int R, int N, int K, int tail, void* C, int ldc, void* stream);
 
 /* ---- debug / test hooks: not part of the drop-in surface ------------------------------------
  * csm_debug_copy: device-to-device copy of an internal buffer (0 h_bb, 1 h_dec, 2 q_bb, 3 q_dec,

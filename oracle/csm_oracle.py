@@ -87,10 +87,15 @@ def rmsnorm(x: torch.Tensor, w: torch.Tensor, eps: float) -> torch.Tensor:
     return w * xf.to(dt)
 
 
-def attention(q: torch.Tensor, k: torch.Tensor, v: torch.Tensor, q_start: int) -> torch.Tensor:
+def attention(q: torch.Tensor, k: torch.Tensor, v: torch.Tensor, q_start: int,
+              key_valid: Optional[torch.Tensor] = None) -> torch.Tensor:
     """hf:integrations/sdpa_attention.py:40-104 restated: GQA by head repetition, scale
     hd^-1/2, fp32 softmax; query i (absolute position q_start+i) sees keys <= that
     position -- causal in prefill, everything cached in a decode step.
+    key_valid [B,T] bool (padded batches, modeling_csm.py:337-342 -> hf:masking_utils.py
+    padding mask): keys of all-zero-mask frames are hidden; a query that sees no key at
+    all gets a zero output (torch >= 2.5 SDPA "safe softmax", which is what the reference
+    runs on in this container).
     q [B,Hq,S,hd]; k,v [B,Hkv,T,hd] -> [B,S,Hq*hd]."""
     B, Hq, S, hd = q.shape
     Hkv, T = k.shape[1], k.shape[2]
@@ -100,8 +105,12 @@ def attention(q: torch.Tensor, k: torch.Tensor, v: torch.Tensor, q_start: int) -
     s = torch.matmul(q.to(torch.float32), kf.transpose(-1, -2)) * (hd ** -0.5)
     qpos = torch.arange(q_start, q_start + S)[:, None]
     kpos = torch.arange(T)[None, :]
-    s = s.masked_fill(kpos > qpos, float("-inf"))
+    hidden = (kpos > qpos)[None, None].expand(B, 1, S, T)
+    if key_valid is not None:
+        hidden = hidden | ~key_valid[:, None, None, :T].bool()
+    s = s.masked_fill(hidden, float("-inf"))
     p = torch.softmax(s, dim=-1)
+    p = torch.where(hidden.all(dim=-1, keepdim=True), torch.zeros_like(p), p)   # fully hidden rows -> 0, not NaN
     o = torch.matmul(p, vf).to(q.dtype)
     return o.transpose(1, 2).reshape(B, S, Hq * hd)
 
@@ -153,9 +162,11 @@ class KVCache:
         self.len = 0
 
 
-def llama_forward(w: LlamaW, x: torch.Tensor, cache: KVCache, trace: Optional[dict] = None) -> torch.Tensor:
+def llama_forward(w: LlamaW, x: torch.Tensor, cache: KVCache, trace: Optional[dict] = None,
+                  key_valid: Optional[torch.Tensor] = None) -> torch.Tensor:
     """hf:modeling_llama.py:375-425 (LlamaModel.forward) with inputs_embeds=x [B,S,H];
-    positions continue from the cache length (:394-397); appends S positions to `cache`."""
+    positions continue from the cache length (:394-397); appends S positions to `cache`.
+    key_valid [B, start+S]: padding mask of a padded prefill (None: nothing hidden)."""
     B, S, H = x.shape
     start = cache.len
     pos = torch.arange(start, start + S)
@@ -172,7 +183,7 @@ def llama_forward(w: LlamaW, x: torch.Tensor, cache: KVCache, trace: Optional[di
         k = apply_rope(k, cos, sin)
         cache.k[l, :, :, start:start + S] = k
         cache.v[l, :, :, start:start + S] = v
-        a = attention(q, cache.k[l, :, :, :start + S], cache.v[l, :, :, :start + S], start)
+        a = attention(q, cache.k[l, :, :, :start + S], cache.v[l, :, :, :start + S], start, key_valid)
         h = r + F.linear(a, lw["o"])
         r = h
         hn = rmsnorm(h, lw["ln2"], w.eps)
@@ -226,7 +237,15 @@ class CSMOracle:
         h = self.embed_sum(ids, mask)
         if trace is not None:
             trace["embed"] = h.clone()
-        hs = llama_forward(self.bb, h, cache, trace)
+        # modeling_csm.py:337-342: frames whose 33 mask entries are all zero are padding.  The 2-D mask reaches
+        # the backbone only in the prefill call: a decode step's [B,1] all-ones mask hides nothing, so cached
+        # padding positions (K = V = 0) ARE attended to from then on (SURVEY.md fact 8 -- the reference's quirk).
+        key_valid = None
+        if mask is not None and ids.shape[1] > 1 and cache.len == 0:
+            fv = mask.sum(dim=-1) > 0
+            if not bool(fv.all()):
+                key_valid = fv
+        hs = llama_forward(self.bb, h, cache, trace, key_valid)
         last_h = hs[:, -1, :]
         c0_logits = F.linear(last_h, self.sd["codebook0_head.weight"])   # :361 (last position only)
         return last_h, c0_logits

@@ -24,41 +24,99 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
 
 from csm_hf_b200.config import CSMConfig, tiny_config  # noqa: E402
-from csm_hf_b200.synthetic import make_context, make_state_dict  # noqa: E402
+from csm_hf_b200.synthetic import make_context, make_padded_context, make_state_dict  # noqa: E402
 from oracle import ref_harness as R  # noqa: E402
 
 GOLD = os.path.join(ROOT, "tests", "golden")
 
 
-def mint(name, cfg_name, cfg, dtype, B, T, n, wseed, jitter, cseed, text_frames, keep_cb=True):
-    sd = make_state_dict(cfg, seed=wseed, norm_jitter=jitter)
-    ids, mask = make_context(cfg, B, T, seed=cseed, text_frames=text_frames)
+_MODELS = {}
+
+
+def ref_model(cfg_name, cfg, dtype, wseed, jitter):
+    """One reference model per (config, dtype, weights): building csm-1b takes a minute."""
+    key = (cfg_name, dtype, wseed, jitter)
+    if key not in _MODELS:
+        _MODELS.clear()                    # at most one 1.5 B-parameter model in memory
+        _MODELS[key] = R.build_reference_model(cfg, make_state_dict(cfg, seed=wseed, norm_jitter=jitter), dtype)
+    return _MODELS[key]
+
+
+def mint(name, cfg_name, cfg, dtype, B, T, n, wseed, jitter, cseed, text_frames, keep_cb=True, cb_rows=None,
+         lengths=None, check_generate=True):
+    """cb_rows: keep the [n,B,31,V] per-codebook logits for these sequences only (large batches: the fixture stays
+    small; ids, last_h and codebook-0 logits are kept for every sequence).  lengths: a left-padded variable-length
+    batch (csm_hf_b200.synthetic.make_padded_context)."""
+    if lengths is None:
+        ids, mask = make_context(cfg, B, T, seed=cseed, text_frames=text_frames)
+    else:
+        ids, mask = make_padded_context(cfg, lengths, T, seed=cseed, text_frames=text_frames)
     t0 = time.time()
-    model = R.build_reference_model(cfg, sd, dtype)
+    model = ref_model(cfg_name, cfg, dtype, wseed, jitter)
     frames, tr = R.reference_trace(model, ids, mask, n)
-    frames2 = R.reference_generate(model, ids, mask, n)
-    assert torch.equal(frames, frames2), "reference generate() != generate_frame() loop"
+    if check_generate:
+        frames2 = R.reference_generate(model, ids, mask, n)
+        assert torch.equal(frames, frames2), "reference generate() != generate_frame() loop"
     out = {
         "recipe": dict(config=cfg_name, dtype=str(dtype).split(".")[-1], batch=B, ctx_frames=T, new_frames=n,
-                       weight_seed=wseed, norm_jitter=jitter, ctx_seed=cseed, text_frames=text_frames),
+                       weight_seed=wseed, norm_jitter=jitter, ctx_seed=cseed, text_frames=text_frames,
+                       lengths=lengths, cb_rows=cb_rows),
         "frames": frames,
         "last_h": torch.stack([t["last_h"] for t in tr]),
         "c0_logits": torch.stack([t["c0_logits"] for t in tr]),
     }
     if keep_cb:
-        out["cb_logits"] = torch.stack([t["cb_logits"] for t in tr])
+        cb = torch.stack([t["cb_logits"] for t in tr])            # [n,B,31,V]
+        out["cb_logits"] = cb if cb_rows is None else cb[:, cb_rows].clone()
     os.makedirs(GOLD, exist_ok=True)
     torch.save(out, os.path.join(GOLD, name))
-    print(f"{name}: frames {tuple(frames.shape)} in {time.time() - t0:.1f}s; c0 of frame0 = {frames[:, 0, 0].tolist()}")
+    print(f"{name}: frames {tuple(frames.shape)} in {time.time() - t0:.1f}s; c0 of frame0 = {frames[:, 0, 0].tolist()}",
+          flush=True)
 
 
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--full", action="store_true", help="also mint the csm-1b config #1 fixtures (6 GB, minutes)")
+    ap.add_argument("--bench", action="store_true",
+                    help="mint the fixtures of the BENCHMARKED configurations: csm-1b bf16, 2048-frame context at batch 1; "
+                         "256-frame context at batch 8 and 32 (tens of minutes of CPU)")
+    ap.add_argument("--padded", action="store_true", help="mint the left-padded variable-length batch fixtures (tiny)")
+    ap.add_argument("--only", default="", help="with --bench: comma list of b1,b8,b32")
     a = ap.parse_args()
     assert R.reference_available(), "needs /root/reference"
     torch.manual_seed(0)
     tiny = tiny_config()
+    if a.padded:
+        # N3: sequences of 8, 5 and 3 frames left-padded to 8 (processor.py:137-169); pads are hidden in the prefill
+        # and attended to (K = V = 0) in the decode steps -- whatever the reference does is the definition
+        for dt, tag in ((torch.float32, "fp32"), (torch.bfloat16, "bf16")):
+            mint(f"tiny_padded_{tag}.pt", "tiny", tiny, dt, B=3, T=8, n=4, wseed=0, jitter=0.1, cseed=5, text_frames=2,
+                 lengths=[8, 5, 3])
+        return
+    if a.bench:
+        full = CSMConfig()
+        only = set(a.only.split(",")) if a.only else {"b1", "b1bf16", "b8", "b32"}
+        # The fixtures of the benchmarked configurations come from the reference's fp32 CPU path (the dtype of
+        # BASELINE.json configs[0]).  Its bf16 CPU path is NOT a usable yardstick at long contexts: at 2048 frames the
+        # reference's own bf16 run sits 5 % (mean) / 26 % (max) of the logit range away from its fp32 run, while a
+        # bf16 pipeline with fp32 accumulation (the oracle, the CUDA engine) stays within 0.7 % / 3 % -- the bf16
+        # fixture of the batch-1 case is kept to show exactly that (tests/test_gpu_parity.py).
+        # BASELINE.json configs[1]: the bench.py default -- 2048-frame context, batch 1 (prefill + two decode frames)
+        if "b1" in only:
+            mint("csm1b_t2048_b1_fp32.pt", "csm-1b", full, torch.float32, B=1, T=2048, n=3, wseed=0, jitter=0.0,
+                 cseed=1234, text_frames=0, check_generate=False)
+        # configs[2]/[3] shapes (batch 8 per GPU / batch 32): same model, 256-frame context so that the CPU reference
+        # finishes in minutes; exercises the NB = 1 / 4 general kernels at real head dims
+        if "b8" in only:
+            mint("csm1b_t256_b8_fp32.pt", "csm-1b", full, torch.float32, B=8, T=256, n=2, wseed=0, jitter=0.0,
+                 cseed=1234, text_frames=0, cb_rows=[0, 7], check_generate=False)
+        if "b32" in only:
+            mint("csm1b_t256_b32_fp32.pt", "csm-1b", full, torch.float32, B=32, T=256, n=2, wseed=0, jitter=0.0,
+                 cseed=1234, text_frames=0, cb_rows=[9, 31], check_generate=False)
+        if "b1bf16" in only:
+            mint("csm1b_t2048_b1_bf16.pt", "csm-1b", full, torch.bfloat16, B=1, T=2048, n=3, wseed=0, jitter=0.0,
+                 cseed=1234, text_frames=0, check_generate=False)
+        return
     for dt, tag in ((torch.float32, "fp32"), (torch.bfloat16, "bf16")):
         mint(f"tiny_{tag}.pt", "tiny", tiny, dt, B=2, T=6, n=4, wseed=0, jitter=0.1, cseed=1234, text_frames=2)
         mint(f"tiny_b1_{tag}.pt", "tiny", tiny, dt, B=1, T=16, n=8, wseed=3, jitter=0.1, cseed=77, text_frames=0)

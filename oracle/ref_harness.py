@@ -1,9 +1,10 @@
 """Drive the UNMODIFIED reference (/root/reference/modeling_csm.py) on CPU.
 
-TEST INFRASTRUCTURE, build-container only: /root/reference does not exist on the GPU
-box, so nothing under tests/ -m gpu, smoke() or bench.py imports this module.  It is
-used by oracle/make_golden.py to mint tests/golden/*.pt and by
-tests/test_oracle_vs_reference.py (skipped when the reference is absent).
+TEST / MEASUREMENT INFRASTRUCTURE: used by oracle/make_golden.py to mint tests/golden/*.pt in
+the build container, and by bench.py's reference arm (`--impl reference`, cpu_baseline), which
+times the reference's own CPU path from the copy oracle/stage_ref.py stages under oracle/_ref/
+(git-ignored; /root/reference itself does not exist on the GPU box).  No test under -m gpu and
+nothing in the product imports this module.
 
 Caveats handled here, each established by probes in SURVEY.md §0 / §8c:
   1. transformers>=5 turns the reference's all-ones [B,1] decode mask into "attend to
@@ -23,7 +24,10 @@ import warnings
 
 import torch
 
+_STAGED = os.path.join(os.path.dirname(os.path.abspath(__file__)), "_ref")   # oracle/stage_ref.py (git-ignored copy)
 REF_DIR = os.environ.get("CSM_REFERENCE_DIR", "/root/reference")
+if not os.path.isfile(os.path.join(REF_DIR, "modeling_csm.py")) and os.path.isfile(os.path.join(_STAGED, "modeling_csm.py")):
+    REF_DIR = _STAGED          # the GPU box: /root/reference does not exist there, the staged copy travels with the repo
 
 
 def reference_available() -> bool:

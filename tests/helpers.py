@@ -4,7 +4,7 @@ import os
 import torch
 
 from csm_hf_b200.config import CSMConfig, tiny_config
-from csm_hf_b200.synthetic import make_context, make_state_dict
+from csm_hf_b200.synthetic import make_context, make_padded_context, make_state_dict
 
 GOLD = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
 
@@ -15,7 +15,10 @@ def load_golden(name):
     cfg = tiny_config() if r["config"] == "tiny" else CSMConfig()
     dtype = getattr(torch, r["dtype"])
     sd = make_state_dict(cfg, seed=r["weight_seed"], norm_jitter=r["norm_jitter"])
-    ids, mask = make_context(cfg, r["batch"], r["ctx_frames"], seed=r["ctx_seed"], text_frames=r["text_frames"])
+    if r.get("lengths"):
+        ids, mask = make_padded_context(cfg, r["lengths"], r["ctx_frames"], seed=r["ctx_seed"], text_frames=r["text_frames"])
+    else:
+        ids, mask = make_context(cfg, r["batch"], r["ctx_frames"], seed=r["ctx_seed"], text_frames=r["text_frames"])
     return g, cfg, dtype, sd, ids, mask
 
 
