@@ -22,7 +22,10 @@ struct PackSrc {
   long long col_stride[3];
 };
 extern "C" {
-cudaError_t csm_launch_stream(const StreamParams* p, int grid, size_t smem, cudaStream_t stream, int cooperative);
+cudaError_t csm_launch_stream_small(const StreamParams* p, int grid, size_t smem, cudaStream_t stream, int cooperative);
+cudaError_t csm_launch_stream_small_stoch(const StreamParams* p, int grid, size_t smem, cudaStream_t stream, int cooperative);
+cudaError_t csm_launch_batch(const StreamParams* p, int grid, size_t smem, cudaStream_t stream, int cooperative);
+cudaError_t csm_launch_batch_stoch(const StreamParams* p, int grid, size_t smem, cudaStream_t stream, int cooperative);
 cudaError_t csm_pack_launch(const PackSrc* src, const int* row_map_dev, int N, int K, int gran, int G, bf16* dst,
                             cudaStream_t stream);
 cudaError_t csm_gemm_launch(const void* map_a, const void* map_w, const GemmParams* p, int sms, cudaStream_t st);
@@ -34,7 +37,7 @@ cudaError_t csm_embed_sum_launch(const long long* ids, const int* mask, int defa
                                  const bf16* text_emb, int V, int H, bf16* out, int rows, cudaStream_t st);
 cudaError_t csm_rmsnorm_rows_launch(const bf16* x, const bf16* w, float eps, int H, bf16* y, int rows, cudaStream_t st);
 cudaError_t csm_take_last_rows_launch(const bf16* h, int S, int H, uint32_t* dst, int b0, int nseq, uint32_t tag,
-                                      cudaStream_t st);
+                                      int plain, cudaStream_t st);
 cudaError_t csm_sample_rows_launch(const bf16* logits, int rows, int V, int topk, float inv_temp, unsigned long long seed,
                                    long long* out, cudaStream_t st);
 cudaError_t csm_untag_rows_launch(const uint32_t* src, long long src_stride, int cols, int rows, bf16* dst, cudaStream_t st);
@@ -126,6 +129,8 @@ struct CsmCtx {
   int direct_mlp = 0;    // MLP activations staged whole in shared memory (max_batch <= 4)
   // shared-memory plan of the frame kernel (fixed at create time for max_batch)
   int m_alloc = 0, slot_bytes = 0, n_slots = 0, rope_bytes = 0, act_region = 0, red_bytes = 0, stream_tpc_max = 0;
+  int a_slots = 2, a_slot_bytes = 0;   // activation-tile ring of the K = 8192 phases (general kernels)
+  int mt2 = 0;                         // CSM_MT2=1: two m-tiles per warp wherever a CTA owns more than one (experiment)
   size_t smem_total = 0;
   long long launches = 0;
   cudaEvent_t ev0 = nullptr, ev1 = nullptr;
@@ -421,7 +426,8 @@ int plan_smem(CsmCtx* ctx) {
       const int rows = (P.q + (cls == 0 ? 1 : 0)) * P.gran;
       gc.rows = rows;
       const int mt = (rows + 15) / 16;
-      const int ns = mt >= 5 ? 8 : (mt >= 3 ? 4 : (mt >= 2 ? 2 : 1));
+      int ns = mt >= 5 ? 8 : (mt >= 3 ? 4 : (mt >= 2 ? 2 : 1));
+      if (ctx->mt2) ns = mt >= 9 ? 8 : (mt >= 5 ? 4 : (mt >= 3 ? 2 : 1));   // every warp takes two m-tiles: half the B-fragment reads
       gc.mtiles = mt;
       gc.ksl = ns == 8 ? 0 : (ns == 4 ? 1 : (ns == 2 ? 2 : 3));
       gc.rows_pad = mt * 16 + 4;
@@ -447,18 +453,7 @@ int plan_smem(CsmCtx* ctx) {
                      CSM_COMPUTE_WARPS * d.hd * 4;
     if (need > ctx->act_region) ctx->act_region = need;
   }
-  if (!ctx->direct_mlp) {
-    // TMA-streamed down_proj input: two slots of [m_alloc][tpc*16+8] bf16 with tpc >= 16 k-tiles
-    const int need = 2 * ctx->m_alloc * (16 * 16 + 8) * 2;
-    if (need > ctx->act_region) ctx->act_region = need;
-  }
-#if defined(CSM_ATT_RING) && CSM_ATT_RING
-  if (!ctx->fuse_attn) {
-    // experiment (csm_stream.inl: attn_bb_phase_ring): per-warp cp.async K/V ring of the backbone attention
-    const int need = CSM_COMPUTE_WARPS * CSM_ATT_RING * 16 * 144;
-    if (need > ctx->act_region) ctx->act_region = need;
-  }
-#endif
+  if (!ctx->fuse_attn && ctx->act_region < 65536) ctx->act_region = 65536;   // general kernels: room for the activation-tile ring
   ctx->act_region = (ctx->act_region + 255) / 256 * 256;
   const int limit = 227 * 1024;
   const int avail = limit - CSM_SM_HDR_BYTES - ctx->rope_bytes - ctx->red_bytes - ctx->act_region;
@@ -470,10 +465,19 @@ int plan_smem(CsmCtx* ctx) {
   if (ctx->n_slots > CSM_MAX_SLOTS) ctx->n_slots = CSM_MAX_SLOTS;
   const char* e = getenv("CSM_RING_SLOTS");
   if (e && atoi(e) >= 2 && atoi(e) <= ctx->n_slots) ctx->n_slots = atoi(e);
-  // activation-stream chunk: two slots of [m_alloc][tpc*16+8] bf16 inside the activation region
-  const int per_row = (ctx->act_region / 2) / (ctx->m_alloc * 2);
-  ctx->stream_tpc_max = (per_row - 8) / 16;
-  if (ctx->stream_tpc_max < 1) return fail(ctx, CSM_ECAPACITY, "activation region too small");
+  // activation-tile ring of the streamed (K = 8192) phases: slots of [m_alloc][tpc*16+8] bf16 inside the activation
+  // region, k-chunks in lockstep with the weight chunks; at least 3 slots so that two copies are in flight while one
+  // tile is consumed, tiles as long as that allows (k16-tile counts in units of 16 = 2 * the widest split-K)
+  {
+    int tpc = 64;
+    for (; tpc > 16; tpc -= 16)
+      if (ctx->act_region / (ctx->m_alloc * (tpc * 16 + 8) * 2) >= 3) break;
+    ctx->stream_tpc_max = tpc;
+    ctx->a_slot_bytes = ctx->m_alloc * (tpc * 16 + 8) * 2;
+    ctx->a_slots = ctx->act_region / ctx->a_slot_bytes;
+    if (ctx->a_slots > CSM_MAX_SLOTS) ctx->a_slots = CSM_MAX_SLOTS;
+    if (ctx->a_slots < 2) return fail(ctx, CSM_ECAPACITY, "activation region too small");
+  }
   ctx->smem_total = (size_t)CSM_SM_HDR_BYTES + ctx->rope_bytes + ctx->red_bytes + ctx->act_region +
                     (size_t)ctx->slot_bytes * ctx->n_slots;
   for (Phase& P : ctx->table) {
@@ -525,6 +529,16 @@ int check_abort(CsmCtx* ctx, cudaStream_t st) {
               "barrier 8/9 ring full 10/11 ring empty), detail %d / 0x%x, thread %d", a[1], a[2], a[3], a[4], a[5], a[6]);
 }
 
+// Two kernel families: engines for <= 2 sequences run the pure-dataflow kernels of csm_stream.inl, larger engines the
+// barrier-separated kernels of csm_batch.inl; each in a greedy and a stochastic-sampling build.
+cudaError_t launch_kernel(CsmCtx* ctx, const StreamParams* p, cudaStream_t st, int cooperative) {
+  if (ctx->fuse_attn)
+    return p->topk > 1 ? csm_launch_stream_small_stoch(p, ctx->G, ctx->smem_total, st, cooperative)
+                       : csm_launch_stream_small(p, ctx->G, ctx->smem_total, st, cooperative);
+  return p->topk > 1 ? csm_launch_batch_stoch(p, ctx->G, ctx->smem_total, st, cooperative)
+                     : csm_launch_batch(p, ctx->G, ctx->smem_total, st, cooperative);
+}
+
 int launch_frame(CsmCtx* ctx, int B, int ph_begin, int ph_end, const long long* ids, const int* mask, int forced,
                  long long* out_frames, long long out_stride, long long out_off, int stop_on_zeros, int pos,
                  cudaStream_t st) {
@@ -546,6 +560,7 @@ int launch_frame(CsmCtx* ctx, int B, int ph_begin, int ph_end, const long long* 
   p.stop_flag = ctx->stop_flag; p.n_frames = ctx->n_frames; p.stop_on_zeros = stop_on_zeros;
   p.m_alloc = ctx->m_alloc; p.slot_bytes = ctx->slot_bytes; p.n_slots = ctx->n_slots;
   p.rope_bytes = ctx->rope_bytes; p.act_region_bytes = ctx->act_region; p.red_bytes = ctx->red_bytes;
+  p.a_slots = ctx->a_slots; p.a_slot_bytes = ctx->a_slot_bytes;
   p.prof = ctx->prof_on ? ctx->prof : nullptr;
   p.n_phases_total = (int)ctx->table.size();
   p.progress = ctx->progress_on ? ctx->progress : nullptr;
@@ -560,13 +575,13 @@ int launch_frame(CsmCtx* ctx, int B, int ph_begin, int ph_end, const long long* 
   if (!ctx->stepped) {
     p.phase_begin = ph_begin; p.phase_end = ph_end; p.use_barrier = 1;
     CK(cudaMemsetAsync(ctx->bar_counter, 0, sizeof(unsigned int), st));
-    CK(csm_launch_stream(&p, ctx->G, ctx->smem_total, st, 1));
+    CK(launch_kernel(ctx, &p, st, 1));
     ctx->launches += 1;
   } else {
     p.use_barrier = 0;
     for (int ph = ph_begin; ph < ph_end; ++ph) {
       p.phase_begin = ph; p.phase_end = ph + 1;
-      CK(csm_launch_stream(&p, ctx->G, ctx->smem_total, st, 0));
+      CK(launch_kernel(ctx, &p, st, 0));
       ctx->launches += 1;
     }
   }
@@ -660,10 +675,11 @@ int prefill(CsmCtx* ctx, const long long* ids, const int* mask, int B, int S, cu
       if ((r = gemm_tc(ctx, ctx->pf_act, d.I, &L.tm_down, g, st))) return r;
       ctx->launches += 3;
     }
-    // hand the last position's residual row to the frame kernel as tagged words of the last backbone phase
+    // hand the last position's residual row to the frame kernel: tagged words of the last backbone phase for the
+    // <= 2-sequence kernels, plain bf16 rows for the general kernels
     for (int rr = 0; rr < ctx->repl; ++rr)
       CK(csm_take_last_rows_launch(ctx->pf_h, S, d.H, ctx->h_bb + (size_t)rr * ctx->Bmax * d.H, b0, nseq,
-                                   (ctx->tagbase + (unsigned)(ctx->ph_head_c0 - 1)) & 0xffffu, st));
+                                   (ctx->tagbase + (unsigned)(ctx->ph_head_c0 - 1)) & 0xffffu, !ctx->fuse_attn, st));
     ctx->launches += 1;
   }
   return 0;
@@ -822,7 +838,7 @@ int csm_create(const CsmShapes* sh, const CsmWeights* w, int max_batch, int max_
   // nothing at 1-2 sequences, which stay pure dataflow.  CSM_BAR_ALL=0/1 overrides.
   if (!ctx->direct_mlp || max_batch > 4) ctx->fuse_attn = 0;   // the SMALL kernels have no streamed-activation path
   ctx->bar_all = !ctx->fuse_attn;                              // (the general kernel family)
-  if (const char* e = getenv("CSM_BAR_ALL")) ctx->bar_all = atoi(e) != 0;
+  if (const char* e = getenv("CSM_MT2")) ctx->mt2 = atoi(e) != 0;
   build_table(ctx);
   if ((r = plan_smem(ctx))) return r;
   DA(ctx->d_table, ctx->table.size());
@@ -1031,8 +1047,8 @@ int csm_debug_copy(CsmCtx* ctx, int which, void* dst_device, int64_t max_bytes, 
     case 3: tsrc = ctx->q_dec; tcols = d.heads * d.hd; tstride = (d.heads + 2 * d.kv) * d.hd; break;
     case 4: tsrc = ctx->attn_bb; tcols = b.heads * b.hd; tstride = tcols; break;
     case 5: tsrc = ctx->attn_dec; tcols = d.heads * d.hd; tstride = tcols; break;
-    case 6: if (ctx->direct_mlp) { tsrc = ctx->mlp_bb; tcols = b.I; tstride = b.I; } else { src = ctx->mlp_bb; n = B * b.I * 2; } break;
-    case 7: if (ctx->direct_mlp) { tsrc = ctx->mlp_dec; tcols = d.I; tstride = d.I; } else { src = ctx->mlp_dec; n = B * d.I * 2; } break;
+    case 6: tsrc = ctx->mlp_bb; tcols = b.I; tstride = b.I; break;
+    case 7: tsrc = ctx->mlp_dec; tcols = d.I; tstride = d.I; break;
     case 8: src = ctx->last_h; n = B * b.H * 2; break;
     case 9: src = ctx->c0_logits; n = B * ctx->V * 2; break;
     case 10: src = ctx->cb_logits; n = B * (CSM_NQ - 1) * ctx->V * 2; break;
@@ -1049,7 +1065,12 @@ int csm_debug_copy(CsmCtx* ctx, int which, void* dst_device, int64_t max_bytes, 
   if (!dst_device) return CSM_OK;
   if (tsrc) {
     if ((int64_t)n > max_bytes) return fail(ctx, CSM_EINVAL, "debug buffer %d needs %lld bytes", which, (long long)n);
-    CK(csm_untag_rows_launch(tsrc, tstride, tcols, (int)B, (bf16*)dst_device, (cudaStream_t)stream));
+    if (ctx->fuse_attn) {
+      CK(csm_untag_rows_launch(tsrc, tstride, tcols, (int)B, (bf16*)dst_device, (cudaStream_t)stream));
+    } else {   // general kernels: the same buffers hold plain bf16 rows
+      CK(cudaMemcpy2DAsync(dst_device, (size_t)tcols * 2, tsrc, (size_t)tstride * 2, (size_t)tcols * 2, B,
+                           cudaMemcpyDeviceToDevice, (cudaStream_t)stream));
+    }
     return CSM_OK;
   }
   if ((int64_t)n > max_bytes) n = (size_t)max_bytes;

@@ -117,9 +117,14 @@ __global__ void csm_frame_valid_kernel(const int* __restrict__ mask, int rows, u
 // ---------------------------------------------------------------- the last position's hidden row per sequence,
 // handed to the frame kernel as tagged words (bf16 | tag of the last backbone phase, csm_common.cuh)
 __global__ void csm_take_last_rows_kernel(const bf16* __restrict__ h, int S, int H, uint32_t* __restrict__ dst, int b0,
-                                          uint32_t tag) {
+                                          uint32_t tag, int plain) {
   const int b = blockIdx.x;
   const unsigned short* src = reinterpret_cast<const unsigned short*>(h + ((size_t)b * S + (S - 1)) * H);
+  if (plain) {   // general kernels: the residual stream is a plain bf16 row
+    unsigned short* d = reinterpret_cast<unsigned short*>(dst) + (size_t)(b0 + b) * H;
+    for (int i = threadIdx.x; i < H; i += blockDim.x) d[i] = src[i];
+    return;
+  }
   uint32_t* d = dst + (size_t)(b0 + b) * H;
   for (int i = threadIdx.x; i < H; i += blockDim.x) d[i] = (tag << 16) | (uint32_t)src[i];
 }
@@ -338,8 +343,8 @@ cudaError_t csm_frame_valid_launch(const int* mask, int rows, unsigned char* val
   return cudaGetLastError();
 }
 cudaError_t csm_take_last_rows_launch(const bf16* h, int S, int H, uint32_t* dst, int b0, int nseq, uint32_t tag,
-                                      cudaStream_t st) {
-  csm_take_last_rows_kernel<<<nseq, 256, 0, st>>>(h, S, H, dst, b0, tag);
+                                      int plain, cudaStream_t st) {
+  csm_take_last_rows_kernel<<<nseq, 256, 0, st>>>(h, S, H, dst, b0, tag, plain);
   return cudaGetLastError();
 }
 cudaError_t csm_untag_rows_launch(const uint32_t* src, long long src_stride, int cols, int rows, bf16* dst, cudaStream_t st) {

@@ -38,34 +38,19 @@
 //   * greedy sampling needs no extra synchronisation: every CTA publishes its best (logit, id) as a tagged
 //     word and the consumers reduce the 148 candidates themselves.
 //
-// This file is compiled four times: {SMALL: engines for <= 2 sequences, nothing on the hot path that is not needed
-// there -- no hang guard, no debug hooks, no poll back-off; general: everything else} x {greedy; STOCH: stochastic
-// top-k sampling}.  Separate translation units, because the small-batch greedy kernel is bound by the instruction
-// count and register pressure of its hot path: code it never executes still costs it 10-20 % when compiled in.
+// This file is the kernel family of engines for <= 2 sequences (pure dataflow, nothing on the hot path that is not
+// needed there), compiled twice: greedy and STOCH (stochastic top-k sampling) -- separate translation units, because
+// the small-batch greedy kernel is bound by the instruction count and register pressure of its hot path: code it
+// never executes still costs it 10-20 % when compiled in.  Engines for 3..32 sequences run csm_batch.inl (plain bf16
+// hand-over, grid barriers, TMA-staged activations).
 #include "csm_common.cuh"
 #include "csm_sample.cuh"
 
-#if !defined(CSM_BUILD_SMALL) || !defined(CSM_BUILD_STOCH)
-#error "include this file from csm_stream_{small,general}{,_stoch}.cu"
+#if !defined(CSM_BUILD_SMALL) || !defined(CSM_BUILD_STOCH) || !CSM_BUILD_SMALL
+#error "include this file from csm_stream_small{,_stoch}.cu (the general kernel family is csm_batch.inl)"
 #endif
 
 // build-time experiment knobs (tools/gpu_variants.sh builds several libraries and times them in one GPU call)
-#ifndef CSM_ATT_RING
-#define CSM_ATT_RING 0   // experiment: stages of a per-warp cp.async K/V ring in the tensor-core backbone attention (0: off)
-#endif
-#if CSM_BUILD_SMALL
-#undef CSM_ATT_RING
-#define CSM_ATT_RING 0
-#endif
-#ifndef CSM_ATT_INLINE
-#define CSM_ATT_INLINE __noinline__
-#endif
-#ifndef CSM_ATT_KBUF
-#define CSM_ATT_KBUF 2   // K / V chunks in flight per warp in the tensor-core backbone attention (register budget)
-#endif
-#ifndef CSM_ATT_VBUF
-#define CSM_ATT_VBUF 2
-#endif
 #ifndef CSM_MMA_UNROLL
 #define CSM_MMA_UNROLL 4
 #endif
@@ -1324,586 +1309,6 @@ __device__ __noinline__ void attn_bb_phase(const StreamParams& p, int layer, int
   }
 }
 
-#if !CSM_BUILD_SMALL
-// Tensor-core form of the same phase (all general kernels): ONE WARP per (sequence, kv-head, 128 positions) unit, no
-// CTA barrier inside the phase, Q.K^T and P.V on mma.sync.m16n8k16.  The scalar form above costs ~1400 instructions
-// per 16 positions (fp32 dot products spread over 8 lanes, butterfly reductions); at 8-32 sequences that made this
-// phase instruction-bound, 14x slower than its K/V bytes take to stream (profiles/r01_phase_profile_b32_v9.txt).
-//
-//   S = Q K^T : A = the REP query heads of the group (rows >= REP are zero), B = 8 cached positions per n-tile, k = the
-//               64 head dims in 4 steps.  The k index of an MMA is a free permutation as long as A and B agree: lane
-//               (g, t) supplies dims 8t..8t+7 and 32+8t..32+8t+7, i.e. two 16-byte loads per K row, and the four
-//               lanes of a row read 64 contiguous bytes per load instruction.
-//   softmax   : the scores of the whole unit (8 chunks x 2 n-tiles x 2) stay in registers; max and sum over the unit
-//               in fp32 (sdpa_attention_forward computes its softmax in fp32), no online rescaling.
-//   O = P V   : the S accumulator fragments of a chunk are the A fragment of P (positions as k).  P is split into
-//               bf16 hi + lo parts (two MMAs), which keeps ~16 mantissa bits of the fp32 probabilities.  B = V with the
-//               output dims permuted (column g of n-tile j is dim 8g + j), so that lane (g, t) reads V as one 16-byte
-//               load per position and builds the fragments with byte permutes.
-// The unit's partial (max, sum, o[64]) and the last-arriver merge over the splits are those of the scalar form.
-// A sequence's result does not depend on the batch it is in (same unit decomposition, same arithmetic).  Out of line.
-template <int REP>
-__device__ CSM_ATT_INLINE void attn_bb_phase_mma(const StreamParams& p, int layer, int src_ph, int ph) {
-  constexpr int HD = 64, SPLIT = CSM_ATT_SPLIT_MMA, NCH = SPLIT / 16;
-  static_assert(REP <= 8, "query heads per kv head");
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, c = blockIdx.x, G = gridDim.x;
-  const int Ttot = p.pos + 1;
-  const int nsplit = (Ttot + SPLIT - 1) / SPLIT;
-  const int nk = p.bb.kv;
-  const int nunits = p.B * nk * nsplit;
-  const int g = lane >> 2, t = lane & 3;        // MMA fragment coordinates
-  const int grp = lane >> 3, dl = lane & 7;     // merge coordinates: head grp, dims 8*dl..
-  const uint32_t qtag = tg(p, src_ph), otag = tg(p, ph);
-  const int Wq = (p.bb.heads + 2 * nk) * HD;    // tagged q | k | v row
-  const float scale = p.bb.scale;
-  compute_sync();   // (the previous phase ended without a CTA barrier)
-#pragma unroll 1
-  for (int unit = warp * G + c; unit < nunits; unit += CSM_COMPUTE_WARPS * G) {
-    const int sp = unit % nsplit;
-    const int kvh = (unit / nsplit) % nk;
-    const int b = unit / (nsplit * nk);
-    const size_t kvbase = (((size_t)layer * p.Bmax + b) * nk + kvh) * (size_t)p.Tcap * HD;
-    const bf16* Kp = p.kc_bb + kvbase;
-    const bf16* Vp = p.vc_bb + kvbase;
-    const int p0 = sp * SPLIT;
-    const int nch = min(NCH, (Ttot - p0 + 15) >> 4);   // chunks with at least one position (>= 1)
-    const uint32_t* kw = p.q_bb + (size_t)b * Wq + p.bb.heads * HD + kvh * HD;   // tagged K / V of position `pos`
-    const uint32_t* vw = kw + nk * HD;
-    if (lane == 0) {   // HBM -> L2: this unit's V (read in the second pass) and the next unit of this warp
-      {
-        const int npos = min(SPLIT, p.pos - p0);
-        if (npos > 0) bulk_prefetch_l2(Vp + (size_t)p0 * HD, (uint32_t)npos * 128u);
-      }
-      const int nu = unit + CSM_COMPUTE_WARPS * G;
-      if (nu < nunits) {
-        const int sp2 = nu % nsplit, kvh2 = (nu / nsplit) % nk, b2 = nu / (nsplit * nk);
-        const size_t off = ((((size_t)layer * p.Bmax + b2) * nk + kvh2) * (size_t)p.Tcap + (size_t)sp2 * SPLIT) * HD;
-        const int npos = min(SPLIT, p.pos - sp2 * SPLIT);   // cached positions only
-        if (npos > 0) {
-          bulk_prefetch_l2(p.kc_bb + off, (uint32_t)npos * 128u);
-          bulk_prefetch_l2(p.vc_bb + off, (uint32_t)npos * 128u);
-        }
-      }
-    }
-    // K rows of a chunk for this lane: positions pc + g and pc + 8 + g (j = 0, 1), dims 8t.. (words 0-3) and 32+8t..
-    // (words 4-7).  Plain word arrays with compile-time indices only (everything below is fully unrolled): an array
-    // of uint4 read through pointer casts stayed in local memory, and a spilled load result is a wait for that load.
-    uint32_t kq[CSM_ATT_KBUF][16];   // chunks in flight: the unit is latency-bound, not instruction-bound
-#define CSM_LOAD_K(bf, ch)                                                                          \
-    do {                                                                                              \
-      _Pragma("unroll") for (int j = 0; j < 2; ++j) {                                                 \
-        const int pj = p0 + 16 * (ch) + 8 * j + g;                                                    \
-        uint4 x0 = make_uint4(0, 0, 0, 0), x1 = make_uint4(0, 0, 0, 0);                               \
-        if (pj < p.pos) {                                                                             \
-          x0 = ldcg_u4(Kp + (size_t)pj * HD + 8 * t);                                                 \
-          x1 = ldcg_u4(Kp + (size_t)pj * HD + 32 + 8 * t);                                            \
-        }                                                                                             \
-        kq[bf][8 * j + 0] = x0.x; kq[bf][8 * j + 1] = x0.y; kq[bf][8 * j + 2] = x0.z; kq[bf][8 * j + 3] = x0.w; \
-        kq[bf][8 * j + 4] = x1.x; kq[bf][8 * j + 5] = x1.y; kq[bf][8 * j + 6] = x1.z; kq[bf][8 * j + 7] = x1.w; \
-      }                                                                                               \
-    } while (0)
-    // Q fragment: head g (rows >= REP are zero), this lane's 16 dims as 8 packed pairs (tagged words from the qkv phase)
-    uint32_t qf[8];
-    {
-      const uint32_t* qw = p.q_bb + (size_t)b * Wq + (kvh * REP + (g < REP ? g : 0)) * HD;
-      uint4 q0, q1, q2, q3;
-      bool ok;
-      unsigned spin = 0;
-      do {
-        q0 = ld_tag4(qw + 8 * t); q1 = ld_tag4(qw + 8 * t + 4);
-        q2 = ld_tag4(qw + 32 + 8 * t); q3 = ld_tag4(qw + 32 + 8 * t + 4);
-        ok = tw_ok4(q0, qtag) & tw_ok4(q1, qtag) & tw_ok4(q2, qtag) & tw_ok4(q3, qtag);
-        if (!ok) poll_backoff(p, spin);
-        if (!ok && spin_giveup(p, spin, ph, W_ATTN_BB_Q, (unsigned)unit)) ok = true;
-      } while (!__all_sync(0xffffffffu, ok));
-      qf[0] = tw_pair(q0.x, q0.y); qf[1] = tw_pair(q0.z, q0.w); qf[2] = tw_pair(q1.x, q1.y); qf[3] = tw_pair(q1.z, q1.w);
-      qf[4] = tw_pair(q2.x, q2.y); qf[5] = tw_pair(q2.z, q2.w); qf[6] = tw_pair(q3.x, q3.y); qf[7] = tw_pair(q3.z, q3.w);
-      if (g >= REP) {
-#pragma unroll
-        for (int i = 0; i < 8; ++i) qf[i] = 0u;
-      }
-    }
-    // The position being processed (`pos`, in the last split only): its K / V are still in flight to the cache, so the
-    // chunks below cover the CACHED positions (< pos) and `pos` is one extra score / one extra P.V step taken from the
-    // tagged row after each pass -- nothing of it is live inside the loops (register budget of this out-of-line
-    // function: ~100; a load result that gets spilled is a wait for that load).
-    const bool has_cur = p.pos >= p0 && p.pos < p0 + SPLIT;   // (warp-uniform)
-    CSM_LOAD_K(0, 0);
-#pragma unroll
-    for (int a = 1; a < CSM_ATT_KBUF - 1; ++a)
-      if (a < nch) CSM_LOAD_K(a, a);
-    // ---- S = Q K^T for the whole unit; s[ch][j][e]: head g, position p0 + 16 ch + 8 j + 2 t + e
-    float s[NCH][2][2];
-#pragma unroll
-    for (int ch = 0; ch < NCH; ++ch) {
-      if (ch + CSM_ATT_KBUF - 1 < nch) CSM_LOAD_K((ch + CSM_ATT_KBUF - 1) % CSM_ATT_KBUF, ch + CSM_ATT_KBUF - 1);
-      if (ch < nch) {
-#pragma unroll
-        for (int j = 0; j < 2; ++j) {
-          float acc[4] = {0.f, 0.f, 0.f, 0.f};
-#pragma unroll
-          for (int i = 0; i < 4; ++i) {
-            const uint32_t a[4] = {qf[2 * i], 0u, qf[2 * i + 1], 0u};
-            mma16816(acc, a, kq[ch % CSM_ATT_KBUF][8 * j + 2 * i], kq[ch % CSM_ATT_KBUF][8 * j + 2 * i + 1]);
-          }
-          const int pj = p0 + 16 * ch + 8 * j + 2 * t;
-          s[ch][j][0] = (pj < p.pos) ? acc[0] * scale : -INFINITY;
-          s[ch][j][1] = (pj + 1 < p.pos) ? acc[1] * scale : -INFINITY;
-        }
-      } else {
-        s[ch][0][0] = s[ch][0][1] = s[ch][1][0] = s[ch][1][1] = -INFINITY;
-      }
-    }
-#undef CSM_LOAD_K
-    // score of `pos`: one more n-tile whose column 0 is the tagged K row (lanes g == 0 supply it), valid in c0 of t == 0
-    float s_cur = -INFINITY;
-    if (has_cur) {
-      uint4 a0, a1, a2, a3;
-      bool ok;
-      unsigned spin = 0;
-      do {
-        a0 = ld_tag4(kw + 8 * t); a1 = ld_tag4(kw + 8 * t + 4);
-        a2 = ld_tag4(kw + 32 + 8 * t); a3 = ld_tag4(kw + 32 + 8 * t + 4);
-        ok = tw_ok4(a0, qtag) & tw_ok4(a1, qtag) & tw_ok4(a2, qtag) & tw_ok4(a3, qtag);
-        if (!ok) poll_backoff(p, spin);
-        if (!ok && spin_giveup(p, spin, ph, W_ATTN_BB_KV, (unsigned)unit)) ok = true;
-      } while (!__all_sync(0xffffffffu, ok));
-      uint32_t kc[8] = {tw_pair(a0.x, a0.y), tw_pair(a0.z, a0.w), tw_pair(a1.x, a1.y), tw_pair(a1.z, a1.w),
-                        tw_pair(a2.x, a2.y), tw_pair(a2.z, a2.w), tw_pair(a3.x, a3.y), tw_pair(a3.z, a3.w)};
-      if (g != 0) {
-#pragma unroll
-        for (int i = 0; i < 8; ++i) kc[i] = 0u;
-      }
-      float acc[4] = {0.f, 0.f, 0.f, 0.f};
-#pragma unroll
-      for (int i = 0; i < 4; ++i) {
-        const uint32_t a[4] = {qf[2 * i], 0u, qf[2 * i + 1], 0u};
-        mma16816(acc, a, kc[2 * i], kc[2 * i + 1]);
-      }
-      if (t == 0) s_cur = acc[0] * scale;
-    }
-    // ---- softmax over the unit (fp32): lanes t = 0..3 of a row share a head
-    float mx = s_cur;
-#pragma unroll
-    for (int ch = 0; ch < NCH; ++ch) mx = fmaxf(mx, fmaxf(fmaxf(s[ch][0][0], s[ch][0][1]), fmaxf(s[ch][1][0], s[ch][1][1])));
-    mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, 1));
-    mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, 2));
-    float ls = 0.f;
-#pragma unroll
-    for (int ch = 0; ch < NCH; ++ch)
-#pragma unroll
-      for (int j = 0; j < 2; ++j)
-#pragma unroll
-        for (int e = 0; e < 2; ++e) {
-          const float pv = __expf(s[ch][j][e] - mx);   // (every unit holds at least one position: mx is finite)
-          s[ch][j][e] = pv;
-          ls += pv;
-        }
-    const float p_cur = __expf(s_cur - mx);   // (0 unless this lane holds the score of `pos`)
-    ls += p_cur;
-    ls += __shfl_xor_sync(0xffffffffu, ls, 1);
-    ls += __shfl_xor_sync(0xffffffffu, ls, 2);
-    // ---- O = P V; o[jn][e]: head g, dim 8 (2 t + e) + jn
-    float o[8][4];
-#pragma unroll
-    for (int jn = 0; jn < 8; ++jn) o[jn][0] = o[jn][1] = o[jn][2] = o[jn][3] = 0.f;
-    // V rows of a chunk for this lane: positions pc + {2t, 2t+1, 2t+8, 2t+9} (j = 0..3), dims 8g..8g+7 (4 words)
-    uint32_t vq[CSM_ATT_VBUF][16];   // chunks in flight (the unit's V was prefetched into L2 when the unit started)
-#define CSM_LOAD_V(bf, ch)                                                                           \
-    do {                                                                                              \
-      _Pragma("unroll") for (int j = 0; j < 4; ++j) {                                                 \
-        const int pj = p0 + 16 * (ch) + 2 * t + (j & 1) + 8 * (j >> 1);                               \
-        uint4 x = make_uint4(0, 0, 0, 0);                                                             \
-        if (pj < p.pos) x = ldcg_u4(Vp + (size_t)pj * HD + 8 * g);                                    \
-        vq[bf][4 * j + 0] = x.x; vq[bf][4 * j + 1] = x.y; vq[bf][4 * j + 2] = x.z; vq[bf][4 * j + 3] = x.w; \
-      }                                                                                               \
-    } while (0)
-    CSM_LOAD_V(0, 0);
-#pragma unroll
-    for (int a = 1; a < CSM_ATT_VBUF - 1; ++a)
-      if (a < nch) CSM_LOAD_V(a, a);
-#pragma unroll
-    for (int ch = 0; ch < NCH; ++ch) {
-      if (ch + CSM_ATT_VBUF - 1 < nch) CSM_LOAD_V((ch + CSM_ATT_VBUF - 1) % CSM_ATT_VBUF, ch + CSM_ATT_VBUF - 1);
-      if (ch < nch) {
-        // A fragments of P: (a0, a2) = positions (2t, 2t+1), (2t+8, 2t+9); bf16 hi + lo parts
-        const float h00 = bfround(s[ch][0][0]), h01 = bfround(s[ch][0][1]), h10 = bfround(s[ch][1][0]), h11 = bfround(s[ch][1][1]);
-        const uint32_t ahi[4] = {pack_bf16(h00, h01), 0u, pack_bf16(h10, h11), 0u};
-        const uint32_t alo[4] = {pack_bf16(s[ch][0][0] - h00, s[ch][0][1] - h01), 0u,
-                                 pack_bf16(s[ch][1][0] - h10, s[ch][1][1] - h11), 0u};
-#pragma unroll
-        for (int wd = 0; wd < 4; ++wd) {   // word wd of the four rows = dims 8g + 2 wd, +1
-          const uint32_t w0 = vq[ch % CSM_ATT_VBUF][0 + wd];    // position 2t
-          const uint32_t w1 = vq[ch % CSM_ATT_VBUF][4 + wd];    // 2t+1
-          const uint32_t w2 = vq[ch % CSM_ATT_VBUF][8 + wd];    // 2t+8
-          const uint32_t w3 = vq[ch % CSM_ATT_VBUF][12 + wd];   // 2t+9
-#pragma unroll
-          for (int e = 0; e < 2; ++e) {
-            const int jn = 2 * wd + e;
-            const uint32_t sel = e ? 0x7632u : 0x5410u;
-            const uint32_t b0 = __byte_perm(w0, w1, sel);
-            const uint32_t b1 = __byte_perm(w2, w3, sel);
-            mma16816(o[jn], ahi, b0, b1);
-            mma16816(o[jn], alo, b0, b1);
-          }
-        }
-      }
-    }
-#undef CSM_LOAD_V
-    // P.V of `pos`: k slot 0 of one more step -- A holds p_cur in lanes t == 0, B the tagged V row in lanes t == 0
-    if (has_cur) {
-      uint4 b0, b1;
-      bool ok;
-      unsigned spin = 0;
-      do {
-        b0 = ld_tag4(vw + 8 * g); b1 = ld_tag4(vw + 8 * g + 4);
-        ok = tw_ok4(b0, qtag) & tw_ok4(b1, qtag);
-        if (!ok) poll_backoff(p, spin);
-        if (!ok && spin_giveup(p, spin, ph, W_ATTN_BB_KV, (unsigned)unit)) ok = true;
-      } while (!__all_sync(0xffffffffu, ok));
-      uint32_t vc[4] = {tw_pair(b0.x, b0.y), tw_pair(b0.z, b0.w), tw_pair(b1.x, b1.y), tw_pair(b1.z, b1.w)};
-      if (t != 0) vc[0] = vc[1] = vc[2] = vc[3] = 0u;
-      const float hc = bfround(p_cur);
-      const uint32_t ahi[4] = {pack_bf16(hc, 0.f), 0u, 0u, 0u};
-      const uint32_t alo[4] = {pack_bf16(p_cur - hc, 0.f), 0u, 0u, 0u};
-#pragma unroll
-      for (int jn = 0; jn < 8; ++jn) {
-        const uint32_t bb0 = (vc[jn >> 1] >> (16 * (jn & 1))) & 0xffffu;   // dim 8g + jn of `pos` in k slot 0
-        mma16816(o[jn], ahi, bb0, 0u);
-        mma16816(o[jn], alo, bb0, 0u);
-      }
-    }
-    // partial (max, sum, o[64]) of this unit: lane (g < REP, t) holds dims 16t..16t+7 (e = 0) and 16t+8.. (e = 1)
-    if (g < REP) {
-      float* part = p.attn_part + (((size_t)b * p.bb.heads + kvh * REP + g) * p.nsplit_max + sp) * (HD + 2);
-#pragma unroll
-      for (int jn = 0; jn < 8; ++jn) {
-        part[2 + 16 * t + jn] = o[jn][0];
-        part[2 + 16 * t + 8 + jn] = o[jn][1];
-      }
-      if (t == 0) { part[0] = mx; part[1] = ls; }
-    }
-    __threadfence();
-    __syncwarp();
-    int last = 0;
-    if (lane == 0) last = atomicAdd(p.attn_cnt + b * nk + kvh, 1u) == (unsigned)nsplit - 1u;
-    last = __shfl_sync(0xffffffffu, last, 0);
-    if (last) {
-      // last unit of this (sequence, kv-head): merge the splits and publish the head outputs
-      __threadfence();
-#pragma unroll
-      for (int h0 = 0; h0 < REP; h0 += 4) {
-        const int h = h0 + grp;
-        if (h < REP) {
-          const float* part = p.attn_part + (((size_t)b * p.bb.heads + kvh * REP + h) * p.nsplit_max) * (HD + 2);
-          // (the loads of several splits are independent: unrolled so that they are in flight together)
-          float M2 = -INFINITY;
-#pragma unroll 6
-          for (int s2 = 0; s2 < nsplit; ++s2) M2 = fmaxf(M2, ldcg_f32(part + (size_t)s2 * (HD + 2)));
-          float L2 = 0.f, O2[8];
-#pragma unroll
-          for (int i = 0; i < 8; ++i) O2[i] = 0.f;
-#pragma unroll 3
-          for (int s2 = 0; s2 < nsplit; ++s2) {
-            const float* ps = part + (size_t)s2 * (HD + 2);
-            const float f = __expf(ldcg_f32(ps) - M2);
-            L2 += f * ldcg_f32(ps + 1);
-#pragma unroll
-            for (int i = 0; i < 8; ++i) O2[i] += f * ldcg_f32(ps + 2 + dl * 8 + i);
-          }
-          uint32_t* od = p.attn_bb + (size_t)b * (p.bb.heads * HD) + (kvh * REP + h) * HD + dl * 8;
-          st_tag4(od, tw_pack(O2[0] / L2, otag), tw_pack(O2[1] / L2, otag), tw_pack(O2[2] / L2, otag), tw_pack(O2[3] / L2, otag));
-          st_tag4(od + 4, tw_pack(O2[4] / L2, otag), tw_pack(O2[5] / L2, otag), tw_pack(O2[6] / L2, otag),
-                  tw_pack(O2[7] / L2, otag));
-        }
-      }
-      if (lane == 0) p.attn_cnt[b * nk + kvh] = 0u;
-    }
-    __syncwarp();
-  }
-}
-#endif
-
-#if CSM_ATT_RING
-// EXPERIMENT (compile with -DCSM_ATT_RING=2 or 3; default off, not validated on a GPU yet -- DESIGN.md section 7): the same
-// phase with the K / V chunks staged in a per-warp shared-memory ring by cp.async instead of registers, so that
-// CSM_ATT_RING - 1 chunks are really in flight (ptxas spills the register prefetch of attn_bb_phase_mma, which makes
-// those loads synchronous).  One stream of 2 * nch chunk copies per unit: K chunks, then V chunks, 16 rows of 128
-// bytes each, padded to 144-byte rows (conflict-free ldmatrix).  Fragments: K with ldmatrix.x4 (natural dim order,
-// so q is read as 8-byte pairs), V with ldmatrix.x4.trans (natural output dims).  The ring lives in the activation
-// region, which no one uses during this phase (host: plan_smem reserves 8 warps x CSM_ATT_RING x 2304 bytes).
-__device__ __forceinline__ uint2 ld_tag2(const uint32_t* q) {
-  uint2 v;
-  asm volatile("ld.relaxed.gpu.global.v2.u32 {%0,%1}, [%2];" : "=r"(v.x), "=r"(v.y) : "l"(q) : "memory");
-  return v;
-}
-__device__ __forceinline__ void ldsm_x4_t(uint32_t (&r)[4], uint32_t addr) {
-  asm volatile("ldmatrix.sync.aligned.m8n8.x4.trans.shared.b16 {%0,%1,%2,%3}, [%4];"
-               : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3])
-               : "r"(addr));
-}
-
-template <int REP>
-__device__ __noinline__ void attn_bb_phase_ring(const StreamParams& p, int layer, int src_ph, int ph) {
-  constexpr int HD = 64, SPLIT = CSM_ATT_SPLIT_MMA, NCH = SPLIT / 16, ST = CSM_ATT_RING, RS = 144, STB = 16 * RS;
-  static_assert(REP <= 8, "query heads per kv head");
-  static_assert(ST >= 2 && ST <= 4, "ring stages");
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, c = blockIdx.x, G = gridDim.x;
-  const int Ttot = p.pos + 1;
-  const int nsplit = (Ttot + SPLIT - 1) / SPLIT;
-  const int nk = p.bb.kv;
-  const int nunits = p.B * nk * nsplit;
-  const int g = lane >> 2, t = lane & 3;        // MMA fragment coordinates
-  const int grp = lane >> 3, dl = lane & 7;     // copy / merge coordinates
-  const uint32_t qtag = tg(p, src_ph), otag = tg(p, ph);
-  const int Wq = (p.bb.heads + 2 * nk) * HD;    // tagged q | k | v row
-  const float scale = p.bb.scale;
-  const uint32_t ring = smem_u32(sm_act(p)) + (uint32_t)warp * (ST * STB);
-  compute_sync();   // (the previous phase ended without a CTA barrier; this one reuses its activation region)
-#pragma unroll 1
-  for (int unit = warp * G + c; unit < nunits; unit += CSM_COMPUTE_WARPS * G) {
-    const int sp = unit % nsplit;
-    const int kvh = (unit / nsplit) % nk;
-    const int b = unit / (nsplit * nk);
-    const size_t kvbase = (((size_t)layer * p.Bmax + b) * nk + kvh) * (size_t)p.Tcap * HD;
-    const bf16* Kp = p.kc_bb + kvbase;
-    const bf16* Vp = p.vc_bb + kvbase;
-    const int p0 = sp * SPLIT;
-    const int nch = min(NCH, (Ttot - p0 + 15) >> 4);   // chunks with at least one position (>= 1)
-    const uint32_t* kw = p.q_bb + (size_t)b * Wq + p.bb.heads * HD + kvh * HD;   // tagged K / V of position `pos`
-    const uint32_t* vw = kw + nk * HD;
-    const bool has_cur = p.pos >= p0 && p.pos < p0 + SPLIT;   // (warp-uniform)
-    if (lane == 0) {   // next unit of this warp: HBM -> L2 while this one is computed
-      const int nu = unit + CSM_COMPUTE_WARPS * G;
-      if (nu < nunits) {
-        const int sp2 = nu % nsplit, kvh2 = (nu / nsplit) % nk, b2 = nu / (nsplit * nk);
-        const size_t off = ((((size_t)layer * p.Bmax + b2) * nk + kvh2) * (size_t)p.Tcap + (size_t)sp2 * SPLIT) * HD;
-        const int npos = min(SPLIT, p.pos - sp2 * SPLIT);   // cached positions only
-        if (npos > 0) {
-          bulk_prefetch_l2(p.kc_bb + off, (uint32_t)npos * 128u);
-          bulk_prefetch_l2(p.vc_bb + off, (uint32_t)npos * 128u);
-        }
-      }
-    }
-    // copy i of the unit's stream (i < nch: K chunk i, else V chunk i - nch) into slot i % ST: lane -> rows grp + 4 r,
-    // 16-byte column dl; rows that are not cached yet (>= pos) are zero-filled.  One cp.async group per copy, also when
-    // there is nothing left to copy (uniform group counting).
-    __syncwarp();   // (the previous unit's last reads of the ring are done)
-#define CSM_RING_ISSUE(i)                                                                                       \
-    do {                                                                                                          \
-      if ((i) < 2 * nch) {                                                                                        \
-        const bf16* src_ = ((i) < nch ? Kp : Vp) + dl * 8;                                                        \
-        const int pc_ = p0 + 16 * ((i) < nch ? (i) : (i) - nch);                                                  \
-        const uint32_t dst_ = ring + (uint32_t)((i) % ST) * STB + (uint32_t)dl * 16u;                             \
-        _Pragma("unroll") for (int r_ = 0; r_ < 4; ++r_) {                                                        \
-          const int row_ = grp + 4 * r_;                                                                          \
-          if (pc_ + row_ < p.pos)                                                                                 \
-            asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst_ + (uint32_t)row_ * RS),            \
-                         "l"(src_ + (size_t)(pc_ + row_) * HD) : "memory");                                      \
-          else                                                                                                    \
-            asm volatile("st.shared.v4.u32 [%0], {%1,%1,%1,%1};" ::"r"(dst_ + (uint32_t)row_ * RS), "r"(0u) : "memory"); \
-        }                                                                                                         \
-      }                                                                                                           \
-      asm volatile("cp.async.commit_group;" ::: "memory");                                                       \
-    } while (0)
-#pragma unroll
-    for (int i = 0; i < ST - 1; ++i) CSM_RING_ISSUE(i);
-    // Q fragments, natural dim order: k-step i, a0 = dims 16 i + 2 t (+1), a2 = dims 16 i + 8 + 2 t (+1)
-    uint32_t qf[8];
-    {
-      const uint32_t* qw = p.q_bb + (size_t)b * Wq + (kvh * REP + (g < REP ? g : 0)) * HD + 2 * t;
-      uint2 q2[8];
-      bool ok;
-      unsigned spin = 0;
-      do {
-        ok = true;
-#pragma unroll
-        for (int i = 0; i < 8; ++i) {
-          q2[i] = ld_tag2(qw + 8 * i);
-          ok &= ((q2[i].x >> 16) == qtag) & ((q2[i].y >> 16) == qtag);
-        }
-        if (!ok) poll_backoff(p, spin);
-        if (!ok && spin_giveup(p, spin, ph, W_ATTN_BB_Q, (unsigned)unit)) ok = true;
-      } while (!__all_sync(0xffffffffu, ok));
-#pragma unroll
-      for (int i = 0; i < 8; ++i) qf[i] = g < REP ? tw_pair(q2[i].x, q2[i].y) : 0u;
-    }
-    // ---- S = Q K^T; s[ch][j][e]: head g, position p0 + 16 ch + 8 j + 2 t + e
-    float s[NCH][2][2];
-#pragma unroll
-    for (int ch = 0; ch < NCH; ++ch) {
-      if (ch < nch) {
-        __syncwarp();                                          // slot (ch - 1) % ST has been read by every lane
-        CSM_RING_ISSUE(ch + ST - 1);
-        asm volatile("cp.async.wait_group %0;" ::"n"(ST - 1) : "memory");   // this lane's part of copy `ch` has landed
-        __syncwarp();                                          // ... and every other lane's
-        const uint32_t slot = ring + (uint32_t)(ch % ST) * STB;
-#pragma unroll
-        for (int j = 0; j < 2; ++j) {
-          float acc[4] = {0.f, 0.f, 0.f, 0.f};
-#pragma unroll
-          for (int hf = 0; hf < 2; ++hf) {   // 32 dims per ldmatrix.x4: matrices = dims 0-7 | 8-15 | 16-23 | 24-31 of rows 8j..8j+7
-            uint32_t kf[4];
-            ldsm_x4(kf, slot + (uint32_t)(8 * j + dl) * RS + (uint32_t)grp * 16u + (uint32_t)hf * 64u);
-            const uint32_t a0[4] = {qf[4 * hf], 0u, qf[4 * hf + 1], 0u};
-            const uint32_t a1[4] = {qf[4 * hf + 2], 0u, qf[4 * hf + 3], 0u};
-            mma16816(acc, a0, kf[0], kf[1]);
-            mma16816(acc, a1, kf[2], kf[3]);
-          }
-          const int pj = p0 + 16 * ch + 8 * j + 2 * t;
-          s[ch][j][0] = (pj < p.pos) ? acc[0] * scale : -INFINITY;
-          s[ch][j][1] = (pj + 1 < p.pos) ? acc[1] * scale : -INFINITY;
-        }
-      } else {
-        s[ch][0][0] = s[ch][0][1] = s[ch][1][0] = s[ch][1][1] = -INFINITY;
-      }
-    }
-    // score of `pos`: one more n-tile whose column 0 is the tagged K row (lanes g == 0 supply it), valid in c0 of t == 0
-    float s_cur = -INFINITY;
-    if (has_cur) {
-      uint2 k2[8];
-      bool ok;
-      unsigned spin = 0;
-      do {
-        ok = true;
-#pragma unroll
-        for (int i = 0; i < 8; ++i) {
-          k2[i] = ld_tag2(kw + 2 * t + 8 * i);
-          ok &= ((k2[i].x >> 16) == qtag) & ((k2[i].y >> 16) == qtag);
-        }
-        if (!ok) poll_backoff(p, spin);
-        if (!ok && spin_giveup(p, spin, ph, W_ATTN_BB_KV, (unsigned)unit)) ok = true;
-      } while (!__all_sync(0xffffffffu, ok));
-      float acc[4] = {0.f, 0.f, 0.f, 0.f};
-#pragma unroll
-      for (int i = 0; i < 4; ++i) {
-        const uint32_t a[4] = {qf[2 * i], 0u, qf[2 * i + 1], 0u};
-        mma16816(acc, a, g == 0 ? tw_pair(k2[2 * i].x, k2[2 * i].y) : 0u, g == 0 ? tw_pair(k2[2 * i + 1].x, k2[2 * i + 1].y) : 0u);
-      }
-      if (t == 0) s_cur = acc[0] * scale;
-    }
-    // ---- softmax over the unit (fp32): lanes t = 0..3 of a row share a head
-    float mx = s_cur;
-#pragma unroll
-    for (int ch = 0; ch < NCH; ++ch) mx = fmaxf(mx, fmaxf(fmaxf(s[ch][0][0], s[ch][0][1]), fmaxf(s[ch][1][0], s[ch][1][1])));
-    mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, 1));
-    mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, 2));
-    float ls = 0.f;
-#pragma unroll
-    for (int ch = 0; ch < NCH; ++ch)
-#pragma unroll
-      for (int j = 0; j < 2; ++j)
-#pragma unroll
-        for (int e = 0; e < 2; ++e) {
-          const float pv = __expf(s[ch][j][e] - mx);
-          s[ch][j][e] = pv;
-          ls += pv;
-        }
-    const float p_cur = __expf(s_cur - mx);   // (0 unless this lane holds the score of `pos`)
-    ls += p_cur;
-    ls += __shfl_xor_sync(0xffffffffu, ls, 1);
-    ls += __shfl_xor_sync(0xffffffffu, ls, 2);
-    // ---- O = P V; o[jn][e]: head g, dim 8 jn + 2 t + e
-    float o[8][4];
-#pragma unroll
-    for (int jn = 0; jn < 8; ++jn) o[jn][0] = o[jn][1] = o[jn][2] = o[jn][3] = 0.f;
-#pragma unroll
-    for (int ch = 0; ch < NCH; ++ch) {
-      if (ch < nch) {
-        __syncwarp();
-        CSM_RING_ISSUE(nch + ch + ST - 1);
-        asm volatile("cp.async.wait_group %0;" ::"n"(ST - 1) : "memory");
-        __syncwarp();
-        const uint32_t slot = ring + (uint32_t)((nch + ch) % ST) * STB;
-        const float h00 = bfround(s[ch][0][0]), h01 = bfround(s[ch][0][1]), h10 = bfround(s[ch][1][0]), h11 = bfround(s[ch][1][1]);
-        const uint32_t ahi[4] = {pack_bf16(h00, h01), 0u, pack_bf16(h10, h11), 0u};
-        const uint32_t alo[4] = {pack_bf16(s[ch][0][0] - h00, s[ch][0][1] - h01), 0u,
-                                 pack_bf16(s[ch][1][0] - h10, s[ch][1][1] - h11), 0u};
-#pragma unroll
-        for (int jp = 0; jp < 4; ++jp) {   // two n-tiles per ldmatrix.x4.trans: matrices = (rows 0-7 | 8-15) x (dims 16 jp.. | 16 jp + 8..)
-          uint32_t vf[4];
-          ldsm_x4_t(vf, slot + (uint32_t)(dl + 8 * (grp & 1)) * RS + (uint32_t)(16 * jp + 8 * (grp >> 1)) * 2u);
-          mma16816(o[2 * jp], ahi, vf[0], vf[1]);
-          mma16816(o[2 * jp], alo, vf[0], vf[1]);
-          mma16816(o[2 * jp + 1], ahi, vf[2], vf[3]);
-          mma16816(o[2 * jp + 1], alo, vf[2], vf[3]);
-        }
-      }
-    }
-    asm volatile("cp.async.wait_group 0;" ::: "memory");
-#undef CSM_RING_ISSUE
-    // P.V of `pos`: k slot 0 of one more step -- A holds p_cur in lanes t == 0, B the tagged V row (dim 8 jn + g) in lanes t == 0
-    if (has_cur) {
-      uint32_t vv[8];
-      bool ok;
-      unsigned spin = 0;
-      do {
-        ok = true;
-#pragma unroll
-        for (int jn = 0; jn < 8; ++jn) {
-          vv[jn] = ld_tag(vw + 8 * jn + g);
-          ok &= (vv[jn] >> 16) == qtag;
-        }
-        if (!ok) poll_backoff(p, spin);
-        if (!ok && spin_giveup(p, spin, ph, W_ATTN_BB_KV, (unsigned)unit)) ok = true;
-      } while (!__all_sync(0xffffffffu, ok));
-      const float hc = bfround(p_cur);
-      const uint32_t ahi[4] = {pack_bf16(hc, 0.f), 0u, 0u, 0u};
-      const uint32_t alo[4] = {pack_bf16(p_cur - hc, 0.f), 0u, 0u, 0u};
-#pragma unroll
-      for (int jn = 0; jn < 8; ++jn) {
-        const uint32_t bb0 = t == 0 ? (vv[jn] & 0xffffu) : 0u;
-        mma16816(o[jn], ahi, bb0, 0u);
-        mma16816(o[jn], alo, bb0, 0u);
-      }
-    }
-    // partial (max, sum, o[64]) of this unit: lane (g < REP, t) holds dims 8 jn + 2 t, + 1
-    if (g < REP) {
-      float* part = p.attn_part + (((size_t)b * p.bb.heads + kvh * REP + g) * p.nsplit_max + sp) * (HD + 2);
-#pragma unroll
-      for (int jn = 0; jn < 8; ++jn) *reinterpret_cast<float2*>(part + 2 + 8 * jn + 2 * t) = make_float2(o[jn][0], o[jn][1]);
-      if (t == 0) { part[0] = mx; part[1] = ls; }
-    }
-    __threadfence();
-    __syncwarp();
-    int last = 0;
-    if (lane == 0) last = atomicAdd(p.attn_cnt + b * nk + kvh, 1u) == (unsigned)nsplit - 1u;
-    last = __shfl_sync(0xffffffffu, last, 0);
-    if (last) {
-      // last unit of this (sequence, kv-head): merge the splits and publish the head outputs
-      __threadfence();
-#pragma unroll
-      for (int h0 = 0; h0 < REP; h0 += 4) {
-        const int h = h0 + grp;
-        if (h < REP) {
-          const float* part = p.attn_part + (((size_t)b * p.bb.heads + kvh * REP + h) * p.nsplit_max) * (HD + 2);
-          float M2 = -INFINITY;
-#pragma unroll 6
-          for (int s2 = 0; s2 < nsplit; ++s2) M2 = fmaxf(M2, ldcg_f32(part + (size_t)s2 * (HD + 2)));
-          float L2 = 0.f, O2[8];
-#pragma unroll
-          for (int i = 0; i < 8; ++i) O2[i] = 0.f;
-#pragma unroll 3
-          for (int s2 = 0; s2 < nsplit; ++s2) {
-            const float* ps = part + (size_t)s2 * (HD + 2);
-            const float f = __expf(ldcg_f32(ps) - M2);
-            L2 += f * ldcg_f32(ps + 1);
-#pragma unroll
-            for (int i = 0; i < 8; ++i) O2[i] += f * ldcg_f32(ps + 2 + dl * 8 + i);
-          }
-          uint32_t* od = p.attn_bb + (size_t)b * (p.bb.heads * HD) + (kvh * REP + h) * HD + dl * 8;
-          st_tag4(od, tw_pack(O2[0] / L2, otag), tw_pack(O2[1] / L2, otag), tw_pack(O2[2] / L2, otag), tw_pack(O2[3] / L2, otag));
-          st_tag4(od + 4, tw_pack(O2[4] / L2, otag), tw_pack(O2[5] / L2, otag), tw_pack(O2[6] / L2, otag),
-                  tw_pack(O2[7] / L2, otag));
-        }
-      }
-      if (lane == 0) p.attn_cnt[b * nk + kvh] = 0u;
-    }
-    __syncwarp();
-  }
-}
-#endif   // CSM_ATT_RING
-
 }  // namespace
 
 // STOCH only makes the kernel's NAME unique per translation unit: template instantiations have weak linkage, two
@@ -2100,15 +1505,7 @@ __global__ void __launch_bounds__(CSM_THREADS, 1) csm_stream_kernel(const __grid
     bool published = false;
     if (type == PH_GEMV) published = gemv_phase<NB, SMALL>(p, P, L, nxt, fetch);
     else if (!SMALL && type == PH_ATTN_DEC) attn_dec_phase(p, P, L);
-    else if (type == PH_ATTN_BB) {
-#if CSM_BUILD_SMALL
-      attn_bb_phase<REP>(p, P.layer, P.src_ph, ph);
-#elif CSM_ATT_RING
-      attn_bb_phase_ring<REP>(p, P.layer, P.src_ph, ph);
-#else
-      attn_bb_phase_mma<REP>(p, P.layer, P.src_ph, ph);
-#endif
-    }
+    else if (type == PH_ATTN_BB) attn_bb_phase<REP>(p, P.layer, P.src_ph, ph);
     else if (type == PH_EMBED) embed_phase(p, ph);
     else finish_phase(p, P.res_ph);
     if (prof) prof[2] = clock64();       // this thread's share of the body done
@@ -2148,36 +1545,15 @@ static StreamKernel pick_rep(int rep) {
   }
 }
 
-// Four launchers, one per translation unit; csm_launch_stream (greedy general unit) dispatches.
-extern "C" {
-cudaError_t csm_launch_stream_small(const StreamParams* p, int grid, size_t smem, cudaStream_t stream, int cooperative);
-cudaError_t csm_launch_stream_small_stoch(const StreamParams* p, int grid, size_t smem, cudaStream_t stream, int cooperative);
-cudaError_t csm_launch_stream_general_stoch(const StreamParams* p, int grid, size_t smem, cudaStream_t stream, int cooperative);
-}
-
-#if CSM_BUILD_SMALL && CSM_BUILD_STOCH
+#if CSM_BUILD_STOCH
 #define CSM_LAUNCHER csm_launch_stream_small_stoch
-#elif CSM_BUILD_SMALL
-#define CSM_LAUNCHER csm_launch_stream_small
-#elif CSM_BUILD_STOCH
-#define CSM_LAUNCHER csm_launch_stream_general_stoch
 #else
-#define CSM_LAUNCHER csm_launch_stream
+#define CSM_LAUNCHER csm_launch_stream_small
 #endif
 
 extern "C" cudaError_t CSM_LAUNCHER(const StreamParams* p, int grid, size_t smem, cudaStream_t stream, int cooperative) {
-#if !CSM_BUILD_SMALL && !CSM_BUILD_STOCH
-  if (p->small) return p->topk > 1 ? csm_launch_stream_small_stoch(p, grid, smem, stream, cooperative)
-                                   : csm_launch_stream_small(p, grid, smem, stream, cooperative);
-  if (p->topk > 1) return csm_launch_stream_general_stoch(p, grid, smem, stream, cooperative);
-#endif
   const int rep = p->bb.heads / p->bb.kv;
-#if CSM_BUILD_SMALL
   StreamKernel k = pick_rep<1, true>(rep);
-#else
-  const int nb = (p->B + 7) / 8;
-  StreamKernel k = nb <= 1 ? pick_rep<1, false>(rep) : (nb <= 2 ? pick_rep<2, false>(rep) : pick_rep<4, false>(rep));
-#endif
   cudaError_t e = cudaFuncSetAttribute((const void*)k, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
   if (e != cudaSuccess) return e;
   if (cooperative) {

@@ -1,4 +1,3 @@
-// Frame kernels: engines for 3..32 sequences, greedy; also the dispatching launcher.  See csm_stream.inl.
-#define CSM_BUILD_SMALL 0
+// general kernel family (engines for 3..32 sequences), greedy sampling
 #define CSM_BUILD_STOCH 0
-#include "csm_stream.inl"
+#include "csm_batch.inl"

@@ -1,4 +1,3 @@
-// Frame kernels: engines for 3..32 sequences, stochastic top-k sampling.  See csm_stream.inl.
-#define CSM_BUILD_SMALL 0
+// general kernel family (engines for 3..32 sequences), stochastic top-k sampling
 #define CSM_BUILD_STOCH 1
-#include "csm_stream.inl"
+#include "csm_batch.inl"

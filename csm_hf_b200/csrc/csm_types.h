@@ -126,6 +126,7 @@ struct StreamParams {
   int m_alloc;                  // activation rows rounded up to 8
   int slot_bytes, n_slots;
   int rope_bytes, act_region_bytes, red_bytes;
+  int a_slots, a_slot_bytes;    // general kernels: ring of [B, k-chunk] activation tiles inside the activation region (K = 8192 phases)
   unsigned long long* prof;     // debug: clock64 stamps [2 CTAs (first,last)][n_phases_total][4], see csm_stream.cu
   int n_phases_total;
   // stochastic top-k sampling (topk <= 1: greedy).  lgt: tagged logits of the last head phase [Bmax][lgt_stride]
