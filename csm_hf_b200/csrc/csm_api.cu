@@ -130,6 +130,7 @@ struct CsmCtx {
   // shared-memory plan of the frame kernel (fixed at create time for max_batch)
   int m_alloc = 0, slot_bytes = 0, n_slots = 0, rope_bytes = 0, act_region = 0, red_bytes = 0, stream_tpc_max = 0;
   int a_slots = 2, a_slot_bytes = 0;   // activation-tile ring of the K = 8192 phases (general kernels)
+  int normw_off = 0;
   int mt2 = 0;                         // CSM_MT2=1: two m-tiles per warp wherever a CTA owns more than one (experiment)
   size_t smem_total = 0;
   long long launches = 0;
@@ -300,9 +301,10 @@ void add_layer_phases(CsmCtx* ctx, Stack& S, int stack, int l, int dec_pos, bool
   uint32_t* at = stack ? ctx->attn_dec : ctx->attn_bb;
   uint32_t* mlp = stack ? ctx->mlp_dec : ctx->mlp_bb;
   const int nq = d.heads * d.hd, nkv = d.kv * d.hd;
+  const int pad = ctx->fuse_attn ? 0 : 8;   // general kernels: rows of the inter-phase vectors are K + 8 apart (csm_batch.inl)
   auto idx = [&]() { return (int)ctx->table.size(); };
   const int iq = idx();
-  Phase P = gemv(ACT_NORM, EPI_QKV, 2, nq + 2 * nkv, d.H, stack, l, L.p_qkv, h, d.H, L.ln1, qb, nq + 2 * nkv, h_ph);
+  Phase P = gemv(ACT_NORM, EPI_QKV, 2, nq + 2 * nkv, d.H, stack, l, L.p_qkv, h, d.H + pad, L.ln1, qb, nq + 2 * nkv, h_ph);
   if (gather_cb >= 0) {
     P.act_mode = ACT_GATHER;
     P.act = ctx->proj_table;
@@ -328,15 +330,15 @@ void add_layer_phases(CsmCtx* ctx, Stack& S, int stack, int l, int dec_pos, bool
     P.type = stack ? PH_ATTN_DEC : PH_ATTN_BB; P.stack = stack; P.layer = l; P.dec_pos = dec_pos; P.src_ph = iq;
     ctx->table.push_back(P);
     io = idx();
-    ctx->table.push_back(gemv(ACT_PLAIN, EPI_RESID, 1, d.H, nq, stack, l, L.p_o, at, nq, nullptr, h, d.H, ia, h_ph));
+    ctx->table.push_back(gemv(ACT_PLAIN, EPI_RESID, 1, d.H, nq, stack, l, L.p_o, at, nq + pad, nullptr, h, d.H + pad, ia, h_ph));
   }
   const int ig = idx();
-  P = gemv(ACT_NORM, EPI_SWIGLU, 2, 2 * d.I, d.H, stack, l, L.p_gu, h, d.H, L.ln2, mlp, d.I, io);
+  P = gemv(ACT_NORM, EPI_SWIGLU, 2, 2 * d.I, d.H, stack, l, L.p_gu, h, d.H + pad, L.ln2, mlp, d.I + pad, io);
   if (!ctx->direct_mlp) P.flags |= CSM_PF_OUT_PLAIN | CSM_PF_BAR_OUT;
   ctx->table.push_back(P);
   const int id = idx();
-  P = gemv(ctx->direct_mlp ? ACT_PLAIN : ACT_STREAM, EPI_RESID, 1, d.H, d.I, stack, l, L.p_down, mlp, d.I, nullptr, h, d.H,
-           ig, io);
+  P = gemv(ctx->direct_mlp ? ACT_PLAIN : ACT_STREAM, EPI_RESID, 1, d.H, d.I, stack, l, L.p_down, mlp, d.I + pad, nullptr, h,
+           d.H + pad, ig, io);
   if (!ctx->direct_mlp) P.flags |= CSM_PF_BAR_IN;
   ctx->table.push_back(P);
   h_ph = id;
@@ -355,7 +357,8 @@ void build_table(CsmCtx* ctx) {
   ctx->ph_head_c0 = (int)ctx->table.size();
   // final norm (-> last_hidden_state) + codebook-0 head + greedy sample (modeling_csm.py:361-365,531-532)
   int head_ph = (int)ctx->table.size();
-  P = gemv(ACT_NORM, EPI_HEAD, 1, ctx->V, b.H, 0, 0, ctx->p_c0, ctx->h_bb, b.H, ctx->bb.norm, ctx->c0_logits, ctx->V, hb_ph);
+  const int pad = ctx->fuse_attn ? 0 : 8;
+  P = gemv(ACT_NORM, EPI_HEAD, 1, ctx->V, b.H, 0, 0, ctx->p_c0, ctx->h_bb, b.H + pad, ctx->bb.norm, ctx->c0_logits, ctx->V, hb_ph);
   P.cb = 0;
   P.norm_out = ctx->last_h;
   ctx->table.push_back(P);
@@ -365,7 +368,7 @@ void build_table(CsmCtx* ctx) {
     // (modeling_csm.py:535-542,564-565)
     int hd_ph = (int)ctx->table.size();
     if (pos == 0) {
-      P = gemv(ACT_NORM, EPI_STORE, 1, d.H, b.H, 0, 0, ctx->p_proj, ctx->h_bb, b.H, ctx->bb.norm, ctx->h_dec, d.H, hb_ph);
+      P = gemv(ACT_NORM, EPI_STORE, 1, d.H, b.H, 0, 0, ctx->p_proj, ctx->h_bb, b.H + pad, ctx->bb.norm, ctx->h_dec, d.H + pad, hb_ph);
       ctx->table.push_back(P);
     }
     // positions 1..31: projection(embedding(token)) is a row of proj_table, gathered by layer 0's qkv phase
@@ -375,7 +378,7 @@ void build_table(CsmCtx* ctx) {
     if (pos >= 1) {
       // audio_head[pos-1] on the decoder's final-norm output, greedy sample (modeling_csm.py:557-560)
       head_ph = (int)ctx->table.size();
-      P = gemv(ACT_NORM, EPI_HEAD, 1, ctx->V, d.H, 1, 0, ctx->p_heads[pos - 1], ctx->h_dec, d.H, ctx->dec.norm,
+      P = gemv(ACT_NORM, EPI_HEAD, 1, ctx->V, d.H, 1, 0, ctx->p_heads[pos - 1], ctx->h_dec, d.H + pad, ctx->dec.norm,
                ctx->cb_logits + (size_t)(pos - 1) * ctx->V, (CSM_NQ - 1) * ctx->V, hd_ph);
       P.cb = pos;
       ctx->table.push_back(P);
@@ -453,7 +456,12 @@ int plan_smem(CsmCtx* ctx) {
                      CSM_COMPUTE_WARPS * d.hd * 4;
     if (need > ctx->act_region) ctx->act_region = need;
   }
-  if (!ctx->fuse_attn && ctx->act_region < 65536) ctx->act_region = 65536;   // general kernels: room for the activation-tile ring
+  if (!ctx->fuse_attn) {
+    // general kernels: the norm weights of a phase are staged behind its rows; room for the activation-tile ring
+    ctx->normw_off = ctx->m_alloc * (kfull + 8) * 2;
+    if (ctx->act_region < ctx->normw_off + kfull * 2) ctx->act_region = ctx->normw_off + kfull * 2;
+    if (ctx->act_region < 65536) ctx->act_region = 65536;
+  }
   ctx->act_region = (ctx->act_region + 255) / 256 * 256;
   const int limit = 227 * 1024;
   const int avail = limit - CSM_SM_HDR_BYTES - ctx->rope_bytes - ctx->red_bytes - ctx->act_region;
@@ -469,9 +477,10 @@ int plan_smem(CsmCtx* ctx) {
   // region, k-chunks in lockstep with the weight chunks; at least 3 slots so that two copies are in flight while one
   // tile is consumed, tiles as long as that allows (k16-tile counts in units of 16 = 2 * the widest split-K)
   {
-    int tpc = 64;
-    for (; tpc > 16; tpc -= 16)
+    int tpc = 64;   // (a power of two: the tiled layout of the producer indexes by shift and mask)
+    for (; tpc > 16; tpc /= 2)
       if (ctx->act_region / (ctx->m_alloc * (tpc * 16 + 8) * 2) >= 3) break;
+    if (const char* e = getenv("CSM_A_TPC")) { int v = atoi(e); if (v == 16 || v == 32 || v == 64) tpc = v < tpc ? v : tpc; }
     ctx->stream_tpc_max = tpc;
     ctx->a_slot_bytes = ctx->m_alloc * (tpc * 16 + 8) * 2;
     ctx->a_slots = ctx->act_region / ctx->a_slot_bytes;
@@ -501,6 +510,28 @@ int plan_smem(CsmCtx* ctx) {
       }
       gc.tpc = tpc;
       gc.nch = nch;
+    }
+    if (P.act_mode == ACT_STREAM) {
+      // the gate/up phase that feeds this streamed phase writes [k-tile][m_alloc][len+8] with len = the k-chunk of this
+      // phase: both CTA classes chunk alike, by a power-of-two number of k16-tiles
+      const bool use0 = P.r > 0, use1 = P.q > 0;
+      int t = ntiles, unit = 2;
+      for (int cls = 0; cls < 2; ++cls)
+        if (cls == 0 ? use0 : use1) {
+          if (P.geo[cls].tpc < t) t = P.geo[cls].tpc;
+          if ((2 << P.geo[cls].ksl) > unit) unit = 2 << P.geo[cls].ksl;
+        }
+      int tp = 1;
+      while (tp * 2 <= t) tp *= 2;
+      if (tp < unit || ntiles % tp || ctx->a_slot_bytes < ctx->m_alloc * (tp * 16 + 8) * 2)
+        return fail(ctx, CSM_EINVAL, "streamed phase %dx%d: no common k-chunk (%d tiles, unit %d)", P.N, P.K, tp, unit);
+      for (int cls = 0; cls < 2; ++cls) {
+        P.geo[cls].tpc = P.geo[cls].rows > 0 ? tp : 0;
+        P.geo[cls].nch = P.geo[cls].rows > 0 ? ntiles / tp : 0;
+      }
+      Phase& Q = ctx->table[P.src_ph];
+      Q.tile_sh = 4;   // log2(16 * tp)
+      while ((16 << (Q.tile_sh - 4)) < tp * 16) ++Q.tile_sh;
     }
   }
   return 0;
@@ -561,6 +592,24 @@ int launch_frame(CsmCtx* ctx, int B, int ph_begin, int ph_end, const long long* 
   p.m_alloc = ctx->m_alloc; p.slot_bytes = ctx->slot_bytes; p.n_slots = ctx->n_slots;
   p.rope_bytes = ctx->rope_bytes; p.act_region_bytes = ctx->act_region; p.red_bytes = ctx->red_bytes;
   p.a_slots = ctx->a_slots; p.a_slot_bytes = ctx->a_slot_bytes;
+  p.hpad = ctx->fuse_attn ? 0 : 8;
+  p.normw_off = ctx->normw_off;
+  p.att_stages = ctx->act_region / (CSM_COMPUTE_WARPS * 4096);
+  if (p.att_stages > 4) p.att_stages = 4;
+  if (const char* e = getenv("CSM_ATT_STAGES")) { int v = atoi(e); if (v >= 1 && v <= p.att_stages) p.att_stages = v; }
+  {
+    // units of the backbone attention: (sequence, kv-head, nsub x 128 positions): the smallest nsub for which every
+    // compute warp of the grid gets at most ONE unit -- a unit is one long chain of dependent L2 / HBM round trips
+    // (K/V pieces, partial, counter, merge), and a warp runs its units one after the other
+    const int blocks = (pos + 1 + CSM_ATT_SPLIT_MMA - 1) / CSM_ATT_SPLIT_MMA;
+    const long long streams = (long long)B * ctx->bb.d.kv, warps = (long long)CSM_COMPUTE_WARPS * ctx->G;
+    int nsub = 1;
+    while (nsub < 8 && streams * ((blocks + nsub - 1) / nsub) > warps) ++nsub;
+    if (const char* e = getenv("CSM_ATT_NSUB")) nsub = atoi(e) > 0 ? atoi(e) : nsub;
+    p.att_nsub = nsub;
+  }
+  p.att_pf_units = 12;   // x 32 KB x 148 CTAs = 57 MB of the 126 MB L2 per layer at most
+  if (const char* e = getenv("CSM_ATT_PF")) p.att_pf_units = atoi(e);
   p.prof = ctx->prof_on ? ctx->prof : nullptr;
   p.n_phases_total = (int)ctx->table.size();
   p.progress = ctx->progress_on ? ctx->progress : nullptr;
@@ -809,7 +858,7 @@ int csm_create(const CsmShapes* sh, const CsmWeights* w, int max_batch, int max_
                  {ctx->mlp_bb, R * B * b.I * 4}, {ctx->mlp_dec, R * B * d.I * 4}};
   DA(ctx->last_h, B * b.H); DA(ctx->c0_logits, B * ctx->V); DA(ctx->cb_logits, B * (CSM_NQ - 1) * ctx->V);
   ctx->nsplit_max = (max_ctx + CSM_ATT_SPLIT_MMA - 1) / CSM_ATT_SPLIT_MMA;   // (sized for the smaller unit of the two kernel families)
-  DA(ctx->attn_part, B * b.heads * ctx->nsplit_max * (b.hd + 2));
+  DA(ctx->attn_part, B * b.heads * ctx->nsplit_max * (b.hd + 4));
   DA(ctx->attn_cnt, B * b.kv);
   DA(ctx->bar_counter, 4);
   ctx->lgt_stride = (ctx->V + 3) / 4 * 4;
@@ -1040,13 +1089,14 @@ int csm_debug_copy(CsmCtx* ctx, int which, void* dst_device, int64_t max_bytes, 
   const uint32_t* tsrc = nullptr;
   long long tstride = 0;
   int tcols = 0;
+  const int gpad = ctx->fuse_attn ? 0 : 8;   // general kernels: plain bf16 rows, K + 8 apart (buffers 6/7: tiled, raw)
   switch (which) {
-    case 0: tsrc = ctx->h_bb; tcols = b.H; tstride = b.H; break;
-    case 1: tsrc = ctx->h_dec; tcols = d.H; tstride = d.H; break;
+    case 0: tsrc = ctx->h_bb; tcols = b.H; tstride = b.H + gpad; break;
+    case 1: tsrc = ctx->h_dec; tcols = d.H; tstride = d.H + gpad; break;
     case 2: tsrc = ctx->q_bb; tcols = b.heads * b.hd; tstride = (b.heads + 2 * b.kv) * b.hd; break;
     case 3: tsrc = ctx->q_dec; tcols = d.heads * d.hd; tstride = (d.heads + 2 * d.kv) * d.hd; break;
-    case 4: tsrc = ctx->attn_bb; tcols = b.heads * b.hd; tstride = tcols; break;
-    case 5: tsrc = ctx->attn_dec; tcols = d.heads * d.hd; tstride = tcols; break;
+    case 4: tsrc = ctx->attn_bb; tcols = b.heads * b.hd; tstride = tcols + gpad; break;
+    case 5: tsrc = ctx->attn_dec; tcols = d.heads * d.hd; tstride = tcols + gpad; break;
     case 6: tsrc = ctx->mlp_bb; tcols = b.I; tstride = b.I; break;
     case 7: tsrc = ctx->mlp_dec; tcols = d.I; tstride = d.I; break;
     case 8: src = ctx->last_h; n = B * b.H * 2; break;

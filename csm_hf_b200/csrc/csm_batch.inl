@@ -38,12 +38,6 @@
 #error "include this file from csm_stream_general{,_stoch}.cu"
 #endif
 
-#ifndef CSM_ATT_KBUF
-#define CSM_ATT_KBUF 2   // K / V chunks in flight per warp in the tensor-core backbone attention (register budget)
-#endif
-#ifndef CSM_ATT_VBUF
-#define CSM_ATT_VBUF 2
-#endif
 #ifndef CSM_MMA_UNROLL
 #define CSM_MMA_UNROLL 4
 #endif
@@ -57,7 +51,8 @@ namespace {
 // ---- shared-memory header (CSM_SM_HDR_BYTES = 4096) ----
 //   [0,64) full[8] | [64,128) empty[8] | [160,168) sflag[2] | [168,172) weight-stream progress |
 //   [256,768) 2 phase descriptors | [768,2816) 512 floats scratch | [2816,2944) tok[32] | [2944,3072) rstd[32] |
-//   [3072,3136) afull[8] | [3136,3200) aempty[8] | [3200,3208) dfull
+//   [3072,3136) afull[8] | [3136,3200) aempty[8] | [3200,3208) dfull | [3328,3584) attention stage barriers [8 warps][4] |
+//   [3584,3616) attention piece counters [8 warps]
 __device__ __forceinline__ uint64_t* sm_full() { return reinterpret_cast<uint64_t*>(csm_smem); }
 __device__ __forceinline__ uint64_t* sm_empty() { return reinterpret_cast<uint64_t*>(csm_smem + 64); }
 __device__ __forceinline__ volatile int* sm_flag() { return reinterpret_cast<volatile int*>(csm_smem + 160); }
@@ -69,6 +64,8 @@ __device__ __forceinline__ float* sm_rstd() { return reinterpret_cast<float*>(cs
 __device__ __forceinline__ uint64_t* sm_afull() { return reinterpret_cast<uint64_t*>(csm_smem + 3072); }
 __device__ __forceinline__ uint64_t* sm_aempty() { return reinterpret_cast<uint64_t*>(csm_smem + 3136); }
 __device__ __forceinline__ uint64_t* sm_dfull() { return reinterpret_cast<uint64_t*>(csm_smem + 3200); }
+__device__ __forceinline__ uint64_t* sm_attbar() { return reinterpret_cast<uint64_t*>(csm_smem + 3328); }
+__device__ __forceinline__ uint32_t* sm_attcnt() { return reinterpret_cast<uint32_t*>(csm_smem + 3584); }
 // cos_dec | sin_dec ([32][hd/2] each) | cos_bb[pos] | sin_bb[pos]
 __device__ __forceinline__ bf16* sm_rope() { return reinterpret_cast<bf16*>(csm_smem + CSM_SM_HDR_BYTES); }
 __device__ __forceinline__ float* sm_red(const StreamParams& p) {
@@ -326,102 +323,82 @@ __device__ __forceinline__ void attn_dec_phase(const StreamParams& p, const Phas
       }
     }
     const float inv = 1.f / l;
-    *reinterpret_cast<uint2*>(orow + (size_t)b * (nh * HD) + head * HD + lane * 4) =
+    *reinterpret_cast<uint2*>(orow + (size_t)b * (nh * HD + p.hpad) + head * HD + lane * 4) =
         make_uint2(pack_bf16(o0 * inv, o1 * inv), pack_bf16(o2 * inv, o3 * inv));
   }
 }
 
 // ------------------------------------------------------------------ RMSNorm of the staged rows, in shared memory
-// Rows [M][astride] bf16 (raw residual-stream rows copied by the TMA engine, or gathered embedding rows) ->
-// LlamaRMSNorm.forward (hf modeling_llama.py:62-67): fp32 x*rsqrt(mean(x^2)+eps) -> bf16 -> *w -> bf16, in place.
-// Sum of squares: per (row, 128-element segment) one warp-shuffle sum, then a fixed-order butterfly over the
-// segments -- a row's result does not depend on the batch it is in.  K/4 is a power of two (checked at create time).
-// Ends with the rows ready but WITHOUT a trailing CTA barrier (the caller syncs).
-__device__ __forceinline__ void norm_rows(const StreamParams& p, const Phase& P, const Lane& L, int astride, bool have_ss) {
-  const int K = P.K, M = p.B, gsh = P.gsh, gmask = (1 << gsh) - 1, total = M << gsh, ppr = 1 << (gsh - 5);
-  bf16* dst = reinterpret_cast<bf16*>(sm_act(p));
-  float* scratch = sm_scratch();
-  if (!have_ss) {
-#pragma unroll 4
-    for (int i = L.tid; i < total; i += CSM_COMPUTE_THREADS) {   // (warp-uniform trip count: total % 32 == 0)
-      const int m = i >> gsh, g = i & gmask;
-      const uint2 v = *reinterpret_cast<const uint2*>(dst + (size_t)m * astride + g * 4);
-      const float a = bf_lo(v.x), b = bf_hi(v.x), c = bf_lo(v.y), d = bf_hi(v.y);
-      const float ss = warp_sum(a * a + b * b + c * c + d * d);
-      if (L.lane == 0) scratch[m * ppr + (g >> 5)] = ss;
-    }
-    compute_sync();
-  }
-  const float eps = P.stack ? p.dec.eps : p.bb.eps;
-  const float fK = (float)K;
-  float* rstd_s = sm_rstd();
-  for (int m = L.warp; m < M; m += CSM_COMPUTE_WARPS) {
-    float ss = scratch[m * ppr + (L.lane & (ppr - 1))];
-    for (int o = ppr >> 1; o > 0; o >>= 1) ss += __shfl_xor_sync(0xffffffffu, ss, o);
-    if (L.lane == 0) rstd_s[m] = rsqrtf(ss / fK + eps);   // mean = sum / K exactly as torch
-  }
-  compute_sync();
-  const bool keep_norm = P.norm_out != nullptr && P.act_mode == ACT_NORM;   // copy of the normalised rows (last_hidden_state)
-  const int sh8 = gsh - 1, mask8 = (1 << sh8) - 1;   // 8-element groups per row
-  const int total8 = M << sh8;
-  const uint4 w8a = __ldg(reinterpret_cast<const uint4*>(P.norm_w) + (L.tid & mask8));
-  const uint4 w8b = __ldg(reinterpret_cast<const uint4*>(P.norm_w) + ((L.tid + CSM_COMPUTE_THREADS) & mask8));
-  const bool wide8 = (1 << sh8) > CSM_COMPUTE_THREADS;
-  int jj = 0;
-#pragma unroll 4
-  for (int i = L.tid; i < total8; i += CSM_COMPUTE_THREADS, ++jj) {
-    const int m = i >> sh8, g = i & mask8;
-    const float rstd = rstd_s[m];
-    const uint4 nw = (wide8 && (jj & 1)) ? w8b : w8a;
-    uint4* px = reinterpret_cast<uint4*>(dst + (size_t)m * astride + g * 8);
-    const uint4 x = *px;
-    uint4 o;
-    o.x = pack_bf16(bf_lo(nw.x) * bfround(bf_lo(x.x) * rstd), bf_hi(nw.x) * bfround(bf_hi(x.x) * rstd));
-    o.y = pack_bf16(bf_lo(nw.y) * bfround(bf_lo(x.y) * rstd), bf_hi(nw.y) * bfround(bf_hi(x.y) * rstd));
-    o.z = pack_bf16(bf_lo(nw.z) * bfround(bf_lo(x.z) * rstd), bf_hi(nw.z) * bfround(bf_hi(x.z) * rstd));
-    o.w = pack_bf16(bf_lo(nw.w) * bfround(bf_lo(x.w) * rstd), bf_hi(nw.w) * bfround(bf_hi(x.w) * rstd));
-    *px = o;
-    if (keep_norm && (m % L.G) == L.c) *reinterpret_cast<uint4*>(P.norm_out + (size_t)m * K + g * 8) = o;
-  }
+// Rows [M][astride] bf16 (raw residual-stream rows copied by the TMA engine) -> LlamaRMSNorm.forward
+// (hf modeling_llama.py:62-67): fp32 x*rsqrt(mean(x^2)+eps) -> bf16 -> *w -> bf16, in place.  ONE WARP PER ROW: a lane
+// holds elements 8*lane + 256*j of its row in registers, the sum of squares is one in-register accumulation and one
+// shuffle reduction per row (fixed order: a row's result does not depend on the batch it is in), and the warp scales
+// its own row right away -- one pass over shared memory, no CTA barrier inside.  K is a multiple of 256, <= 2048.
+// GATHER = true: the rows do not come from shared memory but from the pre-projected embedding table --
+// projection(_embed_audio(codebook, token)) (modeling_csm.py:247-259,564-565) = row token + codebook*V, the token being
+// the sample of the previous head phase (tok[]); the warp of the CTA that owns the sequence also starts the residual
+// stream with the raw row.
+__device__ __forceinline__ uint32_t mul_bf16x2(uint32_t a, uint32_t b) {   // round-to-nearest bf16 products of two packed pairs
+  uint32_t d;
+  asm("mul.rn.bf16x2 %0, %1, %2;" : "=r"(d) : "r"(a), "r"(b));
+  return d;
+}
+__device__ __forceinline__ float sumsq8(const uint4& x) {   // sum of squares of 8 bf16, as a tree (short dependency chain)
+  const float a0 = bf_lo(x.x), a1 = bf_hi(x.x), a2 = bf_lo(x.y), a3 = bf_hi(x.y);
+  const float a4 = bf_lo(x.z), a5 = bf_hi(x.z), a6 = bf_lo(x.w), a7 = bf_hi(x.w);
+  return ((a0 * a0 + a1 * a1) + (a2 * a2 + a3 * a3)) + ((a4 * a4 + a5 * a5) + (a6 * a6 + a7 * a7));
 }
 
-// Decoder input of positions 1..31: projection(_embed_audio(codebook, token)) (modeling_csm.py:247-259,564-565) = row
-// token + codebook*V of the pre-projected table (plain bf16, read-only).  The token is the sample of the previous head
-// phase.  One CTA per sequence also starts the residual stream with the row.  Leaves the rows and their sums of squares.
-__device__ __forceinline__ void gather_rows(const StreamParams& p, const Phase& P, const Lane& L, int astride) {
-  const int K = P.K, M = p.B, gsh = P.gsh, gmask = (1 << gsh) - 1, total = M << gsh, ppr = 1 << (gsh - 5);
+template <bool GATHER>
+__device__ __forceinline__ void norm_rows(const StreamParams& p, const Phase& P, const Lane& L, int astride) {
+  const int K = P.K, M = p.B, nj = K >> 8;   // 256 elements per warp pass
   bf16* dst = reinterpret_cast<bf16*>(sm_act(p));
-#if CSM_BUILD_STOCH
-  sample_tokens(p, P.cb, P.res_ph);
-#else
-  reduce_candidates(p, L.warp, L.lane, L.c, L.G, P.cb, P.res_ph);
-#endif
+  const float eps = P.stack ? p.dec.eps : p.bb.eps;
+  const float fK = (float)K;
+  const bool keep_norm = !GATHER && P.norm_out != nullptr;   // copy of the normalised rows (last_hidden_state)
+  const bf16* tab = GATHER ? P.act + (size_t)(P.cb * p.V) * K : nullptr;
   const int* tok = sm_tok();
-  const bf16* tab = P.act + (size_t)(P.cb * p.V) * K;
-  float* scratch = sm_scratch();
-  bf16* hres = P.norm_out;
-#pragma unroll 1
-  for (int i0 = L.tid; i0 < total; i0 += 4 * CSM_COMPUTE_THREADS) {
-    uint2 v[4];
-#pragma unroll
-    for (int j = 0; j < 4; ++j) {
-      const int i = i0 + j * CSM_COMPUTE_THREADS;
-      if (i < total) v[j] = __ldg(reinterpret_cast<const uint2*>(tab + (size_t)tok[i >> gsh] * K) + (i & gmask));
-    }
-#pragma unroll
-    for (int j = 0; j < 4; ++j) {
-      const int i = i0 + j * CSM_COMPUTE_THREADS;
-      if (i < total) {   // warp-uniform
-        const int m = i >> gsh, g = i & gmask;
-        *reinterpret_cast<uint2*>(dst + (size_t)m * astride + g * 4) = v[j];
-        const float a = bf_lo(v[j].x), b = bf_hi(v[j].x), c = bf_lo(v[j].y), d = bf_hi(v[j].y);
-        const float ss = warp_sum(a * a + b * b + c * c + d * d);
-        if (L.lane == 0) scratch[m * ppr + (g >> 5)] = ss;
-        if ((m % L.G) == L.c) *reinterpret_cast<uint2*>(hres + (size_t)m * K + g * 4) = v[j];
+  const uint4* nwp = reinterpret_cast<const uint4*>(sm_act(p) + p.normw_off) + L.lane;   // norm weights, staged with the rows
+#pragma unroll 2
+  for (int m = L.warp; m < M; m += CSM_COMPUTE_WARPS) {
+    bf16* row = dst + (size_t)m * astride + L.lane * 8;
+    float ss = 0.f;
+    if (GATHER) {
+      // pass 1 reads the table row (global), keeps the raw row in shared memory and, for the owner CTA of the
+      // sequence, starts the residual stream with it
+      const uint4* src = reinterpret_cast<const uint4*>(tab + (size_t)tok[m] * K) + L.lane;
+      uint4* hres = reinterpret_cast<uint4*>(P.norm_out + (size_t)m * (K + p.hpad)) + L.lane;
+      const bool own = (m % L.G) == L.c;
+#pragma unroll 4
+      for (int j = 0; j < nj; ++j) {
+        const uint4 x = __ldg(src + j * 32);
+        *reinterpret_cast<uint4*>(row + j * 256) = x;
+        if (own) hres[j * 32] = x;
+        ss += sumsq8(x);
+      }
+    } else {
+#pragma unroll 4
+      for (int j = 0; j < nj; ++j) {
+        const uint4 x = *reinterpret_cast<const uint4*>(row + j * 256);
+        ss += sumsq8(x);
       }
     }
+    ss = warp_sum(ss);
+    const float rstd = rsqrtf(ss / fK + eps);   // mean = sum / K exactly as torch
+    // pass 2: the lane re-reads its own elements (written by itself: no barrier) and scales them
+#pragma unroll 4
+    for (int j = 0; j < nj; ++j) {
+      const uint4 x = *reinterpret_cast<const uint4*>(row + j * 256);
+      const uint4 nw = nwp[j * 32];
+      uint4 o;   // bf16(x * rstd) as a packed pair, then the bf16 x bf16 -> bf16 product with the weight (one rounding each)
+      o.x = mul_bf16x2(nw.x, pack_bf16(bf_lo(x.x) * rstd, bf_hi(x.x) * rstd));
+      o.y = mul_bf16x2(nw.y, pack_bf16(bf_lo(x.y) * rstd, bf_hi(x.y) * rstd));
+      o.z = mul_bf16x2(nw.z, pack_bf16(bf_lo(x.z) * rstd, bf_hi(x.z) * rstd));
+      o.w = mul_bf16x2(nw.w, pack_bf16(bf_lo(x.w) * rstd, bf_hi(x.w) * rstd));
+      *reinterpret_cast<uint4*>(row + j * 256) = o;
+      if (keep_norm && (m % L.G) == L.c) *reinterpret_cast<uint4*>(P.norm_out + (size_t)m * K + j * 256 + L.lane * 8) = o;
+    }
   }
-  compute_sync();
 }
 
 // ------------------------------------------------------------------ tensor-core inner loop
@@ -596,14 +573,20 @@ __device__ __forceinline__ void gemv_phase(const StreamParams& p, const Phase& P
         compute_sync();
       }
       CSM_STAMP(L, 8);
-      gather_rows(p, P, L, astride);
-      norm_rows(p, P, L, astride, true);
+#if CSM_BUILD_STOCH
+      sample_tokens(p, P.cb, P.res_ph);
+#else
+      reduce_candidates(p, L.warp, L.lane, L.c, L.G, P.cb, P.res_ph);
+#endif
+      mbar_wait_g(p, sm_dfull(), L.dpar, L.ph, W_DFULL);   // (the norm weights, copied by the activation-stream warp)
+      L.dpar ^= 1u;
+      norm_rows<true>(p, P, L, astride);
     } else {
       // the activation-stream warp copies the rows after it has observed the grid barrier of this phase
       mbar_wait_g(p, sm_dfull(), L.dpar, L.ph, W_DFULL);
       L.dpar ^= 1u;
       CSM_STAMP(L, 8);
-      if (P.act_mode == ACT_NORM) norm_rows(p, P, L, astride, false);
+      if (P.act_mode == ACT_NORM) norm_rows<false>(p, P, L, astride);
     }
     compute_sync();
     CSM_STAMP(L, 4);   // activations staged
@@ -657,7 +640,13 @@ __device__ __forceinline__ void gemv_phase(const StreamParams& p, const Phase& P
         st_bf16(o, ldcg_bf16(o) + v0);
       } else if (epi == EPI_SWIGLU) {  // hf modeling_llama.py:183: bf16(silu(gate)) * up -> bf16 ; rows (2j,2j+1)=(gate_j,up_j)
         const float sl = bfround(v0 / (1.f + expf(-v0)));
-        st_bf16(P.out + (size_t)m * out_stride + (gn >> 1), sl * v1);
+        const int j = gn >> 1;
+        if (P.tile_sh) {   // [k-tile][m_alloc][len+8]: the streamed down_proj copies one [B, len+8] tile per bulk copy
+          const int len = 1 << P.tile_sh;
+          st_bf16(P.out + ((size_t)(j >> P.tile_sh) * p.m_alloc + m) * (len + 8) + (j & (len - 1)), sl * v1);
+        } else {
+          st_bf16(P.out + (size_t)m * out_stride + j, sl * v1);
+        }
       } else if (epi == EPI_QKV) {     // rows (2j,2j+1) = RoPE pair (i, i+hd/2) of q/k, or two adjacent v features
         const StackDims& sd = P.stack ? p.dec : p.bb;
         const int half = sd.hd >> 1, hl = sd.hdl - 1;
@@ -832,89 +821,134 @@ __device__ __noinline__ void embed_phase(const StreamParams& p, int ph) {
       }
     }
     if (incol)
-      *reinterpret_cast<uint4*>(hb + (size_t)m * H + col) =
+      *reinterpret_cast<uint4*>(hb + (size_t)m * (H + p.hpad) + col) =
           make_uint4(pack_bf16(acc[0], acc[1]), pack_bf16(acc[2], acc[3]), pack_bf16(acc[4], acc[5]), pack_bf16(acc[6], acc[7]));
   }
 }
 
+// Merge of the split-KV partials of one (sequence, kv-head) by the warp whose unit arrived last: lane (grp, dl) owns
+// dims 8 dl.. of head grp.  All loads of a pass are independent and issued together: the (max, sum) pairs of every
+// split first, then the 64-float partial outputs as 16-byte vectors, four splits (8 loads) at a time.
+template <int REP>
+__device__ __forceinline__ void merge_splits(const StreamParams& p, int b, int kvh, int nsplit, int lane, bf16* orows) {
+  constexpr int HD = 64, PSTR = HD + 4;
+  const int grp = lane >> 3, dl = lane & 7;
+#pragma unroll
+  for (int h0 = 0; h0 < REP; h0 += 4) {
+    const int h = h0 + grp;
+    if (h < REP) {   // (REP < 4: the upper lane groups idle)
+      const float* part = p.attn_part + (((size_t)b * p.bb.heads + kvh * REP + h) * p.nsplit_max) * PSTR;
+      float M2 = -INFINITY;
+#pragma unroll 1
+      for (int s0 = 0; s0 < nsplit; s0 += 8) {
+        float mv[8];
+#pragma unroll
+        for (int i = 0; i < 8; ++i) mv[i] = (s0 + i < nsplit) ? ldcg_f32(part + (size_t)(s0 + i) * PSTR) : -INFINITY;
+#pragma unroll
+        for (int i = 0; i < 8; ++i) M2 = fmaxf(M2, mv[i]);
+      }
+      float L2 = 0.f, O2[8];
+#pragma unroll
+      for (int i = 0; i < 8; ++i) O2[i] = 0.f;
+#pragma unroll 1
+      for (int s0 = 0; s0 < nsplit; s0 += 4) {
+        float2 ml[4];
+        uint4 oa[4], ob[4];
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+          const float* ps = part + (size_t)min(s0 + i, nsplit - 1) * PSTR;
+          ml[i] = __ldcg(reinterpret_cast<const float2*>(ps));
+          oa[i] = ldcg_u4(ps + 4 + dl * 8);
+          ob[i] = ldcg_u4(ps + 8 + dl * 8);
+        }
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+          if (s0 + i < nsplit) {
+            const float f = __expf(ml[i].x - M2);
+            L2 += f * ml[i].y;
+            O2[0] += f * __uint_as_float(oa[i].x); O2[1] += f * __uint_as_float(oa[i].y);
+            O2[2] += f * __uint_as_float(oa[i].z); O2[3] += f * __uint_as_float(oa[i].w);
+            O2[4] += f * __uint_as_float(ob[i].x); O2[5] += f * __uint_as_float(ob[i].y);
+            O2[6] += f * __uint_as_float(ob[i].z); O2[7] += f * __uint_as_float(ob[i].w);
+          }
+        }
+      }
+      const float inv = 1.f / L2;
+      *reinterpret_cast<uint4*>(orows + (size_t)b * (p.bb.heads * HD + p.hpad) + (kvh * REP + h) * HD + dl * 8) =
+          make_uint4(pack_bf16(O2[0] * inv, O2[1] * inv), pack_bf16(O2[2] * inv, O2[3] * inv),
+                     pack_bf16(O2[4] * inv, O2[5] * inv), pack_bf16(O2[6] * inv, O2[7] * inv));
+    }
+  }
+}
+
 // ------------------------------------------------------------------ backbone decode attention (split-KV, GQA)
-// ONE WARP per unit = (sequence, kv-head, 128 cached positions), no CTA barrier inside the phase, Q.K^T and P.V on
-// mma.sync.m16n8k16; the REP query heads of the group share every K/V byte read.  Every position 0..pos comes from the
-// cache: the qkv phase wrote position `pos` before the grid barrier that precedes this phase.
+// ONE WARP per unit = (sequence, kv-head, nsub x 128 cached positions), no CTA barrier inside the phase, Q.K^T and P.V
+// on mma.sync.m16n8k16; the REP query heads of the group share every K/V byte read.  Every position 0..pos comes from
+// the cache: the qkv phase wrote position `pos` before the grid barrier that precedes this phase.
 //
+//   staging   : a unit's K rows (128 bytes per position) and V rows are contiguous in the cache, so they travel as bulk
+//               copies of 32 positions (4 KB) through a per-warp ring of 2-4 stages (the activation region, free during
+//               this phase), each completing on its own mbarrier; lane 0 issues piece n + stages as soon as the warp
+//               has consumed piece n -- across sub-block and unit boundaries, so loads stay in flight while a unit is
+//               reduced and merged.  The L2 prefetch warp pulls the K/V of the CTA's first units into L2 ahead of time.
 //   S = Q K^T : A = the REP query heads of the group (rows >= REP are zero), B = 8 cached positions per n-tile, k = the
 //               64 head dims in 4 steps.  The k index of an MMA is a free permutation as long as A and B agree: lane
-//               (g, t) supplies dims 8t..8t+7 and 32+8t..32+8t+7, i.e. two 16-byte loads per K row, and the four
-//               lanes of a row read 64 contiguous bytes per load instruction.
-//   softmax   : the scores of the whole unit (8 chunks x 2 n-tiles x 2) stay in registers; max and sum over the unit
-//               in fp32 (sdpa_attention_forward computes its softmax in fp32), no online rescaling.
+//               (g, t) supplies dims 8t..8t+7 and 32+8t..32+8t+7 (two 16-byte shared-memory loads per K row).
+//   softmax   : fp32 (sdpa_attention_forward computes its softmax in fp32); the scores of a 128-position sub-block stay
+//               in registers; between sub-blocks the running (max, sum, o) are rescaled (online softmax).
 //   O = P V   : the S accumulator fragments of a chunk are the A fragment of P (positions as k).  P is split into
 //               bf16 hi + lo parts (two MMAs), which keeps ~16 mantissa bits of the fp32 probabilities.  B = V with the
-//               output dims permuted (column g of n-tile j is dim 8g + j), so that lane (g, t) reads V as one 16-byte
-//               load per position and builds the fragments with byte permutes.
+//               output dims permuted (column g of n-tile j is dim 8g + j): lane (g, t) reads V as one 16-byte load per
+//               position and builds the fragments with byte permutes.
+// nsub (host: launch_frame) grows with the batch so that a launch has about one unit per warp: at 32 sequences a unit
+// is 512 positions -- 4x fewer partial results, fences, counters and merges than with 128-position units.
 // Units write (max, sum, o[64]) partials; the last unit of a (sequence, kv-head) to arrive merges the splits and writes
-// the head outputs (plain bf16).  A sequence's result does not depend on the batch it is in.  Out of line.
+// the head outputs (plain bf16).  A sequence's result does not depend on the batch it is in for a given nsub.
 template <int REP>
-__device__ __noinline__ void attn_bb_phase_mma(const StreamParams& p, int layer, int ph) {
-  constexpr int HD = 64, SPLIT = CSM_ATT_SPLIT_MMA, NCH = SPLIT / 16;
+__device__ __noinline__ void attn_bb_phase_tma(const StreamParams& p, int layer, int ph) {
+  constexpr int HD = 64, SUB = CSM_ATT_SPLIT_MMA, NCH = SUB / 16, PS = 32, NP = 2 * SUB / PS, PBYTES = PS * HD * 2;
   static_assert(REP <= 8, "query heads per kv head");
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, c = blockIdx.x, G = gridDim.x;
   const int Ttot = p.pos + 1;
-  const int nsplit = (Ttot + SPLIT - 1) / SPLIT;
+  const int nsub = p.att_nsub, split = SUB * nsub;
+  const int nsplit = (Ttot + split - 1) / split;
   const int nk = p.bb.kv;
   const int nunits = p.B * nk * nsplit;
   const int g = lane >> 2, t = lane & 3;        // MMA fragment coordinates
-  const int grp = lane >> 3, dl = lane & 7;     // merge coordinates: head grp, dims 8*dl..
   const int Wq = (p.bb.heads + 2 * nk) * HD;    // q | k | v row
   const float scale = p.bb.scale;
   const bf16* qrows = reinterpret_cast<const bf16*>(p.q_bb);
   bf16* orows = reinterpret_cast<bf16*>(p.attn_bb);
+  const uint32_t nstg = (uint32_t)p.att_stages;
+  unsigned char* stages = sm_act(p) + (size_t)warp * nstg * PBYTES;
+  uint64_t* bars = sm_attbar() + warp * 4;
+  const int first = warp * G + c, ustep = CSM_COMPUTE_WARPS * G;
+  const uint32_t npu = (uint32_t)(NP * nsub);   // pieces per unit
+  const uint32_t n0 = sm_attcnt()[warp];        // pieces this warp has streamed in earlier phases (barrier parities)
+  if (lane == 0) fence_proxy_async();           // (cache rows written by generic stores before the grid barrier)
+  // piece nn of this phase: unit k = nn / npu of this warp, sub-block sb, q = piece inside it: q < NP/2 -> K rows, else V rows
+  auto issue = [&](uint32_t nn) {
+    const int k = (int)(nn / npu), r = (int)(nn % npu), sb = r / NP, q = r % NP;
+    const int unit = first + k * ustep;
+    if (unit >= nunits) return;
+    const int sp = unit % nsplit, kvh = (unit / nsplit) % nk, b = unit / (nsplit * nk);
+    const int pp = sp * split + sb * SUB + (q % (NP / 2)) * PS;         // first position of the piece
+    const int nv = min(PS, Ttot - pp);
+    const uint32_t slot = (n0 + nn) % nstg;
+    if (nv <= 0) { mbar_arrive(&bars[slot]); return; }                  // nothing cached there: complete the phase empty
+    const bf16* src = (q < NP / 2 ? p.kc_bb : p.vc_bb) +
+                      ((((size_t)layer * p.Bmax + b) * nk + kvh) * (size_t)p.Tcap + pp) * HD;
+    mbar_expect_tx(&bars[slot], (uint32_t)nv * (HD * 2));
+    bulk_g2s(stages + (size_t)slot * PBYTES, src, (uint32_t)nv * (HD * 2), &bars[slot]);
+  };
+  if (lane == 0)
+    for (uint32_t i = 0; i < nstg; ++i) issue(i);
+  uint32_t nn = 0;
 #pragma unroll 1
-  for (int unit = warp * G + c; unit < nunits; unit += CSM_COMPUTE_WARPS * G) {
+  for (int unit = first; unit < nunits; unit += ustep) {
     const int sp = unit % nsplit;
     const int kvh = (unit / nsplit) % nk;
     const int b = unit / (nsplit * nk);
-    const size_t kvbase = (((size_t)layer * p.Bmax + b) * nk + kvh) * (size_t)p.Tcap * HD;
-    const bf16* Kp = p.kc_bb + kvbase;
-    const bf16* Vp = p.vc_bb + kvbase;
-    const int p0 = sp * SPLIT;
-    const int nch = min(NCH, (Ttot - p0 + 15) >> 4);   // chunks with at least one position (>= 1)
-    if (lane == 0) {   // HBM -> L2: this unit's V (read in the second pass) and the next unit of this warp
-      {
-        const int npos = min(SPLIT, Ttot - p0);
-        if (npos > 0) bulk_prefetch_l2(Vp + (size_t)p0 * HD, (uint32_t)npos * 128u);
-      }
-      const int nu = unit + CSM_COMPUTE_WARPS * G;
-      if (nu < nunits) {
-        const int sp2 = nu % nsplit, kvh2 = (nu / nsplit) % nk, b2 = nu / (nsplit * nk);
-        const size_t off = ((((size_t)layer * p.Bmax + b2) * nk + kvh2) * (size_t)p.Tcap + (size_t)sp2 * SPLIT) * HD;
-        const int npos = min(SPLIT, Ttot - sp2 * SPLIT);
-        if (npos > 0) {
-          bulk_prefetch_l2(p.kc_bb + off, (uint32_t)npos * 128u);
-          bulk_prefetch_l2(p.vc_bb + off, (uint32_t)npos * 128u);
-        }
-      }
-    }
-    // K rows of a chunk for this lane: positions pc + g and pc + 8 + g (j = 0, 1), dims 8t.. (words 0-3) and 32+8t..
-    // (words 4-7).  Plain word arrays with compile-time indices only (everything below is fully unrolled).
-    uint32_t kq[CSM_ATT_KBUF][16];   // chunks in flight: the unit is latency-bound, not instruction-bound
-#define CSM_LOAD_K(bf, ch)                                                                          \
-    do {                                                                                              \
-      _Pragma("unroll") for (int j = 0; j < 2; ++j) {                                                 \
-        const int pj = p0 + 16 * (ch) + 8 * j + g;                                                    \
-        uint4 x0 = make_uint4(0, 0, 0, 0), x1 = make_uint4(0, 0, 0, 0);                               \
-        if (pj < Ttot) {                                                                              \
-          x0 = ldcg_u4(Kp + (size_t)pj * HD + 8 * t);                                                 \
-          x1 = ldcg_u4(Kp + (size_t)pj * HD + 32 + 8 * t);                                            \
-        }                                                                                             \
-        kq[bf][8 * j + 0] = x0.x; kq[bf][8 * j + 1] = x0.y; kq[bf][8 * j + 2] = x0.z; kq[bf][8 * j + 3] = x0.w; \
-        kq[bf][8 * j + 4] = x1.x; kq[bf][8 * j + 5] = x1.y; kq[bf][8 * j + 6] = x1.z; kq[bf][8 * j + 7] = x1.w; \
-      }                                                                                               \
-    } while (0)
-    CSM_LOAD_K(0, 0);
-#pragma unroll
-    for (int a = 1; a < CSM_ATT_KBUF - 1; ++a)
-      if (a < nch) CSM_LOAD_K(a, a);
     // Q fragment: head g (rows >= REP are zero), this lane's 16 dims as 8 packed pairs
     uint32_t qf[8];
     {
@@ -926,146 +960,156 @@ __device__ __noinline__ void attn_bb_phase_mma(const StreamParams& p, int layer,
         for (int i = 0; i < 8; ++i) qf[i] = 0u;
       }
     }
-    // ---- S = Q K^T for the whole unit; s[ch][j][e]: head g, position p0 + 16 ch + 8 j + 2 t + e
-    float s[NCH][2][2];
-#pragma unroll
-    for (int ch = 0; ch < NCH; ++ch) {
-      if (ch + CSM_ATT_KBUF - 1 < nch) CSM_LOAD_K((ch + CSM_ATT_KBUF - 1) % CSM_ATT_KBUF, ch + CSM_ATT_KBUF - 1);
-      if (ch < nch) {
-#pragma unroll
-        for (int j = 0; j < 2; ++j) {
-          float acc[4] = {0.f, 0.f, 0.f, 0.f};
-#pragma unroll
-          for (int i = 0; i < 4; ++i) {
-            const uint32_t a[4] = {qf[2 * i], 0u, qf[2 * i + 1], 0u};
-            mma16816(acc, a, kq[ch % CSM_ATT_KBUF][8 * j + 2 * i], kq[ch % CSM_ATT_KBUF][8 * j + 2 * i + 1]);
-          }
-          const int pj = p0 + 16 * ch + 8 * j + 2 * t;
-          s[ch][j][0] = (pj < Ttot) ? acc[0] * scale : -INFINITY;
-          s[ch][j][1] = (pj + 1 < Ttot) ? acc[1] * scale : -INFINITY;
-        }
-      } else {
-        s[ch][0][0] = s[ch][0][1] = s[ch][1][0] = s[ch][1][1] = -INFINITY;
-      }
-    }
-#undef CSM_LOAD_K
-    // ---- softmax over the unit (fp32): lanes t = 0..3 of a row share a head
-    float mx = -INFINITY;
-#pragma unroll
-    for (int ch = 0; ch < NCH; ++ch) mx = fmaxf(mx, fmaxf(fmaxf(s[ch][0][0], s[ch][0][1]), fmaxf(s[ch][1][0], s[ch][1][1])));
-    mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, 1));
-    mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, 2));
-    float ls = 0.f;
-#pragma unroll
-    for (int ch = 0; ch < NCH; ++ch)
-#pragma unroll
-      for (int j = 0; j < 2; ++j)
-#pragma unroll
-        for (int e = 0; e < 2; ++e) {
-          const float pv = __expf(s[ch][j][e] - mx);   // (every unit holds at least one position: mx is finite)
-          s[ch][j][e] = pv;
-          ls += pv;
-        }
-    ls += __shfl_xor_sync(0xffffffffu, ls, 1);
-    ls += __shfl_xor_sync(0xffffffffu, ls, 2);
-    // ---- O = P V; o[jn][e]: head g, dim 8 (2 t + e) + jn
-    float o[8][4];
+    float mrun = -INFINITY, lrun = 0.f;          // running max / sum of head g (same in the 4 lanes of a row)
+    float o[8][4];                               // o[jn][e]: head g, dim 8 (2 t + e) + jn
 #pragma unroll
     for (int jn = 0; jn < 8; ++jn) o[jn][0] = o[jn][1] = o[jn][2] = o[jn][3] = 0.f;
-    // V rows of a chunk for this lane: positions pc + {2t, 2t+1, 2t+8, 2t+9} (j = 0..3), dims 8g..8g+7 (4 words)
-    uint32_t vq[CSM_ATT_VBUF][16];   // chunks in flight (the unit's V was prefetched into L2 when the unit started)
-#define CSM_LOAD_V(bf, ch)                                                                           \
-    do {                                                                                              \
-      _Pragma("unroll") for (int j = 0; j < 4; ++j) {                                                 \
-        const int pj = p0 + 16 * (ch) + 2 * t + (j & 1) + 8 * (j >> 1);                               \
-        uint4 x = make_uint4(0, 0, 0, 0);                                                             \
-        if (pj < Ttot) x = ldcg_u4(Vp + (size_t)pj * HD + 8 * g);                                     \
-        vq[bf][4 * j + 0] = x.x; vq[bf][4 * j + 1] = x.y; vq[bf][4 * j + 2] = x.z; vq[bf][4 * j + 3] = x.w; \
-      }                                                                                               \
-    } while (0)
-    CSM_LOAD_V(0, 0);
+#pragma unroll 1
+    for (int sb = 0; sb < nsub; ++sb) {
+      const int p0 = sp * split + sb * SUB;
+      const int nch = max(0, min(NCH, (Ttot - p0 + 15) >> 4));   // chunks with at least one position
+      // ---- S = Q K^T; s[ch][j][e]: head g, position p0 + 16 ch + 8 j + 2 t + e
+      float s[NCH][2][2];
 #pragma unroll
-    for (int a = 1; a < CSM_ATT_VBUF - 1; ++a)
-      if (a < nch) CSM_LOAD_V(a, a);
+      for (int q = 0; q < NP / 2; ++q, ++nn) {
+        const uint32_t slot = (n0 + nn) % nstg;
+        mbar_wait_g(p, &bars[slot], ((n0 + nn) / nstg) & 1u, ph, W_ATTN_BB_KV);
+        const unsigned char* st = stages + (size_t)slot * PBYTES;
 #pragma unroll
-    for (int ch = 0; ch < NCH; ++ch) {
-      if (ch + CSM_ATT_VBUF - 1 < nch) CSM_LOAD_V((ch + CSM_ATT_VBUF - 1) % CSM_ATT_VBUF, ch + CSM_ATT_VBUF - 1);
-      if (ch < nch) {
-        // A fragments of P: (a0, a2) = positions (2t, 2t+1), (2t+8, 2t+9); bf16 hi + lo parts
-        const float h00 = bfround(s[ch][0][0]), h01 = bfround(s[ch][0][1]), h10 = bfround(s[ch][1][0]), h11 = bfround(s[ch][1][1]);
-        const uint32_t ahi[4] = {pack_bf16(h00, h01), 0u, pack_bf16(h10, h11), 0u};
-        const uint32_t alo[4] = {pack_bf16(s[ch][0][0] - h00, s[ch][0][1] - h01), 0u,
-                                 pack_bf16(s[ch][1][0] - h10, s[ch][1][1] - h11), 0u};
+        for (int cc = 0; cc < PS / 16; ++cc) {
+          const int ch = q * (PS / 16) + cc;
+          if (ch < nch) {
 #pragma unroll
-        for (int wd = 0; wd < 4; ++wd) {   // word wd of the four rows = dims 8g + 2 wd, +1
-          const uint32_t w0 = vq[ch % CSM_ATT_VBUF][0 + wd];    // position 2t
-          const uint32_t w1 = vq[ch % CSM_ATT_VBUF][4 + wd];    // 2t+1
-          const uint32_t w2 = vq[ch % CSM_ATT_VBUF][8 + wd];    // 2t+8
-          const uint32_t w3 = vq[ch % CSM_ATT_VBUF][12 + wd];   // 2t+9
+            for (int j = 0; j < 2; ++j) {
+              // K row of position 16 cc + 8 j + g inside the piece: dims 8t.. and 32 + 8t..
+              const unsigned char* rowp = st + (size_t)(16 * cc + 8 * j + g) * (HD * 2);
+              const uint4 x0 = *reinterpret_cast<const uint4*>(rowp + 16 * t), x1 = *reinterpret_cast<const uint4*>(rowp + 64 + 16 * t);
+              const uint32_t kw[8] = {x0.x, x0.y, x0.z, x0.w, x1.x, x1.y, x1.z, x1.w};
+              float acc[4] = {0.f, 0.f, 0.f, 0.f};
 #pragma unroll
-          for (int e = 0; e < 2; ++e) {
-            const int jn = 2 * wd + e;
-            const uint32_t sel = e ? 0x7632u : 0x5410u;
-            const uint32_t b0 = __byte_perm(w0, w1, sel);
-            const uint32_t b1 = __byte_perm(w2, w3, sel);
-            mma16816(o[jn], ahi, b0, b1);
-            mma16816(o[jn], alo, b0, b1);
+              for (int i = 0; i < 4; ++i) {
+                const uint32_t a[4] = {qf[2 * i], 0u, qf[2 * i + 1], 0u};
+                mma16816(acc, a, kw[2 * i], kw[2 * i + 1]);
+              }
+              const int pj = p0 + 16 * ch + 8 * j + 2 * t;
+              s[ch][j][0] = (pj < Ttot) ? acc[0] * scale : -INFINITY;
+              s[ch][j][1] = (pj + 1 < Ttot) ? acc[1] * scale : -INFINITY;
+            }
+          } else {
+            s[ch][0][0] = s[ch][0][1] = s[ch][1][0] = s[ch][1][1] = -INFINITY;
           }
         }
+        __syncwarp();                              // every lane has read the stage
+        if (lane == 0) issue(nn + nstg);
+      }
+      // ---- softmax of the sub-block (fp32), folded into the running state: lanes t = 0..3 of a row share a head
+      float mx = mrun;
+#pragma unroll
+      for (int ch = 0; ch < NCH; ++ch) mx = fmaxf(mx, fmaxf(fmaxf(s[ch][0][0], s[ch][0][1]), fmaxf(s[ch][1][0], s[ch][1][1])));
+      mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, 1));
+      mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, 2));
+      // (a sub-block past the end of the context leaves mx = mrun; the first sub-block of a unit always holds a position)
+      const float resc = (mrun == -INFINITY) ? 0.f : __expf(mrun - mx);
+      float ls = 0.f;
+#pragma unroll
+      for (int ch = 0; ch < NCH; ++ch)
+#pragma unroll
+        for (int j = 0; j < 2; ++j)
+#pragma unroll
+          for (int e = 0; e < 2; ++e) {
+            const float pv = __expf(s[ch][j][e] - mx);
+            s[ch][j][e] = pv;
+            ls += pv;
+          }
+      ls += __shfl_xor_sync(0xffffffffu, ls, 1);
+      ls += __shfl_xor_sync(0xffffffffu, ls, 2);
+      lrun = lrun * resc + ls;
+      mrun = mx;
+      if (sb > 0) {
+#pragma unroll
+        for (int jn = 0; jn < 8; ++jn) { o[jn][0] *= resc; o[jn][1] *= resc; }   // (rows g: c0, c1; c2, c3 are rows g + 8 = zero heads)
+      }
+      // ---- O += P V
+#pragma unroll
+      for (int q = 0; q < NP / 2; ++q, ++nn) {
+        const uint32_t slot = (n0 + nn) % nstg;
+        mbar_wait_g(p, &bars[slot], ((n0 + nn) / nstg) & 1u, ph, W_ATTN_BB_KV);
+        unsigned char* st = stages + (size_t)slot * PBYTES;
+        {
+          // rows of the piece that are not cached (the tail of the context) hold whatever the stage held before:
+          // zero them (their probabilities are 0, but 0 x garbage must not be NaN)
+          const int nv = Ttot - (p0 + q * PS);
+          if (nv < PS) {   // (warp-uniform)
+            for (int r = max(nv, 0) + (lane >> 3); r < PS; r += 4)
+              *reinterpret_cast<uint4*>(st + (size_t)r * (HD * 2) + (lane & 7) * 16) = make_uint4(0, 0, 0, 0);
+            __syncwarp();
+          }
+        }
+#pragma unroll
+        for (int cc = 0; cc < PS / 16; ++cc) {
+          const int ch = q * (PS / 16) + cc;
+          if (ch < nch) {
+            // A fragments of P: (a0, a2) = positions (2t, 2t+1), (2t+8, 2t+9); bf16 hi + lo parts
+            const float h00 = bfround(s[ch][0][0]), h01 = bfround(s[ch][0][1]), h10 = bfround(s[ch][1][0]), h11 = bfround(s[ch][1][1]);
+            const uint32_t ahi[4] = {pack_bf16(h00, h01), 0u, pack_bf16(h10, h11), 0u};
+            const uint32_t alo[4] = {pack_bf16(s[ch][0][0] - h00, s[ch][0][1] - h01), 0u,
+                                     pack_bf16(s[ch][1][0] - h10, s[ch][1][1] - h11), 0u};
+            // V rows of positions 2t, 2t+1, 2t+8, 2t+9 of the chunk, dims 8g..8g+7
+            const unsigned char* vb = st + (size_t)(16 * cc + 2 * t) * (HD * 2) + 16 * g;
+            const uint4 v0 = *reinterpret_cast<const uint4*>(vb), v1 = *reinterpret_cast<const uint4*>(vb + HD * 2);
+            const uint4 v2 = *reinterpret_cast<const uint4*>(vb + 8 * HD * 2), v3 = *reinterpret_cast<const uint4*>(vb + 9 * HD * 2);
+            const uint32_t w0[4] = {v0.x, v0.y, v0.z, v0.w}, w1[4] = {v1.x, v1.y, v1.z, v1.w};
+            const uint32_t w2[4] = {v2.x, v2.y, v2.z, v2.w}, w3[4] = {v3.x, v3.y, v3.z, v3.w};
+#pragma unroll
+            for (int wd = 0; wd < 4; ++wd) {   // word wd of the four rows = dims 8g + 2 wd, +1
+#pragma unroll
+              for (int e = 0; e < 2; ++e) {
+                const int jn = 2 * wd + e;
+                const uint32_t sel = e ? 0x7632u : 0x5410u;
+                const uint32_t b0 = __byte_perm(w0[wd], w1[wd], sel);
+                const uint32_t b1 = __byte_perm(w2[wd], w3[wd], sel);
+                mma16816(o[jn], ahi, b0, b1);
+                mma16816(o[jn], alo, b0, b1);
+              }
+            }
+          }
+        }
+        __syncwarp();
+        if (lane == 0) issue(nn + nstg);
       }
     }
-#undef CSM_LOAD_V
     // partial (max, sum, o[64]) of this unit: lane (g < REP, t) holds dims 16t..16t+7 (e = 0) and 16t+8.. (e = 1)
     if (g < REP) {
-      float* part = p.attn_part + (((size_t)b * p.bb.heads + kvh * REP + g) * p.nsplit_max + sp) * (HD + 2);
+      float* part = p.attn_part + (((size_t)b * p.bb.heads + kvh * REP + g) * p.nsplit_max + sp) * (HD + 4);
 #pragma unroll
       for (int jn = 0; jn < 8; ++jn) {
-        part[2 + 16 * t + jn] = o[jn][0];
-        part[2 + 16 * t + 8 + jn] = o[jn][1];
+        part[4 + 16 * t + jn] = o[jn][0];
+        part[4 + 16 * t + 8 + jn] = o[jn][1];
       }
-      if (t == 0) { part[0] = mx; part[1] = ls; }
+      if (t == 0) { part[0] = mrun; part[1] = lrun; }
     }
-    __threadfence();
+    // publish the partial: the warp's stores are ordered before lane 0's release by the warp barrier (cumulativity);
+    // the unit that finds the count complete has, through the same atomic's acquire, every other unit's partial
     __syncwarp();
     int last = 0;
-    if (lane == 0) last = atomicAdd(p.attn_cnt + b * nk + kvh, 1u) == (unsigned)nsplit - 1u;
+    if (lane == 0) {
+      unsigned old;
+      asm volatile("atom.acq_rel.gpu.global.add.u32 %0, [%1], 1;" : "=r"(old) : "l"(p.attn_cnt + b * nk + kvh) : "memory");
+      last = old == (unsigned)nsplit - 1u;
+    }
     last = __shfl_sync(0xffffffffu, last, 0);
     if (last) {
       // last unit of this (sequence, kv-head): merge the splits and write the head outputs
-      __threadfence();
-#pragma unroll
-      for (int h0 = 0; h0 < REP; h0 += 4) {
-        const int h = h0 + grp;
-        if (h < REP) {
-          const float* part = p.attn_part + (((size_t)b * p.bb.heads + kvh * REP + h) * p.nsplit_max) * (HD + 2);
-          // (the loads of several splits are independent: unrolled so that they are in flight together)
-          float M2 = -INFINITY;
-#pragma unroll 6
-          for (int s2 = 0; s2 < nsplit; ++s2) M2 = fmaxf(M2, ldcg_f32(part + (size_t)s2 * (HD + 2)));
-          float L2 = 0.f, O2[8];
-#pragma unroll
-          for (int i = 0; i < 8; ++i) O2[i] = 0.f;
-#pragma unroll 3
-          for (int s2 = 0; s2 < nsplit; ++s2) {
-            const float* ps = part + (size_t)s2 * (HD + 2);
-            const float f = __expf(ldcg_f32(ps) - M2);
-            L2 += f * ldcg_f32(ps + 1);
-#pragma unroll
-            for (int i = 0; i < 8; ++i) O2[i] += f * ldcg_f32(ps + 2 + dl * 8 + i);
-          }
-          *reinterpret_cast<uint4*>(orows + (size_t)b * (p.bb.heads * HD) + (kvh * REP + h) * HD + dl * 8) =
-              make_uint4(pack_bf16(O2[0] / L2, O2[1] / L2), pack_bf16(O2[2] / L2, O2[3] / L2),
-                         pack_bf16(O2[4] / L2, O2[5] / L2), pack_bf16(O2[6] / L2, O2[7] / L2));
-        }
-      }
+      merge_splits<REP>(p, b, kvh, nsplit, lane, orows);
       if (lane == 0) p.attn_cnt[b * nk + kvh] = 0u;
     }
     __syncwarp();
   }
+  if (lane == 0) sm_attcnt()[warp] = n0 + nn;
 }
 
-__device__ __forceinline__ bool phase_is_staged(const Phase& P) {   // input rows copied by the activation-stream warp
-  return P.type == PH_GEMV && P.act_mode != ACT_GATHER;
+__device__ __forceinline__ bool phase_is_staged(const Phase& P) {   // something is copied by the activation-stream warp
+  return P.type == PH_GEMV;
 }
 
 }  // namespace
@@ -1095,6 +1139,8 @@ __global__ void __launch_bounds__(CSM_THREADS, 1) csm_batch_kernel(const __grid_
       mbar_init(&sm_aempty()[s], CSM_COMPUTE_WARPS);
     }
     mbar_init(sm_dfull(), 1);
+    for (int i = 0; i < CSM_COMPUTE_WARPS * 4; ++i) mbar_init(&sm_attbar()[i], 1);
+    for (int i = 0; i < CSM_COMPUTE_WARPS; ++i) sm_attcnt()[i] = 0u;
     *sm_prog() = 0u;
     mbar_fence_init();
   }
@@ -1168,10 +1214,14 @@ __global__ void __launch_bounds__(CSM_THREADS, 1) csm_batch_kernel(const __grid_
         if (P.act_mode != ACT_STREAM) {
           if (p.use_barrier && ph > p.phase_begin) grid_wait(p, (unsigned)(ph - p.phase_begin) * L.G, ph);
           fence_proxy_async();
-          const uint32_t rowbytes = (uint32_t)P.K * 2u;
-          mbar_expect_tx(sm_dfull(), rowbytes * (uint32_t)p.B);
-          for (int m = 0; m < p.B; ++m)
-            bulk_g2s(actreg + (size_t)m * (P.K + 8) * 2, actp + (size_t)m * act_stride, rowbytes, sm_dfull());
+          // rows are K + 8 elements apart in global memory as in shared memory: the [B, K+8] block is ONE copy; the
+          // norm weights of the phase ride on the same barrier (gathered phases: the weights only)
+          const uint32_t bytes = P.act_mode == ACT_GATHER ? 0u : (uint32_t)p.B * (uint32_t)(P.K + 8) * 2u;
+          const uint32_t nbytes = P.norm_w != nullptr ? (uint32_t)P.K * 2u : 0u;
+          mbar_expect_tx(sm_dfull(), bytes + nbytes);
+          if (bytes) bulk_g2s(actreg, actp, bytes, sm_dfull());
+          if (nbytes) bulk_g2s(actreg + p.normw_off, P.norm_w, nbytes, sm_dfull());
+          (void)act_stride;
           continue;
         }
         const Geom g = csm_geom(P, L.c);
@@ -1181,15 +1231,13 @@ __global__ void __launch_bounds__(CSM_THREADS, 1) csm_batch_kernel(const __grid_
         const int astride_b = (g.tpc * 16 + 8) * 2;
 #pragma unroll 1
         for (int ch = 0; ch < g.nchunks; ++ch, ++ait) {
-          const int tiles = min(g.tpc, g.ntiles - ch * g.tpc);
-          const uint32_t rowbytes = (uint32_t)tiles * 32u;
+          // the producer (gate/up phase) wrote the tiled layout [k-tile][m_alloc][len+8]: tile `ch` is ONE copy
           const uint32_t s = ait % nsa, round = ait / nsa;
           if (round > 0) mbar_wait_g(p, &sm_aempty()[s], (round - 1u) & 1u, ph, W_AEMPTY);
-          mbar_expect_tx(&sm_afull()[s], rowbytes * (uint32_t)p.B);
-          unsigned char* dst = actreg + (size_t)s * p.a_slot_bytes;
-          const unsigned char* src = reinterpret_cast<const unsigned char*>(actp) + (size_t)ch * g.tpc * 32;
-          for (int m = 0; m < p.B; ++m)
-            bulk_g2s(dst + (size_t)m * astride_b, src + (size_t)m * act_stride * 2, rowbytes, &sm_afull()[s]);
+          const uint32_t bytes = (uint32_t)p.B * (uint32_t)astride_b;
+          mbar_expect_tx(&sm_afull()[s], bytes);
+          bulk_g2s(actreg + (size_t)s * p.a_slot_bytes, reinterpret_cast<const unsigned char*>(actp) + (size_t)ch * p.m_alloc * astride_b,
+                   bytes, &sm_afull()[s]);
         }
       }
     }
@@ -1208,15 +1256,16 @@ __global__ void __launch_bounds__(CSM_THREADS, 1) csm_batch_kernel(const __grid_
         const Phase& P = p.phases[ph];
         if (P.type == PH_ATTN_BB) {
           const int Ttot = p.pos + 1, nk = p.bb.kv;
-          const int nsplit = (Ttot + CSM_ATT_SPLIT_MMA - 1) / CSM_ATT_SPLIT_MMA;
+          const int split = CSM_ATT_SPLIT_MMA * p.att_nsub;
+          const int nsplit = (Ttot + split - 1) / split;
           const int nunits = p.B * nk * nsplit;
           int done = 0;
           // (one warp per unit: the first round of this CTA's eight warps are units c, G + c, ...; later rounds are
           // prefetched by the warps themselves)
-          for (int unit = L.c; unit < nunits && done < CSM_COMPUTE_WARPS; unit += L.G, ++done) {
+          for (int unit = L.c; unit < nunits && done * p.att_nsub < p.att_pf_units; unit += L.G, ++done) {
             const int sp = unit % nsplit, kvh = (unit / nsplit) % nk, b = unit / (nsplit * nk);
-            const size_t off = ((((size_t)P.layer * p.Bmax + b) * nk + kvh) * (size_t)p.Tcap + (size_t)sp * CSM_ATT_SPLIT_MMA) * 64;
-            const int npos = min(CSM_ATT_SPLIT_MMA, p.pos - sp * CSM_ATT_SPLIT_MMA);   // positions cached before this frame
+            const size_t off = ((((size_t)P.layer * p.Bmax + b) * nk + kvh) * (size_t)p.Tcap + (size_t)sp * split) * 64;
+            const int npos = min(split, p.pos - sp * split);   // positions cached before this frame
             if (npos > 0) {
               bulk_prefetch_l2(p.kc_bb + off, (uint32_t)npos * 128u);
               bulk_prefetch_l2(p.vc_bb + off, (uint32_t)npos * 128u);
@@ -1272,7 +1321,7 @@ __global__ void __launch_bounds__(CSM_THREADS, 1) csm_batch_kernel(const __grid_
     if (prof) prof[1] = clock64();       // phase body starts
     if (type == PH_GEMV) gemv_phase<NB>(p, P, L, bar_target);
     else if (type == PH_ATTN_DEC) attn_dec_phase(p, P, L);
-    else if (type == PH_ATTN_BB) attn_bb_phase_mma<REP>(p, P.layer, ph);
+    else if (type == PH_ATTN_BB) attn_bb_phase_tma<REP>(p, P.layer, ph);
     else if (type == PH_EMBED) embed_phase(p, ph);
     else finish_phase(p, P.res_ph);
     if (prof) prof[2] = clock64();       // this thread's share of the body done

@@ -121,7 +121,7 @@ __global__ void csm_take_last_rows_kernel(const bf16* __restrict__ h, int S, int
   const int b = blockIdx.x;
   const unsigned short* src = reinterpret_cast<const unsigned short*>(h + ((size_t)b * S + (S - 1)) * H);
   if (plain) {   // general kernels: the residual stream is a plain bf16 row
-    unsigned short* d = reinterpret_cast<unsigned short*>(dst) + (size_t)(b0 + b) * H;
+    unsigned short* d = reinterpret_cast<unsigned short*>(dst) + (size_t)(b0 + b) * (H + 8);   // rows H + 8 apart
     for (int i = threadIdx.x; i < H; i += blockDim.x) d[i] = src[i];
     return;
   }

@@ -66,7 +66,8 @@ struct __align__(16) Phase {
   int flags;        // CSM_PF_*
   int bar_idx;      // number of BAR_IN phases in table[0..this]
   int gsh;          // log2(K/4) when K/4 is a power of two (staging index math by shifts), else -1
-  int pad0_;
+  int tile_sh;      // general kernels, EPI_SWIGLU feeding a streamed down_proj: log2 of the k-tile length of the output's
+                    // tiled layout [k-tile][m_alloc][len+8] (each [B, len+8] tile is one contiguous bulk copy); 0: row-major
   const bf16* w;        // packed weights, see csm_pack.cu
   const bf16* act;      // activation rows: tagged words (uint32) unless ACT_GATHER (embedding table, bf16) / ACT_STREAM (bf16)
   const bf16* norm_w;   // ACT_NORM weight
@@ -127,6 +128,12 @@ struct StreamParams {
   int slot_bytes, n_slots;
   int rope_bytes, act_region_bytes, red_bytes;
   int a_slots, a_slot_bytes;    // general kernels: ring of [B, k-chunk] activation tiles inside the activation region (K = 8192 phases)
+  int normw_off;                // general kernels: byte offset, inside the activation region, of the staged norm weights (4 KB)
+  int att_nsub;                 // general kernels: 128-position sub-blocks per backbone-attention unit (about one unit per warp)
+  int att_pf_units;             // general kernels: backbone-attention units per CTA whose K/V the L2 prefetcher pulls in ahead
+  int att_stages;               // general kernels: 4 KB stages per warp of the backbone-attention K/V ring (2..4)
+  int hpad;                     // general kernels: elements of padding after every row of the inter-phase vectors (8): a
+                                // [B, K+8] block in global memory is the shared-memory image, copied with ONE bulk copy
   unsigned long long* prof;     // debug: clock64 stamps [2 CTAs (first,last)][n_phases_total][4], see csm_stream.cu
   int n_phases_total;
   // stochastic top-k sampling (topk <= 1: greedy).  lgt: tagged logits of the last head phase [Bmax][lgt_stride]
