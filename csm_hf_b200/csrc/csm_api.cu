@@ -24,8 +24,9 @@ struct PackSrc {
 extern "C" {
 cudaError_t csm_launch_stream_small(const StreamParams* p, int grid, size_t smem, cudaStream_t stream, int cooperative);
 cudaError_t csm_launch_stream_small_stoch(const StreamParams* p, int grid, size_t smem, cudaStream_t stream, int cooperative);
-cudaError_t csm_launch_batch(const StreamParams* p, int grid, size_t smem, cudaStream_t stream, int cooperative);
-cudaError_t csm_launch_batch_stoch(const StreamParams* p, int grid, size_t smem, cudaStream_t stream, int cooperative);
+cudaError_t csm_launch_batch(const StreamParams* p, int grid, size_t smem, cudaStream_t stream, int cooperative, int cluster);
+cudaError_t csm_launch_batch_stoch(const StreamParams* p, int grid, size_t smem, cudaStream_t stream, int cooperative,
+                                   int cluster);
 cudaError_t csm_pack_launch(const PackSrc* src, const int* row_map_dev, int N, int K, int gran, int G, bf16* dst,
                             cudaStream_t stream);
 cudaError_t csm_gemm_launch(const void* map_a, const void* map_w, const GemmParams* p, int sms, cudaStream_t st);
@@ -131,6 +132,8 @@ struct CsmCtx {
   int m_alloc = 0, slot_bytes = 0, n_slots = 0, rope_bytes = 0, act_region = 0, red_bytes = 0, stream_tpc_max = 0;
   int a_slots = 2, a_slot_bytes = 0;   // activation-tile ring of the K = 8192 phases (general kernels)
   int normw_off = 0;
+  int pair = 0;                        // general kernels: CTA pairs (clusters of 2) split K of the streamed phases
+  int xbuf_off = 0;
   int mt2 = 0;                         // CSM_MT2=1: two m-tiles per warp wherever a CTA owns more than one (experiment)
   size_t smem_total = 0;
   long long launches = 0;
@@ -182,22 +185,23 @@ int copy_weight(CsmCtx* ctx, bf16** dst, const void* src, size_t n, cudaStream_t
 }
 
 int pack_matrix(CsmCtx* ctx, bf16** dst, const PackSrc& src, const std::vector<int>* row_map, int N, int K, int gran,
-                cudaStream_t st) {
+                cudaStream_t st, int G = 0) {
+  if (G == 0) G = ctx->G;   // (pair phases: rows are split over G/2 CTA pairs)
   DA(*dst, (size_t)N * K);
   int* d_map = nullptr;
   if (row_map) {
     CK(cudaMalloc(&d_map, row_map->size() * sizeof(int)));
     CK(cudaMemcpyAsync(d_map, row_map->data(), row_map->size() * sizeof(int), cudaMemcpyHostToDevice, st));
   }
-  CK(csm_pack_launch(&src, d_map, N, K, gran, ctx->G, *dst, st));
+  CK(csm_pack_launch(&src, d_map, N, K, gran, G, *dst, st));
   if (d_map) {
     CK(cudaStreamSynchronize(st));
     CK(cudaFree(d_map));
   }
   // every CTA may own at most CSM_MAX_NT*8 rows of a matrix
-  int U = N / gran, per = (U + ctx->G - 1) / ctx->G * gran;
+  int U = N / gran, per = (U + G - 1) / G * gran;
   if (per > CSM_MAX_ROWS)
-    return fail(ctx, CSM_EINVAL, "matrix with %d rows needs %d rows per CTA on a %d-CTA grid (max %d)", N, per, ctx->G,
+    return fail(ctx, CSM_EINVAL, "matrix with %d rows needs %d rows per CTA on a %d-CTA grid (max %d)", N, per, G,
                 CSM_MAX_ROWS);
   return 0;
 }
@@ -265,7 +269,9 @@ int build_stack(CsmCtx* ctx, Stack& S, const CsmLlamaShape& sh, const void* cons
     s.ptr[2] = s.ptr[1]; s.rows[2] = 0;
     for (int i = 0; i < 3; ++i) { s.row_stride[i] = H; s.col_stride[i] = 1; }
     if ((r = pack_matrix(ctx, &L.p_gu, s, &gu_map, 2 * I, H, 2, st))) return r;
-    if ((r = pack_matrix(ctx, &L.p_down, one_src((const bf16*)w[CSM_W_DOWN], H, I, 1), nullptr, H, I, 1, st))) return r;
+    if ((r = pack_matrix(ctx, &L.p_down, one_src((const bf16*)w[CSM_W_DOWN], H, I, 1), nullptr, H, I, 1, st,
+                         ctx->pair ? ctx->G / 2 : 0)))
+      return r;
   }
   int r;
   if ((r = copy_weight(ctx, &S.norm, norm, H, st))) return r;
@@ -340,6 +346,7 @@ void add_layer_phases(CsmCtx* ctx, Stack& S, int stack, int l, int dec_pos, bool
   P = gemv(ctx->direct_mlp ? ACT_PLAIN : ACT_STREAM, EPI_RESID, 1, d.H, d.I, stack, l, L.p_down, mlp, d.I + pad, nullptr, h,
            d.H + pad, ig, io);
   if (!ctx->direct_mlp) P.flags |= CSM_PF_BAR_IN;
+  P.pair = ctx->pair && !ctx->direct_mlp;
   ctx->table.push_back(P);
   h_ph = id;
 }
@@ -416,8 +423,9 @@ int plan_smem(CsmCtx* ctx) {
   for (Phase& P : ctx->table) {
     if (P.type != PH_GEMV) continue;
     const int U = P.N / P.gran;
-    P.q = U / G;
-    P.r = U % G;
+    const int Gp = P.pair ? G / 2 : G;   // pair phases: rows over CTA pairs
+    P.q = U / Gp;
+    P.r = U % Gp;
     const int g4 = P.K / 4;
     P.gsh = -1;
     if ((g4 & (g4 - 1)) == 0) { P.gsh = 0; while ((1 << P.gsh) < g4) ++P.gsh; }
@@ -443,6 +451,11 @@ int plan_smem(CsmCtx* ctx) {
     }
   }
   ctx->red_bytes = (red + 255) / 256 * 256;
+  if (ctx->pair) {   // exchange buffer of the CTA-pair phases: [m_alloc][16] fp32 behind the split-K partials
+    ctx->xbuf_off = ctx->red_bytes;
+    ctx->red_bytes += ctx->m_alloc * 16 * 4;
+    ctx->red_bytes = (ctx->red_bytes + 255) / 256 * 256;
+  }
   ctx->act_region = ctx->m_alloc * (kfull + 8) * 2;
   if (ctx->direct_mlp) {
     const int imax = ctx->bb.d.I > ctx->dec.d.I ? ctx->bb.d.I : ctx->dec.d.I;
@@ -491,7 +504,7 @@ int plan_smem(CsmCtx* ctx) {
                     (size_t)ctx->slot_bytes * ctx->n_slots;
   for (Phase& P : ctx->table) {
     if (P.type != PH_GEMV) continue;
-    const int ntiles = P.K / 16;
+    const int ntiles = P.pair ? P.K / 32 : P.K / 16;   // (pair phases: each CTA of a pair reduces over half of K)
     for (int cls = 0; cls < 2; ++cls) {
       GeoC& gc = P.geo[cls];
       const int rows = gc.rows;
@@ -566,8 +579,9 @@ cudaError_t launch_kernel(CsmCtx* ctx, const StreamParams* p, cudaStream_t st, i
   if (ctx->fuse_attn)
     return p->topk > 1 ? csm_launch_stream_small_stoch(p, ctx->G, ctx->smem_total, st, cooperative)
                        : csm_launch_stream_small(p, ctx->G, ctx->smem_total, st, cooperative);
-  return p->topk > 1 ? csm_launch_batch_stoch(p, ctx->G, ctx->smem_total, st, cooperative)
-                     : csm_launch_batch(p, ctx->G, ctx->smem_total, st, cooperative);
+  const int cluster = ctx->pair ? 2 : 1;
+  return p->topk > 1 ? csm_launch_batch_stoch(p, ctx->G, ctx->smem_total, st, cooperative, cluster)
+                     : csm_launch_batch(p, ctx->G, ctx->smem_total, st, cooperative, cluster);
 }
 
 int launch_frame(CsmCtx* ctx, int B, int ph_begin, int ph_end, const long long* ids, const int* mask, int forced,
@@ -594,6 +608,7 @@ int launch_frame(CsmCtx* ctx, int B, int ph_begin, int ph_end, const long long* 
   p.a_slots = ctx->a_slots; p.a_slot_bytes = ctx->a_slot_bytes;
   p.hpad = ctx->fuse_attn ? 0 : 8;
   p.normw_off = ctx->normw_off;
+  p.xbuf_off = ctx->xbuf_off;
   p.att_stages = ctx->act_region / (CSM_COMPUTE_WARPS * 4096);
   if (p.att_stages > 4) p.att_stages = 4;
   if (const char* e = getenv("CSM_ATT_STAGES")) { int v = atoi(e); if (v >= 1 && v <= p.att_stages) p.att_stages = v; }
@@ -809,6 +824,19 @@ int csm_create(const CsmShapes* sh, const CsmWeights* w, int max_batch, int max_
   ctx->V = sh->audio_vocab;
   ctx->text_vocab = sh->text_vocab;
   const int Hb = sh->backbone.hidden, Hd = sh->decoder.hidden;
+  // Two kernel families.  Engines for <= 2 sequences: pure dataflow (tagged words), decoder attention fused into o_proj,
+  // MLP activations staged whole (csm_stream.inl).  Larger engines: plain bf16 hand-over with a grid barrier per phase,
+  // TMA-staged activations, K = 8192 phases streamed in tiles and split over CTA pairs (csm_batch.inl).
+  ctx->fuse_attn = max_batch <= 2;
+  ctx->direct_mlp = max_batch <= 4;
+  if (const char* e = getenv("CSM_FUSE_ATTN")) ctx->fuse_attn = atoi(e) != 0;
+  if (const char* e = getenv("CSM_DIRECT_MLP")) ctx->direct_mlp = atoi(e) != 0;
+  if (!ctx->direct_mlp || max_batch > 4) ctx->fuse_attn = 0;   // the <= 2-sequence kernels have no streamed-activation path
+  ctx->bar_all = !ctx->fuse_attn;
+  // (a pair finishes at most 32 rows of a streamed matrix: its exchange buffer holds 16 per CTA)
+  ctx->pair = !ctx->fuse_attn && !ctx->direct_mlp && (ctx->G % 2 == 0) &&
+              (Hb + ctx->G / 2 - 1) / (ctx->G / 2) <= 32 && (Hd + ctx->G / 2 - 1) / (ctx->G / 2) <= 32;
+  if (const char* e = getenv("CSM_PAIR")) ctx->pair = ctx->pair && atoi(e) != 0;
   int r;
   if ((r = copy_weight(ctx, &ctx->text_emb, w->text_embeddings, (size_t)sh->text_vocab * Hb, st))) return r;
   if ((r = copy_weight(ctx, &ctx->audio_emb, w->audio_embeddings, (size_t)sh->audio_vocab * CSM_NQ * Hb, st))) return r;
@@ -877,16 +905,6 @@ int csm_create(const CsmShapes* sh, const CsmWeights* w, int max_batch, int max_
   CK(cudaMemsetAsync(ctx->n_frames, 0, 16, st));
   CK(cudaMemsetAsync(ctx->samples, 0, B * CSM_NQ * sizeof(int), st));
   CK(cudaMemsetAsync(ctx->fed, 0, B * CSM_NQ * sizeof(int), st));
-  ctx->fuse_attn = max_batch <= 2;
-  ctx->direct_mlp = max_batch <= 4;
-  if (const char* e = getenv("CSM_FUSE_ATTN")) ctx->fuse_attn = atoi(e) != 0;
-  if (const char* e = getenv("CSM_DIRECT_MLP")) ctx->direct_mlp = atoi(e) != 0;
-  // Engines for > 2 sequences keep a grid barrier between all phases on top of the tagged hand-over: with many
-  // sequences the pure dataflow chain showed rare run-to-run differences (one flaky batch-invariance run) and, before
-  // the poll back-off, multi-second stalls at 24-32 sequences; the barrier costs < 10 % there (phases are long) and
-  // nothing at 1-2 sequences, which stay pure dataflow.  CSM_BAR_ALL=0/1 overrides.
-  if (!ctx->direct_mlp || max_batch > 4) ctx->fuse_attn = 0;   // the SMALL kernels have no streamed-activation path
-  ctx->bar_all = !ctx->fuse_attn;                              // (the general kernel family)
   if (const char* e = getenv("CSM_MT2")) ctx->mt2 = atoi(e) != 0;
   build_table(ctx);
   if ((r = plan_smem(ctx))) return r;
@@ -995,6 +1013,31 @@ int csm_generate(CsmCtx* ctx, const int64_t* ids, const int32_t* mask, int B, in
     // next input row = the 32 new ids + a zero text column, audio slots unmasked (modeling_csm.py:675-690)
     r = frame_impl(ctx, nullptr, nullptr, B, 1, nullptr, (long long*)frames, stride, (long long)f * CSM_NQ,
                    stop_on_all_zeros, st);
+    if (r) return r;
+    ctx->ev_frames += 1;
+  }
+  CK(cudaEventRecord(ctx->ev1, st));
+  return CSM_OK;
+}
+
+int csm_generate_more(CsmCtx* ctx, int B, int n_more, int stop_on_all_zeros, int64_t* frames, void* stream) {
+  if (!ctx) return CSM_EINVAL;
+  if (!frames || n_more < 0) return fail(ctx, CSM_EINVAL, "bad argument");
+  if (ctx->cache_len < 1) return fail(ctx, CSM_EINVAL, "no context to continue: call csm_generate first");
+  if (ctx->cache_len + n_more > ctx->Tcap)
+    return fail(ctx, CSM_ECAPACITY, "context %d + %d more frames exceeds max_ctx %d", ctx->cache_len, n_more, ctx->Tcap);
+  cudaStream_t st = (cudaStream_t)stream;
+  ctx->ev_frames = 0;
+  CK(cudaMemsetAsync(ctx->stop_flag, 0, sizeof(int), st));
+  CK(cudaMemsetAsync(ctx->n_frames, 0, sizeof(int), st));
+  if (n_more == 0) return CSM_OK;
+  CK(cudaMemsetAsync(frames, 0, (size_t)B * n_more * CSM_NQ * sizeof(int64_t), st));
+  const long long stride = (long long)n_more * CSM_NQ;
+  CK(cudaEventRecord(ctx->ev0, st));
+  for (int f = 0; f < n_more; ++f) {
+    // next input row = the 32 ids of the last frame + a zero text column (modeling_csm.py:675-690)
+    int r = frame_impl(ctx, nullptr, nullptr, B, 1, nullptr, (long long*)frames, stride, (long long)f * CSM_NQ,
+                       stop_on_all_zeros, st);
     if (r) return r;
     ctx->ev_frames += 1;
   }

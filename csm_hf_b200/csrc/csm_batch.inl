@@ -31,6 +31,8 @@
 // Work split of a matrix W[N,K]: rows are divided evenly over the CTAs (granule 1 or 2 rows); csm_pack.cu stores each
 // CTA's rows contiguously, k16-tile major, in ldmatrix order.  The WEIGHTS are the 16-row A operand of
 // mma.sync.m16n8k16, the batch rows of the activations the 8-column B operand (NB = 1, 2 or 4 column tiles).
+#include <string.h>
+
 #include "csm_common.cuh"
 #include "csm_sample.cuh"
 
@@ -52,7 +54,7 @@ namespace {
 //   [0,64) full[8] | [64,128) empty[8] | [160,168) sflag[2] | [168,172) weight-stream progress |
 //   [256,768) 2 phase descriptors | [768,2816) 512 floats scratch | [2816,2944) tok[32] | [2944,3072) rstd[32] |
 //   [3072,3136) afull[8] | [3136,3200) aempty[8] | [3200,3208) dfull | [3328,3584) attention stage barriers [8 warps][4] |
-//   [3584,3616) attention piece counters [8 warps]
+//   [3584,3616) attention piece counters [8 warps] | [3616,3624) xbar (K-half partials of the peer CTA have arrived)
 __device__ __forceinline__ uint64_t* sm_full() { return reinterpret_cast<uint64_t*>(csm_smem); }
 __device__ __forceinline__ uint64_t* sm_empty() { return reinterpret_cast<uint64_t*>(csm_smem + 64); }
 __device__ __forceinline__ volatile int* sm_flag() { return reinterpret_cast<volatile int*>(csm_smem + 160); }
@@ -66,6 +68,7 @@ __device__ __forceinline__ uint64_t* sm_aempty() { return reinterpret_cast<uint6
 __device__ __forceinline__ uint64_t* sm_dfull() { return reinterpret_cast<uint64_t*>(csm_smem + 3200); }
 __device__ __forceinline__ uint64_t* sm_attbar() { return reinterpret_cast<uint64_t*>(csm_smem + 3328); }
 __device__ __forceinline__ uint32_t* sm_attcnt() { return reinterpret_cast<uint32_t*>(csm_smem + 3584); }
+__device__ __forceinline__ uint64_t* sm_xbar() { return reinterpret_cast<uint64_t*>(csm_smem + 3616); }
 // cos_dec | sin_dec ([32][hd/2] each) | cos_bb[pos] | sin_bb[pos]
 __device__ __forceinline__ bf16* sm_rope() { return reinterpret_cast<bf16*>(csm_smem + CSM_SM_HDR_BYTES); }
 __device__ __forceinline__ float* sm_red(const StreamParams& p) {
@@ -84,6 +87,7 @@ struct Lane {
   uint32_t slot, slot_par;                     // weight ring position of the consumer side
   uint32_t ait;                                // activation-ring chunks consumed so far (slot = ait % a_slots)
   uint32_t dpar;                               // parity of the next whole-row staging (dfull)
+  uint32_t xpar;                               // parity of the next pair exchange (xbar)
   int ph;                                      // phase being executed
   unsigned long long* prof;                    // debug stamps of this phase (thread 0 of the first / last CTA) or null
 };
@@ -103,7 +107,7 @@ struct Lane {
 // and raises the abort flag, which makes every wait in the grid give up and every later launch return at once; the
 // host reports it as an error (csm_frames_done / csm_generate_frame).  Cost: one counter increment per failed poll.
 enum WaitId { W_STAGE = 1, W_CAND = 2, W_ATTN_DEC = 3, W_ATTN_BB_Q = 4, W_ATTN_BB_KV = 5, W_RESID = 6, W_GRID = 7,
-              W_FULL = 8, W_AFULL = 9, W_EMPTY = 10, W_AEMPTY = 11, W_DFULL = 12 };
+              W_FULL = 8, W_AFULL = 9, W_EMPTY = 10, W_AEMPTY = 11, W_DFULL = 12, W_PAIR = 13 };
 
 __device__ __noinline__ bool spin_slow(const StreamParams& p, unsigned n, int ph, int id, unsigned a, unsigned b) {
   if (*reinterpret_cast<volatile int*>(p.abort_flag) != 0) return true;
@@ -421,7 +425,7 @@ __device__ __forceinline__ void gemv_core(const StreamParams& p, const Phase& P,
                                           int astride) {
   const int M = p.B;
   const int rows = gc.rows, mtiles = gc.mtiles, rows_pad = gc.rows_pad, ksl = gc.ksl;
-  int tpc = gc.tpc, nchunks = gc.nch, ntiles = P.K >> 4;
+  int tpc = gc.tpc, nchunks = gc.nch, ntiles = P.pair ? (P.K >> 5) : (P.K >> 4);   // (pair phases: this CTA's K half)
   float acc[2][NB][4];
 #pragma unroll
   for (int j = 0; j < 2; ++j)
@@ -559,9 +563,10 @@ template <int NB>
 __device__ __forceinline__ void gemv_phase(const StreamParams& p, const Phase& P, Lane& L, unsigned bar_target) {
   const int M = p.B, K = P.K;
   const bool stream = P.act_mode == ACT_STREAM;
-  const bool hi = L.c < P.r;
+  const int cc = P.pair ? (L.c >> 1) : L.c;    // pair phases: q, r, geo are per CTA pair
+  const bool hi = cc < P.r;
   const GeoC& gc = P.geo[hi ? 0 : 1];
-  const int row0 = (L.c * P.q + (hi ? L.c : P.r)) * P.gran;
+  const int row0 = (cc * P.q + (hi ? cc : P.r)) * P.gran;
   const int rows = gc.rows;
   int astride;
   if (!stream) {
@@ -607,6 +612,59 @@ __device__ __forceinline__ void gemv_phase(const StreamParams& p, const Phase& P
   CSM_STAMP(L, 6);     // all warps' MMAs done
   CSM_PROGRESS(p, L.c, L.tid, 1, 2);
 
+  if (P.pair) {
+    // ---- CTA-pair phase (streamed down_proj): this CTA holds the partial sums of its K half for the rows of BOTH CTAs.
+    // It finishes the rows [lo, hi_) of its own half of the pair's rows and sends the partials of the other rows to the
+    // peer's exchange buffer through distributed shared memory (st.shared::cluster), then one release-arrive per warp on
+    // the peer's mbarrier; the peer's contribution for its own rows arrives the same way.  EPI_RESID only.
+    const uint32_t rank = cluster_ctarank(), peer = rank ^ 1u;
+    const int half = (rows + 1) >> 1;
+    const int lo = rank ? half : 0, hi_ = rank ? rows : half, plo = rank ? 0 : half;
+    const int ks = 1 << gc.ksl, rows_pad = gc.rows_pad, kstride = p.m_alloc * rows_pad;
+    const float* red = sm_red(p);
+    float* xbuf = reinterpret_cast<float*>(reinterpret_cast<unsigned char*>(sm_red(p)) + p.xbuf_off);   // [m_alloc][16]
+    const uint32_t peer_xbuf = mapa_u32(smem_u32(xbuf), peer), peer_xbar = mapa_u32(smem_u32(sm_xbar()), peer);
+    const bool mine = u >= lo && u < hi_;
+    float vown[4] = {0.f, 0.f, 0.f, 0.f};   // (M <= 32, mstep >= 8: at most 4 rows m per thread)
+    int it = 0;
+    if (u < upc) {
+#pragma unroll 1
+      for (int m = m_first; m < M; m += mstep, ++it) {
+        const float* r = red + (size_t)m * rows_pad + u;
+        float v = 0.f;
+#pragma unroll
+        for (int kk = 0; kk < 8; ++kk)
+          if (kk < ks) v += r[kk * kstride];
+        if (mine) {
+          if (it == 0) vown[0] = v; else if (it == 1) vown[1] = v; else if (it == 2) vown[2] = v; else vown[3] = v;
+        } else {
+          st_cluster_f32(peer_xbuf + (uint32_t)(m * 16 + (u - plo)) * 4u, v);
+        }
+      }
+    }
+    __syncwarp();
+    if (L.lane == 0) mbar_arrive_remote(peer_xbar);           // 8 warps of the peer CTA complete my xbar
+    {
+      unsigned n = 0;
+      while (!mbar_try_wait_cluster(sm_xbar(), L.xpar)) {
+        if (spin_giveup(p, n, L.ph, W_PAIR, rank)) break;
+      }
+      L.xpar ^= 1u;
+    }
+    if (u < upc && mine) {
+      it = 0;
+#pragma unroll 1
+      for (int m = m_first; m < M; m += mstep, ++it) {
+        const float mv = it == 0 ? vown[0] : (it == 1 ? vown[1] : (it == 2 ? vown[2] : vown[3]));
+        const float pv = xbuf[m * 16 + (u - lo)];
+        // (K half 0) + (K half 1), in this order on both CTAs
+        const float v0 = bfround(rank ? pv + mv : mv + pv);   // nn.Linear output is bf16
+        bf16* o = P.out + (size_t)m * out_stride + row0 + u;
+        st_bf16(o, ldcg_bf16(o) + v0);                         // hf modeling_llama.py:331: residual + f(x), both bf16
+      }
+    }
+    return;
+  }
   // ---- fused epilogues (every output is plain bf16; the grid barrier after the phase publishes it)
   if (u < upc) {
     const int gran = P.gran, ks = 1 << gc.ksl, rows_pad = gc.rows_pad;
@@ -1127,7 +1185,7 @@ __global__ void __launch_bounds__(CSM_THREADS, 1) csm_batch_kernel(const __grid_
   L.lane = threadIdx.x & 31;
   L.c = blockIdx.x;
   L.G = gridDim.x;
-  L.slot = L.slot_par = L.ait = L.dpar = 0;
+  L.slot = L.slot_par = L.ait = L.dpar = L.xpar = 0;
   L.ph = p.phase_begin;
   L.prof = nullptr;
 
@@ -1139,6 +1197,7 @@ __global__ void __launch_bounds__(CSM_THREADS, 1) csm_batch_kernel(const __grid_
       mbar_init(&sm_aempty()[s], CSM_COMPUTE_WARPS);
     }
     mbar_init(sm_dfull(), 1);
+    mbar_init(sm_xbar(), CSM_COMPUTE_WARPS);
     for (int i = 0; i < CSM_COMPUTE_WARPS * 4; ++i) mbar_init(&sm_attbar()[i], 1);
     for (int i = 0; i < CSM_COMPUTE_WARPS; ++i) sm_attcnt()[i] = 0u;
     *sm_prog() = 0u;
@@ -1163,6 +1222,7 @@ __global__ void __launch_bounds__(CSM_THREADS, 1) csm_batch_kernel(const __grid_
           __ldg(reinterpret_cast<const uint4*>(p.phases + p.phase_begin) + L.tid);
   }
   __syncthreads();
+  cluster_sync_all();   // (CTA pairs: the peer's exchange barrier is initialised before anyone arrives on it)
 
   if (L.warp == CSM_COMPUTE_WARPS) {
     // ===================== weight stream producer =====================
@@ -1178,7 +1238,9 @@ __global__ void __launch_bounds__(CSM_THREADS, 1) csm_batch_kernel(const __grid_
         if (P.type != PH_GEMV) continue;
         if (p.progress != nullptr) p.progress[L.c * 4 + 2] = ph;
         const Geom g = csm_geom(P, L.c);
-        const unsigned char* src = reinterpret_cast<const unsigned char*>(P.w) + (size_t)g.row0 * P.K * 2;
+        // (pair phases: the pair's slice holds all K for the pair's rows; this CTA streams its half of the k-tiles)
+        const unsigned char* src = reinterpret_cast<const unsigned char*>(P.w) + (size_t)g.row0 * P.K * 2 +
+                                   (size_t)g.koff * g.rows * 32;
 #pragma unroll 1
         for (int ch = 0; ch < g.nchunks; ++ch) {
           const int tiles = min(g.tpc, g.ntiles - ch * g.tpc);
@@ -1236,7 +1298,8 @@ __global__ void __launch_bounds__(CSM_THREADS, 1) csm_batch_kernel(const __grid_
           if (round > 0) mbar_wait_g(p, &sm_aempty()[s], (round - 1u) & 1u, ph, W_AEMPTY);
           const uint32_t bytes = (uint32_t)p.B * (uint32_t)astride_b;
           mbar_expect_tx(&sm_afull()[s], bytes);
-          bulk_g2s(actreg + (size_t)s * p.a_slot_bytes, reinterpret_cast<const unsigned char*>(actp) + (size_t)ch * p.m_alloc * astride_b,
+          const int tile = g.koff / g.tpc + ch;   // (pair phases: the tiles of this CTA's K half)
+          bulk_g2s(actreg + (size_t)s * p.a_slot_bytes, reinterpret_cast<const unsigned char*>(actp) + (size_t)tile * p.m_alloc * astride_b,
                    bytes, &sm_afull()[s]);
         }
       }
@@ -1277,8 +1340,9 @@ __global__ void __launch_bounds__(CSM_THREADS, 1) csm_batch_kernel(const __grid_
         if (p.progress != nullptr) p.progress[L.c * 4 + 3] = ph;
         if (P.norm_w != nullptr && (ph % L.G) == L.c) bulk_prefetch_l2(P.norm_w, (uint32_t)P.K * 2u);
         const Geom g = csm_geom(P, L.c);
-        const unsigned char* src = reinterpret_cast<const unsigned char*>(P.w) + (size_t)g.row0 * P.K * 2;
-        const uint32_t total = (uint32_t)g.rows * (uint32_t)P.K * 2u;
+        const unsigned char* src = reinterpret_cast<const unsigned char*>(P.w) + (size_t)g.row0 * P.K * 2 +
+                                   (size_t)g.koff * g.rows * 32;
+        const uint32_t total = (uint32_t)g.rows * (uint32_t)g.ntiles * 32u;
 #pragma unroll 1
         for (uint32_t off = 0; off < total; off += 32768u) {
           const uint32_t n = min(32768u, total - off);
@@ -1362,16 +1426,34 @@ static BatchKernel pick_rep(int rep) {
 #define CSM_LAUNCHER csm_launch_batch
 #endif
 
-extern "C" cudaError_t CSM_LAUNCHER(const StreamParams* p, int grid, size_t smem, cudaStream_t stream, int cooperative) {
+extern "C" cudaError_t CSM_LAUNCHER(const StreamParams* p, int grid, size_t smem, cudaStream_t stream, int cooperative,
+                                    int cluster) {
   const int rep = p->bb.heads / p->bb.kv;
   const int nb = (p->B + 7) / 8;
   BatchKernel k = nb <= 1 ? pick_rep<1>(rep) : (nb <= 2 ? pick_rep<2>(rep) : pick_rep<4>(rep));
   cudaError_t e = cudaFuncSetAttribute((const void*)k, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
   if (e != cudaSuccess) return e;
+  cudaLaunchConfig_t cfg;
+  memset(&cfg, 0, sizeof cfg);
+  cfg.gridDim = dim3(grid);
+  cfg.blockDim = dim3(CSM_THREADS);
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = stream;
+  cudaLaunchAttribute attrs[2];
+  int na = 0;
   if (cooperative) {
-    void* args[] = {(void*)p};
-    return cudaLaunchCooperativeKernel((const void*)k, dim3(grid), dim3(CSM_THREADS), args, smem, stream);
+    attrs[na].id = cudaLaunchAttributeCooperative;
+    attrs[na].val.cooperative = 1;
+    ++na;
   }
-  k<<<grid, CSM_THREADS, smem, stream>>>(*p);
-  return cudaGetLastError();
+  if (cluster > 1) {   // CTA pairs (streamed phases split K inside a pair and exchange partial sums through DSMEM)
+    attrs[na].id = cudaLaunchAttributeClusterDimension;
+    attrs[na].val.clusterDim.x = (unsigned)cluster;
+    attrs[na].val.clusterDim.y = 1;
+    attrs[na].val.clusterDim.z = 1;
+    ++na;
+  }
+  cfg.attrs = attrs;
+  cfg.numAttrs = na;
+  return cudaLaunchKernelEx(&cfg, k, *p);
 }

@@ -75,7 +75,9 @@ struct __align__(16) Phase {
   bf16* norm_out;       // optional copy of the normalised rows (last_hidden_state)
   long long pad1_;
   GeoC geo[2];
-  int pad2_[16];
+  int pair;         // general kernels, streamed (K = 8192) phases: the two CTAs of a cluster own the rows of both and split
+                    // K in halves (q, r, geo are per PAIR; weights packed per pair); partial sums meet through DSMEM
+  int pad2_[15];
 };
 static_assert(sizeof(Phase) == 256, "Phase must be 256 bytes");
 
@@ -132,6 +134,8 @@ struct StreamParams {
   int att_nsub;                 // general kernels: 128-position sub-blocks per backbone-attention unit (about one unit per warp)
   int att_pf_units;             // general kernels: backbone-attention units per CTA whose K/V the L2 prefetcher pulls in ahead
   int att_stages;               // general kernels: 4 KB stages per warp of the backbone-attention K/V ring (2..4)
+  int xbuf_off;                 // general kernels: byte offset inside the reduction region of the [m_alloc][16] fp32 buffer the
+                                // peer CTA of a pair writes its K-half partial sums into
   int hpad;                     // general kernels: elements of padding after every row of the inter-phase vectors (8): a
                                 // [B, K+8] block in global memory is the shared-memory image, copied with ONE bulk copy
   unsigned long long* prof;     // debug: clock64 stamps [2 CTAs (first,last)][n_phases_total][4], see csm_stream.cu
@@ -164,20 +168,23 @@ struct GemmParams {
 
 // Row split and chunking of one weight matrix for one CTA.
 struct Geom {
-  int row0, rows;     // packed rows owned by this CTA
-  int ntiles;         // K/16
+  int row0, rows;     // packed rows owned by this CTA (pair phases: by the pair)
+  int ntiles;         // k16-tiles this CTA reduces over: K/16, or K/32 in a pair phase
   int tpc;            // k16-tiles per ring slot
   int nchunks;
+  int koff;           // first k16-tile of this CTA (pair phases: rank * ntiles)
 };
 
 __host__ __device__ inline Geom csm_geom(const Phase& P, int c) {
   Geom g;
-  const int hi = c < P.r;
+  const int cc = P.pair ? (c >> 1) : c;
+  const int hi = cc < P.r;
   const GeoC& gc = P.geo[hi ? 0 : 1];
-  g.row0 = (c * P.q + (hi ? c : P.r)) * P.gran;
+  g.row0 = (cc * P.q + (hi ? cc : P.r)) * P.gran;
   g.rows = gc.rows;
-  g.ntiles = P.K >> 4;
+  g.ntiles = P.pair ? (P.K >> 5) : (P.K >> 4);
   g.tpc = gc.tpc;
   g.nchunks = gc.nch;
+  g.koff = P.pair ? (c & 1) * g.ntiles : 0;
   return g;
 }

@@ -3,11 +3,16 @@
 Sequences are independent everywhere on the path; the only cross-sequence operation of the
 reference is the stop rule `torch.all(new_frame == 0)` over the whole batch
 (modeling_csm.py:662).  So: one process per GPU, a full weight replica each, rank r owns a
-contiguous slice of the batch, no collective on the data path, and ONE all-gather of the
-emitted frame tokens ([B_local, n, 32] int64, 256 B per sequence-frame) at the end.  The
-global stop rule is evaluated on the gathered tensor, which gives exactly the frames the
-single-GPU reference would have kept (generation is deterministic, so running a shard past
-the global stop point cannot change earlier frames).
+contiguous slice of the batch, no collective on the data path, and all-gathers of the emitted
+frame tokens ([B_local, n, 32] int64, 256 B per sequence-frame):
+
+  * stop_on_all_zeros=False: ONE all-gather at the end;
+  * stop_on_all_zeros=True: every rank generates `stop_check_every` frames at a time
+    (CSMModel.generate_more continues the same decode loop), the chunk is all-gathered and the
+    reference's stop rule is evaluated on the gathered frames -- the gather IS the stop-flag
+    exchange -- so a batch that ends early stops within one chunk instead of burning the whole
+    frame budget.  The result is exactly what the single-GPU loop returns (generation is
+    deterministic, running a shard a few frames past the stop point cannot change earlier frames).
 """
 from __future__ import annotations
 
@@ -37,7 +42,6 @@ def truncate_at_global_stop(frames: torch.Tensor) -> torch.Tensor:
 def all_gather_frames(local: torch.Tensor, batch: int, group=None) -> torch.Tensor:
     """[B_local, n, 32] on every rank -> [B, n, 32] on every rank (rank order == batch order)."""
     world = dist.get_world_size(group)
-    rank = dist.get_rank(group)
     per = (batch + world - 1) // world
     n = local.shape[1]
     pad = torch.zeros(per, n, local.shape[2], dtype=local.dtype, device=local.device)
@@ -48,25 +52,58 @@ def all_gather_frames(local: torch.Tensor, batch: int, group=None) -> torch.Tens
     for r in range(world):
         lo, hi = shard_bounds(batch, r, world)
         parts.append(out[r][: hi - lo])
-    del rank
     return torch.cat(parts, dim=0)
+
+
+def _comm_device(model, like: torch.Tensor) -> torch.device:
+    """Tensors handed to the collective live where the backend needs them: on the model's GPU under NCCL."""
+    if dist.get_backend() == "nccl":
+        return torch.device(model.device)
+    return like.device
 
 
 def generate_sharded(model, input_ids: torch.Tensor, attention_mask: Optional[torch.Tensor], max_new_frames: int = 100,
                      temperature: float = 1.0, topk: int = 50, use_cache: bool = True, stop_on_all_zeros: bool = True,
-                     group=None) -> torch.Tensor:
+                     group=None, stop_check_every: int = 16) -> torch.Tensor:
     """`CSMModel.generate` for a batch split over the ranks of `group`.  Every rank passes the
-    full batch and receives the full result."""
+    full batch and receives the full result (on the device of `input_ids`)."""
     world = dist.get_world_size(group)
     rank = dist.get_rank(group)
     B = input_ids.shape[0]
     lo, hi = shard_bounds(B, rank, world)
-    if hi > lo:
-        model.seq_base = lo      # sampling noise is keyed by the global sequence index: sharding does not change a sequence's draw
-        mask = attention_mask[lo:hi] if attention_mask is not None else None
-        local = model.generate(input_ids[lo:hi], mask, max_new_frames=max_new_frames, temperature=temperature,
-                               topk=topk, use_cache=use_cache, stop_on_all_zeros=False)
-    else:
-        local = torch.zeros(0, max_new_frames, 32, dtype=torch.long, device=input_ids.device)
-    frames = all_gather_frames(local, B, group)
-    return truncate_at_global_stop(frames) if stop_on_all_zeros else frames
+    nb = hi - lo
+    out_dev = input_ids.device
+    comm = _comm_device(model, input_ids)
+    chunk = max_new_frames if not stop_on_all_zeros else max(1, min(stop_check_every, max_new_frames))
+    old_base = getattr(model, "seq_base", 0)
+    model.seq_base = lo          # sampling noise is keyed by the global sequence index: sharding does not change a draw
+    try:
+        if nb > 0:
+            mask = attention_mask[lo:hi] if attention_mask is not None else None
+            local = model.generate(input_ids[lo:hi], mask, max_new_frames=chunk, temperature=temperature, topk=topk,
+                                   use_cache=use_cache, stop_on_all_zeros=False, reserve_frames=max_new_frames)
+        else:
+            # an empty shard generates nothing but keeps the per-call sampling counter (part of the noise seed)
+            # in step with the other ranks
+            if not (temperature == 0 or topk == 1):
+                model._sample_calls = getattr(model, "_sample_calls", 0) + 1
+            local = torch.zeros(0, chunk, 32, dtype=torch.long, device=comm)
+        parts, done = [], 0
+        while True:
+            got = all_gather_frames(local.to(comm), B, group)
+            done += got.shape[1]
+            if stop_on_all_zeros:
+                cut = truncate_at_global_stop(got)
+                parts.append(cut)
+                if cut.shape[1] < got.shape[1]:
+                    break
+            else:
+                parts.append(got)
+            if done >= max_new_frames:
+                break
+            n = min(chunk, max_new_frames - done)
+            local = model.generate_more(nb, n, stop_on_all_zeros=False) if nb > 0 else \
+                torch.zeros(0, n, 32, dtype=torch.long, device=comm)
+        return torch.cat(parts, dim=1).to(out_dev)
+    finally:
+        model.seq_base = old_base

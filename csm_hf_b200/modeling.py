@@ -426,7 +426,8 @@ class CSMModel(torch.nn.Module):
 
     # ------------------------------------------------------------------ generate
     def generate(self, input_ids: torch.Tensor, attention_mask: torch.Tensor, max_new_frames: int = 100,
-                 temperature: float = 1.0, topk: int = 50, use_cache: bool = True, stop_on_all_zeros: bool = True):
+                 temperature: float = 1.0, topk: int = 50, use_cache: bool = True, stop_on_all_zeros: bool = True,
+                 reserve_frames: int = 0):
         """modeling_csm.py:591-702 -> LongTensor [B, n, 32] on the device of `input_ids`.
 
         CPU inputs take the host-buffer C-ABI call (csm_generate_host: pinned H2D copy, all
@@ -435,7 +436,7 @@ class CSMModel(torch.nn.Module):
             raise NotImplementedError("use_cache=False loses the context in the reference itself (SURVEY.md fact 6)")
         ids, mask, _ = self._prep_inputs(input_ids, attention_mask) if input_ids.device.type == "cuda" else (None, None, None)
         B, T = input_ids.shape[:2]
-        e = self.engine(B, T + max_new_frames)
+        e = self.engine(B, T + max(max_new_frames, reserve_frames))   # (reserve_frames: room for generate_more)
         self._set_sampling(e, temperature, topk, getattr(self, "seq_base", 0))
         if max_new_frames <= 0:
             return torch.zeros(B, 0, 32, dtype=torch.long, device=input_ids.device)
@@ -459,6 +460,21 @@ class CSMModel(torch.nn.Module):
                    max_new_frames, int(bool(stop_on_all_zeros)), frames.data_ptr(), C.byref(n_out), e._stream())
             n = n_out.value
         self._kv = None
+        self._kv_serial += 1
+        return frames[:, :n].contiguous()
+
+    def generate_more(self, batch: int, n_more: int, stop_on_all_zeros: bool = True) -> torch.Tensor:
+        """Continue the last generate() for up to `n_more` frames (same decode steps, issued as a further chunk):
+        -> LongTensor [B, n, 32] on the model's device.  Used by batch-sharded generation to exchange the stop flag
+        between chunks (csm_hf_b200.dist.generate_sharded)."""
+        e = self._engine
+        if e is None:
+            raise RuntimeError("generate_more needs a preceding generate()")
+        if n_more <= 0:
+            return torch.zeros(batch, 0, 32, dtype=torch.long, device=self.device)
+        frames = torch.empty(batch, n_more, 32, dtype=torch.int64, device=self.device)
+        e.call(e.lib.csm_generate_more, batch, n_more, int(bool(stop_on_all_zeros)), frames.data_ptr(), e._stream())
+        n = e.call(e.lib.csm_frames_done, e._stream())
         self._kv_serial += 1
         return frames[:, :n].contiguous()
 

@@ -17,6 +17,7 @@ EXPORTS = [
     "csm_generate", "csm_frames_done", "csm_generate_host", "csm_info", "csm_set_stepped",
     "csm_last_decode_ms", "csm_last_error", "csm_debug_copy", "csm_debug_run_phases", "csm_debug_set_cache_len",
     "csm_debug_profile_frame", "csm_debug_progress", "csm_set_sampling", "csm_sample_topk", "csm_linear",
+    "csm_generate_more",
 ]
 
 
@@ -76,6 +77,7 @@ def load():
     lib.csm_debug_progress.argtypes = [vp, vp, vp]; lib.csm_debug_progress.restype = i32
     lib.csm_set_sampling.argtypes = [vp, i32, C.c_float, C.c_uint64, i32]; lib.csm_set_sampling.restype = i32
     lib.csm_sample_topk.argtypes = [vp, i32, i32, i32, C.c_float, C.c_uint64, vp, vp]; lib.csm_sample_topk.restype = i32
+    lib.csm_generate_more.argtypes = [vp, i32, i32, i32, i64p, vp]; lib.csm_generate_more.restype = i32
     lib.csm_linear.argtypes = [vp, i32, vp, i32, i32, i32, i32, vp, i32, vp]; lib.csm_linear.restype = i32
     _lib = lib
     return lib

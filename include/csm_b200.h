@@ -115,7 +115,11 @@ int csm_generate_frame(CsmCtx* ctx, const int64_t* ids, const int32_t* mask, int
  * (stop_on_all_zeros, :662-663) is read back with csm_frames_done. */
 int csm_generate(CsmCtx* ctx, const int64_t* ids, const int32_t* mask, int B, int T,
                  int max_new_frames, int stop_on_all_zeros, int64_t* frames, void* stream);
-/* Synchronises `stream` and returns the frame count of the last csm_generate (<0: error). */
+/* Continues the generate() loop (modeling_csm.py:644-690) of the last csm_generate / csm_generate_more call for up to
+ * n_more further frames into frames int64 [B,n_more,32] -- the same decode steps, issued in chunks, so that a caller
+ * that shards a batch over several contexts can exchange the stop flag (:662-663) between chunks. */
+int csm_generate_more(CsmCtx* ctx, int B, int n_more, int stop_on_all_zeros, int64_t* frames, void* stream);
+/* Synchronises `stream` and returns the frame count of the last csm_generate / csm_generate_more (<0: error). */
 int csm_frames_done(CsmCtx* ctx, void* stream);
 
 /* Same as csm_generate with HOST buffers: copies ids/mask in, frames out, synchronises,

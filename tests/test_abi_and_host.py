@@ -101,28 +101,54 @@ sys.path.insert(0, sys.argv[1])
 from csm_hf_b200.dist import generate_sharded, shard_bounds
 dist.init_process_group("gloo", init_method="tcp://127.0.0.1:%s" % sys.argv[2], rank=int(sys.argv[3]), world_size=2)
 class Fake:
-    """Deterministic per-sequence frames, so the gathered result can be checked exactly."""
-    def generate(self, ids, mask, max_new_frames, temperature, topk, use_cache, stop_on_all_zeros):
-        assert stop_on_all_zeros is False
-        base = ids[:, 0, 0:1].unsqueeze(1) * 1000                       # [b,1,1]
-        f = torch.arange(max_new_frames).view(1, -1, 1) * 32 + torch.arange(32).view(1, 1, -1) + 1
+    """Deterministic per-sequence frames, so the gathered result can be checked exactly.  generate() emits the first
+    chunk, generate_more() continues the same sequence of frames (as the engine's csm_generate_more does)."""
+    device = "cpu"
+    calls = 0
+    def _frames(self, base, start, n):
+        f = (torch.arange(start, start + n).view(1, -1, 1) * 32 + torch.arange(32).view(1, 1, -1) + 1)
         out = base + f
-        out[:, 4:] = 0                                                   # every sequence goes silent at frame 4
+        out[:, max(0, 4 - start):] = 0                                   # every sequence goes silent at frame 4
+        return out
+    def generate(self, ids, mask, max_new_frames, temperature, topk, use_cache, stop_on_all_zeros, reserve_frames=0):
+        assert stop_on_all_zeros is False
+        self.base = ids[:, 0, 0:1].unsqueeze(1) * 1000                   # [b,1,1]
+        self.done = max_new_frames
+        Fake.calls += 1
+        return self._frames(self.base, 0, max_new_frames)
+    def generate_more(self, batch, n, stop_on_all_zeros=True):
+        assert stop_on_all_zeros is False and batch == self.base.shape[0]
+        out = self._frames(self.base, self.done, n)
+        self.done += n
+        Fake.calls += 1
         return out
 B = 5
 ids = torch.arange(B).view(B, 1, 1).repeat(1, 3, 33)
-full = generate_sharded(Fake(), ids, None, max_new_frames=6, temperature=0, stop_on_all_zeros=True)
-ref = Fake().generate(ids, None, 6, 0, 1, True, False)[:, :4]
-assert torch.equal(full, ref), (full.shape, ref.shape)
-keep = generate_sharded(Fake(), ids, None, max_new_frames=6, temperature=0, stop_on_all_zeros=False)
-assert keep.shape == (B, 6, 32)
+ref = Fake()
+want = ref._frames(ids[:, 0, 0:1].unsqueeze(1) * 1000, 0, 12)
+# one all-gather at the end when nothing can stop the loop early
+m = Fake(); Fake.calls = 0
+keep = generate_sharded(m, ids, None, max_new_frames=12, temperature=0, stop_on_all_zeros=False)
+assert keep.shape == (B, 12, 32) and torch.equal(keep, want) and Fake.calls == 1
+# chunks of 2 frames: the all-zero frame 4 is seen in the third chunk, the remaining 6 frames are never generated
+m = Fake(); Fake.calls = 0
+full = generate_sharded(m, ids, None, max_new_frames=12, temperature=0, stop_on_all_zeros=True, stop_check_every=2)
+assert torch.equal(full, want[:, :4]), (full.shape,)
+assert Fake.calls == 3 and m.done == 6
+assert getattr(m, "seq_base", None) == 0                                 # restored after the call
+# stop rule never fires: the chunked path returns every frame
+class Loud(Fake):
+    def _frames(self, base, start, n):
+        return base + (torch.arange(start, start + n).view(1, -1, 1) * 32 + torch.arange(32).view(1, 1, -1) + 1)
+loud = generate_sharded(Loud(), ids, None, max_new_frames=7, temperature=0, stop_on_all_zeros=True, stop_check_every=3)
+assert loud.shape == (B, 7, 32)
 dist.barrier(); dist.destroy_process_group()
 print("ok")
 '''
 
 
 def test_sharded_generate_two_ranks_gloo(tmp_path):
-    """world_size-2 run of the sharding + all-gather + global stop rule on CPU (gloo)."""
+    """world_size-2 run of the sharding + all-gather + stop-flag exchange between chunks on CPU (gloo)."""
     script = tmp_path / "worker.py"
     script.write_text(WORKER)
     port = str(29500 + os.getpid() % 2000)
@@ -163,17 +189,35 @@ int main(void) {
 
 
 def test_reference_arm_prints_the_contract_line():
-    """bench.py --impl reference (the oracle port timed on the host cores) at BASELINE.json configs[0] size."""
+    """bench.py --impl reference at BASELINE.json configs[0] size.  BENCH_CPU_PORT=1 times the oracle port (seconds);
+    without it the arm drives the staged reference itself (oracle/_ref, minutes at csm-1b: run on the GPU box)."""
     import json
+    env = dict(os.environ, BENCH_CPU_PORT="1")
     res = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--impl", "reference", "--steps", "1", "--warmup", "0",
                           "--ctx", "16", "--frames", "8", "--cpu-sample-frames", "1"], capture_output=True, text=True,
-                         timeout=600)
+                         timeout=600, env=env)
     assert res.returncode == 0, res.stderr[-2000:]
     line = json.loads(res.stdout.strip().splitlines()[-1])
     assert line["impl"] == "reference" and line["metric"] == "audio_frames_per_s" and line["unit"] == "frames/s"
-    assert line["value"] > 0 and line["higher_is_better"] is True
+    assert line["value"] > 0 and line["higher_is_better"] is True and line["projected"] is True
     assert line["cpu_baseline"]["kind"] == "port" and line["cpu_baseline"]["cores"] >= 1
+    assert line["cpu_baseline"]["projected"] is True
     assert line["e2e"]["value"] == line["value"] and line["e2e"]["h2d_bytes_per_step"] == 0
+
+
+def test_staged_reference_is_what_the_harness_drives():
+    """oracle/stage_ref.py copies the reference's files UNCHANGED under oracle/_ref (git-ignored); ref_harness falls back
+    to that copy where /root/reference does not exist (the GPU box)."""
+    from oracle import ref_harness, stage_ref
+    if not stage_ref.stage():
+        pytest.skip("no reference available in this environment")
+    staged = os.path.join(ROOT, "oracle", "_ref", "modeling_csm.py")
+    assert os.path.isfile(staged) and ref_harness.reference_available()
+    src = os.path.join(stage_ref.REF_SRC, "modeling_csm.py")
+    if os.path.isfile(src):
+        assert open(src, "rb").read() == open(staged, "rb").read()
+    ign = open(os.path.join(ROOT, ".gitignore")).read()
+    assert "oracle/_ref/" in ign
 
 
 def _nvcc():
@@ -183,23 +227,25 @@ def _nvcc():
     return nvcc
 
 
-def test_experiments_for_the_next_round_still_compile(tmp_path):
-    """Two pieces are in the tree but off the product path because they have not been run on a B200 yet (DESIGN.md
-    section 7): the cp.async K/V ring form of the backbone attention (-DCSM_ATT_RING=2, general kernels) and the
-    stand-alone TMA + tcgen05 + TMEM GEMM prototype.  They must keep compiling for sm_100a, and the prototype's SASS
-    must really contain the tensor-memory / TMA instructions it is there to exercise."""
-    nvcc = _nvcc()
-    arch = ["-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-std=c++17"]
-    ring = subprocess.run([nvcc] + arch + ["-cubin", "-DCSM_ATT_RING=2", "-o", str(tmp_path / "ring.cubin"),
-                                           os.path.join(ROOT, "csm_hf_b200", "csrc", "csm_stream_general.cu")],
-                          capture_output=True, text=True)
-    assert ring.returncode == 0, ring.stderr[-2000:]
-    sass = subprocess.run(["/usr/local/cuda/bin/cuobjdump", "-sass", str(tmp_path / "ring.cubin")], capture_output=True, text=True).stdout
-    assert "LDGSTS" in sass and "LDSM" in sass and "HMMA.16816" in sass
-    exe = tmp_path / "umma_gemm"
-    g = subprocess.run([nvcc] + arch + ["-o", str(exe), os.path.join(ROOT, "tools", "micro", "umma_gemm.cu")],
-                       capture_output=True, text=True)
-    assert g.returncode == 0, g.stderr[-2000:]
-    sass = subprocess.run(["/usr/local/cuda/bin/cuobjdump", "-sass", str(exe)], capture_output=True, text=True).stdout
-    for mnemonic in ("UTCHMMA", "UTMALDG", "UTCBAR", "LDTM"):
+def test_product_library_is_blackwell_native():
+    """The shipped library runs its prefill projections on tcgen05 / TMEM / TMA: the SASS of libcsm_b200.so contains
+    the instructions (B200_PROFILING.md: tcgen05.mma -> UTC*MMA, tcgen05.ld -> LDTM, cp.async.bulk.tensor -> UTMALDG,
+    cp.async.bulk -> UBLKCP), and it links no cuBLAS."""
+    _nvcc()
+    from csm_hf_b200 import build
+    lib = build.build()
+    sass = subprocess.run(["/usr/local/cuda/bin/cuobjdump", "-sass", lib], capture_output=True, text=True).stdout
+    for mnemonic in ("UTCHMMA", "UTMALDG", "LDTM", "UBLKCP", "HMMA.16816"):
         assert mnemonic in sass, mnemonic
+    ldd = subprocess.run(["ldd", lib], capture_output=True, text=True).stdout
+    assert "cublas" not in ldd.lower()
+
+
+def test_tcgen05_prototype_still_compiles(tmp_path):
+    """tools/micro/umma_gemm.cu: the stand-alone self-checking GEMM the product kernel (csm_gemm.cu) grew out of
+    (run on a B200: profiles/r02_umma_gemm_selfcheck.txt)."""
+    nvcc = _nvcc()
+    exe = tmp_path / "umma_gemm"
+    g = subprocess.run([nvcc, "-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-std=c++17", "-o", str(exe),
+                        os.path.join(ROOT, "tools", "micro", "umma_gemm.cu")], capture_output=True, text=True)
+    assert g.returncode == 0, g.stderr[-2000:]

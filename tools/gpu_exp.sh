@@ -1,13 +1,14 @@
 #!/bin/bash
 mkdir -p gpurun_out; rm -f gpurun_out/exp.txt
-run() { echo "== B=$B $*" | tee -a gpurun_out/exp.txt; env "$@" timeout 200 python tools/phase_profile.py --batch $B 2>&1 | grep -E "decode frame|attn_bb|K-stream" | tee -a gpurun_out/exp.txt; }
-timeout 600 python -m pytest tests -m gpu -q --timeout 300 -x -k "bench_config or attention or invariance or padded" 2>&1 | tail -4 | tee -a gpurun_out/exp.txt
+run() { echo "== B=$B $*" | tee -a gpurun_out/exp.txt; env "$@" timeout 200 python tools/ncu_target.py --batch $B --frames 60 --reps 2 2>&1 | tail -1 | tee -a gpurun_out/exp.txt; }
+for B in 8; do
+run CSM_PAIR=1
+run CSM_PAIR=0
+run CSM_PAIR=0 CSM_LIB=$PWD/gpurun_variants/lib_oldattn.so
+run CSM_PAIR=0 CSM_LIB=$PWD/gpurun_variants/lib_nopair.so
+run CSM_PAIR=0 CSM_LIB=$PWD/gpurun_variants/lib_both.so
+run CSM_PAIR=1 CSM_LIB=$PWD/gpurun_variants/lib_oldattn.so
+done
 B=32
-run X=1
-run CSM_A_TPC=16
-B=16
-run X=1
-B=8
-run X=1
-run CSM_A_TPC=32
-run CSM_A_TPC=16
+run CSM_PAIR=1 CSM_LIB=$PWD/gpurun_variants/lib_oldattn.so
+run CSM_PAIR=0 CSM_LIB=$PWD/gpurun_variants/lib_both.so
