@@ -147,26 +147,38 @@ __global__ void csm_i32_to_i64_kernel(const int* __restrict__ src, long long* __
 }
 
 // ---------------------------------------------------------------- causal GQA flash attention (prefill), hd = 64
-// grid (ceil(S/64), heads, nseq); 4 warps x 16 query rows.  K/V come from the cache (already rotated),
-// q from the qkv rows.  Online softmax in fp32; P is rounded to bf16 for the PV MMA as every
-// flash kernel (incl. the SDPA kernels the reference dispatches to) does.
+// grid (ceil(S/128), heads, nseq); 8 warps x 16 query rows.  K/V come from the cache (already rotated), q from the qkv
+// rows.  K/V blocks of 64 keys are double-buffered in shared memory with cp.async (the next block is in flight while
+// this one is multiplied); K and V fragments by ldmatrix.  Online softmax in fp32; P is rounded to bf16 for the PV MMA
+// as every flash kernel (incl. the SDPA kernels the reference dispatches to) does.
+// Padding (valid != null): keys of padded frames are hidden; a query that sees no key gets a zero output.
 __device__ __forceinline__ void ldmatrix_x2_trans(uint32_t& r0, uint32_t& r1, const void* smem_row) {
   asm volatile("ldmatrix.sync.aligned.m8n8.x2.trans.shared.b16 {%0,%1}, [%2];"
                : "=r"(r0), "=r"(r1)
                : "r"(smem_u32(smem_row)));
 }
+__device__ __forceinline__ void ldmatrix_x4_plain(uint32_t (&r)[4], const void* smem_row) {
+  asm volatile("ldmatrix.sync.aligned.m8n8.x4.shared.b16 {%0,%1,%2,%3}, [%4];"
+               : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3])
+               : "r"(smem_u32(smem_row)));
+}
+__device__ __forceinline__ void cp_async16(void* dst_smem, const void* src, bool pred) {
+  const int n = pred ? 16 : 0;   // (src-size 0: the 16 bytes are zero-filled)
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(smem_u32(dst_smem)), "l"(src), "r"(n) : "memory");
+}
 
-__global__ void __launch_bounds__(128) csm_flash_prefill_kernel(const bf16* __restrict__ qkv, int S, int pos0, int b0,
+__global__ void __launch_bounds__(256) csm_flash_prefill_kernel(const bf16* __restrict__ qkv, int S, int pos0, int b0,
                                                                 int heads, int kv, const bf16* __restrict__ kc,
                                                                 const bf16* __restrict__ vc, int layer, int Bmax,
                                                                 int Tcap, float scale,
                                                                 const unsigned char* __restrict__ valid,
                                                                 bf16* __restrict__ out) {
-  constexpr int HD = 64, BQ = 64, BK = 64, LDS = 72;
-  __shared__ __align__(16) bf16 sK[BK * LDS];
-  __shared__ __align__(16) bf16 sV[BK * LDS];
-  __shared__ unsigned char sOk[BK];   // padded batches: key of this block visible (valid == null: all visible)
-  const int qt = blockIdx.x, head = blockIdx.y, bl = blockIdx.z;
+  constexpr int HD = 64, BQ = 128, BK = 64, LDS = 72;
+  __shared__ __align__(16) bf16 sK[2][BK * LDS];
+  __shared__ __align__(16) bf16 sV[2][BK * LDS];
+  __shared__ unsigned char sOk[2][BK];   // padded batches: key of the block visible (valid == null: all visible)
+  // the heaviest query blocks (longest causal prefix) are scheduled first
+  const int qt = (int)gridDim.x - 1 - (int)blockIdx.x, head = blockIdx.y, bl = blockIdx.z;
   const int b = b0 + bl;
   const int kvh = head / (heads / kv);
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, g = lane >> 2, t = lane & 3;
@@ -197,35 +209,45 @@ __global__ void __launch_bounds__(128) csm_flash_prefill_kernel(const bf16* __re
   const int last_key = min(pos0 + qt * BQ + BQ - 1, pos0 + S - 1);  // causal limit of the CTA
   const size_t kvbase = (((size_t)layer * Bmax + b) * kv + kvh) * (size_t)Tcap * HD;
   const float sl2 = scale * 1.4426950408889634f;
-  for (int k0 = 0; k0 <= last_key; k0 += BK) {
-    __syncthreads();
-    for (int i = threadIdx.x; i < BK * HD / 8; i += 128) {
-      const int kr = i / (HD / 8), c8 = i % (HD / 8);
-      uint4 kv4 = make_uint4(0, 0, 0, 0), vv4 = make_uint4(0, 0, 0, 0);
-      if (k0 + kr <= last_key) {
-        kv4 = *reinterpret_cast<const uint4*>(kc + kvbase + (size_t)(k0 + kr) * HD + c8 * 8);
-        vv4 = *reinterpret_cast<const uint4*>(vc + kvbase + (size_t)(k0 + kr) * HD + c8 * 8);
-      }
-      *reinterpret_cast<uint4*>(sK + kr * LDS + c8 * 8) = kv4;
-      *reinterpret_cast<uint4*>(sV + kr * LDS + c8 * 8) = vv4;
+  const int nblk = last_key / BK + 1;
+  // asynchronous copy of key block kb into buffer kb & 1: 64 rows x 8 chunks of 16 bytes for K and for V
+  auto load_block = [&](int kb) {
+    const int k0 = kb * BK, buf = kb & 1;
+#pragma unroll
+    for (int i = threadIdx.x; i < BK * HD / 8; i += 256) {
+      const int kr = i >> 3, c8 = i & 7;
+      const bool ok = k0 + kr <= last_key;
+      const size_t off = kvbase + (size_t)(ok ? k0 + kr : 0) * HD + c8 * 8;
+      cp_async16(&sK[buf][kr * LDS + c8 * 8], kc + off, ok);
+      cp_async16(&sV[buf][kr * LDS + c8 * 8], vc + off, ok);
     }
     if (threadIdx.x < BK) {
       const int kk = k0 + (int)threadIdx.x - pos0;   // sequence-local index of the key (valid covers this call's rows)
-      sOk[threadIdx.x] = (valid == nullptr || kk < 0 || kk >= S) ? 1 : valid[(size_t)bl * S + kk];
+      sOk[buf][threadIdx.x] = (valid == nullptr || kk < 0 || kk >= S) ? 1 : valid[(size_t)bl * S + kk];
     }
-    __syncthreads();
-    if (k0 > pos0 + q0 + 15) continue;   // whole block is in this warp's future
+    asm volatile("cp.async.commit_group;" ::: "memory");
+  };
+  load_block(0);
+  for (int kb = 0; kb < nblk; ++kb) {
+    const int k0 = kb * BK, buf = kb & 1;
+    asm volatile("cp.async.wait_group 0;" ::: "memory");
+    __syncthreads();                       // block kb has landed for every thread; everyone is done with buffer buf ^ 1
+    if (kb + 1 < nblk) load_block(kb + 1);
+    if (k0 > pos0 + q0 + 15) continue;     // whole block is in this warp's future
+    const bf16* cK = sK[buf];
+    const bf16* cV = sV[buf];
     float sc[8][4];
 #pragma unroll
     for (int j = 0; j < 8; ++j) {
 #pragma unroll
       for (int q = 0; q < 4; ++q) sc[j][q] = 0.f;
 #pragma unroll
-      for (int kt = 0; kt < 4; ++kt) {
-        const bf16* kp = sK + (8 * j + g) * LDS + kt * 16 + 2 * t;
-        const uint32_t b0r = *reinterpret_cast<const uint32_t*>(kp);
-        const uint32_t b1r = *reinterpret_cast<const uint32_t*>(kp + 8);
-        mma16816(sc[j], qa[kt], b0r, b1r);
+      for (int kp = 0; kp < 2; ++kp) {
+        // four 8x8 matrices: keys 8j..8j+7 x dims 32 kp + {0, 8, 16, 24} = the B fragments of k16-tiles 2 kp, 2 kp + 1
+        uint32_t kf[4];
+        ldmatrix_x4_plain(kf, cK + (8 * j + (lane & 7)) * LDS + 32 * kp + 8 * (lane >> 3));
+        mma16816(sc[j], qa[2 * kp], kf[0], kf[1]);
+        mma16816(sc[j], qa[2 * kp + 1], kf[2], kf[3]);
       }
     }
     // mask + online softmax (base-2 exponent with the scale folded in)
@@ -233,7 +255,7 @@ __global__ void __launch_bounds__(128) csm_flash_prefill_kernel(const bf16* __re
 #pragma unroll
     for (int j = 0; j < 8; ++j) {
       const int key = k0 + 8 * j + 2 * t;
-      const bool ok0 = sOk[8 * j + 2 * t] != 0, ok1 = sOk[8 * j + 2 * t + 1] != 0;
+      const bool ok0 = sOk[buf][8 * j + 2 * t] != 0, ok1 = sOk[buf][8 * j + 2 * t + 1] != 0;
       if (key > p_lo || !ok0) sc[j][0] = -INFINITY;
       if (key + 1 > p_lo || !ok1) sc[j][1] = -INFINITY;
       if (key > p_hi || !ok0) sc[j][2] = -INFINITY;
@@ -270,7 +292,7 @@ __global__ void __launch_bounds__(128) csm_flash_prefill_kernel(const bf16* __re
 #pragma unroll
       for (int jd = 0; jd < 8; ++jd) {
         uint32_t b0r, b1r;
-        ldmatrix_x2_trans(b0r, b1r, sV + (16 * kk + (lane & 15)) * LDS + 8 * jd);
+        ldmatrix_x2_trans(b0r, b1r, cV + (16 * kk + (lane & 15)) * LDS + 8 * jd);
         mma16816(o[jd], pa[kk], b0r, b1r);
       }
     }
@@ -362,8 +384,8 @@ cudaError_t csm_i32_to_i64_launch(const int* src, long long* dst, int n, cudaStr
 cudaError_t csm_flash_prefill_launch(const bf16* qkv, int S, int pos0, int b0, int nseq, int heads, int kv,
                                      const bf16* kc, const bf16* vc, int layer, int Bmax, int Tcap, float scale,
                                      const unsigned char* valid, bf16* out, cudaStream_t st) {
-  dim3 grid((S + 63) / 64, heads, nseq);
-  csm_flash_prefill_kernel<<<grid, 128, 0, st>>>(qkv, S, pos0, b0, heads, kv, kc, vc, layer, Bmax, Tcap, scale, valid, out);
+  dim3 grid((S + 127) / 128, heads, nseq);
+  csm_flash_prefill_kernel<<<grid, 256, 0, st>>>(qkv, S, pos0, b0, heads, kv, kc, vc, layer, Bmax, Tcap, scale, valid, out);
   return cudaGetLastError();
 }
 

@@ -707,15 +707,17 @@ def test_weight_io_and_module_surface(dev, tmp_path):
 
 
 # ------------------------------------------------------------------ protocol stress
-@pytest.mark.parametrize("B", [1, 2])
-def test_dataflow_stress_bit_identical(dev, B):
-    """1 000 frames through the pure-dataflow kernels (engines for <= 2 sequences: no grid barrier between phases),
-    twice: bit-identical ids.  A lost or reordered hand-over would show as a difference (or as the hang guard's error)."""
+@pytest.mark.parametrize("B,frames", [(1, 1000), (2, 1000), (8, 400), (20, 300)])
+def test_protocol_stress_bit_identical(dev, B, frames):
+    """Long runs, twice, bit-identical ids: 1 000 frames through the pure-dataflow kernels (engines for <= 2 sequences:
+    tagged-word hand-over, no grid barrier) and 300-400 frames through the general kernels (grid barrier per phase, TMA
+    staging, CTA-pair exchange through DSMEM, per-warp attention rings whose barrier parities persist across phases).
+    A lost or reordered hand-over would show as a difference, or as the hang guard's error."""
     from csm_hf_b200.modeling import CSMModel
     cfg = tiny_config()
-    model = CSMModel(cfg, make_state_dict(cfg, seed=12, norm_jitter=0.1), device=dev, max_batch=B, max_ctx=1100)
+    model = CSMModel(cfg, make_state_dict(cfg, seed=12, norm_jitter=0.1), device=dev, max_batch=B, max_ctx=frames + 100)
     ids, mask = make_context(cfg, B, 7, seed=90 + B)
-    a = model.generate(ids, mask, max_new_frames=1000, temperature=0, stop_on_all_zeros=False)
-    b = model.generate(ids, mask, max_new_frames=1000, temperature=0, stop_on_all_zeros=False)
-    assert tuple(a.shape) == (B, 1000, 32) and torch.equal(a, b)
+    a = model.generate(ids, mask, max_new_frames=frames, temperature=0, stop_on_all_zeros=False)
+    b = model.generate(ids, mask, max_new_frames=frames, temperature=0, stop_on_all_zeros=False)
+    assert tuple(a.shape) == (B, frames, 32) and torch.equal(a, b)
     model._drop_engine()
