@@ -129,9 +129,11 @@ __device__ __forceinline__ bool spin_giveup(const StreamParams& p, unsigned& n, 
 // finished; phase `ph` may start once all G CTAs have finished phase ph-1.
 __device__ __forceinline__ void grid_wait(const StreamParams& p, unsigned target, int ph) {
   unsigned n = 0;
-  while (ld_acquire_u32(p.bar_counter) < target) {
+  // relaxed polls (no fence per round trip), then ONE acquire load that synchronises with the release increments
+  while (ld_tag(p.bar_counter) < target) {
     if (spin_giveup(p, n, ph, W_GRID, target)) break;
   }
+  (void)ld_acquire_u32(p.bar_counter);
 }
 __device__ __forceinline__ void mbar_wait_g(const StreamParams& p, uint64_t* bar, uint32_t parity, int ph, int id) {
   unsigned n = 0;
@@ -606,6 +608,11 @@ __device__ __forceinline__ void gemv_phase(const StreamParams& p, const Phase& P
   const int m_first = ush >= 8 ? 0 : L.tid >> ush;
   const int epi = P.epi;
   const int out_stride = P.out_stride;
+  // residual element of the first row this thread will update: requested now, used after the MMAs (its L2 round trip
+  // would otherwise sit on the critical path of the epilogue).  Written >= one grid barrier ago.
+  float resid0 = 0.f;
+  if (epi == EPI_RESID && !P.pair && u < upc && m_first < M)
+    resid0 = ldcg_bf16(P.out + (size_t)m_first * out_stride + row0 + u * P.gran);
   if (rows > 0) gemv_core<NB>(p, P, gc, L, stream, astride);
   CSM_STAMP(L, 5);     // this warp's MMAs done
   compute_sync();
@@ -695,7 +702,7 @@ __device__ __forceinline__ void gemv_phase(const StreamParams& p, const Phase& P
       v1 = bfround(v1);
       if (epi == EPI_RESID) {   // hf modeling_llama.py:325,331: residual + f(x), both bf16
         bf16* o = P.out + (size_t)m * out_stride + gn;
-        st_bf16(o, ldcg_bf16(o) + v0);
+        st_bf16(o, (m == m_first ? resid0 : ldcg_bf16(o)) + v0);
       } else if (epi == EPI_SWIGLU) {  // hf modeling_llama.py:183: bf16(silu(gate)) * up -> bf16 ; rows (2j,2j+1)=(gate_j,up_j)
         const float sl = bfround(v0 / (1.f + expf(-v0)));
         const int j = gn >> 1;
