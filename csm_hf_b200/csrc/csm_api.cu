@@ -8,7 +8,9 @@
 #include <stdlib.h>
 #include <string.h>
 
+#include <chrono>
 #include <string>
+#include <thread>
 #include <vector>
 
 #include "../../include/csm_b200.h"
@@ -137,7 +139,8 @@ struct CsmCtx {
   int mt2 = 0;                         // CSM_MT2=1: two m-tiles per warp wherever a CTA owns more than one (experiment)
   size_t smem_total = 0;
   long long launches = 0;
-  cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+  cudaEvent_t ev0 = nullptr, ev1 = nullptr, ev_done = nullptr;
+  double wait_budget_s = 120.0;   // host-side watchdog of csm_frames_done / csm_generate_host (CSM_WAIT_BUDGET_S)
   int ev_frames = 0;
   std::vector<void*> allocs;
   std::string err;
@@ -562,10 +565,34 @@ int begin_epoch(CsmCtx* ctx, cudaStream_t st) {
 void end_epoch(CsmCtx* ctx) { ctx->tagbase += (unsigned)ctx->table.size(); }
 
 // A wait inside a frame kernel timed out (hang guard, csm_stream.cu): report who waited for what.  Synchronises.
+// Host-side watchdog: wait for the stream with a deadline instead of blocking for ever.  The frame kernels of the
+// <= 2-sequence engines carry no in-kernel hang guard (it costs them 13-16 %, measured: DESIGN.md section 3.1), so a lost
+// hand-over there would spin until the driver's own watchdog; the caller at least gets an error, not a hung process.
+int wait_stream(CsmCtx* ctx, cudaStream_t st, double budget_s) {
+  cudaEvent_t ev = ctx->ev_done;
+  CK(cudaEventRecord(ev, st));
+  const auto t0 = std::chrono::steady_clock::now();
+  for (unsigned it = 0;; ++it) {
+    cudaError_t e = cudaEventQuery(ev);
+    if (e == cudaSuccess) return 0;
+    if (e != cudaErrorNotReady) return fail(ctx, CSM_ECUDA, "stream failed: %s", cudaGetErrorString(e));
+    if ((it & 63u) == 63u) {
+      const double dt = std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
+      if (dt > budget_s)
+        return fail(ctx, CSM_ECUDA, "frame kernels did not finish within %.0f s (a hand-over was lost?): the device needs a "
+                    "reset", budget_s);
+      if (dt > 0.002) std::this_thread::sleep_for(std::chrono::microseconds(50));
+    }
+  }
+}
+
 int check_abort(CsmCtx* ctx, cudaStream_t st) {
   int a[8] = {0, 0, 0, 0, 0, 0, 0, 0};
   CK(cudaMemcpyAsync(a, ctx->abort_flag, sizeof a, cudaMemcpyDeviceToHost, st));
-  CK(cudaStreamSynchronize(st));
+  {
+    int r = wait_stream(ctx, st, ctx->wait_budget_s);
+    if (r) return r;
+  }
   if (a[0] == 0) return 0;
   CK(cudaMemsetAsync(ctx->abort_flag, 0, sizeof a, st));   // the engine stays usable (reset + new generate)
   return fail(ctx, CSM_ECUDA,
@@ -918,6 +945,8 @@ int csm_create(const CsmShapes* sh, const CsmWeights* w, int max_batch, int max_
   CK(cudaMemcpyAsync(ctx->d_table, ctx->table.data(), ctx->table.size() * sizeof(Phase), cudaMemcpyHostToDevice, st));
   CK(cudaEventCreate(&ctx->ev0));
   CK(cudaEventCreate(&ctx->ev1));
+  CK(cudaEventCreateWithFlags(&ctx->ev_done, cudaEventDisableTiming));
+  if (const char* e = getenv("CSM_WAIT_BUDGET_S")) ctx->wait_budget_s = atof(e) > 0 ? atof(e) : ctx->wait_budget_s;
   CK(cudaStreamSynchronize(st));
   return CSM_OK;
 }
@@ -934,6 +963,7 @@ int csm_destroy(CsmCtx* ctx) {
   if (ctx->pf_valid) cudaFree(ctx->pf_valid);
   if (ctx->ev0) cudaEventDestroy(ctx->ev0);
   if (ctx->ev1) cudaEventDestroy(ctx->ev1);
+  if (ctx->ev_done) cudaEventDestroy(ctx->ev_done);
   delete ctx;
   return CSM_OK;
 }

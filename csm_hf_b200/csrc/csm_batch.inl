@@ -295,34 +295,45 @@ __device__ __forceinline__ void attn_dec_phase(const StreamParams& p, const Phas
     const size_t kvbase = (((size_t)layer * p.Bmax + b) * nk + kvh) * (size_t)CSM_DEC_POS * HD;
     const bf16* kp = p.kc_dec + kvbase + (size_t)lane * HD;
     const bf16* vp = p.vc_dec + kvbase + lane * 4;
+    // ONE batch of independent loads -- q, this lane's K row, this lane's dims of the first 16 V rows -- so that the unit
+    // costs one L2 round trip instead of three in a row (the phase is a latency chain, nothing here is bandwidth)
     const uint2 q2 = ldcg_u2(qrow + (size_t)b * W + head * HD + lane * 4);
+    uint4 kk[HD / 8];
+#pragma unroll
+    for (int ci = 0; ci < HD / 8; ++ci) kk[ci] = ldcg_u4(kp + ci * 8);   // (rows > dec_pos: in bounds, masked below)
+    uint2 vv[16];
+#pragma unroll
+    for (int j = 0; j < 16; ++j) vv[j] = ldcg_u2(vp + (size_t)j * HD);
     __syncwarp();            // (the previous unit's reads of qs are done)
     *reinterpret_cast<float4*>(qs + lane * 4) = make_float4(bf_lo(q2.x) * sc, bf_hi(q2.x) * sc, bf_lo(q2.y) * sc, bf_hi(q2.y) * sc);
     __syncwarp();            // qs written by all lanes before any lane reads it
     float d = 0.f;
-    if (lane <= dec_pos) {
-#pragma unroll 8
-      for (int ci = 0; ci < HD / 8; ++ci) {
-        const uint4 kv = ldcg_u4(kp + ci * 8);
-        const float4 a = *reinterpret_cast<const float4*>(qs + ci * 8), c4 = *reinterpret_cast<const float4*>(qs + ci * 8 + 4);
-        d += a.x * bf_lo(kv.x) + a.y * bf_hi(kv.x) + a.z * bf_lo(kv.y) + a.w * bf_hi(kv.y);
-        d += c4.x * bf_lo(kv.z) + c4.y * bf_hi(kv.z) + c4.z * bf_lo(kv.w) + c4.w * bf_hi(kv.w);
-      }
+#pragma unroll
+    for (int ci = 0; ci < HD / 8; ++ci) {
+      const float4 a = *reinterpret_cast<const float4*>(qs + ci * 8), c4 = *reinterpret_cast<const float4*>(qs + ci * 8 + 4);
+      d += a.x * bf_lo(kk[ci].x) + a.y * bf_hi(kk[ci].x) + a.z * bf_lo(kk[ci].y) + a.w * bf_hi(kk[ci].y);
+      d += c4.x * bf_lo(kk[ci].z) + c4.y * bf_hi(kk[ci].z) + c4.z * bf_lo(kk[ci].w) + c4.w * bf_hi(kk[ci].w);
     }
     const float s = lane <= dec_pos ? d : -INFINITY;
     const float mx = warp_max(s);
-    const float pe = (lane <= dec_pos) ? __expf(s - mx) : 0.f;
+    const float pe = (lane <= dec_pos) ? __expf(s - mx) : 0.f;   // (0 for positions past dec_pos: stale cache rows drop out)
     const float l = warp_sum(pe);
     float o0 = 0.f, o1 = 0.f, o2 = 0.f, o3 = 0.f;
-#pragma unroll 1
-    for (int t0 = 0; t0 <= dec_pos; t0 += 16) {
-      uint2 vv[16];
 #pragma unroll
-      for (int j = 0; j < 16; ++j) vv[j] = (t0 + j <= dec_pos) ? ldcg_u2(vp + (size_t)(t0 + j) * HD) : make_uint2(0, 0);
+    for (int j = 0; j < 16; ++j) {
+      const float pv = __shfl_sync(0xffffffffu, pe, j);
+      if (j <= dec_pos) {
+        o0 += pv * bf_lo(vv[j].x); o1 += pv * bf_hi(vv[j].x);
+        o2 += pv * bf_lo(vv[j].y); o3 += pv * bf_hi(vv[j].y);
+      }
+    }
+    if (dec_pos >= 16) {   // (warp-uniform) second half of the positions
+#pragma unroll
+      for (int j = 0; j < 16; ++j) vv[j] = (16 + j <= dec_pos) ? ldcg_u2(vp + (size_t)(16 + j) * HD) : make_uint2(0, 0);
 #pragma unroll
       for (int j = 0; j < 16; ++j) {
-        const float pv = __shfl_sync(0xffffffffu, pe, (t0 + j) & 31);
-        if (t0 + j <= dec_pos) {
+        const float pv = __shfl_sync(0xffffffffu, pe, 16 + j);
+        if (16 + j <= dec_pos) {
           o0 += pv * bf_lo(vv[j].x); o1 += pv * bf_hi(vv[j].x);
           o2 += pv * bf_lo(vv[j].y); o3 += pv * bf_hi(vv[j].y);
         }
