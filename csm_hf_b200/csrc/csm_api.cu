@@ -636,9 +636,17 @@ int launch_frame(CsmCtx* ctx, int B, int ph_begin, int ph_end, const long long* 
   p.hpad = ctx->fuse_attn ? 0 : 8;
   p.normw_off = ctx->normw_off;
   p.xbuf_off = ctx->xbuf_off;
-  p.att_stages = ctx->act_region / (CSM_COMPUTE_WARPS * 4096);
-  if (p.att_stages > 4) p.att_stages = 4;
-  if (const char* e = getenv("CSM_ATT_STAGES")) { int v = atoi(e); if (v >= 1 && v <= p.att_stages) p.att_stages = v; }
+  // backbone-attention K/V pieces: as large as the per-warp share of the activation region allows (fewer, larger
+  // bulk copies), at most 128 positions; the stages that fit behind that
+  {
+    const int per_warp = ctx->act_region / CSM_COMPUTE_WARPS;
+    int ps = per_warp >= 16384 ? 128 : (per_warp >= 8192 ? 64 : 32);
+    if (const char* e = getenv("CSM_ATT_PS")) { int v = atoi(e); if ((v == 32 || v == 64 || v == 128) && v * 128 <= per_warp) ps = v; }
+    p.att_ps = ps;
+    p.att_stages = per_warp / (ps * 128);
+    if (p.att_stages > 4) p.att_stages = 4;
+    if (const char* e = getenv("CSM_ATT_STAGES")) { int v = atoi(e); if (v >= 1 && v <= p.att_stages) p.att_stages = v; }
+  }
   {
     // units of the backbone attention: (sequence, kv-head, nsub x 128 positions): the smallest nsub for which every
     // compute warp of the grid gets at most ONE unit -- a unit is one long chain of dependent L2 / HBM round trips

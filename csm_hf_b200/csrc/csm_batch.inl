@@ -963,8 +963,8 @@ __device__ __forceinline__ void merge_splits(const StreamParams& p, int b, int k
 // the cache: the qkv phase wrote position `pos` before the grid barrier that precedes this phase.
 //
 //   staging   : a unit's K rows (128 bytes per position) and V rows are contiguous in the cache, so they travel as bulk
-//               copies of 32 positions (4 KB) through a per-warp ring of 2-4 stages (the activation region, free during
-//               this phase), each completing on its own mbarrier; lane 0 issues piece n + stages as soon as the warp
+//               copies of 32-128 positions (4-16 KB) through a per-warp ring of 1-4 stages (the activation region, free
+//               during this phase), each completing on its own mbarrier; lane 0 issues piece n + stages as soon as the warp
 //               has consumed piece n -- across sub-block and unit boundaries, so loads stay in flight while a unit is
 //               reduced and merged.  The L2 prefetch warp pulls the K/V of the CTA's first units into L2 ahead of time.
 //   S = Q K^T : A = the REP query heads of the group (rows >= REP are zero), B = 8 cached positions per n-tile, k = the
@@ -980,9 +980,9 @@ __device__ __forceinline__ void merge_splits(const StreamParams& p, int b, int k
 // is 512 positions -- 4x fewer partial results, fences, counters and merges than with 128-position units.
 // Units write (max, sum, o[64]) partials; the last unit of a (sequence, kv-head) to arrive merges the splits and writes
 // the head outputs (plain bf16).  A sequence's result does not depend on the batch it is in for a given nsub.
-template <int REP>
+template <int REP, int PS>
 __device__ __noinline__ void attn_bb_phase_tma(const StreamParams& p, int layer, int ph) {
-  constexpr int HD = 64, SUB = CSM_ATT_SPLIT_MMA, NCH = SUB / 16, PS = 32, NP = 2 * SUB / PS, PBYTES = PS * HD * 2;
+  constexpr int HD = 64, SUB = CSM_ATT_SPLIT_MMA, NCH = SUB / 16, NP = 2 * SUB / PS, PBYTES = PS * HD * 2;
   static_assert(REP <= 8, "query heads per kv head");
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, c = blockIdx.x, G = gridDim.x;
   const int Ttot = p.pos + 1;
@@ -1403,7 +1403,13 @@ __global__ void __launch_bounds__(CSM_THREADS, 1) csm_batch_kernel(const __grid_
     if (prof) prof[1] = clock64();       // phase body starts
     if (type == PH_GEMV) gemv_phase<NB>(p, P, L, bar_target);
     else if (type == PH_ATTN_DEC) attn_dec_phase(p, P, L);
-    else if (type == PH_ATTN_BB) attn_bb_phase_tma<REP>(p, P.layer, ph);
+    else if (type == PH_ATTN_BB) {
+      // K/V pieces of 32 / 64 / 128 positions (4 / 8 / 16 KB bulk copies): the TMA engine spends ~0.25-0.35 us per
+      // bulk copy whatever its size (measured), so the largest piece the per-warp share of the activation region holds
+      if (p.att_ps == 128) attn_bb_phase_tma<REP, 128>(p, P.layer, ph);
+      else if (p.att_ps == 64) attn_bb_phase_tma<REP, 64>(p, P.layer, ph);
+      else attn_bb_phase_tma<REP, 32>(p, P.layer, ph);
+    }
     else if (type == PH_EMBED) embed_phase(p, ph);
     else finish_phase(p, P.res_ph);
     if (prof) prof[2] = clock64();       // this thread's share of the body done

@@ -132,6 +132,7 @@ struct StreamParams {
   int a_slots, a_slot_bytes;    // general kernels: ring of [B, k-chunk] activation tiles inside the activation region (K = 8192 phases)
   int normw_off;                // general kernels: byte offset, inside the activation region, of the staged norm weights (4 KB)
   int att_nsub;                 // general kernels: 128-position sub-blocks per backbone-attention unit (about one unit per warp)
+  int att_ps;                   // general kernels: positions per K/V piece of the backbone attention (32, 64 or 128)
   int att_pf_units;             // general kernels: backbone-attention units per CTA whose K/V the L2 prefetcher pulls in ahead
   int att_stages;               // general kernels: 4 KB stages per warp of the backbone-attention K/V ring (2..4)
   int xbuf_off;                 // general kernels: byte offset inside the reduction region of the [m_alloc][16] fp32 buffer the
