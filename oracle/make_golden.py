@@ -82,10 +82,33 @@ def main():
                          "256-frame context at batch 8 and 32 (tens of minutes of CPU)")
     ap.add_argument("--padded", action="store_true", help="mint the left-padded variable-length batch fixtures (tiny)")
     ap.add_argument("--only", default="", help="with --bench: comma list of b1,b8,b32")
+    ap.add_argument("--decisive", action="store_true",
+                    help="search seeds of the tiny config whose FREE-RUNNING greedy ids are the same in the reference's fp32 "
+                         "and bf16 runs (every argmax margin exceeds the arithmetic noise), and mint them")
     a = ap.parse_args()
     assert R.reference_available(), "needs /root/reference"
     torch.manual_seed(0)
     tiny = tiny_config()
+    if a.decisive:
+        # Greedy decoding at random init is chaotic: one near-tie and two correct implementations part ways (SURVEY.md
+        # fact 2).  A fixture on which free-running ids CAN be compared exactly is one where the reference agrees with
+        # itself across precisions: its fp32 and bf16 runs emit identical ids for every frame.
+        found = 0
+        for seed in range(400):   # (one sequence, three frames = 96 argmax decisions: ~1 seed in 30 qualifies)
+            ids, mask = make_context(tiny, 1, 12, seed=7000 + seed, text_frames=2)
+            outs = []
+            for dt in (torch.float32, torch.bfloat16):
+                model = ref_model("tiny", tiny, dt, 40 + seed % 5, 0.1)
+                outs.append(R.reference_generate(model, ids, mask, 3))
+            if torch.equal(outs[0], outs[1]):
+                found += 1
+                mint(f"tiny_decisive{found}_bf16.pt", "tiny", tiny, torch.bfloat16, B=1, T=12, n=3, wseed=40 + seed % 5, jitter=0.1,
+                     cseed=7000 + seed, text_frames=2)
+                print(f"  decisive: weight seed {40 + seed % 5}, context seed {7000 + seed}", flush=True)
+                if found == 3:
+                    break
+        assert found == 3, f"only {found} decisive fixtures found"
+        return
     if a.padded:
         # N3: sequences of 8, 5 and 3 frames left-padded to 8 (processor.py:137-169); pads are hidden in the prefill
         # and attended to (K = V = 0) in the decode steps -- whatever the reference does is the definition

@@ -165,6 +165,20 @@ def test_csm1b_config1_vs_reference_golden(dev):
     del model
 
 
+@pytest.mark.parametrize("i", [1, 2, 3])
+@pytest.mark.parametrize("max_batch", [1, 8])
+def test_free_running_exact_ids_on_decisive_fixtures(dev, i, max_batch):
+    """Bit-exact greedy ids, FREE-RUNNING (no teacher forcing), against the reference -- on the fixtures where that is a
+    well-posed demand: seeds for which the reference's own fp32 and bf16 runs emit identical ids (oracle/make_golden.py
+    --decisive), i.e. every one of the 96 argmax margins exceeds the arithmetic noise.  Both kernel families."""
+    from csm_hf_b200.modeling import CSMModel
+    g, cfg, dtype, sd, ids, mask = load_golden(f"tiny_decisive{i}_bf16.pt")
+    model = CSMModel(cfg, sd, device=dev, max_batch=max_batch, max_ctx=64)
+    frames = model.generate(ids, mask, max_new_frames=g["recipe"]["new_frames"], temperature=0, stop_on_all_zeros=False)
+    assert torch.equal(frames, g["frames"])
+    model._drop_engine()
+
+
 # ------------------------------------------------------------------ properties of the cached path
 def test_cached_decode_equals_recompute(tiny):
     """KV-cached step == prefill of the extended context (SURVEY.md §0.4's functional definition),

@@ -55,6 +55,17 @@ def test_csm1b_config1_fp32_tokens():
     assert (c0 - g["c0_logits"]).abs().max() < 5e-5
 
 
+@pytest.mark.parametrize("i", [1, 2, 3])
+def test_free_running_ids_on_decisive_fixtures(i):
+    """Fixtures on which the reference agrees with ITSELF across precisions (its fp32 and bf16 runs emit the same ids
+    for three free-running frames: oracle/make_golden.py --decisive): every argmax margin exceeds the arithmetic noise,
+    so a correct implementation must reproduce the ids exactly, free-running, no teacher forcing."""
+    g, cfg, dtype, sd, ids, mask = load_golden(f"tiny_decisive{i}_bf16.pt")
+    for dt in (torch.bfloat16, torch.float32):
+        frames = CSMOracle(cfg, sd, dt).generate(ids, mask, g["recipe"]["new_frames"])
+        assert torch.equal(frames, g["frames"]), dt
+
+
 def test_bench_config_t2048_oracle_vs_reference():
     """The benchmarked configuration (csm-1b, 2048-frame context, batch 1), prefill frame: the fp32 oracle reproduces
     the reference's fp32 run (ids exact, logits to 1e-4); the bf16 oracle -- the arithmetic the CUDA engine

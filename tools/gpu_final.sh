@@ -1,9 +1,28 @@
 #!/bin/bash
-# Round-end check of the build in the tree: all GPU parity tests, the default bench line, decode ms/frame at 32 and 8 sequences.
+# Round-end evidence in one call: all GPU tests, the bench line as the driver runs it, per-phase profiles, ncu launch
+# lists and --set full captures of the three kernels that matter.
 mkdir -p gpurun_out
-timeout 400 python -m pytest tests -m gpu -q --timeout 120 > gpurun_out/pytest_gpu.log 2>&1; echo "pytest rc=$?" >> gpurun_out/pytest_gpu.log
-tail -5 gpurun_out/pytest_gpu.log
-timeout 300 python bench.py --steps 3 --warmup 3 > gpurun_out/bench_b1.json 2> gpurun_out/bench_b1.err
-cat gpurun_out/bench_b1.json
-timeout 120 python tools/ncu_target.py --batch 32 --frames 40 --reps 1 2>&1 | tail -1
-timeout 120 python tools/ncu_target.py --batch 8 --frames 60 --reps 1 2>&1 | tail -1
+timeout 1200 python -m pytest tests -m gpu -q --timeout 600 2>&1 | tail -4 | tee gpurun_out/pytest_gpu.log
+BENCH_VERBOSE=1 timeout 1500 python bench.py --gpus 1 --steps 20 --warmup 5 > gpurun_out/bench.json 2> gpurun_out/bench.err
+tail -2 gpurun_out/bench.err
+timeout 900 python bench.py --impl reference --gpus 1 --steps 20 --warmup 5 > gpurun_out/bench_ref.json 2> gpurun_out/bench_ref.err
+for b in 1 8 32; do timeout 300 python tools/phase_profile.py --batch $b 2>&1 | grep -v Warning > gpurun_out/phase_b${b}.txt; done
+for b in 1 8; do
+  timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none -c 600 --csv --log-file gpurun_out/launches_b$b.csv \
+      python tools/ncu_target.py --batch $b --frames 4 > gpurun_out/ncu_launch_b$b.log 2>&1
+done
+timeout 600 ncu --set full --clock-control none --import-source on -k regex:csm_batch_kernel -s 2 -c 1 -o gpurun_out/ncu_batch_b8 -f \
+    python tools/ncu_target.py --batch 8 --frames 5 > gpurun_out/ncu_full_b8.log 2>&1
+timeout 600 ncu --set full --clock-control none --import-source on -k regex:csm_gemm_kernel -s 8 -c 8 -o gpurun_out/ncu_gemm_b8 -f \
+    python tools/ncu_target.py --batch 8 --frames 2 > gpurun_out/ncu_full_gemm.log 2>&1
+timeout 600 ncu --set full --clock-control none --import-source on -k regex:csm_flash_prefill_kernel -s 3 -c 1 -o gpurun_out/ncu_flash_b8 -f \
+    python tools/ncu_target.py --batch 8 --frames 2 > gpurun_out/ncu_full_flash.log 2>&1
+python - <<'PY'
+import json
+j=json.loads(open('gpurun_out/bench.json').read().strip().splitlines()[-1])
+print('value', j['value'], 'e2e', j['e2e']['value'], 'frac', j['roofline']['frac'], 'verified', (j['verified'] or {}).get('ok'), 'launches', j['gpu_launches'])
+for p in j['config']['points']: print(p['batch_per_gpu'], round(p['value'],1), 'ms/frame', round(p['decode_ms_per_frame'],3), 'frac', round(p['roofline']['frac'],3), 'prefill ms', round(p['prefill']['ms_incl_first_frame'],2), 'tf frac', round(p['prefill']['frac'],3))
+print(j.get('cpu_baseline'))
+print(open('gpurun_out/bench_ref.json').read()[-900:])
+PY
+ls -la gpurun_out/*.ncu-rep
