@@ -60,6 +60,16 @@ def measured_peaks():
     return 6650.0, "fallback (B200_PROFILING.md 6.65 TB/s)", 1400.0, "fallback (B200_PROFILING.md ~1.4 PFLOP/s sustained)"
 
 
+def ncu_traffic(batch):
+    """dram__bytes_read.sum + dram__bytes_write.sum of ONE frame launch at this batch size (profiles/traffic.json: taken
+    from the committed ncu --set full captures), or None when that batch size was not captured."""
+    tp = os.path.join(ROOT, "profiles", "traffic.json")
+    if not os.path.isfile(tp):
+        return None
+    with open(tp) as f:
+        return json.load(f).get(f"b{batch}")
+
+
 class ClockSampler:
     Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
          "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
@@ -340,7 +350,7 @@ def main():
                "ms_per_step": ms_step, "steps": steps, "decode_ms_per_frame": dec_per,
                "decode_frames_per_s_per_gpu": batch * 1000.0 / dec_per if dec_per > 0 else 0.0,
                "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                            "algorithmic_bytes_per_launch": abytes},
+                            "algorithmic_bytes_per_launch": abytes, "traffic": ncu_traffic(batch)},
                "prefill": {"ms_incl_first_frame": pre_ms, "bound": "tensor", "achieved": ptf, "peak": tpeak,
                            "unit": "TFLOP/s", "frac": ptf / tpeak},
                "launches": int(eng.info(4) - launches0), "out0": out[0, :3].cpu() if rank == 0 else None}
@@ -399,11 +409,7 @@ def main():
             dist.destroy_process_group()
         return
     e2e_value = GB * a.frames / (e2e_ms / 1000.0 / a.steps)
-    traffic = None
-    tp = os.path.join(ROOT, "profiles", "traffic.json")
-    if os.path.isfile(tp):
-        with open(tp) as f:
-            traffic = json.load(f).get(f"b{a.batch}")
+    traffic = ncu_traffic(a.batch)
     rl = dict(head["roofline"])
     rl.update({"kernel": "csm_stream_kernel (one launch = one frame for the whole batch)", "peak_source": peak_src,
                "traffic": traffic})

@@ -52,12 +52,19 @@ def state_dict_shapes(cfg: CSMConfig) -> Dict[str, Tuple[int, ...]]:
 
 def make_state_dict(cfg: CSMConfig, seed: int = 0, dtype: torch.dtype = torch.float32,
                     std: float = 0.02, norm_jitter: float = 0.0,
-                    head_gain: float = 1.0) -> Dict[str, torch.Tensor]:
+                    head_gain: float = 1.0, head_pair_gain: float = 0.0) -> Dict[str, torch.Tensor]:
     """N(0, std) for every matrix, norm weights 1 (+ jitter), one generator per key.
 
     head_gain multiplies codebook0_head / audio_head: the "peaky" variant of
     SURVEY.md §8d, whose top-1 margins are far above one bf16 ulp so that free-running
     greedy tokens are well defined across accumulation orders.
+
+    head_pair_gain > 0 builds "decisive" heads: in every codebook's head two tokens get the
+    rows +g*r and -g*r (r = the first token's random row), so one of them wins the argmax by
+    a margin of ~2x its own logit unless r.h is within 1/g of zero -- greedy decoding then has
+    margins of hundreds of bf16 ulps and free-running ids are comparable exactly across
+    implementations (oracle/make_golden.py --decisive; a uniform gain would scale the
+    margins and the ulps alike).
     """
     sd: Dict[str, torch.Tensor] = {}
     for name, shape in state_dict_shapes(cfg).items():
@@ -70,6 +77,17 @@ def make_state_dict(cfg: CSMConfig, seed: int = 0, dtype: torch.dtype = torch.fl
             t = torch.empty(shape, dtype=torch.float32).normal_(0.0, std, generator=g)
             if name in ("codebook0_head.weight", "audio_head"):
                 t *= head_gain
+                if head_pair_gain > 0:
+                    V = cfg.audio_vocab_size
+                    if name == "audio_head":                       # [31, H, V]: columns are tokens
+                        for c in range(t.shape[0]):
+                            b = torch.randperm(V, generator=g)[:2]
+                            t[c, :, b[0]] *= head_pair_gain
+                            t[c, :, b[1]] = -t[c, :, b[0]]
+                    else:                                          # [V, H]: rows are tokens
+                        b = torch.randperm(V, generator=g)[:2]
+                        t[b[0]] *= head_pair_gain
+                        t[b[1]] = -t[b[0]]
         sd[name] = t.to(dtype)
     return sd
 

@@ -14,7 +14,7 @@ def load_golden(name):
     r = g["recipe"]
     cfg = tiny_config() if r["config"] == "tiny" else CSMConfig()
     dtype = getattr(torch, r["dtype"])
-    sd = make_state_dict(cfg, seed=r["weight_seed"], norm_jitter=r["norm_jitter"])
+    sd = make_state_dict(cfg, seed=r["weight_seed"], norm_jitter=r["norm_jitter"], head_pair_gain=r.get("head_pair_gain", 0.0))
     if r.get("lengths"):
         ids, mask = make_padded_context(cfg, r["lengths"], r["ctx_frames"], seed=r["ctx_seed"], text_frames=r["text_frames"])
     else:

@@ -34,12 +34,15 @@ for a, s, e, txt in sass:
     tot += s
 top = int(sys.argv[4]) if len(sys.argv) > 4 else 40
 src = open('csm_hf_b200/csrc/csm_stream.inl').read().split('\n')
+bat = open('csm_hf_b200/csrc/csm_batch.inl').read().split('\n')
 com = open('csm_hf_b200/csrc/csm_common.cuh').read().split('\n')
 print("total samples", tot)
 for k, s in samp.most_common(top):
     text = ""
     if k and k[0] in ('csm_stream.cu', 'csm_stream.inl'):
         text = src[k[1] - 1].strip()
+    elif k and k[0] == 'csm_batch.inl':
+        text = bat[k[1] - 1].strip()
     elif k and k[0] == 'csm_common.cuh':
         text = com[k[1] - 1].strip()
     print(f"{100 * s / tot:5.1f}% {s:7d} exec {exe[k]:10d}  {k}  {text[:110]}")
