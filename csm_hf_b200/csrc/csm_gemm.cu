@@ -130,7 +130,7 @@ csm_gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty + 2);
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int mt = (p.R + BM - 1) / BM, nt = (p.N + BN - 1) / BN, ntiles = mt * nt;
-  const int nkb = p.K / BK;
+  const int nkb = (p.K + BK - 1) / BK;   // (a ragged last k-block is zero-filled by TMA on both operands)
 
   if (threadIdx.x == 0) {
     for (int s = 0; s < STAGES; ++s) { mbar_init(&full[s], 1); mbar_init(&empty[s], 1); }
@@ -318,7 +318,9 @@ int csm_gemm_box_rows_w() { return BN; }
 
 cudaError_t csm_gemm_launch(const void* map_a, const void* map_w, const GemmParams* p, int sms, cudaStream_t st) {
   if (p->R <= 0) return cudaSuccess;
-  if (p->K % BK || p->N % 64) return cudaErrorInvalidValue;
+  // STORE / RESID: any K (the tensor maps zero-fill past the end), N a multiple of 32; the fused tails need whole tiles
+  if (p->N % 32 || p->K < 1) return cudaErrorInvalidValue;
+  if ((p->epi == EPI_SWIGLU || p->epi == EPI_QKV) && (p->K % BK || p->N % 64)) return cudaErrorInvalidValue;
   const int mt = (p->R + BM - 1) / BM, nt = (p->N + BN - 1) / BN;
   const int grid = mt * nt < sms ? mt * nt : sms;
   const CUtensorMap& ma = *reinterpret_cast<const CUtensorMap*>(map_a);

@@ -21,7 +21,7 @@ Differences from the reference, all deliberate and documented in DESIGN.md:
   * a float32 attention mask (what CSMProcessor emits when it pads, processor.py:148) is accepted with a
     bf16 model (the reference raises a dtype error there, SURVEY.md fact 5);
   * `past_key_values` is an opaque handle to the engine's in-place KV cache;
-  * `labels` (training) raises NotImplementedError (N1).
+  * `labels` (training): csm_hf_b200/training.py -- loss and parameter gradients from csm_train_step.
 """
 from __future__ import annotations
 
@@ -414,8 +414,9 @@ class CSMModel(torch.nn.Module):
                 output_attentions=None, output_hidden_states=None, return_dict=None, temperature=1.0, topk=50,
                 generate_frame=False, labels=None):
         """Inference branch of modeling_csm.py:292-365,467-482: last_hidden_state + codebook-0 logits."""
-        if labels is not None:
-            raise NotImplementedError("training forward (labels) is the next row (SURVEY.md §8f N1)")
+        if labels is not None:   # training: loss branch of modeling_csm.py:367-465, forward + backward on the GPU
+            from .training import training_forward
+            return training_forward(self, input_ids, attention_mask, labels, return_dict)
         out = self.generate_frame(input_ids, attention_mask, position_ids=position_ids, temperature=0.0, topk=1,
                                   past_key_values=past_key_values, use_cache=use_cache, return_dict=True)
         return_dict = True if return_dict is None else return_dict

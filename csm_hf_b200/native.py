@@ -18,6 +18,8 @@ EXPORTS = [
     "csm_last_decode_ms", "csm_last_error", "csm_debug_copy", "csm_debug_run_phases", "csm_debug_set_cache_len",
     "csm_debug_profile_frame", "csm_debug_progress", "csm_set_sampling", "csm_sample_topk", "csm_linear",
     "csm_generate_more",
+    "csm_train_create", "csm_train_destroy", "csm_train_last_error", "csm_train_launches", "csm_train_step",
+    "csm_train_debug",
 ]
 
 
@@ -78,6 +80,14 @@ def load():
     lib.csm_set_sampling.argtypes = [vp, i32, C.c_float, C.c_uint64, i32]; lib.csm_set_sampling.restype = i32
     lib.csm_sample_topk.argtypes = [vp, i32, i32, i32, C.c_float, C.c_uint64, vp, vp]; lib.csm_sample_topk.restype = i32
     lib.csm_generate_more.argtypes = [vp, i32, i32, i32, i64p, vp]; lib.csm_generate_more.restype = i32
+    lib.csm_train_create.argtypes = [C.POINTER(Shapes), i32, i32, C.POINTER(vp)]; lib.csm_train_create.restype = i32
+    lib.csm_train_destroy.argtypes = [vp]; lib.csm_train_destroy.restype = i32
+    lib.csm_train_last_error.argtypes = [vp]; lib.csm_train_last_error.restype = C.c_char_p
+    lib.csm_train_launches.argtypes = [vp]; lib.csm_train_launches.restype = i32
+    lib.csm_train_step.argtypes = [vp, C.POINTER(Weights), C.POINTER(Weights), i64p, vp, i64p, i32, i32,
+                                   C.POINTER(C.c_float), C.POINTER(C.c_int), vp, vp, vp]
+    lib.csm_train_step.restype = i32
+    lib.csm_train_debug.argtypes = [vp, C.c_char_p, vp, C.c_longlong, C.POINTER(C.c_longlong)]; lib.csm_train_debug.restype = i32
     lib.csm_linear.argtypes = [vp, i32, vp, i32, i32, i32, i32, vp, i32, vp]; lib.csm_linear.restype = i32
     _lib = lib
     return lib

@@ -138,3 +138,27 @@ def make_padded_context(cfg: CSMConfig, lengths, frames: int, seed: int = 1234, 
         ids[b, :npad, nq] = pad_text_id
         mask[b, :npad, :] = 0
     return ids, mask.to(mask_dtype)
+
+
+def make_training_batch(cfg: CSMConfig, batch: int, frames: int, seed: int = 4321, text_frames: int = 2,
+                        amortization_ratio: int = 16, pad: int = 0):
+    """Synthetic training batch in the shape CSMProcessor emits (processor.py:200-380): `text_frames` text-only frames,
+    then audio frames; labels = the audio tokens for codebook 0 on every audio frame and for codebooks 1..31 on one
+    frame in `amortization_ratio` (decoder amortisation, processor.py:340-360), -100 elsewhere.  `pad` > 0 left-pads
+    sequence 0 with that many all-zero-mask frames whose labels are -100 (processor.py:142-160).
+    -> ids [B,S,33] int64, mask [B,S,33] int32, labels [B,S,33] int64."""
+    g = torch.Generator().manual_seed(seed)
+    nq = cfg.audio_num_codebooks
+    ids, mask = make_context(cfg, batch, frames, seed=seed, text_frames=text_frames)
+    labels = torch.full_like(ids, -100)
+    labels[:, text_frames:, 0] = ids[:, text_frames:, 0]
+    n_audio = frames - text_frames
+    for b in range(batch):
+        n_sel = max(1, n_audio // amortization_ratio)
+        sel = torch.randperm(n_audio, generator=g)[:n_sel] + text_frames
+        labels[b, sel, :nq] = ids[b, sel, :nq]
+    if pad:
+        ids[0, :pad] = 0
+        mask[0, :pad] = 0
+        labels[0, :pad] = -100
+    return ids, mask, labels

@@ -184,6 +184,38 @@ int csm_debug_progress(CsmCtx* ctx, int32_t* host_out, void* side_stream);
  * info_host[4*phases] = (type, epilogue, stack, act_mode) per phase. Synchronises. */
 int csm_debug_profile_frame(CsmCtx* ctx, int B, uint64_t* clocks_host, int32_t* info_host, void* stream);
 
+/* ------------------------------------------------------------------------------------------------------------
+ * Training step: CSMModel.forward(input_ids, attention_mask, labels=...) and the backward
+ * of its loss -- reference modeling_csm.py:292-482 (loss branch :367-465), called by CSMTrainer.compute_loss
+ * (train.py:303-326) and differentiated by torch autograd there.
+ *
+ * The training context owns only workspace (saved activations, per-step fused / transposed weight copies); the
+ * parameters and the gradient tensors stay the caller's and are passed on every step, in the reference's layout. */
+typedef struct CsmTrain CsmTrain;
+
+/* max_tokens: largest B*S of a step; max_frames: largest number of frames carrying all 32 audio labels in a step
+ * (the decoder runs on those only: 1/16 amortisation, processor.py:340-360).  rope tables of `shapes` must cover the
+ * longest sequence (backbone) and 33 positions (decoder). */
+int csm_train_create(const CsmShapes* shapes, int max_tokens, int max_frames, CsmTrain** out);
+int csm_train_destroy(CsmTrain* t);
+const char* csm_train_last_error(const CsmTrain* t);
+int csm_train_launches(const CsmTrain* t);
+
+/* weights: the current parameters (device, bf16).  grads: where to WRITE d loss / d parameter (same layout, device,
+ * bf16; not accumulated), or NULL for the loss alone.
+ * ids int64 [B,S,33]; mask int32 [B,S,33] or NULL (= attention_mask=None: all 33 slots summed, nothing padded);
+ * labels int64 [B,S,33] with -100 = ignore.  losses: HOST float[3] = loss, backbone_loss, decoder_loss
+ * (modeling_csm.py:389,467,471); n_frames: HOST int, frames the decoder ran on (may be NULL).
+ * last_h bf16 [B,Hb] and c0_logits bf16 [B,V]: the last position's outputs (:363-365), device, may be NULL.
+ * Synchronises the stream (the frame count is needed on the host, as the reference's nonzero() :399). */
+int csm_train_step(CsmTrain* t, const CsmWeights* weights, const CsmWeights* grads, const int64_t* ids,
+                   const int32_t* mask, const int64_t* labels, int B, int S, float* losses, int* n_frames,
+                   void* last_h, void* c0_logits, void* stream);
+
+/* Tests: host copy of a named intermediate of the last step ("bb.0.qkv", "dec.1.attn", "d.bb.x0", ...); host == NULL
+ * returns only its size in bytes. */
+int csm_train_debug(CsmTrain* t, const char* name, void* host, long long cap, long long* bytes);
+
 #ifdef __cplusplus
 }
 #endif

@@ -84,6 +84,9 @@ def main():
                          "256-frame context at batch 8 and 32 (tens of minutes of CPU)")
     ap.add_argument("--padded", action="store_true", help="mint the left-padded variable-length batch fixtures (tiny)")
     ap.add_argument("--only", default="", help="with --bench: comma list of b1,b8,b32")
+    ap.add_argument("--train", action="store_true",
+                    help="mint the training fixtures (tiny config): the reference's loss triple and parameter gradients of "
+                         "CSMModel.forward(labels=...) + backward on a synthetic amortised, left-padded batch")
     ap.add_argument("--decisive", action="store_true",
                     help="search seeds of the tiny config whose FREE-RUNNING greedy ids are the same in the reference's fp32 "
                          "and bf16 runs (every argmax margin exceeds the arithmetic noise), and mint them")
@@ -91,6 +94,37 @@ def main():
     assert R.reference_available(), "needs /root/reference"
     torch.manual_seed(0)
     tiny = tiny_config()
+    if a.train:
+        from csm_hf_b200.synthetic import make_training_batch
+        recipe = dict(config="tiny", batch=2, frames=24, seed=4321, text_frames=2, amortization_ratio=4, pad=3,
+                      weight_seed=5, norm_jitter=0.1)
+        ids, mask, labels = make_training_batch(tiny, recipe["batch"], recipe["frames"], seed=recipe["seed"],
+                                                text_frames=recipe["text_frames"],
+                                                amortization_ratio=recipe["amortization_ratio"], pad=recipe["pad"])
+        sd = make_state_dict(tiny, seed=recipe["weight_seed"], norm_jitter=recipe["norm_jitter"])
+        for dt, tag in ((torch.float32, "fp32"), (torch.bfloat16, "bf16")):
+            m = R.build_reference_model(tiny, sd, dt)
+            for p in m.parameters():
+                p.requires_grad_(True)
+            out = m(input_ids=ids, attention_mask=mask, labels=labels)   # modeling_csm.py:292-482
+            out.loss.backward()
+            grads = {k: p.grad.detach() for k, p in m.state_dict(keep_vars=True).items()}
+            fx = {"recipe": dict(recipe, dtype=tag), "loss": out.loss.detach().float(),
+                  "backbone_loss": out.backbone_loss.detach().float(), "decoder_loss": out.decoder_loss.detach().float(),
+                  "grad_norms": {k: float(g.float().norm()) for k, g in grads.items()}}
+            if dt == torch.bfloat16:
+                fx["grads"] = {}
+                for k, g in grads.items():   # (embedding tables: only the rows the batch touched are non-zero)
+                    g = g.to(torch.bfloat16)
+                    if k.endswith("embeddings.weight"):
+                        rows = (g != 0).any(dim=1).nonzero().flatten()
+                        fx["grads"][k] = {"shape": tuple(g.shape), "rows": rows, "values": g[rows].clone()}
+                    else:
+                        fx["grads"][k] = g
+            torch.save(fx, os.path.join(GOLD, f"tiny_train_{tag}.pt"))
+            print(f"tiny_train_{tag}.pt: loss {float(out.loss):.6f} = {float(out.backbone_loss):.6f} + "
+                  f"{float(out.decoder_loss):.6f}; {len(grads)} gradients", flush=True)
+        return
     if a.decisive:
         # Greedy decoding at random init is chaotic: one near-tie and two correct implementations part ways (SURVEY.md
         # fact 2).  A fixture on which free-running ids CAN be compared exactly is one where the reference agrees with

@@ -45,3 +45,12 @@ def assert_tokens_match_where_decided(got_tok, want_tok, want_logits, tol_abs, w
     bad = (got_tok != want_tok) & decided
     assert not bool(bad.any()), f"{what}: {int(bad.sum())} decided tokens differ"
     return float(decided.float().mean())
+
+
+def dense_grad(entry):
+    """A gradient of tests/golden/tiny_train_bf16.pt: embedding tables are stored as (rows, values)."""
+    if isinstance(entry, dict):
+        g = torch.zeros(entry["shape"], dtype=entry["values"].dtype)
+        g[entry["rows"]] = entry["values"]
+        return g
+    return entry
