@@ -107,3 +107,36 @@ def generate_sharded(model, input_ids: torch.Tensor, attention_mask: Optional[to
         return torch.cat(parts, dim=1).to(out_dev)
     finally:
         model.seq_base = old_base
+
+
+def allreduce_gradients(model, group=None, bucket_bytes: int = 256 << 20) -> int:
+    """Data-parallel training (plain DP, one replica per GPU): average the parameter gradients
+    over the ranks after loss.backward().  Gradients are packed into flat buckets of ~`bucket_bytes` (3.1 GB of bf16
+    gradients for csm-1b -> a dozen NCCL all-reduces over NVLink instead of 187), summed, scaled by 1/world and
+    unpacked in place.  Works with any backend (gloo on CPU in the tests).  -> number of buckets reduced."""
+    world = dist.get_world_size(group)
+    grads = [p.grad for _, p in sorted(model.named_parameters()) if p.grad is not None]
+    if world == 1 or not grads:
+        return 0
+    buckets, cur, cur_bytes = [], [], 0
+    for g in grads:
+        nbytes = g.numel() * g.element_size()
+        if cur and (cur_bytes + nbytes > bucket_bytes or g.dtype != cur[0].dtype):
+            buckets.append(cur)
+            cur, cur_bytes = [], 0
+        cur.append(g)
+        cur_bytes += nbytes
+    if cur:
+        buckets.append(cur)
+    for b in buckets:
+        flat = torch.cat([g.reshape(-1) for g in b])
+        if flat.dtype == torch.bfloat16 and flat.device.type == "cpu":
+            flat = flat.float()                       # (gloo has no bf16 sum)
+        dist.all_reduce(flat, op=dist.ReduceOp.SUM, group=group)
+        flat.div_(world)
+        off = 0
+        for g in b:
+            n = g.numel()
+            g.copy_(flat[off:off + n].view_as(g))
+            off += n
+    return len(buckets)

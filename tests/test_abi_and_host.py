@@ -249,3 +249,40 @@ def test_tcgen05_prototype_still_compiles(tmp_path):
     g = subprocess.run([nvcc, "-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-std=c++17", "-o", str(exe),
                         os.path.join(ROOT, "tools", "micro", "umma_gemm.cu")], capture_output=True, text=True)
     assert g.returncode == 0, g.stderr[-2000:]
+
+
+GRAD_WORKER = r'''
+import sys, torch, torch.distributed as dist
+sys.path.insert(0, sys.argv[1])
+from csm_hf_b200.dist import allreduce_gradients
+rank = int(sys.argv[3])
+dist.init_process_group("gloo", init_method="tcp://127.0.0.1:%s" % sys.argv[2], rank=rank, world_size=2)
+torch.manual_seed(0)
+m = torch.nn.ModuleDict({"a": torch.nn.Linear(64, 48, bias=False), "b": torch.nn.Linear(48, 8, bias=False),
+                         "c": torch.nn.Embedding(100, 64)}).to(torch.bfloat16)
+both = []
+for r in range(2):
+    g = torch.Generator().manual_seed(10 + r)
+    both.append({k: torch.randn(p.shape, generator=g).to(torch.bfloat16) for k, p in m.named_parameters()})
+for k, p in m.named_parameters():
+    p.grad = both[rank][k].clone()
+n = allreduce_gradients(m, bucket_bytes=8000)            # several buckets
+assert n >= 2, n
+for k, p in m.named_parameters():
+    want = ((both[0][k].float() + both[1][k].float()) / 2).to(torch.bfloat16)
+    assert torch.equal(p.grad, want), k
+dist.barrier(); dist.destroy_process_group()
+print("ok")
+'''
+
+
+def test_gradient_allreduce_two_ranks_gloo(tmp_path):
+    """Data-parallel training plumbing (SURVEY.md 8e / N1): bucketed average of the parameter gradients over 2 ranks."""
+    script = tmp_path / "gworker.py"
+    script.write_text(GRAD_WORKER)
+    port = str(31500 + os.getpid() % 2000)
+    procs = [subprocess.Popen([sys.executable, str(script), ROOT, port, str(r)], stdout=subprocess.PIPE,
+                              stderr=subprocess.STDOUT, text=True) for r in range(2)]
+    outs = [p.communicate(timeout=180)[0] for p in procs]
+    for p, o in zip(procs, outs):
+        assert p.returncode == 0 and "ok" in o, o

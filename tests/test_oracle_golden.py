@@ -4,6 +4,8 @@ import pytest
 import torch
 
 from helpers import assert_logits_close, assert_tokens_match_where_decided, load_golden
+from csm_hf_b200.config import tiny_config
+from csm_hf_b200.synthetic import make_state_dict
 from oracle.csm_oracle import CSMOracle
 
 
@@ -109,3 +111,32 @@ def test_reference_sampler_histograms_follow_topk_softmax():
             assert int(keep.sum()) == c["topk"] + 2          # the k-th value appears three times: all kept
         z = (counts - n * probs).abs() / torch.sqrt(n * probs * (1 - probs)).clamp_min(1.0)
         assert float(z[keep].max()) < 5.0, (name, float(z[keep].max()))
+
+
+def test_training_oracle_vs_reference():
+    """The training restatement (oracle/csm_train_oracle.py) against the reference's own forward(labels=...) + backward
+    (tests/golden/tiny_train_*.pt, oracle/make_golden.py --train): fp32 losses to 1e-5 and every gradient norm to 1e-4;
+    bf16 losses to 2e-3 (+ one bf16 ulp on the bf16 decoder loss) and every gradient within 4 % of its largest entry."""
+    import os
+    from csm_hf_b200.synthetic import make_training_batch
+    from helpers import GOLD, dense_grad
+    from oracle.csm_train_oracle import loss_and_grads
+    for tag, dt in (("fp32", torch.float32), ("bf16", torch.bfloat16)):
+        fx = torch.load(os.path.join(GOLD, f"tiny_train_{tag}.pt"), weights_only=False)
+        r = fx["recipe"]
+        cfg = tiny_config()
+        sd = make_state_dict(cfg, seed=r["weight_seed"], norm_jitter=r["norm_jitter"])
+        ids, mask, labels = make_training_batch(cfg, r["batch"], r["frames"], seed=r["seed"], text_frames=r["text_frames"],
+                                                amortization_ratio=r["amortization_ratio"], pad=r["pad"])
+        (l, bl, dl), grads = loss_and_grads(cfg, sd, dt, ids, mask, labels)
+        tol = 1e-5 if dt == torch.float32 else 2e-3
+        assert abs(float(l) - float(fx["loss"])) <= tol * float(fx["loss"]) + (0.04 if dt == torch.bfloat16 else 0)
+        assert abs(float(bl) - float(fx["backbone_loss"])) <= tol * float(fx["backbone_loss"])
+        for k, n in fx["grad_norms"].items():
+            got = float(grads[k].float().norm())
+            assert abs(got - n) <= (1e-4 if dt == torch.float32 else 2e-2) * n + 1e-12, (tag, k, got, n)
+        if dt == torch.bfloat16:
+            for k, g in fx["grads"].items():
+                want = dense_grad(g).float()
+                err = float((grads[k].float() - want).abs().max())
+                assert err <= 0.04 * float(want.abs().max()), (k, err)
