@@ -70,6 +70,62 @@ def ncu_traffic(batch):
         return json.load(f).get(f"b{batch}")
 
 
+def training_point(cfg, sd, dev, rank, world, seq, tpeak, note, steps=3):
+    """ms per training step (CSMModel.forward(labels=...) + backward, csrc/csm_train.cu) and its tensor-roofline fraction."""
+    import torch.distributed as dist
+    from csm_hf_b200.modeling import CSMModel
+    from csm_hf_b200.synthetic import make_training_batch
+    ok, err, ms, out, F = 1, None, 0.0, None, 0
+    try:
+        tm = CSMModel(cfg, sd, device=dev)
+        tm.requires_grad_(True)
+        ids, mask, labels = [t.to(dev) for t in make_training_batch(cfg, 1, seq, seed=100 + rank, text_frames=16)]
+        F = int((labels[:, :, :32] != -100).all(dim=2).sum())
+        out = tm(input_ids=ids, attention_mask=mask, labels=labels)     # warm-up step, local
+        out.loss.backward()
+        torch.cuda.synchronize()
+    except Exception as e:   # noqa: BLE001
+        ok, err = 0, f"{type(e).__name__}: {e}"
+    if world > 1:
+        flag = torch.tensor([ok], device=dev)
+        dist.all_reduce(flag, op=dist.ReduceOp.MIN)
+        ok = int(flag)
+    if not ok:
+        return {"error": err or "another rank failed"}
+    from csm_hf_b200.dist import allreduce_gradients
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    if world > 1:
+        dist.barrier()
+    torch.cuda.synchronize()
+    e0.record()
+    for _ in range(steps):
+        tm.zero_grad(set_to_none=True)
+        out = tm(input_ids=ids, attention_mask=mask, labels=labels)
+        out.loss.backward()
+        if world > 1:
+            allreduce_gradients(tm)
+    e1.record()
+    torch.cuda.synchronize()
+    t = torch.tensor([e0.elapsed_time(e1) / steps], device=dev)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ms = float(t)
+    sys.path.insert(0, os.path.join(ROOT, "tools"))
+    from train_bench import flops_forward
+    fl = 3 * flops_forward(cfg, 1, seq, F)
+    res = {"workload": f"csm-1b fwd+bwd, seq_len {seq}, one sequence per GPU x {world} GPU(s), 1/16 decoder amortisation "
+                       f"({F} frames), gradients all-reduced over NCCL" if world > 1 else
+                       f"csm-1b fwd+bwd, seq_len {seq}, one sequence, 1/16 decoder amortisation ({F} frames)",
+           "ms_per_step": ms, "steps": steps, "tokens_per_s": world * seq / (ms / 1000.0), "loss": float(out.loss.detach()),
+           "roofline": {"bound": "tensor", "achieved": fl / (ms / 1000.0) / 1e12, "peak": tpeak, "unit": "TFLOP/s",
+                        "frac": fl / (ms / 1000.0) / 1e12 / tpeak, "algorithmic_flops_per_step_per_gpu": fl},
+           "gpu_launches_per_step": tm._train_engine.launches() // (steps + 1)}
+    note(f"training point: {ms:.1f} ms/step")
+    del tm
+    torch.cuda.empty_cache()
+    return res
+
+
 class ClockSampler:
     Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
          "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
@@ -253,6 +309,9 @@ def main():
     ap.add_argument("--frames", type=int, default=200)
     ap.add_argument("--points", default="1,8,32", help="batch sizes per GPU reported under config.points ('' = none)")
     ap.add_argument("--point-steps", type=int, default=2)
+    ap.add_argument("--no-train-point", action="store_true",
+                    help="skip the training-step point (BASELINE config #5: fwd+bwd, seq_len 4096, one sequence per GPU)")
+    ap.add_argument("--train-seq", type=int, default=4096)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-verify", action="store_true")
     ap.add_argument("--cpu-sample-frames", type=int, default=4)
@@ -404,6 +463,13 @@ def main():
             del pm
         pt.pop("out0", None)
         points.append(pt)
+    # BASELINE config #5: one training step = forward with labels + backward (+ NCCL gradient all-reduce
+    # when N > 1), csm-1b, seq_len 4096, one sequence per GPU, 1/16 decoder amortisation.  Reported under config.training;
+    # never allowed to break the generation line.
+    training = None
+    if not a.no_train_point and os.environ.get("BENCH_NO_TRAIN") != "1":
+        model._drop_engine()
+        training = training_point(cfg, sd, dev, rank, world, a.train_seq, tpeak, note)
     if rank != 0:
         if world > 1:
             dist.destroy_process_group()
@@ -423,7 +489,7 @@ def main():
                    "decode_ms_per_frame": head["decode_ms_per_frame"],
                    "decode_frames_per_s_per_gpu": head["decode_frames_per_s_per_gpu"],
                    "prefill": dict(head["prefill"], peak_source=tpeak_src),
-                   "points": points},
+                   "points": points, "training": training},
         "roofline": rl,
         "e2e": {"value": e2e_value, "unit": "frames/s", "h2d_bytes_per_step": int(h_ids.numel() * 8 + h_mask.numel() * 4),
                 "d2h_bytes_per_step": int(a.batch * a.frames * 32 * 8)},

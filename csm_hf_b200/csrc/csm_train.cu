@@ -144,7 +144,7 @@ int gemm(CsmTrain* t, const bf16* A, long long lda, int R, int K, const bf16* Wm
 // dst [cols, rows] (pitch ldd) = src [rows, cols] (pitch lds) transposed
 int transpose(CsmTrain* t, const bf16* src, int rows, int cols, long long lds, bf16* dst, long long ldd, cudaStream_t st) {
   if (rows <= 0 || cols <= 0) return 0;
-  dim3 grid((cols + 31) / 32, (rows + 31) / 32), block(32, 8);
+  dim3 grid((cols + 63) / 64, (rows + 63) / 64), block(32, 8);
   transpose_kernel<<<grid, block, 0, st>>>(src, rows, cols, lds, dst, ldd);
   TCK(cudaGetLastError());
   t->launches += 1;
@@ -192,7 +192,7 @@ int flash_fwd(CsmTrain* t, const TStack& s, const bf16* qkv, int S, int nseq, co
 template <int HD>
 int flash_bwd(CsmTrain* t, const TStack& s, const bf16* qkv, const bf16* d_out, const float* lse, const float* delta, int S,
               int nseq, const unsigned char* valid, bf16* dqkv, float* dq_acc, cudaStream_t st) {
-  const size_t smem = (size_t)4 * 64 * (HD + 8) * 2 + 64 * 4 * 2 + 64;
+  const size_t smem = (size_t)6 * 64 * (HD + 8) * 2 + (size_t)64 * 72 * 2 + 4 * 64 * 4 + 64;
   TCK(cudaFuncSetAttribute((const void*)flash_bwd_kernel<HD>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   dim3 grid((S + 63) / 64, s.kv, nseq);
   flash_bwd_kernel<HD><<<grid, 128, smem, st>>>(qkv, d_out, lse, delta, S, s.heads, s.kv, s.scale, valid, dqkv, dq_acc);
@@ -234,7 +234,7 @@ int stack_forward(CsmTrain* t, TStack& s, int S, int nseq, const unsigned char* 
 int norm_bwd(CsmTrain* t, const TStack& s, const bf16* x, const bf16* w, const bf16* dy, const bf16* dres, bf16* dh, bf16* gw,
              int R, cudaStream_t st) {
   TCK(cudaMemsetAsync(t->dw_acc, 0, (size_t)s.H * 4, st));
-  const int rpb = 64;
+  const int rpb = 16;   // rows per block (8 warps x 2 rows): enough blocks to fill the GPU at a few thousand rows
   rmsnorm_bwd_kernel<<<(R + rpb - 1) / rpb, 256, 0, st>>>(x, w, dy, dres, s.eps, s.H, R, rpb, dh, t->dw_acc);
   TCK(cudaGetLastError());
   if (gw) {

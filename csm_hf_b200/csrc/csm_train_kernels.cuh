@@ -237,20 +237,41 @@ __global__ void __launch_bounds__(128) flash_bwd_kernel(const bf16* __restrict__
                                                         int S, int heads, int kv, float scale,
                                                         const unsigned char* __restrict__ valid, bf16* __restrict__ dqkv,
                                                         float* __restrict__ dq_acc) {
-  constexpr int BK = 64, LDS = HD + 8, C8 = HD / 8;
+  constexpr int BK = 64, LDS = HD + 8, C8 = HD / 8, LDD = BK + 8, TILE = BK * LDS;
   extern __shared__ __align__(16) unsigned char fsm[];
   bf16* sK = reinterpret_cast<bf16*>(fsm);
-  bf16* sV = sK + BK * LDS;
-  bf16* sQ = sV + BK * LDS;
-  bf16* sdO = sQ + BK * LDS;
-  float* sLse = reinterpret_cast<float*>(sdO + BK * LDS);
-  float* sD = sLse + BK;
-  unsigned char* sOk = reinterpret_cast<unsigned char*>(sD + BK);
+  bf16* sV = sK + TILE;
+  bf16* sQ = sV + TILE;             // [2][TILE]
+  bf16* sdO = sQ + 2 * TILE;        // [2][TILE]
+  bf16* sdS = sdO + 2 * TILE;       // [BK keys][LDD]: dS^T of the current block, all four warps' key rows
+  float* sLse = reinterpret_cast<float*>(sdS + BK * LDD);     // [2][BK]
+  float* sD = sLse + 2 * BK;        // [2][BK]
+  unsigned char* sOk = reinterpret_cast<unsigned char*>(sD + 2 * BK);
   const int kvb = blockIdx.x, kvh = blockIdx.y, bl = blockIdx.z;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, g = lane >> 2, t = lane & 3;
   const int rep = heads / kv, nq = heads * HD, nkv = kv * HD, width = nq + 2 * nkv;
   const bf16* base = qkv + (size_t)bl * S * width;
   const int k0 = kvb * BK;
+  const int nqb = (S + BK - 1) / BK;
+  const int per_head = nqb - kvb, nit = rep * per_head;     // iterations: (query head of the group, query block >= key block)
+  const float l2e = 1.4426950408889634f;
+  auto load_q = [&](int it) {
+    const int head = kvh * rep + it / per_head, q0 = (kvb + it % per_head) * BK, buf = it & 1;
+    for (int i = threadIdx.x; i < BK * C8; i += 128) {
+      const int qr = i / C8, c8 = i % C8;
+      const bool ok = q0 + qr < S;
+      const size_t row = (size_t)bl * S + (ok ? q0 + qr : 0);
+      t_cp_async16(&sQ[buf * TILE + qr * LDS + c8 * 8], qkv + row * width + head * HD + c8 * 8, ok);
+      t_cp_async16(&sdO[buf * TILE + qr * LDS + c8 * 8], d_out + row * nq + head * HD + c8 * 8, ok);
+    }
+    if (threadIdx.x < BK) {
+      const int qq = q0 + (int)threadIdx.x;
+      const size_t row = (size_t)bl * S + qq;
+      sLse[buf * BK + threadIdx.x] = qq < S ? lse[row * heads + head] * l2e : INFINITY;   // (exp2 domain; past the end: p = 0)
+      sD[buf * BK + threadIdx.x] = qq < S ? delta[row * heads + head] : 0.f;
+    }
+    asm volatile("cp.async.commit_group;" ::: "memory");
+  };
   // K and V block -> shared memory (rows past the sequence are zero-filled and flagged invisible)
   for (int i = threadIdx.x; i < BK * C8; i += 128) {
     const int kr = i / C8, c8 = i % C8;
@@ -264,7 +285,8 @@ __global__ void __launch_bounds__(128) flash_bwd_kernel(const bf16* __restrict__
     sOk[threadIdx.x] = kk >= S ? 0 : (valid == nullptr ? 1 : valid[(size_t)bl * S + kk]);
   }
   asm volatile("cp.async.commit_group;" ::: "memory");
-  asm volatile("cp.async.wait_group 0;" ::: "memory");
+  load_q(0);
+  asm volatile("cp.async.wait_group 1;" ::: "memory");   // K / V have landed (the first Q / dO block may still be in flight)
   __syncthreads();
   // A fragments of this warp's 16 keys: K and V rows
   uint32_t ka[HD / 16][4], va[HD / 16][4];
@@ -288,96 +310,108 @@ __global__ void __launch_bounds__(128) flash_bwd_kernel(const bf16* __restrict__
     for (int q = 0; q < 4; ++q) { dk[j][q] = 0.f; dv[j][q] = 0.f; }
   const int key_lo = k0 + 16 * warp + g, key_hi = key_lo + 8;
   const bool okk_lo = sOk[16 * warp + g] != 0, okk_hi = sOk[16 * warp + g + 8] != 0;
-  const float sl2 = scale * 1.4426950408889634f, l2e = 1.4426950408889634f;
-  const int nqb = (S + BK - 1) / BK;
-  for (int hq = 0; hq < rep; ++hq) {
-    const int head = kvh * rep + hq;
-    for (int qb = kvb; qb < nqb; ++qb) {
-      const int q0 = qb * BK;
-      __syncthreads();                      // everyone is done with the previous Q / dO block
-      for (int i = threadIdx.x; i < BK * C8; i += 128) {
-        const int qr = i / C8, c8 = i % C8;
-        const bool ok = q0 + qr < S;
-        const size_t row = (size_t)bl * S + (ok ? q0 + qr : 0);
-        t_cp_async16(&sQ[qr * LDS + c8 * 8], qkv + row * width + head * HD + c8 * 8, ok);
-        t_cp_async16(&sdO[qr * LDS + c8 * 8], d_out + row * nq + head * HD + c8 * 8, ok);
-      }
-      if (threadIdx.x < BK) {
-        const int qq = q0 + (int)threadIdx.x;
-        const size_t row = (size_t)bl * S + qq;
-        sLse[threadIdx.x] = qq < S ? lse[row * heads + head] * l2e : INFINITY;   // (exp2 domain; past the end: p = 0)
-        sD[threadIdx.x] = qq < S ? delta[row * heads + head] : 0.f;
-      }
-      asm volatile("cp.async.commit_group;" ::: "memory");
-      asm volatile("cp.async.wait_group 0;" ::: "memory");
-      __syncthreads();
-      // S^T and dP^T: [16 keys x 64 queries]
-      float st[8][4], dp[8][4];
-#pragma unroll
-      for (int j = 0; j < 8; ++j) {
-#pragma unroll
-        for (int q = 0; q < 4; ++q) { st[j][q] = 0.f; dp[j][q] = 0.f; }
-#pragma unroll
-        for (int kp = 0; kp < HD / 32; ++kp) {
-          uint32_t f[4];
-          t_ldsm_x4(f, sQ + (8 * j + (lane & 7)) * LDS + 32 * kp + 8 * (lane >> 3));
-          mma16816(st[j], ka[2 * kp], f[0], f[1]);
-          mma16816(st[j], ka[2 * kp + 1], f[2], f[3]);
-          t_ldsm_x4(f, sdO + (8 * j + (lane & 7)) * LDS + 32 * kp + 8 * (lane >> 3));
-          mma16816(dp[j], va[2 * kp], f[0], f[1]);
-          mma16816(dp[j], va[2 * kp + 1], f[2], f[3]);
-        }
-      }
-      // P^T and dS^T as bf16 A fragments (k16 tile kk = query n-tiles 2kk, 2kk+1); plo/phi keep the 8x8 blocks for dQ
-      uint32_t pa[4][4], dsa[4][4];
-#pragma unroll
-      for (int j = 0; j < 8; ++j) {
-        const int qi = 8 * j + 2 * t, qq = q0 + qi;
-        const float l0 = sLse[qi], l1 = sLse[qi + 1], d0 = sD[qi], d1 = sD[qi + 1];
-        const bool m00 = okk_lo && key_lo <= qq, m01 = okk_lo && key_lo <= qq + 1;
-        const bool m10 = okk_hi && key_hi <= qq, m11 = okk_hi && key_hi <= qq + 1;
-        const float p0 = m00 ? exp2f(st[j][0] * sl2 - l0) : 0.f, p1 = m01 ? exp2f(st[j][1] * sl2 - l1) : 0.f;
-        const float p2 = m10 ? exp2f(st[j][2] * sl2 - l0) : 0.f, p3 = m11 ? exp2f(st[j][3] * sl2 - l1) : 0.f;
-        const float s0 = p0 * (dp[j][0] - d0) * scale, s1 = p1 * (dp[j][1] - d1) * scale;
-        const float s2 = p2 * (dp[j][2] - d0) * scale, s3 = p3 * (dp[j][3] - d1) * scale;
-        const int kk = j >> 1, o2 = (j & 1) * 2;
-        pa[kk][o2] = pack_bf16(p0, p1);
-        pa[kk][o2 + 1] = pack_bf16(p2, p3);
-        dsa[kk][o2] = pack_bf16(s0, s1);
-        dsa[kk][o2 + 1] = pack_bf16(s2, s3);
-      }
-      // dV += P^T dO, dK += dS^T Q   (B fragments: k = query rows, n = head dims -> transposed ldmatrix)
-#pragma unroll
-      for (int kk = 0; kk < 4; ++kk) {
-#pragma unroll
-        for (int jd = 0; jd < HD / 8; ++jd) {
-          uint32_t b0, b1;
-          t_ldsm_x2_trans(b0, b1, sdO + (16 * kk + (lane & 15)) * LDS + 8 * jd);
-          mma16816(dv[jd], pa[kk], b0, b1);
-          t_ldsm_x2_trans(b0, b1, sQ + (16 * kk + (lane & 15)) * LDS + 8 * jd);
-          mma16816(dk[jd], dsa[kk], b0, b1);
-        }
-      }
-      // dQ[16-query tile mq] += dS (queries x this warp's 16 keys) K (keys x dims)
+  const float sl2 = scale * l2e;
 #pragma unroll 1
-      for (int mq = 0; mq < 4; ++mq) {
-        if (q0 + 16 * mq + 15 < k0 + 16 * warp) continue;   // every query of the tile precedes every key of the warp
+  for (int it = 0; it < nit; ++it) {
+    const int head = kvh * rep + it / per_head, q0 = (kvb + it % per_head) * BK, buf = it & 1;
+    asm volatile("cp.async.wait_group 0;" ::: "memory");
+    __syncthreads();                        // block `it` has landed; everyone is done with the other buffer and with sdQ's flush
+    if (it + 1 < nit) load_q(it + 1);       // in flight while this block is multiplied
+    const bf16* cQ = sQ + buf * TILE;
+    const bf16* cdO = sdO + buf * TILE;
+    const float* cLse = sLse + buf * BK;
+    const float* cD = sD + buf * BK;
+    // S^T and dP^T: [16 keys x 64 queries]
+    float st[8][4], dp[8][4];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+#pragma unroll
+      for (int q = 0; q < 4; ++q) { st[j][q] = 0.f; dp[j][q] = 0.f; }
+#pragma unroll
+      for (int kp = 0; kp < HD / 32; ++kp) {
+        uint32_t f[4];
+        t_ldsm_x4(f, cQ + (8 * j + (lane & 7)) * LDS + 32 * kp + 8 * (lane >> 3));
+        mma16816(st[j], ka[2 * kp], f[0], f[1]);
+        mma16816(st[j], ka[2 * kp + 1], f[2], f[3]);
+        t_ldsm_x4(f, cdO + (8 * j + (lane & 7)) * LDS + 32 * kp + 8 * (lane >> 3));
+        mma16816(dp[j], va[2 * kp], f[0], f[1]);
+        mma16816(dp[j], va[2 * kp + 1], f[2], f[3]);
+      }
+    }
+    // P^T and dS^T as bf16 A fragments (k16 tile kk = query n-tiles 2kk, 2kk+1)
+    uint32_t pa[4][4], dsa[4][4];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      const int qi = 8 * j + 2 * t, qq = q0 + qi;
+      const float l0 = cLse[qi], l1 = cLse[qi + 1], d0 = cD[qi], d1 = cD[qi + 1];
+      const bool m00 = okk_lo && key_lo <= qq, m01 = okk_lo && key_lo <= qq + 1;
+      const bool m10 = okk_hi && key_hi <= qq, m11 = okk_hi && key_hi <= qq + 1;
+      const float p0 = m00 ? exp2f(st[j][0] * sl2 - l0) : 0.f, p1 = m01 ? exp2f(st[j][1] * sl2 - l1) : 0.f;
+      const float p2 = m10 ? exp2f(st[j][2] * sl2 - l0) : 0.f, p3 = m11 ? exp2f(st[j][3] * sl2 - l1) : 0.f;
+      const float s0 = p0 * (dp[j][0] - d0) * scale, s1 = p1 * (dp[j][1] - d1) * scale;
+      const float s2 = p2 * (dp[j][2] - d0) * scale, s3 = p3 * (dp[j][3] - d1) * scale;
+      const int kk = j >> 1, o2 = (j & 1) * 2;
+      pa[kk][o2] = pack_bf16(p0, p1);
+      pa[kk][o2 + 1] = pack_bf16(p2, p3);
+      dsa[kk][o2] = pack_bf16(s0, s1);
+      dsa[kk][o2 + 1] = pack_bf16(s2, s3);
+    }
+    // dV += P^T dO, dK += dS^T Q   (B fragments: k = query rows, n = head dims -> transposed ldmatrix)
+#pragma unroll
+    for (int kk = 0; kk < 4; ++kk) {
+#pragma unroll
+      for (int jd = 0; jd < HD / 8; ++jd) {
+        uint32_t b0, b1;
+        t_ldsm_x2_trans(b0, b1, cdO + (16 * kk + (lane & 15)) * LDS + 8 * jd);
+        mma16816(dv[jd], pa[kk], b0, b1);
+        t_ldsm_x2_trans(b0, b1, cQ + (16 * kk + (lane & 15)) * LDS + 8 * jd);
+        mma16816(dk[jd], dsa[kk], b0, b1);
+      }
+    }
+    // dQ = dS K needs all 64 keys of a query row: the warps exchange dS^T through shared memory, then warp w owns queries
+    // 16w..16w+15 (A fragments = transposed 8x8 blocks of the [key][query] tile) and adds its finished rows to the fp32
+    // buffer in global memory (other key blocks add to the same rows)
+    {
+      bf16* wr = sdS + (16 * warp + g) * LDD + 2 * t;
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        const int kk = j >> 1, o2 = (j & 1) * 2;
+        *reinterpret_cast<uint32_t*>(wr + 8 * j) = dsa[kk][o2];
+        *reinterpret_cast<uint32_t*>(wr + 8 * LDD + 8 * j) = dsa[kk][o2 + 1];
+      }
+    }
+    __syncthreads();
+    {
+      float dq[HD / 8][4];
+#pragma unroll
+      for (int jd = 0; jd < HD / 8; ++jd)
+#pragma unroll
+        for (int q = 0; q < 4; ++q) dq[jd][q] = 0.f;
+#pragma unroll
+      for (int kt = 0; kt < 4; ++kt) {
+        if (q0 + 16 * warp + 15 < k0 + 16 * kt) continue;   // every query of this warp precedes every key of the tile
         uint32_t a[4];
-        a[0] = t_movmatrix(dsa[mq][0]);     // keys 0-7  x queries 0-7   -> queries 0-7  x keys 0-7
-        a[1] = t_movmatrix(dsa[mq][2]);     // keys 0-7  x queries 8-15  -> queries 8-15 x keys 0-7
-        a[2] = t_movmatrix(dsa[mq][1]);     // keys 8-15 x queries 0-7   -> queries 0-7  x keys 8-15
-        a[3] = t_movmatrix(dsa[mq][3]);     // keys 8-15 x queries 8-15  -> queries 8-15 x keys 8-15
-        const int ql = q0 + 16 * mq + g, qh = ql + 8;
-        float* rl = dq_acc + ((size_t)bl * S + ql) * nq + head * HD + 2 * t;
-        float* rh = dq_acc + ((size_t)bl * S + qh) * nq + head * HD + 2 * t;
+        {
+          const bf16* p = sdS + (16 * kt + (lane & 7) + ((lane >> 4) & 1) * 8) * LDD + 16 * warp + ((lane >> 3) & 1) * 8;
+          asm volatile("ldmatrix.sync.aligned.m8n8.x4.trans.shared.b16 {%0,%1,%2,%3}, [%4];"
+                       : "=r"(a[0]), "=r"(a[1]), "=r"(a[2]), "=r"(a[3])
+                       : "r"(smem_u32(p)));
+        }
 #pragma unroll
         for (int jd = 0; jd < HD / 8; ++jd) {
-          float acc[4] = {0.f, 0.f, 0.f, 0.f};
           uint32_t b0, b1;
-          t_ldsm_x2_trans(b0, b1, sK + (16 * warp + (lane & 15)) * LDS + 8 * jd);
-          mma16816(acc, a, b0, b1);
-          if (ql < S) red_add_v2(rl + 8 * jd, acc[0], acc[1]);
-          if (qh < S) red_add_v2(rh + 8 * jd, acc[2], acc[3]);
+          t_ldsm_x2_trans(b0, b1, sK + (16 * kt + (lane & 15)) * LDS + 8 * jd);
+          mma16816(dq[jd], a, b0, b1);
+        }
+      }
+      const int ql = q0 + 16 * warp + g, qh = ql + 8;
+      float* rl = dq_acc + ((size_t)bl * S + ql) * nq + head * HD + 2 * t;
+      float* rh = dq_acc + ((size_t)bl * S + qh) * nq + head * HD + 2 * t;
+      if (q0 + 16 * warp + 15 >= k0) {
+#pragma unroll
+        for (int jd = 0; jd < HD / 8; ++jd) {
+          if (ql < S) red_add_v2(rl + 8 * jd, dq[jd][0], dq[jd][1]);
+          if (qh < S) red_add_v2(rh + 8 * jd, dq[jd][2], dq[jd][3]);
         }
       }
     }
@@ -700,19 +734,40 @@ __global__ void embed_bwd_kernel(const bf16* __restrict__ dh, const long long* _
 }
 
 // ---------------------------------------------------------------- layout helpers
-// dst[c, r] = src[r, c]: src [rows, cols] with pitch lds, dst [cols, rows] with pitch ldd.  32 x 32 tiles, block (32, 8).
-__global__ void transpose_kernel(const bf16* __restrict__ src, int rows, int cols, long long lds, bf16* __restrict__ dst,
-                                 long long ldd) {
-  __shared__ bf16 tile[32][34];
-  const int c0 = blockIdx.x * 32, r0 = blockIdx.y * 32;
-  for (int i = threadIdx.y; i < 32; i += 8) {
-    const int r = r0 + i, c = c0 + threadIdx.x;
-    if (r < rows && c < cols) tile[i][threadIdx.x] = src[(size_t)r * lds + c];
+// dst[c, r] = src[r, c]: src [rows, cols] with pitch lds, dst [cols, rows] with pitch ldd.  64 x 64 tiles, block (32, 8):
+// a warp reads 128 contiguous bytes of a source row and writes 128 contiguous bytes of a destination row (pairs of
+// elements per thread on both sides; lds, ldd, rows-pitch even; a ragged edge falls back to single elements).
+__global__ void __launch_bounds__(256) transpose_kernel(const bf16* __restrict__ src, int rows, int cols, long long lds,
+                                                        bf16* __restrict__ dst, long long ldd) {
+  __shared__ bf16 tile[64][66];
+  const int c0 = blockIdx.x * 64, r0 = blockIdx.y * 64;
+  const int tx = threadIdx.x, ty = threadIdx.y;
+  const bool even = ((lds | ldd) & 1) == 0;
+  for (int i = ty; i < 64; i += 8) {
+    const int r = r0 + i, c = c0 + 2 * tx;
+    if (r < rows) {
+      if (even && c + 1 < cols) {
+        *reinterpret_cast<uint32_t*>(&tile[i][2 * tx]) = *reinterpret_cast<const uint32_t*>(src + (size_t)r * lds + c);
+      } else {
+        if (c < cols) tile[i][2 * tx] = src[(size_t)r * lds + c];
+        if (c + 1 < cols) tile[i][2 * tx + 1] = src[(size_t)r * lds + c + 1];
+      }
+    }
   }
   __syncthreads();
-  for (int i = threadIdx.y; i < 32; i += 8) {
-    const int c = c0 + i, r = r0 + threadIdx.x;
-    if (r < rows && c < cols) dst[(size_t)c * ldd + r] = tile[threadIdx.x][i];
+  for (int i = ty; i < 64; i += 8) {
+    const int c = c0 + i, r = r0 + 2 * tx;     // destination row c, destination columns r, r + 1
+    if (c < cols) {
+      if (even && r + 1 < rows) {
+        __nv_bfloat162 v;
+        v.x = tile[2 * tx][i];
+        v.y = tile[2 * tx + 1][i];
+        *reinterpret_cast<__nv_bfloat162*>(dst + (size_t)c * ldd + r) = v;
+      } else {
+        if (r < rows) dst[(size_t)c * ldd + r] = tile[2 * tx][i];
+        if (r + 1 < rows) dst[(size_t)c * ldd + r + 1] = tile[2 * tx + 1][i];
+      }
+    }
   }
 }
 __global__ void f32_to_bf16_kernel(const float* __restrict__ src, long long n, bf16* __restrict__ dst) {
