@@ -51,9 +51,23 @@ __device__ __forceinline__ uint64_t umma_desc_k128(uint32_t saddr) {
   d |= (uint64_t)2 << 61;
   return d;
 }
-// Instruction descriptor: D = F32, A = B = BF16, both K-major, N >> 3 at [17,23), M >> 4 at [24,29)
-__device__ __forceinline__ uint32_t umma_idesc_bf16(int m, int n) {
-  return (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(n >> 3) << 17) | ((uint32_t)(m >> 4) << 24);
+// MN-major operand (the tile is stored [64 k][64 m/n] boxes of 128-byte rows, 128-byte swizzle, as TMA writes a box of a
+// [K, MN] row-major matrix): canonical layout ((8,n),(8,k)):((1,LBO),(8,SBO)) in 16-byte units -- 8 k-rows of one
+// 64-element MN chunk form a 1024-byte swizzle atom; SBO = 1024 (next 8 k-rows inside a box), LBO = 8192 (next
+// 64-element MN chunk = next box).
+__device__ __forceinline__ uint64_t umma_desc_mn128(uint32_t saddr) {
+  uint64_t d = 0;
+  d |= (uint64_t)((saddr & 0x3ffffu) >> 4);
+  d |= (uint64_t)(8192 >> 4) << 16;
+  d |= (uint64_t)(1024 >> 4) << 32;
+  d |= (uint64_t)1 << 46;
+  d |= (uint64_t)2 << 61;
+  return d;
+}
+// Instruction descriptor: D = F32, A = B = BF16, N >> 3 at [17,23), M >> 4 at [24,29); bit 15 / 16: A / B is MN-major
+__device__ __forceinline__ uint32_t umma_idesc_bf16(int m, int n, bool a_mn = false, bool b_mn = false) {
+  return (1u << 4) | (1u << 7) | (1u << 10) | (a_mn ? 1u << 15 : 0u) | (b_mn ? 1u << 16 : 0u) | ((uint32_t)(n >> 3) << 17) |
+         ((uint32_t)(m >> 4) << 24);
 }
 __device__ __forceinline__ void umma_bf16(uint32_t tmem_d, uint64_t da, uint64_t db, uint32_t idesc, uint32_t accumulate) {
   asm volatile(
@@ -118,7 +132,7 @@ __device__ __forceinline__ void swiglu32(bf16* dst, const uint32_t (&r)[32]) {  
   d[1] = make_uint4(o[4], o[5], o[6], o[7]);
 }
 
-template <int EPI>
+template <int EPI, bool A_MN = false, bool B_MN = false>
 __global__ void __launch_bounds__(GEMM_THREADS, 1)
 csm_gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_w, const GemmParams p) {
   extern __shared__ unsigned char smem_raw[];
@@ -157,14 +171,25 @@ csm_gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant
           const uint32_t s = it % STAGES, ph = (it / STAGES) & 1u;
           mbar_wait(&empty[s], ph ^ 1u);                    // (first pass: a fresh barrier passes parity 1)
           mbar_expect_tx(&full[s], STAGE_BYTES);           // rows / columns outside the tensor are zero-filled and counted
-          tma_load_2d(smem + s * STAGE_BYTES, &map_a, &full[s], kb * BK, m0);
-          tma_load_2d(smem + s * STAGE_BYTES + A_BYTES, &map_w, &full[s], kb * BK, n0);
+          unsigned char* sa = smem + s * STAGE_BYTES;
+          if (!A_MN) {
+            tma_load_2d(sa, &map_a, &full[s], kb * BK, m0);
+          } else {                                          // [64 k x 64 m] boxes of the [K, M] matrix
+#pragma unroll
+            for (int i = 0; i < BM / 64; ++i) tma_load_2d(sa + i * 8192, &map_a, &full[s], m0 + 64 * i, kb * BK);
+          }
+          if (!B_MN) {
+            tma_load_2d(sa + A_BYTES, &map_w, &full[s], kb * BK, n0);
+          } else {
+#pragma unroll
+            for (int i = 0; i < BN / 64; ++i) tma_load_2d(sa + A_BYTES + i * 8192, &map_w, &full[s], n0 + 64 * i, kb * BK);
+          }
         }
       }
     }
   } else if (warp == 1) {
     if (lane == 0) {
-      const uint32_t idesc = umma_idesc_bf16(BM, BN);
+      const uint32_t idesc = umma_idesc_bf16(BM, BN, A_MN, B_MN);
       uint32_t it = 0, acc_it = 0;
       for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x, ++acc_it) {
         const uint32_t buf = acc_it & 1u, aph = (acc_it >> 1) & 1u;
@@ -177,9 +202,12 @@ csm_gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant
           tc_fence_after();
           const uint32_t a0 = smem_u32(smem + s * STAGE_BYTES), b0 = a0 + A_BYTES;
 #pragma unroll
-          for (int k = 0; k < BK / UMMA_K; ++k)             // 32 bytes along K inside the 128-byte swizzle atom
-            umma_bf16(tacc, umma_desc_k128(a0 + k * UMMA_K * 2), umma_desc_k128(b0 + k * UMMA_K * 2), idesc,
-                      (kb | k) != 0 ? 1u : 0u);
+          for (int k = 0; k < BK / UMMA_K; ++k) {
+            // K-major: 32 bytes along K inside the 128-byte swizzle atom; MN-major: 16 k-rows = two 1024-byte atoms
+            const uint64_t da = A_MN ? umma_desc_mn128(a0 + k * 2048) : umma_desc_k128(a0 + k * UMMA_K * 2);
+            const uint64_t db = B_MN ? umma_desc_mn128(b0 + k * 2048) : umma_desc_k128(b0 + k * UMMA_K * 2);
+            umma_bf16(tacc, da, db, idesc, (kb | k) != 0 ? 1u : 0u);
+          }
           umma_commit(&empty[s]);                           // slot free once these MMAs have read it
         }
         umma_commit(&tfull[buf]);                           // accumulator complete
@@ -281,11 +309,12 @@ typedef CUresult (*EncodeTiled)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, v
                                 CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
 EncodeTiled g_encode = nullptr;
 
-template <int EPI>
+template <int EPI, bool A_MN = false, bool B_MN = false>
 cudaError_t launch(const CUtensorMap& ma, const CUtensorMap& mw, const GemmParams& p, int grid, cudaStream_t st) {
-  cudaError_t e = cudaFuncSetAttribute((const void*)csm_gemm_kernel<EPI>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES);
+  cudaError_t e = cudaFuncSetAttribute((const void*)csm_gemm_kernel<EPI, A_MN, B_MN>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                       SMEM_BYTES);
   if (e != cudaSuccess) return e;
-  csm_gemm_kernel<EPI><<<grid, GEMM_THREADS, SMEM_BYTES, st>>>(ma, mw, p);
+  csm_gemm_kernel<EPI, A_MN, B_MN><<<grid, GEMM_THREADS, SMEM_BYTES, st>>>(ma, mw, p);
   return cudaGetLastError();
 }
 
@@ -313,6 +342,26 @@ int csm_tmap_2d(void* out, const void* base, long long rows, int K, long long pi
   return r == CUDA_SUCCESS ? 0 : 2;
 }
 
+// Tensor map of an MN-major operand: the matrix is stored [k_rows, mn] row-major (pitch elements between k rows); boxes
+// of [64 k x 64 mn] with the 128-byte swizzle.
+int csm_tmap_2d_mn(void* out, const void* base, long long k_rows, long long mn, long long pitch) {
+  if (!g_encode) {
+    void* fn = nullptr;
+    cudaDriverEntryPointQueryResult qres;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &qres) != cudaSuccess || fn == nullptr)
+      return 1;
+    g_encode = (EncodeTiled)fn;
+  }
+  cuuint64_t dims[2] = {(cuuint64_t)mn, (cuuint64_t)k_rows};
+  cuuint64_t strides[1] = {(cuuint64_t)pitch * 2};
+  cuuint32_t box[2] = {64, (cuuint32_t)BK};
+  cuuint32_t estr[2] = {1, 1};
+  CUresult r = g_encode(reinterpret_cast<CUtensorMap*>(out), CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(base),
+                        dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
+                        CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  return r == CUDA_SUCCESS ? 0 : 2;
+}
+
 int csm_gemm_box_rows_a() { return BM; }
 int csm_gemm_box_rows_w() { return BN; }
 
@@ -325,6 +374,11 @@ cudaError_t csm_gemm_launch(const void* map_a, const void* map_w, const GemmPara
   const int grid = mt * nt < sms ? mt * nt : sms;
   const CUtensorMap& ma = *reinterpret_cast<const CUtensorMap*>(map_a);
   const CUtensorMap& mw = *reinterpret_cast<const CUtensorMap*>(map_w);
+  if (p->a_mn || p->b_mn) {   // transposed operands (gradients): plain store / accumulate only
+    if (p->epi == EPI_STORE && !p->a_mn && p->b_mn) return launch<EPI_STORE, false, true>(ma, mw, *p, grid, st);
+    if (p->epi == EPI_STORE && p->a_mn && p->b_mn) return launch<EPI_STORE, true, true>(ma, mw, *p, grid, st);
+    return cudaErrorInvalidValue;
+  }
   switch (p->epi) {
     case EPI_STORE: return launch<EPI_STORE>(ma, mw, *p, grid, st);
     case EPI_RESID: return launch<EPI_RESID>(ma, mw, *p, grid, st);

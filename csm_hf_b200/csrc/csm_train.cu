@@ -32,6 +32,7 @@
 extern "C" {
 cudaError_t csm_gemm_launch(const void* map_a, const void* map_w, const GemmParams* p, int sms, cudaStream_t st);
 int csm_tmap_2d(void* out, const void* base, long long rows, int K, long long pitch, int box_rows);
+int csm_tmap_2d_mn(void* out, const void* base, long long k_rows, long long mn, long long pitch);
 int csm_gemm_box_rows_a();
 int csm_gemm_box_rows_w();
 cudaError_t csm_embed_sum_launch(const long long* ids, const int* mask, int default_mask, const bf16* audio_emb,
@@ -84,6 +85,7 @@ struct CsmTrain {
   float *row_loss = nullptr, *losses = nullptr;        // device [3]
   float *audio_acc = nullptr, *text_acc = nullptr;     // fp32 gradients of the embedding tables
   int launches = 0;
+  bool mn_operands = true;   // gradients read W, dY and X as MN-major tcgen05 operands (CSM_TRAIN_TRANSPOSE=1: transposed copies)
   std::map<std::string, std::pair<const void*, size_t>> dbg;   // named intermediates of the last step (tests)
 };
 
@@ -141,6 +143,44 @@ int gemm(CsmTrain* t, const bf16* A, long long lda, int R, int K, const bf16* Wm
   t->launches += 1;
   return 0;
 }
+// Input gradient: dX[R, K] = dY[R, N] W[N, K] -- W in its natural [N, K] layout is the MN-major B operand of a product
+// whose contraction runs over N: no transposed weight copy.
+int gemm_dgrad(CsmTrain* t, const bf16* dY, long long ldy, int R, int N, const bf16* Wm, long long ldw, int K, bf16* dX, int ldx,
+               cudaStream_t st) {
+  if (R <= 0) return 0;
+  CUtensorMap ma, mw;
+  if (csm_tmap_2d(&ma, dY, R, N, ldy, csm_gemm_box_rows_a()) || csm_tmap_2d_mn(&mw, Wm, N, K, ldw))
+    return tfail(t, CSM_ECUDA, "cuTensorMapEncodeTiled failed for an input-gradient product [%d,%d] x [%d,%d]", R, N, N, K);
+  GemmParams g;
+  memset(&g, 0, sizeof g);
+  g.R = R; g.N = K; g.K = N; g.epi = EPI_STORE; g.C = dX; g.ldc = ldx; g.b_mn = 1;
+  TCK(csm_gemm_launch(&ma, &mw, &g, t->sms, st));
+  t->launches += 1;
+  return 0;
+}
+// Weight gradient: dW[N, K] = dY[R, N]^T X[R, K] -- dY and X in their natural row-per-token layouts are both MN-major
+// operands of a product whose contraction runs over the R tokens (a ragged last block of tokens is zero-filled by TMA).
+int gemm_wgrad(CsmTrain* t, const bf16* dY, long long ldy, const bf16* X, long long ldx, int R, int N, int K, bf16* dW, int ldw,
+               cudaStream_t st) {
+  if (R <= 0) return 0;
+  CUtensorMap ma, mw;
+  if (csm_tmap_2d_mn(&ma, dY, R, N, ldy) || csm_tmap_2d_mn(&mw, X, R, K, ldx))
+    return tfail(t, CSM_ECUDA, "cuTensorMapEncodeTiled failed for a weight-gradient product [%d,%d]^T x [%d,%d]", R, N, R, K);
+  GemmParams g;
+  memset(&g, 0, sizeof g);
+  g.R = N; g.N = K; g.K = R; g.epi = EPI_STORE; g.C = dW; g.ldc = ldw; g.a_mn = 1; g.b_mn = 1;
+  TCK(csm_gemm_launch(&ma, &mw, &g, t->sms, st));
+  t->launches += 1;
+  return 0;
+}
+// dX = dY W with W [N, K] natural; WT = its transposed copy [K, N] for the CSM_TRAIN_TRANSPOSE=1 path
+int gemm(CsmTrain* t, const bf16* A, long long lda, int R, int K, const bf16* Wm, long long ldw, int N, bf16* C, int ldc,
+         int epi, cudaStream_t st);
+int dgrad(CsmTrain* t, const bf16* dY, long long ldy, int R, int N, const bf16* Wm, long long ldw, int K, const bf16* WT,
+          bf16* dX, int ldx, cudaStream_t st) {
+  if (t->mn_operands) return gemm_dgrad(t, dY, ldy, R, N, Wm, ldw, K, dX, ldx, st);
+  return gemm(t, dY, ldy, R, N, WT, N, K, dX, ldx, EPI_STORE, st);
+}
 // dst [cols, rows] (pitch ldd) = src [rows, cols] (pitch lds) transposed
 int transpose(CsmTrain* t, const bf16* src, int rows, int cols, long long lds, bf16* dst, long long ldd, cudaStream_t st) {
   if (rows <= 0 || cols <= 0) return 0;
@@ -154,6 +194,7 @@ int transpose(CsmTrain* t, const bf16* src, int rows, int cols, long long lds, b
 // K-major dimension of the GEMM
 int wgrad(CsmTrain* t, const bf16* dY, long long ldy, const bf16* X, long long ldx, int R, int N, int K, bf16* dW, int ldw,
           cudaStream_t st) {
+  if (t->mn_operands) return gemm_wgrad(t, dY, ldy, X, ldx, R, N, K, dW, ldw, st);
   const int Rp = rup(R, 8);
   TRY(transpose(t, dY, R, N, ldy, t->tA, Rp, st));
   TRY(transpose(t, X, R, K, ldx, t->tB, Rp, st));
@@ -255,11 +296,11 @@ int stack_backward(CsmTrain* t, TStack& s, const char* tag, int S, int nseq, con
     const std::string pre = std::string("d.") + tag + "." + std::to_string(l) + ".";
     TRY(note(t, pre + "h_out", dh, (size_t)R * s.H * 2, st));
     // ---- MLP: h_out = h_mid + down(act), act = silu(gate) * up, gate|up = Wgu hn2, hn2 = norm(h_mid)
-    TRY(gemm(t, dh, s.H, R, s.H, y.WdownT, s.H, s.I, t->dAct, s.I, EPI_STORE, st));
+    TRY(dgrad(t, dh, s.H, R, s.H, y.down, s.I, s.I, y.WdownT, t->dAct, s.I, st));
     if (want_grads) TRY(wgrad(t, dh, s.H, y.act, s.I, R, s.H, s.I, y.gdown, s.I, st));
     swiglu_bwd_kernel<<<nblocks((long long)R * s.I / 2), 256, 0, st>>>(y.gu, t->dAct, R, s.I, t->dGU);
     TCK(cudaGetLastError());
-    TRY(gemm(t, t->dGU, 2 * s.I, R, 2 * s.I, y.WguT, 2 * s.I, s.H, t->dHn, s.H, EPI_STORE, st));
+    TRY(dgrad(t, t->dGU, 2 * s.I, R, 2 * s.I, y.Wgu, s.H, s.H, y.WguT, t->dHn, s.H, st));
     if (want_grads) {
       TRY(wgrad(t, t->dGU, 2 * s.I, y.hn2, s.H, R, 2 * s.I, s.H, t->dWtmp, s.H, st));
       TRY(copy_rows(t, y.ggate, t->dWtmp, (size_t)s.I * s.H, st));
@@ -270,7 +311,7 @@ int stack_backward(CsmTrain* t, TStack& s, const char* tag, int S, int nseq, con
     TRY(norm_bwd(t, s, y.h_mid, y.ln2, t->dHn, dh, dh, want_grads ? y.gln2 : nullptr, R, st));
     TRY(note(t, pre + "h_mid", dh, (size_t)R * s.H * 2, st));
     // ---- attention: h_mid = h_in + o(attn), attn = sdpa(rope(q), rope(k), v), q|k|v = Wqkv hn1, hn1 = norm(h_in)
-    TRY(gemm(t, dh, s.H, R, s.H, y.WoT, s.H, s.nq, t->dAttn, s.nq, EPI_STORE, st));
+    TRY(dgrad(t, dh, s.H, R, s.H, y.o, s.nq, s.nq, y.WoT, t->dAttn, s.nq, st));
     if (want_grads) TRY(wgrad(t, dh, s.H, y.attn, s.nq, R, s.H, s.nq, y.go, s.nq, st));
     attn_delta_kernel<<<nblocks((long long)R * s.heads * 32, 256, 1 << 30), 256, 0, st>>>(y.attn, t->dAttn, R, s.heads, s.hd,
                                                                                             t->delta);
@@ -285,7 +326,7 @@ int stack_backward(CsmTrain* t, TStack& s, const char* tag, int S, int nseq, con
     TCK(cudaGetLastError());
     TRY(note(t, pre + "attn", t->dAttn, (size_t)R * s.nq * 2, st));
     TRY(note(t, pre + "qkv_raw", t->dQKV, (size_t)R * s.W * 2, st));   // gradient w.r.t. the un-rotated q | k | v
-    TRY(gemm(t, t->dQKV, s.W, R, s.W, y.WqkvT, s.W, s.H, t->dHn, s.H, EPI_STORE, st));
+    TRY(dgrad(t, t->dQKV, s.W, R, s.W, y.Wqkv, s.H, s.H, y.WqkvT, t->dHn, s.H, st));
     TRY(note(t, pre + "hn1", t->dHn, (size_t)R * s.H * 2, st));
     if (want_grads) {
       TRY(wgrad(t, t->dQKV, s.W, y.hn1, s.H, R, s.W, s.H, t->dWtmp, s.H, st));
@@ -358,7 +399,7 @@ int bind_stack(CsmTrain* t, TStack& s, const void* const* w, const void* const* 
     TRY(copy_rows(t, y.Wqkv + ((size_t)s.nq + kvw) * s.H, y.v, kvw * s.H, st));
     TRY(copy_rows(t, y.Wgu, y.gate, (size_t)s.I * s.H, st));
     TRY(copy_rows(t, y.Wgu + (size_t)s.I * s.H, y.up, (size_t)s.I * s.H, st));
-    if (g) {
+    if (g && !t->mn_operands) {
       TRY(transpose(t, y.Wqkv, s.W, s.H, s.H, y.WqkvT, s.W, st));      // [W, H] -> [H, W]
       TRY(transpose(t, y.o, s.H, s.nq, s.nq, y.WoT, s.H, st));         // [H, nq] -> [nq, H]
       TRY(transpose(t, y.Wgu, 2 * s.I, s.H, s.H, y.WguT, 2 * s.I, st)); // [2I, H] -> [H, 2I]
@@ -385,6 +426,7 @@ int csm_train_create(const CsmShapes* sh, int max_tokens, int max_frames, CsmTra
   TCK(cudaDeviceGetAttribute(&t->sms, cudaDevAttrMultiProcessorCount, dev));
   t->V = sh->audio_vocab; t->Vp = rup(sh->audio_vocab, 64); t->text_vocab = sh->text_vocab;
   t->max_tokens = max_tokens; t->max_frames = max_frames;
+  t->mn_operands = getenv("CSM_TRAIN_TRANSPOSE") == nullptr;
   if (sh->backbone.n_pos < 1 || sh->decoder.n_pos < 33) return tfail(t, CSM_EINVAL, "rope tables: the decoder needs 33 positions");
   const int Rd = max_frames * 33;
   TRY(setup_stack(t, t->bb, sh->backbone, max_tokens));
@@ -486,7 +528,7 @@ int csm_train_step(CsmTrain* t, const CsmWeights* w, const CsmWeights* g, const 
   TRY(copy_rows(t, t->Wc0p, c0, (size_t)V * b.H, st));
   TCK(cudaMemsetAsync(t->AHt, 0, (size_t)31 * Vp * d.H * 2, st));
   for (int c = 0; c < 31; ++c) TRY(transpose(t, ah + (size_t)c * d.H * V, d.H, V, V, t->AHt + (size_t)c * Vp * d.H, d.H, st));
-  if (want) {
+  if (want && !t->mn_operands) {
     TRY(transpose(t, t->Wc0p, Vp, b.H, b.H, t->Wc0pT, Vp, st));
     TRY(transpose(t, proj, d.H, b.H, b.H, t->WprojT, d.H, st));
     TCK(cudaMemsetAsync(t->AHp, 0, (size_t)31 * Vp * d.H * 2, st));
@@ -574,7 +616,7 @@ int csm_train_step(CsmTrain* t, const CsmWeights* w, const CsmWeights* g, const 
     TCK(cudaMemsetAsync(t->audio_acc, 0, (size_t)V * 32 * b.H * 4, st));
     TCK(cudaMemsetAsync(t->text_acc, 0, (size_t)t->text_vocab * b.H * 4, st));
     // codebook-0 head: d hf = dlogits0 Wc0, d Wc0 = dlogits0^T hf
-    TRY(gemm(t, t->logits0, Vp, R, Vp, t->Wc0pT, Vp, b.H, t->dh_bb, b.H, EPI_STORE, st));
+    TRY(dgrad(t, t->logits0, Vp, R, Vp, t->Wc0p, b.H, b.H, t->Wc0pT, t->dh_bb, b.H, st));
     TRY(wgrad(t, t->logits0, Vp, b.hf, b.H, R, Vp, b.H, t->dWtmp, b.H, st));
     TRY(copy_rows(t, (bf16*)g->codebook0_head, t->dWtmp, (size_t)V * b.H, st));
     if (F > 0) {
@@ -583,7 +625,8 @@ int csm_train_step(CsmTrain* t, const CsmWeights* w, const CsmWeights* g, const 
       bf16* dAH = t->dWtmp + (size_t)Vp * b.H;    // [Hd, Vp] scratch behind the codebook-0 gradient
       for (int c = 0; c < 31; ++c) {
         const bf16* dl = t->logits_d + (size_t)c * F * Vp;
-        TRY(gemm(t, dl, Vp, F, Vp, t->AHp + (size_t)c * d.H * Vp, Vp, d.H, t->dhdf + (size_t)(c + 1) * d.H, 33 * d.H, EPI_STORE, st));
+        TRY(dgrad(t, dl, Vp, F, Vp, t->AHt + (size_t)c * Vp * d.H, d.H, d.H, t->AHp + (size_t)c * d.H * Vp,
+                  t->dhdf + (size_t)(c + 1) * d.H, 33 * d.H, st));
         TRY(wgrad(t, d.hf + (size_t)(c + 1) * d.H, (long long)33 * d.H, dl, Vp, F, d.H, Vp, dAH, Vp, st));
         TCK(cudaMemcpy2DAsync((bf16*)g->audio_head + (size_t)c * d.H * V, (size_t)V * 2, dAH, (size_t)Vp * 2, (size_t)V * 2,
                               (size_t)d.H, cudaMemcpyDeviceToDevice, st));
@@ -592,7 +635,7 @@ int csm_train_step(CsmTrain* t, const CsmWeights* w, const CsmWeights* g, const 
       TRY(stack_backward(t, d, "dec", 33, F, nullptr, t->dh_dec, true, st));
       TRY(note(t, "d.dec_x0", t->dh_dec, (size_t)Rd * d.H * 2, st));
       // projection: d dec_in = d x0 Wproj, d Wproj = d x0^T dec_in
-      TRY(gemm(t, t->dh_dec, d.H, Rd, d.H, t->WprojT, d.H, b.H, t->d_dec_in, b.H, EPI_STORE, st));
+      TRY(dgrad(t, t->dh_dec, d.H, Rd, d.H, proj, b.H, b.H, t->WprojT, t->d_dec_in, b.H, st));
       TRY(wgrad(t, t->dh_dec, d.H, t->dec_in, b.H, Rd, d.H, b.H, (bf16*)g->projection, b.H, st));
       decoder_scatter_kernel<<<Rd, 256, 0, st>>>(t->d_dec_in, ids_ll, t->frames, S, V, b.H, t->dh_bb, t->audio_acc);
       TCK(cudaGetLastError());

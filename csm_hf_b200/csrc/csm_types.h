@@ -165,6 +165,10 @@ struct GemmParams {
   int S, pos0, b0, heads, kv, layer, Bmax, Tcap;
   bf16 *kc, *vc;
   const bf16 *cos_t, *sin_t;    // [n_pos][32]
+  // operand layouts (EPI_STORE / EPI_RESID only): 0 = K-major (rows of the matrix are contiguous along the contraction),
+  // 1 = MN-major (the matrix is stored [K, rows]: contiguous along its M / N dimension) -- dX = dY W reads W [N_out, K_in]
+  // as an MN-major B operand, dW = dY^T X reads dY and X as MN-major operands: no transposed copies
+  int a_mn, b_mn;
 };
 
 // Row split and chunking of one weight matrix for one CTA.
