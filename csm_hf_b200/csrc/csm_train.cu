@@ -224,6 +224,8 @@ int flash_fwd(CsmTrain* t, const TStack& s, const bf16* qkv, int S, int nseq, co
               cudaStream_t st) {
   const size_t smem = (size_t)4 * 64 * (HD + 8) * 2 + 128;
   TCK(cudaFuncSetAttribute((const void*)flash_fwd_kernel<HD>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  TCK(cudaFuncSetAttribute((const void*)flash_fwd_kernel<HD>, cudaFuncAttributePreferredSharedMemoryCarveout,
+                           cudaSharedmemCarveoutMaxShared));
   dim3 grid((S + 127) / 128, s.heads, nseq);
   flash_fwd_kernel<HD><<<grid, 256, smem, st>>>(qkv, S, s.heads, s.kv, s.scale, valid, out, lse);
   TCK(cudaGetLastError());
@@ -235,6 +237,8 @@ int flash_bwd(CsmTrain* t, const TStack& s, const bf16* qkv, const bf16* d_out, 
               int nseq, const unsigned char* valid, bf16* dqkv, float* dq_acc, cudaStream_t st) {
   const size_t smem = (size_t)6 * 64 * (HD + 8) * 2 + (size_t)64 * 72 * 2 + 4 * 64 * 4 + 64;
   TCK(cudaFuncSetAttribute((const void*)flash_bwd_kernel<HD>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  TCK(cudaFuncSetAttribute((const void*)flash_bwd_kernel<HD>, cudaFuncAttributePreferredSharedMemoryCarveout,
+                           cudaSharedmemCarveoutMaxShared));
   dim3 grid((S + 63) / 64, s.kv, nseq);
   flash_bwd_kernel<HD><<<grid, 128, smem, st>>>(qkv, d_out, lse, delta, S, s.heads, s.kv, s.scale, valid, dqkv, dq_acc);
   TCK(cudaGetLastError());

@@ -67,7 +67,7 @@ __global__ void rope_rows_kernel(bf16* __restrict__ x, int ld, int rows, int S, 
 // cp.async.  qkv row = rotated q heads | rotated k heads | v heads.  Query i of a sequence sees keys <= i that are valid
 // (valid == null: all).  Saves lse = log(sum exp(scale * s)) per (row, head); a row that sees nothing: out 0, lse 0.
 template <int HD>
-__global__ void __launch_bounds__(256) flash_fwd_kernel(const bf16* __restrict__ qkv, int S, int heads, int kv, float scale,
+__global__ void __launch_bounds__(256, HD == 64 ? 2 : 1) flash_fwd_kernel(const bf16* __restrict__ qkv, int S, int heads, int kv, float scale,
                                                         const unsigned char* __restrict__ valid, bf16* __restrict__ out,
                                                         float* __restrict__ lse) {
   constexpr int BQ = 128, BK = 64, LDS = HD + 8, C8 = HD / 8;
