@@ -72,6 +72,7 @@ def ncu_traffic(batch):
 
 def training_point(cfg, sd, dev, rank, world, seq, tpeak, note, steps=3):
     """ms per training step (CSMModel.forward(labels=...) + backward, csrc/csm_train.cu) and its tensor-roofline fraction."""
+    import torch
     import torch.distributed as dist
     from csm_hf_b200.modeling import CSMModel
     from csm_hf_b200.synthetic import make_training_batch
@@ -308,7 +309,7 @@ def main():
     ap.add_argument("--ctx", type=int, default=2048)
     ap.add_argument("--frames", type=int, default=200)
     ap.add_argument("--points", default="1,8,32", help="batch sizes per GPU reported under config.points ('' = none)")
-    ap.add_argument("--point-steps", type=int, default=2)
+    ap.add_argument("--point-steps", type=int, default=3)
     ap.add_argument("--no-train-point", action="store_true",
                     help="skip the training-step point (BASELINE config #5: fwd+bwd, seq_len 4096, one sequence per GPU)")
     ap.add_argument("--train-seq", type=int, default=4096)
@@ -367,7 +368,7 @@ def main():
             dist.barrier()
         torch.cuda.synchronize()
 
-    def measure(batch, steps, warmup):
+    def measure(batch, steps, warmup, headline=False):
         """Device-resident inputs, `steps` timed generate() calls after `warmup`: -> (model, dict)."""
         model = CSMModel(cfg, sd, device=dev, max_batch=batch, max_ctx=a.ctx + a.frames + 8)
         GB = batch * world
@@ -389,24 +390,29 @@ def main():
         dec_ms, dec_n = 0.0, 0
         fence()
         ev0.record()
+        marks = []
         for _ in range(steps):
             out = step()
             ms, n = model.last_decode_ms()
             dec_ms += ms
             dec_n += n
+            marks.append(torch.cuda.Event(enable_timing=True))
+            marks[-1].record()
         ev1.record()
         fence()
-        t = torch.tensor([ev0.elapsed_time(ev1), dec_ms / max(dec_n, 1)], device=dev, dtype=torch.float64)
+        per = sorted(b.elapsed_time(c) for b, c in zip([ev0] + marks[:-1], marks))
+        t = torch.tensor([ev0.elapsed_time(ev1), dec_ms / max(dec_n, 1), per[len(per) // 2] if len(per) % 2 else
+                          0.5 * (per[len(per) // 2 - 1] + per[len(per) // 2])], device=dev, dtype=torch.float64)
         if world > 1:
             dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        ms_total, dec_per = [float(x) for x in t.cpu()]
-        ms_step = ms_total / steps
+        ms_total, dec_per, ms_median = [float(x) for x in t.cpu()]
+        ms_step = ms_total / steps if headline else ms_median   # (points: the median step, robust to a one-off stall)
         abytes = algorithmic_bytes(batch, t_mean)
         achieved = abytes / (dec_per / 1000.0) / 1e9 if dec_per > 0 else 0.0
         pre_ms = max(ms_step - dec_per * (a.frames - 1), 1e-6)       # prefill + the first frame's launch
         ptf = prefill_flops(batch, a.ctx) / (pre_ms / 1000.0) / 1e12
         res = {"batch_per_gpu": batch, "global_batch": GB, "value": GB * a.frames / (ms_step / 1000.0), "unit": "frames/s",
-               "ms_per_step": ms_step, "steps": steps, "decode_ms_per_frame": dec_per,
+               "ms_per_step": ms_step, "ms_per_step_median": ms_median, "steps": steps, "decode_ms_per_frame": dec_per,
                "decode_frames_per_s_per_gpu": batch * 1000.0 / dec_per if dec_per > 0 else 0.0,
                "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                             "algorithmic_bytes_per_launch": abytes, "traffic": ncu_traffic(batch)},
@@ -419,7 +425,7 @@ def main():
     if rank == 0:
         sampler.start()
     note("headline point starts")
-    model, head, (ids, mask) = measure(a.batch, a.steps, max(a.warmup, 3))
+    model, head, (ids, mask) = measure(a.batch, a.steps, max(a.warmup, 3), headline=True)
     note("timed device steps done")
     # end to end through host buffers (same process, same engine)
     lo = rank * a.batch

@@ -232,7 +232,7 @@ __global__ void attn_delta_kernel(const bf16* __restrict__ o, const bf16* __rest
 // as A fragments; dQ += dS K takes the transposed 8x8 blocks (movmatrix) and is reduced into an fp32 buffer in global
 // memory (several key blocks and four warps contribute to a query row).
 template <int HD>
-__global__ void __launch_bounds__(128) flash_bwd_kernel(const bf16* __restrict__ qkv, const bf16* __restrict__ d_out,
+__global__ void __launch_bounds__(128, HD == 64 ? 3 : 1) flash_bwd_kernel(const bf16* __restrict__ qkv, const bf16* __restrict__ d_out,
                                                         const float* __restrict__ lse, const float* __restrict__ delta,
                                                         int S, int heads, int kv, float scale,
                                                         const unsigned char* __restrict__ valid, bf16* __restrict__ dqkv,
@@ -321,65 +321,69 @@ __global__ void __launch_bounds__(128) flash_bwd_kernel(const bf16* __restrict__
     const bf16* cdO = sdO + buf * TILE;
     const float* cLse = sLse + buf * BK;
     const float* cD = sD + buf * BK;
-    // S^T and dP^T: [16 keys x 64 queries]
-    float st[8][4], dp[8][4];
+    // The 64 queries of the block in two halves of 32 (register budget: three CTAs per SM at head dim 64).  Per half:
+    // S^T and dP^T as [16 keys x 32 queries] accumulators; P^T = exp(scale s - lse), dS^T = P^T (dP^T - D) scale as bf16
+    // A fragments (k16 tile = two query n-tiles); dV += P^T dO and dK += dS^T Q (B fragments: k = query rows, n = head
+    // dims -> transposed ldmatrix); dS^T goes to shared memory for the dQ product below.
+#pragma unroll 1
+    for (int hf = 0; hf < 2; ++hf) {
+      float st[4][4], dp[4][4];
 #pragma unroll
-    for (int j = 0; j < 8; ++j) {
+      for (int j4 = 0; j4 < 4; ++j4) {
+        const int j = 4 * hf + j4;
 #pragma unroll
-      for (int q = 0; q < 4; ++q) { st[j][q] = 0.f; dp[j][q] = 0.f; }
+        for (int q = 0; q < 4; ++q) { st[j4][q] = 0.f; dp[j4][q] = 0.f; }
 #pragma unroll
-      for (int kp = 0; kp < HD / 32; ++kp) {
-        uint32_t f[4];
-        t_ldsm_x4(f, cQ + (8 * j + (lane & 7)) * LDS + 32 * kp + 8 * (lane >> 3));
-        mma16816(st[j], ka[2 * kp], f[0], f[1]);
-        mma16816(st[j], ka[2 * kp + 1], f[2], f[3]);
-        t_ldsm_x4(f, cdO + (8 * j + (lane & 7)) * LDS + 32 * kp + 8 * (lane >> 3));
-        mma16816(dp[j], va[2 * kp], f[0], f[1]);
-        mma16816(dp[j], va[2 * kp + 1], f[2], f[3]);
+        for (int kp = 0; kp < HD / 32; ++kp) {
+          uint32_t f[4];
+          t_ldsm_x4(f, cQ + (8 * j + (lane & 7)) * LDS + 32 * kp + 8 * (lane >> 3));
+          mma16816(st[j4], ka[2 * kp], f[0], f[1]);
+          mma16816(st[j4], ka[2 * kp + 1], f[2], f[3]);
+          t_ldsm_x4(f, cdO + (8 * j + (lane & 7)) * LDS + 32 * kp + 8 * (lane >> 3));
+          mma16816(dp[j4], va[2 * kp], f[0], f[1]);
+          mma16816(dp[j4], va[2 * kp + 1], f[2], f[3]);
+        }
+      }
+      uint32_t pa[2][4], dsa[2][4];
+#pragma unroll
+      for (int j4 = 0; j4 < 4; ++j4) {
+        const int qi = 8 * (4 * hf + j4) + 2 * t, qq = q0 + qi;
+        const float l0 = cLse[qi], l1 = cLse[qi + 1], d0 = cD[qi], d1 = cD[qi + 1];
+        const bool m00 = okk_lo && key_lo <= qq, m01 = okk_lo && key_lo <= qq + 1;
+        const bool m10 = okk_hi && key_hi <= qq, m11 = okk_hi && key_hi <= qq + 1;
+        const float p0 = m00 ? exp2f(st[j4][0] * sl2 - l0) : 0.f, p1 = m01 ? exp2f(st[j4][1] * sl2 - l1) : 0.f;
+        const float p2 = m10 ? exp2f(st[j4][2] * sl2 - l0) : 0.f, p3 = m11 ? exp2f(st[j4][3] * sl2 - l1) : 0.f;
+        const float s0 = p0 * (dp[j4][0] - d0) * scale, s1 = p1 * (dp[j4][1] - d1) * scale;
+        const float s2 = p2 * (dp[j4][2] - d0) * scale, s3 = p3 * (dp[j4][3] - d1) * scale;
+        const int kk = j4 >> 1, o2 = (j4 & 1) * 2;
+        pa[kk][o2] = pack_bf16(p0, p1);
+        pa[kk][o2 + 1] = pack_bf16(p2, p3);
+        dsa[kk][o2] = pack_bf16(s0, s1);
+        dsa[kk][o2 + 1] = pack_bf16(s2, s3);
+      }
+#pragma unroll
+      for (int k2 = 0; k2 < 2; ++k2) {
+        const int kk = 2 * hf + k2;
+#pragma unroll
+        for (int jd = 0; jd < HD / 8; ++jd) {
+          uint32_t b0, b1;
+          t_ldsm_x2_trans(b0, b1, cdO + (16 * kk + (lane & 15)) * LDS + 8 * jd);
+          mma16816(dv[jd], pa[k2], b0, b1);
+          t_ldsm_x2_trans(b0, b1, cQ + (16 * kk + (lane & 15)) * LDS + 8 * jd);
+          mma16816(dk[jd], dsa[k2], b0, b1);
+        }
+      }
+      bf16* wr = sdS + (16 * warp + g) * LDD + 32 * hf + 2 * t;
+#pragma unroll
+      for (int j4 = 0; j4 < 4; ++j4) {
+        const int kk = j4 >> 1, o2 = (j4 & 1) * 2;
+        *reinterpret_cast<uint32_t*>(wr + 8 * j4) = dsa[kk][o2];
+        *reinterpret_cast<uint32_t*>(wr + 8 * LDD + 8 * j4) = dsa[kk][o2 + 1];
       }
     }
-    // P^T and dS^T as bf16 A fragments (k16 tile kk = query n-tiles 2kk, 2kk+1)
-    uint32_t pa[4][4], dsa[4][4];
-#pragma unroll
-    for (int j = 0; j < 8; ++j) {
-      const int qi = 8 * j + 2 * t, qq = q0 + qi;
-      const float l0 = cLse[qi], l1 = cLse[qi + 1], d0 = cD[qi], d1 = cD[qi + 1];
-      const bool m00 = okk_lo && key_lo <= qq, m01 = okk_lo && key_lo <= qq + 1;
-      const bool m10 = okk_hi && key_hi <= qq, m11 = okk_hi && key_hi <= qq + 1;
-      const float p0 = m00 ? exp2f(st[j][0] * sl2 - l0) : 0.f, p1 = m01 ? exp2f(st[j][1] * sl2 - l1) : 0.f;
-      const float p2 = m10 ? exp2f(st[j][2] * sl2 - l0) : 0.f, p3 = m11 ? exp2f(st[j][3] * sl2 - l1) : 0.f;
-      const float s0 = p0 * (dp[j][0] - d0) * scale, s1 = p1 * (dp[j][1] - d1) * scale;
-      const float s2 = p2 * (dp[j][2] - d0) * scale, s3 = p3 * (dp[j][3] - d1) * scale;
-      const int kk = j >> 1, o2 = (j & 1) * 2;
-      pa[kk][o2] = pack_bf16(p0, p1);
-      pa[kk][o2 + 1] = pack_bf16(p2, p3);
-      dsa[kk][o2] = pack_bf16(s0, s1);
-      dsa[kk][o2 + 1] = pack_bf16(s2, s3);
-    }
-    // dV += P^T dO, dK += dS^T Q   (B fragments: k = query rows, n = head dims -> transposed ldmatrix)
-#pragma unroll
-    for (int kk = 0; kk < 4; ++kk) {
-#pragma unroll
-      for (int jd = 0; jd < HD / 8; ++jd) {
-        uint32_t b0, b1;
-        t_ldsm_x2_trans(b0, b1, cdO + (16 * kk + (lane & 15)) * LDS + 8 * jd);
-        mma16816(dv[jd], pa[kk], b0, b1);
-        t_ldsm_x2_trans(b0, b1, cQ + (16 * kk + (lane & 15)) * LDS + 8 * jd);
-        mma16816(dk[jd], dsa[kk], b0, b1);
-      }
-    }
-    // dQ = dS K needs all 64 keys of a query row: the warps exchange dS^T through shared memory, then warp w owns queries
+    // dQ = dS K needs all 64 keys of a query row: after the exchange through shared memory warp w owns queries
     // 16w..16w+15 (A fragments = transposed 8x8 blocks of the [key][query] tile) and adds its finished rows to the fp32
     // buffer in global memory (other key blocks add to the same rows)
-    {
-      bf16* wr = sdS + (16 * warp + g) * LDD + 2 * t;
-#pragma unroll
-      for (int j = 0; j < 8; ++j) {
-        const int kk = j >> 1, o2 = (j & 1) * 2;
-        *reinterpret_cast<uint32_t*>(wr + 8 * j) = dsa[kk][o2];
-        *reinterpret_cast<uint32_t*>(wr + 8 * LDD + 8 * j) = dsa[kk][o2 + 1];
-      }
-    }
     __syncthreads();
     {
       float dq[HD / 8][4];

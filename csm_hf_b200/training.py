@@ -178,6 +178,14 @@ def training_forward(model, input_ids: torch.Tensor, attention_mask: Optional[to
         if attention_mask.shape != input_ids.shape:
             raise ValueError("attention_mask must match input_ids")
         mask = (attention_mask != 0).to(device=dev, dtype=torch.int32).contiguous()   # (the processor pads with float32 masks)
+    nq, V = cfg.audio_num_codebooks, cfg.audio_vocab_size
+    # ids index the embedding tables and labels index the logits on the device: out-of-range values must not get there
+    if int(ids[..., :nq].min()) < 0 or int(ids[..., :nq].max()) >= V or int(ids[..., nq].min()) < 0 \
+            or int(ids[..., nq].max()) >= cfg.text_vocab_size:
+        raise IndexError("input_ids out of range of the embedding tables")
+    lab_a = lab[..., :nq]
+    if bool(((lab_a < 0) & (lab_a != -100)).any()) or int(lab_a.max()) >= V:
+        raise IndexError(f"labels must be -100 or in [0, {V})")
     names = list(state_dict_shapes(cfg).keys())
     params = dict(model.named_parameters())
     missing = [k for k in names if k not in params]

@@ -87,6 +87,9 @@ def main():
     ap.add_argument("--train", action="store_true",
                     help="mint the training fixtures (tiny config): the reference's loss triple and parameter gradients of "
                          "CSMModel.forward(labels=...) + backward on a synthetic amortised, left-padded batch")
+    ap.add_argument("--train-1b", action="store_true",
+                    help="mint the csm-1b training fixture: loss triple and per-parameter gradient norms of the reference's "
+                         "fp32 forward(labels=...) + backward on a 96-frame batch (minutes of CPU, 12 GB)")
     ap.add_argument("--decisive", action="store_true",
                     help="search seeds of the tiny config whose FREE-RUNNING greedy ids are the same in the reference's fp32 "
                          "and bf16 runs (every argmax margin exceeds the arithmetic noise), and mint them")
@@ -94,6 +97,36 @@ def main():
     assert R.reference_available(), "needs /root/reference"
     torch.manual_seed(0)
     tiny = tiny_config()
+    if a.train_1b:
+        from csm_hf_b200.synthetic import make_training_batch
+        cfg = CSMConfig()
+        recipe = dict(config="csm1b", batch=2, frames=96, seed=777, text_frames=4, amortization_ratio=8, pad=5,
+                      weight_seed=0, norm_jitter=0.0)
+        ids, mask, labels = make_training_batch(cfg, recipe["batch"], recipe["frames"], seed=recipe["seed"],
+                                                text_frames=recipe["text_frames"],
+                                                amortization_ratio=recipe["amortization_ratio"], pad=recipe["pad"])
+        sd = make_state_dict(cfg, seed=recipe["weight_seed"])
+        m = R.build_reference_model(cfg, sd, torch.float32)
+        for p in m.parameters():
+            p.requires_grad_(True)
+        t0 = time.time()
+        out = m(input_ids=ids, attention_mask=mask, labels=labels)
+        out.loss.backward()
+        grads = {k: p.grad.detach() for k, p in m.state_dict(keep_vars=True).items()}
+        # a few gradient rows in full, besides every norm: the codebook-0 head rows of the labelled tokens and one
+        # projection row of every matrix kind of the first and the last backbone layer
+        samples = {}
+        for k in ("backbone.layers.0.self_attn.q_proj.weight", "backbone.layers.15.mlp.down_proj.weight",
+                  "decoder.layers.3.mlp.gate_proj.weight", "projection.weight", "backbone.layers.7.self_attn.v_proj.weight"):
+            samples[k] = grads[k][:4].clone()
+        samples["audio_head"] = grads["audio_head"][:, :2, :].clone()
+        fx = {"recipe": dict(recipe, dtype="fp32"), "loss": out.loss.detach(), "backbone_loss": out.backbone_loss.detach(),
+              "decoder_loss": out.decoder_loss.detach(),
+              "grad_norms": {k: float(g.norm()) for k, g in grads.items()}, "grad_samples": samples}
+        torch.save(fx, os.path.join(GOLD, "csm1b_train_fp32.pt"))
+        print(f"csm1b_train_fp32.pt: loss {float(out.loss.detach()):.6f} = {float(out.backbone_loss.detach()):.6f} + "
+              f"{float(out.decoder_loss.detach()):.6f}; {len(grads)} gradient norms in {time.time() - t0:.0f}s", flush=True)
+        return
     if a.train:
         from csm_hf_b200.synthetic import make_training_batch
         recipe = dict(config="tiny", batch=2, frames=24, seed=4321, text_frames=2, amortization_ratio=4, pad=3,

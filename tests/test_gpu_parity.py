@@ -355,8 +355,6 @@ def test_errors_are_loud(tiny):
         model.generate(ids, mask, max_new_frames=2, temperature=-1.0, topk=5)
     with pytest.raises(ValueError):
         model.generate(ids, mask.float() * 0.5, max_new_frames=2, temperature=0)      # a float mask must be 0 / 1
-    with pytest.raises(NotImplementedError):
-        model.forward(ids, mask, labels=ids)
     bad = ids.clone()
     bad[0, 0, 0] = cfg.audio_vocab_size
     with pytest.raises(IndexError):

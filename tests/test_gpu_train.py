@@ -164,3 +164,46 @@ def test_training_errors_are_loud(dev):
         model(input_ids=ids, attention_mask=mask, labels=labels[:, :-1])
     with pytest.raises(ValueError):
         model(input_ids=ids[:, :, :5], attention_mask=mask, labels=labels)
+    bad = ids.clone()
+    bad[0, 3, 2] = cfg.audio_vocab_size
+    with pytest.raises(IndexError):
+        model(input_ids=bad, attention_mask=mask, labels=labels)
+    badl = labels.clone()
+    badl[1, 5, 0] = cfg.audio_vocab_size + 3
+    with pytest.raises(IndexError):
+        model(input_ids=ids, attention_mask=mask, labels=badl)
+
+
+def test_csm1b_loss_and_gradient_norms_vs_reference_fixture(dev):
+    """csm-1b dimensions (16 + 4 layers, head dims 64 and 128, vocabulary 2051 padded to 2112 columns, 2 x 96 frames
+    left-padded, 1/8 amortisation) against the reference's fp32 CPU forward(labels=...) + backward
+    (tests/golden/csm1b_train_fp32.pt, oracle/make_golden.py --train-1b): loss triple within 1 %, the norm of every one
+    of the 187 parameter gradients within 6 %, and the stored gradient rows within 6 % of their largest entry
+    (bf16 pipeline against an fp32 reference)."""
+    from csm_hf_b200.config import CSMConfig
+    from csm_hf_b200.modeling import CSMModel
+    fx = torch.load(os.path.join(GOLD, "csm1b_train_fp32.pt"), weights_only=False)
+    r = fx["recipe"]
+    cfg = CSMConfig()
+    sd = make_state_dict(cfg, seed=r["weight_seed"], norm_jitter=r["norm_jitter"])
+    ids, mask, labels = make_training_batch(cfg, r["batch"], r["frames"], seed=r["seed"], text_frames=r["text_frames"],
+                                            amortization_ratio=r["amortization_ratio"], pad=r["pad"])
+    model = CSMModel(cfg, sd, device=dev)
+    model.requires_grad_(True)
+    out = model(input_ids=ids, attention_mask=mask, labels=labels)
+    for k in ("loss", "backbone_loss", "decoder_loss"):
+        got, want = float(getattr(out, k).detach()), float(fx[k])
+        assert abs(got - want) <= 1e-2 * want, (k, got, want)
+    out.loss.backward()
+    worst = 0.0
+    for k, p in model.named_parameters():
+        want = fx["grad_norms"][k]
+        got = float(p.grad.float().norm())
+        worst = max(worst, abs(got - want) / want)
+        assert abs(got - want) <= 0.06 * want, (k, got, want)
+    for k, rows in fx["grad_samples"].items():
+        g = dict(model.named_parameters())[k].grad
+        got = g[:, :2, :] if k == "audio_head" else g[:4]
+        grad_close(got, rows, f"rows of {k}", rel=0.06, cos_min=0.998)
+    del model
+    torch.cuda.empty_cache()
