@@ -70,7 +70,7 @@ def ncu_traffic(batch):
         return json.load(f).get(f"b{batch}")
 
 
-def training_point(cfg, sd, dev, rank, world, seq, tpeak, note, steps=3):
+def training_point(cfg, sd, dev, rank, world, seq, tpeak, note, steps=5):
     """ms per training step (CSMModel.forward(labels=...) + backward, csrc/csm_train.cu) and its tensor-roofline fraction."""
     import torch
     import torch.distributed as dist
@@ -82,8 +82,10 @@ def training_point(cfg, sd, dev, rank, world, seq, tpeak, note, steps=3):
         tm.requires_grad_(True)
         ids, mask, labels = [t.to(dev) for t in make_training_batch(cfg, 1, seq, seed=100 + rank, text_frames=16)]
         F = int((labels[:, :, :32] != -100).all(dim=2).sum())
-        out = tm(input_ids=ids, attention_mask=mask, labels=labels)     # warm-up step, local
-        out.loss.backward()
+        for _ in range(2):                                                # warm-up steps, local
+            tm.zero_grad(set_to_none=True)
+            out = tm(input_ids=ids, attention_mask=mask, labels=labels)
+            out.loss.backward()
         torch.cuda.synchronize()
     except Exception as e:   # noqa: BLE001
         ok, err = 0, f"{type(e).__name__}: {e}"
@@ -120,7 +122,7 @@ def training_point(cfg, sd, dev, rank, world, seq, tpeak, note, steps=3):
            "ms_per_step": ms, "steps": steps, "tokens_per_s": world * seq / (ms / 1000.0), "loss": float(out.loss.detach()),
            "roofline": {"bound": "tensor", "achieved": fl / (ms / 1000.0) / 1e12, "peak": tpeak, "unit": "TFLOP/s",
                         "frac": fl / (ms / 1000.0) / 1e12 / tpeak, "algorithmic_flops_per_step_per_gpu": fl},
-           "gpu_launches_per_step": tm._train_engine.launches() // (steps + 1)}
+           "gpu_launches_per_step": tm._train_engine.launches() // (steps + 2)}
     note(f"training point: {ms:.1f} ms/step")
     del tm
     torch.cuda.empty_cache()
