@@ -118,6 +118,14 @@ def allreduce_gradients(model, group=None, bucket_bytes: int = 256 << 20) -> int
     grads = [p.grad for _, p in sorted(model.named_parameters()) if p.grad is not None]
     if world == 1 or not grads:
         return 0
+    flat = getattr(model, "_grad_flat", None)
+    if flat is not None and len(grads) == len(list(model.parameters())) and \
+            all(g.untyped_storage().data_ptr() == flat.untyped_storage().data_ptr() for g in grads):
+        # gradients of csm_train_step are views into one flat buffer (training.py): one collective, no copies
+        # (the few padding elements between the views are reduced along; nothing reads them)
+        dist.all_reduce(flat, op=dist.ReduceOp.SUM, group=group)
+        flat.div_(world)
+        return 1
     buckets, cur, cur_bytes = [], [], 0
     for g in grads:
         nbytes = g.numel() * g.element_size()

@@ -201,7 +201,17 @@ def training_forward(model, input_ids: torch.Tensor, attention_mask: Optional[to
             eng.close()
         eng = TrainEngine(cfg, dev, B * S, max(n_frames_cap, 1), S)
         model._train_engine = eng
-    grads = {k: torch.empty_like(p) for k, p in zip(names, plist)} if want else None
+    grads = None
+    if want:
+        # one flat bf16 buffer, the gradient tensors are views into it: data-parallel training all-reduces the buffer in
+        # ONE NCCL call without packing / unpacking copies (dist.allreduce_gradients)
+        sizes = [p.numel() for p in plist]
+        flat = torch.empty(sum(-(-n // 8) * 8 for n in sizes), dtype=torch.bfloat16, device=dev)   # 16-byte aligned views
+        grads, off = {}, 0
+        for k, p, n in zip(names, plist, sizes):
+            grads[k] = flat[off:off + n].view(p.shape)
+            off += -(-n // 8) * 8
+        model._grad_flat = flat
     losses, n_frames, last_h, c0 = eng.step({k: p.data for k, p in zip(names, plist)}, grads, ids, mask, lab)
     vals = torch.tensor(losses, dtype=torch.float32, device=dev)
     loss = vals[0]

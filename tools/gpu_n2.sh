@@ -10,3 +10,10 @@ j=json.loads(open('gpurun_out/bench_n2.json').read().strip().splitlines()[-1])
 print('N=2 value', j['value'], 'e2e', j['e2e']['value'], 'frac', j['roofline']['frac'], 'verified', (j['verified'] or {}).get('ok'))
 for p in j['config']['points']: print(' batch/gpu', p['batch_per_gpu'], 'global', p['global_batch'], round(p['value'],1), 'frames/s', round(p['decode_ms_per_frame'],3), 'ms/frame')
 PY
+python - <<'PY'
+import json
+j=json.loads(open('gpurun_out/bench_n2.json').read().strip().splitlines()[-1])
+print('training point:', j['config'].get('training'))
+PY
+timeout 600 python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 --master-port 29613 \
+   tools/train_bench.py --seq 4096 --batch 1 --steps 5 --warmup 2 2>&1 | tail -1 | tee gpurun_out/train_bench_n2.json
