@@ -1,0 +1,336 @@
+// Causal GQA flash attention forward on the 5th-generation tensor cores (tcgen05 / TMEM / TMA), head dim 64.
+//
+// Replaces the mma.sync forward of the training step (csm_train_kernels.cuh flash_fwd_kernel<64>) for whole sequences of
+// qkv rows [rows, W] = rotated q heads | rotated k heads | v heads (hf sdpa_attention_forward, integrations/
+// sdpa_attention.py:40-104, as LlamaAttention.forward calls it, modeling_llama.py:251-289).
+//
+// One CTA = 128 query rows of one head; key blocks of 128.  192 threads:
+//   warp 0      TMA producer: the Q tile once, then K and V blocks into a 2-stage ring (boxes of the qkv matrix itself:
+//               K as a K-major [128 keys x 64] tile, V as two MN-major [64 keys x 64 dims] boxes)
+//   warp 1      MMA issuer (one lane): S = Q K^T (M 128, N 128, K 64) into one of two TMEM accumulators, and, once the
+//               softmax warps have written P, O_blk = P V (M 128, N 64, K 128: P K-major from shared memory, V MN-major);
+//               S of block j+1 is issued before P V of block j, so the tensor core works during the softmax
+//   warps 2..5  softmax, one thread per query row (= TMEM lane): two passes over the S row in TMEM (row max, then
+//               exp2 / row sum / bf16 P written to shared memory in the 128-byte-swizzle layout the MMA reads), then
+//               O = O * corr + O_blk in registers (fp32); at the end O / l -> bf16 rows and the log-sum-exp
+// Masking: causal inside the diagonal block; keys of padded frames (valid[] == 0) everywhere.
+#include <cuda.h>
+
+#include "csm_common.cuh"
+
+namespace {
+
+constexpr int BQ = 128, BKV = 128, HD = 64;
+constexpr int Q_BYTES = BQ * HD * 2, K_BYTES = BKV * HD * 2, V_BYTES = BKV * HD * 2, P_BYTES = BQ * BKV * 2;
+constexpr int FT_THREADS = 192;
+constexpr int FT_SMEM = Q_BYTES + 2 * (K_BYTES + V_BYTES) + P_BYTES + 1024 /* alignment */ + 512 /* barriers, flags */;
+
+__device__ __forceinline__ void ft_tma_load(void* dst, const CUtensorMap* map, uint64_t* bar, int c0, int c1) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];" ::"r"(
+          smem_u32(dst)),
+      "l"(map), "r"(smem_u32(bar)), "r"(c0), "r"(c1)
+      : "memory");
+}
+__device__ __forceinline__ uint64_t ft_desc_k128(uint32_t saddr) {   // K-major, 128-byte rows, 8-row groups 1024 B apart
+  uint64_t d = 0;
+  d |= (uint64_t)((saddr & 0x3ffffu) >> 4);
+  d |= (uint64_t)1 << 16;
+  d |= (uint64_t)(1024 >> 4) << 32;
+  d |= (uint64_t)1 << 46;
+  d |= (uint64_t)2 << 61;
+  return d;
+}
+__device__ __forceinline__ uint64_t ft_desc_mn128(uint32_t saddr) {  // MN-major: [64 k][64 mn] boxes, see csm_gemm.cu
+  uint64_t d = 0;
+  d |= (uint64_t)((saddr & 0x3ffffu) >> 4);
+  d |= (uint64_t)(8192 >> 4) << 16;
+  d |= (uint64_t)(1024 >> 4) << 32;
+  d |= (uint64_t)1 << 46;
+  d |= (uint64_t)2 << 61;
+  return d;
+}
+__device__ __forceinline__ uint32_t ft_idesc(int m, int n, bool b_mn) {
+  return (1u << 4) | (1u << 7) | (1u << 10) | (b_mn ? 1u << 16 : 0u) | ((uint32_t)(n >> 3) << 17) | ((uint32_t)(m >> 4) << 24);
+}
+__device__ __forceinline__ void ft_umma(uint32_t tmem_d, uint64_t da, uint64_t db, uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}" ::"r"(tmem_d),
+      "l"(da), "l"(db), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+__device__ __forceinline__ void ft_commit(uint64_t* bar) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void ft_ld32(uint32_t taddr, uint32_t (&r)[32]) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+      "{%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15,%16,%17,%18,%19,%20,%21,%22,%23,%24,%25,%26,%27,%28,%29,%30,%31}, [%32];"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]), "=r"(r[9]),
+        "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]), "=r"(r[16]), "=r"(r[17]), "=r"(r[18]),
+        "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]), "=r"(r[24]), "=r"(r[25]), "=r"(r[26]), "=r"(r[27]),
+        "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+      : "r"(taddr));
+}
+__device__ __forceinline__ void ft_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
+__device__ __forceinline__ void ft_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void ft_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+
+struct FlashTcParams {
+  int S, heads, kv, nseq;
+  float scale;
+  const unsigned char* valid;   // [nseq * S] or null
+  bf16* out;                    // [nseq * S, heads * 64]
+  float* lse;                   // [nseq * S, heads] or null
+};
+
+__global__ void __launch_bounds__(FT_THREADS, 1)
+csm_flash_tc_kernel(const __grid_constant__ CUtensorMap map_qk, const __grid_constant__ CUtensorMap map_v, const FlashTcParams p) {
+  extern __shared__ unsigned char ft_raw[];
+  unsigned char* smem = reinterpret_cast<unsigned char*>(((uintptr_t)ft_raw + 1023) & ~(uintptr_t)1023);
+  unsigned char* sQ = smem;
+  unsigned char* sK = sQ + Q_BYTES;                 // [2][K_BYTES]
+  unsigned char* sV = sK + 2 * K_BYTES;             // [2][V_BYTES]
+  unsigned char* sP = sV + 2 * V_BYTES;             // two K-halves of [128 x 64]
+  uint64_t* bars = reinterpret_cast<uint64_t*>(sP + P_BYTES);
+  uint64_t* q_full = bars;            // 1
+  uint64_t* kv_full = bars + 1;       // 2
+  uint64_t* kv_empty = bars + 3;      // 2
+  uint64_t* s_full = bars + 5;        // 2
+  uint64_t* s_empty = bars + 7;       // 2
+  uint64_t* p_full = bars + 9;
+  uint64_t* p_empty = bars + 10;
+  uint64_t* o_full = bars + 11;
+  uint64_t* o_empty = bars + 12;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 13);
+  uint32_t* sVm = reinterpret_cast<uint32_t*>(bars + 14);            // [2][4] visibility masks of a key block (valid != null)
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int qt = (int)gridDim.x - 1 - (int)blockIdx.x, head = blockIdx.y, bl = blockIdx.z;   // heaviest tiles first
+  const int kvh = head / (p.heads / p.kv);
+  const int nq = p.heads * HD, nkv = p.kv * HD;
+  const int row0 = bl * p.S;                     // first row of this sequence in the qkv matrix
+  const int q0 = qt * BQ;
+  const int nblk = qt + 1;                       // causal: key blocks 0 .. qt
+
+  if (threadIdx.x == 0) {
+    mbar_init(q_full, 1);
+    for (int i = 0; i < 2; ++i) { mbar_init(&kv_full[i], 1); mbar_init(&kv_empty[i], 1); mbar_init(&s_full[i], 1); mbar_init(&s_empty[i], 4); }
+    mbar_init(p_full, 4);
+    mbar_init(p_empty, 1);
+    mbar_init(o_full, 1);
+    mbar_init(o_empty, 4);
+    mbar_fence_init();
+    asm volatile("prefetch.tensormap [%0];" ::"l"(&map_qk) : "memory");
+    asm volatile("prefetch.tensormap [%0];" ::"l"(&map_v) : "memory");
+  }
+  if (warp == 0) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(512) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  ft_fence_before();
+  __syncthreads();
+  ft_fence_after();
+  const uint32_t tmem = *tmem_slot;
+  const uint32_t tS0 = tmem, tO = tmem + 256;
+
+  if (warp == 0) {
+    if (lane == 0) {
+      mbar_expect_tx(q_full, Q_BYTES);
+      ft_tma_load(sQ, &map_qk, q_full, head * HD, row0 + q0);
+      for (int j = 0; j < nblk; ++j) {
+        const int st = j & 1;
+        mbar_wait(&kv_empty[st], ((j >> 1) & 1) ^ 1);
+        mbar_expect_tx(&kv_full[st], K_BYTES + V_BYTES);
+        ft_tma_load(sK + st * K_BYTES, &map_qk, &kv_full[st], nq + kvh * HD, row0 + j * BKV);
+        ft_tma_load(sV + st * V_BYTES, &map_v, &kv_full[st], nq + nkv + kvh * HD, row0 + j * BKV);
+        ft_tma_load(sV + st * V_BYTES + 8192, &map_v, &kv_full[st], nq + nkv + kvh * HD, row0 + j * BKV + 64);
+      }
+    }
+  } else if (warp == 1) {
+    if (lane == 0) {
+      const uint32_t idS = ft_idesc(BQ, BKV, false), idO = ft_idesc(BQ, HD, true);
+      const uint32_t aQ = smem_u32(sQ), aP = smem_u32(sP);
+      mbar_wait(q_full, 0);
+      auto issue_s = [&](int j) {
+        const int st = j & 1;
+        mbar_wait(&kv_full[st], (j >> 1) & 1);
+        mbar_wait(&s_empty[st], ((j >> 1) & 1) ^ 1);
+        ft_fence_after();
+        const uint32_t aK = smem_u32(sK + st * K_BYTES);
+#pragma unroll
+        for (int k = 0; k < HD / 16; ++k)
+          ft_umma(tS0 + st * BKV, ft_desc_k128(aQ + k * 32), ft_desc_k128(aK + k * 32), idS, k != 0 ? 1u : 0u);
+        ft_commit(&s_full[st]);
+      };
+      issue_s(0);
+      for (int j = 0; j < nblk; ++j) {
+        if (j + 1 < nblk) issue_s(j + 1);
+        const int st = j & 1;
+        mbar_wait(p_full, j & 1);
+        mbar_wait(o_empty, (j & 1) ^ 1);
+        ft_fence_after();
+        const uint32_t aV = smem_u32(sV + st * V_BYTES);
+#pragma unroll
+        for (int k = 0; k < BKV / 16; ++k)     // 16 keys per MMA: P column block (k / 4 = 64-key half), V k-rows 16k..
+          ft_umma(tO, ft_desc_k128(aP + (k >> 2) * (BQ * 128) + (k & 3) * 32), ft_desc_mn128(aV + k * 2048), idO, k != 0 ? 1u : 0u);
+        ft_commit(o_full);
+        ft_commit(&kv_empty[st]);
+        ft_commit(p_empty);
+      }
+    }
+  } else {
+    const int qd = warp & 3;                      // TMEM lanes 32 qd .. 32 qd + 31
+    const int r = qd * 32 + lane;                 // row of the tile = query q0 + r
+    const int qrow = q0 + r;
+    const uint32_t lane_base = (uint32_t)(qd * 32) << 16;
+    const float sl2 = p.scale * 1.4426950408889634f;
+    float o[HD];
+#pragma unroll
+    for (int i = 0; i < HD; ++i) o[i] = 0.f;
+    float m = -INFINITY, l = 0.f;
+    const int st_tid = threadIdx.x - 64;          // 0..127 among the softmax threads: key st_tid of a block
+    const int qd_w = (threadIdx.x - 64) >> 5;      // which 32-key chunk this warp's ballot describes
+    for (int j = 0; j < nblk; ++j) {
+      const int st = j & 1;
+      const bool diag = j == qt;
+      // visibility of the block's 128 keys as four 32-bit masks: padding (valid[] == 0; one ballot per softmax warp,
+      // exchanged through shared memory) and the causal limit of this thread's row (only the diagonal block cuts)
+      uint32_t vm[4] = {0xffffffffu, 0xffffffffu, 0xffffffffu, 0xffffffffu};
+      if (p.valid != nullptr) {
+        const int key = j * BKV + st_tid;
+        const bool ok = key < p.S && p.valid[(size_t)row0 + key] != 0;
+        const uint32_t b = __ballot_sync(0xffffffffu, ok);
+        if (lane == 0) sVm[st * 4 + qd_w] = b;
+        asm volatile("bar.sync 1, 128;" ::: "memory");
+#pragma unroll
+        for (int c = 0; c < 4; ++c) vm[c] = sVm[st * 4 + c];
+      }
+      if (diag) {
+#pragma unroll
+        for (int c = 0; c < 4; ++c) {
+          const int nvis = qrow - (j * BKV + c * 32) + 1;      // keys of the chunk at or before the query
+          vm[c] &= nvis >= 32 ? 0xffffffffu : (nvis <= 0 ? 0u : ((1u << nvis) - 1u));
+        }
+      }
+      mbar_wait(&s_full[st], (j >> 1) & 1);
+      ft_fence_after();
+      const uint32_t tS = tS0 + st * BKV + lane_base;
+      // pass 1: row maximum over the visible keys
+      float mx = m;
+#pragma unroll 1
+      for (int c = 0; c < 4; ++c) {
+        uint32_t v[32];
+        ft_ld32(tS + c * 32, v);
+        ft_ld_wait();
+        const uint32_t w = c == 0 ? vm[0] : (c == 1 ? vm[1] : (c == 2 ? vm[2] : vm[3]));
+        if (w == 0xffffffffu) {
+#pragma unroll
+          for (int i = 0; i < 32; ++i) mx = fmaxf(mx, __uint_as_float(v[i]));
+        } else {
+#pragma unroll
+          for (int i = 0; i < 32; ++i) mx = fmaxf(mx, ((w >> i) & 1u) ? __uint_as_float(v[i]) : -INFINITY);
+        }
+      }
+      const float corr = (mx == -INFINITY) ? 1.f : exp2f((m - mx) * sl2);   // (m = -inf: exp2(-inf) = 0)
+      const float ms = (mx == -INFINITY) ? 0.f : mx * sl2;
+      m = mx;
+      mbar_wait(p_empty, (j & 1) ^ 1);             // P V of the previous block has read the P tile
+      // pass 2: p = exp2(scale' s - scale' max), row sum, bf16 P -> shared memory (128-byte swizzle, two 64-key halves)
+      float sum = 0.f;
+#pragma unroll 1
+      for (int c = 0; c < 4; ++c) {
+        uint32_t v[32];
+        ft_ld32(tS + c * 32, v);
+        ft_ld_wait();
+        const uint32_t w = c == 0 ? vm[0] : (c == 1 ? vm[1] : (c == 2 ? vm[2] : vm[3]));
+        uint32_t pk[16];
+        if (w == 0xffffffffu) {
+#pragma unroll
+          for (int i = 0; i < 32; i += 2) {
+            const float p0 = exp2f(__uint_as_float(v[i]) * sl2 - ms), p1 = exp2f(__uint_as_float(v[i + 1]) * sl2 - ms);
+            sum += p0 + p1;
+            pk[i >> 1] = pack_bf16(p0, p1);
+          }
+        } else {
+#pragma unroll
+          for (int i = 0; i < 32; i += 2) {
+            const float p0 = ((w >> i) & 1u) ? exp2f(__uint_as_float(v[i]) * sl2 - ms) : 0.f;
+            const float p1 = ((w >> (i + 1)) & 1u) ? exp2f(__uint_as_float(v[i + 1]) * sl2 - ms) : 0.f;
+            sum += p0 + p1;
+            pk[i >> 1] = pack_bf16(p0, p1);
+          }
+        }
+        unsigned char* base = sP + (c >> 1) * (BQ * 128) + (r >> 3) * 1024 + (r & 7) * 128;
+#pragma unroll
+        for (int q4 = 0; q4 < 4; ++q4) {
+          const int chunk = (c & 1) * 4 + q4;       // 16-byte chunk of the 128-byte row
+          *reinterpret_cast<uint4*>(base + ((chunk ^ (r & 7)) << 4)) = make_uint4(pk[4 * q4], pk[4 * q4 + 1], pk[4 * q4 + 2], pk[4 * q4 + 3]);
+        }
+      }
+      l = l * corr + sum;
+      asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // P written here is read by the tensor core (async proxy)
+      ft_fence_before();
+      __syncwarp();
+      if (lane == 0) {
+        mbar_arrive(p_full);
+        mbar_arrive(&s_empty[st]);                 // this warp's lanes of S are free for block j + 2
+      }
+      // O = O * corr + P V
+      mbar_wait(o_full, j & 1);
+      ft_fence_after();
+#pragma unroll
+      for (int c = 0; c < 2; ++c) {
+        uint32_t v[32];
+        ft_ld32(tO + lane_base + c * 32, v);
+        ft_ld_wait();
+#pragma unroll
+        for (int i = 0; i < 32; ++i) o[c * 32 + i] = o[c * 32 + i] * corr + __uint_as_float(v[i]);
+      }
+      ft_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(o_empty);
+    }
+    if (qrow < p.S) {
+      const float inv = l > 0.f ? 1.f / l : 0.f;    // a row that saw no key (padded frame): zero output
+      uint4* dst = reinterpret_cast<uint4*>(p.out + ((size_t)row0 + qrow) * nq + head * HD);
+#pragma unroll
+      for (int q8 = 0; q8 < 8; ++q8)
+        dst[q8] = make_uint4(pack_bf16(o[8 * q8] * inv, o[8 * q8 + 1] * inv), pack_bf16(o[8 * q8 + 2] * inv, o[8 * q8 + 3] * inv),
+                             pack_bf16(o[8 * q8 + 4] * inv, o[8 * q8 + 5] * inv), pack_bf16(o[8 * q8 + 6] * inv, o[8 * q8 + 7] * inv));
+      if (p.lse) p.lse[((size_t)row0 + qrow) * p.heads + head] = l > 0.f ? m * p.scale + logf(l) : 0.f;
+    }
+  }
+  ft_fence_before();
+  __syncthreads();
+  if (warp == 0) {
+    ft_fence_after();
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "r"(512) : "memory");
+  }
+}
+
+}  // namespace
+
+extern "C" {
+int csm_tmap_2d(void* out, const void* base, long long rows, int K, long long pitch, int box_rows);
+int csm_tmap_2d_mn(void* out, const void* base, long long k_rows, long long mn, long long pitch);
+
+// qkv [nseq * S, W] rows (W = (heads + 2 kv) * 64), out [nseq * S, heads * 64], lse [nseq * S, heads] (may be null).
+// Returns cudaErrorInvalidValue for shapes this kernel does not cover (the caller falls back to nothing: it is an error).
+cudaError_t csm_flash_tc_launch(const bf16* qkv, int S, int nseq, int heads, int kv, float scale, const unsigned char* valid,
+                                bf16* out, float* lse, cudaStream_t st) {
+  const int W = (heads + 2 * kv) * HD;
+  const long long rows = (long long)nseq * S;
+  CUtensorMap mqk, mv;
+  if (csm_tmap_2d(&mqk, qkv, rows, W, W, BQ) || csm_tmap_2d_mn(&mv, qkv, rows, W, W)) return cudaErrorInvalidValue;
+  cudaError_t e = cudaFuncSetAttribute((const void*)csm_flash_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, FT_SMEM);
+  if (e != cudaSuccess) return e;
+  FlashTcParams p;
+  p.S = S; p.heads = heads; p.kv = kv; p.nseq = nseq; p.scale = scale; p.valid = valid; p.out = out; p.lse = lse;
+  dim3 grid((S + BQ - 1) / BQ, heads, nseq);
+  csm_flash_tc_kernel<<<grid, FT_THREADS, FT_SMEM, st>>>(mqk, mv, p);
+  return cudaGetLastError();
+}
+}  // extern "C"

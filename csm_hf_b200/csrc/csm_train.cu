@@ -39,6 +39,8 @@ cudaError_t csm_embed_sum_launch(const long long* ids, const int* mask, int defa
                                  const bf16* text_emb, int V, int H, bf16* out, int rows, cudaStream_t st);
 cudaError_t csm_rmsnorm_rows_launch(const bf16* x, const bf16* w, float eps, int H, bf16* y, int rows, cudaStream_t st);
 cudaError_t csm_frame_valid_launch(const int* mask, int rows, unsigned char* valid, int* any_pad, cudaStream_t st);
+cudaError_t csm_flash_tc_launch(const bf16* qkv, int S, int nseq, int heads, int kv, float scale, const unsigned char* valid,
+                                bf16* out, float* lse, cudaStream_t st);
 }
 
 namespace {
@@ -85,6 +87,7 @@ struct CsmTrain {
   float *row_loss = nullptr, *losses = nullptr;        // device [3]
   float *audio_acc = nullptr, *text_acc = nullptr;     // fp32 gradients of the embedding tables
   int launches = 0;
+  bool flash_tc = true;      // head-dim-64 attention forward on tcgen05
   bool mn_operands = true;   // gradients read W, dY and X as MN-major tcgen05 operands (CSM_TRAIN_TRANSPOSE=1: transposed copies)
   std::map<std::string, std::pair<const void*, size_t>> dbg;   // named intermediates of the last step (tests)
 };
@@ -257,8 +260,14 @@ int stack_forward(CsmTrain* t, TStack& s, int S, int nseq, const unsigned char* 
     rope_rows_kernel<false><<<nblocks((long long)R * (s.heads + s.kv) * (s.hd / 2)), 256, 0, st>>>(
         y.qkv, s.W, R, S, s.heads + s.kv, s.hd, s.cos_t, s.sin_t);
     TCK(cudaGetLastError());
-    if (s.hd == 64) TRY(flash_fwd<64>(t, s, y.qkv, S, nseq, valid, y.attn, y.lse, st));
-    else TRY(flash_fwd<128>(t, s, y.qkv, S, nseq, valid, y.attn, y.lse, st));
+    if (s.hd == 64 && t->flash_tc) {   // tcgen05 forward (csm_flash_tc.cu); CSM_FLASH_MMA=1: the mma.sync kernel
+      TCK(csm_flash_tc_launch(y.qkv, S, nseq, s.heads, s.kv, s.scale, valid, y.attn, y.lse, st));
+      t->launches += 1;
+    } else if (s.hd == 64) {
+      TRY(flash_fwd<64>(t, s, y.qkv, S, nseq, valid, y.attn, y.lse, st));
+    } else {
+      TRY(flash_fwd<128>(t, s, y.qkv, S, nseq, valid, y.attn, y.lse, st));
+    }
     TRY(copy_rows(t, y.h_mid, y.h_in, (size_t)R * s.H, st));
     TRY(gemm(t, y.attn, s.nq, R, s.nq, y.o, s.nq, s.H, y.h_mid, s.H, EPI_RESID, st));
     TCK(csm_rmsnorm_rows_launch(y.h_mid, y.ln2, s.eps, s.H, y.hn2, R, st));
@@ -431,6 +440,7 @@ int csm_train_create(const CsmShapes* sh, int max_tokens, int max_frames, CsmTra
   t->V = sh->audio_vocab; t->Vp = rup(sh->audio_vocab, 64); t->text_vocab = sh->text_vocab;
   t->max_tokens = max_tokens; t->max_frames = max_frames;
   t->mn_operands = getenv("CSM_TRAIN_TRANSPOSE") == nullptr;
+  t->flash_tc = getenv("CSM_FLASH_MMA") == nullptr;
   if (sh->backbone.n_pos < 1 || sh->decoder.n_pos < 33) return tfail(t, CSM_EINVAL, "rope tables: the decoder needs 33 positions");
   const int Rd = max_frames * 33;
   TRY(setup_stack(t, t->bb, sh->backbone, max_tokens));
