@@ -22,8 +22,9 @@ namespace {
 
 constexpr int BQ = 128, BKV = 128, HD = 64;
 constexpr int Q_BYTES = BQ * HD * 2, K_BYTES = BKV * HD * 2, V_BYTES = BKV * HD * 2, P_BYTES = BQ * BKV * 2;
-constexpr int FT_THREADS = 192;
-constexpr int FT_SMEM = Q_BYTES + 2 * (K_BYTES + V_BYTES) + P_BYTES + 1024 /* alignment */ + 512 /* barriers, flags */;
+constexpr int FT_THREADS = 320;   // TMA warp, MMA warp, 8 softmax warps
+constexpr int FT_SMEM = Q_BYTES + 2 * (K_BYTES + V_BYTES) + P_BYTES + 1024 /* alignment */ + 256 /* barriers, masks */ +
+                        4 * 128 * 4 /* row maxima of the two halves, double-buffered */;
 
 __device__ __forceinline__ void ft_tma_load(void* dst, const CUtensorMap* map, uint64_t* bar, int c0, int c1) {
   asm volatile(
@@ -106,6 +107,7 @@ csm_flash_tc_kernel(const __grid_constant__ CUtensorMap map_qk, const __grid_con
   uint64_t* o_empty = bars + 12;
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 13);
   uint32_t* sVm = reinterpret_cast<uint32_t*>(bars + 14);            // [2][4] visibility masks of a key block (valid != null)
+  float* sMax = reinterpret_cast<float*>(bars + 32);                 // [2 stages][2 halves][128 rows]
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int qt = (int)gridDim.x - 1 - (int)blockIdx.x, head = blockIdx.y, bl = blockIdx.z;   // heaviest tiles first
@@ -117,11 +119,11 @@ csm_flash_tc_kernel(const __grid_constant__ CUtensorMap map_qk, const __grid_con
 
   if (threadIdx.x == 0) {
     mbar_init(q_full, 1);
-    for (int i = 0; i < 2; ++i) { mbar_init(&kv_full[i], 1); mbar_init(&kv_empty[i], 1); mbar_init(&s_full[i], 1); mbar_init(&s_empty[i], 4); }
-    mbar_init(p_full, 4);
+    for (int i = 0; i < 2; ++i) { mbar_init(&kv_full[i], 1); mbar_init(&kv_empty[i], 1); mbar_init(&s_full[i], 1); mbar_init(&s_empty[i], 8); }
+    mbar_init(p_full, 8);
     mbar_init(p_empty, 1);
     mbar_init(o_full, 1);
-    mbar_init(o_empty, 4);
+    mbar_init(o_empty, 8);
     mbar_fence_init();
     asm volatile("prefetch.tensormap [%0];" ::"l"(&map_qk) : "memory");
     asm volatile("prefetch.tensormap [%0];" ::"l"(&map_v) : "memory");
@@ -182,50 +184,53 @@ csm_flash_tc_kernel(const __grid_constant__ CUtensorMap map_qk, const __grid_con
       }
     }
   } else {
+    // Two threads per query row: warps 2..5 own keys 0..63 of every block and output dims 0..31, warps 6..9 keys 64..127
+    // and dims 32..63 (a warp may touch TMEM lanes 32 (warp % 4) .. +31 only; both halves of a row share those lanes).
+    // The halves exchange their row maximum through shared memory once per block; the row sums are combined at the end.
     const int qd = warp & 3;                      // TMEM lanes 32 qd .. 32 qd + 31
+    const int hf = (warp - 2) >> 2;               // which half of the keys / output dims
     const int r = qd * 32 + lane;                 // row of the tile = query q0 + r
     const int qrow = q0 + r;
     const uint32_t lane_base = (uint32_t)(qd * 32) << 16;
     const float sl2 = p.scale * 1.4426950408889634f;
-    float o[HD];
+    float o[32];
 #pragma unroll
-    for (int i = 0; i < HD; ++i) o[i] = 0.f;
-    float m = -INFINITY, l = 0.f;
-    const int st_tid = threadIdx.x - 64;          // 0..127 among the softmax threads: key st_tid of a block
-    const int qd_w = (threadIdx.x - 64) >> 5;      // which 32-key chunk this warp's ballot describes
+    for (int i = 0; i < 32; ++i) o[i] = 0.f;
+    float m = -INFINITY, l = 0.f, corr_prev = 1.f;
+    const int st_tid = threadIdx.x - 64;          // 0..255 among the softmax threads
     for (int j = 0; j < nblk; ++j) {
       const int st = j & 1;
       const bool diag = j == qt;
-      // visibility of the block's 128 keys as four 32-bit masks: padding (valid[] == 0; one ballot per softmax warp,
-      // exchanged through shared memory) and the causal limit of this thread's row (only the diagonal block cuts)
-      uint32_t vm[4] = {0xffffffffu, 0xffffffffu, 0xffffffffu, 0xffffffffu};
+      // visibility of this thread's 64 keys as two 32-bit masks: padding (valid[] == 0; ballots of the first four
+      // softmax warps, one key each, exchanged through shared memory) and the causal limit of the row (diagonal block)
+      uint32_t vm0 = 0xffffffffu, vm1 = 0xffffffffu;
       if (p.valid != nullptr) {
-        const int key = j * BKV + st_tid;
-        const bool ok = key < p.S && p.valid[(size_t)row0 + key] != 0;
-        const uint32_t b = __ballot_sync(0xffffffffu, ok);
-        if (lane == 0) sVm[st * 4 + qd_w] = b;
-        asm volatile("bar.sync 1, 128;" ::: "memory");
-#pragma unroll
-        for (int c = 0; c < 4; ++c) vm[c] = sVm[st * 4 + c];
+        if (st_tid < 128) {
+          const int key = j * BKV + st_tid;
+          const bool ok = key < p.S && p.valid[(size_t)row0 + key] != 0;
+          const uint32_t bl_ = __ballot_sync(0xffffffffu, ok);
+          if (lane == 0) sVm[st * 4 + (st_tid >> 5)] = bl_;
+        }
+        asm volatile("bar.sync 1, 256;" ::: "memory");
+        vm0 = sVm[st * 4 + 2 * hf];
+        vm1 = sVm[st * 4 + 2 * hf + 1];
       }
       if (diag) {
-#pragma unroll
-        for (int c = 0; c < 4; ++c) {
-          const int nvis = qrow - (j * BKV + c * 32) + 1;      // keys of the chunk at or before the query
-          vm[c] &= nvis >= 32 ? 0xffffffffu : (nvis <= 0 ? 0u : ((1u << nvis) - 1u));
-        }
+        const int n0 = qrow - (j * BKV + hf * 64) + 1, n1 = n0 - 32;      // keys of each chunk at or before the query
+        vm0 &= n0 >= 32 ? 0xffffffffu : (n0 <= 0 ? 0u : ((1u << n0) - 1u));
+        vm1 &= n1 >= 32 ? 0xffffffffu : (n1 <= 0 ? 0u : ((1u << n1) - 1u));
       }
       mbar_wait(&s_full[st], (j >> 1) & 1);
       ft_fence_after();
-      const uint32_t tS = tS0 + st * BKV + lane_base;
-      // pass 1: row maximum over the visible keys
-      float mx = m;
+      const uint32_t tS = tS0 + st * BKV + lane_base + hf * 64;
+      // pass 1: maximum over this thread's visible keys, then over the row (the other half's through shared memory)
+      float mx = -INFINITY;
 #pragma unroll 1
-      for (int c = 0; c < 4; ++c) {
+      for (int c = 0; c < 2; ++c) {
         uint32_t v[32];
         ft_ld32(tS + c * 32, v);
         ft_ld_wait();
-        const uint32_t w = c == 0 ? vm[0] : (c == 1 ? vm[1] : (c == 2 ? vm[2] : vm[3]));
+        const uint32_t w = c == 0 ? vm0 : vm1;
         if (w == 0xffffffffu) {
 #pragma unroll
           for (int i = 0; i < 32; ++i) mx = fmaxf(mx, __uint_as_float(v[i]));
@@ -234,18 +239,21 @@ csm_flash_tc_kernel(const __grid_constant__ CUtensorMap map_qk, const __grid_con
           for (int i = 0; i < 32; ++i) mx = fmaxf(mx, ((w >> i) & 1u) ? __uint_as_float(v[i]) : -INFINITY);
         }
       }
+      sMax[(st * 2 + hf) * 128 + r] = mx;
+      asm volatile("bar.sync 2, 256;" ::: "memory");
+      mx = fmaxf(fmaxf(mx, sMax[(st * 2 + (hf ^ 1)) * 128 + r]), m);
       const float corr = (mx == -INFINITY) ? 1.f : exp2f((m - mx) * sl2);   // (m = -inf: exp2(-inf) = 0)
       const float ms = (mx == -INFINITY) ? 0.f : mx * sl2;
       m = mx;
       mbar_wait(p_empty, (j & 1) ^ 1);             // P V of the previous block has read the P tile
-      // pass 2: p = exp2(scale' s - scale' max), row sum, bf16 P -> shared memory (128-byte swizzle, two 64-key halves)
+      // pass 2: p = exp2(scale' s - scale' max), partial row sum, bf16 P -> this half's [128 x 64] tile (128-byte swizzle)
       float sum = 0.f;
 #pragma unroll 1
-      for (int c = 0; c < 4; ++c) {
+      for (int c = 0; c < 2; ++c) {
         uint32_t v[32];
         ft_ld32(tS + c * 32, v);
         ft_ld_wait();
-        const uint32_t w = c == 0 ? vm[0] : (c == 1 ? vm[1] : (c == 2 ? vm[2] : vm[3]));
+        const uint32_t w = c == 0 ? vm0 : vm1;
         uint32_t pk[16];
         if (w == 0xffffffffu) {
 #pragma unroll
@@ -263,10 +271,10 @@ csm_flash_tc_kernel(const __grid_constant__ CUtensorMap map_qk, const __grid_con
             pk[i >> 1] = pack_bf16(p0, p1);
           }
         }
-        unsigned char* base = sP + (c >> 1) * (BQ * 128) + (r >> 3) * 1024 + (r & 7) * 128;
+        unsigned char* base = sP + hf * (BQ * 128) + (r >> 3) * 1024 + (r & 7) * 128;
 #pragma unroll
         for (int q4 = 0; q4 < 4; ++q4) {
-          const int chunk = (c & 1) * 4 + q4;       // 16-byte chunk of the 128-byte row
+          const int chunk = c * 4 + q4;             // 16-byte chunk of the 128-byte row
           *reinterpret_cast<uint4*>(base + ((chunk ^ (r & 7)) << 4)) = make_uint4(pk[4 * q4], pk[4 * q4 + 1], pk[4 * q4 + 2], pk[4 * q4 + 3]);
         }
       }
@@ -276,31 +284,46 @@ csm_flash_tc_kernel(const __grid_constant__ CUtensorMap map_qk, const __grid_con
       __syncwarp();
       if (lane == 0) {
         mbar_arrive(p_full);
-        mbar_arrive(&s_empty[st]);                 // this warp's lanes of S are free for block j + 2
+        mbar_arrive(&s_empty[st]);                 // this warp's part of S is free for block j + 2
       }
-      // O = O * corr + P V
-      mbar_wait(o_full, j & 1);
-      ft_fence_after();
-#pragma unroll
-      for (int c = 0; c < 2; ++c) {
+      // O = O * corr + P V of the PREVIOUS block (this thread's 32 output dims): P V of block j runs on the tensor core
+      // while these threads do the softmax of block j + 1, its result is folded in one iteration later
+      if (j > 0) {
+        mbar_wait(o_full, (j - 1) & 1);
+        ft_fence_after();
         uint32_t v[32];
-        ft_ld32(tO + lane_base + c * 32, v);
+        ft_ld32(tO + lane_base + hf * 32, v);
         ft_ld_wait();
 #pragma unroll
-        for (int i = 0; i < 32; ++i) o[c * 32 + i] = o[c * 32 + i] * corr + __uint_as_float(v[i]);
+        for (int i = 0; i < 32; ++i) o[i] = o[i] * corr_prev + __uint_as_float(v[i]);
+        ft_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(o_empty);
       }
-      ft_fence_before();
-      __syncwarp();
-      if (lane == 0) mbar_arrive(o_empty);
+      corr_prev = corr;
     }
+    {
+      mbar_wait(o_full, (nblk - 1) & 1);
+      ft_fence_after();
+      uint32_t v[32];
+      ft_ld32(tO + lane_base + hf * 32, v);
+      ft_ld_wait();
+#pragma unroll
+      for (int i = 0; i < 32; ++i) o[i] = o[i] * corr_prev + __uint_as_float(v[i]);
+      ft_fence_before();
+    }
+    // the row sum = both halves' partial sums (same running maximum on both sides)
+    sMax[hf * 128 + r] = l;
+    asm volatile("bar.sync 2, 256;" ::: "memory");
+    l += sMax[(hf ^ 1) * 128 + r];
     if (qrow < p.S) {
       const float inv = l > 0.f ? 1.f / l : 0.f;    // a row that saw no key (padded frame): zero output
-      uint4* dst = reinterpret_cast<uint4*>(p.out + ((size_t)row0 + qrow) * nq + head * HD);
+      uint4* dst = reinterpret_cast<uint4*>(p.out + ((size_t)row0 + qrow) * nq + head * HD + hf * 32);
 #pragma unroll
-      for (int q8 = 0; q8 < 8; ++q8)
+      for (int q8 = 0; q8 < 4; ++q8)
         dst[q8] = make_uint4(pack_bf16(o[8 * q8] * inv, o[8 * q8 + 1] * inv), pack_bf16(o[8 * q8 + 2] * inv, o[8 * q8 + 3] * inv),
                              pack_bf16(o[8 * q8 + 4] * inv, o[8 * q8 + 5] * inv), pack_bf16(o[8 * q8 + 6] * inv, o[8 * q8 + 7] * inv));
-      if (p.lse) p.lse[((size_t)row0 + qrow) * p.heads + head] = l > 0.f ? m * p.scale + logf(l) : 0.f;
+      if (p.lse && hf == 0) p.lse[((size_t)row0 + qrow) * p.heads + head] = l > 0.f ? m * p.scale + logf(l) : 0.f;
     }
   }
   ft_fence_before();
