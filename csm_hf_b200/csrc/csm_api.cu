@@ -46,6 +46,9 @@ cudaError_t csm_sample_rows_launch(const bf16* logits, int rows, int V, int topk
 cudaError_t csm_untag_rows_launch(const uint32_t* src, long long src_stride, int cols, int rows, bf16* dst, cudaStream_t st);
 cudaError_t csm_i64_to_i32_launch(const long long* src, int* dst, int n, cudaStream_t st);
 cudaError_t csm_i32_to_i64_launch(const int* src, long long* dst, int n, cudaStream_t st);
+cudaError_t csm_flash_tc_prefill_launch(const bf16* qkv, int S, int b0, int nseq, int heads, int kv, const bf16* kc,
+                                        const bf16* vc, int layer, int layers, int Bmax, int Tcap, float scale,
+                                        const unsigned char* valid, bf16* out, cudaStream_t st);
 cudaError_t csm_flash_prefill_launch(const bf16* qkv, int S, int pos0, int b0, int nseq, int heads, int kv,
                                      const bf16* kc, const bf16* vc, int layer, int Bmax, int Tcap, float scale,
                                      const unsigned char* valid, bf16* out, cudaStream_t st);
@@ -75,6 +78,7 @@ struct Stack {
 }  // namespace
 
 struct CsmCtx {
+  bool flash_tc = getenv("CSM_FLASH_MMA") == nullptr;   // prefill attention on tcgen05 (csm_flash_tc.cu)
   int device = 0, sms = 0, G = 0;
   int Bmax = 0, Tcap = 0;
   int V = 0, text_vocab = 0;
@@ -763,8 +767,12 @@ int prefill(CsmCtx* ctx, const long long* ids, const int* mask, int B, int S, cu
       g.S = S; g.pos0 = pos0; g.b0 = b0; g.heads = d.heads; g.kv = d.kv; g.layer = l; g.Bmax = ctx->Bmax; g.Tcap = ctx->Tcap;
       g.kc = ctx->kc_bb; g.vc = ctx->vc_bb; g.cos_t = ctx->bb.cos_t; g.sin_t = ctx->bb.sin_t;
       if ((r = gemm_tc(ctx, ctx->pf_hn, d.H, &L.tm_qkv, g, st))) return r;
-      CK(csm_flash_prefill_launch(ctx->pf_qkv, S, pos0, b0, nseq, d.heads, d.kv, ctx->kc_bb, ctx->vc_bb, l, ctx->Bmax,
-                                  ctx->Tcap, d.scale, valid, ctx->pf_attn, st));
+      if (pos0 == 0 && d.hd == 64 && ctx->flash_tc)   // tcgen05 flash attention (csm_flash_tc.cu); CSM_FLASH_MMA=1: mma.sync
+        CK(csm_flash_tc_prefill_launch(ctx->pf_qkv, S, b0, nseq, d.heads, d.kv, ctx->kc_bb, ctx->vc_bb, l, d.L, ctx->Bmax,
+                                       ctx->Tcap, d.scale, valid, ctx->pf_attn, st));
+      else
+        CK(csm_flash_prefill_launch(ctx->pf_qkv, S, pos0, b0, nseq, d.heads, d.kv, ctx->kc_bb, ctx->vc_bb, l, ctx->Bmax,
+                                    ctx->Tcap, d.scale, valid, ctx->pf_attn, st));
       g.N = d.H; g.K = nq; g.epi = EPI_RESID; g.C = ctx->pf_h; g.ldc = d.H;
       if ((r = gemm_tc(ctx, ctx->pf_attn, nq, &L.tm_o, g, st))) return r;
       CK(csm_rmsnorm_rows_launch(ctx->pf_h, L.ln2, d.eps, d.H, ctx->pf_hn, R, st));

@@ -15,6 +15,7 @@
 //               O = O * corr + O_blk in registers (fp32); at the end O / l -> bf16 rows and the log-sum-exp
 // Masking: causal inside the diagonal block; keys of padded frames (valid[] == 0) everywhere.
 #include <cuda.h>
+#include <string.h>
 
 #include "csm_common.cuh"
 
@@ -79,8 +80,19 @@ __device__ __forceinline__ void ft_ld_wait() { asm volatile("tcgen05.wait::ld.sy
 __device__ __forceinline__ void ft_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void ft_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
 
+__device__ __forceinline__ float ft_ex2(float x) {   // 2^x on the special-function unit (one MUFU.EX2; 2^-inf = 0)
+  float y;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
+
 struct FlashTcParams {
   int S, heads, kv, nseq;
+  // where the K / V rows of (sequence bl, kv head h, position t) live in their matrices:
+  //   row = kv_row_base + bl * kv_row_seq + h * kv_row_head + t,   column = k_col / v_col + h * kv_col_head
+  // training: rows of the qkv matrix itself; prefill: the KV cache [layer][sequence][kv head][Tcap][64]
+  long long kv_row_base;
+  int kv_row_seq, kv_row_head, k_col, v_col, kv_col_head;
   float scale;
   const unsigned char* valid;   // [nseq * S] or null
   bf16* out;                    // [nseq * S, heads * 64]
@@ -88,7 +100,8 @@ struct FlashTcParams {
 };
 
 __global__ void __launch_bounds__(FT_THREADS, 1)
-csm_flash_tc_kernel(const __grid_constant__ CUtensorMap map_qk, const __grid_constant__ CUtensorMap map_v, const FlashTcParams p) {
+csm_flash_tc_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant__ CUtensorMap map_k,
+                    const __grid_constant__ CUtensorMap map_v, const FlashTcParams p) {
   extern __shared__ unsigned char ft_raw[];
   unsigned char* smem = reinterpret_cast<unsigned char*>(((uintptr_t)ft_raw + 1023) & ~(uintptr_t)1023);
   unsigned char* sQ = smem;
@@ -112,7 +125,7 @@ csm_flash_tc_kernel(const __grid_constant__ CUtensorMap map_qk, const __grid_con
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int qt = (int)gridDim.x - 1 - (int)blockIdx.x, head = blockIdx.y, bl = blockIdx.z;   // heaviest tiles first
   const int kvh = head / (p.heads / p.kv);
-  const int nq = p.heads * HD, nkv = p.kv * HD;
+  const int nq = p.heads * HD;
   const int row0 = bl * p.S;                     // first row of this sequence in the qkv matrix
   const int q0 = qt * BQ;
   const int nblk = qt + 1;                       // causal: key blocks 0 .. qt
@@ -125,7 +138,8 @@ csm_flash_tc_kernel(const __grid_constant__ CUtensorMap map_qk, const __grid_con
     mbar_init(o_full, 1);
     mbar_init(o_empty, 8);
     mbar_fence_init();
-    asm volatile("prefetch.tensormap [%0];" ::"l"(&map_qk) : "memory");
+    asm volatile("prefetch.tensormap [%0];" ::"l"(&map_q) : "memory");
+    asm volatile("prefetch.tensormap [%0];" ::"l"(&map_k) : "memory");
     asm volatile("prefetch.tensormap [%0];" ::"l"(&map_v) : "memory");
   }
   if (warp == 0) {
@@ -141,14 +155,16 @@ csm_flash_tc_kernel(const __grid_constant__ CUtensorMap map_qk, const __grid_con
   if (warp == 0) {
     if (lane == 0) {
       mbar_expect_tx(q_full, Q_BYTES);
-      ft_tma_load(sQ, &map_qk, q_full, head * HD, row0 + q0);
+      ft_tma_load(sQ, &map_q, q_full, head * HD, row0 + q0);
+      const int krow = (int)(p.kv_row_base + (long long)bl * p.kv_row_seq + (long long)kvh * p.kv_row_head);
+      const int kcol = p.k_col + kvh * p.kv_col_head, vcol = p.v_col + kvh * p.kv_col_head;
       for (int j = 0; j < nblk; ++j) {
         const int st = j & 1;
         mbar_wait(&kv_empty[st], ((j >> 1) & 1) ^ 1);
         mbar_expect_tx(&kv_full[st], K_BYTES + V_BYTES);
-        ft_tma_load(sK + st * K_BYTES, &map_qk, &kv_full[st], nq + kvh * HD, row0 + j * BKV);
-        ft_tma_load(sV + st * V_BYTES, &map_v, &kv_full[st], nq + nkv + kvh * HD, row0 + j * BKV);
-        ft_tma_load(sV + st * V_BYTES + 8192, &map_v, &kv_full[st], nq + nkv + kvh * HD, row0 + j * BKV + 64);
+        ft_tma_load(sK + st * K_BYTES, &map_k, &kv_full[st], kcol, krow + j * BKV);
+        ft_tma_load(sV + st * V_BYTES, &map_v, &kv_full[st], vcol, krow + j * BKV);
+        ft_tma_load(sV + st * V_BYTES + 8192, &map_v, &kv_full[st], vcol, krow + j * BKV + 64);
       }
     }
   } else if (warp == 1) {
@@ -223,55 +239,59 @@ csm_flash_tc_kernel(const __grid_constant__ CUtensorMap map_qk, const __grid_con
       mbar_wait(&s_full[st], (j >> 1) & 1);
       ft_fence_after();
       const uint32_t tS = tS0 + st * BKV + lane_base + hf * 64;
+      // this thread's 64 scores: both TMEM loads in flight together, kept in registers for both passes
+      uint32_t v0[32], v1[32];
+      ft_ld32(tS, v0);
+      ft_ld32(tS + 32, v1);
+      ft_ld_wait();
       // pass 1: maximum over this thread's visible keys, then over the row (the other half's through shared memory)
       float mx = -INFINITY;
-#pragma unroll 1
-      for (int c = 0; c < 2; ++c) {
-        uint32_t v[32];
-        ft_ld32(tS + c * 32, v);
-        ft_ld_wait();
-        const uint32_t w = c == 0 ? vm0 : vm1;
-        if (w == 0xffffffffu) {
+      if (vm0 == 0xffffffffu) {
 #pragma unroll
-          for (int i = 0; i < 32; ++i) mx = fmaxf(mx, __uint_as_float(v[i]));
-        } else {
+        for (int i = 0; i < 32; ++i) mx = fmaxf(mx, __uint_as_float(v0[i]));
+      } else {
 #pragma unroll
-          for (int i = 0; i < 32; ++i) mx = fmaxf(mx, ((w >> i) & 1u) ? __uint_as_float(v[i]) : -INFINITY);
-        }
+        for (int i = 0; i < 32; ++i) mx = fmaxf(mx, ((vm0 >> i) & 1u) ? __uint_as_float(v0[i]) : -INFINITY);
+      }
+      if (vm1 == 0xffffffffu) {
+#pragma unroll
+        for (int i = 0; i < 32; ++i) mx = fmaxf(mx, __uint_as_float(v1[i]));
+      } else {
+#pragma unroll
+        for (int i = 0; i < 32; ++i) mx = fmaxf(mx, ((vm1 >> i) & 1u) ? __uint_as_float(v1[i]) : -INFINITY);
       }
       sMax[(st * 2 + hf) * 128 + r] = mx;
       asm volatile("bar.sync 2, 256;" ::: "memory");
       mx = fmaxf(fmaxf(mx, sMax[(st * 2 + (hf ^ 1)) * 128 + r]), m);
-      const float corr = (mx == -INFINITY) ? 1.f : exp2f((m - mx) * sl2);   // (m = -inf: exp2(-inf) = 0)
+      const float corr = (mx == -INFINITY) ? 1.f : ft_ex2((m - mx) * sl2);   // (m = -inf: ex2(-inf) = 0)
       const float ms = (mx == -INFINITY) ? 0.f : mx * sl2;
       m = mx;
       mbar_wait(p_empty, (j & 1) ^ 1);             // P V of the previous block has read the P tile
-      // pass 2: p = exp2(scale' s - scale' max), partial row sum, bf16 P -> this half's [128 x 64] tile (128-byte swizzle)
+      // pass 2: p = 2^(scale' s - scale' max), partial row sum, bf16 P -> this half's [128 x 64] tile (128-byte swizzle)
       float sum = 0.f;
-#pragma unroll 1
+      unsigned char* base = sP + hf * (BQ * 128) + (r >> 3) * 1024 + (r & 7) * 128;
+#pragma unroll
       for (int c = 0; c < 2; ++c) {
-        uint32_t v[32];
-        ft_ld32(tS + c * 32, v);
-        ft_ld_wait();
         const uint32_t w = c == 0 ? vm0 : vm1;
         uint32_t pk[16];
         if (w == 0xffffffffu) {
 #pragma unroll
           for (int i = 0; i < 32; i += 2) {
-            const float p0 = exp2f(__uint_as_float(v[i]) * sl2 - ms), p1 = exp2f(__uint_as_float(v[i + 1]) * sl2 - ms);
+            const float s0 = __uint_as_float(c == 0 ? v0[i] : v1[i]), s1 = __uint_as_float(c == 0 ? v0[i + 1] : v1[i + 1]);
+            const float p0 = ft_ex2(s0 * sl2 - ms), p1 = ft_ex2(s1 * sl2 - ms);
             sum += p0 + p1;
             pk[i >> 1] = pack_bf16(p0, p1);
           }
         } else {
 #pragma unroll
           for (int i = 0; i < 32; i += 2) {
-            const float p0 = ((w >> i) & 1u) ? exp2f(__uint_as_float(v[i]) * sl2 - ms) : 0.f;
-            const float p1 = ((w >> (i + 1)) & 1u) ? exp2f(__uint_as_float(v[i + 1]) * sl2 - ms) : 0.f;
+            const float s0 = __uint_as_float(c == 0 ? v0[i] : v1[i]), s1 = __uint_as_float(c == 0 ? v0[i + 1] : v1[i + 1]);
+            const float p0 = ((w >> i) & 1u) ? ft_ex2(s0 * sl2 - ms) : 0.f;
+            const float p1 = ((w >> (i + 1)) & 1u) ? ft_ex2(s1 * sl2 - ms) : 0.f;
             sum += p0 + p1;
             pk[i >> 1] = pack_bf16(p0, p1);
           }
         }
-        unsigned char* base = sP + hf * (BQ * 128) + (r >> 3) * 1024 + (r & 7) * 128;
 #pragma unroll
         for (int q4 = 0; q4 < 4; ++q4) {
           const int chunk = c * 4 + q4;             // 16-byte chunk of the 128-byte row
@@ -340,20 +360,48 @@ extern "C" {
 int csm_tmap_2d(void* out, const void* base, long long rows, int K, long long pitch, int box_rows);
 int csm_tmap_2d_mn(void* out, const void* base, long long k_rows, long long mn, long long pitch);
 
-// qkv [nseq * S, W] rows (W = (heads + 2 kv) * 64), out [nseq * S, heads * 64], lse [nseq * S, heads] (may be null).
-// Returns cudaErrorInvalidValue for shapes this kernel does not cover (the caller falls back to nothing: it is an error).
+static cudaError_t ft_launch(const CUtensorMap& mq, const CUtensorMap& mk, const CUtensorMap& mv, const FlashTcParams& p,
+                             cudaStream_t st) {
+  cudaError_t e = cudaFuncSetAttribute((const void*)csm_flash_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, FT_SMEM);
+  if (e != cudaSuccess) return e;
+  dim3 grid((p.S + BQ - 1) / BQ, p.heads, p.nseq);
+  csm_flash_tc_kernel<<<grid, FT_THREADS, FT_SMEM, st>>>(mq, mk, mv, p);
+  return cudaGetLastError();
+}
+
+// Training: qkv [nseq * S, W] rows (W = (heads + 2 kv) * 64) hold q, k and v; out [nseq * S, heads * 64],
+// lse [nseq * S, heads] (may be null).
 cudaError_t csm_flash_tc_launch(const bf16* qkv, int S, int nseq, int heads, int kv, float scale, const unsigned char* valid,
                                 bf16* out, float* lse, cudaStream_t st) {
   const int W = (heads + 2 * kv) * HD;
   const long long rows = (long long)nseq * S;
   CUtensorMap mqk, mv;
   if (csm_tmap_2d(&mqk, qkv, rows, W, W, BQ) || csm_tmap_2d_mn(&mv, qkv, rows, W, W)) return cudaErrorInvalidValue;
-  cudaError_t e = cudaFuncSetAttribute((const void*)csm_flash_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, FT_SMEM);
-  if (e != cudaSuccess) return e;
   FlashTcParams p;
+  memset(&p, 0, sizeof p);
   p.S = S; p.heads = heads; p.kv = kv; p.nseq = nseq; p.scale = scale; p.valid = valid; p.out = out; p.lse = lse;
-  dim3 grid((S + BQ - 1) / BQ, heads, nseq);
-  csm_flash_tc_kernel<<<grid, FT_THREADS, FT_SMEM, st>>>(mqk, mv, p);
-  return cudaGetLastError();
+  p.kv_row_base = 0; p.kv_row_seq = S; p.kv_row_head = 0; p.k_col = heads * HD; p.v_col = (heads + kv) * HD; p.kv_col_head = HD;
+  return ft_launch(mqk, mqk, mv, p, st);
+}
+
+// Context prefill into an empty cache (CSMModel.generate_frame with S > 1, modeling_csm.py:484-552 -> hf LlamaAttention):
+// q rows [nseq * S, W] of this group of sequences; K / V already rotated and stored in the cache
+// [layer][Bmax][kv][Tcap][64] by the QKV GEMM's epilogue; sequences b0 .. b0 + nseq - 1; out [nseq * S, heads * 64].
+cudaError_t csm_flash_tc_prefill_launch(const bf16* qkv, int S, int b0, int nseq, int heads, int kv, const bf16* kc,
+                                        const bf16* vc, int layer, int layers, int Bmax, int Tcap, float scale,
+                                        const unsigned char* valid, bf16* out, cudaStream_t st) {
+  const int W = (heads + 2 * kv) * HD;
+  const long long crow = (long long)layers * Bmax * kv * Tcap;
+  if (crow >= (1ll << 31)) return cudaErrorInvalidValue;
+  CUtensorMap mq, mk, mv;
+  if (csm_tmap_2d(&mq, qkv, (long long)nseq * S, W, W, BQ) || csm_tmap_2d(&mk, kc, crow, HD, HD, BKV) ||
+      csm_tmap_2d_mn(&mv, vc, crow, HD, HD))
+    return cudaErrorInvalidValue;
+  FlashTcParams p;
+  memset(&p, 0, sizeof p);
+  p.S = S; p.heads = heads; p.kv = kv; p.nseq = nseq; p.scale = scale; p.valid = valid; p.out = out; p.lse = nullptr;
+  p.kv_row_base = ((long long)layer * Bmax + b0) * kv * Tcap; p.kv_row_seq = kv * Tcap; p.kv_row_head = Tcap;
+  p.k_col = 0; p.v_col = 0; p.kv_col_head = 0;
+  return ft_launch(mq, mk, mv, p, st);
 }
 }  // extern "C"
