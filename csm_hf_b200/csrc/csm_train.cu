@@ -41,6 +41,9 @@ cudaError_t csm_rmsnorm_rows_launch(const bf16* x, const bf16* w, float eps, int
 cudaError_t csm_frame_valid_launch(const int* mask, int rows, unsigned char* valid, int* any_pad, cudaStream_t st);
 cudaError_t csm_flash_tc_launch(const bf16* qkv, int S, int nseq, int heads, int kv, float scale, const unsigned char* valid,
                                 bf16* out, float* lse, cudaStream_t st);
+cudaError_t csm_flash_tc_bwd_launch(const bf16* qkv, const bf16* d_out, const float* lse, const float* delta, int S, int nseq,
+                                    int heads, int kv, float scale, const unsigned char* valid, bf16* dqkv, float* dq_acc,
+                                    cudaStream_t st);
 }
 
 namespace {
@@ -88,6 +91,7 @@ struct CsmTrain {
   float *audio_acc = nullptr, *text_acc = nullptr;     // fp32 gradients of the embedding tables
   int launches = 0;
   bool flash_tc = true;      // head-dim-64 attention forward on tcgen05
+  bool flash_tc_bwd = true;  // ... and backward
   bool mn_operands = true;   // gradients read W, dY and X as MN-major tcgen05 operands (CSM_TRAIN_TRANSPOSE=1: transposed copies)
   std::map<std::string, std::pair<const void*, size_t>> dbg;   // named intermediates of the last step (tests)
 };
@@ -330,7 +334,10 @@ int stack_backward(CsmTrain* t, TStack& s, const char* tag, int S, int nseq, con
                                                                                             t->delta);
     TCK(cudaGetLastError());
     TCK(cudaMemsetAsync(t->dq_acc, 0, (size_t)R * s.nq * 4, st));
-    if (s.hd == 64) TRY(flash_bwd<64>(t, s, y.qkv, t->dAttn, y.lse, t->delta, S, nseq, valid, t->dQKV, t->dq_acc, st));
+    if (s.hd == 64 && t->flash_tc_bwd) {   // tcgen05 backward (csm_flash_tc_bwd.cu); CSM_FLASH_BWD_MMA=1: the mma.sync kernel
+      TCK(csm_flash_tc_bwd_launch(y.qkv, t->dAttn, y.lse, t->delta, S, nseq, s.heads, s.kv, s.scale, valid, t->dQKV, t->dq_acc, st));
+      t->launches += 1;
+    } else if (s.hd == 64) TRY(flash_bwd<64>(t, s, y.qkv, t->dAttn, y.lse, t->delta, S, nseq, valid, t->dQKV, t->dq_acc, st));
     else TRY(flash_bwd<128>(t, s, y.qkv, t->dAttn, y.lse, t->delta, S, nseq, valid, t->dQKV, t->dq_acc, st));
     f32_to_bf16_rows_kernel<<<nblocks((long long)R * s.nq / 2), 256, 0, st>>>(t->dq_acc, R, s.nq, t->dQKV, s.W);
     TCK(cudaGetLastError());
@@ -441,6 +448,7 @@ int csm_train_create(const CsmShapes* sh, int max_tokens, int max_frames, CsmTra
   t->max_tokens = max_tokens; t->max_frames = max_frames;
   t->mn_operands = getenv("CSM_TRAIN_TRANSPOSE") == nullptr;
   t->flash_tc = getenv("CSM_FLASH_MMA") == nullptr;
+  t->flash_tc_bwd = getenv("CSM_FLASH_MMA") == nullptr && getenv("CSM_FLASH_BWD_MMA") == nullptr;
   if (sh->backbone.n_pos < 1 || sh->decoder.n_pos < 33) return tfail(t, CSM_EINVAL, "rope tables: the decoder needs 33 positions");
   const int Rd = max_frames * 33;
   TRY(setup_stack(t, t->bb, sh->backbone, max_tokens));
