@@ -123,8 +123,11 @@ def allreduce_gradients(model, group=None, bucket_bytes: int = 256 << 20) -> int
             all(g.untyped_storage().data_ptr() == flat.untyped_storage().data_ptr() for g in grads):
         # gradients of csm_train_step are views into one flat buffer (training.py): one collective, no copies
         # (the few padding elements between the views are reduced along; nothing reads them)
-        dist.all_reduce(flat, op=dist.ReduceOp.SUM, group=group)
-        flat.div_(world)
+        if dist.get_backend(group) == "nccl":
+            dist.all_reduce(flat, op=dist.ReduceOp.AVG, group=group)      # (the average inside the collective)
+        else:
+            dist.all_reduce(flat, op=dist.ReduceOp.SUM, group=group)
+            flat.div_(world)
         return 1
     buckets, cur, cur_bytes = [], [], 0
     for g in grads:
