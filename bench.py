@@ -98,6 +98,14 @@ def training_point(cfg, sd, dev, rank, world, seq, tpeak, note, steps=5):
     from csm_hf_b200.dist import allreduce_gradients
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     if world > 1:
+        # (only now, after every rank has completed local steps: from here on each step contains collectives)
+        from csm_hf_b200.training import enable_data_parallel
+        enable_data_parallel(tm)         # gradient all-reduce on a side stream, overlapped with the backward
+        for _ in range(2):
+            tm.zero_grad(set_to_none=True)
+            out = tm(input_ids=ids, attention_mask=mask, labels=labels)
+            out.loss.backward()
+            allreduce_gradients(tm)
         dist.barrier()
     torch.cuda.synchronize()
     e0.record()

@@ -90,6 +90,15 @@ struct CsmTrain {
   float *row_loss = nullptr, *losses = nullptr;        // device [3]
   float *audio_acc = nullptr, *text_acc = nullptr;     // fp32 gradients of the embedding tables
   int launches = 0;
+  // a step split in two calls (csm_train_step_begin / _end): what the second half needs
+  struct {
+    bool active = false, want = false;
+    int B = 0, S = 0, split = 0;
+    const long long* ids = nullptr;
+    const int* mask = nullptr;
+    const unsigned char* valid = nullptr;
+    bf16 *g_audio = nullptr, *g_text = nullptr;
+  } pend;
   bool flash_tc = true;      // head-dim-64 attention forward on tcgen05
   bool flash_tc_bwd = true;  // ... and backward
   bool mn_operands = true;   // gradients read W, dY and X as MN-major tcgen05 operands (CSM_TRAIN_TRANSPOSE=1: transposed copies)
@@ -306,9 +315,10 @@ int norm_bwd(CsmTrain* t, const TStack& s, const bf16* x, const bf16* w, const b
 // Adjoint of stack_forward.  dh: gradient w.r.t. the residual stream after the last layer on entry (the final norm's
 // adjoint has been applied by the caller), w.r.t. the stack's input on return.  Writes the layers' weight gradients.
 int stack_backward(CsmTrain* t, TStack& s, const char* tag, int S, int nseq, const unsigned char* valid, bf16* dh,
-                   bool want_grads, cudaStream_t st) {
+                   bool want_grads, cudaStream_t st, int l_hi = -1, int l_lo = 0) {
   const int R = nseq * S;
-  for (int l = s.L - 1; l >= 0; --l) {
+  if (l_hi < 0) l_hi = s.L - 1;
+  for (int l = l_hi; l >= l_lo; --l) {
     TLayer& y = s.layers[l];
     const std::string pre = std::string("d.") + tag + "." + std::to_string(l) + ".";
     TRY(note(t, pre + "h_out", dh, (size_t)R * s.H * 2, st));
@@ -520,12 +530,14 @@ int csm_train_debug(CsmTrain* t, const char* name, void* host, long long cap, lo
   return 0;
 }
 
-int csm_train_step(CsmTrain* t, const CsmWeights* w, const CsmWeights* g, const int64_t* ids, const int32_t* mask,
-                   const int64_t* labels, int B, int S, float* losses_host, int* n_frames_host, void* last_h_out,
-                   void* c0_logits_out, void* stream) {
+int csm_train_step_begin(CsmTrain* t, const CsmWeights* w, const CsmWeights* g, const int64_t* ids, const int32_t* mask,
+                         const int64_t* labels, int B, int S, int split_layer, int* n_frames_host, void* last_h_out,
+                         void* c0_logits_out, void* stream) {
   if (!t) return CSM_EINVAL;
   cudaStream_t st = (cudaStream_t)stream;
-  if (!w || !ids || !labels || !losses_host) return tfail(t, CSM_EINVAL, "null weights / ids / labels / losses");
+  t->pend.active = false;
+  if (!w || !ids || !labels) return tfail(t, CSM_EINVAL, "null weights / ids / labels");
+  if (split_layer < 0 || split_layer > t->bb.L) return tfail(t, CSM_EINVAL, "split_layer %d outside [0, %d]", split_layer, t->bb.L);
   const int R = B * S;
   if (B < 1 || S < 2 || R > t->max_tokens) return tfail(t, CSM_ECAPACITY, "B*S = %d exceeds max_tokens %d (or S < 2)", R, t->max_tokens);
   if (S > t->bb.n_pos) return tfail(t, CSM_ECAPACITY, "sequence length %d exceeds the %d rope positions", S, t->bb.n_pos);
@@ -681,16 +693,35 @@ int csm_train_step(CsmTrain* t, const CsmWeights* w, const CsmWeights* g, const 
       }
     }
     TRY(note(t, "d.bb.hf", t->dh_bb, (size_t)R * b.H * 2, st));
-    // backbone: final norm, layers, embedding tables
+    // backbone: final norm, then the layers from the last one down to split_layer (the rest in csm_train_step_end)
     TRY(norm_bwd(t, b, b.h_out, b.norm, t->dh_bb, nullptr, t->dh_bb, b.gnorm, R, st));
-    TRY(stack_backward(t, b, "bb", S, B, valid, t->dh_bb, true, st));
+    if (split_layer < b.L) TRY(stack_backward(t, b, "bb", S, B, valid, t->dh_bb, true, st, b.L - 1, split_layer));
+    t->pend.g_audio = (bf16*)g->audio_embeddings;
+    t->pend.g_text = (bf16*)g->text_embeddings;
+  }
+  t->pend.active = true; t->pend.want = want; t->pend.B = B; t->pend.S = S; t->pend.split = split_layer;
+  t->pend.ids = ids_ll; t->pend.mask = mask; t->pend.valid = valid;
+  return 0;
+}
+
+/* Second half of a step started with csm_train_step_begin: the backbone layers below split_layer, the embedding-table
+ * gradients, and the losses (synchronises the stream). */
+int csm_train_step_end(CsmTrain* t, float* losses_host, void* stream) {
+  if (!t || !losses_host) return CSM_EINVAL;
+  cudaStream_t st = (cudaStream_t)stream;
+  if (!t->pend.active) return tfail(t, CSM_EINVAL, "csm_train_step_end without csm_train_step_begin");
+  t->pend.active = false;
+  TStack& b = t->bb;
+  const int B = t->pend.B, S = t->pend.S, R = B * S, V = t->V;
+  if (t->pend.want) {
+    if (t->pend.split > 0) TRY(stack_backward(t, b, "bb", S, B, t->pend.valid, t->dh_bb, true, st, t->pend.split - 1, 0));
     TRY(note(t, "d.bb.x0", t->dh_bb, (size_t)R * b.H * 2, st));
-    embed_bwd_kernel<<<R, 256, 0, st>>>(t->dh_bb, ids_ll, mask, V, b.H, t->audio_acc, t->text_acc);
+    embed_bwd_kernel<<<R, 256, 0, st>>>(t->dh_bb, t->pend.ids, t->pend.mask, V, b.H, t->audio_acc, t->text_acc);
     TCK(cudaGetLastError());
-    f32_to_bf16_kernel<<<nblocks((long long)V * 32 * b.H / 2), 256, 0, st>>>(t->audio_acc, (long long)V * 32 * b.H, (bf16*)g->audio_embeddings);
+    f32_to_bf16_kernel<<<nblocks((long long)V * 32 * b.H / 2), 256, 0, st>>>(t->audio_acc, (long long)V * 32 * b.H, t->pend.g_audio);
     TCK(cudaGetLastError());
     f32_to_bf16_kernel<<<nblocks((long long)t->text_vocab * b.H / 2), 256, 0, st>>>(t->text_acc, (long long)t->text_vocab * b.H,
-                                                                                   (bf16*)g->text_embeddings);
+                                                                                   t->pend.g_text);
     TCK(cudaGetLastError());
     t->launches += 3;
   }
@@ -701,6 +732,15 @@ int csm_train_step(CsmTrain* t, const CsmWeights* w, const CsmWeights* g, const 
   losses_host[2] = l3[2];
   losses_host[0] = l3[1] + l3[2];   // modeling_csm.py:471: loss = backbone_loss + decoder_loss
   return 0;
+}
+
+int csm_train_step(CsmTrain* t, const CsmWeights* w, const CsmWeights* g, const int64_t* ids, const int32_t* mask,
+                   const int64_t* labels, int B, int S, float* losses_host, int* n_frames_host, void* last_h_out,
+                   void* c0_logits_out, void* stream) {
+  if (!losses_host) return t ? tfail(t, CSM_EINVAL, "null losses") : CSM_EINVAL;
+  int r = csm_train_step_begin(t, w, g, ids, mask, labels, B, S, 0, n_frames_host, last_h_out, c0_logits_out, stream);
+  if (r) return r;
+  return csm_train_step_end(t, losses_host, stream);
 }
 
 }  // extern "C"

@@ -114,6 +114,9 @@ def allreduce_gradients(model, group=None, bucket_bytes: int = 256 << 20) -> int
     over the ranks after loss.backward().  Gradients are packed into flat buckets of ~`bucket_bytes` (3.1 GB of bf16
     gradients for csm-1b -> a dozen NCCL all-reduces over NVLink instead of 187), summed, scaled by 1/world and
     unpacked in place.  Works with any backend (gloo on CPU in the tests).  -> number of buckets reduced."""
+    if getattr(model, "_grads_reduced", False):      # training.enable_data_parallel averaged them during the backward
+        model._grads_reduced = False
+        return 0
     world = dist.get_world_size(group)
     grads = [p.grad for _, p in sorted(model.named_parameters()) if p.grad is not None]
     if world == 1 or not grads:

@@ -19,7 +19,7 @@ EXPORTS = [
     "csm_debug_profile_frame", "csm_debug_progress", "csm_set_sampling", "csm_sample_topk", "csm_linear",
     "csm_generate_more",
     "csm_train_create", "csm_train_destroy", "csm_train_last_error", "csm_train_launches", "csm_train_step",
-    "csm_train_debug",
+    "csm_train_debug", "csm_train_step_begin", "csm_train_step_end",
 ]
 
 
@@ -87,6 +87,10 @@ def load():
     lib.csm_train_step.argtypes = [vp, C.POINTER(Weights), C.POINTER(Weights), i64p, vp, i64p, i32, i32,
                                    C.POINTER(C.c_float), C.POINTER(C.c_int), vp, vp, vp]
     lib.csm_train_step.restype = i32
+    lib.csm_train_step_begin.argtypes = [vp, C.POINTER(Weights), C.POINTER(Weights), i64p, vp, i64p, i32, i32, i32,
+                                         C.POINTER(C.c_int), vp, vp, vp]
+    lib.csm_train_step_begin.restype = i32
+    lib.csm_train_step_end.argtypes = [vp, C.POINTER(C.c_float), vp]; lib.csm_train_step_end.restype = i32
     lib.csm_train_debug.argtypes = [vp, C.c_char_p, vp, C.c_longlong, C.POINTER(C.c_longlong)]; lib.csm_train_debug.restype = i32
     lib.csm_linear.argtypes = [vp, i32, vp, i32, i32, i32, i32, vp, i32, vp]; lib.csm_linear.restype = i32
     _lib = lib

@@ -128,6 +128,34 @@ class TrainEngine:
         self._check(rc)
         return [float(x) for x in losses], int(nfr.value), last_h, c0
 
+    def step_begin(self, params, grads, ids, mask, labels, split_layer: int):
+        """First call of a split step (csm_train_step_begin); -> (n_frames, last_h, c0_logits).  step_end() must follow."""
+        B, S = ids.shape[:2]
+        keep: list = []
+        w = _weights_struct(self.cfg, params, keep)
+        g = _weights_struct(self.cfg, grads, keep)
+        nfr = C.c_int(0)
+        last_h = torch.empty(B, self.cfg.backbone_config.hidden_size, dtype=torch.bfloat16, device=self.device)
+        c0 = torch.empty(B, self.cfg.audio_vocab_size, dtype=torch.bfloat16, device=self.device)
+        self._pending_keep = (keep, w, g, ids, mask, labels)      # alive until step_end returns
+        with torch.cuda.device(self.device):
+            st = C.c_void_p(torch.cuda.current_stream(self.device).cuda_stream)
+            rc = self.lib.csm_train_step_begin(self.ctx, C.byref(w), C.byref(g), ids.data_ptr(),
+                                               mask.data_ptr() if mask is not None else None, labels.data_ptr(), B, S,
+                                               split_layer, C.byref(nfr), last_h.data_ptr(), c0.data_ptr(), st)
+        self._check(rc)
+        return int(nfr.value), last_h, c0
+
+    def step_end(self):
+        """Second call of a split step: -> losses [3] (synchronises the stream)."""
+        losses = (C.c_float * 3)()
+        with torch.cuda.device(self.device):
+            st = C.c_void_p(torch.cuda.current_stream(self.device).cuda_stream)
+            rc = self.lib.csm_train_step_end(self.ctx, losses, st)
+        self._pending_keep = None
+        self._check(rc)
+        return [float(x) for x in losses]
+
     def debug(self, name: str, dtype=torch.bfloat16) -> torch.Tensor:
         """Host copy of a named intermediate of the last step (tests)."""
         n = C.c_longlong(0)
@@ -202,17 +230,49 @@ def training_forward(model, input_ids: torch.Tensor, attention_mask: Optional[to
         eng = TrainEngine(cfg, dev, B * S, max(n_frames_cap, 1), S)
         model._train_engine = eng
     grads = None
+    ddp = getattr(model, "_ddp", None) if want else None
     if want:
-        # one flat bf16 buffer, the gradient tensors are views into it: data-parallel training all-reduces the buffer in
-        # ONE NCCL call without packing / unpacking copies (dist.allreduce_gradients)
-        sizes = [p.numel() for p in plist]
-        flat = torch.empty(sum(-(-n // 8) * 8 for n in sizes), dtype=torch.bfloat16, device=dev)   # 16-byte aligned views
-        grads, off = {}, 0
-        for k, p, n in zip(names, plist, sizes):
-            grads[k] = flat[off:off + n].view(p.shape)
-            off += -(-n // 8) * 8
+        # one flat bf16 buffer, the gradient tensors are views into it: data-parallel training all-reduces the buffer
+        # without packing / unpacking copies.  Layout: first the gradients that become final LAST in the backward
+        # (embedding tables, backbone layers below the split), then the rest -- the two halves are averaged separately,
+        # the second one while the backward of the first is still running (enable_data_parallel below).
+        split = ddp["split"] if ddp else 0
+        late = [k for k in names if k.endswith("embeddings.weight") or
+                (k.startswith("backbone.layers.") and int(k.split(".")[2]) < split)]
+        order = late + [k for k in names if k not in set(late)]
+        pmap = dict(zip(names, plist))
+        sizes = {k: -(-pmap[k].numel() // 8) * 8 for k in order}                     # 16-byte aligned views
+        flat = torch.empty(sum(sizes.values()), dtype=torch.bfloat16, device=dev)
+        grads, off, late_end = {}, 0, 0
+        for k in order:
+            grads[k] = flat[off:off + pmap[k].numel()].view(pmap[k].shape)
+            off += sizes[k]
+            if k in late:
+                late_end = off
         model._grad_flat = flat
-    losses, n_frames, last_h, c0 = eng.step({k: p.data for k, p in zip(names, plist)}, grads, ids, mask, lab)
+    pdata = {k: p.data for k, p in zip(names, plist)}
+    if ddp:
+        import torch.distributed as dist
+        group, side = ddp["group"], ddp["stream"]
+        cur = torch.cuda.current_stream(dev)
+        op = dist.ReduceOp.AVG if dist.get_backend(group) == "nccl" else dist.ReduceOp.SUM
+        n_frames, last_h, c0 = eng.step_begin(pdata, grads, ids, mask, lab, split)
+        ev = torch.cuda.Event()
+        ev.record(cur)
+        flat.record_stream(side)
+        with torch.cuda.stream(side):           # averaged on the side stream while the rest of the backward runs
+            side.wait_event(ev)
+            dist.all_reduce(flat[late_end:], op=op, group=group)
+        losses = eng.step_end()
+        with torch.cuda.stream(side):
+            if late_end:
+                dist.all_reduce(flat[:late_end], op=op, group=group)
+            if op == dist.ReduceOp.SUM:
+                flat.div_(dist.get_world_size(group))
+        cur.wait_stream(side)
+        model._grads_reduced = True
+    else:
+        losses, n_frames, last_h, c0 = eng.step(pdata, grads, ids, mask, lab)
     vals = torch.tensor(losses, dtype=torch.float32, device=dev)
     loss = vals[0]
     if want:
@@ -224,3 +284,15 @@ def training_forward(model, input_ids: torch.Tensor, attention_mask: Optional[to
     if return_dict is False:
         return (loss, last_h, c0)
     return out
+
+
+def enable_data_parallel(model, group=None, split_layer: Optional[int] = None):
+    """Data-parallel training with the gradient all-reduce overlapped with the backward: every later
+    `model(..., labels=...)` step averages its gradients over `group` itself (two NCCL all-reduces on a side stream, the
+    first one -- decoder, heads and the backbone layers >= split_layer -- while the backbone layers below split_layer are
+    still in their backward), and `dist.allreduce_gradients(model)` becomes a no-op for that step.
+    split_layer defaults to a quarter of the backbone's layers."""
+    L = model.config.backbone_config.num_hidden_layers
+    split = max(0, min(L, L // 4 if split_layer is None else split_layer))
+    model._ddp = {"group": group, "split": split, "stream": torch.cuda.Stream(device=model.device)}
+    return model

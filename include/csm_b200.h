@@ -212,6 +212,17 @@ int csm_train_step(CsmTrain* t, const CsmWeights* weights, const CsmWeights* gra
                    const int32_t* mask, const int64_t* labels, int B, int S, float* losses, int* n_frames,
                    void* last_h, void* c0_logits, void* stream);
 
+/* The same step in two calls, so that a data-parallel caller can start averaging the gradients that are already final
+ * while the rest of the backward runs: _begin enqueues the forward, the losses and the backward down to (and including)
+ * backbone layer split_layer -- the gradients of the decoder, the heads, the projection, the backbone norm and the backbone
+ * layers >= split_layer are then final in stream order; _end enqueues the backbone layers below split_layer and the
+ * embedding-table gradients, reads the losses back and synchronises.  split_layer in [0, layers]; the weight / gradient
+ * pointer arrays of _begin must stay alive until _end returns. */
+int csm_train_step_begin(CsmTrain* t, const CsmWeights* weights, const CsmWeights* grads, const int64_t* ids,
+                         const int32_t* mask, const int64_t* labels, int B, int S, int split_layer, int* n_frames,
+                         void* last_h, void* c0_logits, void* stream);
+int csm_train_step_end(CsmTrain* t, float* losses, void* stream);
+
 /* Tests: host copy of a named intermediate of the last step ("bb.0.qkv", "dec.1.attn", "d.bb.x0", ...); host == NULL
  * returns only its size in bytes. */
 int csm_train_debug(CsmTrain* t, const char* name, void* host, long long cap, long long* bytes);

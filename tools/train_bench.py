@@ -56,9 +56,12 @@ def main():
         import torch.distributed as dist
         dist.init_process_group("nccl", device_id=dev)
         from csm_hf_b200.dist import allreduce_gradients
+        from csm_hf_b200.training import enable_data_parallel
     cfg = tiny_config() if a.tiny else CSMConfig()
     model = CSMModel(cfg, make_state_dict(cfg, seed=0, dtype=torch.bfloat16), device=dev)
     model.requires_grad_(True)
+    if world > 1 and os.environ.get("CSM_DDP_OVERLAP", "1") != "0":
+        enable_data_parallel(model)      # gradient all-reduce overlapped with the backward (training.py)
     ids, mask, labels = make_training_batch(cfg, a.batch, a.seq, seed=100 + rank, text_frames=16, amortization_ratio=a.ratio)
     ids, mask, labels = ids.to(dev), mask.to(dev), labels.to(dev)
     F = int((labels[:, :, :32] != -100).all(dim=2).sum())
