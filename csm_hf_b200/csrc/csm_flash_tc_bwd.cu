@@ -5,7 +5,7 @@
 //   v columns of the gradient rows) and dQ (fp32 reductions into a buffer the caller rounds afterwards).
 //
 // One CTA = one block of 128 keys of one kv head; it keeps dK and dV of its keys in TENSOR MEMORY across the 4 query heads
-// of the GQA group and every query block at or after the key block (no atomics for dK / dV).  320 threads:
+// of the GQA group and every query block at or after the key block (no atomics for dK / dV).  576 threads:
 //   warp 0      TMA producer: K and V block once; per iteration (query head, 128-query block) the Q and dO tiles (2 stages)
 //   warp 1      MMA issuer.  Per iteration, all five products on tcgen05 (M 128):
 //                 S^T  = K Q^T        (K-major x K-major, N 128)      dP^T = V dO^T       (same)
@@ -13,11 +13,11 @@
 //                 dK  += dS^T Q       (likewise with the Q tile)
 //                 dQ   = dS K         (the dS^T tile read as an MN-major A operand, the K tile as an MN-major B operand)
 //               S^T / dP^T of iteration i+1 are issued as soon as the softmax threads have pulled iteration i's into registers
-//   warps 2..9  two threads per key row: scores and dP out of TMEM, P^T = 2^(scale' s - lse'), dS^T = P^T (dP^T - D) scale
-//               written as bf16 tiles in the 128-byte-swizzle layout; the dQ tile of the previous iteration is read out of
-//               TMEM (thread = query row) and added to the fp32 buffer with 16-byte reductions; at the end dK / dV rows
+//   warps 2..17 four threads per key row: scores and dP out of TMEM, P^T = 2^(scale' s - lse'), dS'^T = P^T (dP^T - D)
+//               (the softmax scale is applied to dQ and dK on the way out) written as bf16 tiles in the 128-byte-swizzle
+//               layout; the dQ tile of the previous iteration (two accumulators) is read out of TMEM (thread = query row)
+//               and added to the fp32 buffer with 16-byte reductions; at the end the dK / dV rows
 #include <cuda.h>
-#include <stdlib.h>
 #include <string.h>
 
 #include "csm_tc.cuh"
@@ -38,7 +38,6 @@ struct FlashBwdParams {
   const float* delta;           // [nseq * S, heads]
   bf16* dqkv;                   // [nseq * S, W]: the k and v columns are written
   float* dq_acc;                // [nseq * S, heads * 64] fp32, zeroed by the caller
-  int skip_dq;                  // experiment: do not add the dQ tiles (timing without the reductions)
 };
 
 __global__ void __launch_bounds__(FB_THREADS, 1)
@@ -180,7 +179,7 @@ csm_flash_tc_bwd_kernel(const __grid_constant__ CUtensorMap map_qkv, const __gri
       __syncwarp();
       if (lane == 0) mbar_arrive(&dq_empty[itp & 1]);
       const int q = q0_prev + r;
-      if (q < p.S && !p.skip_dq) {
+      if (q < p.S) {
         float* dst = p.dq_acc + ((size_t)row0 + q) * nq + head_prev * HDB + qq * 16;
 #pragma unroll
         for (int i = 0; i < 16; i += 4)
@@ -312,7 +311,6 @@ cudaError_t csm_flash_tc_bwd_launch(const bf16* qkv, const bf16* d_out, const fl
   memset(&p, 0, sizeof p);
   p.S = S; p.heads = heads; p.kv = kv; p.nseq = nseq; p.scale = scale; p.valid = valid; p.lse = lse; p.delta = delta;
   p.dqkv = dqkv; p.dq_acc = dq_acc;
-  p.skip_dq = getenv("CSM_FBWD_SKIP_DQ") != nullptr;
   dim3 grid((S + BB - 1) / BB, kv, nseq);
   csm_flash_tc_bwd_kernel<<<grid, FB_THREADS, FB_SMEM, st>>>(mq, mdo, p);
   return cudaGetLastError();

@@ -329,9 +329,13 @@ int stack_backward(CsmTrain* t, TStack& s, const char* tag, int S, int nseq, con
     TCK(cudaGetLastError());
     TRY(dgrad(t, t->dGU, 2 * s.I, R, 2 * s.I, y.Wgu, s.H, s.H, y.WguT, t->dHn, s.H, st));
     if (want_grads) {
-      TRY(wgrad(t, t->dGU, 2 * s.I, y.hn2, s.H, R, 2 * s.I, s.H, t->dWtmp, s.H, st));
-      TRY(copy_rows(t, y.ggate, t->dWtmp, (size_t)s.I * s.H, st));
-      TRY(copy_rows(t, y.gup, t->dWtmp + (size_t)s.I * s.H, (size_t)s.I * s.H, st));
+      // (gate | up gradients adjacent in the caller's buffer -- the flat layout of training.py: written in place)
+      bf16* dgu = y.gup == y.ggate + (size_t)s.I * s.H ? y.ggate : t->dWtmp;
+      TRY(wgrad(t, t->dGU, 2 * s.I, y.hn2, s.H, R, 2 * s.I, s.H, dgu, s.H, st));
+      if (dgu == t->dWtmp) {
+        TRY(copy_rows(t, y.ggate, t->dWtmp, (size_t)s.I * s.H, st));
+        TRY(copy_rows(t, y.gup, t->dWtmp + (size_t)s.I * s.H, (size_t)s.I * s.H, st));
+      }
     }
     TRY(note(t, pre + "act", t->dAct, (size_t)R * s.I * 2, st));
     TRY(note(t, pre + "hn2", t->dHn, (size_t)R * s.H * 2, st));
@@ -359,10 +363,14 @@ int stack_backward(CsmTrain* t, TStack& s, const char* tag, int S, int nseq, con
     TRY(dgrad(t, t->dQKV, s.W, R, s.W, y.Wqkv, s.H, s.H, y.WqkvT, t->dHn, s.H, st));
     TRY(note(t, pre + "hn1", t->dHn, (size_t)R * s.H * 2, st));
     if (want_grads) {
-      TRY(wgrad(t, t->dQKV, s.W, y.hn1, s.H, R, s.W, s.H, t->dWtmp, s.H, st));
-      TRY(copy_rows(t, y.gq, t->dWtmp, (size_t)s.nq * s.H, st));
-      TRY(copy_rows(t, y.gk, t->dWtmp + (size_t)s.nq * s.H, (size_t)s.kv * s.hd * s.H, st));
-      TRY(copy_rows(t, y.gv, t->dWtmp + (size_t)(s.nq + s.kv * s.hd) * s.H, (size_t)s.kv * s.hd * s.H, st));
+      const size_t kvw = (size_t)s.kv * s.hd;
+      bf16* dqkvw = (y.gk == y.gq + (size_t)s.nq * s.H && y.gv == y.gk + kvw * s.H) ? y.gq : t->dWtmp;   // (see gate | up)
+      TRY(wgrad(t, t->dQKV, s.W, y.hn1, s.H, R, s.W, s.H, dqkvw, s.H, st));
+      if (dqkvw == t->dWtmp) {
+        TRY(copy_rows(t, y.gq, t->dWtmp, (size_t)s.nq * s.H, st));
+        TRY(copy_rows(t, y.gk, t->dWtmp + (size_t)s.nq * s.H, kvw * s.H, st));
+        TRY(copy_rows(t, y.gv, t->dWtmp + ((size_t)s.nq + kvw) * s.H, kvw * s.H, st));
+      }
     }
     TRY(norm_bwd(t, s, y.h_in, y.ln1, t->dHn, dh, dh, want_grads ? y.gln1 : nullptr, R, st));
     t->launches += 5;
