@@ -270,7 +270,7 @@ int stack_forward(CsmTrain* t, TStack& s, int S, int nseq, const unsigned char* 
     TLayer& y = s.layers[l];
     TCK(csm_rmsnorm_rows_launch(y.h_in, y.ln1, s.eps, s.H, y.hn1, R, st));
     TRY(gemm(t, y.hn1, s.H, R, s.H, y.Wqkv, s.H, s.W, y.qkv, s.W, EPI_STORE, st));
-    rope_rows_kernel<false><<<nblocks((long long)R * (s.heads + s.kv) * (s.hd / 2)), 256, 0, st>>>(
+    rope_rows_kernel<false><<<nblocks((long long)R * (s.heads + s.kv) * (s.hd / 16)), 256, 0, st>>>(
         y.qkv, s.W, R, S, s.heads + s.kv, s.hd, s.cos_t, s.sin_t);
     TCK(cudaGetLastError());
     if (s.hd == 64 && t->flash_tc) {   // tcgen05 forward (csm_flash_tc.cu); CSM_FLASH_MMA=1: the mma.sync kernel
@@ -285,7 +285,7 @@ int stack_forward(CsmTrain* t, TStack& s, int S, int nseq, const unsigned char* 
     TRY(gemm(t, y.attn, s.nq, R, s.nq, y.o, s.nq, s.H, y.h_mid, s.H, EPI_RESID, st));
     TCK(csm_rmsnorm_rows_launch(y.h_mid, y.ln2, s.eps, s.H, y.hn2, R, st));
     TRY(gemm(t, y.hn2, s.H, R, s.H, y.Wgu, s.H, 2 * s.I, y.gu, 2 * s.I, EPI_STORE, st));
-    swiglu_fwd_kernel<<<nblocks((long long)R * s.I / 2), 256, 0, st>>>(y.gu, R, s.I, y.act);
+    swiglu_fwd_kernel<<<nblocks((long long)R * s.I / 8), 256, 0, st>>>(y.gu, R, s.I, y.act);
     TCK(cudaGetLastError());
     bf16* nxt = l + 1 < s.L ? s.layers[l + 1].h_in : s.h_out;
     TRY(copy_rows(t, nxt, y.h_mid, (size_t)R * s.H, st));
@@ -325,7 +325,7 @@ int stack_backward(CsmTrain* t, TStack& s, const char* tag, int S, int nseq, con
     // ---- MLP: h_out = h_mid + down(act), act = silu(gate) * up, gate|up = Wgu hn2, hn2 = norm(h_mid)
     TRY(dgrad(t, dh, s.H, R, s.H, y.down, s.I, s.I, y.WdownT, t->dAct, s.I, st));
     if (want_grads) TRY(wgrad(t, dh, s.H, y.act, s.I, R, s.H, s.I, y.gdown, s.I, st));
-    swiglu_bwd_kernel<<<nblocks((long long)R * s.I / 2), 256, 0, st>>>(y.gu, t->dAct, R, s.I, t->dGU);
+    swiglu_bwd_kernel<<<nblocks((long long)R * s.I / 8), 256, 0, st>>>(y.gu, t->dAct, R, s.I, t->dGU);
     TCK(cudaGetLastError());
     TRY(dgrad(t, t->dGU, 2 * s.I, R, 2 * s.I, y.Wgu, s.H, s.H, y.WguT, t->dHn, s.H, st));
     if (want_grads) {
@@ -355,7 +355,7 @@ int stack_backward(CsmTrain* t, TStack& s, const char* tag, int S, int nseq, con
     else TRY(flash_bwd<128>(t, s, y.qkv, t->dAttn, y.lse, t->delta, S, nseq, valid, t->dQKV, t->dq_acc, st));
     f32_to_bf16_rows_kernel<<<nblocks((long long)R * s.nq / 2), 256, 0, st>>>(t->dq_acc, R, s.nq, t->dQKV, s.W);
     TCK(cudaGetLastError());
-    rope_rows_kernel<true><<<nblocks((long long)R * (s.heads + s.kv) * (s.hd / 2)), 256, 0, st>>>(
+    rope_rows_kernel<true><<<nblocks((long long)R * (s.heads + s.kv) * (s.hd / 16)), 256, 0, st>>>(
         t->dQKV, s.W, R, S, s.heads + s.kv, s.hd, s.cos_t, s.sin_t);
     TCK(cudaGetLastError());
     TRY(note(t, pre + "attn", t->dAttn, (size_t)R * s.nq * 2, st));

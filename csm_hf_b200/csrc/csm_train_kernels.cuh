@@ -44,21 +44,32 @@ __device__ __forceinline__ void red_add_v4(float* p, float a, float b, float c, 
 template <bool BWD>
 __global__ void rope_rows_kernel(bf16* __restrict__ x, int ld, int rows, int S, int nheads, int hd,
                                  const bf16* __restrict__ cs, const bf16* __restrict__ sn) {
-  const int half = hd >> 1;
-  const long long total = (long long)rows * nheads * half;
+  const int half = hd >> 1, h8 = half >> 3;     // 8 rotation pairs (two 16-byte vectors of x, one each of cos / sin) per thread
+  const long long total = (long long)rows * nheads * h8;
   for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
-    const int e = (int)(i % half), h = (int)((i / half) % nheads), r = (int)(i / ((long long)half * nheads));
+    const int e = (int)(i % h8) * 8, h = (int)((i / h8) % nheads), r = (int)(i / ((long long)h8 * nheads));
     const int pos = r % S;
-    const float c = __bfloat162float(cs[(size_t)pos * half + e]), s = __bfloat162float(sn[(size_t)pos * half + e]);
+    const uint4 c4 = __ldg(reinterpret_cast<const uint4*>(cs + (size_t)pos * half + e));
+    const uint4 s4 = __ldg(reinterpret_cast<const uint4*>(sn + (size_t)pos * half + e));
     bf16* p = x + (size_t)r * ld + h * hd + e;
-    const float a = __bfloat162float(p[0]), b = __bfloat162float(p[half]);
-    if (!BWD) {
-      p[0] = __float2bfloat16_rn(bfround(a * c) + bfround(-b * s));
-      p[half] = __float2bfloat16_rn(bfround(b * c) + bfround(a * s));
-    } else {
-      p[0] = __float2bfloat16_rn(a * c + b * s);
-      p[half] = __float2bfloat16_rn(b * c - a * s);
+    const uint4 a4 = *reinterpret_cast<const uint4*>(p), b4 = *reinterpret_cast<const uint4*>(p + half);
+    const uint32_t cw[4] = {c4.x, c4.y, c4.z, c4.w}, sw[4] = {s4.x, s4.y, s4.z, s4.w};
+    const uint32_t aw[4] = {a4.x, a4.y, a4.z, a4.w}, bw[4] = {b4.x, b4.y, b4.z, b4.w};
+    uint32_t o1[4], o2[4];
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+      const float a0 = bf_lo(aw[q]), a1 = bf_hi(aw[q]), b0 = bf_lo(bw[q]), b1 = bf_hi(bw[q]);
+      const float c0 = bf_lo(cw[q]), c1 = bf_hi(cw[q]), s0 = bf_lo(sw[q]), s1 = bf_hi(sw[q]);
+      if (!BWD) {
+        o1[q] = pack_bf16(bfround(a0 * c0) + bfround(-b0 * s0), bfround(a1 * c1) + bfround(-b1 * s1));
+        o2[q] = pack_bf16(bfround(b0 * c0) + bfround(a0 * s0), bfround(b1 * c1) + bfround(a1 * s1));
+      } else {
+        o1[q] = pack_bf16(a0 * c0 + b0 * s0, a1 * c1 + b1 * s1);
+        o2[q] = pack_bf16(b0 * c0 - a0 * s0, b1 * c1 - a1 * s1);
+      }
     }
+    *reinterpret_cast<uint4*>(p) = make_uint4(o1[0], o1[1], o1[2], o1[3]);
+    *reinterpret_cast<uint4*>(p + half) = make_uint4(o2[0], o2[1], o2[2], o2[3]);
   }
 }
 
@@ -450,39 +461,52 @@ __global__ void f32_to_bf16_rows_kernel(const float* __restrict__ src, int rows,
 // ---------------------------------------------------------------- SwiGLU on [R, 2I] rows = gate | up
 // hf modeling_llama.py:183: bf16(silu(gate)) * up -> bf16
 __global__ void swiglu_fwd_kernel(const bf16* __restrict__ gu, int rows, int I, bf16* __restrict__ act) {
-  const long long total = (long long)rows * I / 2;
+  const long long total = (long long)rows * I / 8;     // 8 elements (one 16-byte vector of gate, up and the output) per thread
   for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
-    const long long e = i * 2;
+    const long long e = i * 8;
     const int r = (int)(e / I), c = (int)(e % I);
-    const uint32_t gw = *reinterpret_cast<const uint32_t*>(gu + (size_t)r * 2 * I + c);
-    const uint32_t uw = *reinterpret_cast<const uint32_t*>(gu + (size_t)r * 2 * I + I + c);
-    const float g0 = bf_lo(gw), g1 = bf_hi(gw);
-    const float s0 = bfround(g0 / (1.f + expf(-g0))), s1 = bfround(g1 / (1.f + expf(-g1)));
-    *reinterpret_cast<uint32_t*>(act + (size_t)r * I + c) = pack_bf16(s0 * bf_lo(uw), s1 * bf_hi(uw));
+    const uint4 g4 = *reinterpret_cast<const uint4*>(gu + (size_t)r * 2 * I + c);
+    const uint4 u4 = *reinterpret_cast<const uint4*>(gu + (size_t)r * 2 * I + I + c);
+    const uint32_t gw[4] = {g4.x, g4.y, g4.z, g4.w}, uw[4] = {u4.x, u4.y, u4.z, u4.w};
+    uint32_t o[4];
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+      const float g0 = bf_lo(gw[q]), g1 = bf_hi(gw[q]);
+      const float s0 = bfround(g0 / (1.f + expf(-g0))), s1 = bfround(g1 / (1.f + expf(-g1)));
+      o[q] = pack_bf16(s0 * bf_lo(uw[q]), s1 * bf_hi(uw[q]));
+    }
+    *reinterpret_cast<uint4*>(act + (size_t)r * I + c) = make_uint4(o[0], o[1], o[2], o[3]);
   }
 }
 // d gate = d act * up * silu'(gate), d up = d act * silu(gate)   (autograd of F.silu(g) * u on bf16 tensors)
 __global__ void swiglu_bwd_kernel(const bf16* __restrict__ gu, const bf16* __restrict__ dact, int rows, int I,
                                   bf16* __restrict__ dgu) {
-  const long long total = (long long)rows * I / 2;
+  const long long total = (long long)rows * I / 8;
   for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
-    const long long e = i * 2;
+    const long long e = i * 8;
     const int r = (int)(e / I), c = (int)(e % I);
-    const uint32_t gw = *reinterpret_cast<const uint32_t*>(gu + (size_t)r * 2 * I + c);
-    const uint32_t uw = *reinterpret_cast<const uint32_t*>(gu + (size_t)r * 2 * I + I + c);
-    const uint32_t dw = *reinterpret_cast<const uint32_t*>(dact + (size_t)r * I + c);
-    float dg[2], du[2];
-    const float gg[2] = {bf_lo(gw), bf_hi(gw)}, uu[2] = {bf_lo(uw), bf_hi(uw)}, dd[2] = {bf_lo(dw), bf_hi(dw)};
+    const uint4 g4 = *reinterpret_cast<const uint4*>(gu + (size_t)r * 2 * I + c);
+    const uint4 u4 = *reinterpret_cast<const uint4*>(gu + (size_t)r * 2 * I + I + c);
+    const uint4 d4 = *reinterpret_cast<const uint4*>(dact + (size_t)r * I + c);
+    const uint32_t gw[4] = {g4.x, g4.y, g4.z, g4.w}, uw[4] = {u4.x, u4.y, u4.z, u4.w}, dw[4] = {d4.x, d4.y, d4.z, d4.w};
+    uint32_t og[4], ou[4];
 #pragma unroll
-    for (int k = 0; k < 2; ++k) {
-      const float sg = 1.f / (1.f + expf(-gg[k]));
-      const float silu = bfround(gg[k] * sg);
-      du[k] = dd[k] * silu;
-      const float dsilu = bfround(dd[k] * uu[k]);            // gradient reaching silu's output (a bf16 tensor)
-      dg[k] = dsilu * (sg * (1.f + gg[k] * (1.f - sg)));
+    for (int q = 0; q < 4; ++q) {
+      float dg[2], du[2];
+      const float gg[2] = {bf_lo(gw[q]), bf_hi(gw[q])}, uu[2] = {bf_lo(uw[q]), bf_hi(uw[q])}, dd[2] = {bf_lo(dw[q]), bf_hi(dw[q])};
+#pragma unroll
+      for (int k = 0; k < 2; ++k) {
+        const float sg = 1.f / (1.f + expf(-gg[k]));
+        const float silu = bfround(gg[k] * sg);
+        du[k] = dd[k] * silu;
+        const float dsilu = bfround(dd[k] * uu[k]);            // gradient reaching silu's output (a bf16 tensor)
+        dg[k] = dsilu * (sg * (1.f + gg[k] * (1.f - sg)));
+      }
+      og[q] = pack_bf16(dg[0], dg[1]);
+      ou[q] = pack_bf16(du[0], du[1]);
     }
-    *reinterpret_cast<uint32_t*>(dgu + (size_t)r * 2 * I + c) = pack_bf16(dg[0], dg[1]);
-    *reinterpret_cast<uint32_t*>(dgu + (size_t)r * 2 * I + I + c) = pack_bf16(du[0], du[1]);
+    *reinterpret_cast<uint4*>(dgu + (size_t)r * 2 * I + c) = make_uint4(og[0], og[1], og[2], og[3]);
+    *reinterpret_cast<uint4*>(dgu + (size_t)r * 2 * I + I + c) = make_uint4(ou[0], ou[1], ou[2], ou[3]);
   }
 }
 
