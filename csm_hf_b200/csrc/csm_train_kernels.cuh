@@ -515,7 +515,7 @@ __global__ void swiglu_bwd_kernel(const bf16* __restrict__ gu, const bf16* __res
 // dh[r] = (dres ? dres[r] : 0) + bf16(dx)   (the residual stream's gradient, updated in place when dres == dh);
 // dw += sum_r dy[r] * bf16(xh[r]) accumulated in fp32 (one atomic per column per block of rows).
 // One warp per row, 8 rows per block of 256 threads; H <= 2048.
-__global__ void __launch_bounds__(256) rmsnorm_bwd_kernel(const bf16* __restrict__ x, const bf16* __restrict__ w,
+__global__ void __launch_bounds__(256, 2) rmsnorm_bwd_kernel(const bf16* __restrict__ x, const bf16* __restrict__ w,
                                                           const bf16* dy, const bf16* dres, float eps, int H,
                                                           int rows, int rows_per_block, bf16* dh, float* __restrict__ dw_acc) {
   __shared__ float sdw[2048];
