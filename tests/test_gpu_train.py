@@ -234,3 +234,78 @@ def test_split_step_equals_single_call(dev):
                 assert torch.equal(grads[k], ref[k]), (split, k)
             else:
                 grad_close(grads[k], ref[k].cpu(), f"split {split}: {k}", rel=0.02, cos_min=0.9999)
+
+
+# ------------------------------------------------------------------ the tcgen05 attention kernels on their own
+def _flash_lib():
+    import ctypes as C
+    from csm_hf_b200 import native
+    lib = native.load()
+    vp = C.c_void_p
+    lib.csm_flash_tc_launch.argtypes = [vp, C.c_int, C.c_int, C.c_int, C.c_int, C.c_float, vp, vp, vp, vp]
+    lib.csm_flash_tc_launch.restype = C.c_int
+    lib.csm_flash_tc_bwd_launch.argtypes = [vp, vp, vp, vp, C.c_int, C.c_int, C.c_int, C.c_int, C.c_float, vp, vp, vp, vp]
+    lib.csm_flash_tc_bwd_launch.restype = C.c_int
+    return lib
+
+
+@pytest.mark.parametrize("S,nseq,heads,kv,padded", [(128, 1, 4, 2, False), (200, 2, 4, 1, False), (333, 2, 8, 2, True),
+                                                     (1000, 1, 32, 8, False)])
+def test_tcgen05_flash_forward_backward_vs_fp32_sdpa(dev, S, nseq, heads, kv, padded):
+    """csm_flash_tc_kernel / csm_flash_tc_bwd_kernel (head dim 64) against torch's SDPA and its autograd in fp32 on the same
+    bf16 inputs: ragged lengths (S not a multiple of the 128-row tiles), several sequences, GQA ratios 2 / 4 / 8, and a
+    left-padded sequence (keys of padded frames hidden; hf sdpa_attention_forward semantics).  Tolerances: output 1 % of
+    its scale (P is rounded to bf16 before P V, as in every flash kernel), log-sum-exp 1e-3, gradients 2 % of each
+    tensor's largest entry."""
+    import ctypes as C
+    lib = _flash_lib()
+    HD = 64
+    W = (heads + 2 * kv) * HD
+    g = torch.Generator().manual_seed(S + heads)
+    qkv = (torch.randn(nseq * S, W, generator=g) * 0.7).to(torch.bfloat16).to(dev)
+    d_out = (torch.randn(nseq * S, heads * HD, generator=g) * 0.5).to(torch.bfloat16).to(dev)
+    valid = None
+    if padded:
+        valid = torch.ones(nseq, S, dtype=torch.uint8)
+        valid[0, :37] = 0
+        valid = valid.to(dev).contiguous()
+    out = torch.zeros(nseq * S, heads * HD, dtype=torch.bfloat16, device=dev)
+    lse = torch.zeros(nseq * S, heads, dtype=torch.float32, device=dev)
+    st = C.c_void_p(torch.cuda.current_stream(dev).cuda_stream)
+    scale = HD ** -0.5
+    vptr = valid.data_ptr() if valid is not None else None
+    assert lib.csm_flash_tc_launch(qkv.data_ptr(), S, nseq, heads, kv, C.c_float(scale), vptr, out.data_ptr(), lse.data_ptr(), st) == 0
+    # fp32 reference with autograd
+    x = qkv.float().view(nseq, S, W)
+    q = x[..., : heads * HD].reshape(nseq, S, heads, HD).transpose(1, 2).clone().requires_grad_(True)
+    k = x[..., heads * HD: (heads + kv) * HD].reshape(nseq, S, kv, HD).transpose(1, 2).clone().requires_grad_(True)
+    v = x[..., (heads + kv) * HD:].reshape(nseq, S, kv, HD).transpose(1, 2).clone().requires_grad_(True)
+    rep = heads // kv
+    s = (q @ k.repeat_interleave(rep, dim=1).transpose(-1, -2)) * scale
+    hide = torch.ones(S, S, dtype=torch.bool, device=dev).triu(1)[None, None].expand(nseq, 1, S, S)
+    if valid is not None:
+        hide = hide | (valid == 0)[:, None, None, :]
+    s = s.masked_fill(hide, float("-inf"))
+    p = torch.softmax(s, dim=-1)
+    p = torch.where(hide.all(dim=-1, keepdim=True), torch.zeros_like(p), p)       # rows that see nothing -> 0
+    ref = (p @ v.repeat_interleave(rep, dim=1)).transpose(1, 2).reshape(nseq * S, heads * HD)
+    live = ~hide.all(dim=-1).expand(nseq, heads, S).transpose(1, 2).reshape(nseq * S, heads)
+    assert float((out.float() - ref).abs().max()) <= 0.01 * float(ref.abs().max())
+    ref_lse = torch.logsumexp(s, dim=-1).transpose(1, 2).reshape(nseq * S, heads)
+    assert float((lse - ref_lse)[live].abs().max()) <= 1e-3
+    ref.backward(d_out.float())
+    # backward through the kernel: D = rowsum(dO * O) as the training step computes it
+    delta = (d_out.float() * out.float()).view(nseq * S, heads, HD).sum(-1).contiguous()
+    dqkv = torch.zeros_like(qkv)
+    dq_acc = torch.zeros(nseq * S, heads * HD, dtype=torch.float32, device=dev)
+    assert lib.csm_flash_tc_bwd_launch(qkv.data_ptr(), d_out.data_ptr(), lse.data_ptr(), delta.data_ptr(), S, nseq, heads, kv,
+                                       C.c_float(scale), vptr, dqkv.data_ptr(), dq_acc.data_ptr(), st) == 0
+    torch.cuda.synchronize()
+    want_dq = q.grad.transpose(1, 2).reshape(nseq * S, heads * HD)
+    want_dk = k.grad.transpose(1, 2).reshape(nseq * S, kv * HD)
+    want_dv = v.grad.transpose(1, 2).reshape(nseq * S, kv * HD)
+    got_dk = dqkv[:, heads * HD: (heads + kv) * HD].float()
+    got_dv = dqkv[:, (heads + kv) * HD:].float()
+    for name, got, want in (("dQ", dq_acc, want_dq), ("dK", got_dk, want_dk), ("dV", got_dv, want_dv)):
+        err = float((got - want).abs().max())
+        assert err <= 0.02 * float(want.abs().max()), f"{name}: max err {err:.4g} of {float(want.abs().max()):.4g}"
