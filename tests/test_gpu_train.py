@@ -309,3 +309,17 @@ def test_tcgen05_flash_forward_backward_vs_fp32_sdpa(dev, S, nseq, heads, kv, pa
     for name, got, want in (("dQ", dq_acc, want_dq), ("dK", got_dk, want_dk), ("dV", got_dv, want_dv)):
         err = float((got - want).abs().max())
         assert err <= 0.02 * float(want.abs().max()), f"{name}: max err {err:.4g} of {float(want.abs().max()):.4g}"
+
+
+def test_fallback_knobs_keep_working(dev):
+    """The documented knobs that switch the training step back to its earlier formulations -- mma.sync attention
+    (CSM_FLASH_MMA=1) and transposed copies instead of MN-major GEMM operands (CSM_TRAIN_TRANSPOSE=1) -- still pass the
+    reference-fixture test (they are read when the library's contexts are created: a fresh process)."""
+    import subprocess
+    import sys
+    env = dict(os.environ, CSM_FLASH_MMA="1", CSM_TRAIN_TRANSPOSE="1")
+    here = os.path.abspath(__file__)
+    r = subprocess.run([sys.executable, "-m", "pytest", here, "-q", "-m", "gpu", "-k",
+                        "loss_and_gradients_vs_reference_fixture or left_padded or first_frame_selected"],
+                       env=env, capture_output=True, text=True, timeout=600)
+    assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-2000:]
